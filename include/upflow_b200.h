@@ -1,0 +1,150 @@
+/*
+ * upflow_b200 -- C ABI of the B200-native UPFlow decoder hot path.
+ *
+ * Drop-in boundary.  The reference's only native
+ * boundary is the pybind module `correlation_cuda`
+ * (model/correlation_package/correlation_cuda.cc:169-172: forward/backward);
+ * everything else on the hot path is ATen called from Python
+ * (model/pwc_modules.py, model/upflow.py, utils/tools.py).  Each entry point
+ * below names the reference routine it replaces.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no torch types.  Every pointer is a
+ *    DEVICE pointer owned by the caller; the library never allocates, never
+ *    synchronises and never throws.  Work is enqueued on `stream`
+ *    (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *  - return 0 on success, otherwise a negative UPF_E* code or a positive
+ *    cudaError_t; upf_last_error() returns a thread-local message.
+ *  - tensors are fp32, PIXEL-MAJOR ("NHWC"): element (n, y, x, c) of a tensor
+ *    with row pitch `ld` lives at base[((n*H + y)*W + x)*ld + c].  `ld` may be
+ *    larger than the channel count, so a tensor can be a channel slice of a
+ *    wider buffer (this is how the dense blocks avoid every torch.cat of
+ *    model/pwc_modules.py:280-284).  torch `channels_last` tensors are this
+ *    layout with ld == C.
+ *  - "stats" buffers are double[N][C][2] = (sum x, sum x*x) over the H*W
+ *    pixels of one image and channel; they are ACCUMULATED into (caller zeroes
+ *    them, e.g. with cudaMemsetAsync on the same stream).
+ */
+#ifndef UPFLOW_B200_H
+#define UPFLOW_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UPF_ABI_VERSION 1
+
+#define UPF_EINVAL   (-1)  /* bad argument (shape, alignment, unsupported value) */
+#define UPF_ENOTSUP  (-2)  /* valid request this build cannot serve            */
+#define UPF_EDRIVER  (-3)  /* CUDA driver entry point / tensor-map failure     */
+
+int         upf_abi_version(void);
+const char* upf_last_error(void);
+/* number of kernels this library has launched in the calling process */
+long long   upf_launch_count(void);
+
+/* a1+a2+a3 (+ apply half of a5): cost volume + LeakyReLU, optionally with the
+ * per-image per-channel normalisation fused into the operand load.
+ *   replaces correlation_cuda.forward (correlation_cuda.cc:10-87, kernels
+ *   correlation_cuda_kernel.cu:15-114), Corr_pyTorch.forward
+ *   (utils/pytorch_correlation.py:27-50), nn.LeakyReLU on the result
+ *   (model/upflow.py:563-564) and normalize_features' apply step
+ *   (model/upflow.py:126-135).
+ * out[n,y,x,(dy+d)*(2d+1)+(dx+d)] = lrelu( (1/C) sum_c a[n,y,x,c]*b[n,y+dy,x+dx,c] ),
+ * b zero outside the image; a=(f1-mean1)*rstd1, b=(f2-mean2)*rstd2 when the
+ * stats pointers are non-NULL (mean = s/npix, var = unbiased, rstd=1/sqrt(var+1e-16)).
+ * max_disp in {1..6}; slope = 1.0f disables the activation.
+ * f2_batch_shift: image n of f1 is matched with image (n + shift) % N of f2 /
+ * stats2 (the decoder stacks the forward and backward directions in one batch:
+ * images [im1.., im2..], partner = shift by N/2; 0 = plain). */
+int upf_corr_lrelu_fwd(const float* f1, int ld1, const float* f2, int ld2,
+                       float* out, int ldo, int N, int H, int W, int C, int max_disp,
+                       const double* stats1, const double* stats2, int f2_batch_shift,
+                       float slope, void* stream);
+
+/* a11: gradients of the (un-normalised) cost volume wrt f1 and f2.
+ *   replaces correlation_cuda.backward (correlation_cuda.cc:89-167, kernels
+ *   correlation_cuda_kernel.cu:116-300).  `out` is the saved forward output;
+ *   when slope != 1 the LeakyReLU derivative is taken from its sign. */
+int upf_corr_lrelu_bwd(const float* f1, int ld1, const float* f2, int ld2,
+                       const float* out, int ldo, const float* grad_out, int ldg,
+                       float* grad_f1, int ldg1, float* grad_f2, int ldg2,
+                       int N, int H, int W, int C, int max_disp, float slope, void* stream);
+
+/* a4 (+ stats half of a5): bilinear warp by a pixel-space flow with the
+ * `mask >= 1.0` validity mask, bit-faithful to F.grid_sample as the reference
+ * calls it.
+ *   replaces WarpingLayer_no_div.forward (model/pwc_modules.py:184-207) and,
+ *   with use_mask=0, tools.torch_warp (utils/tools.py:1274-1304).
+ * flow is [N,H,W,>=2] (u,v) with pitch ldf.  If stats != NULL the (sum, sum^2)
+ * of the OUTPUT are accumulated per (n,c).  x_batch_shift: output image n
+ * samples image (n + shift) % N of x (see upf_corr_lrelu_fwd). */
+int upf_warp_fwd(const float* x, int ldx, const float* flow, int ldf, float* out, int ldo,
+                 int N, int H, int W, int C, int align_corners, int use_mask,
+                 int x_batch_shift, double* stats, void* stream);
+
+/* a11: backward of upf_warp_fwd wrt x (scatter-add; grad_x must be zeroed by the
+ * caller) and wrt flow (grad_flow [N,H,W,2], written).  Either may be NULL. */
+int upf_warp_bwd(const float* x, int ldx, const float* flow, int ldf, const float* grad_out, int ldg,
+                 float* grad_x, int ldgx, float* grad_flow, int ldgf,
+                 int N, int H, int W, int C, int align_corners, int use_mask, void* stream);
+
+/* a5: normalize_features (model/upflow.py:94-137) with
+ * moments_across_channels=False, moments_across_images=False (test.py:24-26). */
+int upf_featnorm_stats(const float* x, int ldx, int N, int H, int W, int C, double* stats, void* stream);
+int upf_featnorm_apply(const float* x, int ldx, const double* stats, float* out, int ldo,
+                       int N, int H, int W, int C, void* stream);
+
+/* a6: upsample2d_flow_as / upsample2d_as (model/pwc_modules.py:72-90):
+ * bilinear, align_corners=True, channel c multiplied by scale[c] afterwards
+ * (scale = {W/w, H/h} for flows, NULL = no scaling).  C <= 4. */
+int upf_resize_bilinear(const float* in, int ldi, int h, int w, float* out, int ldo, int H, int W,
+                        int N, int C, const float* scale_host, void* stream);
+
+/* a7 blend: sgu_model.forward's last line (model/upflow.py:79-88).
+ *   inter  [N,ih,iw,>=3] = (inter_flow u, v, mask LOGIT) as the dense block emits it
+ *   flow_init [N,H,W,2]  = the flow to refine at OUTPUT resolution
+ * same resolution (ih==H, iw==W):
+ *   out = warp(flow_init, inter_flow)*(1-sigmoid(m)) + flow_init*sigmoid(m)
+ * output-level variant (ih<H): inter_flow is bilinearly upsampled (align_corners
+ * =True) and scaled by (W/iw, H/ih); sigmoid(m) is upsampled AFTER the sigmoid
+ * (model/upflow.py:84-86). */
+int upf_sgu_blend(const float* flow_init, int ldf, const float* inter, int ldi, int ih, int iw,
+                  float* out, int ldo, int N, int H, int W, int align_corners, void* stream);
+
+/* a8/a9 (+ the dense block of a7): Conv2d(k in {1,3}, pad=((k-1)*dil)/2) + bias
+ * + LeakyReLU(slope) [+ residual], reading an input channel slice and writing
+ * an output channel slice.
+ *   replaces conv() (model/pwc_modules.py:10-31) as used by
+ *   FlowEstimatorDense_v2 (:279-286), ContextNetwork_v2_ (:401-412) and
+ *   sgu_model's dense block (model/upflow.py:52-60); torch.cat disappears.
+ * weight layout (prepared once by the host): w[tap][cin][cout_pad] fp32 with
+ * tap = ky*k+kx, cout_pad = round_up(Cout, 4) for UPF_CONV_FP32;
+ *   residual (nullable) [N,Ho,Wo,>=Cout] pitch ldr is added AFTER the activation.
+ * precision: UPF_CONV_FP32 = SIMT fp32 FMA (bit-faithful class, any k/stride);
+ *            UPF_CONV_TF32 = tcgen05 tensor cores, TF32 operands, fp32
+ *            accumulate in TMEM (3x3/1x1 stride 1; needs the packed weights of
+ *            upf_conv_tc_pack_weights). */
+#define UPF_CONV_FP32 0
+#define UPF_CONV_TF32 1
+int upf_conv2d_fwd(const float* x, int ldx, const float* w, const float* bias,
+                   float* out, int ldo, const float* residual, int ldr,
+                   int N, int H, int W, int Cin, int Cout, int ksize, int stride, int dilation,
+                   float slope, int precision, void* stream);
+
+/* TF32 tensor-core path: weights packed as [tap][cout_pad16][cin_pad32] fp32
+ * (K-major rows of 32 input channels), done on the device from the SIMT layout. */
+long long upf_conv_tc_packed_elems(int Cin, int Cout, int ksize);
+int upf_conv_tc_pack_weights(const float* w_simt, float* w_packed, int Cin, int Cout, int ksize, void* stream);
+
+/* layout helpers for callers holding NCHW-contiguous tensors (the reference's
+ * layout): strided copy between [N,C,H,W] planes and pixel-major rows. */
+int upf_nchw_to_nhwc(const float* in, float* out, int ldo, int N, int C, int H, int W, void* stream);
+int upf_nhwc_to_nchw(const float* in, int ldi, float* out, int N, int C, int H, int W, void* stream);
+/* out[n,y,x,0:C] = in[n,y,x,0:C] between two pitched buffers */
+int upf_copy_channels(const float* in, int ldi, float* out, int ldo, long long npix, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UPFLOW_B200_H */

@@ -70,6 +70,8 @@ def install(patch_training=False):
     subprocess or purge ``sys.modules`` through ``purge()``)."""
     if not have_reference():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    if _installed.get("mods") is not None and sys.modules.get("model.upflow") is not _installed["mods"].upflow:
+        _installed.clear()          # somebody (the drop-in) replaced `model` since: import afresh
     if _installed.get("mods") is None:
         import torch.utils.data.dataloader as dl
         if not hasattr(dl, "_DataLoaderIter"):
@@ -79,8 +81,16 @@ def install(patch_training=False):
                 importlib.import_module(name)
             except Exception:
                 _stub(name)
-        if REFERENCE_ROOT not in sys.path:
-            sys.path.insert(0, REFERENCE_ROOT)
+        # the product's drop-in mirror uses the same top-level names: evict it
+        for k in list(sys.modules):
+            if k.split(".")[0] in ("model", "utils"):
+                f = getattr(sys.modules[k], "__file__", "") or ""
+                if not f.startswith(REFERENCE_ROOT):
+                    del sys.modules[k]
+        sys.path[:] = [p for p in sys.path if not p.rstrip("/").endswith("upflow_pytorch_b200/dropin")]
+        if REFERENCE_ROOT in sys.path:
+            sys.path.remove(REFERENCE_ROOT)
+        sys.path.insert(0, REFERENCE_ROOT)
         mods = types.SimpleNamespace()
         mods.upflow = importlib.import_module("model.upflow")
         mods.pwc_modules = importlib.import_module("model.pwc_modules")

@@ -1,0 +1,76 @@
+"""CPU tier: the C-ABI library builds for sm_100a, loads without a GPU, and
+exports every symbol include/upflow_b200.h declares with the arity the ctypes
+binding uses.  No compute calls."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "upflow_b200.h")
+
+
+def _declarations():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = {}
+    for m in re.finditer(r"\b(?:int|long long|const char\*)\s+(upf_\w+)\s*\(([^)]*)\)\s*;", src):
+        name, args = m.group(1), m.group(2).strip()
+        decls[name] = 0 if args in ("", "void") else len(args.split(","))
+    return decls
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from upflow_pytorch_b200 import build
+    return build.build()
+
+
+def test_header_declares_the_hot_path():
+    d = _declarations()
+    for name in ("upf_corr_lrelu_fwd", "upf_corr_lrelu_bwd", "upf_warp_fwd", "upf_warp_bwd", "upf_featnorm_stats",
+                 "upf_featnorm_apply", "upf_resize_bilinear", "upf_sgu_blend", "upf_conv2d_fwd",
+                 "upf_conv_tc_pack_weights", "upf_last_error"):
+        assert name in d
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    for name in _declarations():
+        assert hasattr(lib, name), name
+
+
+def test_ctypes_signatures_match_header(lib_path):
+    from upflow_pytorch_b200 import _ext
+    d = _declarations()
+    assert set(d) == set(_ext.SIGNATURES)
+    for name, n in d.items():
+        assert len(_ext.SIGNATURES[name][1]) == n, name
+    lib = _ext.load()
+    assert lib.upf_abi_version() == 1
+    assert lib.upf_launch_count() == 0
+
+
+def test_bad_arguments_return_codes_not_crashes(lib_path):
+    """argument validation happens on the host before any launch (works without a GPU)"""
+    from upflow_pytorch_b200 import _ext
+    lib = _ext.load()
+    rc = lib.upf_corr_lrelu_fwd(None, 32, None, 32, None, 81, 1, 8, 8, 32, 4, None, None, 0, 0.1, None)
+    assert rc == -1 and b"null" in lib.upf_last_error()
+    rc = lib.upf_conv2d_fwd(ctypes.c_void_p(16), 32, ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), 32,
+                            None, 0, 1, 8, 8, 32, 32, 5, 1, 1, 0.1, 0, None)
+    assert rc == -1 and b"kernel size" in lib.upf_last_error()
+
+
+def test_sass_has_blackwell_tensor_and_tma_instructions(lib_path):
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", lib_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass or "SM100" in sass.upper()
+    assert re.search(r"UTC\w*MMA", sass), "tcgen05.mma missing"
+    assert "UTMALDG" in sass, "TMA loads missing"
+    assert "LDTM" in sass, "tcgen05.ld missing"

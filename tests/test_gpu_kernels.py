@@ -1,0 +1,289 @@
+"""Parity of every CUDA kernel, called through the C ABI (ctypes), against the
+CPU oracle and the golden vectors produced by the reference.  -m gpu."""
+import math
+
+import pytest
+import torch
+
+from oracle import cpu_oracle as O
+from oracle import ref_port as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def upf():
+    from upflow_pytorch_b200 import _ext, ops
+    _ext.load()
+    return ops
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _cuda(t):
+    return t.cuda()
+
+
+def _regen(seed, shape):
+    return torch.randn(shape, generator=_g(seed))
+
+
+# ------------------------------------------------------------------ correlation
+def test_corr_golden(upf, golden):
+    """BASELINE config 1 (1x32x64x64, d=4) and the ragged / d=2 / d=6 / C=196 cases, vs Corr_pyTorch outputs."""
+    for c in golden("corr"):
+        f1 = c["f1"] if c["f1"] is not None else _regen(c["seed"], c["shape"])
+        f2 = c["f2"] if c["f2"] is not None else _regen(c["seed"] + 100, c["shape"])
+        out = upf.correlation(_cuda(f1), _cuda(f2), c["d"]).cpu()
+        assert out.shape == c["out"].shape
+        err = (out - c["out"]).abs().max().item()
+        assert err <= 1e-5, (c["shape"], c["d"], err)          # fp32 sum of C products
+        lr = upf.correlation(_cuda(f1), _cuda(f2), c["d"], leaky_slope=0.1).cpu()
+        ref = torch.nn.functional.leaky_relu(c["out"], 0.1)
+        assert (lr - ref).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("layout", ["nchw", "channels_last"])
+@pytest.mark.parametrize("shape,d", [((2, 32, 47, 156), 4), ((1, 64, 24, 78), 4), ((2, 128, 12, 39), 4),
+                                     ((1, 96, 33, 70), 4), ((1, 32, 40, 100), 2), ((1, 32, 37, 65), 6),
+                                     ((1, 7, 9, 33), 3), ((1, 32, 3, 2), 4)])
+def test_corr_vs_oracle(upf, shape, d, layout):
+    f1, f2 = _regen(1, shape), _regen(2, shape)
+    a, b = _cuda(f1), _cuda(f2)
+    if layout == "channels_last":
+        a, b = a.contiguous(memory_format=torch.channels_last), b.contiguous(memory_format=torch.channels_last)
+    out = upf.correlation(a, b, d).cpu()
+    ref = O.correlation(f1.double(), f2.double(), d).float()
+    assert (out - ref).abs().max().item() <= 1e-5
+
+
+def test_corr_fused_norm_matches_two_step(upf):
+    """normalize_features + correlation + LeakyReLU fused (what the engine runs) vs the oracle chain."""
+    from upflow_pytorch_b200.ops import Slice
+    shape = (2, 64, 24, 78)
+    f1 = _regen(3, shape) * 2 + 0.5
+    f2 = _regen(4, shape).relu() * 1.5
+    a, b = upf.to_pixel_major(_cuda(f1)), upf.to_pixel_major(_cuda(f2))
+    s1 = torch.zeros(2, 64, 2, dtype=torch.float64, device="cuda")
+    s2 = torch.zeros_like(s1)
+    upf.k_stats(a, s1)
+    upf.k_stats(b, s2)
+    out = torch.empty(2, 24, 78, 81, device="cuda")
+    upf.k_corr(a, b, out, 4, s1, s2, slope=0.1)
+    ref = O.correlation(O.normalize_features(f1.double()), O.normalize_features(f2.double()), 4, 0.1).float()
+    assert (out.permute(0, 3, 1, 2).cpu() - ref).abs().max().item() <= 2e-5
+    # batch shift: image n of f1 against image (n+1)%2 of f2
+    upf.k_corr(a, b, out, 4, s1, s2, f2_shift=1, slope=0.1)
+    ref = O.correlation(O.normalize_features(f1.double()), O.normalize_features(f2.double())[[1, 0]], 4, 0.1).float()
+    assert (out.permute(0, 3, 1, 2).cpu() - ref).abs().max().item() <= 2e-5
+
+
+def test_corr_into_channel_slice(upf):
+    """writes exactly its 81 channels of a 576-wide buffer"""
+    from upflow_pytorch_b200.ops import Slice
+    f1, f2 = _regen(5, (1, 32, 20, 45)), _regen(6, (1, 32, 20, 45))
+    X = torch.full((1, 20, 45, 576), 7.0, device="cuda")
+    upf.k_corr(upf.to_pixel_major(_cuda(f1)), upf.to_pixel_major(_cuda(f2)), Slice(X, 0, 81), 4, slope=1.0)
+    ref = O.correlation(f1, f2, 4)
+    assert (X[..., :81].permute(0, 3, 1, 2).cpu() - ref).abs().max().item() <= 1e-5
+    assert (X[..., 81:] == 7.0).all()
+
+
+def test_corr_backward(upf):
+    shape, d = (2, 12, 9, 14), 3
+    f1 = _regen(7, shape).cuda().requires_grad_()
+    f2 = _regen(8, shape).cuda().requires_grad_()
+    go = _regen(9, (2, 49, 9, 14))
+    upf.correlation(f1, f2, d).backward(go.cuda())
+    g1, g2 = O.correlation_backward(f1.detach().cpu().double(), f2.detach().cpu().double(), go.double(), d)
+    assert (f1.grad.cpu() - g1.float()).abs().max().item() <= 1e-5
+    assert (f2.grad.cpu() - g2.float()).abs().max().item() <= 1e-5
+
+
+# ------------------------------------------------------------------ warp
+def test_warp_golden_mask_bit_exact(upf, golden):
+    for w in golden("warp"):
+        out = upf.warp(_cuda(w["x"]), _cuda(w["flow"])).cpu()
+        ref = w["out"]
+        assert torch.equal((ref == 0).all(1), (out == 0).all(1)), w["kind"]     # mask >= 1.0, pixel for pixel
+        tol = 2e-6 * max(1.0, ref.abs().max().item())
+        assert (out - ref).abs().max().item() <= tol
+        nm = upf.warp(_cuda(w["x"]), _cuda(w["flow"]), use_mask=False).cpu()
+        assert (nm - w["out_nomask"]).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("hw", [(47, 156), (94, 311), (375, 1242), (1, 1), (2, 7)])
+@pytest.mark.parametrize("C", [32, 196, 3])
+def test_warp_vs_oracle_kitti_sizes(upf, hw, C):
+    H, W = hw
+    if H * W * C > 375 * 1242 * 32:
+        pytest.skip("large")
+    x = _regen(11, (1, C, H, W))
+    for fl in (_regen(12, (1, 2, H, W)) * 3, torch.randint(-3, 4, (1, 2, H, W), generator=_g(13)).float()):
+        out = upf.warp(_cuda(x), _cuda(fl)).cpu()
+        ref = O.warp_mask(x, fl)
+        assert torch.equal((ref == 0).all(1), (out == 0).all(1))
+        assert (out - ref).abs().max().item() <= 4e-6
+        out = upf.warp(_cuda(x), _cuda(fl), align_corners=True).cpu()
+        ref = O.warp_mask(x, fl, align_corners=True)
+        assert torch.equal((ref == 0).all(1), (out == 0).all(1))
+        assert (out - ref).abs().max().item() <= 4e-6
+
+
+def test_warp_fused_moments(upf):
+    from upflow_pytorch_b200.ops import Slice
+    x = _regen(14, (2, 96, 24, 78)).relu()
+    fl = _regen(15, (2, 2, 24, 78)) * 2
+    a, f = upf.to_pixel_major(_cuda(x)), upf.to_pixel_major(_cuda(fl))
+    out = torch.empty_like(a)
+    st = torch.zeros(2, 96, 2, dtype=torch.float64, device="cuda")
+    upf.k_warp(a, f, out, False, True, x_shift=1, stats=st)
+    ref = O.warp_mask(x[[1, 0]], fl)
+    assert (out.permute(0, 3, 1, 2).cpu() - ref).abs().max().item() <= 4e-6
+    s = st.cpu()
+    assert (s[..., 0] - ref.double().sum((2, 3))).abs().max().item() <= 1e-3
+    assert ((s[..., 1] - (ref.double() ** 2).sum((2, 3))).abs() / (1 + s[..., 1].abs())).max().item() <= 1e-5
+
+
+def test_warp_backward_matches_grid_sample_autograd(upf):
+    """gradients vs torch CPU autograd of the op-for-op port (F.grid_sample)"""
+    x = _regen(16, (1, 5, 9, 11)).double()
+    fl = (_regen(17, (1, 2, 9, 11)) * 1.5).double()
+    xr, fr = x.clone().requires_grad_(), fl.clone().requires_grad_()
+    go = _regen(18, (1, 5, 9, 11)).double()
+    # double-precision reference: the port's formula with explicit align_corners=False
+    grid = P._vgrid(fr)
+    ref = torch.nn.functional.grid_sample(xr, grid, padding_mode="zeros", align_corners=False)
+    ref.backward(go)
+    xg, fg = x.float().cuda().requires_grad_(), fl.float().cuda().requires_grad_()
+    upf.warp(xg, fg, use_mask=False).backward(go.float().cuda())
+    assert (xg.grad.cpu() - xr.grad.float()).abs().max().item() <= 1e-5
+    assert (fg.grad.cpu() - fr.grad.float()).abs().max().item() <= 1e-4
+
+
+# ------------------------------------------------------------------ normalisation / resize / blend
+def test_normalize_golden(upf, golden):
+    for n in golden("norm"):
+        out = upf.normalize_features(_cuda(n["f"])).cpu()
+        assert (out - n["out"]).abs().max().item() <= 3e-6
+
+
+def test_resize_golden(upf, golden):
+    for u in golden("upsample"):
+        h, w = u["hw"]
+        out = upf.resize_bilinear(_cuda(u["x"]), h, w, flow_rate=u["if_rate"]).cpu()
+        assert (out - u["out"]).abs().max().item() <= 4e-6
+
+
+@pytest.mark.parametrize("src,dst", [((94, 311), (375, 1242)), ((6, 20), (12, 39)), ((109, 256), (436, 1024))])
+def test_resize_vs_oracle(upf, src, dst):
+    x = _regen(19, (2, 2, *src)) * 4
+    out = upf.resize_bilinear(_cuda(x), *dst, flow_rate=True).cpu()
+    ref = O.upsample2d_flow_as(x, *dst)
+    assert (out - ref).abs().max().item() <= 2e-5
+
+
+def test_sgu_blend_golden(upf, golden):
+    s = golden("sgu")
+    # teacher-forced with the reference's own inter_flow / (pre-sigmoid) mask: rebuild the logit
+    logit = torch.logit(s["inter_mask"].double()).float()
+    inter = torch.cat([s["inter_flow"], logit], 1)
+    out = upf.sgu_blend(_cuda(s["flow"]), _cuda(inter)).cpu()
+    assert (out - s["flow_up"]).abs().max().item() <= 2e-5
+
+
+def test_sgu_blend_vs_oracle_both_variants(upf):
+    flow = _regen(20, (2, 2, 24, 40)) * 3
+    inter = torch.cat([_regen(21, (2, 2, 24, 40)) * 1.5, _regen(22, (2, 1, 24, 40)) * 2], 1)
+    out = upf.sgu_blend(_cuda(flow), _cuda(inter)).cpu()
+    ref = O.sgu_blend(flow, inter[:, :2], torch.sigmoid(inter[:, 2:3]))
+    assert (out - ref).abs().max().item() <= 5e-6
+    # output-level variant: inter at 24x40, flow at 95x158
+    big = _regen(23, (2, 2, 95, 158)) * 5
+    out = upf.sgu_blend(_cuda(big), _cuda(inter)).cpu()
+    iflow = O.upsample2d_flow_as(inter[:, :2], 95, 158)
+    imask = O.resize_bilinear_ac(torch.sigmoid(inter[:, 2:3]), 95, 158)
+    ref = O.sgu_blend(big, iflow, imask)
+    assert (out - ref).abs().max().item() <= 2e-5
+
+
+# ------------------------------------------------------------------ convolution
+CONV_CASES = [  # (Cin, Cout, k, stride, dil, H, W)
+    (115, 128, 3, 1, 1, 12, 39), (563, 2, 3, 1, 1, 12, 20), (128, 96, 3, 1, 8, 24, 30), (96, 64, 3, 1, 16, 24, 30),
+    (196, 32, 1, 1, 1, 6, 20), (3, 16, 3, 2, 1, 37, 50), (16, 16, 3, 1, 1, 19, 25), (64, 3, 3, 1, 1, 9, 9),
+    (32, 32, 3, 2, 1, 20, 21),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fp32_vs_oracle(upf, case):
+    Cin, Cout, k, stride, dil, H, W = case
+    x = _regen(30, (2, Cin, H, W))
+    w = _regen(31, (Cout, Cin, k, k)) * (2.0 / (Cin * k * k)) ** 0.5
+    b = _regen(32, (Cout,)) * 0.1
+    wp, _ = upf.pack_conv_weight(_cuda(w))
+    out = upf.conv2d(_cuda(x), wp, _cuda(b), Cout, k, stride, dil, 0.1).cpu()
+    ref = O.conv2d_direct(x.double(), w.double(), b.double(), dil, stride, 0.1).float()
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[3] == 1])
+def test_conv_tf32_tensor_core_vs_oracle(upf, case):
+    """tcgen05 path: operands are truncated to TF32 (10-bit mantissa), fp32 accumulate.  Tolerance: the oracle run
+    on TF32-truncated operands must match to fp32 rounding; vs the exact oracle the error is ~2^-10 relative."""
+    from upflow_pytorch_b200 import _ext
+    Cin, Cout, k, stride, dil, H, W = case
+    x = _regen(30, (2, Cin, H, W))
+    w = _regen(31, (Cout, Cin, k, k)) * (2.0 / (Cin * k * k)) ** 0.5
+    b = _regen(32, (Cout,)) * 0.1
+    _, wtc = upf.pack_conv_weight(_cuda(w), tc=True)
+    out = upf.conv2d(_cuda(x), wtc, _cuda(b), Cout, k, stride, dil, 0.1, precision=_ext.CONV_TF32).cpu()
+
+    def trunc(t):
+        return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    ref_t = O.conv2d_direct(trunc(x).double(), trunc(w).double(), b.double(), dil, stride, 0.1).float()
+    ref = O.conv2d_direct(x.double(), w.double(), b.double(), dil, stride, 0.1).float()
+    err_t = (out - ref_t).abs().max().item()
+    err = (out - ref).abs().max().item()
+    print("tf32 conv", case, "err vs truncated-operand oracle", err_t, "vs exact", err)
+    assert err <= 1e-2
+    assert err_t <= 5e-4
+
+
+def test_dense_block_and_context_golden(golden):
+    """a8/a9 through the drop-in modules (reference names) with the reference's own outputs."""
+    import upflow_pytorch_b200 as pkg
+    pkg.install_dropin()
+    from model import pwc_modules
+    pwc_modules.set_conv_precision("fp32")
+    e = golden("estimator")
+    sd = P.det_state_dict(e["wseed"])
+    est = pwc_modules.FlowEstimatorDense_v2(115).cuda()
+    est.load_state_dict({k[len("flow_estimators."):]: v for k, v in sd.items() if k.startswith("flow_estimators.")})
+    with torch.no_grad():
+        x5, out = est(e["x"].cuda())
+    assert (x5.cpu() - e["x5"]).abs().max().item() <= 3e-5
+    assert (out.cpu() - e["out"]).abs().max().item() <= 3e-5
+    c = golden("context")
+    ctx = pwc_modules.ContextNetwork_v2_(565).cuda()
+    ctx.load_state_dict({k[len("context_networks."):]: v for k, v in sd.items() if k.startswith("context_networks.")})
+    with torch.no_grad():
+        o = ctx(c["x"].cuda())
+    assert (o.cpu() - c["out"]).abs().max().item() <= 3e-5
+
+
+def test_layout_roundtrip(upf):
+    x = _regen(40, (2, 37, 13, 29)).cuda()
+    a = upf.to_pixel_major(x)
+    assert torch.equal(a.permute(0, 3, 1, 2), x)
+    assert torch.equal(upf.to_nchw_contiguous(a), x)
+    padded = upf.to_pixel_major(x, ld=40)
+    assert torch.equal(padded[..., :37].permute(0, 3, 1, 2), x) and (padded[..., 37:] == 0).all()
+
+
+def test_cpu_tensors_fail_loudly(upf):
+    with pytest.raises(RuntimeError):
+        upf.correlation(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4, 8, 8), 4)

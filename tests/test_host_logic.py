@@ -1,0 +1,156 @@
+"""CPU tier: host-side logic of the package -- drop-in API surface, state-dict
+contract, the weight permutation that maps the reference's prepend-order dense
+blocks onto append-only buffers, loud failure without CUDA."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ref_port as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def dropin():
+    import upflow_pytorch_b200 as pkg
+    pkg.install_dropin()
+    import model.upflow as up
+    import model.pwc_modules as pm
+    assert up.__file__.startswith(pkg.DROPIN_DIR)
+    return pkg, up, pm
+
+
+def test_state_dict_contract(dropin):
+    """80 tensors, the reference's names and shapes"""
+    pkg, up, pm = dropin
+    net = pkg.build_model(device="cpu")
+    sd = net.state_dict()
+    shapes = P.reference_param_shapes()
+    assert set(sd) == set(shapes)
+    assert all(tuple(sd[k].shape) == shapes[k] for k in sd)
+    assert sum(v.numel() for v in sd.values()) == 3494549
+    net.load_state_dict(P.det_state_dict(1))           # strict load works
+
+
+def test_api_surface(dropin):
+    pkg, up, pm = dropin
+    for name in ("conv", "initialize_msra", "upsample2d_flow_as", "upsample_flow", "FlowEstimatorDense_v2",
+                 "ContextNetwork_v2_", "WarpingLayer_no_div", "FeatureExtractor"):
+        assert hasattr(pm, name)
+    assert hasattr(up, "UPFlow_net") and hasattr(up.network_tools, "sgu_model")
+    from model.correlation_package.correlation import Correlation, CorrelationFunction
+    from utils.pytorch_correlation import Corr_pyTorch
+    from utils.tools import tools
+    Correlation(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1, corr_multiply=1)
+    Corr_pyTorch(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1)
+    with pytest.raises(AssertionError):
+        Corr_pyTorch(pad_size=3, max_displacement=4)          # same argument check as the reference
+    with pytest.raises(NotImplementedError):
+        Correlation(pad_size=20, kernel_size=3, max_displacement=20, stride1=1, stride2=2)
+    conf = up.UPFlow_net.config()
+    assert conf.if_sgu_upsample is False and conf.if_use_cor_pytorch is False       # reference defaults
+    name = conf.get_name(print_now=False)
+    assert "if_sgu_upsample|False_" in name
+    assert isinstance(tools.occ_check_model(obj_out_all='obj'), object)
+
+
+def test_no_cpu_fallback(dropin):
+    pkg, up, pm = dropin
+    net = pkg.build_model(device="cpu")
+    x = torch.zeros(1, 3, 64, 64)
+    with pytest.raises(RuntimeError):
+        net({"im1": x, "im2": x, "if_loss": False})
+    from upflow_pytorch_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.warp(torch.zeros(1, 4, 8, 8), torch.zeros(1, 2, 8, 8))
+    if not torch.cuda.is_available():
+        from upflow_pytorch_b200.engine import DecoderEngine
+        with pytest.raises(RuntimeError):
+            DecoderEngine(P.det_state_dict(0))
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "upflow_pytorch_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                if "import oracle" in src or "from oracle" in src or "/root/reference" in src:
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+
+
+def test_dense_block_weight_permutation():
+    """Emulate the engine's append-only X buffer with torch convs on CPU using the PACKED weights and compare with
+    the reference-order dense block: validates _dense_slots / pack_conv_weight (pure host logic)."""
+    from upflow_pytorch_b200 import ops
+    from upflow_pytorch_b200.engine import EST_CH, X_FLOW2, X_LD, X_OFF, _dense_slots
+    sd = P.det_state_dict(11)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 115, 7, 9, generator=g)
+    x5_ref, out_ref = P.dense(x, sd, "flow_estimators")
+    flow2 = torch.randn(1, 2, 7, 9, generator=g)
+    ctx_ref = P._conv(torch.cat([x5_ref, flow2], 1), sd, "context_networks.convs.0")
+
+    X = torch.zeros(1, X_LD, 7, 9)
+    X[:, :115] = x
+    names = ("conv1", "conv2", "conv3", "conv4", "conv5", "conv_last")
+    widths = (128,) + tuple(o + c for o, c in zip(X_OFF, EST_CH))
+
+    def run(key, slots, width, relu=True):
+        w, _ = ops.pack_conv_weight(sd[key + ".0.weight"], slots, width)          # [9, width, cout_pad]
+        cout = sd[key + ".0.bias"].numel()
+        wt = w[:, :, :cout].reshape(3, 3, width, cout).permute(3, 2, 0, 1).contiguous()
+        y = F.conv2d(X[:, :width], wt, sd[key + ".0.bias"], padding=1)
+        return F.leaky_relu(y, 0.1) if relu else y
+
+    for k, name in enumerate(names):
+        y = run("flow_estimators." + name, _dense_slots(115, range(115), X_OFF, EST_CH, k), widths[k], relu=k < 5)
+        if k < 5:
+            X[:, X_OFF[k]:X_OFF[k] + EST_CH[k]] = y
+        else:
+            assert (y - out_ref).abs().max().item() < 1e-5
+    X[:, X_FLOW2:X_FLOW2 + 2] = flow2
+    slots = _dense_slots(115, range(115), X_OFF, EST_CH, 5) + [X_FLOW2, X_FLOW2 + 1]
+    y = run("context_networks.convs.0", slots, X_LD)
+    assert (y - ctx_ref).abs().max().item() < 1e-5
+    # x5 in reference order can be read back from the buffer
+    x5 = torch.cat([X[:, X_OFF[k]:X_OFF[k] + EST_CH[k]] for k in (4, 3, 2, 1, 0)] + [X[:, :115]], 1)
+    assert (x5 - x5_ref).abs().max().item() < 1e-5
+
+
+def test_reference_test_py_constructs_against_dropin(tmp_path):
+    """Drop-in acceptance on the host side: with our `model`/`utils` ahead of the reference's on
+    sys.path, the reference's own test.py imports and builds Test_model (CPU, no forward).  Needs the reference
+    tree, so it only runs in the authoring container."""
+    from oracle import ref_shims
+    if not ref_shims.have_reference():
+        pytest.skip("reference tree not mounted")
+    code = r'''
+import sys, types, importlib.machinery, contextlib, io
+sys.path.insert(0, %r)
+import upflow_pytorch_b200 as pkg
+for name in ("imageio", "png", "tensorflow"):
+    m = types.ModuleType(name); m.__spec__ = importlib.machinery.ModuleSpec(name, None); sys.modules[name] = m
+import torch.utils.data.dataloader as dl
+dl._DataLoaderIter = dl._BaseDataLoaderIter
+sys.path.insert(0, %r)            # the reference (provides test.py and dataset/)
+pkg.install_dropin()              # ours first
+# dataset.kitti_dataset needs a few names our utils.tools does not carry at import time: none expected
+import test as ref_test
+ref_test.if_cuda = False
+import model.upflow
+assert model.upflow.__file__.startswith(pkg.DROPIN_DIR), model.upflow.__file__
+with contextlib.redirect_stdout(io.StringIO()):
+    tm = ref_test.Test_model(pretrain_path=%r)
+n = sum(p.numel() for p in tm.net_work.parameters())
+assert n == 3494549, n
+print("OK", type(tm.net_work).__module__)
+''' % (ROOT, ref_shims.REFERENCE_ROOT, ref_shims.CHECKPOINT)
+    r = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "OK model.upflow" in r.stdout

@@ -1,0 +1,76 @@
+"""ctypes binding of libupflow_b200.so (include/upflow_b200.h).
+
+The library is the product: there is NO fallback.  If it is missing, or a call
+is attempted without a CUDA device, this module raises."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libupflow_b200.so")
+
+_c = ctypes
+_P = _c.c_void_p
+_I = _c.c_int
+_F = _c.c_float
+_LL = _c.c_longlong
+
+# name -> (restype, argtypes); mirrors include/upflow_b200.h one to one
+SIGNATURES = {
+    "upf_abi_version": (_I, []),
+    "upf_last_error": (_c.c_char_p, []),
+    "upf_launch_count": (_LL, []),
+    "upf_corr_lrelu_fwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _F, _P]),
+    "upf_corr_lrelu_bwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "upf_warp_fwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "upf_warp_bwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "upf_featnorm_stats": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "upf_featnorm_apply": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "upf_resize_bilinear": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _c.POINTER(_F), _P]),
+    "upf_sgu_blend": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "upf_conv2d_fwd": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P]),
+    "upf_conv_tc_packed_elems": (_LL, [_I, _I, _I]),
+    "upf_conv_tc_pack_weights": (_I, [_P, _P, _I, _I, _I, _P]),
+    "upf_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "upf_nhwc_to_nchw": (_I, [_P, _I, _P, _I, _I, _I, _I, _P]),
+    "upf_copy_channels": (_I, [_P, _I, _P, _I, _LL, _I, _P]),
+}
+
+CONV_FP32 = 0
+CONV_TF32 = 1
+
+_lib = None
+
+
+class UpflowLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (building is ``__graft_entry__.build()`` /
+    ``python -m upflow_pytorch_b200.build``); raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise UpflowLibraryError(
+            "%s not found: build it with `python -m upflow_pytorch_b200.build` "
+            "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the header and the .so disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.upf_abi_version() != 1:
+        raise UpflowLibraryError("ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().upf_last_error()
+        raise RuntimeError("upflow_b200.%s failed (%d): %s" % (what, code, msg.decode() if msg else ""))
+
+
+def launch_count():
+    return int(load().upf_launch_count())

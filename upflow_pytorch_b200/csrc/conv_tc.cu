@@ -1,0 +1,390 @@
+// 3x3 / 1x1 stride-1 convolution on the 5th-generation tensor cores (sm_100a):
+// implicit GEMM, TF32 operands read straight from the fp32 feature buffers,
+// fp32 accumulation in tensor memory.
+//
+// Replaces the cuDNN calls behind conv() (model/pwc_modules.py:10-31) for the
+// dense flow estimator (:279-286), the dilated context network (:401-412) and
+// the SGU dense block (model/upflow.py:52-60).
+//
+//   GEMM view  D[M=128 pixels, N=Cout] += A[M, K] * B[N, K]^T,  K = taps x Cin
+//   A  : im2col-free.  The activation tensor is a 4-D TMA tensor
+//        (C, W, H, N); for tap (ky,kx) and channel block kc the producer issues
+//        ONE box load {32 ch, TW, TH, 1} at (kc*32, x0+(kx-1)*dil, y0+(ky-1)*dil, n).
+//        TMA's out-of-bounds zero fill IS the convolution's zero padding (and
+//        the K remainder when Cin % 32 != 0).  The box lands in shared memory as
+//        128 rows (pixels) x 128 bytes with SWIZZLE_128B = the canonical K-major
+//        UMMA operand layout.
+//   B  : weights pre-packed [tap][cout_pad16][cin_pad32]; box {32, BN, 1}.
+//   D  : TMEM, 128 lanes (pixels) x BN columns (output channels), fp32.
+//   pipeline: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread,
+//        tcgen05.mma.cta_group::1.kind::tf32, 4 x K=8 per 32-channel block),
+//        warps 2-5 = epilogue (tcgen05.ld 32x32b -> bias + LeakyReLU + residual
+//        -> 16-byte stores into the output channel slice).  smem full/empty
+//        mbarriers ring over NSTAGE stages; tcgen05.commit releases stages and
+//        publishes the accumulator.
+//   Two CTAs are resident per SM so one CTA's epilogue overlaps the other's
+//   main loop.
+#include "upf_common.cuh"
+
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+
+namespace upf {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_KC = 32;               // channels per K block (128 B of fp32)
+constexpr int TC_A_BYTES = 128 * 128;   // 128 pixels x 128 B
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+// K-major, SWIZZLE_128B shared-memory operand descriptor (rows of 128 B, 8-row
+// atoms 1024 B apart): start>>4 | LBO(unused for swizzled K-major)=1 | SBO=1024>>4 |
+// version=1 (sm_100) | layout_type=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+struct TcParams {
+  float* out; int ldo;
+  const float* res; int ldr;
+  const float* bias;
+  int H, W, Cout, BN;          // BN = cout padded to 16
+  int TH, TW, tiles_x, tiles_y;
+  int ks, dil, kblocks;        // kblocks = ceil(Cin/32)
+  int nstage, tmem_cols;
+  float slope;
+};
+
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages: A | B] ... then barriers
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t stage_bytes = TC_A_BYTES + ((b_bytes + 1023u) & ~1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)p.nstage * stage_bytes);
+  uint64_t* full = bars;                       // [nstage]
+  uint64_t* empty = bars + p.nstage;           // [nstage]
+  uint64_t* accum_full = bars + 2 * p.nstage;  // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.nstage + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int tile = blockIdx.x;
+  const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+  const int ty = tile % p.tiles_y;
+  const int n = tile / p.tiles_y;
+  const int x0 = tx * p.TW, y0 = ty * p.TH;
+  const int taps = p.ks * p.ks;
+  const int iters = taps * p.kblocks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < p.nstage; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    mbar_init(smem_u32(accum_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const int half = (p.ks - 1) / 2;
+      int it = 0;
+      for (int tap = 0; tap < taps; ++tap) {
+        const int ky = tap / p.ks, kx = tap - ky * p.ks;
+        const int cy = y0 + (ky - half) * p.dil, cx = x0 + (kx - half) * p.dil;
+        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          const int s = it % p.nstage;
+          const uint32_t ph = (uint32_t)(it / p.nstage) & 1u;
+          mbar_wait(smem_u32(&empty[s]), ph ^ 1u);            // slot free (first pass returns at once)
+          const uint32_t a_dst = smem_u32(base + (size_t)s * stage_bytes);
+          const uint32_t b_dst = a_dst + TC_A_BYTES;
+          const uint32_t fb = smem_u32(&full[s]);
+          mbar_expect_tx(fb, TC_A_BYTES + b_bytes);
+          tma_load_4d(a_dst, &map_x, fb, kb * TC_KC, cx, cy, n);
+          tma_load_3d(b_dst, &map_w, fb, kb * TC_KC, 0, tap);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor: D=f32 (bit4), A=B=TF32 (2<<7, 2<<10), K-major both, N>>3 @17, M>>4 @24
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % p.nstage;
+      const uint32_t ph = (uint32_t)(it / p.nstage) & 1u;
+      mbar_wait(smem_u32(&full[s]), ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(base + (size_t)s * stage_bytes);
+        const uint64_t da = umma_desc_sw128(a_addr);
+        const uint64_t db = umma_desc_sw128(a_addr + TC_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 bytes): advance the start address inside the swizzle atom
+          umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(smem_u32(&empty[s]));                      // frees the stage when these MMAs retire
+        if (it == iters - 1) umma_commit(smem_u32(accum_full));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                                    // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;                             // pixel index inside the tile
+    const int py = y0 + row / p.TW, px = x0 + row % p.TW;
+    const bool valid = (py < p.H) && (px < p.W);
+    const size_t pix = ((size_t)n * p.H + py) * p.W + px;
+    float* o = p.out + pix * p.ldo;
+    const float* r = p.res ? p.res + pix * p.ldr : nullptr;
+    const bool vec_out = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    mbar_wait(smem_u32(accum_full), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (valid) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int co = c0 + j;
+          float acc = __uint_as_float(v[j]);
+          if (co < p.Cout) {
+            acc = lrelu(acc + __ldg(p.bias + co), p.slope);
+            if (r) acc += __ldg(r + co);
+          }
+          f[j] = acc;
+        }
+        if (vec_out && c0 + 16 <= p.Cout) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < p.Cout) o[c0 + j] = f[j];
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// weights: SIMT layout [tap][cin][cout_pad4] -> packed [tap][cout_pad16][cin_pad32]
+__global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int Cin, int Cout, int taps,
+                                    int cout_pad4, int cout_pad16, int cin_pad32) {
+  const long long total = (long long)taps * cout_pad16 * cin_pad32;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin_pad32);
+    const int co = (int)((i / cin_pad32) % cout_pad16);
+    const int tap = (int)(i / ((long long)cin_pad32 * cout_pad16));
+    float v = 0.f;
+    if (ci < Cin && co < Cout) v = w[((size_t)tap * Cin + ci) * cout_pad4 + co];
+    wp[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; long long a, b, c, d, e;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && a == o.a && b == o.b && c == o.c && d == o.d && e == o.e; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    for (long long v : {k.a, k.b, k.c, k.d, k.e}) h = h * 1000003u ^ std::hash<long long>()(v);
+    return h;
+  }
+};
+static std::mutex g_map_mu;
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+static int encode_cached(const MapKey& key, CUtensorMap* out, cuuint32_t rank, void* ptr, const cuuint64_t* dims,
+                         const cuuint64_t* strides, const cuuint32_t* box) {
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return 0; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled not available"); return UPF_EDRIVER; }
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return UPF_EDRIVER; }
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps.emplace(key, *out);
+  return 0;
+}
+
+static void pick_tile(int H, int W, int* TH, int* TW) {
+  // 128 pixels per tile; pick the shape (TW multiple of 8) wasting the fewest pixels
+  long long best = -1;
+  for (int tw = 8; tw <= 128; tw <<= 1) {
+    const int th = 128 / tw;
+    const long long cover = (long long)((H + th - 1) / th) * ((W + tw - 1) / tw);
+    if (best < 0 || cover < best || (cover == best && tw == 16)) { best = cover; *TH = th; *TW = tw; }
+  }
+}
+
+int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
+                  const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int dil, float slope,
+                  cudaStream_t st) {
+  UPF_REQUIRE(Cout <= 128, "conv_tc: Cout %d > 128", Cout);
+  UPF_REQUIRE((ldx % 4) == 0 && aligned16(x) && aligned16(w_packed), "conv_tc: input pitch/pointer must be 16-byte aligned");
+  const int BN = (Cout + 15) & ~15;
+  const int kblocks = (Cin + TC_KC - 1) / TC_KC;
+  const int cin_pad = kblocks * TC_KC;
+  const int taps = ks * ks;
+  int TH = 8, TW = 16;
+  pick_tile(H, W, &TH, &TW);
+
+  CUtensorMap mx, mw;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
+    const cuuint32_t box[4] = {TC_KC, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+    MapKey key{x, ldx, ((long long)H << 32) | (unsigned)W, ((long long)N << 32) | (unsigned)Cin, TW, 4};
+    int e = encode_cached(key, &mx, 4, const_cast<float*>(x), dims, strides, box);
+    if (e) return e;
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)BN, (cuuint64_t)taps};
+    const cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 4, (cuuint64_t)cin_pad * BN * 4};
+    const cuuint32_t box[3] = {TC_KC, (cuuint32_t)BN, 1};
+    MapKey key{w_packed, cin_pad, BN, taps, 0, 3};
+    int e = encode_cached(key, &mw, 3, const_cast<float*>(w_packed), dims, strides, box);
+    if (e) return e;
+  }
+
+  TcParams p;
+  p.out = out; p.ldo = ldo; p.res = res; p.ldr = ldr; p.bias = bias;
+  p.H = H; p.W = W; p.Cout = Cout; p.BN = BN;
+  p.TH = TH; p.TW = TW; p.tiles_x = (W + TW - 1) / TW; p.tiles_y = (H + TH - 1) / TH;
+  p.ks = ks; p.dil = dil; p.kblocks = kblocks;
+  p.slope = slope;
+  p.tmem_cols = BN <= 32 ? 32 : (BN <= 64 ? 64 : 128);
+  const int stage_bytes = TC_A_BYTES + ((BN * 128 + 1023) & ~1023);
+  int nstage = (108 * 1024) / stage_bytes;       // two CTAs per SM
+  if (nstage > 6) nstage = 6;
+  if (nstage < 2) nstage = 2;
+  p.nstage = nstage;
+  const size_t smem = (size_t)nstage * stage_bytes + (2 * nstage + 2) * 8 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("conv_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_set = true;
+  }
+  const long long tiles = (long long)p.tiles_x * p.tiles_y * N;
+  conv_tc_kernel<<<(unsigned)tiles, TC_THREADS, smem, st>>>(mx, mw, p);
+  return check_launch("conv_tc");
+}
+
+}  // namespace upf
+
+extern "C" long long upf_conv_tc_packed_elems(int Cin, int Cout, int ksize) {
+  const long long cin_pad = (Cin + 31) / 32 * 32, cout_pad = (Cout + 15) / 16 * 16;
+  return (long long)ksize * ksize * cout_pad * cin_pad;
+}
+
+extern "C" int upf_conv_tc_pack_weights(const float* w_simt, float* w_packed, int Cin, int Cout, int ksize, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(w_simt && w_packed && Cin > 0 && Cout > 0 && (ksize == 1 || ksize == 3), "pack_weights: bad argument");
+  const int taps = ksize * ksize;
+  const int cout_pad4 = (Cout + 3) & ~3, cout_pad16 = (Cout + 15) & ~15, cin_pad32 = (Cin + 31) / 32 * 32;
+  const long long total = (long long)taps * cout_pad16 * cin_pad32;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w_simt, w_packed, Cin, Cout, taps, cout_pad4,
+                                                                         cout_pad16, cin_pad32);
+  return check_launch("pack_weights");
+}

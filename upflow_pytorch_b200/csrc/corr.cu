@@ -1,0 +1,318 @@
+// Fused cost volume + (optional) feature normalisation + LeakyReLU, forward and
+// backward, for sm_100a.
+//
+// Replaces correlation_cuda_kernel.cu:15-114 (channels_first x2 + one block of
+// 32 threads per output pixel, 81 serial shared-memory reductions) and the
+// F.unfold formulation of utils/pytorch_correlation.py:27-50.
+//
+// Forward design (HBM-bound at C=32: 4*(2C+81) B/pixel vs 2*81*C flop/pixel):
+//   * one CTA owns an 8-row x 32-column pixel tile; the f2 search window
+//     ((8+2d) x (32+2d) positions) and the f1 tile are staged ONCE in shared
+//     memory, 32 channels (one 128-byte row) per position, 16-byte chunks
+//     XOR-swizzled by (position & 7) -- the layout TMA's SWIZZLE_128B produces
+//     -- so that 8 consecutive lanes reading the same chunk of 8 consecutive
+//     positions hit 8 different bank groups;
+//   * zero padding is produced while staging (out-of-image positions are
+//     written as zeros): no padded copy, no transpose, no memset;
+//   * the normalisation (x-mean)/std of model/upflow.py:126-135 is applied in
+//     registers between the global load and the shared store, so normalised
+//     tensors never exist in HBM;
+//   * warp w handles horizontal displacement dx = w - d, lane l handles column
+//     l of the tile and walks the 8 rows: every f2 value loaded from shared
+//     memory feeds up to 8 pixels x 4 channels = 32 FMAs and every f1 value 9
+//     (register tile 8 pixels x (2d+1) vertical displacements, 3 FMA per float
+//     read from shared memory);
+//   * results are transposed through shared memory and stored as contiguous
+//     (2d+1)^2-float runs per pixel straight into the channel slice of the
+//     decoder's feature buffer.
+#include "upf_common.cuh"
+
+namespace upf {
+
+constexpr int CORR_TX = 32;   // tile columns == lanes
+constexpr int CORR_TY = 8;    // tile rows == pixels per thread
+constexpr int CORR_CC = 32;   // channels staged per pass (128 B per position)
+
+template <int D>
+struct CorrCfg {
+  static constexpr int WIN = 2 * D + 1;
+  static constexpr int NWARPS = WIN;
+  static constexpr int NT = NWARPS * 32;
+  static constexpr int HROWS = CORR_TY + 2 * D;
+  static constexpr int HCOLS = CORR_TX + 2 * D;
+  static constexpr int HPOS = HROWS * HCOLS;
+  static constexpr int F1POS = CORR_TX * CORR_TY;
+  static constexpr int NOUT = WIN * WIN;
+  static constexpr int STAGE_BYTES = (HPOS + F1POS) * CORR_CC * 4;
+  static constexpr int OUT_BYTES = F1POS * NOUT * 4;
+  static constexpr int SMEM_BYTES = (STAGE_BYTES > OUT_BYTES ? STAGE_BYTES : OUT_BYTES) + 4 * CORR_CC * 4;
+};
+
+__device__ __forceinline__ int swz(int pos, int chunk) { return pos * 32 + (((chunk ^ pos) & 7) << 2); }  // float index
+
+// stage `npos` positions x 32 channels of one operand into swizzled smem
+template <int NT, bool VEC>
+__device__ __forceinline__ void corr_stage(float* __restrict__ dst, const float* __restrict__ src, int ld,
+                                           int n, int H, int W, int C, int c0, int y_org, int x_org, int cols,
+                                           int npos, const float* __restrict__ mean, const float* __restrict__ stdv,
+                                           bool norm) {
+  const int units = npos * 8;
+  for (int u = threadIdx.x; u < units; u += NT) {
+    const int pos = u >> 3, chunk = u & 7;
+    const int r = pos / cols, cidx = pos - r * cols;
+    const int y = y_org + r, x = x_org + cidx;
+    const int c = c0 + chunk * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y >= 0 && y < H && x >= 0 && x < W && c < C) {
+      const float* p = src + ((size_t)((size_t)n * H + y) * W + x) * ld + c;
+      if (VEC) {
+        v = ldg4(p);
+      } else {
+        v.x = __ldg(p);
+        if (c + 1 < C) v.y = __ldg(p + 1);
+        if (c + 2 < C) v.z = __ldg(p + 2);
+        if (c + 3 < C) v.w = __ldg(p + 3);
+      }
+      if (norm) {
+        const int k = chunk * 4;
+        v.x = __fdiv_rn(__fsub_rn(v.x, mean[k + 0]), stdv[k + 0]);
+        v.y = __fdiv_rn(__fsub_rn(v.y, mean[k + 1]), stdv[k + 1]);
+        v.z = __fdiv_rn(__fsub_rn(v.z, mean[k + 2]), stdv[k + 2]);
+        v.w = __fdiv_rn(__fsub_rn(v.w, mean[k + 3]), stdv[k + 3]);
+        if (!VEC) {  // channels past C must stay exactly zero
+          if (c + 1 >= C) v.y = 0.f;
+          if (c + 2 >= C) v.z = 0.f;
+          if (c + 3 >= C) v.w = 0.f;
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(dst + swz(pos, chunk)) = v;
+  }
+}
+
+template <int D, bool VEC>
+__global__ void __launch_bounds__(CorrCfg<D>::NT, (D <= 4 ? 2 : 1))
+corr_fwd_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__ f2, int ld2,
+                float* __restrict__ out, int ldo, int H, int W, int C,
+                const double* __restrict__ stats1, const double* __restrict__ stats2,
+                float slope, int tiles_x, int tiles_y, int n2_shift, int N) {
+  using K = CorrCfg<D>;
+  extern __shared__ __align__(128) float smem[];
+  float* s_f2 = smem;
+  float* s_f1 = smem + K::HPOS * CORR_CC;
+  float* s_stat = smem + (K::SMEM_BYTES / 4 - 4 * CORR_CC);   // mean1,std1,mean2,std2 of the current chunk
+  float* s_out = smem;                                        // overlays the staging area
+
+  int tile = blockIdx.x;
+  const int tx = tile % tiles_x; tile /= tiles_x;
+  const int ty = tile % tiles_y;
+  const int n = tile / tiles_y;
+  const int n2 = (n + n2_shift) % N;
+  const int x0 = tx * CORR_TX, y0 = ty * CORR_TY;
+  const int lane = threadIdx.x & 31, dxi = threadIdx.x >> 5;
+  const bool norm = stats1 != nullptr;
+  const double npix = (double)H * (double)W;
+
+  float acc[CORR_TY][K::WIN];
+#pragma unroll
+  for (int p = 0; p < CORR_TY; ++p)
+#pragma unroll
+    for (int q = 0; q < K::WIN; ++q) acc[p][q] = 0.f;
+
+  for (int c0 = 0; c0 < C; c0 += CORR_CC) {
+    if (c0 > 0) __syncthreads();          // previous pass finished reading the stage
+    if (norm) {
+      if (threadIdx.x < 2 * CORR_CC) {
+        const int which = threadIdx.x >> 5, k = threadIdx.x & 31, c = c0 + k;
+        float m = 0.f, s = 1.f;
+        if (c < C) stats_to_mean_std((which ? stats2 + ((size_t)n2 * C + c) * 2 : stats1 + ((size_t)n * C + c) * 2), npix, m, s);
+        s_stat[which * 2 * CORR_CC + k] = m;
+        s_stat[which * 2 * CORR_CC + CORR_CC + k] = s;
+      }
+      __syncthreads();
+    }
+    corr_stage<K::NT, VEC>(s_f2, f2, ld2, n2, H, W, C, c0, y0 - D, x0 - D, K::HCOLS, K::HPOS,
+                           s_stat + 2 * CORR_CC, s_stat + 3 * CORR_CC, norm);
+    corr_stage<K::NT, VEC>(s_f1, f1, ld1, n, H, W, C, c0, y0, x0, CORR_TX, K::F1POS,
+                           s_stat, s_stat + CORR_CC, norm);
+    __syncthreads();
+
+    const int cend = (C - c0 < CORR_CC ? C - c0 : CORR_CC);
+    const int nchunk = (cend + 3) >> 2;
+    for (int ch = 0; ch < nchunk; ++ch) {
+      float4 a[CORR_TY];
+#pragma unroll
+      for (int p = 0; p < CORR_TY; ++p)
+        a[p] = *reinterpret_cast<const float4*>(s_f1 + swz(p * CORR_TX + lane, ch));
+#pragma unroll
+      for (int j = 0; j < K::HROWS; ++j) {
+        const float4 b = *reinterpret_cast<const float4*>(s_f2 + swz(j * K::HCOLS + lane + dxi, ch));
+#pragma unroll
+        for (int p = 0; p < CORR_TY; ++p) {
+          const int dyi = j - p;
+          if (dyi >= 0 && dyi < K::WIN) {
+            float s = acc[p][dyi];
+            s = fmaf(a[p].x, b.x, s);
+            s = fmaf(a[p].y, b.y, s);
+            s = fmaf(a[p].z, b.z, s);
+            s = fmaf(a[p].w, b.w, s);
+            acc[p][dyi] = s;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();   // staging area is dead: reuse it for the output transpose
+
+  // mean over channels (torch.mean, utils/pytorch_correlation.py:47): exact
+  // reciprocal when C is a power of two, true division otherwise
+  const bool pow2 = (C & (C - 1)) == 0;
+  const float inv = 1.0f / (float)C, fC = (float)C;
+#pragma unroll
+  for (int p = 0; p < CORR_TY; ++p)
+#pragma unroll
+    for (int q = 0; q < K::WIN; ++q) {
+      float v = pow2 ? acc[p][q] * inv : __fdiv_rn(acc[p][q], fC);
+      s_out[(p * CORR_TX + lane) * K::NOUT + q * K::WIN + dxi] = lrelu(v, slope);
+    }
+  __syncthreads();
+
+  // coalesced store: each tile row is 32 pixels x NOUT contiguous floats (pitch ldo)
+  for (int r = 0; r < CORR_TY; ++r) {
+    const int y = y0 + r;
+    if (y >= H) break;
+    const int wvalid = (W - x0 < CORR_TX ? W - x0 : CORR_TX);
+    float* orow = out + ((size_t)((size_t)n * H + y) * W + x0) * ldo;
+    const float* srow = s_out + r * CORR_TX * K::NOUT;
+    const int total = wvalid * K::NOUT;
+    for (int e = threadIdx.x; e < total; e += K::NT) {
+      const int px = e / K::NOUT, k = e - px * K::NOUT;
+      orow[(size_t)px * ldo + k] = srow[e];
+    }
+  }
+}
+
+template <int D>
+static int launch_corr_fwd(const float* f1, int ld1, const float* f2, int ld2, float* out, int ldo,
+                           int N, int H, int W, int C, const double* s1, const double* s2, int shift,
+                           float slope, cudaStream_t st) {
+  using K = CorrCfg<D>;
+  const int tiles_x = (W + CORR_TX - 1) / CORR_TX, tiles_y = (H + CORR_TY - 1) / CORR_TY;
+  const long long tiles = (long long)tiles_x * tiles_y * N;
+  UPF_REQUIRE(tiles > 0 && tiles < (1ll << 31), "corr: bad tile count %lld", tiles);
+  const bool vec = (C % 4 == 0) && (ld1 % 4 == 0) && (ld2 % 4 == 0) && aligned16(f1) && aligned16(f2);
+  cudaError_t e;
+  if (vec) {
+    e = cudaFuncSetAttribute(corr_fwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("corr smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    corr_fwd_kernel<D, true><<<(unsigned)tiles, K::NT, K::SMEM_BYTES, st>>>(f1, ld1, f2, ld2, out, ldo, H, W, C, s1, s2,
+                                                                          slope, tiles_x, tiles_y, shift, N);
+  } else {
+    e = cudaFuncSetAttribute(corr_fwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("corr smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    corr_fwd_kernel<D, false><<<(unsigned)tiles, K::NT, K::SMEM_BYTES, st>>>(f1, ld1, f2, ld2, out, ldo, H, W, C, s1,
+                                                                           s2, slope, tiles_x, tiles_y, shift, N);
+  }
+  return check_launch("corr_fwd");
+}
+
+// --------------------------------------------------------------------------
+// backward (correlation_cuda_kernel.cu:116-300).  One thread per (pixel,
+// 4-channel group): gO (pre-multiplied by the LeakyReLU derivative and 1/C) is
+// read 81 times per pixel from L1/L2, f1/f2 rows are 128-byte coalesced.
+//   g1[n,y,x,c] = sum_k g[n,y,x,k]        * f2[n,y+dy,x+dx,c]
+//   g2[n,y,x,c] = sum_k g[n,y-dy,x-dx,k]  * f1[n,y-dy,x-dx,c]
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+corr_bwd_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__ f2, int ld2,
+                const float* __restrict__ outv, int ldo, const float* __restrict__ go, int ldg,
+                float* __restrict__ g1, int ldg1, float* __restrict__ g2, int ldg2,
+                int N, int H, int W, int C, int D, float slope) {
+  const int cg = (C + 3) >> 2;
+  const long long total = (long long)N * H * W * cg;
+  const int WIN = 2 * D + 1;
+  const float invC = 1.0f / (float)C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cg) * 4;
+    long long pix = i / cg;
+    const int x = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    float a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+    const float* go_p = go + (size_t)pix * ldg;
+    const float* ov_p = outv ? outv + (size_t)pix * ldo : nullptr;
+    for (int dy = -D; dy <= D; ++dy)
+      for (int dx = -D; dx <= D; ++dx) {
+        const int k = (dy + D) * WIN + dx + D;
+        // gradient wrt f1 at (y,x): partner f2 at (y+dy,x+dx)
+        int yy = y + dy, xx = x + dx;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          float g = __ldg(go_p + k) * invC;
+          if (ov_p && __ldg(ov_p + k) < 0.f) g *= slope;
+          const float* q = f2 + ((size_t)((size_t)n * H + yy) * W + xx) * ld2 + c;
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (c + t < C) a1[t] = fmaf(g, __ldg(q + t), a1[t]);
+        }
+        // gradient wrt f2 at (y,x): partner f1 at (y-dy,x-dx), whose output channel k looked at us
+        yy = y - dy; xx = x - dx;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          const size_t ppix = (size_t)((size_t)n * H + yy) * W + xx;
+          float g = __ldg(go + ppix * ldg + k) * invC;
+          if (outv && __ldg(outv + ppix * ldo + k) < 0.f) g *= slope;
+          const float* q = f1 + ppix * ld1 + c;
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (c + t < C) a2[t] = fmaf(g, __ldg(q + t), a2[t]);
+        }
+      }
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (c + t < C) {
+        if (g1) g1[(size_t)pix * ldg1 + c + t] = a1[t];
+        if (g2) g2[(size_t)pix * ldg2 + c + t] = a2[t];
+      }
+  }
+}
+
+}  // namespace upf
+
+extern "C" int upf_corr_lrelu_fwd(const float* f1, int ld1, const float* f2, int ld2, float* out, int ldo,
+                                  int N, int H, int W, int C, int max_disp,
+                                  const double* stats1, const double* stats2, int f2_batch_shift,
+                                  float slope, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(f1 && f2 && out, "corr: null tensor");
+  UPF_REQUIRE(f2_batch_shift >= 0 && f2_batch_shift < N, "corr: batch shift out of range");
+  UPF_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "corr: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
+  UPF_REQUIRE(ld1 >= C && ld2 >= C, "corr: pitch smaller than C");
+  const int nout = (2 * max_disp + 1) * (2 * max_disp + 1);
+  UPF_REQUIRE(ldo >= nout, "corr: output pitch %d < %d", ldo, nout);
+  UPF_REQUIRE((stats1 == nullptr) == (stats2 == nullptr), "corr: give both stats or neither");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (max_disp) {
+    case 1: return launch_corr_fwd<1>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);
+    case 2: return launch_corr_fwd<2>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);
+    case 3: return launch_corr_fwd<3>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);
+    case 4: return launch_corr_fwd<4>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);
+    case 5: return launch_corr_fwd<5>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);
+    case 6: return launch_corr_fwd<6>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);
+    default: set_error("corr: max_disp %d not in 1..6", max_disp); return UPF_ENOTSUP;
+  }
+}
+
+extern "C" int upf_corr_lrelu_bwd(const float* f1, int ld1, const float* f2, int ld2, const float* out, int ldo,
+                                  const float* grad_out, int ldg, float* grad_f1, int ldg1, float* grad_f2, int ldg2,
+                                  int N, int H, int W, int C, int max_disp, float slope, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(f1 && f2 && grad_out, "corr_bwd: null tensor");
+  UPF_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && max_disp >= 1 && max_disp <= 6, "corr_bwd: bad shape");
+  UPF_REQUIRE(slope == 1.0f || out != nullptr, "corr_bwd: LeakyReLU derivative needs the forward output");
+  const long long total = (long long)N * H * W * ((C + 3) / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > UPF_NUM_SMS * 32) blocks = UPF_NUM_SMS * 32;
+  corr_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(f1, ld1, f2, ld2, slope == 1.0f ? nullptr : out,
+                                                                     ldo, grad_out, ldg, grad_f1, ldg1, grad_f2, ldg2,
+                                                                     N, H, W, C, max_disp, slope);
+  return check_launch("corr_bwd");
+}

@@ -1,0 +1,121 @@
+// Shared host/device helpers for the upflow_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/upflow_b200.h"
+
+#define UPF_NUM_SMS 148   // B200: 2 dies x 74 SMs
+
+namespace upf {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+// every launch goes through here so that a bad configuration is reported to
+// the caller as a return code (the reference printf's and AT_ERRORs instead:
+// correlation_cuda_kernel.cu:383-390, correlation_cuda.cc:81-83)
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  count_launch();
+  return 0;
+}
+
+#define UPF_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      upf::set_error(__VA_ARGS__);        \
+      return UPF_EINVAL;                  \
+    }                                     \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v < 0.f ? v * slope : v; }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// mean / rstd of one (image, channel) from accumulated double sums; the
+// reference uses torch.mean and the UNBIASED torch.var (model/upflow.py:113-114)
+// and std = sqrt(var + 1e-16) (:126)
+__device__ __forceinline__ void stats_to_mean_std(const double* s, double npix, float& mean, float& stdv) {
+  double m = s[0] / npix;
+  double var = (s[1] - s[0] * m) / (npix - 1.0);
+  if (var < 0.0) var = 0.0;
+  mean = (float)m;
+  // the reference rounds var to fp32, adds 1e-16 in fp32, takes an fp32 sqrt and divides
+  float varf = (float)var;
+  stdv = sqrtf(varf + 1e-16f);   // callers DIVIDE by it, like the reference (f / std)
+}
+
+// ---- bilinear sampling coordinates, bit-faithful to the reference --------
+// pixel + flow -> [-1,1] with three separately rounded ops (pwc_modules.py:195-198),
+// then ATen's grid_sampler_unnormalize (native/cuda/GridSampler.cuh:23-31); for
+// align_corners=False the CPU and CUDA ATen kernels both evaluate
+// ((g+1)*size-1)/2 with one rounding (fused multiply-add).
+__device__ __forceinline__ float sample_coord(float pix, float disp, int size, int align_corners) {
+  float denom = (float)(size > 1 ? size - 1 : 1);
+  float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn(pix, disp)), denom), 1.0f);
+  float gp1 = __fadd_rn(g, 1.0f);
+  if (align_corners) return __fmul_rn(__fmul_rn(gp1, 0.5f), (float)(size - 1));
+  return __fmaf_rn(gp1, 0.5f * (float)size, -0.5f);
+}
+
+struct BilinearTaps {
+  int x0, y0;            // north-west corner (x1 = x0+1, y1 = y0+1)
+  float w_nw, w_ne, w_sw, w_se;
+  bool in_nw, in_ne, in_sw, in_se;
+  float wsum;            // sum of in-bounds weights, accumulated nw, ne, sw, se from 0
+};
+
+__device__ __forceinline__ BilinearTaps bilinear_taps(float ix, float iy, int H, int W) {
+  BilinearTaps t;
+  float fx0 = floorf(ix), fy0 = floorf(iy);
+  float fx1 = __fadd_rn(fx0, 1.0f), fy1 = __fadd_rn(fy0, 1.0f);
+  t.w_nw = __fmul_rn(__fsub_rn(fx1, ix), __fsub_rn(fy1, iy));
+  t.w_ne = __fmul_rn(__fsub_rn(ix, fx0), __fsub_rn(fy1, iy));
+  t.w_sw = __fmul_rn(__fsub_rn(fx1, ix), __fsub_rn(iy, fy0));
+  t.w_se = __fmul_rn(__fsub_rn(ix, fx0), __fsub_rn(iy, fy0));
+  // clamp before the int conversion so wild flows cannot overflow
+  float cx = fminf(fmaxf(fx0, -2.0f), (float)W + 1.0f);
+  float cy = fminf(fmaxf(fy0, -2.0f), (float)H + 1.0f);
+  t.x0 = (int)cx;
+  t.y0 = (int)cy;
+  bool xin0 = t.x0 >= 0 && t.x0 < W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+  bool yin0 = t.y0 >= 0 && t.y0 < H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+  // NaN coordinates sample nothing
+  bool ok = (ix == ix) && (iy == iy);
+  t.in_nw = ok && xin0 && yin0;
+  t.in_ne = ok && xin1 && yin0;
+  t.in_sw = ok && xin0 && yin1;
+  t.in_se = ok && xin1 && yin1;
+  float s = 0.0f;
+  if (t.in_nw) s = __fadd_rn(s, t.w_nw);
+  if (t.in_ne) s = __fadd_rn(s, t.w_ne);
+  if (t.in_sw) s = __fadd_rn(s, t.w_sw);
+  if (t.in_se) s = __fadd_rn(s, t.w_se);
+  t.wsum = s;
+  return t;
+}
+
+// align_corners=True source tap of F.interpolate(bilinear)
+// (ATen native/cuda/UpSample.cuh:100-124: scale=(in-1)/(out-1), src=scale*dst)
+struct AxisTap { int i0, i1; float l0, l1; };
+__device__ __forceinline__ AxisTap axis_tap(int dst, int n_in, float scale) {
+  AxisTap t;
+  float src = __fmul_rn(scale, (float)dst);
+  t.i0 = (int)src;
+  if (t.i0 > n_in - 1) t.i0 = n_in - 1;
+  t.i1 = t.i0 + (t.i0 < n_in - 1 ? 1 : 0);
+  t.l1 = __fsub_rn(src, (float)t.i0);
+  t.l0 = __fsub_rn(1.0f, t.l1);
+  return t;
+}
+inline float host_ac_scale(int n_in, int n_out) { return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.0f; }
+
+}  // namespace upf

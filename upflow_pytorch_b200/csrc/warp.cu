@@ -1,0 +1,330 @@
+// Bilinear warp + validity mask (+ per-channel moments of the result), its
+// backward, and the per-image per-channel feature normalisation.
+//
+// Replaces WarpingLayer_no_div.forward (model/pwc_modules.py:184-207: host-built
+// mesh + host-built ones(B,C,H,W) + two grid_sample passes + compare + multiply)
+// and tools.torch_warp (utils/tools.py:1274-1304) with ONE pass: the four
+// gathers are 16-byte loads of pixel-major rows, the validity mask is computed
+// once per pixel (not per channel), and the per-(image,channel) sum / sum of
+// squares that normalize_features (model/upflow.py:94-137) needs afterwards
+// are reduced on the fly (registers -> shared memory -> one double atomic per
+// channel per CTA).
+#include "upf_common.cuh"
+
+namespace upf {
+
+constexpr int WARP_NT = 256;
+
+// thread layout: `lpp` lanes per pixel (each lane owns 4 consecutive channels
+// per pass), WARP_NT/lpp pixels per CTA step; a CTA strides over the pixels of
+// ONE image so the moment reduction stays per image.
+template <bool VEC>
+__global__ void __launch_bounds__(WARP_NT)
+warp_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ flow, int ldf,
+                float* __restrict__ out, int ldo, int H, int W, int C, int align_corners, int use_mask,
+                double* __restrict__ stats, int lpp, int ctas_per_image, int x_shift, int N) {
+  extern __shared__ double s_red[];   // [2][cgroups*4] when stats
+  const int n = blockIdx.x / ctas_per_image;
+  const int cta = blockIdx.x - n * ctas_per_image;
+  const int ppc = WARP_NT / lpp;                 // pixels per CTA step
+  const int sub = threadIdx.x % lpp;             // which 4-channel group (first pass)
+  const int pslot = threadIdx.x / lpp;
+  const int cgroups = (C + 3) >> 2;
+  const int passes = (cgroups + lpp - 1) / lpp;
+  const int npix = H * W;
+  const size_t img = (size_t)n * npix;
+  const long long ximg = (long long)((n + x_shift) % N) * npix;
+
+  // per-thread moment accumulators for up to 2 passes (C <= 8*lpp <= 256)
+  float sm[2][4], sq[2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) sm[a][t] = sq[a][t] = 0.f;
+
+  for (int p = cta * ppc + pslot; p < npix; p += ctas_per_image * ppc) {
+    const int y = p / W, xpix = p - y * W;
+    const float* fl = flow + (img + p) * ldf;
+    const float u = __ldg(fl), v = __ldg(fl + 1);
+    const float ix = sample_coord((float)xpix, u, W, align_corners);
+    const float iy = sample_coord((float)y, v, H, align_corners);
+    const BilinearTaps t = bilinear_taps(ix, iy, H, W);
+    const bool keep = !use_mask || t.wsum >= 1.0f;      // mask = (grid_sample(ones) >= 1.0), pwc_modules.py:205-206
+    const float* r_nw = x + (ximg + (long long)t.y0 * W + t.x0) * (long long)ldx;   // may point outside: only dereferenced when in_*
+    const float* r_ne = r_nw + ldx;
+    const float* r_sw = r_nw + (size_t)W * ldx;
+    const float* r_se = r_sw + ldx;
+    float* o = out + (img + p) * ldo;
+#pragma unroll 2
+    for (int pass = 0; pass < passes; ++pass) {
+      const int c = (pass * lpp + sub) * 4;
+      if (c >= C) break;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (keep) {
+        // same accumulation order as ATen's grid_sampler_2d: nw, ne, sw, se
+        if (VEC) {
+          if (t.in_nw) { float4 q = ldg4(r_nw + c); acc.x = fmaf(q.x, t.w_nw, acc.x); acc.y = fmaf(q.y, t.w_nw, acc.y); acc.z = fmaf(q.z, t.w_nw, acc.z); acc.w = fmaf(q.w, t.w_nw, acc.w); }
+          if (t.in_ne) { float4 q = ldg4(r_ne + c); acc.x = fmaf(q.x, t.w_ne, acc.x); acc.y = fmaf(q.y, t.w_ne, acc.y); acc.z = fmaf(q.z, t.w_ne, acc.z); acc.w = fmaf(q.w, t.w_ne, acc.w); }
+          if (t.in_sw) { float4 q = ldg4(r_sw + c); acc.x = fmaf(q.x, t.w_sw, acc.x); acc.y = fmaf(q.y, t.w_sw, acc.y); acc.z = fmaf(q.z, t.w_sw, acc.z); acc.w = fmaf(q.w, t.w_sw, acc.w); }
+          if (t.in_se) { float4 q = ldg4(r_se + c); acc.x = fmaf(q.x, t.w_se, acc.x); acc.y = fmaf(q.y, t.w_se, acc.y); acc.z = fmaf(q.z, t.w_se, acc.z); acc.w = fmaf(q.w, t.w_se, acc.w); }
+        } else {
+          float* a = &acc.x;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (c + k < C) {
+              float s = 0.f;
+              if (t.in_nw) s = fmaf(__ldg(r_nw + c + k), t.w_nw, s);
+              if (t.in_ne) s = fmaf(__ldg(r_ne + c + k), t.w_ne, s);
+              if (t.in_sw) s = fmaf(__ldg(r_sw + c + k), t.w_sw, s);
+              if (t.in_se) s = fmaf(__ldg(r_se + c + k), t.w_se, s);
+              a[k] = s;
+            }
+        }
+      }
+      if (VEC) {
+        *reinterpret_cast<float4*>(o + c) = acc;
+      } else {
+        const float* a = &acc.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (c + k < C) o[c + k] = a[k];
+      }
+      if (stats && pass < 2) {
+        sm[pass][0] += acc.x; sm[pass][1] += acc.y; sm[pass][2] += acc.z; sm[pass][3] += acc.w;
+        sq[pass][0] = fmaf(acc.x, acc.x, sq[pass][0]); sq[pass][1] = fmaf(acc.y, acc.y, sq[pass][1]);
+        sq[pass][2] = fmaf(acc.z, acc.z, sq[pass][2]); sq[pass][3] = fmaf(acc.w, acc.w, sq[pass][3]);
+      }
+    }
+  }
+
+  if (stats) {
+    // CTA reduction in double: s_red[k] (sum), s_red[4*cgroups + k] (sum of squares)
+    const int nch = cgroups * 4;
+    for (int i = threadIdx.x; i < 2 * nch; i += WARP_NT) s_red[i] = 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int c = (pass * lpp + sub) * 4;
+      if (pass < passes && c < C) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          atomicAdd(&s_red[c + k], (double)sm[pass][k]);
+          atomicAdd(&s_red[nch + c + k], (double)sq[pass][k]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += WARP_NT) {
+      atomicAdd(&stats[((size_t)n * C + c) * 2 + 0], s_red[c]);
+      atomicAdd(&stats[((size_t)n * C + c) * 2 + 1], s_red[nch + c]);
+    }
+  }
+}
+
+// moments of an existing tensor (same reduction skeleton, no sampling)
+__global__ void __launch_bounds__(WARP_NT)
+featnorm_stats_kernel(const float* __restrict__ x, int ldx, int H, int W, int C, double* __restrict__ stats,
+                      int lpp, int ctas_per_image, int vec) {
+  extern __shared__ double s_red[];
+  const int n = blockIdx.x / ctas_per_image;
+  const int cta = blockIdx.x - n * ctas_per_image;
+  const int ppc = WARP_NT / lpp;
+  const int sub = threadIdx.x % lpp, pslot = threadIdx.x / lpp;
+  const int cgroups = (C + 3) >> 2;
+  const int passes = (cgroups + lpp - 1) / lpp;
+  const int npix = H * W;
+  const size_t img = (size_t)n * npix;
+  float sm[2][4], sq[2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) sm[a][t] = sq[a][t] = 0.f;
+  // fp32 partial sums run over at most ~npix/(ctas*ppc) values before they are
+  // widened to double, which keeps the moments accurate to ~1e-7 relative
+  for (int p = cta * ppc + pslot; p < npix; p += ctas_per_image * ppc) {
+    const float* r = x + (img + p) * ldx;
+#pragma unroll 2
+    for (int pass = 0; pass < passes && pass < 2; ++pass) {
+      const int c = (pass * lpp + sub) * 4;
+      if (c >= C) break;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (vec) { float4 q = ldg4(r + c); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+      else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (c + k < C) v[k] = __ldg(r + c + k);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { sm[pass][k] += v[k]; sq[pass][k] = fmaf(v[k], v[k], sq[pass][k]); }
+    }
+  }
+  const int nch = cgroups * 4;
+  for (int i = threadIdx.x; i < 2 * nch; i += WARP_NT) s_red[i] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int c = (pass * lpp + sub) * 4;
+    if (pass < passes && c < C) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        atomicAdd(&s_red[c + k], (double)sm[pass][k]);
+        atomicAdd(&s_red[nch + c + k], (double)sq[pass][k]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += WARP_NT) {
+    atomicAdd(&stats[((size_t)n * C + c) * 2 + 0], s_red[c]);
+    atomicAdd(&stats[((size_t)n * C + c) * 2 + 1], s_red[nch + c]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+featnorm_apply_kernel(const float* __restrict__ x, int ldx, const double* __restrict__ stats,
+                      float* __restrict__ out, int ldo, int H, int W, int C, long long total) {
+  const double npix = (double)H * (double)W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pix = i / C;
+    const int n = (int)(pix / ((long long)H * W));
+    float m, s;
+    stats_to_mean_std(stats + ((size_t)n * C + c) * 2, npix, m, s);
+    out[(size_t)pix * ldo + c] = __fdiv_rn(__fsub_rn(__ldg(x + (size_t)pix * ldx + c), m), s);
+  }
+}
+
+// ---- backward of the warp: d/dx (scatter-add) and d/dflow -----------------
+// ATen grid_sampler_2d_backward semantics: the mask (a comparison) carries no
+// gradient; masked pixels propagate nothing.
+__global__ void __launch_bounds__(256)
+warp_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ flow, int ldf,
+                const float* __restrict__ go, int ldg, float* __restrict__ gx, int ldgx,
+                float* __restrict__ gflow, int ldgf, int N, int H, int W, int C, int align_corners, int use_mask) {
+  // one warp per pixel, lanes stride over channels
+  const long long npix = (long long)N * H * W;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long p = warp0; p < npix; p += nwarps) {
+    const int xpix = (int)(p % W);
+    const int y = (int)((p / W) % H);
+    const long long n = p / ((long long)W * H);
+    const float* fl = flow + (size_t)p * ldf;
+    const float ix = sample_coord((float)xpix, __ldg(fl), W, align_corners);
+    const float iy = sample_coord((float)y, __ldg(fl + 1), H, align_corners);
+    const BilinearTaps t = bilinear_taps(ix, iy, H, W);
+    const bool keep = !use_mask || t.wsum >= 1.0f;
+    float gix = 0.f, giy = 0.f;
+    if (keep) {
+      const long long base = ((long long)n * H + t.y0) * W + t.x0;   // corners are only touched when in_*
+      const float fx0 = floorf(ix), fy0 = floorf(iy);
+      const float ax1 = (fx0 + 1.f) - ix, ax0 = ix - fx0, ay1 = (fy0 + 1.f) - iy, ay0 = iy - fy0;
+      for (int c = lane; c < C; c += 32) {
+        const float g = __ldg(go + (size_t)p * ldg + c);
+        if (gx) {
+          if (t.in_nw) atomicAdd(gx + base * ldgx + c, g * t.w_nw);
+          if (t.in_ne) atomicAdd(gx + (base + 1) * ldgx + c, g * t.w_ne);
+          if (t.in_sw) atomicAdd(gx + (base + W) * ldgx + c, g * t.w_sw);
+          if (t.in_se) atomicAdd(gx + (base + W + 1) * ldgx + c, g * t.w_se);
+        }
+        if (gflow) {
+          const float v_nw = t.in_nw ? __ldg(x + base * ldx + c) : 0.f;
+          const float v_ne = t.in_ne ? __ldg(x + (base + 1) * ldx + c) : 0.f;
+          const float v_sw = t.in_sw ? __ldg(x + (base + W) * ldx + c) : 0.f;
+          const float v_se = t.in_se ? __ldg(x + (base + W + 1) * ldx + c) : 0.f;
+          gix += g * ((v_ne - v_nw) * ay1 + (v_se - v_sw) * ay0);
+          giy += g * ((v_sw - v_nw) * ax1 + (v_se - v_ne) * ax0);
+        }
+      }
+    }
+    if (gflow) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        gix += __shfl_xor_sync(0xffffffffu, gix, o);
+        giy += __shfl_xor_sync(0xffffffffu, giy, o);
+      }
+      if (lane == 0) {
+        // d ix / d u: pixel->[-1,1] is 2/(W-1), unnormalise is W/2 (or (W-1)/2)
+        const float sx = align_corners ? 1.0f : (float)W / (float)(W > 1 ? W - 1 : 1);
+        const float sy = align_corners ? 1.0f : (float)H / (float)(H > 1 ? H - 1 : 1);
+        gflow[(size_t)p * ldgf + 0] = gix * sx;
+        gflow[(size_t)p * ldgf + 1] = giy * sy;
+      }
+    }
+  }
+}
+
+static int pick_lpp(int C) {
+  int cg = (C + 3) / 4;
+  int lpp = 1;
+  while (lpp < cg && lpp < 32) lpp <<= 1;   // power of two <= 32 dividing WARP_NT
+  return lpp;
+}
+
+}  // namespace upf
+
+extern "C" int upf_warp_fwd(const float* x, int ldx, const float* flow, int ldf, float* out, int ldo,
+                            int N, int H, int W, int C, int align_corners, int use_mask, int x_batch_shift,
+                            double* stats, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(x && flow && out, "warp: null tensor");
+  UPF_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && ldx >= C && ldo >= C && ldf >= 2, "warp: bad shape");
+  UPF_REQUIRE(stats == nullptr || C <= 256, "warp: fused moments need C <= 256");
+  UPF_REQUIRE(x_batch_shift >= 0 && x_batch_shift < N, "warp: batch shift out of range");
+  const int lpp = pick_lpp(C);
+  const int ppc = WARP_NT / lpp;
+  int per_image = (H * W + ppc - 1) / ppc;
+  const int cap = (UPF_NUM_SMS * 8 + N - 1) / N;     // ~8 CTAs per SM over the whole batch
+  if (per_image > cap) per_image = cap;
+  if (per_image < 1) per_image = 1;
+  const bool vec = (C % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(x) && aligned16(out);
+  const size_t smem = stats ? (size_t)2 * ((C + 3) / 4) * 4 * sizeof(double) : 0;
+  if (vec)
+    warp_fwd_kernel<true><<<N * per_image, WARP_NT, smem, (cudaStream_t)stream>>>(x, ldx, flow, ldf, out, ldo, H, W, C,
+                                                                                 align_corners, use_mask, stats, lpp, per_image, x_batch_shift, N);
+  else
+    warp_fwd_kernel<false><<<N * per_image, WARP_NT, smem, (cudaStream_t)stream>>>(x, ldx, flow, ldf, out, ldo, H, W, C,
+                                                                                  align_corners, use_mask, stats, lpp, per_image, x_batch_shift, N);
+  return check_launch("warp_fwd");
+}
+
+extern "C" int upf_warp_bwd(const float* x, int ldx, const float* flow, int ldf, const float* grad_out, int ldg,
+                            float* grad_x, int ldgx, float* grad_flow, int ldgf,
+                            int N, int H, int W, int C, int align_corners, int use_mask, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(x && flow && grad_out, "warp_bwd: null tensor");
+  UPF_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "warp_bwd: bad shape");
+  const long long npix = (long long)N * H * W;
+  long long blocks = (npix * 32 + 255) / 256;
+  if (blocks > UPF_NUM_SMS * 16) blocks = UPF_NUM_SMS * 16;
+  warp_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, flow, ldf, grad_out, ldg, grad_x, ldgx,
+                                                                     grad_flow, ldgf, N, H, W, C, align_corners, use_mask);
+  return check_launch("warp_bwd");
+}
+
+extern "C" int upf_featnorm_stats(const float* x, int ldx, int N, int H, int W, int C, double* stats, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(x && stats, "featnorm_stats: null tensor");
+  UPF_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= 256 && ldx >= C, "featnorm_stats: bad shape (C<=256)");
+  const int lpp = pick_lpp(C);
+  const int ppc = WARP_NT / lpp;
+  int per_image = (H * W + ppc * 8 - 1) / (ppc * 8);
+  const int cap = (UPF_NUM_SMS * 8 + N - 1) / N;
+  if (per_image > cap) per_image = cap;
+  if (per_image < 1) per_image = 1;
+  const int vec = (C % 4 == 0) && (ldx % 4 == 0) && aligned16(x);
+  const size_t smem = (size_t)2 * ((C + 3) / 4) * 4 * sizeof(double);
+  featnorm_stats_kernel<<<N * per_image, WARP_NT, smem, (cudaStream_t)stream>>>(x, ldx, H, W, C, stats, lpp, per_image, vec);
+  return check_launch("featnorm_stats");
+}
+
+extern "C" int upf_featnorm_apply(const float* x, int ldx, const double* stats, float* out, int ldo,
+                                  int N, int H, int W, int C, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(x && stats && out, "featnorm_apply: null tensor");
+  UPF_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && ldx >= C && ldo >= C, "featnorm_apply: bad shape");
+  const long long total = (long long)N * H * W * C;
+  long long blocks = (total + 255) / 256;
+  if (blocks > UPF_NUM_SMS * 16) blocks = UPF_NUM_SMS * 16;
+  featnorm_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, stats, out, ldo, H, W, C, total);
+  return check_launch("featnorm_apply");
+}

@@ -1,0 +1,232 @@
+"""Drop-in for the reference's model/upflow.py: `network_tools.sgu_model`,
+`network_tools.normalize_features` and `UPFlow_net` (config / update / forward /
+forward_2_frame_v3 / decode_level_res / self_guided_upsample / load_model) with
+the reference's names, signatures, output dictionary and state-dict keys
+(SURVEY.md sections 3.5, 8b).
+
+Inference (`if_loss=False`, the path test.py drives, test.py:40-47) runs on
+`upflow_pytorch_b200.engine.DecoderEngine` -- both flow directions stacked,
+fused kernels, no torch.cat.  The per-level methods keep the reference's
+module-level semantics for callers that use them directly.  The loss branch
+(model/upflow.py:394-491) is outside the hot path (SURVEY.md section 2 rows
+12-14) and is not provided in this round.
+"""
+from __future__ import absolute_import, division, print_function
+
+import collections
+
+import torch
+import torch.nn as nn
+
+from model.correlation_package.correlation import Correlation
+from model.pwc_modules import (ContextNetwork_v2_, FeatureExtractor, FlowEstimatorDense_v2, WarpingLayer_no_div,
+                               _DenseBlock, conv, initialize_msra, upsample2d_flow_as, upsample_flow)
+from upflow_pytorch_b200 import ops
+from upflow_pytorch_b200.engine import DecoderEngine
+from utils.pytorch_correlation import Corr_pyTorch
+from utils.tools import tools
+
+
+class network_tools():
+    class sgu_model(tools.abstract_model):
+        """Self-guided upsample (model/upflow.py:20-92)."""
+
+        def __init__(self):
+            super(network_tools.sgu_model, self).__init__()
+
+            class FlowEstimatorDense_temp(_DenseBlock):
+                def __init__(self, ch_in, f_channels=(128, 128, 96, 64, 32), ch_out=2):
+                    super(FlowEstimatorDense_temp, self).__init__()
+                    self.num_feature_channel = self._build(ch_in, f_channels, ch_out)
+
+            self.warping_layer = WarpingLayer_no_div()
+            self.dense_estimator_mask = FlowEstimatorDense_temp(64, f_channels=(32, 32, 32, 16, 8), ch_out=3)
+            self.upsample_output_conv = nn.Sequential(conv(3, 16, kernel_size=3, stride=1, dilation=1),
+                                                      conv(16, 16, stride=2),
+                                                      conv(16, 32, kernel_size=3, stride=1, dilation=1),
+                                                      conv(32, 32, stride=2), )
+
+        def forward(self, flow_init, feature_1, feature_2, output_level_flow=None):
+            h, w = flow_init.shape[2:]
+            h_f, w_f = feature_1.shape[2:]
+            if h != h_f or w != w_f:
+                flow_init = upsample2d_flow_as(flow_init, feature_1, mode="bilinear", if_rate=True)
+            feature_2_warp = self.warping_layer(feature_2, flow_init)
+            _, x_out = self.dense_estimator_mask(torch.cat((feature_1, feature_2_warp), dim=1))
+            if output_level_flow is not None:
+                flow_init = output_level_flow
+            # sigmoid, the two upsamples, torch_warp and the blend are one kernel (upf_sgu_blend)
+            flow_up = ops.sgu_blend(flow_init, x_out)
+            inter_flow = x_out[:, :2, :, :]
+            inter_mask = torch.sigmoid(x_out[:, 2:3, :, :])
+            if output_level_flow is not None:
+                inter_flow = upsample2d_flow_as(inter_flow, output_level_flow, mode="bilinear", if_rate=True)
+                inter_mask = upsample2d_flow_as(inter_mask, output_level_flow, mode="bilinear")
+            return flow_init, flow_up, inter_flow, inter_mask
+
+        def output_conv(self, x):
+            return self.upsample_output_conv(x)
+
+    @classmethod
+    def normalize_features(cls, feature_list, normalize, center, moments_across_channels=True,
+                           moments_across_images=True):
+        """model/upflow.py:94-137.  The kernel implements the configuration the shipped model uses
+        (per image, per channel: test.py:24-26); other moment modes are rejected rather than approximated."""
+        if moments_across_channels or moments_across_images or not (normalize and center):
+            raise NotImplementedError("only normalize=center=True with per-image per-channel moments "
+                                      "(norm_moments_across_channels=False, norm_moments_across_images=False)")
+        return [ops.normalize_features(f) for f in feature_list]
+
+
+class UPFlow_net(tools.abstract_model):
+    class config(tools.abstract_config):
+        def __init__(self):
+            # identical attribute set and defaults to model/upflow.py:293-323
+            self.occ_type = 'for_back_check'
+            self.alpha_1 = 0.1
+            self.alpha_2 = 0.5
+            self.occ_check_obj_out_all = 'obj'
+            self.stop_occ_gradient = False
+            self.smooth_level = 'final'
+            self.smooth_type = 'edge'
+            self.smooth_order_1_weight = 1
+            self.smooth_order_2_weight = 0
+            self.photo_loss_type = 'abs_robust'
+            self.photo_loss_delta = 0.4
+            self.photo_loss_use_occ = False
+            self.photo_loss_census_weight = 0
+            self.if_norm_before_cost_volume = False
+            self.norm_moments_across_channels = True
+            self.norm_moments_across_images = True
+            self.multi_scale_distillation_weight = 0
+            self.multi_scale_distillation_style = 'upup'
+            self.multi_scale_distillation_occ = True
+            self.if_froze_pwc = False
+            self.input_or_sp_input = 1
+            self.if_use_boundary_warp = True
+            self.if_sgu_upsample = False
+            self.if_use_cor_pytorch = False
+
+        def __call__(self, ):
+            return UPFlow_net(self)
+
+    # extra, non-reference knobs of the B200 build (class attributes so `config` stays identical)
+    conv_precision = "tf32"      # 'tf32' = tcgen05 tensor cores (what cuDNN does by default), 'fp32' = strict SIMT
+
+    def __init__(self, conf: config):
+        super(UPFlow_net, self).__init__()
+        self.conf = conf
+        self.search_range = 4
+        self.num_chs = [3, 16, 32, 64, 96, 128, 196]
+        self.estimator_f_channels = (128, 128, 96, 64, 32)
+        self.context_f_channels = (128, 128, 128, 96, 64, 32, 2)
+        self.output_level = 4
+        self.num_levels = 7
+        self.leakyRELU = nn.LeakyReLU(0.1, inplace=True)
+        self.feature_pyramid_extractor = FeatureExtractor(self.num_chs)
+        self.warping_layer = WarpingLayer_no_div()
+        self.dim_corr = (self.search_range * 2 + 1) ** 2
+        self.num_ch_in = self.dim_corr + 32 + 2
+        self.flow_estimators = FlowEstimatorDense_v2(self.num_ch_in, f_channels=self.estimator_f_channels)
+        self.context_networks = ContextNetwork_v2_(self.flow_estimators.n_channels + 2,
+                                                   f_channels=self.context_f_channels)
+        self.conv_1x1 = nn.ModuleList([conv(196, 32, kernel_size=1, stride=1, dilation=1),
+                                       conv(128, 32, kernel_size=1, stride=1, dilation=1),
+                                       conv(96, 32, kernel_size=1, stride=1, dilation=1),
+                                       conv(64, 32, kernel_size=1, stride=1, dilation=1),
+                                       conv(32, 32, kernel_size=1, stride=1, dilation=1)])
+        self.occ_check_model_ls = []
+        self.correlation_pytorch = Corr_pyTorch(pad_size=self.search_range, kernel_size=1,
+                                                max_displacement=self.search_range, stride1=1, stride2=1)
+        self.sgi_model = network_tools.sgu_model() if self.conf.if_sgu_upsample else None
+        self.occ_check_model = tools.occ_check_model(occ_type=self.conf.occ_type, occ_alpha_1=self.conf.alpha_1,
+                                                     occ_alpha_2=self.conf.alpha_2,
+                                                     obj_out_all=self.conf.occ_check_obj_out_all)
+        initialize_msra(self.modules())
+        if self.conf.if_froze_pwc:
+            self.froze_PWC()
+        self._engine = None
+        self._engine_key = None
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _get_engine(self):
+        params = list(self.parameters())
+        key = (self.conv_precision, params[0].device, tuple(p._version for p in params),
+               tuple(p.data_ptr() for p in params))
+        if self._engine is None or self._engine_key != key:
+            if not (self.conf.if_norm_before_cost_volume and not self.conf.norm_moments_across_channels
+                    and not self.conf.norm_moments_across_images):
+                raise NotImplementedError(
+                    "the fused decoder implements the shipped configuration (test.py:22-30): "
+                    "if_norm_before_cost_volume=True, norm_moments_across_channels=False, "
+                    "norm_moments_across_images=False")
+            self._engine = DecoderEngine(self.state_dict(), device=params[0].device, precision=self.conv_precision,
+                                         use_sgu=bool(self.conf.if_sgu_upsample))
+            self._engine_key = key
+        return self._engine
+
+    def forward(self, input_dict: dict):
+        """model/upflow.py:370-392 (inference branch)."""
+        if input_dict['if_loss']:
+            raise NotImplementedError("the unsupervised-loss branch (model/upflow.py:394-491) is outside the decoder "
+                                      "hot path and not part of this build yet")
+        im1, im2 = input_dict['im1'], input_dict['im2']
+        output_dict = {}
+        flow_f, flow_b, flows = self.forward_2_frame_v3(im1, im2, if_loss=False)
+        occ_fw, occ_bw = self.occ_check_model(flow_f=flow_f, flow_b=flow_b)
+        output_dict['flow_f_out'] = flow_f
+        output_dict['flow_b_out'] = flow_b
+        output_dict['occ_fw'] = occ_fw
+        output_dict['occ_bw'] = occ_bw
+        return output_dict
+
+    def forward_2_frame_v3(self, x1_raw, x2_raw, if_loss=False):
+        """model/upflow.py:494-533 on the fused engine; outputs are fresh tensors."""
+        if not x1_raw.is_cuda:
+            raise RuntimeError("UPFlow_net (upflow_pytorch_b200) runs on CUDA only: move the model and the inputs "
+                               "with .cuda(); there is no CPU path")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("training through the fused decoder needs the backward kernels (not built yet); "
+                                      "call under torch.no_grad()")
+        f, b, flows = self._get_engine().forward(x1_raw.float(), x2_raw.float())
+        return f.clone(), b.clone(), [[a.clone(), c.clone()] for a, c in flows]
+
+    def decode_level_res(self, level, flow_1, flow_2, feature_1, feature_1_1x1, feature_2, feature_2_1x1, img_ori_1,
+                         img_ori_2):
+        """model/upflow.py:535-573, module by module (both directions)."""
+        flow_1_up = upsample2d_flow_as(flow_1, feature_1, mode="bilinear", if_rate=True)
+        flow_2_up = upsample2d_flow_as(flow_2, feature_2, mode="bilinear", if_rate=True)
+        if level == 0:
+            feature_2_warp, feature_1_warp = feature_2, feature_1
+        else:
+            if self.conf.if_sgu_upsample:
+                flow_1_up = self.self_guided_upsample(flow_1_up, feature_1_1x1, feature_2_1x1)
+                flow_2_up = self.self_guided_upsample(flow_2_up, feature_2_1x1, feature_1_1x1)
+            feature_2_warp = self.warping_layer(feature_2, flow_1_up)
+            feature_1_warp = self.warping_layer(feature_1, flow_2_up)
+        if self.conf.if_norm_before_cost_volume:
+            feature_1, feature_2_warp = network_tools.normalize_features(
+                (feature_1, feature_2_warp), normalize=True, center=True,
+                moments_across_channels=self.conf.norm_moments_across_channels,
+                moments_across_images=self.conf.norm_moments_across_images)
+            feature_2, feature_1_warp = network_tools.normalize_features(
+                (feature_2, feature_1_warp), normalize=True, center=True,
+                moments_across_channels=self.conf.norm_moments_across_channels,
+                moments_across_images=self.conf.norm_moments_across_images)
+        # both correlation back ends of the reference (:557-562) are the same fused kernel here, LeakyReLU included
+        out_corr_relu_1 = ops.correlation(feature_1, feature_2_warp, self.search_range, leaky_slope=0.1)
+        out_corr_relu_2 = ops.correlation(feature_2, feature_1_warp, self.search_range, leaky_slope=0.1)
+        feature_int_1, flow_res_1 = self.flow_estimators(torch.cat([out_corr_relu_1, feature_1_1x1, flow_1_up], dim=1))
+        feature_int_2, flow_res_2 = self.flow_estimators(torch.cat([out_corr_relu_2, feature_2_1x1, flow_2_up], dim=1))
+        flow_fine_1 = self.context_networks(torch.cat([feature_int_1, flow_1_up + flow_res_1], dim=1))
+        flow_fine_2 = self.context_networks(torch.cat([feature_int_2, flow_2_up + flow_res_2], dim=1))
+        return flow_1_up, flow_2_up, flow_res_1 + flow_fine_1, flow_res_2 + flow_fine_2
+
+    def froze_PWC(self):
+        for m in (self.feature_pyramid_extractor, self.flow_estimators, self.context_networks, self.conv_1x1):
+            for param in m.parameters():
+                param.requires_grad = False
+
+    def self_guided_upsample(self, flow_up_bilinear, feature_1, feature_2, output_level_flow=None):
+        _, out_flow, _, _ = self.sgi_model(flow_up_bilinear, feature_1, feature_2, output_level_flow=output_level_flow)
+        return out_flow

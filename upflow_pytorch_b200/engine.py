@@ -1,0 +1,277 @@
+"""The decoder engine: UPFlow's two-frame forward (forward_2_frame_v3,
+model/upflow.py:494-533, with decode_level_res :535-573 and sgu_model.forward
+:71-89) re-hosted on the library's kernels.
+
+What changes relative to the reference's orchestration (results do not):
+  * the forward and the backward flow directions share weights and have no data
+    dependence inside a level, so they are STACKED in one batch of N = 2B
+    images ([im1.., im2..]); "the other image" is a batch shift of B that the
+    warp / correlation kernels apply while addressing (no swapped copies);
+  * activations are pixel-major (NHWC).  Each dense block lives in ONE
+    append-only buffer per level (X: 576 channels for the flow estimator, S:
+    192 for the SGU block); convolutions read a channel prefix and write their
+    output slice in place, so none of the 302 torch.cat calls of a KITTI
+    forward exist.  The reference PREPENDS new features
+    (model/pwc_modules.py:280-284); the fixed permutation between the two
+    orders is folded into the packed weights once, at load time;
+  * LeakyReLU, bias, residual flow additions, feature normalisation, the
+    validity mask and the flow rescale are fused into the producing kernels;
+  * no host-side tensor construction, no host<->device copies and no
+    synchronisation inside the forward: it is capturable in a CUDA graph.
+
+X buffer channel map (estimator input order of the reference is
+[corr 81 | f_1x1 32 | flow 2], model/upflow.py:565):
+    0..80 corr | 81..112 f_1x1 | 113..114 flow_up | 115..116 flow_up+flow_res
+    | 117..127 zero | 128 conv1 | 256 conv2 | 384 conv3 | 480 conv4 | 544 conv5
+"""
+import torch
+
+from . import _ext, ops
+from .ops import Slice
+
+NUM_CHS = (196, 128, 96, 64, 32)          # decoder levels 0..4 (1/64 .. 1/4), model/upflow.py:336
+EST_CH = (128, 128, 96, 64, 32)           # model/upflow.py:338
+CTX_CH = (128, 128, 128, 96, 64, 32, 2)   # model/upflow.py:339
+CTX_DIL = (1, 2, 4, 8, 16, 1, 1)          # model/pwc_modules.py:401-409
+SGU_CH = (32, 32, 32, 16, 8)              # model/upflow.py:62
+X_LD = 576
+X_CORR, X_F1X1, X_FLOW, X_FLOW2 = 0, 81, 113, 115
+X_OFF = (128, 256, 384, 480, 544)         # conv1..conv5 output offsets
+S_LD = 192
+S_OFF = (64, 96, 128, 160, 176)
+SLOPE = 0.1
+
+
+def _dense_slots(x_width, x_slots, out_offsets, out_channels, k):
+    """Slots, in the append-only buffer, of the reference's input channels of
+    the k-th conv (k=0..5) of a dense block: reference order is
+    [conv_k-1 out, ..., conv_1 out, x]."""
+    slots = []
+    for j in range(k - 1, -1, -1):
+        slots += list(range(out_offsets[j], out_offsets[j] + out_channels[j]))
+    slots += list(x_slots)
+    return slots
+
+
+class ConvSpec:
+    __slots__ = ("w", "w_tc", "bias", "cin", "cout", "k", "stride", "dil", "slope")
+
+    def __init__(self, weight, bias, stride=1, dil=1, relu=True, in_slots=None, cin_total=None, tc=True):
+        self.cout, _, self.k, _ = weight.shape
+        self.cin = cin_total or weight.shape[1]
+        self.stride, self.dil = stride, dil
+        self.slope = SLOPE if relu else 1.0
+        self.w, self.w_tc = ops.pack_conv_weight(weight, in_slots, cin_total, tc=tc and stride == 1)
+        self.bias = bias.detach().float().contiguous()
+
+
+class DecoderEngine:
+    def __init__(self, state_dict, device="cuda", precision="tf32", align_corners=False, use_sgu=True):
+        """state_dict: the reference's parameter names."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("DecoderEngine needs a CUDA device: the decoder path has no CPU implementation")
+        _ext.load()
+        self.device = torch.device(device)
+        self.precision = precision
+        self.tc = precision == "tf32"
+        self.align_corners = bool(align_corners)
+        self.use_sgu = use_sgu
+        self._ws = {}
+        self.load_weights(state_dict)
+
+    # ------------------------------------------------------------ weights
+    def load_weights(self, sd):
+        g = lambda k: sd[k].detach().to(self.device, torch.float32)
+        tc = self.tc
+
+        def spec(key, **kw):
+            return ConvSpec(g(key + ".0.weight"), g(key + ".0.bias"), tc=tc, **kw)
+
+        self.enc = []
+        for l in range(6):
+            self.enc.append((spec(f"feature_pyramid_extractor.convs.{l}.0", stride=2),
+                             spec(f"feature_pyramid_extractor.convs.{l}.1")))
+        self.conv1x1 = [spec(f"conv_1x1.{l}") for l in range(5)]
+        # flow estimator: input x = X[0:115]
+        x_slots = list(range(115))
+        self.est = []
+        names = ("conv1", "conv2", "conv3", "conv4", "conv5", "conv_last")
+        widths = (128,) + tuple(o + c for o, c in zip(X_OFF, EST_CH))      # prefix each conv reads
+        for k, name in enumerate(names):
+            self.est.append(spec(f"flow_estimators.{name}", relu=(k < 5),
+                                 in_slots=_dense_slots(115, x_slots, X_OFF, EST_CH, k), cin_total=widths[k]))
+        # context network: input = [x5 (563) | flow_up+flow_res (2)]
+        ctx0_slots = _dense_slots(115, x_slots, X_OFF, EST_CH, 5) + [X_FLOW2, X_FLOW2 + 1]
+        self.ctx = []
+        for i in range(7):
+            kw = dict(dil=CTX_DIL[i], relu=(i < 6))
+            if i == 0:
+                kw.update(in_slots=ctx0_slots, cin_total=X_LD)
+            self.ctx.append(spec(f"context_networks.convs.{i}", **kw))
+        self.sgu = None
+        if self.use_sgu:
+            s_slots = list(range(64))
+            swidths = (64,) + tuple(o + c for o, c in zip(S_OFF, SGU_CH))
+            self.sgu = [spec(f"sgi_model.dense_estimator_mask.{name}", relu=(k < 5),
+                             in_slots=_dense_slots(64, s_slots, S_OFF, SGU_CH, k), cin_total=swidths[k])
+                        for k, name in enumerate(names)]
+            self.outconv = [spec(f"sgi_model.upsample_output_conv.{i}", stride=s) for i, s in enumerate((1, 2, 1, 2))]
+
+    # ------------------------------------------------------------ helpers
+    def _conv(self, cs, x, out, residual=None):
+        use_tc = self.tc and cs.w_tc is not None and cs.stride == 1
+        ops.k_conv(x, cs.w_tc if use_tc else cs.w, cs.bias, out, cs.k, cs.stride, cs.dil, cs.slope, residual,
+                   _ext.CONV_TF32 if use_tc else _ext.CONV_FP32)
+
+    def _workspace(self, B, H, W):
+        key = (B, H, W)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        dev = self.device
+        N = 2 * B
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        sizes = [(H, W)]
+        for _ in range(6):
+            h, w = sizes[-1]
+            sizes.append(((h + 1) // 2, (w + 1) // 2))       # stride-2 pad-1 3x3 conv
+        ws = {"sizes": sizes, "N": N}
+        # encoder features: full-res input [N,H,W,4(3 used)], level tensors (two convs each)
+        ws["im"] = z(N, H, W, 4)
+        chs = (16, 32, 64, 96, 128, 196)
+        ws["enc_a"] = [z(N, *sizes[l + 1], chs[l]) for l in range(6)]
+        ws["enc_b"] = [z(N, *sizes[l + 1], chs[l]) for l in range(6)]
+        lv = []
+        for l in range(5):
+            h, w = sizes[6 - l]
+            d = {"hw": (h, w), "X": z(N, h, w, X_LD), "T0": z(N, h, w, 128), "T1": z(N, h, w, 128),
+                 "flow": z(N, h, w, 2), "xw": z(N, h, w, NUM_CHS[l]),
+                 "stats_own": torch.zeros(N, NUM_CHS[l], 2, dtype=torch.float64, device=dev),
+                 "stats_w": torch.zeros(N, NUM_CHS[l], 2, dtype=torch.float64, device=dev)}
+            if self.use_sgu and l > 0:
+                d["S"] = z(N, h, w, S_LD)
+                d["inter"] = z(N, h, w, 4)
+                d["flow_bil"] = z(N, h, w, 2)
+            lv.append(d)
+        ws["levels"] = lv
+        if self.use_sgu:
+            h4, w4 = sizes[2]
+            ws["oc_a"] = z(N, H, W, 16)
+            ws["oc_b"] = z(N, *sizes[1], 16)
+            ws["oc_c"] = z(N, *sizes[1], 32)
+            ws["S_out"] = z(N, h4, w4, S_LD)
+            ws["inter_out"] = z(N, h4, w4, 4)
+            ws["flow_full_bil"] = z(N, H, W, 2)
+        ws["flow_out"] = z(N, H, W, 2)
+        self._ws[key] = ws
+        return ws
+
+    def _sgu_dense(self, S, inter):
+        """FlowEstimatorDense_temp (model/upflow.py:24-60) on the S buffer."""
+        for k in range(5):
+            self._conv(self.sgu[k], Slice(S, 0, self.sgu[k].cin), Slice(S, S_OFF[k], SGU_CH[k]))
+        self._conv(self.sgu[5], Slice(S, 0, self.sgu[5].cin), Slice(inter, 0, 3))
+
+    # ------------------------------------------------------------ forward
+    def encode(self, ws, im1, im2):
+        """FeatureExtractor (model/pwc_modules.py:122-142) on [im1; im2]."""
+        B = im1.shape[0]
+        im = ws["im"]
+        for i, x in enumerate((im1, im2)):
+            v = x.permute(0, 2, 3, 1)
+            if x.is_contiguous():
+                _ext.check(_ext.load().upf_nchw_to_nhwc(ops._p(x), ops._p(im, i * B * im.shape[1] * im.shape[2] * 4), 4,
+                                                        B, 3, x.shape[2], x.shape[3], ops._stream()), "nchw_to_nhwc")
+            else:
+                ops.k_copy(Slice(v.contiguous()), Slice(im[i * B:(i + 1) * B], 0, 3))
+        x = Slice(im, 0, 3)
+        for l in range(6):
+            self._conv(self.enc[l][0], x, Slice(ws["enc_a"][l]))
+            self._conv(self.enc[l][1], Slice(ws["enc_a"][l]), Slice(ws["enc_b"][l]))
+            x = Slice(ws["enc_b"][l])
+        return ws["enc_b"]
+
+    def forward(self, im1, im2, taps=None):
+        """Returns (flow_f_out, flow_b_out, flows) like forward_2_frame_v3:
+        NCHW-shaped [B,2,H,W] views; flows = per-level [fw, bw], finest first."""
+        ops._require_cuda(im1, im2)
+        B, _, H, W = im1.shape
+        ws = self._workspace(B, H, W)
+        N = 2 * B
+        ac = self.align_corners
+        feats = self.encode(ws, im1, im2)              # index l -> 1/2^(l+1); decoder level L uses feats[5-L]
+        prev_flow = None
+        flows = []
+        for L in range(5):
+            d = ws["levels"][L]
+            h, w = d["hw"]
+            F = Slice(feats[5 - L])
+            C = NUM_CHS[L]
+            X = d["X"]
+            flow_up = Slice(X, X_FLOW, 2)
+            # 1x1 adapter (model/upflow.py:508-513) straight into its estimator slot
+            self._conv(self.conv1x1[L], F, Slice(X, X_F1X1, 32))
+            if L == 0:
+                X[..., X_FLOW:X_FLOW + 2].zero_()      # upsampling a zero flow (model/upflow.py:504-505, :536)
+            else:
+                ph, pw = ws["levels"][L - 1]["hw"]
+                if self.use_sgu:
+                    bil = Slice(d["flow_bil"])
+                    ops.k_resize(prev_flow, bil, (w / pw, h / ph))
+                    S = d["S"]
+                    ops.k_copy(Slice(X, X_F1X1, 32), Slice(S, 0, 32))
+                    ops.k_warp(Slice(X, X_F1X1, 32), bil, Slice(S, 32, 32), ac, True, x_shift=B)
+                    self._sgu_dense(S, d["inter"])
+                    ops.k_sgu_blend(bil, Slice(d["inter"], 0, 3), flow_up, ac)
+                else:
+                    ops.k_resize(prev_flow, flow_up, (w / pw, h / ph))
+            # feature statistics (model/upflow.py:549-555), warp + its statistics (:546-547)
+            d["stats_own"].zero_()
+            ops.k_stats(F, d["stats_own"])
+            if L == 0:
+                ops.k_corr(F, F, Slice(X, X_CORR, 81), 4, d["stats_own"], d["stats_own"], f2_shift=B, slope=SLOPE)
+            else:
+                d["stats_w"].zero_()
+                ops.k_warp(F, flow_up, Slice(d["xw"]), ac, True, x_shift=B, stats=d["stats_w"])
+                ops.k_corr(F, Slice(d["xw"]), Slice(X, X_CORR, 81), 4, d["stats_own"], d["stats_w"], slope=SLOPE)
+            # dense flow estimator (model/pwc_modules.py:279-286)
+            for k in range(5):
+                self._conv(self.est[k], Slice(X, 0, self.est[k].cin), Slice(X, X_OFF[k], EST_CH[k]))
+            # flow_up + flow_res -> context input slot (model/upflow.py:567)
+            self._conv(self.est[5], Slice(X, 0, X_LD), Slice(X, X_FLOW2, 2), residual=flow_up)
+            # context network (model/pwc_modules.py:401-412); last conv adds (flow_up + flow_res): :569-572, :519
+            t_in = Slice(X, 0, X_LD)
+            bufs = (d["T0"], d["T1"])
+            for i in range(6):
+                t_out = Slice(bufs[i % 2], 0, CTX_CH[i])
+                self._conv(self.ctx[i], t_in, t_out)
+                t_in = t_out
+            self._conv(self.ctx[6], t_in, Slice(d["flow"]), residual=Slice(X, X_FLOW2, 2))
+            prev_flow = Slice(d["flow"])
+            flows.append(d["flow"])
+            if taps is not None:
+                taps.append({"level": L, "flow_up": X[..., X_FLOW:X_FLOW + 2].permute(0, 3, 1, 2).clone(),
+                             "corr": X[..., :81].permute(0, 3, 1, 2).clone(),
+                             "xw": d["xw"].permute(0, 3, 1, 2).clone() if L > 0 else None,
+                             "flow": d["flow"].permute(0, 3, 1, 2).clone()})
+        # ---- 1/4 -> full resolution (model/upflow.py:522-530)
+        h4, w4 = ws["levels"][4]["hw"]
+        out = Slice(ws["flow_out"])
+        if self.use_sgu:
+            bil = Slice(ws["flow_full_bil"])
+            ops.k_resize(prev_flow, bil, (W / w4, H / h4))
+            # sgi_model.output_conv on both images (model/upflow.py:66-69, :527-528)
+            self._conv(self.outconv[0], Slice(ws["im"], 0, 3), Slice(ws["oc_a"]))
+            self._conv(self.outconv[1], Slice(ws["oc_a"]), Slice(ws["oc_b"]))
+            self._conv(self.outconv[2], Slice(ws["oc_b"]), Slice(ws["oc_c"]))
+            S = ws["S_out"]
+            self._conv(self.outconv[3], Slice(ws["oc_c"]), Slice(S, 0, 32))
+            # the flow handed to sgu_model here is the 1/4-res flow itself (already at feature size, :73-75)
+            ops.k_warp(Slice(S, 0, 32), prev_flow, Slice(S, 32, 32), ac, True, x_shift=B)
+            self._sgu_dense(S, ws["inter_out"])
+            ops.k_sgu_blend(bil, Slice(ws["inter_out"], 0, 3), out, ac)
+        else:
+            ops.k_resize(prev_flow, out, (W / w4, H / h4))
+        fo = ws["flow_out"].permute(0, 3, 1, 2)
+        lvl = [[f[:B].permute(0, 3, 1, 2), f[B:].permute(0, 3, 1, 2)] for f in flows]
+        return fo[:B], fo[B:], lvl[::-1]

@@ -1,0 +1,342 @@
+"""Tensor-level wrappers over the C ABI (include/upflow_b200.h).
+
+Two layers:
+  * ``k_*`` functions: thin launchers on PIXEL-MAJOR buffers (torch tensors of
+    shape [N,H,W,ld], contiguous; a channel slice is (buffer, channel offset,
+    channel count)).  The decoder engine (engine.py) uses only these.
+  * NCHW-in / NCHW-out functions with the reference's operator semantics
+    (``correlation``, ``warp``, ``normalize_features``, ``upsample2d_flow_as``,
+    ``conv2d`` ...) used by the drop-in modules.  Inputs in torch
+    ``channels_last`` memory format are used in place; NCHW-contiguous inputs
+    are transposed by the library's own copy kernel.  Outputs are NCHW-shaped
+    views of pixel-major storage (== channels_last tensors).
+
+PyTorch is plumbing here: allocation, streams, autograd bookkeeping.  All
+arithmetic runs in libupflow_b200.so; there is no fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _ext
+
+LRELU_SLOPE = 0.1
+
+
+def _lib():
+    return _ext.load()
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, offset_elems=0):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr() + 4 * offset_elems)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("upflow_pytorch_b200 ops need CUDA tensors (no CPU path exists); got %s" % t.device)
+        if t.dtype != torch.float32:
+            raise RuntimeError("upflow_pytorch_b200 ops are fp32; got %s" % t.dtype)
+
+
+class Slice:
+    """Channels [c0, c0+C) of a pixel-major buffer [N,H,W,ld]."""
+    __slots__ = ("buf", "c0", "C")
+
+    def __init__(self, buf, c0=0, C=None):
+        assert buf.dim() == 4 and buf.is_contiguous(), "pixel-major buffers are contiguous [N,H,W,ld]"
+        self.buf = buf
+        self.c0 = c0
+        self.C = buf.shape[3] - c0 if C is None else C
+        assert 0 <= c0 and c0 + self.C <= buf.shape[3]
+
+    @property
+    def ld(self):
+        return self.buf.shape[3]
+
+    @property
+    def N(self):
+        return self.buf.shape[0]
+
+    @property
+    def H(self):
+        return self.buf.shape[1]
+
+    @property
+    def W(self):
+        return self.buf.shape[2]
+
+    def ptr(self):
+        return _p(self.buf, self.c0)
+
+    def nchw(self):
+        """NCHW-shaped view (channels_last strides) of this slice."""
+        return self.buf[..., self.c0:self.c0 + self.C].permute(0, 3, 1, 2)
+
+
+def _as_slice(x):
+    return x if isinstance(x, Slice) else Slice(x)
+
+
+# ---------------------------------------------------------------- launchers
+def k_corr(f1, f2, out, max_disp=4, stats1=None, stats2=None, f2_shift=0, slope=LRELU_SLOPE):
+    f1, f2, out = _as_slice(f1), _as_slice(f2), _as_slice(out)
+    assert f1.C == f2.C and out.C == (2 * max_disp + 1) ** 2
+    _ext.check(_lib().upf_corr_lrelu_fwd(f1.ptr(), f1.ld, f2.ptr(), f2.ld, out.ptr(), out.ld, f1.N, f1.H, f1.W, f1.C,
+                                         max_disp, _p(stats1), _p(stats2), f2_shift, slope, _stream()), "corr_lrelu_fwd")
+
+
+def k_corr_bwd(f1, f2, out, grad_out, grad_f1, grad_f2, max_disp=4, slope=1.0):
+    f1, f2, grad_out = _as_slice(f1), _as_slice(f2), _as_slice(grad_out)
+    out = _as_slice(out) if out is not None else None
+    g1, g2 = _as_slice(grad_f1), _as_slice(grad_f2)
+    _ext.check(_lib().upf_corr_lrelu_bwd(f1.ptr(), f1.ld, f2.ptr(), f2.ld, out.ptr() if out else None,
+                                         out.ld if out else 0, grad_out.ptr(), grad_out.ld, g1.ptr(), g1.ld, g2.ptr(),
+                                         g2.ld, f1.N, f1.H, f1.W, f1.C, max_disp, slope, _stream()), "corr_lrelu_bwd")
+
+
+def k_warp(x, flow, out, align_corners=False, use_mask=True, x_shift=0, stats=None):
+    x, flow, out = _as_slice(x), _as_slice(flow), _as_slice(out)
+    assert flow.C >= 2 and out.C == x.C
+    _ext.check(_lib().upf_warp_fwd(x.ptr(), x.ld, flow.ptr(), flow.ld, out.ptr(), out.ld, out.N, out.H, out.W, x.C,
+                                   int(align_corners), int(use_mask), x_shift, _p(stats), _stream()), "warp_fwd")
+
+
+def k_warp_bwd(x, flow, grad_out, grad_x, grad_flow, align_corners=False, use_mask=True):
+    x, flow, grad_out = _as_slice(x), _as_slice(flow), _as_slice(grad_out)
+    gx = _as_slice(grad_x) if grad_x is not None else None
+    gf = _as_slice(grad_flow) if grad_flow is not None else None
+    _ext.check(_lib().upf_warp_bwd(x.ptr(), x.ld, flow.ptr(), flow.ld, grad_out.ptr(), grad_out.ld,
+                                   gx.ptr() if gx else None, gx.ld if gx else 0, gf.ptr() if gf else None,
+                                   gf.ld if gf else 0, x.N, x.H, x.W, x.C, int(align_corners), int(use_mask), _stream()),
+               "warp_bwd")
+
+
+def k_stats(x, stats):
+    x = _as_slice(x)
+    assert stats.dtype == torch.float64 and stats.numel() >= x.N * x.C * 2
+    _ext.check(_lib().upf_featnorm_stats(x.ptr(), x.ld, x.N, x.H, x.W, x.C, ctypes.c_void_p(stats.data_ptr()), _stream()),
+               "featnorm_stats")
+
+
+def k_norm_apply(x, stats, out):
+    x, out = _as_slice(x), _as_slice(out)
+    _ext.check(_lib().upf_featnorm_apply(x.ptr(), x.ld, ctypes.c_void_p(stats.data_ptr()), out.ptr(), out.ld, x.N, x.H,
+                                         x.W, x.C, _stream()), "featnorm_apply")
+
+
+def k_resize(src, out, scale=None):
+    src, out = _as_slice(src), _as_slice(out)
+    assert src.C == out.C <= 4
+    sc = None
+    if scale is not None:
+        sc = (ctypes.c_float * 4)(*([float(s) for s in scale] + [1.0] * (4 - len(scale))))
+    _ext.check(_lib().upf_resize_bilinear(src.ptr(), src.ld, src.H, src.W, out.ptr(), out.ld, out.H, out.W, src.N, src.C,
+                                          sc, _stream()), "resize_bilinear")
+
+
+def k_sgu_blend(flow_init, inter, out, align_corners=False):
+    flow_init, inter, out = _as_slice(flow_init), _as_slice(inter), _as_slice(out)
+    _ext.check(_lib().upf_sgu_blend(flow_init.ptr(), flow_init.ld, inter.ptr(), inter.ld, inter.H, inter.W, out.ptr(),
+                                    out.ld, out.N, out.H, out.W, int(align_corners), _stream()), "sgu_blend")
+
+
+def k_conv(x, weight, bias, out, ksize, stride=1, dilation=1, slope=LRELU_SLOPE, residual=None, precision=_ext.CONV_FP32):
+    """weight: the layout matching ``precision`` (see pack_conv_weight)."""
+    x, out = _as_slice(x), _as_slice(out)
+    res = _as_slice(residual) if residual is not None else None
+    _ext.check(_lib().upf_conv2d_fwd(x.ptr(), x.ld, _p(weight), _p(bias), out.ptr(), out.ld, res.ptr() if res else None,
+                                     res.ld if res else 0, x.N, x.H, x.W, x.C, out.C, ksize, stride, dilation,
+                                     float(slope), int(precision), _stream()), "conv2d_fwd")
+
+
+def k_copy(src, dst):
+    src, dst = _as_slice(src), _as_slice(dst)
+    assert src.C == dst.C
+    _ext.check(_lib().upf_copy_channels(src.ptr(), src.ld, dst.ptr(), dst.ld, src.N * src.H * src.W, src.C, _stream()),
+               "copy_channels")
+
+
+# ---------------------------------------------------------------- weights
+def pack_conv_weight(weight, in_slots=None, cin_total=None, tc=False):
+    """nn.Conv2d weight [Cout,Cin,k,k] -> library layouts.
+
+    in_slots[i] = position, inside the input slice the kernel reads, of the
+    reference's input channel i (identity when None); cin_total = width of that
+    slice (unused slots get zero weights -- this is how the dense blocks'
+    prepend-concatenation order (model/pwc_modules.py:280-284) is mapped onto
+    append-only buffers).  Returns (w_simt [taps,cin_total,cout_pad4], w_tc or None)."""
+    Cout, Cin, k, _ = weight.shape
+    cin_total = cin_total or Cin
+    cout_pad = (Cout + 3) // 4 * 4
+    w = torch.zeros(k * k, cin_total, cout_pad, dtype=torch.float32, device=weight.device)
+    src = weight.detach().float().permute(2, 3, 1, 0).reshape(k * k, Cin, Cout)
+    if in_slots is None:
+        w[:, :Cin, :Cout] = src
+    else:
+        idx = torch.as_tensor(in_slots, dtype=torch.long, device=weight.device)
+        w[:, idx, :Cout] = src
+    w = w.contiguous()
+    w_tc = None
+    if tc:
+        n = _lib().upf_conv_tc_packed_elems(cin_total, Cout, k)
+        w_tc = torch.empty(n, dtype=torch.float32, device=weight.device)
+        _ext.check(_lib().upf_conv_tc_pack_weights(_p(w), _p(w_tc), cin_total, Cout, k, _stream()), "conv_tc_pack_weights")
+    return w, w_tc
+
+
+# ---------------------------------------------------------------- NCHW <-> pixel-major
+def to_pixel_major(x, ld=None):
+    """[N,C,H,W] tensor -> pixel-major buffer [N,H,W,ld>=C].  channels_last
+    inputs with ld==C are returned as a view."""
+    _require_cuda(x)
+    N, C, H, W = x.shape
+    v = x.permute(0, 2, 3, 1)
+    if (ld is None or ld == C) and v.is_contiguous():
+        return v
+    ld = ld or C
+    out = torch.empty(N, H, W, ld, dtype=torch.float32, device=x.device) if ld == C else \
+        torch.zeros(N, H, W, ld, dtype=torch.float32, device=x.device)
+    if x.is_contiguous():
+        _ext.check(_lib().upf_nchw_to_nhwc(_p(x), _p(out), ld, N, C, H, W, _stream()), "nchw_to_nhwc")
+    else:
+        if not v.is_contiguous():
+            xc = x.contiguous()
+            _ext.check(_lib().upf_nchw_to_nhwc(_p(xc), _p(out), ld, N, C, H, W, _stream()), "nchw_to_nhwc")
+        else:
+            k_copy(Slice(v), Slice(out, 0, C))
+    return out
+
+
+def to_nchw_contiguous(buf, C=None):
+    s = _as_slice(buf) if C is None else Slice(buf, 0, C)
+    out = torch.empty(s.N, s.C, s.H, s.W, dtype=torch.float32, device=s.buf.device)
+    _ext.check(_lib().upf_nhwc_to_nchw(s.ptr(), s.ld, _p(out), s.N, s.C, s.H, s.W, _stream()), "nhwc_to_nchw")
+    return out
+
+
+def _new(N, H, W, C, like):
+    return torch.empty(N, H, W, C, dtype=torch.float32, device=like.device)
+
+
+# ---------------------------------------------------------------- reference-semantics operators (NCHW in/out)
+class _CorrelationFn(torch.autograd.Function):
+    """Correlation(pad=d, k=1, maxd=d, s1=s2=1) -- model/correlation_package/correlation.py:6-44."""
+
+    @staticmethod
+    def forward(ctx, in1, in2, max_disp, slope):
+        a, b = to_pixel_major(in1), to_pixel_major(in2)
+        N, H, W, C = a.shape
+        out = _new(N, H, W, (2 * max_disp + 1) ** 2, in1)
+        k_corr(a, b, out, max_disp, slope=slope)
+        ctx.save_for_backward(a, b, out)
+        ctx.max_disp, ctx.slope = max_disp, slope
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad):
+        a, b, out = ctx.saved_tensors
+        g = to_pixel_major(grad)
+        g1, g2 = torch.empty_like(a), torch.empty_like(b)
+        k_corr_bwd(a, b, out if ctx.slope != 1.0 else None, g, g1, g2, ctx.max_disp, ctx.slope)
+        return g1.permute(0, 3, 1, 2), g2.permute(0, 3, 1, 2), None, None
+
+
+def correlation(in1, in2, max_disp=4, leaky_slope=None):
+    """Cost volume [B,(2d+1)^2,H,W]; ``leaky_slope`` fuses the LeakyReLU of model/upflow.py:563-564."""
+    _require_cuda(in1, in2)
+    if in1.shape != in2.shape:
+        raise RuntimeError("correlation: shape mismatch %s vs %s" % (tuple(in1.shape), tuple(in2.shape)))
+    return _CorrelationFn.apply(in1, in2, max_disp, 1.0 if leaky_slope is None else float(leaky_slope))
+
+
+class _WarpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, flow, align_corners, use_mask):
+        a, f = to_pixel_major(x), to_pixel_major(flow)
+        out = torch.empty_like(a)
+        k_warp(a, f, out, align_corners, use_mask)
+        ctx.save_for_backward(a, f)
+        ctx.cfg = (align_corners, use_mask)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad):
+        a, f = ctx.saved_tensors
+        g = to_pixel_major(grad)
+        gx = torch.zeros_like(a) if ctx.needs_input_grad[0] else None
+        gf = torch.empty_like(f) if ctx.needs_input_grad[1] else None
+        k_warp_bwd(a, f, g, gx, gf, *ctx.cfg)
+        return (gx.permute(0, 3, 1, 2) if gx is not None else None,
+                gf.permute(0, 3, 1, 2) if gf is not None else None, None, None)
+
+
+def warp(x, flow, align_corners=False, use_mask=True):
+    """WarpingLayer_no_div (model/pwc_modules.py:184-207); use_mask=False = tools.torch_warp (utils/tools.py:1274-1304)."""
+    _require_cuda(x, flow)
+    if flow.shape[1] != 2 or flow.shape[0] != x.shape[0] or flow.shape[2:] != x.shape[2:]:
+        raise RuntimeError("warp: flow must be [B,2,H,W] matching x")
+    return _WarpFn.apply(x, flow, bool(align_corners), bool(use_mask))
+
+
+def normalize_features(x):
+    """Per-image per-channel (x-mean)/sqrt(var+1e-16), unbiased var (model/upflow.py:108-135)."""
+    _require_cuda(x)
+    a = to_pixel_major(x)
+    N, H, W, C = a.shape
+    stats = torch.zeros(N, C, 2, dtype=torch.float64, device=x.device)
+    k_stats(a, stats)
+    out = torch.empty_like(a)
+    k_norm_apply(a, stats, out)
+    return out.permute(0, 3, 1, 2)
+
+
+def resize_bilinear(x, h, w, flow_rate=False):
+    """F.interpolate(bilinear, align_corners=True) [+ u*=w/w_, v*=h/h_]  (model/pwc_modules.py:72-90)."""
+    _require_cuda(x)
+    a = to_pixel_major(x)
+    N, hi, wi, C = a.shape
+    if C > 4:
+        raise RuntimeError("resize_bilinear: at most 4 channels (flows and masks)")
+    out = _new(N, h, w, C, x)
+    scale = None
+    if flow_rate:
+        if C != 2:
+            raise RuntimeError("if_rate=True needs a 2-channel flow")
+        scale = (w / wi, h / hi)
+    k_resize(a, out, scale)
+    return out.permute(0, 3, 1, 2)
+
+
+def sgu_blend(flow_init, inter, align_corners=False):
+    """flow_up of sgu_model.forward (model/upflow.py:79-88) from flow_init [B,2,H,W] at output resolution and the dense
+    block's raw 3-channel output ``inter`` (inter_flow u,v + mask logit), at the same or a lower resolution."""
+    _require_cuda(flow_init, inter)
+    f, i = to_pixel_major(flow_init), to_pixel_major(inter)
+    out = torch.empty_like(f)
+    k_sgu_blend(f, i, out, align_corners)
+    return out.permute(0, 3, 1, 2)
+
+
+def conv2d(x, w_packed, bias, cout, ksize, stride=1, dilation=1, slope=LRELU_SLOPE, precision=_ext.CONV_FP32):
+    """conv() of model/pwc_modules.py:10-31 on an NCHW tensor with pre-packed weights (pack_conv_weight)."""
+    _require_cuda(x)
+    C = x.shape[1]
+    if precision == _ext.CONV_TF32 and C % 4:
+        a = Slice(to_pixel_major(x, ld=(C + 3) // 4 * 4), 0, C)     # TMA needs a 16-byte pixel pitch
+    else:
+        a = Slice(to_pixel_major(x))
+    pad = ((ksize - 1) * dilation) // 2
+    Ho = (a.H + 2 * pad - dilation * (ksize - 1) - 1) // stride + 1
+    Wo = (a.W + 2 * pad - dilation * (ksize - 1) - 1) // stride + 1
+    out = _new(a.N, Ho, Wo, cout, x)
+    k_conv(a, w_packed, bias, out, ksize, stride, dilation, slope, None, precision)
+    return out.permute(0, 3, 1, 2)
