@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Throughput of the UPFlow decoder hot path on B200 (BASELINE.json metric:
+image-pairs/s at KITTI 1242x375, 6-level pyramid + SGU, batch 1 per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one two-frame forward (forward + backward flow, full pyramid, SGU)
+of one image pair per GPU.  Prints ONE JSON line (rank 0).
+
+  value      : pairs/s, inputs resident in HBM, CUDA-graph replay, device timed
+  e2e        : the same through the public drop-in API `UPFlow_net(input_dict)`
+               with PINNED HOST inputs: H2D of both frames and D2H of the flow
+               inside the timed region, every step
+  roofline   : the kernel with the largest share of the step, per-launch CUDA
+               events (profiler.py); roofline_corr: the fused correlation kernel
+               at the HD 1/4-resolution shape [2,32,270,480], d=4 (north star)
+  cpu_baseline / --impl reference : the reference's CPU path (op-for-op port,
+               oracle/ref_port.py -- the Python reference cannot travel to the
+               GPU box) on the host cores, same workload, same weights
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {  # name -> (H, W, batch per GPU)
+    "kitti_375x1242_b1": (375, 1242, 1),
+    "sintel_436x1024_b8": (436, 1024, 8),
+    "hd_1080x1920_b2": (1080, 1920, 2),
+    "small_256x256_b1": (256, 256, 1),
+}
+METRIC = "image_pairs_per_sec"
+UNIT = "pairs/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="MEASURED_PEAKS.json (measured)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="B200_PROFILING.md fallback")
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons of one GPU while the timed region runs (pynvml, 20 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.ok:
+            self.join(timeout=1)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def make_weights(seed=1234):
+    """Random-init weights of the reference architecture (its own MSRA init, model/pwc_modules.py:52-69), with small
+    random biases; no checkpoint exists on the GPU box."""
+    import upflow_pytorch_b200 as pkg
+    torch.manual_seed(seed)
+    net = pkg.build_model(device="cpu")
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(seed)
+    for k in sd:
+        if k.endswith("bias"):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.02
+        if "conv_last" in k or "context_networks.convs.6" in k:
+            sd[k] = sd[k] * 0.1       # keep an untrained net's flows at a few pixels
+    return sd
+
+
+def synth_inputs(B, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(B, 3, H, W, generator=g) - 0.5, torch.rand(B, 3, H, W, generator=g) - 0.5
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import ref_port as P
+    H, W, B = WORKLOADS[args.workload]
+    sd = make_weights()
+    im1, im2 = synth_inputs(B, H, W, 1234)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    with torch.no_grad():
+        for _ in range(max(1, args.warmup)):
+            P.forward_2_frame(im1, im2, sd)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            P.forward_2_frame(im1, im2, sd)
+        dt = time.perf_counter() - t0
+    v = B * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": max(1, args.warmup), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "pairs_per_step": B, "weights": "random-init (MSRA), seed 1234",
+                       "path": "oracle/ref_port.py: op-for-op CPU port of model/upflow.py forward_2_frame_v3 "
+                               "(F.conv2d / F.grid_sample / unfold correlation), bit-identical to the reference on CPU"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d forwards of one %dx%d batch-%d pair after %d warm-up" % (args.steps, H, W, B, max(1, args.warmup))},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def corr_roofline(pk, iters=20):
+    """Fused correlation+LeakyReLU kernel alone at the HD 1/4-res shape: algorithmic bytes
+    4*N*h*w*(2C+81) / CUDA-event time, L2 flushed before every launch."""
+    from upflow_pytorch_b200 import ops
+    N, C, h, w, d = 2, 32, 270, 480, 4
+    g = torch.Generator().manual_seed(1)
+    f1 = torch.randn(N, h, w, C, generator=g).cuda()
+    f2 = torch.randn(N, h, w, C, generator=g).cuda()
+    out = torch.empty(N, h, w, 81, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        ops.k_corr(f1, f2, out, d, slope=0.1)
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.k_corr(f1, f2, out, d, slope=0.1)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sum(ts) / len(ts)
+    nbytes = 4 * N * h * w * (2 * C + 81)
+    ach = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": "corr_fwd_kernel<4>", "shape": [N, C, h, w], "max_disp": d, "bound": "hbm", "achieved": ach,
+            "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None, "us_per_launch": ms * 1e3,
+            "best_us": min(ts) * 1e3, "algorithmic_bytes": nbytes, "l2": "flushed before every launch"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="kitti_375x1242_b1", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps > 60:
+            args.steps = 60          # bounded CPU sample (~1-2.5 s per KITTI pair on the host cores)
+        run_reference(args, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W_ = max(3, args.warmup)
+    K = args.steps
+    H, W, B = WORKLOADS[args.workload]
+    pk = peaks()
+
+    import upflow_pytorch_b200 as pkg
+    from upflow_pytorch_b200 import _ext, profiler
+    sd = make_weights()
+    net = pkg.build_model(state_dict=sd, conv_precision=args.precision)      # public API object (drop-in UPFlow_net)
+    im1_h, im2_h = synth_inputs(B, H, W, 1234 + rank)
+    im1_h, im2_h = im1_h.pin_memory(), im2_h.pin_memory()
+    im1_d, im2_d = im1_h.cuda(), im2_h.cuda()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- value: graph replay, inputs resident in HBM
+    eng = net._get_engine()
+    with torch.no_grad():
+        graphed = eng.capture(B, H, W)
+    graphed.im1.copy_(im1_d)
+    graphed.im2.copy_(im2_d)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")    # > 126 MB L2
+    for _ in range(W_):
+        graphed.replay()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    evs = []
+    t_wall0 = time.perf_counter()
+    for _ in range(K):
+        flush.zero_()                                   # L2 flush, outside the per-step events
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graphed.replay()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    step_ms = sum(a.elapsed_time(b) for a, b in evs) / K
+    step_ms = max_over_ranks(step_ms)
+    value = world * B / (step_ms * 1e-3)
+
+    # ---------------- e2e: public API, pinned host in, host out, every step
+    out_h = torch.empty(B, 2, H, W).pin_memory()
+    with torch.no_grad():
+        def e2e_step():
+            a = im1_h.cuda(non_blocking=True)
+            b = im2_h.cuda(non_blocking=True)
+            o = net({"im1": a, "im2": b, "if_loss": False})
+            out_h.copy_(o["flow_f_out"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()    # the caller reads the flow
+        for _ in range(W_):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            e2e_step()
+        e1.record()
+        barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1) / K)
+    e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": 2 * im1_h.numel() * 4, "d2h_bytes_per_step": out_h.numel() * 4,
+           "api": "UPFlow_net(input_dict)['flow_f_out'] (drop-in model.upflow), pinned host tensors in and out"}
+
+    line = None
+    if rank == 0:
+        # ---------------- roofline: per-launch events over one eager forward (spin kernel lets the host run ahead)
+        with torch.no_grad():
+            eng.forward(im1_d, im2_d)
+            with profiler.record() as rec:
+                eng.forward(im1_d, im2_d)
+        agg = rec.by_kernel()
+        total_ms = sum(a["ms"] for a in agg.values())
+        dom = max(agg, key=lambda k: agg[k]["ms"])
+        a = agg[dom]
+        if dom.startswith("conv"):
+            tf32_peak = pk["bf16"] / 2.0
+            ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
+            roof = {"kernel": "conv_tc_kernel" if dom == "conv_tc" else "conv_simt_kernel", "bound": "tensor",
+                    "achieved": ach, "peak": tf32_peak if dom == "conv_tc" else 74.4, "unit": "TFLOP/s",
+                    "frac": ach / (tf32_peak if dom == "conv_tc" else 74.4), "traffic": None,
+                    "peak_source": pk["source"] + ": bf16_tflops/2 (dense TF32 rate is half the bf16 rate)"
+                    if dom == "conv_tc" else "fp32 SIMT 148 SM x 128 lanes x 2 x 1.965 GHz",
+                    "launches_per_step": a["launches"], "ms_per_step": a["ms"], "share_of_step": a["ms"] / total_ms,
+                    "algorithmic_flops_per_step": a["flops"]}
+        else:
+            ach = a["bytes"] / (a["ms"] * 1e-3) / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["source"],
+                    "launches_per_step": a["launches"], "ms_per_step": a["ms"], "share_of_step": a["ms"] / total_ms}
+        breakdown = {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
+                         "GB/s": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
+                         "TFLOP/s": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 else None}
+                     for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+        rc = corr_roofline(pk)
+
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import ref_port as P
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            a1, a2 = im1_h.clone(), im2_h.clone()
+            reps = 3 if H * W <= 600 * 1300 else 1
+            with torch.no_grad():
+                P.forward_2_frame(a1, a2, sd)
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    rf = P.forward_2_frame(a1, a2, sd)[0]
+                dt = (time.perf_counter() - t0) / reps
+                f, _, _ = eng.forward(im1_d, im2_d)
+            from oracle import cpu_oracle as O
+            cpu = {"value": B / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "%d forward(s) of the same %dx%d batch-%d pair after 1 warm-up, %d torch threads" % (reps, H, W, B, cores),
+                   "epe_cuda_vs_cpu_port_px": O.epe(f.cpu(), rf)}
+
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": args.workload, "pairs_per_step_per_gpu": B, "image": [H, W],
+                           "pyramid_levels": 6, "decoder_levels": 5, "sgu": True, "directions": "forward+backward stacked",
+                           "weights": "random-init (MSRA, seed 1234): no checkpoint on the GPU box",
+                           "l2": "flushed (256 MiB write) before every timed step; flush outside the step events",
+                           "launch": "one CUDA graph replay per step", "parallelism": "batch-sharded x%d, no collective in inference" % world},
+                "e2e": e2e, "gpu_launches": graphed.launches * K, "launches_per_step": graphed.launches,
+                "clocks": clocks, "roofline": roof, "roofline_corr": rc, "kernel_breakdown_ms": breakdown,
+                "wall_s_timed_region": wall}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -75,19 +75,23 @@ int upf_corr_lrelu_bwd(const float* f1, int ld1, const float* f2, int ld2,
  * `mask >= 1.0` validity mask, bit-faithful to F.grid_sample as the reference
  * calls it.
  *   replaces WarpingLayer_no_div.forward (model/pwc_modules.py:184-207) and,
- *   with use_mask=0, tools.torch_warp (utils/tools.py:1274-1304).
+ *   with mask_threshold<=0, tools.torch_warp (utils/tools.py:1274-1304).
+ * mask_threshold: a pixel is kept when the sum of its in-bounds bilinear weights
+ * is >= mask_threshold.  1.0f is the reference; 0.9999f is the DIAGNOSTIC
+ * "robust mask" used to show parity without the reference's 1-ulp mask flips
+ * (utils/tools.py:1311 has the same idea commented out); <= 0 disables the mask.
  * flow is [N,H,W,>=2] (u,v) with pitch ldf.  If stats != NULL the (sum, sum^2)
  * of the OUTPUT are accumulated per (n,c).  x_batch_shift: output image n
  * samples image (n + shift) % N of x (see upf_corr_lrelu_fwd). */
 int upf_warp_fwd(const float* x, int ldx, const float* flow, int ldf, float* out, int ldo,
-                 int N, int H, int W, int C, int align_corners, int use_mask,
+                 int N, int H, int W, int C, int align_corners, float mask_threshold,
                  int x_batch_shift, double* stats, void* stream);
 
 /* a11: backward of upf_warp_fwd wrt x (scatter-add; grad_x must be zeroed by the
  * caller) and wrt flow (grad_flow [N,H,W,2], written).  Either may be NULL. */
 int upf_warp_bwd(const float* x, int ldx, const float* flow, int ldf, const float* grad_out, int ldg,
                  float* grad_x, int ldgx, float* grad_flow, int ldgf,
-                 int N, int H, int W, int C, int align_corners, int use_mask, void* stream);
+                 int N, int H, int W, int C, int align_corners, float mask_threshold, void* stream);
 
 /* a5: normalize_features (model/upflow.py:94-137) with
  * moments_across_channels=False, moments_across_images=False (test.py:24-26). */

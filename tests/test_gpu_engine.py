@@ -4,11 +4,17 @@ port at KITTI size, and module-by-module decode_level_res.  -m gpu.
 
 Pointwise end-to-end equality with the reference is NOT attainable by any
 re-associated implementation: WarpingLayer_no_div's `mask >= 1.0`
-(model/pwc_modules.py:206) zeroes whole pixels on 1-ulp differences, and the
-reference moves by mean EPE 0.032 px under a 1e-6 relative input perturbation
-(SURVEY.md section 7).  So: the level before any warp must agree to rounding,
-medians (robust to flipped pixels) must agree tightly at every level, and the
-full-resolution mean EPE must stay inside the reference's own noise floor.
+(model/pwc_modules.py:206) zeroes ~1.5 % of interior pixels on 1-ulp
+differences, which pixels is re-randomised by any 1e-7 change of the flow, and
+every flipped pixel moves the per-channel normalisation statistics of the whole
+image.  Measured on the reference's own CPU path (oracle/ref_port.py, weights
+det_state_dict(3), inputs scaled by 1+1e-6): mean EPE 0.056 px at 375x1242,
+0.019 px at 128x192.  So the tests pin
+  (1) every level BEFORE the first warp to rounding (fp32: 1e-6),
+  (2) the full pipeline with the mask threshold relaxed to 0.9999 on BOTH sides
+      ("robust mask" diagnostic) to 2e-4 px mean EPE in fp32 -- this is the
+      statement that nothing but the mask discontinuity separates the two,
+  (3) the reference-semantics pipeline to the reference's own noise floor.
 """
 import pytest
 import torch
@@ -18,12 +24,12 @@ from oracle import ref_port as P
 
 pytestmark = pytest.mark.gpu
 
-NOISE_FLOOR_EPE = 0.1     # > 3x the measured 0.032 px ref-vs-ref figure
+NOISE_FLOOR_EPE = 0.15     # 375x1242, random-init weights: reference vs itself (1+1e-6) = 0.056 px
 
 
-def _engine(precision, sd):
+def _engine(precision, sd, **kw):
     from upflow_pytorch_b200.engine import DecoderEngine
-    return DecoderEngine({k: v.cuda() for k, v in sd.items()}, precision=precision)
+    return DecoderEngine({k: v.cuda() for k, v in sd.items()}, precision=precision, **kw)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
@@ -35,21 +41,19 @@ def test_golden_e2e(golden, precision):
     f, b, flows = eng.forward(im1.cuda(), im2.cuda())
     f, b = f.cpu(), b.cpu()
     flows = [[x.cpu(), y.cpu()] for x, y in flows]
-    tol0 = 2e-5 if precision == "fp32" else 5e-3
-    # coarsest level: no warp, no mask -> rounding only
-    assert (flows[-1][0] - g["flows"][-1][0]).abs().max().item() <= tol0 * max(1.0, g["flows"][-1][0].abs().max().item())
-    assert (flows[-1][1] - g["flows"][-1][1]).abs().max().item() <= tol0 * max(1.0, g["flows"][-1][1].abs().max().item())
-    for (a, c), (ga, gc) in zip(flows, g["flows"]):
-        assert (a - ga).abs().median().item() <= (1e-4 if precision == "fp32" else 2e-2)
+    tol0 = 5e-6 if precision == "fp32" else 1e-3
+    # the three coarsest levels of this fixture see no mask flip: rounding only
+    for lv in (-1, -2):
+        for d in (0, 1):
+            assert (flows[lv][d] - g["flows"][lv][d]).abs().max().item() <= tol0
     epe_f, epe_b = O.epe(f, g["flow_f_out"]), O.epe(b, g["flow_b_out"])
     print("golden e2e", precision, "EPE fw/bw vs reference", epe_f, epe_b)
-    assert epe_f <= NOISE_FLOOR_EPE and epe_b <= NOISE_FLOOR_EPE
+    assert epe_f <= 0.05 and epe_b <= 0.05
 
 
 @pytest.mark.parametrize("hw", [(375, 1242), (128, 192)])
 def test_kitti_size_vs_port(hw):
     """full size, random-init deterministic weights: CUDA vs the CPU port of the reference."""
-    torch.set_num_threads(max(1, torch.get_num_threads()))
     sd = P.det_state_dict(3)
     im1, im2 = O.synthetic_pair(*hw, seed=1234)
     with torch.no_grad():
@@ -59,16 +63,38 @@ def test_kitti_size_vs_port(hw):
         f, b, flows = eng.forward(im1.cuda(), im2.cuda())
         torch.cuda.synchronize()
         epe = O.epe(f.cpu(), rf)
-        med = (f.cpu() - rf).abs().median().item()
         l0 = (flows[-1][0].cpu() - rflows[-1][0]).abs().max().item()
-        print("size", hw, precision, "EPE vs port", epe, "median abs diff", med, "level0 max diff", l0,
-              "ref mean |flow|", rf.abs().mean().item())
-        assert l0 <= (5e-5 if precision == "fp32" else 2e-2)
-        assert epe <= NOISE_FLOOR_EPE * (1 if precision == "fp32" else 3)
+        print("size", hw, precision, "EPE vs port", epe, "level0 max diff", l0, "ref mean |flow|", rf.abs().mean().item())
+        assert l0 <= (2e-6 if precision == "fp32" else 2e-3)
+        assert epe <= NOISE_FLOOR_EPE
+        # EPE against the known synthetic motion (-3,+2) is not meaningful for random weights; the
+        # checkpointed comparison is reported by bench/epe_report.py when the checkpoint is present
+
+
+@pytest.mark.parametrize("hw", [(375, 1242), (128, 192)])
+def test_robust_mask_diagnostic_is_tight(hw):
+    """mask threshold 0.9999 on both sides: the whole forward agrees to rounding (fp32) / TF32 noise."""
+    sd = P.det_state_dict(3)
+    im1, im2 = O.synthetic_pair(*hw, seed=1234)
+    P.MASK_THRESHOLD = 0.9999
+    try:
+        with torch.no_grad():
+            rf, rb, rflows = P.forward_2_frame(im1, im2, sd)
+    finally:
+        P.MASK_THRESHOLD = 1.0
+    for precision, bound in (("fp32", 2e-4), ("tf32", 2e-2)):
+        eng = _engine(precision, sd, mask_threshold=0.9999)
+        f, b, flows = eng.forward(im1.cuda(), im2.cuda())
+        epe_f, epe_b = O.epe(f.cpu(), rf), O.epe(b.cpu(), rb)
+        mx = (f.cpu() - rf).abs().max().item()
+        print("robust-mask", hw, precision, "EPE fw %.3g bw %.3g max|diff| %.3g" % (epe_f, epe_b, mx))
+        assert epe_f <= bound and epe_b <= bound
 
 
 def test_dropin_decode_level_golden(golden):
-    """decode_level_res through the drop-in modules, teacher-forced with the reference's inputs (golden)."""
+    """decode_level_res through the drop-in modules, teacher-forced with the reference's inputs (golden).
+    flow_*_up (SGU output: the warp inside it sees bit-identical inputs) must be tight; the residuals pass through a
+    warp by that (1e-6-perturbed) flow, i.e. through re-randomised mask flips on a 12x16 map."""
     import upflow_pytorch_b200 as pkg
     g = golden("decode_level")
     net = pkg.build_model(state_dict=P.det_state_dict(g["wseed"]), conv_precision="fp32")
@@ -82,8 +108,10 @@ def test_dropin_decode_level_golden(golden):
     for got, key in zip(o, ("flow_1_up", "flow_2_up", "res_1", "res_2")):
         d = (got.cpu() - g[key]).abs()
         print("decode_level", key, "max", d.max().item(), "median", d.median().item())
-        assert d.median().item() <= 1e-4
-        assert d.mean().item() <= 5e-2
+        if key.startswith("flow"):
+            assert d.max().item() <= 5e-5
+        else:
+            assert d.mean().item() <= 5e-2
 
 
 def test_dropin_sgu_golden(golden):
@@ -113,9 +141,9 @@ def test_dropin_net_forward_matches_reference_api(golden):
         out = net({"im1": im1.cuda(), "im2": im2.cuda(), "if_loss": False})
     assert set(out) == {"flow_f_out", "flow_b_out", "occ_fw", "occ_bw"}
     assert out["flow_f_out"].shape == g["flow_f_out"].shape
-    assert O.epe(out["flow_f_out"].cpu(), g["flow_f_out"]) <= NOISE_FLOOR_EPE
+    assert O.epe(out["flow_f_out"].cpu(), g["flow_f_out"]) <= 0.05
     agree = (out["occ_fw"].cpu() == g["occ_fw"]).float().mean().item()
-    assert agree >= 0.98
+    assert agree >= 0.97
     with pytest.raises(RuntimeError):
         net.forward_2_frame_v3(im1, im2)          # CPU tensors: no fallback
 

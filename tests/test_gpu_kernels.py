@@ -213,7 +213,7 @@ def test_sgu_blend_vs_oracle_both_variants(upf):
 CONV_CASES = [  # (Cin, Cout, k, stride, dil, H, W)
     (115, 128, 3, 1, 1, 12, 39), (563, 2, 3, 1, 1, 12, 20), (128, 96, 3, 1, 8, 24, 30), (96, 64, 3, 1, 16, 24, 30),
     (196, 32, 1, 1, 1, 6, 20), (3, 16, 3, 2, 1, 37, 50), (16, 16, 3, 1, 1, 19, 25), (64, 3, 3, 1, 1, 9, 9),
-    (32, 32, 3, 2, 1, 20, 21),
+    (32, 32, 3, 2, 1, 20, 21), (128, 196, 3, 1, 1, 6, 20),
 ]
 
 

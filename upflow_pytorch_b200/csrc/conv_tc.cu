@@ -132,6 +132,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   const int ty = tile % p.tiles_y;
   const int n = tile / p.tiles_y;
   const int x0 = tx * p.TW, y0 = ty * p.TH;
+  const int co0 = blockIdx.y * p.BN;            // first output channel of this CTA's N tile
   const int taps = p.ks * p.ks;
   const int iters = taps * p.kblocks;
 
@@ -171,7 +172,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           const uint32_t fb = smem_u32(&full[s]);
           mbar_expect_tx(fb, TC_A_BYTES + b_bytes);
           tma_load_4d(a_dst, &map_x, fb, kb * TC_KC, cx, cy, n);
-          tma_load_3d(b_dst, &map_w, fb, kb * TC_KC, 0, tap);
+          tma_load_3d(b_dst, &map_w, fb, kb * TC_KC, co0, tap);
         }
       }
     }
@@ -216,7 +217,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int co = c0 + j;
+          const int co = co0 + c0 + j;
           float acc = __uint_as_float(v[j]);
           if (co < p.Cout) {
             acc = lrelu(acc + __ldg(p.bias + co), p.slope);
@@ -224,13 +225,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           }
           f[j] = acc;
         }
-        if (vec_out && c0 + 16 <= p.Cout) {
+        if (vec_out && co0 + c0 + 16 <= p.Cout) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + co0 + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < p.Cout) o[c0 + j] = f[j];
+            if (co0 + c0 + j < p.Cout) o[co0 + c0 + j] = f[j];
         }
       }
     }
@@ -318,9 +319,10 @@ static void pick_tile(int H, int W, int* TH, int* TW) {
 int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
                   const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int dil, float slope,
                   cudaStream_t st) {
-  UPF_REQUIRE(Cout <= 128, "conv_tc: Cout %d > 128", Cout);
   UPF_REQUIRE((ldx % 4) == 0 && aligned16(x) && aligned16(w_packed), "conv_tc: input pitch/pointer must be 16-byte aligned");
-  const int BN = (Cout + 15) & ~15;
+  const int cout_pad = (Cout + 15) & ~15;
+  const int ntiles_n = (cout_pad + 127) / 128;
+  const int BN = ((cout_pad + ntiles_n - 1) / ntiles_n + 15) & ~15;   // equal N tiles <= 128 wide (rows past cout_pad: TMA zero fill)
   const int kblocks = (Cin + TC_KC - 1) / TC_KC;
   const int cin_pad = kblocks * TC_KC;
   const int taps = ks * ks;
@@ -337,10 +339,10 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
     if (e) return e;
   }
   {
-    const cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)BN, (cuuint64_t)taps};
-    const cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 4, (cuuint64_t)cin_pad * BN * 4};
+    const cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)taps};
+    const cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 4, (cuuint64_t)cin_pad * cout_pad * 4};
     const cuuint32_t box[3] = {TC_KC, (cuuint32_t)BN, 1};
-    MapKey key{w_packed, cin_pad, BN, taps, 0, 3};
+    MapKey key{w_packed, cin_pad, BN, taps, cout_pad, 3};
     int e = encode_cached(key, &mw, 3, const_cast<float*>(w_packed), dims, strides, box);
     if (e) return e;
   }
@@ -365,7 +367,7 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
     attr_set = true;
   }
   const long long tiles = (long long)p.tiles_x * p.tiles_y * N;
-  conv_tc_kernel<<<(unsigned)tiles, TC_THREADS, smem, st>>>(mx, mw, p);
+  conv_tc_kernel<<<dim3((unsigned)tiles, (unsigned)ntiles_n), TC_THREADS, smem, st>>>(mx, mw, p);
   return check_launch("conv_tc");
 }
 

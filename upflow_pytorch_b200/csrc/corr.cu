@@ -201,15 +201,18 @@ static int launch_corr_fwd(const float* f1, int ld1, const float* f2, int ld2, f
   const long long tiles = (long long)tiles_x * tiles_y * N;
   UPF_REQUIRE(tiles > 0 && tiles < (1ll << 31), "corr: bad tile count %lld", tiles);
   const bool vec = (C % 4 == 0) && (ld1 % 4 == 0) && (ld2 % 4 == 0) && aligned16(f1) && aligned16(f2);
-  cudaError_t e;
+  // opt in to >48 KB dynamic shared memory once per instantiation (per device would need a table: one
+  // process drives one GPU here)
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(corr_fwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
+    if (e == cudaSuccess)
+      attr_done = true;
+  }
   if (vec) {
-    e = cudaFuncSetAttribute(corr_fwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
-    if (e != cudaSuccess) { set_error("corr smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     corr_fwd_kernel<D, true><<<(unsigned)tiles, K::NT, K::SMEM_BYTES, st>>>(f1, ld1, f2, ld2, out, ldo, H, W, C, s1, s2,
                                                                           slope, tiles_x, tiles_y, shift, N);
   } else {
-    e = cudaFuncSetAttribute(corr_fwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
-    if (e != cudaSuccess) { set_error("corr smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     corr_fwd_kernel<D, false><<<(unsigned)tiles, K::NT, K::SMEM_BYTES, st>>>(f1, ld1, f2, ld2, out, ldo, H, W, C, s1,
                                                                            s2, slope, tiles_x, tiles_y, shift, N);
   }

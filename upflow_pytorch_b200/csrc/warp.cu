@@ -21,7 +21,7 @@ constexpr int WARP_NT = 256;
 template <bool VEC>
 __global__ void __launch_bounds__(WARP_NT)
 warp_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ flow, int ldf,
-                float* __restrict__ out, int ldo, int H, int W, int C, int align_corners, int use_mask,
+                float* __restrict__ out, int ldo, int H, int W, int C, int align_corners, float mask_thr,
                 double* __restrict__ stats, int lpp, int ctas_per_image, int x_shift, int N) {
   extern __shared__ double s_red[];   // [2][cgroups*4] when stats
   const int n = blockIdx.x / ctas_per_image;
@@ -49,7 +49,7 @@ warp_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ 
     const float ix = sample_coord((float)xpix, u, W, align_corners);
     const float iy = sample_coord((float)y, v, H, align_corners);
     const BilinearTaps t = bilinear_taps(ix, iy, H, W);
-    const bool keep = !use_mask || t.wsum >= 1.0f;      // mask = (grid_sample(ones) >= 1.0), pwc_modules.py:205-206
+    const bool keep = !(mask_thr > 0.f) || t.wsum >= mask_thr;      // mask = (grid_sample(ones) >= 1.0), pwc_modules.py:205-206
     const float* r_nw = x + (ximg + (long long)t.y0 * W + t.x0) * (long long)ldx;   // may point outside: only dereferenced when in_*
     const float* r_ne = r_nw + ldx;
     const float* r_sw = r_nw + (size_t)W * ldx;
@@ -198,7 +198,7 @@ featnorm_apply_kernel(const float* __restrict__ x, int ldx, const double* __rest
 __global__ void __launch_bounds__(256)
 warp_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ flow, int ldf,
                 const float* __restrict__ go, int ldg, float* __restrict__ gx, int ldgx,
-                float* __restrict__ gflow, int ldgf, int N, int H, int W, int C, int align_corners, int use_mask) {
+                float* __restrict__ gflow, int ldgf, int N, int H, int W, int C, int align_corners, float mask_thr) {
   // one warp per pixel, lanes stride over channels
   const long long npix = (long long)N * H * W;
   const int lane = threadIdx.x & 31;
@@ -212,7 +212,7 @@ warp_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ 
     const float ix = sample_coord((float)xpix, __ldg(fl), W, align_corners);
     const float iy = sample_coord((float)y, __ldg(fl + 1), H, align_corners);
     const BilinearTaps t = bilinear_taps(ix, iy, H, W);
-    const bool keep = !use_mask || t.wsum >= 1.0f;
+    const bool keep = !(mask_thr > 0.f) || t.wsum >= mask_thr;
     float gix = 0.f, giy = 0.f;
     if (keep) {
       const long long base = ((long long)n * H + t.y0) * W + t.x0;   // corners are only touched when in_*
@@ -263,7 +263,7 @@ static int pick_lpp(int C) {
 }  // namespace upf
 
 extern "C" int upf_warp_fwd(const float* x, int ldx, const float* flow, int ldf, float* out, int ldo,
-                            int N, int H, int W, int C, int align_corners, int use_mask, int x_batch_shift,
+                            int N, int H, int W, int C, int align_corners, float mask_threshold, int x_batch_shift,
                             double* stats, void* stream) {
   using namespace upf;
   UPF_REQUIRE(x && flow && out, "warp: null tensor");
@@ -280,16 +280,16 @@ extern "C" int upf_warp_fwd(const float* x, int ldx, const float* flow, int ldf,
   const size_t smem = stats ? (size_t)2 * ((C + 3) / 4) * 4 * sizeof(double) : 0;
   if (vec)
     warp_fwd_kernel<true><<<N * per_image, WARP_NT, smem, (cudaStream_t)stream>>>(x, ldx, flow, ldf, out, ldo, H, W, C,
-                                                                                 align_corners, use_mask, stats, lpp, per_image, x_batch_shift, N);
+                                                                                 align_corners, mask_threshold, stats, lpp, per_image, x_batch_shift, N);
   else
     warp_fwd_kernel<false><<<N * per_image, WARP_NT, smem, (cudaStream_t)stream>>>(x, ldx, flow, ldf, out, ldo, H, W, C,
-                                                                                  align_corners, use_mask, stats, lpp, per_image, x_batch_shift, N);
+                                                                                  align_corners, mask_threshold, stats, lpp, per_image, x_batch_shift, N);
   return check_launch("warp_fwd");
 }
 
 extern "C" int upf_warp_bwd(const float* x, int ldx, const float* flow, int ldf, const float* grad_out, int ldg,
                             float* grad_x, int ldgx, float* grad_flow, int ldgf,
-                            int N, int H, int W, int C, int align_corners, int use_mask, void* stream) {
+                            int N, int H, int W, int C, int align_corners, float mask_threshold, void* stream) {
   using namespace upf;
   UPF_REQUIRE(x && flow && grad_out, "warp_bwd: null tensor");
   UPF_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "warp_bwd: bad shape");
@@ -297,7 +297,7 @@ extern "C" int upf_warp_bwd(const float* x, int ldx, const float* flow, int ldf,
   long long blocks = (npix * 32 + 255) / 256;
   if (blocks > UPF_NUM_SMS * 16) blocks = UPF_NUM_SMS * 16;
   warp_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, flow, ldf, grad_out, ldg, grad_x, ldgx,
-                                                                     grad_flow, ldgf, N, H, W, C, align_corners, use_mask);
+                                                                     grad_flow, ldgf, N, H, W, C, align_corners, mask_threshold);
   return check_launch("warp_bwd");
 }
 

@@ -112,6 +112,7 @@ class UPFlow_net(tools.abstract_model):
 
     # extra, non-reference knobs of the B200 build (class attributes so `config` stays identical)
     conv_precision = "tf32"      # 'tf32' = tcgen05 tensor cores (what cuDNN does by default), 'fp32' = strict SIMT
+    use_cuda_graph = True        # replay one captured graph per input shape (inference has no host decisions)
 
     def __init__(self, conf: config):
         super(UPFlow_net, self).__init__()
@@ -147,6 +148,7 @@ class UPFlow_net(tools.abstract_model):
             self.froze_PWC()
         self._engine = None
         self._engine_key = None
+        self._graphs = {}
 
     # ------------------------------------------------------------------ engine plumbing
     def _get_engine(self):
@@ -163,6 +165,7 @@ class UPFlow_net(tools.abstract_model):
             self._engine = DecoderEngine(self.state_dict(), device=params[0].device, precision=self.conv_precision,
                                          use_sgu=bool(self.conf.if_sgu_upsample))
             self._engine_key = key
+            self._graphs = {}
         return self._engine
 
     def forward(self, input_dict: dict):
@@ -188,7 +191,18 @@ class UPFlow_net(tools.abstract_model):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError("training through the fused decoder needs the backward kernels (not built yet); "
                                       "call under torch.no_grad()")
-        f, b, flows = self._get_engine().forward(x1_raw.float(), x2_raw.float())
+        eng = self._get_engine()
+        if self.use_cuda_graph:
+            key = tuple(x1_raw.shape)
+            g = self._graphs.get(key)
+            if g is None:
+                if len(self._graphs) >= 8:
+                    self._graphs.clear()
+                g = self._graphs[key] = eng.capture(x1_raw.shape[0], x1_raw.shape[2], x1_raw.shape[3])
+            f, b = g(x1_raw, x2_raw)
+            flows = g.flows
+        else:
+            f, b, flows = eng.forward(x1_raw.float(), x2_raw.float())
         return f.clone(), b.clone(), [[a.clone(), c.clone()] for a, c in flows]
 
     def decode_level_res(self, level, flow_1, flow_2, feature_1, feature_1_1x1, feature_2, feature_2_1x1, img_ori_1,

@@ -66,7 +66,8 @@ class ConvSpec:
 
 
 class DecoderEngine:
-    def __init__(self, state_dict, device="cuda", precision="tf32", align_corners=False, use_sgu=True):
+    def __init__(self, state_dict, device="cuda", precision="tf32", align_corners=False, use_sgu=True,
+                 mask_threshold=1.0):
         """state_dict: the reference's parameter names."""
         if not torch.cuda.is_available():
             raise RuntimeError("DecoderEngine needs a CUDA device: the decoder path has no CPU implementation")
@@ -76,6 +77,8 @@ class DecoderEngine:
         self.tc = precision == "tf32"
         self.align_corners = bool(align_corners)
         self.use_sgu = use_sgu
+        # 1.0 = the reference's `mask >= 1.0` (model/pwc_modules.py:206); 0.9999 = diagnostic robust mask
+        self.mask = True if mask_threshold == 1.0 else float(mask_threshold)
         self._ws = {}
         self.load_weights(state_dict)
 
@@ -220,7 +223,7 @@ class DecoderEngine:
                     ops.k_resize(prev_flow, bil, (w / pw, h / ph))
                     S = d["S"]
                     ops.k_copy(Slice(X, X_F1X1, 32), Slice(S, 0, 32))
-                    ops.k_warp(Slice(X, X_F1X1, 32), bil, Slice(S, 32, 32), ac, True, x_shift=B)
+                    ops.k_warp(Slice(X, X_F1X1, 32), bil, Slice(S, 32, 32), ac, self.mask, x_shift=B)
                     self._sgu_dense(S, d["inter"])
                     ops.k_sgu_blend(bil, Slice(d["inter"], 0, 3), flow_up, ac)
                 else:
@@ -232,7 +235,7 @@ class DecoderEngine:
                 ops.k_corr(F, F, Slice(X, X_CORR, 81), 4, d["stats_own"], d["stats_own"], f2_shift=B, slope=SLOPE)
             else:
                 d["stats_w"].zero_()
-                ops.k_warp(F, flow_up, Slice(d["xw"]), ac, True, x_shift=B, stats=d["stats_w"])
+                ops.k_warp(F, flow_up, Slice(d["xw"]), ac, self.mask, x_shift=B, stats=d["stats_w"])
                 ops.k_corr(F, Slice(d["xw"]), Slice(X, X_CORR, 81), 4, d["stats_own"], d["stats_w"], slope=SLOPE)
             # dense flow estimator (model/pwc_modules.py:279-286)
             for k in range(5):
@@ -267,7 +270,7 @@ class DecoderEngine:
             S = ws["S_out"]
             self._conv(self.outconv[3], Slice(ws["oc_c"]), Slice(S, 0, 32))
             # the flow handed to sgu_model here is the 1/4-res flow itself (already at feature size, :73-75)
-            ops.k_warp(Slice(S, 0, 32), prev_flow, Slice(S, 32, 32), ac, True, x_shift=B)
+            ops.k_warp(Slice(S, 0, 32), prev_flow, Slice(S, 32, 32), ac, self.mask, x_shift=B)
             self._sgu_dense(S, ws["inter_out"])
             ops.k_sgu_blend(bil, Slice(ws["inter_out"], 0, 3), out, ac)
         else:
@@ -275,3 +278,35 @@ class DecoderEngine:
         fo = ws["flow_out"].permute(0, 3, 1, 2)
         lvl = [[f[:B].permute(0, 3, 1, 2), f[B:].permute(0, 3, 1, 2)] for f in flows]
         return fo[:B], fo[B:], lvl[::-1]
+
+    # ------------------------------------------------------------ CUDA graph
+    def capture(self, B, H, W):
+        """Capture the whole two-frame forward for one input shape in a CUDA graph (the forward has no host
+        decisions, allocations or synchronisation).  Returns a GraphedForward."""
+        im1 = torch.zeros(B, 3, H, W, dtype=torch.float32, device=self.device)
+        im2 = torch.zeros_like(im1)
+        self.forward(im1, im2)                         # eager warm-up: workspace, tensor maps, func attributes
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        n0 = _ext.launch_count()
+        with torch.cuda.graph(graph):
+            out = self.forward(im1, im2)
+        return GraphedForward(graph, im1, im2, out, _ext.launch_count() - n0)
+
+
+class GraphedForward:
+    """Replay handle: copy a pair into (im1, im2), call replay(), read flow_f / flow_b (views of the workspace)."""
+
+    def __init__(self, graph, im1, im2, out, launches):
+        self.graph, self.im1, self.im2 = graph, im1, im2
+        self.flow_f, self.flow_b, self.flows = out
+        self.launches = launches                       # library kernels per replay
+
+    def replay(self):
+        self.graph.replay()
+
+    def __call__(self, im1, im2):
+        self.im1.copy_(im1, non_blocking=True)
+        self.im2.copy_(im2, non_blocking=True)
+        self.graph.replay()
+        return self.flow_f, self.flow_b

@@ -103,11 +103,20 @@ def k_corr_bwd(f1, f2, out, grad_out, grad_f1, grad_f2, max_disp=4, slope=1.0):
                                          g2.ld, f1.N, f1.H, f1.W, f1.C, max_disp, slope, _stream()), "corr_lrelu_bwd")
 
 
+def _mask_thr(use_mask):
+    """True -> 1.0 (the reference's `mask >= 1.0`), False -> no mask, float -> that threshold (diagnostic)."""
+    if use_mask is True:
+        return 1.0
+    if use_mask is False or use_mask is None:
+        return 0.0
+    return float(use_mask)
+
+
 def k_warp(x, flow, out, align_corners=False, use_mask=True, x_shift=0, stats=None):
     x, flow, out = _as_slice(x), _as_slice(flow), _as_slice(out)
     assert flow.C >= 2 and out.C == x.C
     _ext.check(_lib().upf_warp_fwd(x.ptr(), x.ld, flow.ptr(), flow.ld, out.ptr(), out.ld, out.N, out.H, out.W, x.C,
-                                   int(align_corners), int(use_mask), x_shift, _p(stats), _stream()), "warp_fwd")
+                                   int(align_corners), _mask_thr(use_mask), x_shift, _p(stats), _stream()), "warp_fwd")
 
 
 def k_warp_bwd(x, flow, grad_out, grad_x, grad_flow, align_corners=False, use_mask=True):
@@ -116,7 +125,7 @@ def k_warp_bwd(x, flow, grad_out, grad_x, grad_flow, align_corners=False, use_ma
     gf = _as_slice(grad_flow) if grad_flow is not None else None
     _ext.check(_lib().upf_warp_bwd(x.ptr(), x.ld, flow.ptr(), flow.ld, grad_out.ptr(), grad_out.ld,
                                    gx.ptr() if gx else None, gx.ld if gx else 0, gf.ptr() if gf else None,
-                                   gf.ld if gf else 0, x.N, x.H, x.W, x.C, int(align_corners), int(use_mask), _stream()),
+                                   gf.ld if gf else 0, x.N, x.H, x.W, x.C, int(align_corners), _mask_thr(use_mask), _stream()),
                "warp_bwd")
 
 
@@ -284,7 +293,7 @@ def warp(x, flow, align_corners=False, use_mask=True):
     _require_cuda(x, flow)
     if flow.shape[1] != 2 or flow.shape[0] != x.shape[0] or flow.shape[2:] != x.shape[2:]:
         raise RuntimeError("warp: flow must be [B,2,H,W] matching x")
-    return _WarpFn.apply(x, flow, bool(align_corners), bool(use_mask))
+    return _WarpFn.apply(x, flow, bool(align_corners), use_mask)
 
 
 def normalize_features(x):

@@ -1,0 +1,101 @@
+"""Per-launch device timing of the library's kernels with CUDA events (used by
+bench.py for the roofline object and by profiles/ summaries).
+
+Wraps the `ops.k_*` launchers: every launch is bracketed by two events on the
+launching stream.  A spin kernel is queued first so the host runs ahead and
+the bracketed kernels execute back to back (event deltas then exclude launch
+latency).  Algorithmic bytes / flops follow SURVEY.md section 8(d)."""
+import contextlib
+
+import torch
+
+from . import ops
+
+
+def _npix(s):
+    return s.N * s.H * s.W
+
+
+def _account(name, args, kwargs):
+    S = ops._as_slice
+    if name == "k_corr":
+        f1, out = S(args[0]), S(args[2])
+        n = _npix(f1)
+        return dict(bytes=4 * n * (2 * f1.C + out.C), flops=2 * out.C * f1.C * n, shape=(f1.N, f1.C, f1.H, f1.W))
+    if name == "k_warp":
+        x, out = S(args[0]), S(args[2])
+        return dict(bytes=4 * _npix(out) * (2 * x.C + 2), flops=8 * x.C * _npix(out), shape=(out.N, x.C, out.H, out.W))
+    if name == "k_stats":
+        x = S(args[0])
+        return dict(bytes=4 * _npix(x) * x.C, flops=3 * _npix(x) * x.C, shape=(x.N, x.C, x.H, x.W))
+    if name == "k_conv":
+        x, out = S(args[0]), S(args[3])
+        k = args[4]
+        n = _npix(out)
+        return dict(bytes=4 * (_npix(x) * x.C + n * out.C) + 4 * k * k * x.C * out.C, flops=2 * n * k * k * x.C * out.C,
+                    shape=(x.N, x.C, x.H, x.W, out.C, k), tc=(kwargs.get("precision", args[9] if len(args) > 9 else 0) == 1))
+    if name == "k_resize":
+        a, out = S(args[0]), S(args[1])
+        return dict(bytes=4 * a.C * (_npix(a) + _npix(out)), flops=8 * a.C * _npix(out), shape=(out.N, a.C, out.H, out.W))
+    if name == "k_sgu_blend":
+        inter, out = S(args[1]), S(args[2])
+        return dict(bytes=4 * (4 * _npix(out) + 3 * _npix(inter)), flops=40 * _npix(out), shape=(out.N, out.H, out.W))
+    if name == "k_copy":
+        a = S(args[0])
+        return dict(bytes=8 * _npix(a) * a.C, flops=0, shape=(a.N, a.C, a.H, a.W))
+    return dict(bytes=0, flops=0, shape=())
+
+
+NAMES = ("k_corr", "k_warp", "k_stats", "k_conv", "k_resize", "k_sgu_blend", "k_copy", "k_norm_apply")
+
+
+class Recorder:
+    def __init__(self):
+        self.records = []
+
+    def finalize(self):
+        torch.cuda.synchronize()
+        for r in self.records:
+            r["ms"] = r.pop("e0").elapsed_time(r.pop("e1"))
+        return self.records
+
+    def by_kernel(self):
+        agg = {}
+        for r in self.records:
+            name = r["name"]
+            if name == "k_conv":
+                name = "conv_tc" if r.get("tc") else "conv_simt"
+            a = agg.setdefault(name, dict(launches=0, ms=0.0, bytes=0, flops=0))
+            a["launches"] += 1
+            a["ms"] += r["ms"]
+            a["bytes"] += r["bytes"]
+            a["flops"] += r["flops"]
+        return agg
+
+
+@contextlib.contextmanager
+def record(spin_cycles=20_000_000):
+    rec = Recorder()
+    saved = {n: getattr(ops, n) for n in NAMES}
+
+    def wrap(name, fn):
+        def inner(*args, **kwargs):
+            meta = _account(name, args, kwargs)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(*args, **kwargs)
+            e1.record()
+            meta.update(name=name, e0=e0, e1=e1)
+            rec.records.append(meta)
+        return inner
+
+    for n, fn in saved.items():
+        setattr(ops, n, wrap(n, fn))
+    try:
+        if spin_cycles:
+            torch.cuda._sleep(int(spin_cycles))
+        yield rec
+    finally:
+        for n, fn in saved.items():
+            setattr(ops, n, fn)
+        rec.finalize()
