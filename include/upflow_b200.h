@@ -128,7 +128,10 @@ int upf_sgu_blend(const float* flow_init, int ldf, const float* inter, int ldi, 
  * precision: UPF_CONV_FP32 = SIMT fp32 FMA (bit-faithful class, any k/stride);
  *            UPF_CONV_TF32 = tcgen05 tensor cores, TF32 operands, fp32
  *            accumulate in TMEM (3x3/1x1 stride 1; needs the packed weights of
- *            upf_conv_tc_pack_weights). */
+ *            upf_conv_tc_pack_weights).
+ *            The tensor-core path takes stride 1 or 2; when the grid cannot fill the 148 SMs it splits the K
+ *            loop over a thread-block cluster and reduces through distributed shared memory in a fixed order
+ *            (bitwise reproducible, no scratch buffer). */
 #define UPF_CONV_FP32 0
 #define UPF_CONV_TF32 1
 int upf_conv2d_fwd(const float* x, int ldx, const float* w, const float* bias,

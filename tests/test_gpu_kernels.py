@@ -287,3 +287,34 @@ def test_layout_roundtrip(upf):
 def test_cpu_tensors_fail_loudly(upf):
     with pytest.raises(RuntimeError):
         upf.correlation(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4, 8, 8), 4)
+
+
+@pytest.mark.parametrize("case", [(576, 128, 3, 1, 1, 6, 20), (128, 96, 3, 1, 8, 12, 39), (184, 3, 3, 1, 1, 24, 78),
+                                  (196, 32, 1, 1, 1, 6, 20), (96, 128, 3, 2, 1, 24, 78), (16, 32, 3, 2, 1, 47, 61),
+                                  (128, 196, 3, 2, 1, 12, 39)])
+def test_conv_tf32_cluster_split_k_and_stride2(upf, case):
+    """small grids split the K loop over a thread-block cluster (DSMEM reduction in rank order): same bits on every
+    run, fp32-rounding agreement with the TF32-truncated oracle; stride 2 is walked by TMA element strides."""
+    from upflow_pytorch_b200 import _ext
+    from upflow_pytorch_b200.ops import Slice
+    Cin, Cout, k, stride, dil, H, W = case
+    x = _regen(50, (2, Cin, H, W))
+    w = _regen(51, (Cout, Cin, k, k)) * (2.0 / (Cin * k * k)) ** 0.5
+    b = _regen(52, (Cout,)) * 0.1
+    _, wtc = upf.pack_conv_weight(_cuda(w), tc=True)
+
+    def trunc(t):
+        return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    ref = O.conv2d_direct(trunc(x).double(), trunc(w).double(), b.double(), dil, stride, 0.1).float()
+    res = _regen(53, tuple(ref.shape))
+    ld = (Cin + 3) // 4 * 4
+    a = Slice(upf.to_pixel_major(_cuda(x), ld=ld), 0, Cin)
+    r = upf.to_pixel_major(_cuda(res))
+    outs = []
+    for _ in range(2):
+        out = torch.full((2, ref.shape[2], ref.shape[3], Cout), float("nan"), device="cuda")
+        upf.k_conv(a, wtc, _cuda(b), out, k, stride, dil, 0.1, r, _ext.CONV_TF32)
+        outs.append(out.clone())
+    assert torch.equal(outs[0], outs[1])
+    err = (outs[0].permute(0, 3, 1, 2).cpu() - (ref + res)).abs().max().item()
+    assert err <= 5e-4, err

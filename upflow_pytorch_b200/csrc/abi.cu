@@ -21,7 +21,7 @@ int conv2d_fwd_simt(const float* x, int ldx, const float* w, const float* bias, 
                     const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
                     float slope, cudaStream_t st);
 int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
-                  const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int dil,
+                  const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
                   float slope, cudaStream_t st);
 
 }  // namespace upf
@@ -43,8 +43,7 @@ extern "C" int upf_conv2d_fwd(const float* x, int ldx, const float* w, const flo
     return conv2d_fwd_simt(x, ldx, w, bias, out, ldo, residual, ldr, N, H, W, Cin, Cout, ksize, stride, dilation,
                            slope, (cudaStream_t)stream);
   if (precision == UPF_CONV_TF32) {
-    UPF_REQUIRE(stride == 1, "conv: the tensor-core path is stride 1 only");
-    return conv2d_fwd_tc(x, ldx, w, bias, out, ldo, residual, ldr, N, H, W, Cin, Cout, ksize, dilation, slope,
+    return conv2d_fwd_tc(x, ldx, w, bias, out, ldo, residual, ldr, N, H, W, Cin, Cout, ksize, stride, dilation, slope,
                          (cudaStream_t)stream);
   }
   set_error("conv: unknown precision %d", precision);

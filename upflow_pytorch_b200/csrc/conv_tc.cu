@@ -1,19 +1,21 @@
-// 3x3 / 1x1 stride-1 convolution on the 5th-generation tensor cores (sm_100a):
-// implicit GEMM, TF32 operands read straight from the fp32 feature buffers,
-// fp32 accumulation in tensor memory.
+// 3x3 / 1x1 convolution (stride 1 or 2, any dilation) on the 5th-generation
+// tensor cores (sm_100a): implicit GEMM, TF32 operands read straight from the
+// fp32 feature buffers, fp32 accumulation in tensor memory.
 //
 // Replaces the cuDNN calls behind conv() (model/pwc_modules.py:10-31) for the
-// dense flow estimator (:279-286), the dilated context network (:401-412) and
-// the SGU dense block (model/upflow.py:52-60).
+// dense flow estimator (:279-286), the dilated context network (:401-412), the
+// SGU dense block (model/upflow.py:52-60), the 1x1 adapters (:349-353), the
+// feature pyramid (pwc_modules.py:122-142) and sgu output_conv (upflow.py:66-69).
 //
 //   GEMM view  D[M=128 pixels, N=Cout] += A[M, K] * B[N, K]^T,  K = taps x Cin
-//   A  : im2col-free.  The activation tensor is a 4-D TMA tensor
-//        (C, W, H, N); for tap (ky,kx) and channel block kc the producer issues
-//        ONE box load {32 ch, TW, TH, 1} at (kc*32, x0+(kx-1)*dil, y0+(ky-1)*dil, n).
-//        TMA's out-of-bounds zero fill IS the convolution's zero padding (and
-//        the K remainder when Cin % 32 != 0).  The box lands in shared memory as
-//        128 rows (pixels) x 128 bytes with SWIZZLE_128B = the canonical K-major
-//        UMMA operand layout.
+//   A  : im2col-free.  The activation tensor is a 4-D TMA tensor (C, W, H, N);
+//        for tap (ky,kx) and channel block kb the producer issues ONE box load
+//        {32 ch, TW*s, TH*s, 1} with element strides {1,s,s,1} at
+//        (kb*32, x0*s+(kx-1)*dil, y0*s+(ky-1)*dil, n): TMA walks the strided
+//        window itself (stride-2 convs cost nothing extra) and its out-of-bounds
+//        zero fill IS the convolution's zero padding (and the K remainder when
+//        Cin % 32 != 0).  The box lands in shared memory as 128 rows (pixels) x
+//        128 bytes with SWIZZLE_128B = the canonical K-major UMMA operand.
 //   B  : weights pre-packed [tap][cout_pad16][cin_pad32]; box {32, BN, 1}.
 //   D  : TMEM, 128 lanes (pixels) x BN columns (output channels), fp32.
 //   pipeline: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread,
@@ -22,8 +24,13 @@
 //        -> 16-byte stores into the output channel slice).  smem full/empty
 //        mbarriers ring over NSTAGE stages; tcgen05.commit releases stages and
 //        publishes the accumulator.
-//   Two CTAs are resident per SM so one CTA's epilogue overlaps the other's
-//   main loop.
+//   small grids (the 1/64..1/16 pyramid levels have 2..30 pixel tiles for 148
+//        SMs): the K loop is split over a THREAD-BLOCK CLUSTER of S<=8 CTAs
+//        (grid z).  Each CTA parks its partial accumulator tile in its own
+//        shared memory; after a cluster barrier every CTA reduces 128/S rows by
+//        reading its peers' tiles through distributed shared memory in rank
+//        order (bitwise reproducible, no global scratch, no atomics) and runs
+//        the epilogue for those rows.
 #include "upf_common.cuh"
 
 #include <cuda.h>
@@ -101,17 +108,52 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank) {
+  uint32_t remote;
+  float4 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
+  return v;
+}
 
 struct TcParams {
   float* out; int ldo;
   const float* res; int ldr;
   const float* bias;
-  int H, W, Cout, BN;          // BN = cout padded to 16
+  int Ho, Wo, Cout, BN;        // output size; BN = N tile (multiple of 16, <= 128)
   int TH, TW, tiles_x, tiles_y;
-  int ks, dil, kblocks;        // kblocks = ceil(Cin/32)
+  int ks, dil, stride, kblocks; // kblocks = ceil(Cin/32)
   int nstage, tmem_cols;
+  int splits, ips;             // K split over a cluster of `splits` CTAs, `ips` iterations each
   float slope;
 };
+
+// bias + LeakyReLU (+ residual) and the store of 4 consecutive output channels of one pixel
+__device__ __forceinline__ void store4(const TcParams& p, float* o, const float* r, int co, float4 f, bool vec_out) {
+  float v[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (co + j < p.Cout) {
+      float a = lrelu(v[j] + __ldg(p.bias + co + j), p.slope);
+      if (r) a += __ldg(r + co + j);
+      v[j] = a;
+    }
+  if (vec_out && co + 4 <= p.Cout) {
+    *reinterpret_cast<float4*>(o + co) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (co + j < p.Cout) o[co + j] = v[j];
+  }
+}
 
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
@@ -131,10 +173,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   const int tx = tile % p.tiles_x; tile /= p.tiles_x;
   const int ty = tile % p.tiles_y;
   const int n = tile / p.tiles_y;
-  const int x0 = tx * p.TW, y0 = ty * p.TH;
-  const int co0 = blockIdx.y * p.BN;            // first output channel of this CTA's N tile
+  const int x0 = tx * p.TW, y0 = ty * p.TH;      // output-pixel origin of this tile
+  const int co0 = blockIdx.y * p.BN;             // first output channel of this CTA's N tile
   const int taps = p.ks * p.ks;
-  const int iters = taps * p.kblocks;
+  const int iters_all = taps * p.kblocks;
+  const int it_begin = blockIdx.z * p.ips;
+  const int iters = (iters_all - it_begin < p.ips ? iters_all - it_begin : p.ips);   // >= 1 by construction
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -155,27 +199,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
+  const bool vec_out = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+  const int pitch = p.BN + 4;                    // floats per row of the parked partial tile (bank-conflict free)
+  float* part = reinterpret_cast<float*>(base);  // overlays the (drained) pipeline stages
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       const int half = (p.ks - 1) / 2;
-      int it = 0;
-      for (int tap = 0; tap < taps; ++tap) {
+      for (int it = 0; it < iters; ++it) {
+        const int g = it_begin + it;
+        const int tap = g / p.kblocks, kb = g - tap * p.kblocks;
         const int ky = tap / p.ks, kx = tap - ky * p.ks;
-        const int cy = y0 + (ky - half) * p.dil, cx = x0 + (kx - half) * p.dil;
-        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-          const int s = it % p.nstage;
-          const uint32_t ph = (uint32_t)(it / p.nstage) & 1u;
-          mbar_wait(smem_u32(&empty[s]), ph ^ 1u);            // slot free (first pass returns at once)
-          const uint32_t a_dst = smem_u32(base + (size_t)s * stage_bytes);
-          const uint32_t b_dst = a_dst + TC_A_BYTES;
-          const uint32_t fb = smem_u32(&full[s]);
-          mbar_expect_tx(fb, TC_A_BYTES + b_bytes);
-          tma_load_4d(a_dst, &map_x, fb, kb * TC_KC, cx, cy, n);
-          tma_load_3d(b_dst, &map_w, fb, kb * TC_KC, co0, tap);
-        }
+        const int cy = y0 * p.stride + (ky - half) * p.dil, cx = x0 * p.stride + (kx - half) * p.dil;
+        const int s = it % p.nstage;
+        const uint32_t ph = (uint32_t)(it / p.nstage) & 1u;
+        mbar_wait(smem_u32(&empty[s]), ph ^ 1u);            // slot free (first pass returns at once)
+        const uint32_t a_dst = smem_u32(base + (size_t)s * stage_bytes);
+        const uint32_t b_dst = a_dst + TC_A_BYTES;
+        const uint32_t fb = smem_u32(&full[s]);
+        mbar_expect_tx(fb, TC_A_BYTES + b_bytes);
+        tma_load_4d(a_dst, &map_x, fb, kb * TC_KC, cx, cy, n);
+        tma_load_3d(b_dst, &map_w, fb, kb * TC_KC, co0, tap);
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // instruction descriptor: D=f32 (bit4), A=B=TF32 (2<<7, 2<<10), K-major both, N>>3 @17, M>>4 @24
@@ -201,43 +249,68 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                                    // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;                             // pixel index inside the tile
-    const int py = y0 + row / p.TW, px = x0 + row % p.TW;
-    const bool valid = (py < p.H) && (px < p.W);
-    const size_t pix = ((size_t)n * p.H + py) * p.W + px;
-    float* o = p.out + pix * p.ldo;
-    const float* r = p.res ? p.res + pix * p.ldr : nullptr;
-    const bool vec_out = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     mbar_wait(smem_u32(accum_full), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (valid) {
-        float f[16];
+    if (p.splits == 1) {
+      const int py = y0 + row / p.TW, px = x0 + row % p.TW;
+      const bool valid = (py < p.Ho) && (px < p.Wo);
+      const size_t pix = ((size_t)n * p.Ho + py) * p.Wo + px;
+      float* o = p.out + pix * p.ldo;
+      const float* r = p.res ? p.res + pix * p.ldr : nullptr;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (valid) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int co = co0 + c0 + j;
-          float acc = __uint_as_float(v[j]);
-          if (co < p.Cout) {
-            acc = lrelu(acc + __ldg(p.bias + co), p.slope);
-            if (r) acc += __ldg(r + co);
-          }
-          f[j] = acc;
+          for (int j = 0; j < 16; j += 4)
+            store4(p, o, r, co0 + c0 + j, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                      __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), vec_out);
         }
-        if (vec_out && co0 + c0 + 16 <= p.Cout) {
+      }
+    } else {
+      // park the partial accumulator tile in this CTA's shared memory (the stages are drained: every TMA load
+      // was consumed and the last MMA has retired)
+      float* mine = part + row * pitch;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + co0 + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (co0 + c0 + j < p.Cout) o[co0 + c0 + j] = f[j];
-        }
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(mine + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
-  __syncthreads();
+
+  if (p.splits > 1) {
+    // ---- cluster reduction through distributed shared memory, rank order (deterministic)
+    cluster_sync_all();
+    const int rank = (int)cluster_ctarank();
+    const int rows_per = 128 / p.splits;
+    const int c4n = p.BN >> 2;
+    const uint32_t part_addr = smem_u32(part);
+    for (int u = threadIdx.x; u < rows_per * c4n; u += TC_THREADS) {
+      const int rl = u / c4n, c4 = u - rl * c4n;
+      const int row = rank * rows_per + rl;
+      const uint32_t off = part_addr + (uint32_t)(row * pitch + c4 * 4) * 4u;
+      float4 acc = ld_dsmem_f4(off, 0);
+      for (int sp = 1; sp < p.splits; ++sp) {
+        const float4 t = ld_dsmem_f4(off, (uint32_t)sp);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+      const int py = y0 + row / p.TW, px = x0 + row % p.TW;
+      if (py < p.Ho && px < p.Wo) {
+        const size_t pix = ((size_t)n * p.Ho + py) * p.Wo + px;
+        store4(p, p.out + pix * p.ldo, p.res ? p.res + pix * p.ldr : nullptr, co0 + c4 * 4, acc, vec_out);
+      }
+    }
+    cluster_sync_all();          // nobody leaves while a peer may still read its tile
+  } else {
+    __syncthreads();
+  }
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -291,13 +364,12 @@ static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 static int encode_cached(const MapKey& key, CUtensorMap* out, cuuint32_t rank, void* ptr, const cuuint64_t* dims,
-                         const cuuint64_t* strides, const cuuint32_t* box) {
+                         const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr) {
   std::lock_guard<std::mutex> lk(g_map_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return 0; }
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled not available"); return UPF_EDRIVER; }
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return UPF_EDRIVER; }
@@ -306,10 +378,10 @@ static int encode_cached(const MapKey& key, CUtensorMap* out, cuuint32_t rank, v
   return 0;
 }
 
-static void pick_tile(int H, int W, int* TH, int* TW) {
+static void pick_tile(int H, int W, int max_tw, int* TH, int* TW) {
   // 128 pixels per tile; pick the shape (TW multiple of 8) wasting the fewest pixels
   long long best = -1;
-  for (int tw = 8; tw <= 128; tw <<= 1) {
+  for (int tw = 8; tw <= max_tw; tw <<= 1) {
     const int th = 128 / tw;
     const long long cover = (long long)((H + th - 1) / th) * ((W + tw - 1) / tw);
     if (best < 0 || cover < best || (cover == best && tw == 16)) { best = cover; *TH = th; *TW = tw; }
@@ -317,9 +389,14 @@ static void pick_tile(int H, int W, int* TH, int* TW) {
 }
 
 int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
-                  const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int dil, float slope,
-                  cudaStream_t st) {
+                  const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
+                  float slope, cudaStream_t st) {
   UPF_REQUIRE((ldx % 4) == 0 && aligned16(x) && aligned16(w_packed), "conv_tc: input pitch/pointer must be 16-byte aligned");
+  UPF_REQUIRE(stride == 1 || stride == 2, "conv_tc: stride %d not in {1,2}", stride);
+  const int pad = ((ks - 1) * dil) / 2;
+  const int Ho = (H + 2 * pad - dil * (ks - 1) - 1) / stride + 1;
+  const int Wo = (W + 2 * pad - dil * (ks - 1) - 1) / stride + 1;
+  UPF_REQUIRE(Ho > 0 && Wo > 0, "conv_tc: empty output");
   const int cout_pad = (Cout + 15) & ~15;
   const int ntiles_n = (cout_pad + 127) / 128;
   const int BN = ((cout_pad + ntiles_n - 1) / ntiles_n + 15) & ~15;   // equal N tiles <= 128 wide (rows past cout_pad: TMA zero fill)
@@ -327,38 +404,54 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   const int cin_pad = kblocks * TC_KC;
   const int taps = ks * ks;
   int TH = 8, TW = 16;
-  pick_tile(H, W, &TH, &TW);
+  pick_tile(Ho, Wo, 256 / stride > 128 ? 128 : 256 / stride, &TH, &TW);   // TMA box extents are <= 256 elements
 
   CUtensorMap mx, mw;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
-    const cuuint32_t box[4] = {TC_KC, (cuuint32_t)TW, (cuuint32_t)TH, 1};
-    MapKey key{x, ldx, ((long long)H << 32) | (unsigned)W, ((long long)N << 32) | (unsigned)Cin, TW, 4};
-    int e = encode_cached(key, &mx, 4, const_cast<float*>(x), dims, strides, box);
+    const cuuint32_t box[4] = {TC_KC, (cuuint32_t)(TW * stride), (cuuint32_t)(TH * stride), 1};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    MapKey key{x, ldx, ((long long)H << 32) | (unsigned)W, ((long long)N << 32) | (unsigned)Cin, TW * 4 + stride, 4};
+    int e = encode_cached(key, &mx, 4, const_cast<float*>(x), dims, strides, box, estr);
     if (e) return e;
   }
   {
     const cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)taps};
     const cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 4, (cuuint64_t)cin_pad * cout_pad * 4};
     const cuuint32_t box[3] = {TC_KC, (cuuint32_t)BN, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
     MapKey key{w_packed, cin_pad, BN, taps, cout_pad, 3};
-    int e = encode_cached(key, &mw, 3, const_cast<float*>(w_packed), dims, strides, box);
+    int e = encode_cached(key, &mw, 3, const_cast<float*>(w_packed), dims, strides, box, estr);
     if (e) return e;
   }
 
   TcParams p;
   p.out = out; p.ldo = ldo; p.res = res; p.ldr = ldr; p.bias = bias;
-  p.H = H; p.W = W; p.Cout = Cout; p.BN = BN;
-  p.TH = TH; p.TW = TW; p.tiles_x = (W + TW - 1) / TW; p.tiles_y = (H + TH - 1) / TH;
-  p.ks = ks; p.dil = dil; p.kblocks = kblocks;
+  p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.BN = BN;
+  p.TH = TH; p.TW = TW; p.tiles_x = (Wo + TW - 1) / TW; p.tiles_y = (Ho + TH - 1) / TH;
+  p.ks = ks; p.dil = dil; p.stride = stride; p.kblocks = kblocks;
   p.slope = slope;
   p.tmem_cols = BN <= 32 ? 32 : (BN <= 64 ? 64 : 128);
   const int stage_bytes = TC_A_BYTES + ((BN * 128 + 1023) & ~1023);
-  int nstage = (108 * 1024) / stage_bytes;       // two CTAs per SM
-  if (nstage > 6) nstage = 6;
+  const long long tiles = (long long)p.tiles_x * p.tiles_y * N;
+  const long long ctas = tiles * ntiles_n;
+  // split-K over a cluster when the grid cannot fill the chip: the K loop (taps x channel blocks) is the only
+  // parallelism left at the coarse pyramid levels
+  const int iters_all = taps * kblocks;
+  int splits = 1;
+  while (splits < 8 && ctas * splits * 2 <= 2 * UPF_NUM_SMS && iters_all / (splits * 2) >= 3) splits *= 2;
+  int ips = (iters_all + splits - 1) / splits;
+  while (splits > 1 && (splits - 1) * ips >= iters_all) { splits >>= 1; ips = (iters_all + splits - 1) / splits; }   // no empty CTA
+  // stages: two CTAs per SM when the grid is large (epilogue/main-loop overlap across CTAs); a single
+  // resident CTA gets the whole shared memory so that more TMA loads are in flight (latency-bound regime)
+  const bool one_cta = ctas * splits <= 2 * UPF_NUM_SMS;
+  int nstage = ((one_cta ? 200 : 108) * 1024) / stage_bytes;
+  if (nstage > (one_cta ? 12 : 6)) nstage = one_cta ? 12 : 6;
   if (nstage < 2) nstage = 2;
+  if (splits > 1 && (long long)nstage * stage_bytes < 128ll * (BN + 4) * 4) { splits = 1; ips = iters_all; }
   p.nstage = nstage;
+  p.splits = splits; p.ips = ips;
   const size_t smem = (size_t)nstage * stage_bytes + (2 * nstage + 2) * 8 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -366,8 +459,20 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
     if (e != cudaSuccess) { set_error("conv_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
-  const long long tiles = (long long)p.tiles_x * p.tiles_y * N;
-  conv_tc_kernel<<<dim3((unsigned)tiles, (unsigned)ntiles_n), TC_THREADS, smem, st>>>(mx, mw, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)tiles, (unsigned)ntiles_n, (unsigned)splits);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = (unsigned)splits;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel, mx, mw, p);
+  if (e != cudaSuccess) { set_error("conv_tc launch: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return (int)e; }
   return check_launch("conv_tc");
 }
 

@@ -39,59 +39,73 @@ struct CorrCfg {
   static constexpr int NWARPS = WIN;
   static constexpr int NT = NWARPS * 32;
   static constexpr int HROWS = CORR_TY + 2 * D;
-  static constexpr int HCOLS = CORR_TX + 2 * D;
+  static constexpr int HCOLS = (CORR_TX + 2 * D + 7) & ~7;   // multiple of 8: the swizzle phase of a column is row-independent
   static constexpr int HPOS = HROWS * HCOLS;
   static constexpr int F1POS = CORR_TX * CORR_TY;
   static constexpr int NOUT = WIN * WIN;
   static constexpr int STAGE_BYTES = (HPOS + F1POS) * CORR_CC * 4;
   static constexpr int OUT_BYTES = F1POS * NOUT * 4;
   static constexpr int SMEM_BYTES = (STAGE_BYTES > OUT_BYTES ? STAGE_BYTES : OUT_BYTES) + 4 * CORR_CC * 4;
+  static constexpr int MIN_CTAS = (2 * (SMEM_BYTES + 1024) <= 233472 && 2 * NT <= 1024) ? 2 : 1;
 };
 
 __device__ __forceinline__ int swz(int pos, int chunk) { return pos * 32 + (((chunk ^ pos) & 7) << 2); }  // float index
 
-// stage `npos` positions x 32 channels of one operand into swizzled smem
-template <int NT, bool VEC>
+// stage `npos` positions x 32 channels of one operand into swizzled smem.  Loads are issued in batches of
+// CORR_LB per thread before any is consumed (memory-level parallelism); the normalisation (x-mean)*rstd
+// is applied in registers; out-of-image positions and channels >= C are written as zeros (= the zero
+// padding of the correlation AFTER normalisation, as in the reference).
+constexpr int CORR_LB = 4;
+template <int NT, int COLS, bool VEC>
 __device__ __forceinline__ void corr_stage(float* __restrict__ dst, const float* __restrict__ src, int ld,
-                                           int n, int H, int W, int C, int c0, int y_org, int x_org, int cols,
-                                           int npos, const float* __restrict__ mean, const float* __restrict__ stdv,
+                                           int n, int H, int W, int C, int c0, int y_org, int x_org,
+                                           int npos, const float* __restrict__ mean, const float* __restrict__ rstd,
                                            bool norm) {
   const int units = npos * 8;
-  for (int u = threadIdx.x; u < units; u += NT) {
-    const int pos = u >> 3, chunk = u & 7;
-    const int r = pos / cols, cidx = pos - r * cols;
-    const int y = y_org + r, x = x_org + cidx;
-    const int c = c0 + chunk * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (y >= 0 && y < H && x >= 0 && x < W && c < C) {
-      const float* p = src + ((size_t)((size_t)n * H + y) * W + x) * ld + c;
-      if (VEC) {
-        v = ldg4(p);
-      } else {
-        v.x = __ldg(p);
-        if (c + 1 < C) v.y = __ldg(p + 1);
-        if (c + 2 < C) v.z = __ldg(p + 2);
-        if (c + 3 < C) v.w = __ldg(p + 3);
-      }
-      if (norm) {
-        const int k = chunk * 4;
-        v.x = __fdiv_rn(__fsub_rn(v.x, mean[k + 0]), stdv[k + 0]);
-        v.y = __fdiv_rn(__fsub_rn(v.y, mean[k + 1]), stdv[k + 1]);
-        v.z = __fdiv_rn(__fsub_rn(v.z, mean[k + 2]), stdv[k + 2]);
-        v.w = __fdiv_rn(__fsub_rn(v.w, mean[k + 3]), stdv[k + 3]);
-        if (!VEC) {  // channels past C must stay exactly zero
-          if (c + 1 >= C) v.y = 0.f;
-          if (c + 2 >= C) v.z = 0.f;
-          if (c + 3 >= C) v.w = 0.f;
+  const float* img = src + (size_t)n * H * W * ld;
+  for (int u0 = threadIdx.x; u0 < units; u0 += NT * CORR_LB) {
+    float4 v[CORR_LB];
+    bool ok[CORR_LB];
+#pragma unroll
+    for (int i = 0; i < CORR_LB; ++i) {
+      const int u = u0 + i * NT;
+      const int pos = u >> 3, chunk = u & 7;
+      const int r = pos / COLS, cidx = pos - r * COLS;
+      const int y = y_org + r, x = x_org + cidx;
+      const int c = c0 + chunk * 4;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ok[i] = u < units && y >= 0 && y < H && x >= 0 && x < W && c < C;
+      if (ok[i]) {
+        const float* p = img + ((size_t)y * W + x) * ld + c;
+        if (VEC) {
+          v[i] = ldg4(p);
+        } else {
+          v[i].x = __ldg(p);
+          if (c + 1 < C) v[i].y = __ldg(p + 1);
+          if (c + 2 < C) v[i].z = __ldg(p + 2);
+          if (c + 3 < C) v[i].w = __ldg(p + 3);
         }
       }
     }
-    *reinterpret_cast<float4*>(dst + swz(pos, chunk)) = v;
+#pragma unroll
+    for (int i = 0; i < CORR_LB; ++i) {
+      const int u = u0 + i * NT;
+      const int pos = u >> 3, chunk = u & 7;
+      if (norm && ok[i]) {
+        const int k = chunk * 4;
+        const int c = c0 + k;
+        v[i].x = __fmul_rn(__fsub_rn(v[i].x, mean[k + 0]), rstd[k + 0]);
+        v[i].y = (VEC || c + 1 < C) ? __fmul_rn(__fsub_rn(v[i].y, mean[k + 1]), rstd[k + 1]) : 0.f;
+        v[i].z = (VEC || c + 2 < C) ? __fmul_rn(__fsub_rn(v[i].z, mean[k + 2]), rstd[k + 2]) : 0.f;
+        v[i].w = (VEC || c + 3 < C) ? __fmul_rn(__fsub_rn(v[i].w, mean[k + 3]), rstd[k + 3]) : 0.f;
+      }
+      if (u < units) *reinterpret_cast<float4*>(dst + swz(pos, chunk)) = v[i];
+    }
   }
 }
 
 template <int D, bool VEC>
-__global__ void __launch_bounds__(CorrCfg<D>::NT, (D <= 4 ? 2 : 1))
+__global__ void __launch_bounds__(CorrCfg<D>::NT, CorrCfg<D>::MIN_CTAS)
 corr_fwd_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__ f2, int ld2,
                 float* __restrict__ out, int ldo, int H, int W, int C,
                 const double* __restrict__ stats1, const double* __restrict__ stats2,
@@ -100,7 +114,7 @@ corr_fwd_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__
   extern __shared__ __align__(128) float smem[];
   float* s_f2 = smem;
   float* s_f1 = smem + K::HPOS * CORR_CC;
-  float* s_stat = smem + (K::SMEM_BYTES / 4 - 4 * CORR_CC);   // mean1,std1,mean2,std2 of the current chunk
+  float* s_stat = smem + (K::SMEM_BYTES / 4 - 4 * CORR_CC);   // mean1,rstd1,mean2,rstd2 of the current chunk
   float* s_out = smem;                                        // overlays the staging area
 
   int tile = blockIdx.x;
@@ -119,34 +133,42 @@ corr_fwd_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__
 #pragma unroll
     for (int q = 0; q < K::WIN; ++q) acc[p][q] = 0.f;
 
+  // shared-memory read addresses: position = row*COLS + column with COLS % 8 == 0, so the XOR phase
+  // depends on the column only and every row is a compile-time offset
+  const int col2 = lane + dxi;
+  const float* a_base = s_f1 + lane * 32;
+  const float* b_base = s_f2 + col2 * 32;
+
   for (int c0 = 0; c0 < C; c0 += CORR_CC) {
     if (c0 > 0) __syncthreads();          // previous pass finished reading the stage
     if (norm) {
       if (threadIdx.x < 2 * CORR_CC) {
         const int which = threadIdx.x >> 5, k = threadIdx.x & 31, c = c0 + k;
-        float m = 0.f, s = 1.f;
-        if (c < C) stats_to_mean_std((which ? stats2 + ((size_t)n2 * C + c) * 2 : stats1 + ((size_t)n * C + c) * 2), npix, m, s);
+        float m = 0.f, sd = 1.f;
+        if (c < C) stats_to_mean_std((which ? stats2 + ((size_t)n2 * C + c) * 2 : stats1 + ((size_t)n * C + c) * 2), npix, m, sd);
         s_stat[which * 2 * CORR_CC + k] = m;
-        s_stat[which * 2 * CORR_CC + CORR_CC + k] = s;
+        // (x-mean)*(1/std): within 1 ulp of the reference's (x-mean)/std; 1/std itself is a correctly rounded division
+        s_stat[which * 2 * CORR_CC + CORR_CC + k] = __fdiv_rn(1.0f, sd);
       }
       __syncthreads();
     }
-    corr_stage<K::NT, VEC>(s_f2, f2, ld2, n2, H, W, C, c0, y0 - D, x0 - D, K::HCOLS, K::HPOS,
-                           s_stat + 2 * CORR_CC, s_stat + 3 * CORR_CC, norm);
-    corr_stage<K::NT, VEC>(s_f1, f1, ld1, n, H, W, C, c0, y0, x0, CORR_TX, K::F1POS,
-                           s_stat, s_stat + CORR_CC, norm);
+    corr_stage<K::NT, K::HCOLS, VEC>(s_f2, f2, ld2, n2, H, W, C, c0, y0 - D, x0 - D, K::HPOS,
+                                     s_stat + 2 * CORR_CC, s_stat + 3 * CORR_CC, norm);
+    corr_stage<K::NT, CORR_TX, VEC>(s_f1, f1, ld1, n, H, W, C, c0, y0, x0, K::F1POS, s_stat, s_stat + CORR_CC, norm);
     __syncthreads();
 
     const int cend = (C - c0 < CORR_CC ? C - c0 : CORR_CC);
     const int nchunk = (cend + 3) >> 2;
+#pragma unroll 1
     for (int ch = 0; ch < nchunk; ++ch) {
+      const float* ap = a_base + (((ch ^ lane) & 7) << 2);
+      const float* bp = b_base + (((ch ^ col2) & 7) << 2);
       float4 a[CORR_TY];
 #pragma unroll
-      for (int p = 0; p < CORR_TY; ++p)
-        a[p] = *reinterpret_cast<const float4*>(s_f1 + swz(p * CORR_TX + lane, ch));
+      for (int p = 0; p < CORR_TY; ++p) a[p] = *reinterpret_cast<const float4*>(ap + p * CORR_TX * 32);
 #pragma unroll
       for (int j = 0; j < K::HROWS; ++j) {
-        const float4 b = *reinterpret_cast<const float4*>(s_f2 + swz(j * K::HCOLS + lane + dxi, ch));
+        const float4 b = *reinterpret_cast<const float4*>(bp + j * K::HCOLS * 32);
 #pragma unroll
         for (int p = 0; p < CORR_TY; ++p) {
           const int dyi = j - p;
@@ -164,30 +186,35 @@ corr_fwd_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__
   }
   __syncthreads();   // staging area is dead: reuse it for the output transpose
 
-  // mean over channels (torch.mean, utils/pytorch_correlation.py:47): exact
-  // reciprocal when C is a power of two, true division otherwise
-  const bool pow2 = (C & (C - 1)) == 0;
-  const float inv = 1.0f / (float)C, fC = (float)C;
+  // mean over channels (torch.mean = sum / C, utils/pytorch_correlation.py:47): q = s*(1/C) followed by one
+  // Newton correction is the correctly rounded quotient (exact product when C is a power of two)
+  const float fC = (float)C, inv = __fdiv_rn(1.0f, fC);
 #pragma unroll
   for (int p = 0; p < CORR_TY; ++p)
 #pragma unroll
     for (int q = 0; q < K::WIN; ++q) {
-      float v = pow2 ? acc[p][q] * inv : __fdiv_rn(acc[p][q], fC);
+      const float s = acc[p][q];
+      float v = __fmul_rn(s, inv);
+      v = __fmaf_rn(__fmaf_rn(-v, fC, s), inv, v);
       s_out[(p * CORR_TX + lane) * K::NOUT + q * K::WIN + dxi] = lrelu(v, slope);
     }
   __syncthreads();
 
   // coalesced store: each tile row is 32 pixels x NOUT contiguous floats (pitch ldo)
+  const int wvalid = (W - x0 < CORR_TX ? W - x0 : CORR_TX);
+  const int total = wvalid * K::NOUT;
   for (int r = 0; r < CORR_TY; ++r) {
     const int y = y0 + r;
     if (y >= H) break;
-    const int wvalid = (W - x0 < CORR_TX ? W - x0 : CORR_TX);
     float* orow = out + ((size_t)((size_t)n * H + y) * W + x0) * ldo;
     const float* srow = s_out + r * CORR_TX * K::NOUT;
-    const int total = wvalid * K::NOUT;
-    for (int e = threadIdx.x; e < total; e += K::NT) {
-      const int px = e / K::NOUT, k = e - px * K::NOUT;
-      orow[(size_t)px * ldo + k] = srow[e];
+    if (ldo == K::NOUT) {
+      for (int e = threadIdx.x; e < total; e += K::NT) orow[e] = srow[e];       // one contiguous run
+    } else {
+      for (int e = threadIdx.x; e < total; e += K::NT) {
+        const int px = e / K::NOUT, k = e - px * K::NOUT;
+        orow[(size_t)px * ldo + k] = srow[e];
+      }
     }
   }
 }
@@ -207,7 +234,12 @@ static int launch_corr_fwd(const float* f1, int ld1, const float* f2, int ld2, f
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(corr_fwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
     if (e == cudaSuccess)
-      attr_done = true;
+      e = cudaFuncSetAttribute(corr_fwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("corr smem attr: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_done = true;
   }
   if (vec) {
     corr_fwd_kernel<D, true><<<(unsigned)tiles, K::NT, K::SMEM_BYTES, st>>>(f1, ld1, f2, ld2, out, ldo, H, W, C, s1, s2,

@@ -61,7 +61,8 @@ class ConvSpec:
         self.cin = cin_total or weight.shape[1]
         self.stride, self.dil = stride, dil
         self.slope = SLOPE if relu else 1.0
-        self.w, self.w_tc = ops.pack_conv_weight(weight, in_slots, cin_total, tc=tc and stride == 1)
+        # tensor cores for everything but the 3-channel image convs (K = 27: one quarter-empty K block per tap)
+        self.w, self.w_tc = ops.pack_conv_weight(weight, in_slots, cin_total, tc=tc and stride in (1, 2) and self.cin >= 16)
         self.bias = bias.detach().float().contiguous()
 
 
@@ -122,7 +123,7 @@ class DecoderEngine:
 
     # ------------------------------------------------------------ helpers
     def _conv(self, cs, x, out, residual=None):
-        use_tc = self.tc and cs.w_tc is not None and cs.stride == 1
+        use_tc = self.tc and cs.w_tc is not None
         ops.k_conv(x, cs.w_tc if use_tc else cs.w, cs.bias, out, cs.k, cs.stride, cs.dil, cs.slope, residual,
                    _ext.CONV_TF32 if use_tc else _ext.CONV_FP32)
 
