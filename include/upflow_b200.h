@@ -144,6 +144,12 @@ int upf_conv2d_fwd(const float* x, int ldx, const float* w, const float* bias,
 long long upf_conv_tc_packed_elems(int Cin, int Cout, int ksize);
 int upf_conv_tc_pack_weights(const float* w_simt, float* w_packed, int Cin, int Cout, int ksize, void* stream);
 
+/* test / tuning hook, not part of the hot path: enable the shared-halo tensor-core kernel (conv_halo.cu) and pick
+ * its shared-memory-descriptor base-offset convention; returns 0. */
+int upf_debug_conv_halo(int enabled, int bo_mode);
+/* debug: device buffer of 8 int64 receiving CTA 0's per-role wait / busy cycle counters of the halo kernel (NULL = off) */
+int upf_debug_probe(void* device_buffer_8x_int64);
+
 /* layout helpers for callers holding NCHW-contiguous tensors (the reference's
  * layout): strided copy between [N,C,H,W] planes and pixel-major rows. */
 int upf_nchw_to_nhwc(const float* in, float* out, int ldo, int N, int C, int H, int W, void* stream);

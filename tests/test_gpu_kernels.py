@@ -48,7 +48,12 @@ def test_corr_golden(upf, golden):
 @pytest.mark.parametrize("layout", ["nchw", "channels_last"])
 @pytest.mark.parametrize("shape,d", [((2, 32, 47, 156), 4), ((1, 64, 24, 78), 4), ((2, 128, 12, 39), 4),
                                      ((1, 96, 33, 70), 4), ((1, 32, 40, 100), 2), ((1, 32, 37, 65), 6),
-                                     ((1, 7, 9, 33), 3), ((1, 32, 3, 2), 4)])
+                                     ((1, 7, 9, 33), 3), ((1, 32, 3, 2), 4),
+                                     # > 16384 pixels: the tiled shared-memory kernel (smaller images take the
+                                     # one-CTA-per-pixel kernel)
+                                     ((1, 32, 130, 140), 4), ((2, 64, 100, 100), 4), ((1, 96, 128, 131), 2),
+                                     ((1, 32, 129, 130), 6), ((1, 7, 129, 130), 3), ((1, 196, 128, 129), 4),
+                                     ((1, 32, 150, 120), 1), ((1, 36, 140, 120), 5)])
 def test_corr_vs_oracle(upf, shape, d, layout):
     f1, f2 = _regen(1, shape), _regen(2, shape)
     a, b = _cuda(f1), _cuda(f2)

@@ -1,0 +1,32 @@
+"""A/B timing of the whole KITTI forward (CUDA-graph replay, L2 flushed per step) under conv dispatch variants,
+on ONE box in ONE process.  python tools/ab_forward.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from upflow_pytorch_b200 import _ext
+from upflow_pytorch_b200.engine import DecoderEngine
+lib = _ext.load()
+H, W, B = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "kitti_375x1242_b1"]
+sd = bench.make_weights()
+im1, im2 = bench.synth_inputs(B, H, W, 1234)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+variants = [("halo off", 0, 1 << 16), ("halo Cin>=512", 1, 513 << 16), ("halo Cin>=384", 1, 385 << 16), ("halo Cin>=192", 1, 193 << 16),
+            ("halo Cin>=128", 1, 129 << 16), ("halo Cin>=64", 1, 65 << 16), ("halo all", 1, 1 << 16)]
+for rep in range(2):
+    for name, en, mode in variants:
+        lib.upf_debug_conv_halo(en, mode | (128 << 8))
+        eng = DecoderEngine({k: v.cuda() for k, v in sd.items()}, precision="tf32")
+        with torch.no_grad():
+            g = eng.capture(B, H, W)
+        g.im1.copy_(im1.cuda()); g.im2.copy_(im2.cuda())
+        for _ in range(5):
+            g.replay()
+        ts = []
+        for _ in range(20):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        print("%-16s median %.3f ms  min %.3f ms  (%.1f pairs/s)" % (name, ts[len(ts) // 2], ts[0], B * 1e3 / ts[len(ts) // 2]), flush=True)

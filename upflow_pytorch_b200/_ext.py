@@ -30,6 +30,8 @@ SIGNATURES = {
     "upf_conv2d_fwd": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P]),
     "upf_conv_tc_packed_elems": (_LL, [_I, _I, _I]),
     "upf_conv_tc_pack_weights": (_I, [_P, _P, _I, _I, _I, _P]),
+    "upf_debug_conv_halo": (_I, [_I, _I]),
+    "upf_debug_probe": (_I, [_P]),
     "upf_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "upf_nhwc_to_nchw": (_I, [_P, _I, _P, _I, _I, _I, _I, _P]),
     "upf_copy_channels": (_I, [_P, _I, _P, _I, _LL, _I, _P]),

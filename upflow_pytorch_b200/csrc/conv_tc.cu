@@ -31,9 +31,8 @@
 //        reading its peers' tiles through distributed shared memory in rank
 //        order (bitwise reproducible, no global scratch, no atomics) and runs
 //        the epilogue for those rows.
-#include "upf_common.cuh"
+#include "tc_common.cuh"
 
-#include <cuda.h>
 #include <mutex>
 #include <unordered_map>
 
@@ -42,87 +41,6 @@ namespace upf {
 constexpr int TC_THREADS = 192;
 constexpr int TC_KC = 32;               // channels per K block (128 B of fp32)
 constexpr int TC_A_BYTES = 128 * 128;   // 128 pixels x 128 B
-
-// ---------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t"
-      "}" : "=r"(pred));
-  return pred != 0;
-}
-// K-major, SWIZZLE_128B shared-memory operand descriptor (rows of 128 B, 8-row
-// atoms 1024 B apart): start>>4 | LBO(unused for swizzled K-major)=1 | SBO=1024>>4 |
-// version=1 (sm_100) | layout_type=2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank) {
-  uint32_t remote;
-  float4 v;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
-  return v;
-}
 
 struct TcParams {
   float* out; int ldo;
@@ -133,16 +51,19 @@ struct TcParams {
   int ks, dil, stride, kblocks; // kblocks = ceil(Cin/32)
   int nstage, tmem_cols;
   int splits, ips;             // K split over a cluster of `splits` CTAs, `ips` iterations each
+  // every operand tile is fetched as several small TMA boxes (bw x bh output pixels / b_rows weight rows each):
+  // one box is walked row by row (~10 ns per 128-byte row, measured), independent boxes proceed concurrently
+  int bw, bh, nbx, nby, b_rows, nbb;
   float slope;
 };
 
 // bias + LeakyReLU (+ residual) and the store of 4 consecutive output channels of one pixel
-__device__ __forceinline__ void store4(const TcParams& p, float* o, const float* r, int co, float4 f, bool vec_out) {
+__device__ __forceinline__ void store4(const TcParams& p, const float* s_bias, int co0, float* o, const float* r, int co, float4 f, bool vec_out) {
   float v[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     if (co + j < p.Cout) {
-      float a = lrelu(v[j] + __ldg(p.bias + co + j), p.slope);
+      float a = lrelu(v[j] + s_bias[co + j - co0], p.slope);
       if (r) a += __ldg(r + co + j);
       v[j] = a;
     }
@@ -159,7 +80,9 @@ __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages: A | B] ... then barriers
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (a uintptr_t round trip would turn every later
+  // access into a generic-address load: measured 4x slower epilogue)
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t b_bytes = (uint32_t)p.BN * 128u;
   const uint32_t stage_bytes = TC_A_BYTES + ((b_bytes + 1023u) & ~1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)p.nstage * stage_bytes);
@@ -167,6 +90,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   uint64_t* empty = bars + p.nstage;           // [nstage]
   uint64_t* accum_full = bars + 2 * p.nstage;  // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.nstage + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);      // [BN]: the L1 is tiny next to ~100-200 KB of shared memory
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int tile = blockIdx.x;
@@ -189,6 +113,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     }
     mbar_init(smem_u32(accum_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x >= 64 && (int)threadIdx.x - 64 < p.BN) {
+    const int co = blockIdx.y * p.BN + (int)threadIdx.x - 64;
+    s_bias[threadIdx.x - 64] = co < p.Cout ? __ldg(p.bias + co) : 0.f;
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -219,8 +147,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const uint32_t b_dst = a_dst + TC_A_BYTES;
         const uint32_t fb = smem_u32(&full[s]);
         mbar_expect_tx(fb, TC_A_BYTES + b_bytes);
-        tma_load_4d(a_dst, &map_x, fb, kb * TC_KC, cx, cy, n);
-        tma_load_3d(b_dst, &map_w, fb, kb * TC_KC, co0, tap);
+        for (int jy = 0; jy < p.nby; ++jy)
+          for (int jx = 0; jx < p.nbx; ++jx)
+            tma_load_4d(a_dst + (uint32_t)((jy * p.bh * p.TW + jx * p.bw) * 128), &map_x, fb, kb * TC_KC,
+                        cx + jx * p.bw * p.stride, cy + jy * p.bh * p.stride, n);
+        for (int jb = 0; jb < p.nbb; ++jb)
+          tma_load_3d(b_dst + (uint32_t)(jb * p.b_rows * 128), &map_w, fb, kb * TC_KC, co0 + jb * p.b_rows, tap);
       }
     }
     __syncwarp();
@@ -264,7 +196,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
-            store4(p, o, r, co0 + c0 + j, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+            store4(p, s_bias, co0, o, r, co0 + c0 + j, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
                                                       __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), vec_out);
         }
       }
@@ -304,7 +236,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       const int py = y0 + row / p.TW, px = x0 + row % p.TW;
       if (py < p.Ho && px < p.Wo) {
         const size_t pix = ((size_t)n * p.Ho + py) * p.Wo + px;
-        store4(p, p.out + pix * p.ldo, p.res ? p.res + pix * p.ldr : nullptr, co0 + c4 * 4, acc, vec_out);
+        store4(p, s_bias, co0, p.out + pix * p.ldo, p.res ? p.res + pix * p.ldr : nullptr, co0 + c4 * 4, acc, vec_out);
       }
     }
     cluster_sync_all();          // nobody leaves while a peer may still read its tile
@@ -349,10 +281,6 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-struct MapKey {
-  const void* ptr; long long a, b, c, d, e;
-  bool operator==(const MapKey& o) const { return ptr == o.ptr && a == o.a && b == o.b && c == o.c && d == o.d && e == o.e; }
-};
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = std::hash<const void*>()(k.ptr);
@@ -363,7 +291,7 @@ struct MapKeyHash {
 static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
-static int encode_cached(const MapKey& key, CUtensorMap* out, cuuint32_t rank, void* ptr, const cuuint64_t* dims,
+int encode_cached(const MapKey& key, CUtensorMap* out, cuuint32_t rank, void* ptr, const cuuint64_t* dims,
                          const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr) {
   std::lock_guard<std::mutex> lk(g_map_mu);
   auto it = g_maps.find(key);
@@ -388,11 +316,24 @@ static void pick_tile(int H, int W, int max_tw, int* TH, int* TW) {
   }
 }
 
+int g_tc_box_rows = 128;  // pixels (128-byte rows) per TMA box (128 = one box per tile).  Measured: SMALLER boxes are
+                          // slower (tools/test_halo.py: 16-row boxes cost 1.5-2x), so the tile is fetched as one box
+
+int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
+                    const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
+                    float slope, cudaStream_t st, int* taken);
+
 int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
                   const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
                   float slope, cudaStream_t st) {
   UPF_REQUIRE((ldx % 4) == 0 && aligned16(x) && aligned16(w_packed), "conv_tc: input pitch/pointer must be 16-byte aligned");
   UPF_REQUIRE(stride == 1 || stride == 2, "conv_tc: stride %d not in {1,2}", stride);
+  {
+    // fine pyramid levels, 3x3 / dilation <= 4: the halo kernel loads the activation tile once for all nine taps
+    int taken = 0;
+    const int e = conv2d_fwd_halo(x, ldx, w_packed, bias, out, ldo, res, ldr, N, H, W, Cin, Cout, ks, stride, dil, slope, st, &taken);
+    if (e != 0 || taken) return e;
+  }
   const int pad = ((ks - 1) * dil) / 2;
   const int Ho = (H + 2 * pad - dil * (ks - 1) - 1) / stride + 1;
   const int Wo = (W + 2 * pad - dil * (ks - 1) - 1) / stride + 1;
@@ -406,22 +347,29 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   int TH = 8, TW = 16;
   pick_tile(Ho, Wo, 256 / stride > 128 ? 128 : 256 / stride, &TH, &TW);   // TMA box extents are <= 256 elements
 
+  // sub-boxes: `box_rows` pixels each, either whole tile rows (TW <= box_rows) or a segment of one row
+  const int box_rows = (g_tc_box_rows >= 8 && g_tc_box_rows <= 128) ? g_tc_box_rows : 128;
+  const int bw = TW < box_rows ? TW : box_rows;
+  int bh = box_rows / bw;
+  if (bh > TH) bh = TH;
+  int b_rows = BN < box_rows ? BN : box_rows;
+  while (BN % b_rows) b_rows -= 8;           // BN is a multiple of 16
   CUtensorMap mx, mw;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
-    const cuuint32_t box[4] = {TC_KC, (cuuint32_t)(TW * stride), (cuuint32_t)(TH * stride), 1};
+    const cuuint32_t box[4] = {TC_KC, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), 1};
     const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    MapKey key{x, ldx, ((long long)H << 32) | (unsigned)W, ((long long)N << 32) | (unsigned)Cin, TW * 4 + stride, 4};
+    MapKey key{x, ldx, ((long long)H << 32) | (unsigned)W, ((long long)N << 32) | (unsigned)Cin, (bw * 1000 + bh) * 4 + stride, 4};
     int e = encode_cached(key, &mx, 4, const_cast<float*>(x), dims, strides, box, estr);
     if (e) return e;
   }
   {
     const cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)taps};
     const cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 4, (cuuint64_t)cin_pad * cout_pad * 4};
-    const cuuint32_t box[3] = {TC_KC, (cuuint32_t)BN, 1};
+    const cuuint32_t box[3] = {TC_KC, (cuuint32_t)b_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    MapKey key{w_packed, cin_pad, BN, taps, cout_pad, 3};
+    MapKey key{w_packed, cin_pad, b_rows, taps, cout_pad, 3};
     int e = encode_cached(key, &mw, 3, const_cast<float*>(w_packed), dims, strides, box, estr);
     if (e) return e;
   }
@@ -431,6 +379,7 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.BN = BN;
   p.TH = TH; p.TW = TW; p.tiles_x = (Wo + TW - 1) / TW; p.tiles_y = (Ho + TH - 1) / TH;
   p.ks = ks; p.dil = dil; p.stride = stride; p.kblocks = kblocks;
+  p.bw = bw; p.bh = bh; p.nbx = TW / bw; p.nby = TH / bh; p.b_rows = b_rows; p.nbb = BN / b_rows;
   p.slope = slope;
   p.tmem_cols = BN <= 32 ? 32 : (BN <= 64 ? 64 : 128);
   const int stage_bytes = TC_A_BYTES + ((BN * 128 + 1023) & ~1023);
@@ -440,19 +389,19 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   // parallelism left at the coarse pyramid levels
   const int iters_all = taps * kblocks;
   int splits = 1;
-  while (splits < 8 && ctas * splits * 2 <= 2 * UPF_NUM_SMS && iters_all / (splits * 2) >= 3) splits *= 2;
+  while (splits < 8 && ctas * splits * 2 <= UPF_NUM_SMS && iters_all / (splits * 2) >= 3) splits *= 2;   // stay within one wave
   int ips = (iters_all + splits - 1) / splits;
   while (splits > 1 && (splits - 1) * ips >= iters_all) { splits >>= 1; ips = (iters_all + splits - 1) / splits; }   // no empty CTA
   // stages: two CTAs per SM when the grid is large (epilogue/main-loop overlap across CTAs); a single
   // resident CTA gets the whole shared memory so that more TMA loads are in flight (latency-bound regime)
-  const bool one_cta = ctas * splits <= 2 * UPF_NUM_SMS;
+  const bool one_cta = ctas * splits <= UPF_NUM_SMS;
   int nstage = ((one_cta ? 200 : 108) * 1024) / stage_bytes;
   if (nstage > (one_cta ? 12 : 6)) nstage = one_cta ? 12 : 6;
   if (nstage < 2) nstage = 2;
   if (splits > 1 && (long long)nstage * stage_bytes < 128ll * (BN + 4) * 4) { splits = 1; ips = iters_all; }
   p.nstage = nstage;
   p.splits = splits; p.ips = ips;
-  const size_t smem = (size_t)nstage * stage_bytes + (2 * nstage + 2) * 8 + 1024;
+  const size_t smem = (size_t)nstage * stage_bytes + (2 * nstage + 2) * 8 + 16 + BN * 4 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -105,7 +105,11 @@ __device__ __forceinline__ void corr_stage(float* __restrict__ dst, const float*
 }
 
 template <int D, bool VEC>
-__global__ void __launch_bounds__(CorrCfg<D>::NT, CorrCfg<D>::MIN_CTAS)
+// (__maxnreg__ instead of a min-blocks hint: ptxas otherwise settles on 96 registers and spills accumulators
+// inside the channel loop; 112 x 288 threads x 2 CTAs = 64512 registers still fits the SM; registers are granted per warp in units of 512,
+// so the single-CTA 13-warp variant (d = 6) gets 144, not 152)
+// (measured: the 13-warp d = 6 variant launches with 128 registers and fails with 144)
+__global__ void __launch_bounds__(CorrCfg<D>::NT) __maxnreg__(CorrCfg<D>::MIN_CTAS == 2 ? 112 : 128)
 corr_fwd_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__ f2, int ld2,
                 float* __restrict__ out, int ldo, int H, int W, int C,
                 const double* __restrict__ stats1, const double* __restrict__ stats2,
@@ -310,6 +314,115 @@ corr_bwd_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__
   }
 }
 
+// --------------------------------------------------------------------------
+// small images (the 1/64 .. 1/8 pyramid levels: a few hundred to a few thousand
+// pixels, up to 196 channels): the tiled kernel above would run on a handful of
+// CTAs looping over 7 channel passes.  Here ONE CTA owns ONE pixel: its
+// (normalised) f1 vector sits in shared memory, 4 lanes share a displacement
+// (each a quarter of the channels, 16-byte loads that hit L1 because neighbouring
+// CTAs read the same f2 rows), and a 2-step shuffle finishes the dot product.
+// --------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(704)
+corr_small_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__ f2, int ld2,
+                  float* __restrict__ out, int ldo, int H, int W, int C, int D,
+                  const double* __restrict__ stats1, const double* __restrict__ stats2,
+                  float slope, int n2_shift, int N) {
+  extern __shared__ __align__(16) float sm[];        // a[Cp] | mean2[Cp] | rstd2[Cp]
+  const int Cp = (C + 3) & ~3;
+  float* s_a = sm;
+  float* s_m2 = sm + Cp;
+  float* s_r2 = sm + 2 * Cp;
+  const int pix = blockIdx.x;                         // linear (n, y, x)
+  const int x = pix % W, y = (pix / W) % H, n = pix / (W * H);
+  const int n2 = (n + n2_shift) % N;
+  const bool norm = stats1 != nullptr;
+  const double npix = (double)H * (double)W;
+  const float* a_src = f1 + (size_t)pix * ld1;
+  for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
+    float a = 0.f, m2 = 0.f, r2 = 1.f;
+    if (c < C) {
+      a = __ldg(a_src + c);
+      if (norm) {
+        float m1, sd1, sd2;
+        stats_to_mean_std(stats1 + ((size_t)n * C + c) * 2, npix, m1, sd1);
+        stats_to_mean_std(stats2 + ((size_t)n2 * C + c) * 2, npix, m2, sd2);
+        a = __fmul_rn(__fsub_rn(a, m1), __fdiv_rn(1.0f, sd1));
+        r2 = __fdiv_rn(1.0f, sd2);
+      }
+    }
+    s_a[c] = a; s_m2[c] = m2; s_r2[c] = r2;
+  }
+  __syncthreads();
+
+  const int WIN = 2 * D + 1, NOUT = WIN * WIN;
+  const int k = threadIdx.x >> 2, part = threadIdx.x & 3;       // displacement, channel quarter
+  float acc = 0.f;
+  if (k < NOUT) {
+    const int dy = k / WIN - D, dx = k % WIN - D;
+    const int yy = y + dy, xx = x + dx;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const float* b_src = f2 + ((size_t)((size_t)n2 * H + yy) * W + xx) * ld2;
+      // channel groups of 4 are dealt round-robin to the 4 lanes of the displacement
+      for (int c = part * 4; c < C; c += 16) {
+        float4 b;
+        if (VEC) {
+          b = ldg4(b_src + c);
+        } else {
+          b.x = __ldg(b_src + c);
+          b.y = c + 1 < C ? __ldg(b_src + c + 1) : 0.f;
+          b.z = c + 2 < C ? __ldg(b_src + c + 2) : 0.f;
+          b.w = c + 3 < C ? __ldg(b_src + c + 3) : 0.f;
+        }
+        const float4 a = *reinterpret_cast<const float4*>(s_a + c);
+        if (norm) {
+          const float4 m = *reinterpret_cast<const float4*>(s_m2 + c);
+          const float4 r = *reinterpret_cast<const float4*>(s_r2 + c);
+          b.x = __fmul_rn(__fsub_rn(b.x, m.x), r.x);
+          b.y = __fmul_rn(__fsub_rn(b.y, m.y), r.y);
+          b.z = __fmul_rn(__fsub_rn(b.z, m.z), r.z);
+          b.w = __fmul_rn(__fsub_rn(b.w, m.w), r.w);
+          if (!VEC) {                                       // padded channels carry a = 0 already; keep b finite
+            if (c + 1 >= C) b.y = 0.f;
+            if (c + 2 >= C) b.z = 0.f;
+            if (c + 3 >= C) b.w = 0.f;
+          }
+        }
+        acc = fmaf(a.x, b.x, acc);
+        acc = fmaf(a.y, b.y, acc);
+        acc = fmaf(a.z, b.z, acc);
+        acc = fmaf(a.w, b.w, acc);
+      }
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  if (k < NOUT && part == 0) {
+    const float fC = (float)C, inv = __fdiv_rn(1.0f, fC);
+    float v = __fmul_rn(acc, inv);
+    v = __fmaf_rn(__fmaf_rn(-v, fC, acc), inv, v);          // correctly rounded acc / C
+    out[(size_t)pix * ldo + k] = lrelu(v, slope);
+  }
+}
+
+constexpr long long CORR_SMALL_MAX_PIX = 4096;   // measured: at 2x47x156 (C=64) the tiled kernel is already 2x faster
+
+static int launch_corr_small(const float* f1, int ld1, const float* f2, int ld2, float* out, int ldo,
+                             int N, int H, int W, int C, int D, const double* s1, const double* s2, int shift,
+                             float slope, cudaStream_t st) {
+  const int nout = (2 * D + 1) * (2 * D + 1);
+  const int threads = ((nout * 4 + 31) / 32) * 32;          // 4 lanes per displacement
+  UPF_REQUIRE(threads <= 704, "corr_small: window too large");
+  const bool vec = (C % 4 == 0) && (ld2 % 4 == 0) && aligned16(f2);
+  const size_t smem = (size_t)3 * ((C + 3) & ~3) * sizeof(float);
+  const unsigned grid = (unsigned)((long long)N * H * W);
+  if (vec)
+    corr_small_kernel<true><<<grid, threads, smem, st>>>(f1, ld1, f2, ld2, out, ldo, H, W, C, D, s1, s2, slope, shift, N);
+  else
+    corr_small_kernel<false><<<grid, threads, smem, st>>>(f1, ld1, f2, ld2, out, ldo, H, W, C, D, s1, s2, slope, shift, N);
+  return check_launch("corr_small");
+}
+
 }  // namespace upf
 
 extern "C" int upf_corr_lrelu_fwd(const float* f1, int ld1, const float* f2, int ld2, float* out, int ldo,
@@ -325,6 +438,11 @@ extern "C" int upf_corr_lrelu_fwd(const float* f1, int ld1, const float* f2, int
   UPF_REQUIRE(ldo >= nout, "corr: output pitch %d < %d", ldo, nout);
   UPF_REQUIRE((stats1 == nullptr) == (stats2 == nullptr), "corr: give both stats or neither");
   cudaStream_t st = (cudaStream_t)stream;
+  UPF_REQUIRE(max_disp >= 1 && max_disp <= 6, "corr: max_disp %d not in 1..6", max_disp);
+  // coarse pyramid levels: too few 8x32 tiles to occupy the chip (and up to 7 channel passes each)
+  // (the choice depends on the IMAGE size only, never on N: an image must give the same bits in any batch)
+  if ((long long)H * W <= CORR_SMALL_MAX_PIX / 2 && C <= 1024)
+    return launch_corr_small(f1, ld1, f2, ld2, out, ldo, N, H, W, C, max_disp, stats1, stats2, f2_batch_shift, slope, st);
   switch (max_disp) {
     case 1: return launch_corr_fwd<1>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);
     case 2: return launch_corr_fwd<2>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);

@@ -273,7 +273,9 @@ extern "C" int upf_warp_fwd(const float* x, int ldx, const float* flow, int ldf,
   const int lpp = pick_lpp(C);
   const int ppc = WARP_NT / lpp;
   int per_image = (H * W + ppc - 1) / ppc;
-  const int cap = (UPF_NUM_SMS * 8 + N - 1) / N;     // ~8 CTAs per SM over the whole batch
+  // the CTA count per image fixes how the fp32 partial moments are grouped: it must depend on the image
+  // size only, never on N, so that an image gives the same bits in any batch (batch sharding relies on it)
+  const int cap = UPF_NUM_SMS * 4;
   if (per_image > cap) per_image = cap;
   if (per_image < 1) per_image = 1;
   const bool vec = (C % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(x) && aligned16(out);
@@ -308,7 +310,7 @@ extern "C" int upf_featnorm_stats(const float* x, int ldx, int N, int H, int W, 
   const int lpp = pick_lpp(C);
   const int ppc = WARP_NT / lpp;
   int per_image = (H * W + ppc * 8 - 1) / (ppc * 8);
-  const int cap = (UPF_NUM_SMS * 8 + N - 1) / N;
+  const int cap = UPF_NUM_SMS * 4;                   // independent of N (see upf_warp_fwd)
   if (per_image > cap) per_image = cap;
   if (per_image < 1) per_image = 1;
   const int vec = (C % 4 == 0) && (ldx % 4 == 0) && aligned16(x);
