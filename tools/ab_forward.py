@@ -1,5 +1,5 @@
 """A/B timing of the whole KITTI forward (CUDA-graph replay, L2 flushed per step) under conv dispatch variants,
-on ONE box in ONE process.  python tools/ab_forward.py"""
+on ONE box in ONE process.  python tools/ab_forward.py [workload]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,11 +11,13 @@ H, W, B = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "kitti_375x1242_
 sd = bench.make_weights()
 im1, im2 = bench.synth_inputs(B, H, W, 1234)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-variants = [("halo off", 0, 1 << 16), ("halo Cin>=512", 1, 513 << 16), ("halo Cin>=384", 1, 385 << 16), ("halo Cin>=192", 1, 193 << 16),
-            ("halo Cin>=128", 1, 129 << 16), ("halo Cin>=64", 1, 65 << 16), ("halo all", 1, 1 << 16)]
+# (name, halo enabled, mode bits: bit3 = PDL off, bits 8-15 box rows, bits 16.. min Cin + 1)
+variants = [("halo>=64, PDL on", 1, (65 << 16) | (128 << 8)), ("halo>=64, PDL off", 1, (65 << 16) | (128 << 8) | 8),
+            ("halo off, PDL on", 0, (65 << 16) | (128 << 8)), ("halo off, PDL off", 0, (65 << 16) | (128 << 8) | 8)]
+ref = None
 for rep in range(2):
     for name, en, mode in variants:
-        lib.upf_debug_conv_halo(en, mode | (128 << 8))
+        lib.upf_debug_conv_halo(en, mode)
         eng = DecoderEngine({k: v.cuda() for k, v in sd.items()}, precision="tf32")
         with torch.no_grad():
             g = eng.capture(B, H, W)
@@ -29,4 +31,9 @@ for rep in range(2):
             e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         ts.sort()
-        print("%-16s median %.3f ms  min %.3f ms  (%.1f pairs/s)" % (name, ts[len(ts) // 2], ts[0], B * 1e3 / ts[len(ts) // 2]), flush=True)
+        out = g.flow_f.clone()
+        if ref is None:
+            ref = out
+        print("%-20s median %.3f ms  min %.3f ms  (%.1f pairs/s)  mean|flow diff vs first| %.3g" % (
+            name, ts[len(ts) // 2], ts[0], B * 1e3 / ts[len(ts) // 2], (out - ref).abs().mean().item()), flush=True)
+lib.upf_debug_conv_halo(1, (65 << 16) | (128 << 8))

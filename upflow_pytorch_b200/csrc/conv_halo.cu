@@ -5,10 +5,12 @@
 // Two measured facts shape this kernel (B200, tools/test_halo.py):
 //  (1) conv_tc.cu issues one TMA box per (tap, channel block): every activation
 //      byte travels L2 -> shared memory nine times;
-//  (2) an SS-mode tcgen05.mma of M=128 rows costs ~130-170 cycles whatever N is
-//      (the A operand is fetched from shared memory row by row), so with the
-//      pixels as M and Cout <= 128 as N the tensor pipe cannot exceed ~50 % of its
-//      TF32 rate, and 12 % at Cout = 32.
+//  (2) tcgen05.mma kind::tf32 M=128 K=8 costs 46 / 49 / 65 / 129 cycles at
+//      N = 16-32 / 64 / 128 / 256 (tools/microbench/tc_probe.cu; the shifted-window
+//      operand below costs nothing extra): one N=256 instruction per K step keeps the
+//      issue rate low and the accumulator in one TMEM tile.  (For Cout <= 64 the
+//      untransposed form -- pixels as M, 46-49 cycles per 128 pixels -- would be up to
+//      1.4x cheaper in tensor time; not built yet.)
 // Here  D^T[Cout (M=128, zero-padded), pixels (N = 128 or 256)] += Wt[Cout, K] * X[pixels, K]^T :
 // the weights tile of a tap is the A operand (128 rows), the activation window is
 // the B operand with N = 256 pixels per instruction.  A CTA owns an 8-column x
@@ -68,6 +70,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   uint64_t* accum_full = emptyB + p.nb;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
 
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the next kernel's prologue start early (PDL)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int tile = blockIdx.x;
   const int tx = tile % p.tiles_x; tile /= p.tiles_x;
@@ -93,6 +96,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, bias) touched
+  // only this CTA's own state and constant weights, and may overlap the tail of the previous kernel in the stream;
+  // from here on we read activations / write outputs, so wait for the upstream grid to complete and flush.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===================== TMA producer: weight tiles (one per tap) =====================
@@ -251,6 +258,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 static int g_halo_bo_mode = 0;   // measured on B200: the 128-byte swizzle is applied to absolute shared-memory address bits,
                                  // so shifted windows of a swizzled box need NO base_offset (bo_mode 1 gives garbage)
 extern int g_tc_box_rows;
+extern int g_tc_pdl;
 static int g_halo_enabled = 1;
 static int g_halo_min_cin = 64;    // A/B on the whole KITTI forward (tools/ab_forward.py): off 3.83 ms, >=192 3.72, >=64 3.60, all 3.61
 static long long* g_halo_probe = nullptr;
@@ -327,7 +335,20 @@ int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float*
     if (e != cudaSuccess) { set_error("conv_halo smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
-  conv_halo_kernel<<<(unsigned)tiles, HC_THREADS, smem, st>>>(mx, mw, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)tiles);
+  cfg.blockDim = dim3(HC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_tc_pdl ? 1 : 0;
+  {
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel, mx, mw, p);
+    if (e != cudaSuccess) { set_error("conv_halo launch: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return (int)e; }
+  }
   *taken = 1;
   return check_launch("conv_halo");
 }
@@ -344,6 +365,7 @@ extern "C" int upf_debug_probe(void* device_buffer_8x_int64) {
 extern "C" int upf_debug_conv_halo(int enabled, int bo_mode) {
   upf::g_halo_enabled = enabled & 1;
   upf::g_halo_bo_mode = bo_mode & 7;
+  upf::g_tc_pdl = (bo_mode & 8) ? 0 : 1;
   if ((bo_mode >> 8) & 0xff) upf::g_tc_box_rows = (bo_mode >> 8) & 0xff;     // tuning: rows per TMA box in bits 8..15 (0 = keep)
   if (bo_mode >> 16) upf::g_halo_min_cin = (bo_mode >> 16) - 1;              // tuning: min Cin + 1 in bits 16.. (0 = keep)
   return 0;

@@ -92,6 +92,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.nstage + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);      // [BN]: the L1 is tiny next to ~100-200 KB of shared memory
 
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the next kernel's prologue start early (PDL)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int tile = blockIdx.x;
   const int tx = tile % p.tiles_x; tile /= p.tiles_x;
@@ -126,6 +127,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, bias) touched
+  // only this CTA's own state and constant weights, and may overlap the tail of the previous kernel in the stream;
+  // from here on we read activations / write outputs, so wait for the upstream grid to complete and flush.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const bool vec_out = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
   const int pitch = p.BN + 4;                    // floats per row of the parked partial tile (bank-conflict free)
@@ -316,6 +321,7 @@ static void pick_tile(int H, int W, int max_tw, int* TH, int* TW) {
   }
 }
 
+int g_tc_pdl = 1;         // programmatic dependent launch between consecutive conv kernels (upf_debug_conv_halo bit 3 = off)
 int g_tc_box_rows = 128;  // pixels (128-byte rows) per TMA box (128 = one box per tile).  Measured: SMALLER boxes are
                           // slower (tools/test_halo.py: 16-row boxes cost 1.5-2x), so the tile is fetched as one box
 
@@ -413,13 +419,15 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = (unsigned)splits;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_tc_pdl ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel, mx, mw, p);
   if (e != cudaSuccess) { set_error("conv_tc launch: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return (int)e; }
   return check_launch("conv_tc");
