@@ -323,3 +323,38 @@ def test_conv_tf32_cluster_split_k_and_stride2(upf, case):
     assert torch.equal(outs[0], outs[1])
     err = (outs[0].permute(0, 3, 1, 2).cpu() - (ref + res)).abs().max().item()
     assert err <= 5e-4, err
+
+
+@pytest.mark.parametrize("shape,d", [((2, 32, 270, 480), 4), ((1, 16, 256, 512), 3), ((1, 36, 250, 480), 1), ((1, 64, 272, 448), 2)])
+def test_corr_pipelined_persistent_kernel(upf, shape, d):
+    """>= 444 tiles: the persistent TMA / warp-specialised kernel (corr_pipe.cu), raw and with fused normalisation +
+    LeakyReLU, into a channel slice; and bit-for-bit agreement with the tiled kernel is NOT required (different
+    summation order) -- both must meet the same 1e-5 bound against the fp64 oracle."""
+    from upflow_pytorch_b200 import _ext
+    from upflow_pytorch_b200.ops import Slice
+    N, C, H, W = shape
+    f1, f2 = _regen(60, shape), _regen(61, shape) * 1.5 + 0.3
+    a, b = upf.to_pixel_major(_cuda(f1)), upf.to_pixel_major(_cuda(f2))
+    D2 = (2 * d + 1) ** 2
+    ref = O.correlation(f1.double(), f2.double(), d).float()
+    out = torch.empty(N, H, W, D2, device="cuda")
+    upf.k_corr(a, b, out, d, slope=1.0)
+    assert (out.permute(0, 3, 1, 2).cpu() - ref).abs().max().item() <= 1e-5
+    # fused normalisation + LeakyReLU + batch shift, written into a slice of a wider buffer
+    s1 = torch.zeros(N, C, 2, dtype=torch.float64, device="cuda")
+    s2 = torch.zeros_like(s1)
+    upf.k_stats(a, s1)
+    upf.k_stats(b, s2)
+    X = torch.full((N, H, W, D2 + 15), 3.0, device="cuda")
+    upf.k_corr(a, b, Slice(X, 0, D2), d, s1, s2, f2_shift=N - 1, slope=0.1)
+    refn = O.correlation(O.normalize_features(f1.double()), O.normalize_features(f2.double())[[(n + N - 1) % N for n in range(N)]], d, 0.1).float()
+    assert (X[..., :D2].permute(0, 3, 1, 2).cpu() - refn).abs().max().item() <= 2e-5
+    assert (X[..., D2:] == 3.0).all()
+    # the same call through the tiled kernel (debug switch) agrees to rounding
+    _ext.load().upf_debug_corr_pipe(0)
+    try:
+        out2 = torch.empty_like(out)
+        upf.k_corr(a, b, out2, d, slope=1.0)
+    finally:
+        _ext.load().upf_debug_corr_pipe(1)
+    assert (out2 - out).abs().max().item() <= 1e-5

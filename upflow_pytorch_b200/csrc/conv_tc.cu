@@ -297,14 +297,15 @@ static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 int encode_cached(const MapKey& key, CUtensorMap* out, cuuint32_t rank, void* ptr, const cuuint64_t* dims,
-                         const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr) {
+                  const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, int swizzle_bytes) {
   std::lock_guard<std::mutex> lk(g_map_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return 0; }
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled not available"); return UPF_EDRIVER; }
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return UPF_EDRIVER; }
   if (g_maps.size() > 4096) g_maps.clear();
   g_maps.emplace(key, *out);

@@ -405,6 +405,10 @@ corr_small_kernel(const float* __restrict__ f1, int ld1, const float* __restrict
   }
 }
 
+int launch_corr_pipe(const float* f1, int ld1, const float* f2, int ld2, float* out, int ldo,
+                     int N, int H, int W, int C, int D, const double* s1, const double* s2, int shift,
+                     float slope, cudaStream_t st, int* taken);
+
 constexpr long long CORR_SMALL_MAX_PIX = 4096;   // measured: at 2x47x156 (C=64) the tiled kernel is already 2x faster
 
 static int launch_corr_small(const float* f1, int ld1, const float* f2, int ld2, float* out, int ldo,
@@ -443,6 +447,13 @@ extern "C" int upf_corr_lrelu_fwd(const float* f1, int ld1, const float* f2, int
   // (the choice depends on the IMAGE size only, never on N: an image must give the same bits in any batch)
   if ((long long)H * W <= CORR_SMALL_MAX_PIX / 2 && C <= 1024)
     return launch_corr_small(f1, ld1, f2, ld2, out, ldo, N, H, W, C, max_disp, stats1, stats2, f2_batch_shift, slope, st);
+  {
+    // large images, d <= 4: persistent warp-specialised kernel (loads overlap the FMA loop), corr_pipe.cu
+    int taken = 0;
+    const int e = launch_corr_pipe(f1, ld1, f2, ld2, out, ldo, N, H, W, C, max_disp, stats1, stats2, f2_batch_shift, slope,
+                                   st, &taken);
+    if (e != 0 || taken) return e;
+  }
   switch (max_disp) {
     case 1: return launch_corr_fwd<1>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);
     case 2: return launch_corr_fwd<2>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);

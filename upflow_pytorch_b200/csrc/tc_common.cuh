@@ -100,6 +100,6 @@ struct MapKey {
   bool operator==(const MapKey& o) const { return ptr == o.ptr && a == o.a && b == o.b && c == o.c && d == o.d && e == o.e; }
 };
 int encode_cached(const MapKey& key, CUtensorMap* out, cuuint32_t rank, void* ptr, const cuuint64_t* dims,
-                  const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr);
+                  const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, int swizzle_bytes = 128);
 
 }  // namespace upf
