@@ -147,6 +147,9 @@ int upf_conv_tc_pack_weights(const float* w_simt, float* w_packed, int Cin, int 
 /* test / tuning hook, not part of the hot path: enable the shared-halo tensor-core kernel (conv_halo.cu) and pick
  * its shared-memory-descriptor base-offset convention; returns 0. */
 int upf_debug_conv_halo(int enabled, int bo_mode);
+/* test / tuning hook: enable the linear-window tensor-core kernel (conv_win.cu), its minimum Cin (<0 = keep) and the
+ * 4-row units per CTA (0 = automatic) */
+int upf_debug_conv_win(int enabled, int min_cin, int force_m);
 /* test / tuning hook: 0 routes large-image correlations to the non-pipelined tiled kernel (corr.cu) */
 int upf_debug_corr_pipe(int enabled);
 /* debug: device buffer of 8 int64 receiving CTA 0's per-role wait / busy cycle counters of the halo kernel (NULL = off) */

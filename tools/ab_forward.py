@@ -11,13 +11,14 @@ H, W, B = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "kitti_375x1242_
 sd = bench.make_weights()
 im1, im2 = bench.synth_inputs(B, H, W, 1234)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-# (name, halo enabled, mode bits: bit3 = PDL off, bits 8-15 box rows, bits 16.. min Cin + 1)
-variants = [("halo>=64, PDL on", 1, (65 << 16) | (128 << 8)), ("halo>=64, PDL off", 1, (65 << 16) | (128 << 8) | 8),
-            ("halo off, PDL on", 0, (65 << 16) | (128 << 8)), ("halo off, PDL off", 0, (65 << 16) | (128 << 8) | 8)]
+# (name, win mode (bit0 on, bit1 every Cout), win min Cin, halo enabled)
+HALO = (65 << 16) | (128 << 8)
+variants = [("win<=64 + halo", 1, 0, 1), ("win off, halo", 0, 0, 1), ("win all Cout", 3, 0, 1), ("win<=64 Cin>=64 + halo", 1, 64, 1), ("win off, halo off", 0, 0, 0)]
 ref = None
 for rep in range(2):
-    for name, en, mode in variants:
-        lib.upf_debug_conv_halo(en, mode)
+    for name, wmode, wmin, hen in variants:
+        lib.upf_debug_conv_win(wmode, wmin, 0)
+        lib.upf_debug_conv_halo(hen, HALO)
         eng = DecoderEngine({k: v.cuda() for k, v in sd.items()}, precision="tf32")
         with torch.no_grad():
             g = eng.capture(B, H, W)
@@ -34,6 +35,7 @@ for rep in range(2):
         out = g.flow_f.clone()
         if ref is None:
             ref = out
-        print("%-20s median %.3f ms  min %.3f ms  (%.1f pairs/s)  mean|flow diff vs first| %.3g" % (
+        print("%-26s median %.3f ms  min %.3f ms  (%.1f pairs/s)  mean|flow diff vs first| %.3g" % (
             name, ts[len(ts) // 2], ts[0], B * 1e3 / ts[len(ts) // 2], (out - ref).abs().mean().item()), flush=True)
-lib.upf_debug_conv_halo(1, (65 << 16) | (128 << 8))
+lib.upf_debug_conv_win(1, 0, 0)
+lib.upf_debug_conv_halo(1, HALO)

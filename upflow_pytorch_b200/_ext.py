@@ -32,6 +32,7 @@ SIGNATURES = {
     "upf_conv_tc_pack_weights": (_I, [_P, _P, _I, _I, _I, _P]),
     "upf_debug_conv_halo": (_I, [_I, _I]),
     "upf_debug_probe": (_I, [_P]),
+    "upf_debug_conv_win": (_I, [_I, _I, _I]),
     "upf_debug_corr_pipe": (_I, [_I]),
     "upf_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "upf_nhwc_to_nchw": (_I, [_P, _I, _P, _I, _I, _I, _I, _P]),

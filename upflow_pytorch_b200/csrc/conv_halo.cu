@@ -261,7 +261,7 @@ extern int g_tc_box_rows;
 extern int g_tc_pdl;
 static int g_halo_enabled = 1;
 static int g_halo_min_cin = 64;    // A/B on the whole KITTI forward (tools/ab_forward.py): off 3.83 ms, >=192 3.72, >=64 3.60, all 3.61
-static long long* g_halo_probe = nullptr;
+long long* g_halo_probe = nullptr;
 
 // returns 1 when the launch was taken, 0 when the shape is not eligible (caller falls through to conv_tc), <0 / cudaError on failure
 int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,

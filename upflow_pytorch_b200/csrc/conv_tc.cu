@@ -18,8 +18,12 @@
 //        128 bytes with SWIZZLE_128B = the canonical K-major UMMA operand.
 //   B  : weights pre-packed [tap][cout_pad16][cin_pad32]; box {32, BN, 1}.
 //   D  : TMEM, 128 lanes (pixels) x BN columns (output channels), fp32.
-//   pipeline: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread,
-//        tcgen05.mma.cta_group::1.kind::tf32, 4 x K=8 per 32-channel block),
+//   pipeline: warp 0 = TMA producer, warps 1 and 6 = MMA issuers (one elected thread each,
+//        tcgen05.mma.cta_group::1.kind::tf32, 4 x K=8 per 32-channel block).  TWO issuers because one cannot keep
+//        the tensor pipe busy: 4 MMAs + tcgen05.commit + mbarrier poll take 634 cycles of the issuing thread against
+//        259 cycles of MMA work at N=128 (tools/microbench/tc_probe.cu).  Issuer w takes the K iterations with
+//        it % 2 == w into its OWN accumulator (TMEM columns w*BN..), so each accumulator has one issuer and a fixed
+//        order (bitwise reproducible); the epilogue adds the two.
 //        warps 2-5 = epilogue (tcgen05.ld 32x32b -> bias + LeakyReLU + residual
 //        -> 16-byte stores into the output channel slice).  smem full/empty
 //        mbarriers ring over NSTAGE stages; tcgen05.commit releases stages and
@@ -38,7 +42,7 @@
 
 namespace upf {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 224;         // warps: 0 TMA, 1 and 6 MMA issuers, 2-5 epilogue
 constexpr int TC_KC = 32;               // channels per K block (128 B of fp32)
 constexpr int TC_A_BYTES = 128 * 128;   // 128 pixels x 128 B
 
@@ -112,7 +116,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       mbar_init(smem_u32(&full[s]), 1);
       mbar_init(smem_u32(&empty[s]), 1);
     }
-    mbar_init(smem_u32(accum_full), 1);
+    mbar_init(smem_u32(accum_full), iters >= 2 ? 2 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x >= 64 && (int)threadIdx.x - 64 < p.BN) {
@@ -161,11 +165,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 6) {
+    // ===================== MMA issuers =====================
     // instruction descriptor: D=f32 (bit4), A=B=TF32 (2<<7, 2<<10), K-major both, N>>3 @17, M>>4 @24
+    const int wi = warp == 1 ? 0 : 1;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
-    for (int it = 0; it < iters; ++it) {
+    const uint32_t tacc = tmem_base + (uint32_t)(wi * p.BN);
+    for (int it = wi; it < iters; it += 2) {
       const int s = it % p.nstage;
       const uint32_t ph = (uint32_t)(it / p.nstage) & 1u;
       mbar_wait(smem_u32(&full[s]), ph);
@@ -176,9 +182,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const uint64_t db = umma_desc_sw128(a_addr + TC_A_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 bytes): advance the start address inside the swizzle atom
-          umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_tf32(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > wi || k > 0) ? 1u : 0u);
         umma_commit(smem_u32(&empty[s]));                      // frees the stage when these MMAs retire
-        if (it == iters - 1) umma_commit(smem_u32(accum_full));
+        if (it + 2 >= iters) umma_commit(smem_u32(accum_full));
       }
       __syncwarp();
     }
@@ -186,6 +192,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                                    // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;                             // pixel index inside the tile
+    const bool two = iters >= 2;
     mbar_wait(smem_u32(accum_full), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (p.splits == 1) {
@@ -197,7 +204,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (two) {                                             // second issuer's accumulator (odd K iterations)
+          uint32_t v2[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.BN + c0), v2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        } else {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
@@ -212,7 +227,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (two) {
+          uint32_t v2[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.BN + c0), v2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        } else {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
           *reinterpret_cast<float4*>(mine + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
@@ -330,6 +353,10 @@ int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float*
                     const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
                     float slope, cudaStream_t st, int* taken);
 
+int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
+                   const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
+                   float slope, cudaStream_t st, int* taken);
+
 int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
                   const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
                   float slope, cudaStream_t st) {
@@ -338,6 +365,8 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   {
     // fine pyramid levels, 3x3 / dilation <= 4: the halo kernel loads the activation tile once for all nine taps
     int taken = 0;
+    const int e0 = conv2d_fwd_win(x, ldx, w_packed, bias, out, ldo, res, ldr, N, H, W, Cin, Cout, ks, stride, dil, slope, st, &taken);
+    if (e0 != 0 || taken) return e0;
     const int e = conv2d_fwd_halo(x, ldx, w_packed, bias, out, ldo, res, ldr, N, H, W, Cin, Cout, ks, stride, dil, slope, st, &taken);
     if (e != 0 || taken) return e;
   }
@@ -388,7 +417,7 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   p.ks = ks; p.dil = dil; p.stride = stride; p.kblocks = kblocks;
   p.bw = bw; p.bh = bh; p.nbx = TW / bw; p.nby = TH / bh; p.b_rows = b_rows; p.nbb = BN / b_rows;
   p.slope = slope;
-  p.tmem_cols = BN <= 32 ? 32 : (BN <= 64 ? 64 : 128);
+  p.tmem_cols = BN <= 16 ? 32 : (BN <= 32 ? 64 : (BN <= 64 ? 128 : 256));   // two accumulators (one per MMA issuer)
   const int stage_bytes = TC_A_BYTES + ((BN * 128 + 1023) & ~1023);
   const long long tiles = (long long)p.tiles_x * p.tiles_y * N;
   const long long ctas = tiles * ntiles_n;

@@ -1,0 +1,373 @@
+// 3x3 stride-1 convolution, dilation 1/2/4, tensor cores (tcgen05, TF32): pixels as the M dimension, the
+// activation halo loaded ONCE per 32-channel block, the nine taps read it as LINEARLY SHIFTED WINDOWS, one weight
+// fetch shared by up to four accumulators, and TWO MMA-issuing warps.
+//
+// Measured facts that shape it (B200; tools/microbench/tc_probe.cu "conv-like issue pattern", tools/test_win.py):
+//  (1) a single issuing thread cannot keep the tensor pipe busy with this loop shape: per tap it issues 4*m MMAs, one
+//      or two tcgen05.commit and one mbarrier poll, and the pipe idles for ~280 cycles around every commit
+//      (M=128, N=128: 4 MMAs + commit + poll = 634 cycles against 259 of MMA work; N=256: 635 against 515).
+//      conv_halo.cu hides most of it behind N=256 instructions; with N <= 128 it does not hide.  TWO issuing warps,
+//      each with its own accumulators, overlap one warp's commit with the other's MMAs: 16 MMAs + commits in 1029
+//      cycles = 64.3 per N=128 MMA, the full tensor rate.
+//  (2) MMAs that accumulate into the same TMEM tile back to back cost >= 87 cycles each whatever N is; interleaved
+//      with another accumulator they cost 65 (N=128) / 40 (N<=32).  So K steps are the OUTER loop, units the inner.
+//  (3) with the pixels as M a layer with few output channels is cheap (40 cycles per 128 pixels and K=8 at N<=32,
+//      against 64 in the transposed form of conv_halo.cu, which pays for M = 128 output channels whatever Cout is)
+//      -- and 84% of the estimator's K volume has Cout < 128.
+// Layout.  A CTA owns a tile of 4*m rows x (32 - 2d) columns (m = 1, 2 or 4 "units" of 4 rows).  Per channel block it
+// loads one halo box {32 ch, 32 positions, 4m + 2d rows}: position (r, c) lies at byte (r*32 + c)*128 of the stage
+// (SWIZZLE_128B).  Because a halo row is exactly 32 positions, the operand of unit u and tap (ky, kx) -- M index
+// j = h*32 + w, h < 4 -- is the CONTIGUOUS range of 128 positions starting at (4u + ky*d)*32 + kx*d: a plain K-major
+// SWIZZLE_128B descriptor (SBO = 1024 B) with a shifted start address (base_offset 0: measured, the swizzle is a
+// function of absolute shared-memory address bits).  Columns w >= 32 - 2d of every row wrap into the next halo row:
+// they are computed and never stored (6% / 12% / 25% of the MMA work at d = 1 / 2 / 4), which buys a halo of
+// 1.33 loaded bytes per useful pixel-channel at m = 4, d = 1 (conv_halo.cu: 2.1) and ONE weight tile per tap feeding
+// m accumulators.
+// Work split between the two issuers (both deterministic: every accumulator has ONE issuer and a fixed order):
+//   tap split  (2*m*BN <= 512 TMEM columns): issuer w takes the taps with (kb*9 + tap) % 2 == w into its own set of
+//              m accumulators; the epilogue adds the two sets.  A weight slot is released by the one issuer that read it.
+//   unit split (m = 4, BN > 64): issuer w takes units w, w+2 of every tap; a weight slot is released by both.
+//   accumulators: [128 positions x BN channels] fp32 tiles in TMEM; TMEM lane = position, so the epilogue thread of
+//   lane j owns one pixel and stores its channels as 16-byte vectors straight from registers.
+//   warps: 0 = weight TMA, 1 and 7 = MMA issuers, 2-5 = epilogue, 6 = halo TMA.
+#include "tc_common.cuh"
+
+namespace upf {
+
+constexpr int CW_THREADS = 256;
+constexpr int CW_POS = 32;                         // halo positions per row
+constexpr int CW_ROW_BYTES = CW_POS * 128;         // 4096
+
+struct WinParams {
+  float* out; int ldo;
+  const float* res; int ldr;
+  const float* bias;
+  int H, W, Cout, BN;
+  int m, dil, kblocks;
+  int tiles_x, tiles_y;
+  int na, nb;
+  int a_bytes, b_stage_bytes;
+  int tmem_cols;
+  int tap_split;              // 1: issuers alternate taps (two accumulator sets), 0: issuers alternate units
+  long long* probe;
+  float slope;
+};
+
+template <bool PROBE>
+__global__ void __launch_bounds__(CW_THREADS)
+conv_win_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const WinParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps shared-space addressing
+  uint8_t* a_ring = base;
+  uint8_t* b_ring = base + (size_t)p.na * p.a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.nb * p.b_stage_bytes);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + p.na;
+  uint64_t* fullB = emptyA + p.na;
+  uint64_t* emptyB = fullB + p.nb;
+  uint64_t* accum_full = emptyB + p.nb;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + ((2 * p.na + 2 * p.nb + 2) & ~1));   // 16-byte aligned
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);                        // 128 floats, 16-byte aligned
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int tile = blockIdx.x;
+  const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+  const int ty = tile % p.tiles_y;
+  const int n = tile / p.tiles_y;
+  const int d = p.dil;
+  const int useful = CW_POS - 2 * d;
+  const int x0 = tx * useful, y0 = ty * 4 * p.m;
+  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < p.na; ++s) { mbar_init(smem_u32(&fullA[s]), 1); mbar_init(smem_u32(&emptyA[s]), 2); }
+    for (int s = 0; s < p.nb; ++s) { mbar_init(smem_u32(&fullB[s]), 1); mbar_init(smem_u32(&emptyB[s]), p.tap_split ? 1 : 2); }
+    mbar_init(smem_u32(accum_full), 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2 && warp < 6) {                                  // bias is a constant weight: safe before the dependency wait
+    const int c = (int)threadIdx.x - 64;
+    s_bias[c] = c < p.Cout ? __ldg(p.bias + c) : 0.f;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above touched only this CTA's state and constant weights
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp == 0) {
+    // ===================== TMA producer: weight tiles (one per tap and channel block) =====================
+    if (elect_one()) {
+      long long w_eb = 0, t_start = PROBE ? clock64() : 0;
+      const int total = p.kblocks * 9;
+      for (int ib = 0; ib < total; ++ib) {
+        const int kb = ib / 9, tap = ib - kb * 9;
+        const int sb = ib % p.nb;
+        const long long t0 = PROBE ? clock64() : 0;
+        mbar_wait(smem_u32(&emptyB[sb]), (((uint32_t)(ib / p.nb)) & 1u) ^ 1u);
+        if (PROBE) w_eb += clock64() - t0;
+        const uint32_t fb = smem_u32(&fullB[sb]);
+        mbar_expect_tx(fb, b_bytes);
+        tma_load_3d(smem_u32(b_ring + (size_t)sb * p.b_stage_bytes), &map_w, fb, kb * 32, 0, tap);
+      }
+      if (PROBE && p.probe && blockIdx.x == 0) { p.probe[1] = w_eb; p.probe[2] = clock64() - t_start; }
+    }
+    __syncwarp();
+  } else if (warp == 6) {
+    // ===================== TMA producer: halo boxes (one per channel block) =====================
+    if (elect_one()) {
+      long long w_ea = 0;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        const int sa = kb % p.na;
+        const long long t0 = PROBE ? clock64() : 0;
+        mbar_wait(smem_u32(&emptyA[sa]), (((uint32_t)(kb / p.na)) & 1u) ^ 1u);
+        if (PROBE) w_ea += clock64() - t0;
+        const uint32_t fa = smem_u32(&fullA[sa]);
+        mbar_expect_tx(fa, (uint32_t)p.a_bytes);
+        tma_load_4d(smem_u32(a_ring + (size_t)sa * p.a_bytes), &map_x, fa, kb * 32, x0 - d, y0 - d, n);
+      }
+      if (PROBE && p.probe && blockIdx.x == 0) p.probe[0] = w_ea;
+    }
+    __syncwarp();
+  } else if (warp == 1 || warp == 7) {
+    // ===================== MMA issuers: M = 128 positions, N = BN output channels =====================
+    const int wi = warp == 1 ? 0 : 1;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+    const int total = p.kblocks * 9;
+    const int step = p.tap_split ? 2 : 1;
+    const int u0 = p.tap_split ? 0 : wi, ustep = p.tap_split ? 1 : 2;
+    const uint32_t tset = tmem_base + (uint32_t)(p.tap_split ? wi * p.m * p.BN : 0);
+    int kb_ready = -1;
+    uint32_t acc = 0;
+    long long w_fa = 0, w_fb = 0, t_start = PROBE ? clock64() : 0;
+    for (int ib = p.tap_split ? wi : 0; ib < total; ib += step) {
+      const int kb = ib / 9, tap = ib - kb * 9;
+      const int sa = kb % p.na, sb = ib % p.nb;
+      if (kb != kb_ready) {
+        const long long t0 = PROBE ? clock64() : 0;
+        mbar_wait(smem_u32(&fullA[sa]), ((uint32_t)(kb / p.na)) & 1u);
+        if (PROBE) w_fa += clock64() - t0;
+        kb_ready = kb;
+      }
+      {
+        const long long t0 = PROBE ? clock64() : 0;
+        mbar_wait(smem_u32(&fullB[sb]), ((uint32_t)(ib / p.nb)) & 1u);
+        if (PROBE) w_fb += clock64() - t0;
+      }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const int ky = tap / 3, kx = tap - ky * 3;
+        const uint64_t dw = umma_desc_sw128(smem_u32(b_ring + (size_t)sb * p.b_stage_bytes));
+        const uint64_t dx = umma_desc_sw128(smem_u32(a_ring + (size_t)sa * p.a_bytes) + (uint32_t)(((ky * d) * CW_POS + kx * d) * 128));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          for (int u = u0; u < p.m; u += ustep)      // unit u: 4 halo rows = 16 KB further (1024 descriptor units)
+            umma_tf32(tset + (uint32_t)(u * p.BN), dx + (uint64_t)(u * 1024 + k * 2), dw + (uint64_t)(k * 2), idesc, acc | (uint32_t)k);
+        }
+        umma_commit(smem_u32(&emptyB[sb]));
+        if ((ib + step) / 9 != kb) umma_commit(smem_u32(&emptyA[sa]));     // this issuer's last tap of the channel block
+        if (ib + step >= total) umma_commit(smem_u32(accum_full));
+      }
+      __syncwarp();
+      acc = 1;
+    }
+    if (PROBE && p.probe && blockIdx.x == 0 && lane == 0 && wi == 0) { p.probe[3] = w_fa; p.probe[4] = w_fb; p.probe[5] = clock64() - t_start; }
+  } else {
+    // ===================== epilogue (warps 2..5): lane = position, one pixel per thread and unit =====================
+    const int q = warp & 3;                                    // TMEM lane quarter = row h of the unit
+    const bool vec_out = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    const size_t img = (size_t)n * p.H * p.W;
+    const int x = x0 + lane;
+    const bool col_ok = lane < useful && x < p.W;
+    const uint32_t set2 = (uint32_t)(p.m * p.BN);
+    mbar_wait(smem_u32(accum_full), 0);
+    const long long t_e1 = PROBE ? clock64() : 0;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int u = 0; u < p.m; ++u) {
+      const int y = y0 + 4 * u + q;
+      const bool ok = col_ok && y < p.H;
+      const size_t pix = img + (size_t)y * p.W + x;
+      float* orow = p.out + pix * p.ldo;
+      const float* rrow = p.res ? p.res + pix * p.ldr : nullptr;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * p.BN);
+      for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        if (c0 + 16 < p.BN) tmem_ld16(taddr + (uint32_t)(c0 + 16), v + 16);      // warp-uniform
+        if (p.tap_split) {                                                       // second accumulator set (odd taps)
+          uint32_t v2[32];
+          tmem_ld16(taddr + set2 + (uint32_t)c0, v2);
+          if (c0 + 16 < p.BN) tmem_ld16(taddr + set2 + (uint32_t)(c0 + 16), v2 + 16);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const int nv = (c0 + 16 < p.BN) ? 32 : 16;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nv) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        } else {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        if (!ok) continue;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int c = c0 + j;
+          if (c >= p.Cout) break;
+          const float4 bv = *reinterpret_cast<const float4*>(s_bias + c);
+          float f[4] = {lrelu(__uint_as_float(v[j]) + bv.x, p.slope), lrelu(__uint_as_float(v[j + 1]) + bv.y, p.slope),
+                        lrelu(__uint_as_float(v[j + 2]) + bv.z, p.slope), lrelu(__uint_as_float(v[j + 3]) + bv.w, p.slope)};
+          if (rrow) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (c + k < p.Cout) f[k] += __ldg(rrow + c + k);
+          }
+          if (vec_out && c + 4 <= p.Cout) {
+            *reinterpret_cast<float4*>(orow + c) = make_float4(f[0], f[1], f[2], f[3]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (c + k < p.Cout) orow[c + k] = f[k];
+          }
+        }
+      }
+    }
+    if (PROBE && p.probe && blockIdx.x == 0 && threadIdx.x == 64) { p.probe[6] = 0; p.probe[7] = clock64() - t_e1; }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+extern int g_tc_pdl;
+extern long long* g_halo_probe;
+static int g_win_enabled = 1;
+static int g_win_min_cin = 0;
+static int g_win_max_cout = 64;   // measured (tools/test_win.py, 1/4- and 1/8-res KITTI): faster than conv_halo.cu for Cout <= 64
+                                  // (544->32: 97 vs 139 us, 480->64: 108 vs 130, 576->2: 91 vs 131), slower for 96..128
+static int g_win_force_m = 0;
+
+// returns with *taken = 1 when the launch was made, 0 when the shape is not eligible (caller falls through)
+int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
+                   const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
+                   float slope, cudaStream_t st, int* taken) {
+  *taken = 0;
+  if (!g_win_enabled || ks != 3 || stride != 1 || !(dil == 1 || dil == 2 || dil == 4) || Cout > 128) return 0;
+  if (Cin < g_win_min_cin || Cout > g_win_max_cout) return 0;
+  const int BN = (Cout + 15) & ~15;
+  const int kblocks = (Cin + 31) / 32;
+  const int cin_pad = kblocks * 32;
+  const int useful = CW_POS - 2 * dil;
+  const int tiles_x = (W + useful - 1) / useful;
+  const int b_stage_bytes = BN * 128;                        // multiple of 2048
+  const int budget = 224 * 1024;
+  // units per CTA and issuer split: minimise waves x (time of one tap), modelled from the microbenchmark --
+  // one issuer needs ~(490 + 145 m) cycles per tap (4m MMAs + commit + poll), two run in parallel, and the tensor
+  // pipe needs 4 m T(N) cycles per tap, T = 40 / 49 / 57 / 65 cycles at N <= 32 / 64 / 96 / 128.
+  // Ties go to the larger tile (fewer weight fetches per pixel).  force_m: +8 forces the unit split.
+  const double T = BN <= 32 ? 40. : BN <= 64 ? 49. : BN <= 96 ? 57. : 65.;
+  int m = 0, tap_split = 1;
+  double best = 1e30;
+  for (int cand = 4; cand >= 1; cand >>= 1) {
+    if ((g_win_force_m & 7) && cand != (g_win_force_m & 7)) continue;
+    int split = (2 * cand * BN <= 512) ? 1 : 0;
+    if (g_win_force_m & 8) split = 0;
+    if (!split && (cand * BN > 512 || cand < 2)) continue;
+    const int a_bytes = (4 * cand + 2 * dil) * CW_ROW_BYTES;
+    if (2 * a_bytes + 3 * b_stage_bytes > budget) continue;
+    const long long t = (long long)tiles_x * ((H + 4 * cand - 1) / (4 * cand)) * N;
+    const double issuer = split ? (490. + 145. * cand) / 2 : (490. + 145. * cand / 2);
+    const double tap_time = issuer > 4. * cand * T ? issuer : 4. * cand * T;
+    const double cost = (double)((t + UPF_NUM_SMS - 1) / UPF_NUM_SMS) * tap_time;
+    if (cost < best * 0.97) { best = cost; m = cand; tap_split = split; }
+  }
+  if (m == 0) return 0;
+  const int tiles_y = (H + 4 * m - 1) / (4 * m);
+  const long long tiles = (long long)tiles_x * tiles_y * N;
+  if (tiles * m < 96) return 0;                              // coarse levels: the cluster split-K kernel is the better fit
+  const int rows = 4 * m + 2 * dil;
+
+  CUtensorMap mx, mw;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
+    const cuuint32_t box[4] = {32, CW_POS, (cuuint32_t)rows, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    MapKey key{x, ldx, ((long long)H << 32) | (unsigned)W, ((long long)N << 32) | (unsigned)Cin, 200000 + rows, 4};
+    int e = encode_cached(key, &mx, 4, const_cast<float*>(x), dims, strides, box, estr);
+    if (e) return e;
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)BN, 9};
+    const cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 4, (cuuint64_t)cin_pad * BN * 4};
+    const cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    MapKey key{w_packed, cin_pad, BN, 9, BN, 3};
+    int e = encode_cached(key, &mw, 3, const_cast<float*>(w_packed), dims, strides, box, estr);
+    if (e) return e;
+  }
+  WinParams p;
+  p.out = out; p.ldo = ldo; p.res = res; p.ldr = ldr; p.bias = bias;
+  p.H = H; p.W = W; p.Cout = Cout; p.BN = BN; p.m = m; p.dil = dil; p.kblocks = kblocks;
+  p.tiles_x = tiles_x; p.tiles_y = tiles_y;
+  p.a_bytes = rows * CW_ROW_BYTES;
+  p.b_stage_bytes = b_stage_bytes;
+  p.slope = slope;
+  p.probe = g_halo_probe;
+  int cols = 32;
+  while (cols < (tap_split ? 2 : 1) * m * BN) cols <<= 1;
+  p.tmem_cols = cols;
+  p.tap_split = tap_split;
+  int na = (kblocks >= 3 && 3 * p.a_bytes + 4 * b_stage_bytes <= budget) ? 3 : 2;
+  if (na > kblocks) na = kblocks;
+  int nb = (budget - na * p.a_bytes) / b_stage_bytes;
+  if (nb > 9) nb = 9;
+  if (nb < 2) return 0;
+  p.na = na; p.nb = nb;
+  // the windows of the last unit read up to 2*dil positions past their stage: the weight ring follows the halo ring
+  const size_t smem = (size_t)na * p.a_bytes + (size_t)nb * b_stage_bytes + (2 * na + 2 * nb + 2) * 8 + 16 + 128 * 4 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_win_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_win_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("conv_win smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_set = true;
+  }
+  if (smem > 227 * 1024) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)tiles);
+  cfg.blockDim = dim3(CW_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_tc_pdl ? 1 : 0;
+  {
+    cudaError_t e = p.probe ? cudaLaunchKernelEx(&cfg, conv_win_kernel<true>, mx, mw, p) : cudaLaunchKernelEx(&cfg, conv_win_kernel<false>, mx, mw, p);
+    if (e != cudaSuccess) { set_error("conv_win launch: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return (int)e; }
+  }
+  *taken = 1;
+  return check_launch("conv_win");
+}
+
+}  // namespace upf
+
+// test / tuning hook (not part of the hot-path ABI): enable / disable the window kernel, set its minimum Cin and
+// force the units per CTA (0 = automatic)
+extern "C" int upf_debug_conv_win(int enabled, int min_cin, int force_m) {
+  upf::g_win_enabled = enabled & 1;
+  upf::g_win_max_cout = (enabled & 2) ? 128 : 64;      // bit 1: take every Cout <= 128 (A/B runs)
+  if (min_cin >= 0) upf::g_win_min_cin = min_cin;
+  upf::g_win_force_m = force_m;
+  return 0;
+}
