@@ -218,7 +218,7 @@ def test_sgu_blend_vs_oracle_both_variants(upf):
 CONV_CASES = [  # (Cin, Cout, k, stride, dil, H, W)
     (115, 128, 3, 1, 1, 12, 39), (563, 2, 3, 1, 1, 12, 20), (128, 96, 3, 1, 8, 24, 30), (96, 64, 3, 1, 16, 24, 30),
     (196, 32, 1, 1, 1, 6, 20), (3, 16, 3, 2, 1, 37, 50), (16, 16, 3, 1, 1, 19, 25), (64, 3, 3, 1, 1, 9, 9),
-    (32, 32, 3, 2, 1, 20, 21), (128, 196, 3, 1, 1, 6, 20),
+    (32, 32, 3, 2, 1, 20, 21), (128, 196, 3, 1, 1, 6, 20), (3, 16, 3, 1, 1, 33, 47), (4, 8, 3, 1, 1, 20, 30), (2, 30, 3, 2, 1, 21, 22),
 ]
 
 
@@ -358,3 +358,44 @@ def test_corr_pipelined_persistent_kernel(upf, shape, d):
     finally:
         _ext.load().upf_debug_corr_pipe(1)
     assert (out2 - out).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("case", [(200, 128, 1, 70, 200), (168, 24, 2, 66, 150), (96, 64, 4, 64, 130), (40, 3, 1, 90, 95)])
+def test_conv_tf32_large_grid_kernels_agree(upf, case):
+    """Fine pyramid levels: the same 3x3 convolution through the per-tap kernel (conv_tc.cu, two CTAs per SM), the
+    shared-halo kernel (conv_halo.cu) and the linear-window kernel (conv_win.cu; 1, 2 and 4 units per CTA, two MMA
+    issuers) -- each must match the TF32-truncated oracle to fp32 rounding, repeat bit for bit, and leave the
+    neighbouring channels of the output buffer alone."""
+    from upflow_pytorch_b200 import _ext
+    from upflow_pytorch_b200.ops import Slice
+    lib = _ext.load()
+    Cin, Cout, dil, H, W = case
+    x = _regen(70, (2, Cin, H, W))
+    w = _regen(71, (Cout, Cin, 3, 3)) * (2.0 / (Cin * 9)) ** 0.5
+    b = _regen(72, (Cout,)) * 0.1
+    _, wtc = upf.pack_conv_weight(_cuda(w), tc=True)
+
+    def trunc(t):
+        return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    ref = O.conv2d_direct(trunc(x).double(), trunc(w).double(), b.double(), dil, 1, 0.1).float()
+    ld = (Cin + 3) // 4 * 4 + 8
+    a = Slice(upf.to_pixel_major(_cuda(x), ld=ld), 0, Cin)
+    ldo = (Cout + 3) // 4 * 4 + 4
+    HALO = (1 << 16) | (128 << 8)
+    modes = {"tap": (0, 0, 0), "halo": (0, 0, 1), "win": (3, 0, 0), "win m1": (3, 1, 0), "win m2": (3, 2, 0), "win m4": (3, 4, 0)}
+    try:
+        for name, (wen, fm, hen) in modes.items():
+            lib.upf_debug_conv_win(wen, 0, fm)
+            lib.upf_debug_conv_halo(hen, HALO)
+            outs = []
+            for _ in range(3):
+                buf = torch.full((2, H, W, ldo), 7.0, device="cuda")
+                upf.k_conv(a, wtc, _cuda(b), Slice(buf, 0, Cout), 3, 1, dil, 0.1, None, _ext.CONV_TF32)
+                outs.append(buf)
+            assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), name
+            assert (outs[0][..., Cout:] == 7.0).all(), name
+            err = (outs[0][..., :Cout].permute(0, 3, 1, 2).cpu() - ref).abs().max().item()
+            assert err <= 5e-4, (name, err)
+    finally:
+        lib.upf_debug_conv_win(1, 0, 0)
+        lib.upf_debug_conv_halo(1, (65 << 16) | (128 << 8))

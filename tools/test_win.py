@@ -26,10 +26,11 @@ def run(N, h, w, cin, cout, dil, ld=576, resid=False):
     for name, (wen, fm, hen) in MODES:
         lib.upf_debug_conv_win(wen, 0, fm)
         lib.upf_debug_conv_halo(hen, (1 << 16) | (128 << 8))
-        out = torch.full((N, h, w, cout + 3), float("nan"), device="cuda")
+        out = torch.full((N, h, w, cout + 4), float("nan"), device="cuda")     # 16-byte aligned pitch, like the engine's buffers
         call = lambda: ops.k_conv(Slice(X, 0, cin), wtc, b, Slice(out, 0, cout), 3, 1, dil, 0.1, r, _ext.CONV_TF32)
         probe.zero_()
         lib.upf_debug_probe(ctypes.c_void_p(probe.data_ptr()))
+        if os.environ.get('TW_TRACE'): print('  launching', name, flush=True)
         call()
         torch.cuda.synchronize()
         pr = probe.cpu().tolist()
@@ -54,11 +55,14 @@ def run(N, h, w, cin, cout, dil, ld=576, resid=False):
             name, us, fl / us / 1e6, err, int(torch.isnan(o[..., :cout]).sum()), untouched, pr[0], pr[1], pr[3], pr[4], pr[5], pr[7]), flush=True)
 
 
-for args in ((2, 94, 311, 576, 128, 1), (2, 94, 311, 544, 32, 1), (2, 94, 311, 480, 64, 1), (2, 94, 311, 384, 96, 1), (2, 94, 311, 576, 2, 1),
-             (2, 94, 311, 128, 128, 1), (2, 94, 311, 64, 32, 1), (2, 94, 311, 184, 3, 1), (2, 94, 311, 128, 128, 2), (2, 94, 311, 128, 128, 4),
-             (2, 94, 311, 32, 2, 1, 576, True),
-             (2, 47, 156, 576, 128, 1), (2, 47, 156, 256, 128, 1), (2, 47, 156, 544, 32, 1), (2, 47, 156, 128, 96, 4),
-             (2, 188, 621, 32, 32, 1, 32), (2, 375, 1242, 16, 16, 1, 16), (2, 24, 78, 576, 128, 1), (1, 37, 61, 100, 50, 2, 100)):
+SHAPES = ((2, 94, 311, 576, 128, 1), (2, 94, 311, 544, 32, 1), (2, 94, 311, 480, 64, 1), (2, 94, 311, 384, 96, 1), (2, 94, 311, 576, 2, 1),
+          (2, 94, 311, 128, 128, 1), (2, 94, 311, 64, 32, 1), (2, 94, 311, 184, 3, 1), (2, 94, 311, 128, 128, 2), (2, 94, 311, 128, 128, 4),
+          (2, 94, 311, 32, 2, 1, 576, True),
+          (2, 47, 156, 576, 128, 1), (2, 47, 156, 256, 128, 1), (2, 47, 156, 544, 32, 1), (2, 47, 156, 128, 96, 4),
+          (2, 188, 621, 32, 32, 1, 32), (2, 375, 1242, 16, 16, 1, 16), (2, 24, 78, 576, 128, 1), (1, 37, 61, 100, 50, 2, 100))
+if len(sys.argv) > 1:
+    SHAPES = SHAPES[:int(sys.argv[1])]
+for args in SHAPES:
     run(*args)
 lib.upf_debug_conv_win(1, 0, 0)
 lib.upf_debug_conv_halo(1, (65 << 16) | (128 << 8))

@@ -155,6 +155,85 @@ static void launch_simt(const float* x, int ldx, const float* w, const float* bi
                                                           Cout, cout_pad, ks, stride, dil, slope, vec_in);
 }
 
+
+// ---------------------------------------------------------------- first layers: 3x3, Cin <= 4 (the RGB image)
+// The image convolutions (FeatureExtractor conv 3->16 stride 2, model/pwc_modules.py:122-142, and the full-resolution
+// 3->16 of the output-level SGU, model/upflow.py:360-372) have K = 27: the implicit-GEMM tiles above spend their time
+// on staging (152 us at 2x375x1242, against 71 MB = 11 us of HBM traffic).  Direct form: Cout/4 threads per output
+// pixel, each owning 4 output channels -- a warp writes 32/(Cout/4) pixels x Cout channels as one contiguous run of
+// 16-byte stores; the 27 inputs come through L1 (neighbouring pixels share them), the weights from shared memory.
+template <int CIN>
+__global__ void __launch_bounds__(256)
+conv_c3_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ bias,
+               float* __restrict__ out, int ldo, const float* __restrict__ res, int ldr,
+               int N, int H, int W, int Ho, int Wo, int Cout, int cout_pad, int stride, float slope) {
+  extern __shared__ float s_w[];                         // [9*CIN][cout_pad] then bias[cout_pad]
+  for (int i = threadIdx.x; i < 9 * CIN * cout_pad; i += blockDim.x) s_w[i] = __ldg(w + i);
+  float* s_b = s_w + 9 * CIN * cout_pad;
+  for (int i = threadIdx.x; i < cout_pad; i += blockDim.x) s_b[i] = i < Cout ? __ldg(bias + i) : 0.f;
+  __syncthreads();
+  const int tpp = cout_pad >> 2;                         // threads per pixel (power of two <= 32)
+  const bool vec_out = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  // persistent CTAs (the weights are staged once): a work item is 256/tpp consecutive pixels of one output row
+  const int ppb = 256 >> (__ffs(tpp) - 1);               // pixels per item (tpp is a power of two)
+  const int nxb = (Wo + ppb - 1) / ppb;
+  const int items = nxb * Ho * N;
+  const int c0 = (threadIdx.x & (tpp - 1)) * 4;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int xb = item % nxb, row = item / nxb;         // CTA-uniform
+    const int oy = row % Ho;
+    const long long n = row / Ho;
+    const int ox = xb * ppb + (threadIdx.x >> (__ffs(tpp) - 1));
+    if (ox >= Wo) continue;
+    const long long pix = (n * Ho + oy) * Wo + ox;
+    float4 acc = *reinterpret_cast<const float4*>(s_b + c0);
+    const float* xn = x + (size_t)n * H * W * ldx;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * stride + ky - 1;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * stride + kx - 1;
+        if (ix < 0 || ix >= W) continue;
+        const float* px = xn + ((size_t)iy * W + ix) * ldx;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float v = __ldg(px + ci);
+          const float4 wv = *reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * CIN + ci) * cout_pad + c0);
+          acc.x = fmaf(v, wv.x, acc.x); acc.y = fmaf(v, wv.y, acc.y); acc.z = fmaf(v, wv.z, acc.z); acc.w = fmaf(v, wv.w, acc.w);
+        }
+      }
+    }
+    float f[4] = {lrelu(acc.x, slope), lrelu(acc.y, slope), lrelu(acc.z, slope), lrelu(acc.w, slope)};
+    if (res) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c0 + k < Cout) f[k] += __ldg(res + (size_t)pix * ldr + c0 + k);
+    }
+    float* o = out + (size_t)pix * ldo + c0;
+    if (vec_out && c0 + 4 <= Cout) {
+      *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c0 + k < Cout) o[k] = f[k];
+    }
+  }
+}
+
+template <int CIN>
+static int launch_c3(const float* x, int ldx, const float* w, const float* bias, float* out, int ldo, const float* res, int ldr,
+                     int N, int H, int W, int Ho, int Wo, int Cout, int cout_pad, int stride, float slope, cudaStream_t st) {
+  const size_t smem = (size_t)(9 * CIN + 1) * cout_pad * sizeof(float);
+  const int ppb = 256 / (cout_pad >> 2);
+  long long items = (long long)((Wo + ppb - 1) / ppb) * Ho * N;
+  UPF_REQUIRE(items < (1ll << 31), "conv_c3: too many pixels");
+  const long long cap = (long long)UPF_NUM_SMS * 8;
+  conv_c3_kernel<CIN><<<(unsigned)(items < cap ? items : cap), 256, smem, st>>>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, stride, slope);
+  return check_launch("conv_c3");
+}
+
 int conv2d_fwd_simt(const float* x, int ldx, const float* w, const float* bias, float* out, int ldo,
                     const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
                     float slope, cudaStream_t st) {
@@ -165,6 +244,14 @@ int conv2d_fwd_simt(const float* x, int ldx, const float* w, const float* bias, 
   const int cout_pad = (Cout + 3) & ~3;
   UPF_REQUIRE(aligned16(w), "conv: weights must be 16-byte aligned");
   const int vec_in = (ldx % 4 == 0) && aligned16(x);
+  if (ks == 3 && dil == 1 && Cin <= 4 && (cout_pad == 4 || cout_pad == 8 || cout_pad == 16 || cout_pad == 32)) {
+    switch (Cin) {
+      case 1: return launch_c3<1>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, stride, slope, st);
+      case 2: return launch_c3<2>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, stride, slope, st);
+      case 3: return launch_c3<3>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, stride, slope, st);
+      default: return launch_c3<4>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, stride, slope, st);
+    }
+  }
   if (cout_pad > 64)
     launch_simt<128, 128, 8, 8>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cin, Cout, cout_pad, ks, stride, dil, slope, vec_in, st);
   else if (cout_pad > 32)

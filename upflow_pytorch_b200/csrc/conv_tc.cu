@@ -433,6 +433,8 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   const bool one_cta = ctas * splits <= UPF_NUM_SMS;
   int nstage = ((one_cta ? 200 : 108) * 1024) / stage_bytes;
   if (nstage > (one_cta ? 12 : 6)) nstage = one_cta ? 12 : 6;
+  nstage &= ~1;        // EVEN: issuer w then owns the stages of parity w and sees every phase of their barriers -- with an odd
+                       // ring an issuer would revisit a stage two phases later, which a parity wait cannot tell from the stale one
   if (nstage < 2) nstage = 2;
   if (splits > 1 && (long long)nstage * stage_bytes < 128ll * (BN + 4) * 4) { splits = 1; ips = iters_all; }
   p.nstage = nstage;

@@ -329,7 +329,9 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
   int na = (kblocks >= 3 && 3 * p.a_bytes + 4 * b_stage_bytes <= budget) ? 3 : 2;
   if (na > kblocks) na = kblocks;
   int nb = (budget - na * p.a_bytes) / b_stage_bytes;
-  if (nb > 9) nb = 9;
+  if (nb > 8) nb = 8;
+  if (tap_split) nb &= ~1;   // EVEN: each issuer then owns the weight slots of its parity and sees every phase of their barriers
+                             // (an odd ring would bring an issuer back to a slot two phases later -- parity waits cannot tell)
   if (nb < 2) return 0;
   p.na = na; p.nb = nb;
   // the windows of the last unit read up to 2*dil positions past their stage: the weight ring follows the halo ring

@@ -7,13 +7,48 @@
 // gathers are 16-byte loads of pixel-major rows, the validity mask is computed
 // once per pixel (not per channel), and the per-(image,channel) sum / sum of
 // squares that normalize_features (model/upflow.py:94-137) needs afterwards
-// are reduced on the fly (registers -> shared memory -> one double atomic per
-// channel per CTA).
+// are reduced on the fly (registers -> warp shuffles -> one shared-memory slot per
+// warp -> one double atomic per channel per CTA).
 #include "upf_common.cuh"
 
 namespace upf {
 
 constexpr int WARP_NT = 256;
+
+// CTA reduction of the per-thread fp32 partial moments, in double and in a FIXED order: xor-shuffle tree over the
+// lanes of a warp that own the same channels, one shared-memory slot per warp (no shared-memory atomics: 4096
+// contended double CAS loops per CTA cost more than the warp itself -- 39 vs 16 us at 2x32x94x311), warps summed in
+// index order, then one global atomicAdd per channel and CTA (exact in double for fp32-valued partials, so the
+// result does not depend on the order the CTAs arrive in).   s_red: [WARP_NT/32][2][4*cgroups] doubles.
+__device__ __forceinline__ void cta_reduce_moments(const float (&sm)[2][4], const float (&sq)[2][4], int lpp, int sub, int passes,
+                                                   int C, int cgroups, double* s_red, double* stats_n) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nch = cgroups * 4;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int c = (pass * lpp + sub) * 4;
+    const bool active = pass < passes && c < C;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      double a = active ? (double)sm[pass][k] : 0.0, b = active ? (double)sq[pass][k] : 0.0;
+      for (int off = lpp; off < 32; off <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+      }
+      if (active && lane < lpp) {
+        s_red[(size_t)(warp * 2 + 0) * nch + c + k] = a;
+        s_red[(size_t)(warp * 2 + 1) * nch + c + k] = b;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += WARP_NT) {
+    const int which = i / C, c = i - which * C;
+    double t = 0.0;
+    for (int w = 0; w < WARP_NT / 32; ++w) t += s_red[(size_t)(w * 2 + which) * nch + c];
+    atomicAdd(&stats_n[(size_t)c * 2 + which], t);
+  }
+}
 
 // thread layout: `lpp` lanes per pixel (each lane owns 4 consecutive channels
 // per pass), WARP_NT/lpp pixels per CTA step; a CTA strides over the pixels of
@@ -97,28 +132,7 @@ warp_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ 
     }
   }
 
-  if (stats) {
-    // CTA reduction in double: s_red[k] (sum), s_red[4*cgroups + k] (sum of squares)
-    const int nch = cgroups * 4;
-    for (int i = threadIdx.x; i < 2 * nch; i += WARP_NT) s_red[i] = 0.0;
-    __syncthreads();
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      const int c = (pass * lpp + sub) * 4;
-      if (pass < passes && c < C) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          atomicAdd(&s_red[c + k], (double)sm[pass][k]);
-          atomicAdd(&s_red[nch + c + k], (double)sq[pass][k]);
-        }
-      }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += WARP_NT) {
-      atomicAdd(&stats[((size_t)n * C + c) * 2 + 0], s_red[c]);
-      atomicAdd(&stats[((size_t)n * C + c) * 2 + 1], s_red[nch + c]);
-    }
-  }
+  if (stats) cta_reduce_moments(sm, sq, lpp, sub, passes, C, cgroups, s_red, stats + (size_t)n * C * 2);
 }
 
 // moments of an existing tensor (same reduction skeleton, no sampling)
@@ -157,25 +171,7 @@ featnorm_stats_kernel(const float* __restrict__ x, int ldx, int H, int W, int C,
       for (int k = 0; k < 4; ++k) { sm[pass][k] += v[k]; sq[pass][k] = fmaf(v[k], v[k], sq[pass][k]); }
     }
   }
-  const int nch = cgroups * 4;
-  for (int i = threadIdx.x; i < 2 * nch; i += WARP_NT) s_red[i] = 0.0;
-  __syncthreads();
-#pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-    const int c = (pass * lpp + sub) * 4;
-    if (pass < passes && c < C) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        atomicAdd(&s_red[c + k], (double)sm[pass][k]);
-        atomicAdd(&s_red[nch + c + k], (double)sq[pass][k]);
-      }
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += WARP_NT) {
-    atomicAdd(&stats[((size_t)n * C + c) * 2 + 0], s_red[c]);
-    atomicAdd(&stats[((size_t)n * C + c) * 2 + 1], s_red[nch + c]);
-  }
+  cta_reduce_moments(sm, sq, lpp, sub, passes, C, cgroups, s_red, stats + (size_t)n * C * 2);
 }
 
 __global__ void __launch_bounds__(256)
@@ -279,7 +275,7 @@ extern "C" int upf_warp_fwd(const float* x, int ldx, const float* flow, int ldf,
   if (per_image > cap) per_image = cap;
   if (per_image < 1) per_image = 1;
   const bool vec = (C % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(x) && aligned16(out);
-  const size_t smem = stats ? (size_t)2 * ((C + 3) / 4) * 4 * sizeof(double) : 0;
+  const size_t smem = stats ? (size_t)(WARP_NT / 32) * 2 * ((C + 3) / 4) * 4 * sizeof(double) : 0;
   if (vec)
     warp_fwd_kernel<true><<<N * per_image, WARP_NT, smem, (cudaStream_t)stream>>>(x, ldx, flow, ldf, out, ldo, H, W, C,
                                                                                  align_corners, mask_threshold, stats, lpp, per_image, x_batch_shift, N);
@@ -314,7 +310,7 @@ extern "C" int upf_featnorm_stats(const float* x, int ldx, int N, int H, int W, 
   if (per_image > cap) per_image = cap;
   if (per_image < 1) per_image = 1;
   const int vec = (C % 4 == 0) && (ldx % 4 == 0) && aligned16(x);
-  const size_t smem = (size_t)2 * ((C + 3) / 4) * 4 * sizeof(double);
+  const size_t smem = (size_t)(WARP_NT / 32) * 2 * ((C + 3) / 4) * 4 * sizeof(double);
   featnorm_stats_kernel<<<N * per_image, WARP_NT, smem, (cudaStream_t)stream>>>(x, ldx, H, W, C, stats, lpp, per_image, vec);
   return check_launch("featnorm_stats");
 }
