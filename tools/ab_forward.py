@@ -11,14 +11,14 @@ H, W, B = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "kitti_375x1242_
 sd = bench.make_weights()
 im1, im2 = bench.synth_inputs(B, H, W, 1234)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-# (name, win mode (bit0 on, bit1 every Cout), win min Cin, halo enabled)
+# (name, win mode (bit0 on, bit1 every Cout), win min Cin, halo enabled, PDL off)
 HALO = (65 << 16) | (128 << 8)
-variants = [("win<=64 + halo", 1, 0, 1), ("win off, halo", 0, 0, 1), ("win all Cout", 3, 0, 1), ("win<=64 Cin>=64 + halo", 1, 64, 1), ("win off, halo off", 0, 0, 0)]
+variants = [("default", 1, 0, 1, 0), ("PDL off", 1, 0, 1, 8), ("win all Cout", 3, 0, 1, 0), ("win off, halo", 0, 0, 1, 0)]
 ref = None
 for rep in range(2):
-    for name, wmode, wmin, hen in variants:
+    for name, wmode, wmin, hen, nopdl in variants:
         lib.upf_debug_conv_win(wmode, wmin, 0)
-        lib.upf_debug_conv_halo(hen, HALO)
+        lib.upf_debug_conv_halo(hen, HALO | nopdl)
         eng = DecoderEngine({k: v.cuda() for k, v in sd.items()}, precision="tf32")
         with torch.no_grad():
             g = eng.capture(B, H, W)

@@ -20,6 +20,7 @@ conv_simt_kernel(const float* __restrict__ x, int ldx, const float* __restrict__
                  float* __restrict__ out, int ldo, const float* __restrict__ res, int ldr,
                  int N, int H, int W, int Ho, int Wo, int Cin, int Cout, int cout_pad,
                  int ks, int stride, int dil, float slope, int vec_in) {
+  pdl_prologue();
   static_assert((BM / TM) * (BN / TN) == CS_NT, "thread grid");
   constexpr int A_PER = BM * CS_BK / 4 / CS_NT;      // float4 loads of A per thread per stage
   static_assert(A_PER >= 1, "tile too small");
@@ -151,7 +152,7 @@ static void launch_simt(const float* x, int ldx, const float* w, const float* bi
                         int cout_pad, int ks, int stride, int dil, float slope, int vec_in, cudaStream_t st) {
   const long long M = (long long)N * Ho * Wo;
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((cout_pad + BN - 1) / BN));
-  conv_simt_kernel<BM, BN, TM, TN><<<grid, CS_NT, 0, st>>>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cin,
+  UPF_LAUNCH((conv_simt_kernel<BM, BN, TM, TN>), grid, CS_NT, 0, st, x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cin,
                                                           Cout, cout_pad, ks, stride, dil, slope, vec_in);
 }
 
@@ -159,65 +160,91 @@ static void launch_simt(const float* x, int ldx, const float* w, const float* bi
 // ---------------------------------------------------------------- first layers: 3x3, Cin <= 4 (the RGB image)
 // The image convolutions (FeatureExtractor conv 3->16 stride 2, model/pwc_modules.py:122-142, and the full-resolution
 // 3->16 of the output-level SGU, model/upflow.py:360-372) have K = 27: the implicit-GEMM tiles above spend their time
-// on staging (152 us at 2x375x1242, against 71 MB = 11 us of HBM traffic).  Direct form: Cout/4 threads per output
-// pixel, each owning 4 output channels -- a warp writes 32/(Cout/4) pixels x Cout channels as one contiguous run of
-// 16-byte stores; the 27 inputs come through L1 (neighbouring pixels share them), the weights from shared memory.
-template <int CIN>
+// on staging (152 us at 2x375x1242, against 71 MB = 11 us of HBM traffic).  Direct form, persistent CTAs (weights are
+// staged in shared memory once): a thread owns C3_PX consecutive output pixels x 4 output channels, so every input
+// value it loads (through L1; neighbouring threads share them) and every weight quad is used C3_PX times;
+// Cout/4 threads share a pixel group, and a warp's stores are 64-byte runs.
+constexpr int C3_PX = 4;
+
+template <int CIN, int STRIDE>
 __global__ void __launch_bounds__(256)
 conv_c3_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ bias,
                float* __restrict__ out, int ldo, const float* __restrict__ res, int ldr,
-               int N, int H, int W, int Ho, int Wo, int Cout, int cout_pad, int stride, float slope) {
+               int N, int H, int W, int Ho, int Wo, int Cout, int cout_pad, float slope) {
+  pdl_prologue();
   extern __shared__ float s_w[];                         // [9*CIN][cout_pad] then bias[cout_pad]
   for (int i = threadIdx.x; i < 9 * CIN * cout_pad; i += blockDim.x) s_w[i] = __ldg(w + i);
   float* s_b = s_w + 9 * CIN * cout_pad;
   for (int i = threadIdx.x; i < cout_pad; i += blockDim.x) s_b[i] = i < Cout ? __ldg(bias + i) : 0.f;
   __syncthreads();
-  const int tpp = cout_pad >> 2;                         // threads per pixel (power of two <= 32)
+  constexpr int COLS = (C3_PX - 1) * STRIDE + 3;         // input columns a thread touches
+  const int tpp = cout_pad >> 2;                         // threads per pixel group (power of two <= 32)
+  const int sh = __ffs(tpp) - 1;
   const bool vec_out = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  // persistent CTAs (the weights are staged once): a work item is 256/tpp consecutive pixels of one output row
-  const int ppb = 256 >> (__ffs(tpp) - 1);               // pixels per item (tpp is a power of two)
-  const int nxb = (Wo + ppb - 1) / ppb;
+  const int gpb = 256 >> sh;                             // pixel groups per work item
+  const int ngx = (Wo + C3_PX - 1) / C3_PX;              // pixel groups per output row
+  const int nxb = (ngx + gpb - 1) / gpb;
   const int items = nxb * Ho * N;
   const int c0 = (threadIdx.x & (tpp - 1)) * 4;
+  // (staging the three input rows in shared memory was measured and is SLOWER: 68 vs 56 us at 2x375x1242 -- the two
+  //  extra CTA barriers per item cost more than the gathers through L1)
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int xb = item % nxb, row = item / nxb;         // CTA-uniform
     const int oy = row % Ho;
     const long long n = row / Ho;
-    const int ox = xb * ppb + (threadIdx.x >> (__ffs(tpp) - 1));
-    if (ox >= Wo) continue;
-    const long long pix = (n * Ho + oy) * Wo + ox;
-    float4 acc = *reinterpret_cast<const float4*>(s_b + c0);
-    const float* xn = x + (size_t)n * H * W * ldx;
+    const int g = xb * gpb + (threadIdx.x >> sh);
+    if (g >= ngx) continue;
+    const int ox0 = g * C3_PX;
+    float4 acc[C3_PX];
+    const float4 b4 = *reinterpret_cast<const float4*>(s_b + c0);
+#pragma unroll
+    for (int j = 0; j < C3_PX; ++j) acc[j] = b4;
+    const int ix0 = ox0 * STRIDE - 1;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      const int iy = oy * stride + ky - 1;
-      if (iy < 0 || iy >= H) continue;
+      const int iy = oy * STRIDE + ky - 1;
+      if (iy < 0 || iy >= H) continue;                   // warp-uniform (one output row per item)
+      const float* prow = x + (((size_t)n * H + iy) * W) * ldx;
+      float v[COLS][CIN];
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = ox * stride + kx - 1;
-        if (ix < 0 || ix >= W) continue;
-        const float* px = xn + ((size_t)iy * W + ix) * ldx;
+      for (int cx = 0; cx < COLS; ++cx) {
+        const int ix = ix0 + cx;
+        const bool in = ix >= 0 && ix < W;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) v[cx][ci] = in ? __ldg(prow + (size_t)ix * ldx + ci) : 0.f;
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {
-          const float v = __ldg(px + ci);
           const float4 wv = *reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * CIN + ci) * cout_pad + c0);
-          acc.x = fmaf(v, wv.x, acc.x); acc.y = fmaf(v, wv.y, acc.y); acc.z = fmaf(v, wv.z, acc.z); acc.w = fmaf(v, wv.w, acc.w);
+#pragma unroll
+          for (int j = 0; j < C3_PX; ++j) {
+            const float a = v[j * STRIDE + kx][ci];
+            acc[j].x = fmaf(a, wv.x, acc[j].x); acc[j].y = fmaf(a, wv.y, acc[j].y);
+            acc[j].z = fmaf(a, wv.z, acc[j].z); acc[j].w = fmaf(a, wv.w, acc[j].w);
+          }
         }
+    }
+#pragma unroll
+    for (int j = 0; j < C3_PX; ++j) {
+      const int ox = ox0 + j;
+      if (ox >= Wo) break;
+      const long long pix = (n * Ho + oy) * Wo + ox;
+      float f[4] = {lrelu(acc[j].x, slope), lrelu(acc[j].y, slope), lrelu(acc[j].z, slope), lrelu(acc[j].w, slope)};
+      if (res) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (c0 + k < Cout) f[k] += __ldg(res + (size_t)pix * ldr + c0 + k);
       }
-    }
-    float f[4] = {lrelu(acc.x, slope), lrelu(acc.y, slope), lrelu(acc.z, slope), lrelu(acc.w, slope)};
-    if (res) {
+      float* o = out + (size_t)pix * ldo + c0;
+      if (vec_out && c0 + 4 <= Cout) {
+        *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+      } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (c0 + k < Cout) f[k] += __ldg(res + (size_t)pix * ldr + c0 + k);
-    }
-    float* o = out + (size_t)pix * ldo + c0;
-    if (vec_out && c0 + 4 <= Cout) {
-      *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (c0 + k < Cout) o[k] = f[k];
+        for (int k = 0; k < 4; ++k)
+          if (c0 + k < Cout) o[k] = f[k];
+      }
     }
   }
 }
@@ -225,12 +252,17 @@ conv_c3_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w
 template <int CIN>
 static int launch_c3(const float* x, int ldx, const float* w, const float* bias, float* out, int ldo, const float* res, int ldr,
                      int N, int H, int W, int Ho, int Wo, int Cout, int cout_pad, int stride, float slope, cudaStream_t st) {
+  const int gpb = 256 / (cout_pad >> 2);
   const size_t smem = (size_t)(9 * CIN + 1) * cout_pad * sizeof(float);
-  const int ppb = 256 / (cout_pad >> 2);
-  long long items = (long long)((Wo + ppb - 1) / ppb) * Ho * N;
+  const int ngx = (Wo + C3_PX - 1) / C3_PX;
+  const long long items = (long long)((ngx + gpb - 1) / gpb) * Ho * N;
   UPF_REQUIRE(items < (1ll << 31), "conv_c3: too many pixels");
   const long long cap = (long long)UPF_NUM_SMS * 8;
-  conv_c3_kernel<CIN><<<(unsigned)(items < cap ? items : cap), 256, smem, st>>>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, stride, slope);
+  const unsigned grid = (unsigned)(items < cap ? items : cap);
+  if (stride == 1)
+    UPF_LAUNCH((conv_c3_kernel<CIN, 1>), grid, 256, smem, st, x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, slope);
+  else
+    UPF_LAUNCH((conv_c3_kernel<CIN, 2>), grid, 256, smem, st, x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, slope);
   return check_launch("conv_c3");
 }
 
@@ -244,7 +276,7 @@ int conv2d_fwd_simt(const float* x, int ldx, const float* w, const float* bias, 
   const int cout_pad = (Cout + 3) & ~3;
   UPF_REQUIRE(aligned16(w), "conv: weights must be 16-byte aligned");
   const int vec_in = (ldx % 4 == 0) && aligned16(x);
-  if (ks == 3 && dil == 1 && Cin <= 4 && (cout_pad == 4 || cout_pad == 8 || cout_pad == 16 || cout_pad == 32)) {
+  if (ks == 3 && dil == 1 && (stride == 1 || stride == 2) && Cin <= 4 && (cout_pad == 4 || cout_pad == 8 || cout_pad == 16 || cout_pad == 32)) {
     switch (Cin) {
       case 1: return launch_c3<1>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, stride, slope, st);
       case 2: return launch_c3<2>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, stride, slope, st);

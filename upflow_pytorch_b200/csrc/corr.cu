@@ -114,6 +114,7 @@ corr_fwd_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__
                 float* __restrict__ out, int ldo, int H, int W, int C,
                 const double* __restrict__ stats1, const double* __restrict__ stats2,
                 float slope, int tiles_x, int tiles_y, int n2_shift, int N) {
+  pdl_prologue();
   using K = CorrCfg<D>;
   extern __shared__ __align__(128) float smem[];
   float* s_f2 = smem;
@@ -246,10 +247,10 @@ static int launch_corr_fwd(const float* f1, int ld1, const float* f2, int ld2, f
     attr_done = true;
   }
   if (vec) {
-    corr_fwd_kernel<D, true><<<(unsigned)tiles, K::NT, K::SMEM_BYTES, st>>>(f1, ld1, f2, ld2, out, ldo, H, W, C, s1, s2,
+    UPF_LAUNCH((corr_fwd_kernel<D, true>), (unsigned)tiles, K::NT, K::SMEM_BYTES, st, f1, ld1, f2, ld2, out, ldo, H, W, C, s1, s2,
                                                                           slope, tiles_x, tiles_y, shift, N);
   } else {
-    corr_fwd_kernel<D, false><<<(unsigned)tiles, K::NT, K::SMEM_BYTES, st>>>(f1, ld1, f2, ld2, out, ldo, H, W, C, s1,
+    UPF_LAUNCH((corr_fwd_kernel<D, false>), (unsigned)tiles, K::NT, K::SMEM_BYTES, st, f1, ld1, f2, ld2, out, ldo, H, W, C, s1,
                                                                            s2, slope, tiles_x, tiles_y, shift, N);
   }
   return check_launch("corr_fwd");
@@ -267,6 +268,7 @@ corr_bwd_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__
                 const float* __restrict__ outv, int ldo, const float* __restrict__ go, int ldg,
                 float* __restrict__ g1, int ldg1, float* __restrict__ g2, int ldg2,
                 int N, int H, int W, int C, int D, float slope) {
+  pdl_prologue();
   const int cg = (C + 3) >> 2;
   const long long total = (long long)N * H * W * cg;
   const int WIN = 2 * D + 1;
@@ -328,6 +330,7 @@ corr_small_kernel(const float* __restrict__ f1, int ld1, const float* __restrict
                   float* __restrict__ out, int ldo, int H, int W, int C, int D,
                   const double* __restrict__ stats1, const double* __restrict__ stats2,
                   float slope, int n2_shift, int N) {
+  pdl_prologue();
   extern __shared__ __align__(16) float sm[];        // a[Cp] | mean2[Cp] | rstd2[Cp]
   const int Cp = (C + 3) & ~3;
   float* s_a = sm;
@@ -421,9 +424,9 @@ static int launch_corr_small(const float* f1, int ld1, const float* f2, int ld2,
   const size_t smem = (size_t)3 * ((C + 3) & ~3) * sizeof(float);
   const unsigned grid = (unsigned)((long long)N * H * W);
   if (vec)
-    corr_small_kernel<true><<<grid, threads, smem, st>>>(f1, ld1, f2, ld2, out, ldo, H, W, C, D, s1, s2, slope, shift, N);
+    UPF_LAUNCH((corr_small_kernel<true>), grid, threads, smem, st, f1, ld1, f2, ld2, out, ldo, H, W, C, D, s1, s2, slope, shift, N);
   else
-    corr_small_kernel<false><<<grid, threads, smem, st>>>(f1, ld1, f2, ld2, out, ldo, H, W, C, D, s1, s2, slope, shift, N);
+    UPF_LAUNCH((corr_small_kernel<false>), grid, threads, smem, st, f1, ld1, f2, ld2, out, ldo, H, W, C, D, s1, s2, slope, shift, N);
   return check_launch("corr_small");
 }
 
@@ -475,7 +478,7 @@ extern "C" int upf_corr_lrelu_bwd(const float* f1, int ld1, const float* f2, int
   const long long total = (long long)N * H * W * ((C + 3) / 4);
   long long blocks = (total + 255) / 256;
   if (blocks > UPF_NUM_SMS * 32) blocks = UPF_NUM_SMS * 32;
-  corr_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(f1, ld1, f2, ld2, slope == 1.0f ? nullptr : out,
+  UPF_LAUNCH((corr_bwd_kernel), (unsigned)blocks, 256, 0, (cudaStream_t)stream, f1, ld1, f2, ld2, slope == 1.0f ? nullptr : out,
                                                                      ldo, grad_out, ldg, grad_f1, ldg1, grad_f2, ldg2,
                                                                      N, H, W, C, max_disp, slope);
   return check_launch("corr_bwd");

@@ -57,6 +57,7 @@ corr_pipe_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant
                  float* __restrict__ out, int ldo, int H, int W, int C,
                  const double* __restrict__ stats1, const double* __restrict__ stats2,
                  float slope, int tiles_x, int tiles_y, int n2_shift, int N, int total_tiles) {
+  pdl_prologue();
   using K = CPCfg<D>;
   extern __shared__ __align__(1024) float smem_raw_f[];
   // (pointer arithmetic on the __shared__ array keeps every access an LDS/STS)
@@ -296,7 +297,7 @@ static int launch_corr_pipe_t(const float* f1, int ld1, const float* f2, int ld2
     if (e) return e;
   }
   const unsigned grid = (unsigned)(tiles < UPF_NUM_SMS ? tiles : UPF_NUM_SMS);
-  corr_pipe_kernel<D><<<grid, K::NT, K::SMEM_BYTES, st>>>(m1, m2, out, ldo, H, W, C, s1, s2, slope, tiles_x, tiles_y, shift,
+  UPF_LAUNCH((corr_pipe_kernel<D>), grid, K::NT, K::SMEM_BYTES, st, m1, m2, out, ldo, H, W, C, s1, s2, slope, tiles_x, tiles_y, shift,
                                                           N, (int)tiles);
   return check_launch("corr_pipe");
 }

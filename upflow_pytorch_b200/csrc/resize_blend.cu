@@ -15,6 +15,7 @@ namespace upf {
 __global__ void __launch_bounds__(256)
 resize_bilinear_kernel(const float* __restrict__ in, int ldi, int h, int w, float* __restrict__ out, int ldo,
                        int H, int W, int N, int C, float sh, float sw, float4 mul) {
+  pdl_prologue();
   const long long total = (long long)N * H * W;
   const float m[4] = {mul.x, mul.y, mul.z, mul.w};
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(256)
 sgu_blend_kernel(const float* __restrict__ flow_init, int ldf, const float* __restrict__ inter, int ldi, int ih, int iw,
                  float* __restrict__ out, int ldo, int N, int H, int W, int align_corners,
                  float sh, float sw, float rate_u, float rate_v) {
+  pdl_prologue();
   const long long total = (long long)N * H * W;
   const bool same = (ih == H && iw == W);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -101,6 +103,7 @@ sgu_blend_kernel(const float* __restrict__ flow_init, int ldf, const float* __re
 // sides stay coalesced.
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int ldo, int C, int HW) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -118,6 +121,7 @@ nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int l
 
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int C, int HW) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -136,6 +140,7 @@ nhwc_to_nchw_kernel(const float* __restrict__ in, int ldi, float* __restrict__ o
 __global__ void __launch_bounds__(256)
 copy_channels_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int ldo, long long npix, int C,
                      int vec) {
+  pdl_prologue();
   if (vec) {
     const int cg = C >> 2;
     const long long total = npix * cg;
@@ -173,7 +178,7 @@ extern "C" int upf_resize_bilinear(const float* in, int ldi, int h, int w, float
     float* m = &mul.x;
     for (int c = 0; c < C; ++c) m[c] = scale_host[c];
   }
-  resize_bilinear_kernel<<<grid_for((long long)N * H * W), 256, 0, (cudaStream_t)stream>>>(
+  UPF_LAUNCH((resize_bilinear_kernel), grid_for((long long)N * H * W), 256, 0, (cudaStream_t)stream, 
       in, ldi, h, w, out, ldo, H, W, N, C, host_ac_scale(h, H), host_ac_scale(w, W), mul);
   return check_launch("resize_bilinear");
 }
@@ -186,7 +191,7 @@ extern "C" int upf_sgu_blend(const float* flow_init, int ldf, const float* inter
   UPF_REQUIRE(out != flow_init, "sgu_blend: cannot run in place (neighbouring pixels are gathered)");
   // rate = ratio of SIZES as python floats (model/pwc_modules.py:84-85), rounded to fp32 at the multiply
   const float rate_u = (float)((double)W / (double)iw), rate_v = (float)((double)H / (double)ih);
-  sgu_blend_kernel<<<grid_for((long long)N * H * W), 256, 0, (cudaStream_t)stream>>>(
+  UPF_LAUNCH((sgu_blend_kernel), grid_for((long long)N * H * W), 256, 0, (cudaStream_t)stream, 
       flow_init, ldf, inter, ldi, ih, iw, out, ldo, N, H, W, align_corners, host_ac_scale(ih, H), host_ac_scale(iw, W),
       rate_u, rate_v);
   return check_launch("sgu_blend");
@@ -198,7 +203,7 @@ extern "C" int upf_nchw_to_nhwc(const float* in, float* out, int ldo, int N, int
   UPF_REQUIRE(N <= 65535 && (C + 31) / 32 <= 65535, "nchw_to_nhwc: N or C too large");
   const int HW = H * W;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N);
-  nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, ldo, C, HW);
+  UPF_LAUNCH((nchw_to_nhwc_kernel), grid, 256, 0, (cudaStream_t)stream, in, out, ldo, C, HW);
   return check_launch("nchw_to_nhwc");
 }
 
@@ -208,7 +213,7 @@ extern "C" int upf_nhwc_to_nchw(const float* in, int ldi, float* out, int N, int
   UPF_REQUIRE(N <= 65535 && (C + 31) / 32 <= 65535, "nhwc_to_nchw: N or C too large");
   const int HW = H * W;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N);
-  nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, ldi, out, C, HW);
+  UPF_LAUNCH((nhwc_to_nchw_kernel), grid, 256, 0, (cudaStream_t)stream, in, ldi, out, C, HW);
   return check_launch("nhwc_to_nchw");
 }
 
@@ -216,6 +221,6 @@ extern "C" int upf_copy_channels(const float* in, int ldi, float* out, int ldo, 
   using namespace upf;
   UPF_REQUIRE(in && out && npix > 0 && C > 0 && ldi >= C && ldo >= C, "copy_channels: bad argument");
   const int vec = (C % 4 == 0) && (ldi % 4 == 0) && (ldo % 4 == 0) && aligned16(in) && aligned16(out);
-  copy_channels_kernel<<<grid_for(npix * (vec ? C / 4 : C)), 256, 0, (cudaStream_t)stream>>>(in, ldi, out, ldo, npix, C, vec);
+  UPF_LAUNCH((copy_channels_kernel), grid_for(npix * (vec ? C / 4 : C)), 256, 0, (cudaStream_t)stream, in, ldi, out, ldo, npix, C, vec);
   return check_launch("copy_channels");
 }

@@ -34,6 +34,33 @@ inline int check_launch(const char* what) {
     }                                     \
   } while (0)
 
+// Programmatic dependent launch (PDL).  Every forward kernel starts with pdl_prologue(): it lets the NEXT kernel in the
+// stream be scheduled while this one runs, and then waits until the PREVIOUS grid has completed and flushed -- so the
+// only thing that overlaps is launch latency and CTA scheduling, never data.  UPF_LAUNCH adds the matching launch
+// attribute (upf_debug_conv_halo bit 3 turns it off for A/B runs).  Inside a captured graph the edges become
+// programmatic dependencies: bit-identical results, a few microseconds less per launch.
+extern int g_tc_pdl;
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory");
+}
+struct PdlLaunch {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  PdlLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_tc_pdl ? 1 : 0;
+  }
+};
+#define UPF_LAUNCH(kernel, grid, block, smem, st, ...)                      \
+  do {                                                                      \
+    upf::PdlLaunch _l(dim3(grid), dim3(block), (size_t)(smem), (st));       \
+    (void)cudaLaunchKernelEx(&_l.cfg, kernel, __VA_ARGS__);                 \
+  } while (0)
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v < 0.f ? v * slope : v; }

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(WARP_NT)
 warp_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ flow, int ldf,
                 float* __restrict__ out, int ldo, int H, int W, int C, int align_corners, float mask_thr,
                 double* __restrict__ stats, int lpp, int ctas_per_image, int x_shift, int N) {
+  pdl_prologue();
   extern __shared__ double s_red[];   // [2][cgroups*4] when stats
   const int n = blockIdx.x / ctas_per_image;
   const int cta = blockIdx.x - n * ctas_per_image;
@@ -139,6 +140,7 @@ warp_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ 
 __global__ void __launch_bounds__(WARP_NT)
 featnorm_stats_kernel(const float* __restrict__ x, int ldx, int H, int W, int C, double* __restrict__ stats,
                       int lpp, int ctas_per_image, int vec) {
+  pdl_prologue();
   extern __shared__ double s_red[];
   const int n = blockIdx.x / ctas_per_image;
   const int cta = blockIdx.x - n * ctas_per_image;
@@ -177,6 +179,7 @@ featnorm_stats_kernel(const float* __restrict__ x, int ldx, int H, int W, int C,
 __global__ void __launch_bounds__(256)
 featnorm_apply_kernel(const float* __restrict__ x, int ldx, const double* __restrict__ stats,
                       float* __restrict__ out, int ldo, int H, int W, int C, long long total) {
+  pdl_prologue();
   const double npix = (double)H * (double)W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(256)
 warp_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ flow, int ldf,
                 const float* __restrict__ go, int ldg, float* __restrict__ gx, int ldgx,
                 float* __restrict__ gflow, int ldgf, int N, int H, int W, int C, int align_corners, float mask_thr) {
+  pdl_prologue();
   // one warp per pixel, lanes stride over channels
   const long long npix = (long long)N * H * W;
   const int lane = threadIdx.x & 31;
@@ -277,10 +281,10 @@ extern "C" int upf_warp_fwd(const float* x, int ldx, const float* flow, int ldf,
   const bool vec = (C % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(x) && aligned16(out);
   const size_t smem = stats ? (size_t)(WARP_NT / 32) * 2 * ((C + 3) / 4) * 4 * sizeof(double) : 0;
   if (vec)
-    warp_fwd_kernel<true><<<N * per_image, WARP_NT, smem, (cudaStream_t)stream>>>(x, ldx, flow, ldf, out, ldo, H, W, C,
+    UPF_LAUNCH((warp_fwd_kernel<true>), N * per_image, WARP_NT, smem, (cudaStream_t)stream, x, ldx, flow, ldf, out, ldo, H, W, C,
                                                                                  align_corners, mask_threshold, stats, lpp, per_image, x_batch_shift, N);
   else
-    warp_fwd_kernel<false><<<N * per_image, WARP_NT, smem, (cudaStream_t)stream>>>(x, ldx, flow, ldf, out, ldo, H, W, C,
+    UPF_LAUNCH((warp_fwd_kernel<false>), N * per_image, WARP_NT, smem, (cudaStream_t)stream, x, ldx, flow, ldf, out, ldo, H, W, C,
                                                                                   align_corners, mask_threshold, stats, lpp, per_image, x_batch_shift, N);
   return check_launch("warp_fwd");
 }
@@ -294,7 +298,7 @@ extern "C" int upf_warp_bwd(const float* x, int ldx, const float* flow, int ldf,
   const long long npix = (long long)N * H * W;
   long long blocks = (npix * 32 + 255) / 256;
   if (blocks > UPF_NUM_SMS * 16) blocks = UPF_NUM_SMS * 16;
-  warp_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, flow, ldf, grad_out, ldg, grad_x, ldgx,
+  UPF_LAUNCH((warp_bwd_kernel), (unsigned)blocks, 256, 0, (cudaStream_t)stream, x, ldx, flow, ldf, grad_out, ldg, grad_x, ldgx,
                                                                      grad_flow, ldgf, N, H, W, C, align_corners, mask_threshold);
   return check_launch("warp_bwd");
 }
@@ -311,7 +315,7 @@ extern "C" int upf_featnorm_stats(const float* x, int ldx, int N, int H, int W, 
   if (per_image < 1) per_image = 1;
   const int vec = (C % 4 == 0) && (ldx % 4 == 0) && aligned16(x);
   const size_t smem = (size_t)(WARP_NT / 32) * 2 * ((C + 3) / 4) * 4 * sizeof(double);
-  featnorm_stats_kernel<<<N * per_image, WARP_NT, smem, (cudaStream_t)stream>>>(x, ldx, H, W, C, stats, lpp, per_image, vec);
+  UPF_LAUNCH((featnorm_stats_kernel), N * per_image, WARP_NT, smem, (cudaStream_t)stream, x, ldx, H, W, C, stats, lpp, per_image, vec);
   return check_launch("featnorm_stats");
 }
 
@@ -323,6 +327,6 @@ extern "C" int upf_featnorm_apply(const float* x, int ldx, const double* stats, 
   const long long total = (long long)N * H * W * C;
   long long blocks = (total + 255) / 256;
   if (blocks > UPF_NUM_SMS * 16) blocks = UPF_NUM_SMS * 16;
-  featnorm_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, stats, out, ldo, H, W, C, total);
+  UPF_LAUNCH((featnorm_apply_kernel), (unsigned)blocks, 256, 0, (cudaStream_t)stream, x, ldx, stats, out, ldo, H, W, C, total);
   return check_launch("featnorm_apply");
 }
