@@ -2,7 +2,9 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from upflow_pytorch_b200 import ops
+from upflow_pytorch_b200 import ops, _ext
+if len(sys.argv) > 1:
+    _ext.load().upf_debug_corr_pipe(int(sys.argv[1]))   # 0 = tiled kernel only, n > 1 = pipelined kernel from n tiles on
 peak = 6547.8
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for (N, C, h, w) in ((2, 32, 270, 480), (2, 32, 94, 311), (2, 64, 47, 156), (2, 196, 6, 20)):

@@ -1,145 +1,172 @@
 // Correlation + normalisation + LeakyReLU, pipelined variant for large images
-// (max_disp <= 4, C % 4 == 0): persistent CTAs (one per SM), warp-specialised.
+// (C % 4 == 0): persistent CTAs (one per SM), warp-specialised, mbarrier ring.
 //
 // corr.cu's tiled kernel alternates "stage a tile" and "compute a tile" inside
 // every CTA and relies on a second resident CTA for overlap; ncu shows the two
 // phases serialised most of the time (35 % of stall samples wait on the staging
-// loads, 25 % FMA-pipe utilisation).  Here three warp roles run concurrently:
-//   * (2d+1) COMPUTE warps run the same register-tiled inner product as corr.cu
-//     (warp = horizontal displacement, lane = tile column, 8 rows x (2d+1)
-//     vertical displacements per thread) on 16-channel chunks;
-//   * two LOADER warps fetch the NEXT chunk (of this tile or of the CTA's next
-//     tile) by TMA into the other half of a two-stage shared-memory ring: two box
-//     loads per chunk (f2 search window {16 ch, 40, 16}, f1 tile {16 ch, 32, 8}),
-//     SWIZZLE_64B, out-of-bounds zero fill = the zero padding of the correlation;
-//     it waits for the bytes (mbarrier) and applies the normalisation
-//     (x-mean)*(1/std) in place to the in-image positions;
-//   * one STORER warp copies the finished (2d+1)^2-float result rows from the
-//     transpose buffer to global memory while the compute warps are already in
-//     the next tile.
-// Named barriers (bar.sync / bar.arrive) hand the stages and the transpose
-// buffer back and forth; there is no __syncthreads in the steady state.
-// Shared-memory rows are 64 bytes (16 channels); the 16-byte chunk index is
-// XOR-swizzled with (position >> 1) & 3 (= TMA's SWIZZLE_64B) so that 8
+// loads, 25 % FMA-pipe utilisation).  Here the roles run concurrently:
+//   * (2d+1) COMPUTE warps run the register-tiled inner product (warp =
+//     horizontal displacement, lane = tile column, TY rows x (2d+1) vertical
+//     displacements per thread) on 8-channel chunks;
+//   * one ISSUER thread keeps a ring of four chunks in flight by TMA: two box
+//     loads per chunk (f2 search window {8 ch, TX+2d, TY+2d}, f1 tile {8 ch, TX, TY}),
+//     SWIZZLE_32B, out-of-bounds zero fill = the zero padding of the correlation.
+//     It runs up to three chunks ahead of the compute warps (first version: two
+//     16-channel stages, refilled only when drained -- ncu: 14 % of the compute
+//     warps' samples waited for the load, HBM latency under load is 2-3 us);
+//   * with fused normalisation two NORMALISER warps apply (x-mean)*(1/std) in
+//     place to the in-image positions of a landed chunk and hand it on.
+// Handshakes are mbarriers: full[s] (TMA bytes), ready[s] (normalised), empty[s]
+// (one arrival per compute warp).  The finished tile goes through a transpose
+// buffer (pitch = (2d+1)^2 floats, odd: conflict-free).  A contiguous output
+// ([N,H,W,(2d+1)^2], W % 4 == 0) leaves it as one shared->global BULK COPY per
+// tile row (cp.async.bulk, one thread, drained while the warps compute on); a
+// channel slice of a wider buffer is written by the compute warps of schedulers
+// 1..3, a warp per pixel.  (first version: ONE storer warp copying 83 KB per tile
+// was busy 93 % of the time and the compute warps spent 14 % of theirs waiting
+// for it.  Also tried and measured slower, 67.6 vs 61.4 us: raw sums parked
+// column-minor and six finisher warps converting and storing them.)
+// Shared-memory rows are 32 bytes (8 channels); the 16-byte chunk index is
+// XOR-swizzled with (position >> 2) & 1 (= TMA's SWIZZLE_32B) so that 8
 // consecutive lanes reading the same chunk of 8 consecutive positions hit 8
 // distinct 16-byte bank groups.
 #include "tc_common.cuh"
 
 namespace upf {
 
-constexpr int CP_TX = 32, CP_TY = 8, CP_CC = 16;   // tile, channels per chunk
-constexpr int CP_NLOAD = 2, CP_NSTORE = 1;         // loader warps (TMA wait + in-place normalisation), storer warps
+constexpr int CP_TX = 32, CP_CC = 8, CP_STAGES = 4;   // tile width, channels per chunk, ring depth
 
 template <int D>
 struct CPCfg {
   static constexpr int WIN = 2 * D + 1;
-  static constexpr int NCW = WIN;                             // compute warps
-  static constexpr int NT = (NCW + CP_NLOAD + CP_NSTORE) * 32;
-  static constexpr int HROWS = CP_TY + 2 * D;
+  static constexpr int TY = D <= 4 ? 8 : 4;                  // tile rows (the transpose buffer bounds it)
+  static constexpr int NCW = WIN;                             // compute warps 0 .. NCW-1
+  static constexpr int ISS = NCW;                             // issuer warp (one thread)
+  static constexpr int NNORM = 2;                             // normaliser warps (exit at once without statistics)
+  static constexpr int NT = (NCW + 1 + NNORM) * 32;
+  static constexpr int HROWS = TY + 2 * D;
   static constexpr int HCOLS = (CP_TX + 2 * D + 7) & ~7;
   static constexpr int HPOS = HROWS * HCOLS;
-  static constexpr int F1POS = CP_TX * CP_TY;
+  static constexpr int F1POS = CP_TX * TY;
   static constexpr int NOUT = WIN * WIN;
-  static constexpr int STAGE_FLOATS = (HPOS + F1POS) * CP_CC;
-  static constexpr int OUT_FLOATS = F1POS * NOUT;
-  static constexpr int SMEM_BYTES = (2 * STAGE_FLOATS + OUT_FLOATS) * 4 + 1024;
+  static constexpr int STAGE_FLOATS = (HPOS + F1POS) * CP_CC;  // multiple of 64 floats (256 B)
+  static constexpr int OUT_FLOATS = F1POS * NOUT;              // [pixel][displacement]: odd pitch, conflict-free
+  static constexpr int SMEM_BYTES = (CP_STAGES * STAGE_FLOATS + OUT_FLOATS) * 4 + 1024;
 };
 
-__device__ __forceinline__ int cp_swz(int pos, int chunk) { return pos * CP_CC + (((chunk ^ (pos >> 1)) & 3) << 2); }
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 
-// barrier ids: 1,2 = FULL[stage] (loaders -> compute); 3,4 = EMPTY[stage] (compute -> loaders);
-//              5 = OUT_FULL (compute -> storer); 6 = OUT_EMPTY (storer -> compute); 7 = loaders only
 template <int D>
 __global__ void __launch_bounds__(CPCfg<D>::NT, 1)
 corr_pipe_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                  float* __restrict__ out, int ldo, int H, int W, int C,
                  const double* __restrict__ stats1, const double* __restrict__ stats2,
-                 float slope, int tiles_x, int tiles_y, int n2_shift, int N, int total_tiles) {
+                 float slope, int tiles_x, int tiles_y, int n2_shift, int N, int total_tiles, int bulk_out) {
   pdl_prologue();
   using K = CPCfg<D>;
+  constexpr int TY = K::TY;
   extern __shared__ __align__(1024) float smem_raw_f[];
   // (pointer arithmetic on the __shared__ array keeps every access an LDS/STS)
   float* smem = smem_raw_f + (((1024u - (smem_u32(smem_raw_f) & 1023u)) & 1023u) >> 2);
-  float* s_out = smem + 2 * K::STAGE_FLOATS;
+  float* s_out = smem + CP_STAGES * K::STAGE_FLOATS;
   __shared__ __align__(16) float s_stat[4][256];       // mean1, rstd1, mean2, rstd2 of the image being staged
-  __shared__ uint64_t s_mbar[2];
+  __shared__ uint64_t s_full[CP_STAGES], s_ready[CP_STAGES], s_empty[CP_STAGES];
+  const bool norm = stats1 != nullptr;
   if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&s_mbar[0]), 1);
-    mbar_init(smem_u32(&s_mbar[1]), 1);
+    for (int s = 0; s < CP_STAGES; ++s) {
+      mbar_init(smem_u32(&s_full[s]), 1);
+      mbar_init(smem_u32(&s_ready[s]), K::NNORM);
+      mbar_init(smem_u32(&s_empty[s]), K::NCW);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool norm = stats1 != nullptr;
   const int nchunks = (C + CP_CC - 1) / CP_CC;
   const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  constexpr int N_FE = (K::NCW + CP_NLOAD) * 32;        // participants of FULL / EMPTY
-  constexpr int N_OUT = (K::NCW + CP_NSTORE) * 32;      // participants of OUT_FULL / OUT_EMPTY
 
-  if (warp >= K::NCW && warp < K::NCW + CP_NLOAD) {
-    // ============================== LOADER WARPS ==============================
-    const int lt = threadIdx.x - K::NCW * 32;           // 0 .. 63
-    constexpr int NLT = CP_NLOAD * 32;
-    const double npix = (double)H * (double)W;
-    int stat_n = -1;
-    long long it = 0;
-    for (int tloc = 0; tloc < my_tiles; ++tloc) {
-      int tile = blockIdx.x + tloc * gridDim.x;
-      const int tx = tile % tiles_x; tile /= tiles_x;
-      const int ty = tile % tiles_y;
-      const int n = tile / tiles_y, n2 = (n + n2_shift) % N;
-      const int x0 = tx * CP_TX, y0 = ty * CP_TY;
-      if (norm && n != stat_n) {                        // per-image statistics table (this warp only)
-        named_sync(7, NLT);
-        for (int c = lt; c < C; c += NLT) {
-          float m, sd;
-          stats_to_mean_std(stats1 + ((size_t)n * C + c) * 2, npix, m, sd);
-          s_stat[0][c] = m; s_stat[1][c] = __fdiv_rn(1.0f, sd);
-          stats_to_mean_std(stats2 + ((size_t)n2 * C + c) * 2, npix, m, sd);
-          s_stat[2][c] = m; s_stat[3][c] = __fdiv_rn(1.0f, sd);
-        }
-        named_sync(7, NLT);
-        stat_n = n;
-      }
-      for (int chunk = 0; chunk < nchunks; ++chunk, ++it) {
-        const int s = (int)(it & 1);
-        const int c0 = chunk * CP_CC;
-        if (it >= 2) named_sync(3 + s, N_FE);           // the compute warps have drained this stage
-        float* st2 = smem + s * K::STAGE_FLOATS;
-        float* st1 = st2 + K::HPOS * CP_CC;
-        if (lt == 0) {
-          // generic-proxy reads/writes of this stage (compute warps, normalisation) precede the async-proxy refill
+  if (warp == K::ISS) {
+    // ============================== ISSUER (one thread) ==============================
+    if (lane == 0) {
+      long long it = 0;
+      for (int tloc = 0; tloc < my_tiles; ++tloc) {
+        int tile = blockIdx.x + tloc * gridDim.x;
+        const int tx = tile % tiles_x; tile /= tiles_x;
+        const int ty = tile % tiles_y;
+        const int n = tile / tiles_y, n2 = (n + n2_shift) % N;
+        const int x0 = tx * CP_TX, y0 = ty * TY;
+        for (int chunk = 0; chunk < nchunks; ++chunk, ++it) {
+          const int s = (int)(it % CP_STAGES);
+          const uint32_t ph = (uint32_t)((it / CP_STAGES) & 1);
+          if (it >= CP_STAGES) mbar_wait(smem_u32(&s_empty[s]), ph ^ 1u);   // the compute warps have drained this slot
+          // generic-proxy accesses of this slot (compute warps, normalisation) precede the async-proxy refill
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          const uint32_t mb = smem_u32(&s_mbar[s]);
+          float* st2 = smem + s * K::STAGE_FLOATS;
+          float* st1 = st2 + K::HPOS * CP_CC;
+          const uint32_t mb = smem_u32(&s_full[s]);
           mbar_expect_tx(mb, (uint32_t)(K::STAGE_FLOATS * 4));
-          tma_load_4d(smem_u32(st2), &map2, mb, c0, x0 - D, y0 - D, n2);
-          tma_load_4d(smem_u32(st1), &map1, mb, c0, x0, y0, n);
+          tma_load_4d(smem_u32(st2), &map2, mb, chunk * CP_CC, x0 - D, y0 - D, n2);
+          tma_load_4d(smem_u32(st1), &map1, mb, chunk * CP_CC, x0, y0, n);
         }
-        mbar_wait(smem_u32(&s_mbar[s]), (uint32_t)((it >> 1) & 1));
-        if (norm) {
-          // in-place (x - mean) * (1/std) on the in-image positions; TMA's zero fill stays zero.  A lane keeps one
-          // 16-byte channel quad (its mean / rstd in registers) and walks positions, 8 per step.
-          const int ch = lt & 3, q0 = lt >> 2;            // 16 position slots per pass
-          const int c = c0 + ch * 4;
+      }
+    }
+  } else if (warp >= K::NCW) {
+    const int si = warp - K::NCW - 1;
+    if (norm) {
+      // ============================== NORMALISER WARPS ==============================
+      const int lt = si * 32 + lane;
+      constexpr int NLT = K::NNORM * 32, PS = K::NNORM * 16;  // threads, position slots per pass
+      const double npix = (double)H * (double)W;
+      const int ch = lt & 1, q0 = lt >> 1;                // a lane keeps one 16-byte channel quad
+      int stat_n = -1;
+      long long it = 0;
+      for (int tloc = 0; tloc < my_tiles; ++tloc) {
+        int tile = blockIdx.x + tloc * gridDim.x;
+        const int tx = tile % tiles_x; tile /= tiles_x;
+        const int ty = tile % tiles_y;
+        const int n = tile / tiles_y, n2 = (n + n2_shift) % N;
+        const int x0 = tx * CP_TX, y0 = ty * TY;
+        if (n != stat_n) {                                // per-image statistics table (these warps only)
+          named_sync(7, NLT);
+          for (int c = lt; c < C; c += NLT) {
+            float m, sd;
+            stats_to_mean_std(stats1 + ((size_t)n * C + c) * 2, npix, m, sd);
+            s_stat[0][c] = m; s_stat[1][c] = __fdiv_rn(1.0f, sd);
+            stats_to_mean_std(stats2 + ((size_t)n2 * C + c) * 2, npix, m, sd);
+            s_stat[2][c] = m; s_stat[3][c] = __fdiv_rn(1.0f, sd);
+          }
+          named_sync(7, NLT);
+          stat_n = n;
+        }
+        for (int chunk = 0; chunk < nchunks; ++chunk, ++it) {
+          const int s = (int)(it % CP_STAGES);
+          const uint32_t ph = (uint32_t)((it / CP_STAGES) & 1);
+          float* st2 = smem + s * K::STAGE_FLOATS;
+          float* st1 = st2 + K::HPOS * CP_CC;
+          mbar_wait(smem_u32(&s_full[s]), ph);
+          const int c = chunk * CP_CC + ch * 4;
           if (c < C) {
+            // in-place (x - mean) * (1/std) on the in-image positions; TMA's zero fill stays zero
             const float4 m2 = *reinterpret_cast<const float4*>(&s_stat[2][c]), r2 = *reinterpret_cast<const float4*>(&s_stat[3][c]);
-            constexpr int P2 = (K::HCOLS + 15) / 16;
-            for (int r = 0; r < K::HROWS; ++r) {
-              const int y = y0 - D + r;
-              if (y < 0 || y >= H) continue;
-              float4 v[P2];
-              float4* qp[P2];
+            constexpr int U = 4;
+            for (int p0 = q0; p0 < K::HPOS; p0 += PS * U) {
+              float4 v[U];
+              float4* qp[U];
 #pragma unroll
-              for (int i = 0; i < P2; ++i) {                 // loads first (independent), then the arithmetic and the stores
-                const int cc = q0 + 16 * i, x = x0 - D + cc;
-                qp[i] = (cc < K::HCOLS && x >= 0 && x < W) ? reinterpret_cast<float4*>(st2 + cp_swz(r * K::HCOLS + cc, ch)) : nullptr;
+              for (int i = 0; i < U; ++i) {                 // loads first (independent), then the arithmetic and the stores
+                const int pos = p0 + PS * i;
+                const int r = pos / K::HCOLS, cc = pos - r * K::HCOLS;
+                const int y = y0 - D + r, x = x0 - D + cc;
+                qp[i] = (pos < K::HPOS && y >= 0 && y < H && x >= 0 && x < W)
+                            ? reinterpret_cast<float4*>(st2 + pos * CP_CC + (((ch ^ (pos >> 2)) & 1) << 2)) : nullptr;
                 if (qp[i]) v[i] = *qp[i];
               }
 #pragma unroll
-              for (int i = 0; i < P2; ++i)
+              for (int i = 0; i < U; ++i)
                 if (qp[i]) {
                   v[i].x = __fmul_rn(__fsub_rn(v[i].x, m2.x), r2.x); v[i].y = __fmul_rn(__fsub_rn(v[i].y, m2.y), r2.y);
                   v[i].z = __fmul_rn(__fsub_rn(v[i].z, m2.z), r2.z); v[i].w = __fmul_rn(__fsub_rn(v[i].w, m2.w), r2.w);
@@ -147,17 +174,18 @@ corr_pipe_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant
                 }
             }
             const float4 m1 = *reinterpret_cast<const float4*>(&s_stat[0][c]), r1 = *reinterpret_cast<const float4*>(&s_stat[1][c]);
-            for (int r = 0; r < CP_TY; r += 2) {
-              float4 v[4];
-              float4* qp[4];
+            for (int p0 = q0; p0 < K::F1POS; p0 += PS * U) {
+              float4 v[U];
+              float4* qp[U];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int rr = r + (i >> 1), cc = q0 + 16 * (i & 1);
-                qp[i] = (y0 + rr < H && x0 + cc < W) ? reinterpret_cast<float4*>(st1 + cp_swz(rr * CP_TX + cc, ch)) : nullptr;
+              for (int i = 0; i < U; ++i) {
+                const int pos = p0 + PS * i;                // CP_TX == 32: row = pos >> 5, column = pos & 31
+                qp[i] = (pos < K::F1POS && y0 + (pos >> 5) < H && x0 + (pos & 31) < W)
+                            ? reinterpret_cast<float4*>(st1 + pos * CP_CC + (((ch ^ (pos >> 2)) & 1) << 2)) : nullptr;
                 if (qp[i]) v[i] = *qp[i];
               }
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
+              for (int i = 0; i < U; ++i)
                 if (qp[i]) {
                   v[i].x = __fmul_rn(__fsub_rn(v[i].x, m1.x), r1.x); v[i].y = __fmul_rn(__fsub_rn(v[i].y, m1.y), r1.y);
                   v[i].z = __fmul_rn(__fsub_rn(v[i].z, m1.z), r1.z); v[i].w = __fmul_rn(__fsub_rn(v[i].w, m1.w), r1.w);
@@ -165,106 +193,124 @@ corr_pipe_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant
                 }
             }
           }
-        }
-        named_arrive(1 + s, N_FE);                      // stage s is full
-      }
-    }
-  } else if (warp >= K::NCW + CP_NLOAD) {
-    // ============================== STORER WARP(S) ==============================
-    const int st = threadIdx.x - (K::NCW + CP_NLOAD) * 32;
-    constexpr int NST = CP_NSTORE * 32;
-    for (int tloc = 0; tloc < my_tiles; ++tloc) {
-      int tile = blockIdx.x + tloc * gridDim.x;
-      const int tx = tile % tiles_x; tile /= tiles_x;
-      const int ty = tile % tiles_y;
-      const int n = tile / tiles_y;
-      const int x0 = tx * CP_TX, y0 = ty * CP_TY;
-      named_sync(5, N_OUT);                             // the tile's results are in s_out
-      const int wvalid = (W - x0 < CP_TX ? W - x0 : CP_TX);
-      for (int r = 0; r < CP_TY; ++r) {
-        const int y = y0 + r;
-        if (y >= H) break;
-        float* orow = out + ((size_t)((size_t)n * H + y) * W + x0) * ldo;
-        const float* srow = s_out + r * CP_TX * K::NOUT;
-        if (ldo == K::NOUT) {
-          const int total = wvalid * K::NOUT;           // one contiguous run
-          if ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) {
-            const int t4 = total >> 2;
-            for (int e = st; e < t4; e += NST) reinterpret_cast<float4*>(orow)[e] = reinterpret_cast<const float4*>(srow)[e];
-            for (int e = (t4 << 2) + st; e < total; e += NST) orow[e] = srow[e];
-          } else {
-            for (int e = st; e < total; e += NST) orow[e] = srow[e];
-          }
-        } else {
-          // one warp per pixel: NOUT consecutive floats, lanes stride the run
-          for (int px = warp - K::NCW - CP_NLOAD; px < wvalid; px += CP_NSTORE) {
-            float* o = orow + (size_t)px * ldo;
-            const float* sp = srow + px * K::NOUT;
-            for (int k = lane; k < K::NOUT; k += 32) o[k] = sp[k];
-          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&s_ready[s]));   // release: the in-place writes are visible to the waiters
         }
       }
-      named_arrive(6, N_OUT);                           // s_out may be overwritten
     }
   } else {
     // ============================== COMPUTE WARPS ==============================
     const int dxi = warp;
     const int col2 = lane + dxi;
-    float acc[CP_TY][K::WIN];
+    constexpr int NCT = K::NCW * 32;                    // compute threads
+    const int ct = threadIdx.x;                         // compute warps are warps 0 .. NCW-1
+    const int swa = (lane >> 2) & 1, swb = (col2 >> 2) & 1;
+    float acc[TY][K::WIN];
     long long it = 0;
     for (int tloc = 0; tloc < my_tiles; ++tloc) {
 #pragma unroll
-      for (int p = 0; p < CP_TY; ++p)
+      for (int p = 0; p < TY; ++p)
 #pragma unroll
         for (int q = 0; q < K::WIN; ++q) acc[p][q] = 0.f;
       for (int chunk = 0; chunk < nchunks; ++chunk, ++it) {
-        const int s = (int)(it & 1);
-        named_sync(1 + s, N_FE);                        // wait until the loader filled stage s
+        const int s = (int)(it % CP_STAGES);
+        const uint32_t ph = (uint32_t)((it / CP_STAGES) & 1);
+        mbar_wait(smem_u32(norm ? &s_ready[s] : &s_full[s]), ph);
         const float* stage = smem + s * K::STAGE_FLOATS;
         const float* a_base = stage + K::HPOS * CP_CC + lane * CP_CC;
         const float* b_base = stage + col2 * CP_CC;
         const int cend = (C - chunk * CP_CC < CP_CC ? C - chunk * CP_CC : CP_CC);
-        const int nq = (cend + 3) >> 2;
-#pragma unroll 1
-        for (int ch = 0; ch < nq; ++ch) {
-          const float* ap = a_base + (((ch ^ (lane >> 1)) & 3) << 2);
-          const float* bp = b_base + (((ch ^ (col2 >> 1)) & 3) << 2);
-          float4 a[CP_TY];
 #pragma unroll
-          for (int p = 0; p < CP_TY; ++p) a[p] = *reinterpret_cast<const float4*>(ap + p * CP_TX * CP_CC);
+        for (int ch = 0; ch < CP_CC / 4; ++ch) {
+          if (ch * 4 < cend) {
+            const float* ap = a_base + ((ch ^ swa) << 2);
+            const float* bp = b_base + ((ch ^ swb) << 2);
+            float4 a[TY];
 #pragma unroll
-          for (int j = 0; j < K::HROWS; ++j) {
-            const float4 b = *reinterpret_cast<const float4*>(bp + j * K::HCOLS * CP_CC);
+            for (int p = 0; p < TY; ++p) a[p] = *reinterpret_cast<const float4*>(ap + p * CP_TX * CP_CC);
 #pragma unroll
-            for (int p = 0; p < CP_TY; ++p) {
-              const int dyi = j - p;
-              if (dyi >= 0 && dyi < K::WIN) {
-                float sacc = acc[p][dyi];
-                sacc = fmaf(a[p].x, b.x, sacc);
-                sacc = fmaf(a[p].y, b.y, sacc);
-                sacc = fmaf(a[p].z, b.z, sacc);
-                sacc = fmaf(a[p].w, b.w, sacc);
-                acc[p][dyi] = sacc;
+            for (int j = 0; j < K::HROWS; ++j) {
+              const float4 b = *reinterpret_cast<const float4*>(bp + j * K::HCOLS * CP_CC);
+#pragma unroll
+              for (int p = 0; p < TY; ++p) {
+                const int dyi = j - p;
+                if (dyi >= 0 && dyi < K::WIN) {
+                  float sacc = acc[p][dyi];
+                  sacc = fmaf(a[p].x, b.x, sacc);
+                  sacc = fmaf(a[p].y, b.y, sacc);
+                  sacc = fmaf(a[p].z, b.z, sacc);
+                  sacc = fmaf(a[p].w, b.w, sacc);
+                  acc[p][dyi] = sacc;
+                }
               }
             }
           }
         }
-        named_arrive(3 + s, N_FE);                      // stage s may be refilled
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_empty[s]));   // slot s may be refilled
       }
-      // ---- tile done: mean over channels, LeakyReLU, transpose into s_out for the storer warps
-      if (tloc > 0) named_sync(6, N_OUT);               // previous tile's rows have left s_out
+      // ---- tile done: mean over channels, LeakyReLU, transpose through s_out, copy-out
+      int tile = blockIdx.x + tloc * gridDim.x;
+      const int tx = tile % tiles_x; tile /= tiles_x;
+      const int ty = tile % tiles_y;
+      const int n = tile / tiles_y;
+      const int x0 = tx * CP_TX, y0 = ty * TY;
+      if (bulk_out && ct == 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile's rows were read
+      named_sync(1, NCT);                               // the previous tile's rows have left s_out
       const float fC = (float)C, inv = __fdiv_rn(1.0f, fC);
+      if ((C & (C - 1)) == 0) {                         // power of two: sum * (1/C) is the correctly rounded mean
 #pragma unroll
-      for (int p = 0; p < CP_TY; ++p)
+        for (int p = 0; p < TY; ++p)
 #pragma unroll
-        for (int q = 0; q < K::WIN; ++q) {
-          const float sacc = acc[p][q];
-          float v = __fmul_rn(sacc, inv);
-          v = __fmaf_rn(__fmaf_rn(-v, fC, sacc), inv, v);       // correctly rounded sum / C (torch.mean)
-          s_out[(p * CP_TX + lane) * K::NOUT + q * K::WIN + dxi] = lrelu(v, slope);
+          for (int q = 0; q < K::WIN; ++q)
+            s_out[(p * CP_TX + lane) * K::NOUT + q * K::WIN + dxi] = lrelu(__fmul_rn(acc[p][q], inv), slope);
+      } else {
+#pragma unroll
+        for (int p = 0; p < TY; ++p)
+#pragma unroll
+          for (int q = 0; q < K::WIN; ++q) {
+            const float sacc = acc[p][q];
+            float v = __fmul_rn(sacc, inv);
+            v = __fmaf_rn(__fmaf_rn(-v, fC, sacc), inv, v);     // correctly rounded sum / C (torch.mean)
+            s_out[(p * CP_TX + lane) * K::NOUT + q * K::WIN + dxi] = lrelu(v, slope);
+          }
+      }
+      if (bulk_out) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> bulk-copy reads
+      named_sync(2, NCT);
+      const int wvalid = (W - x0 < CP_TX ? W - x0 : CP_TX);
+      const int hvalid = (H - y0 < TY ? H - y0 : TY);
+      if (bulk_out) {
+        // every tile row is ONE contiguous, 16-byte aligned run of wvalid * NOUT floats in shared and in global
+        // memory: one bulk copy per row, issued by one thread, drained by the copy engine while the warps compute on
+        if (ct == 32) {
+          const uint32_t nbytes = (uint32_t)(wvalid * K::NOUT * 4);
+          for (int r = 0; r < hvalid; ++r) {
+            float* orow = out + ((size_t)((size_t)n * H + y0 + r) * W + x0) * K::NOUT;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(orow), "r"(smem_u32(s_out + r * CP_TX * K::NOUT)), "r"(nbytes) : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-      named_arrive(5, N_OUT);
+      } else if (warp & 3) {
+        // channel slice of a wider buffer: a warp per pixel, NOUT consecutive floats.  Scheduler 0 hosts three compute
+        // warps, the others two: the copy is done by the warps of schedulers 1..3 only (ncu: the warps of the
+        // lighter schedulers waited 17 % of their time at the tile barrier)
+        constexpr int NCOPY = K::NCW - ((K::NCW + 3) >> 2);
+        const int npx = hvalid * CP_TX;
+        float* obase = out + ((size_t)((size_t)n * H + y0) * W + x0) * ldo;
+        for (int px = warp - ((warp + 3) >> 2); px < npx; px += NCOPY) {
+          const int r = px >> 5, cx = px & 31;
+          if (cx < wvalid) {
+            float* o = obase + (r * W + cx) * ldo;
+            const float* sp = s_out + px * K::NOUT;
+#pragma unroll
+            for (int k = 0; k < (K::NOUT + 31) / 32; ++k)
+              if (k * 32 + lane < K::NOUT) o[k * 32 + lane] = sp[k * 32 + lane];
+          }
+        }
+      }
     }
+    if (bulk_out && ct == 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 }
 
@@ -273,7 +319,7 @@ static int launch_corr_pipe_t(const float* f1, int ld1, const float* f2, int ld2
                               int N, int H, int W, int C, const double* s1, const double* s2, int shift,
                               float slope, cudaStream_t st) {
   using K = CPCfg<D>;
-  const int tiles_x = (W + CP_TX - 1) / CP_TX, tiles_y = (H + CP_TY - 1) / CP_TY;
+  const int tiles_x = (W + CP_TX - 1) / CP_TX, tiles_y = (H + K::TY - 1) / K::TY;
   const long long tiles = (long long)tiles_x * tiles_y * N;
   static bool attr_done = false;
   if (!attr_done) {
@@ -286,23 +332,29 @@ static int launch_corr_pipe_t(const float* f1, int ld1, const float* f2, int ld2
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const cuuint64_t str1[3] = {(cuuint64_t)ld1 * 4, (cuuint64_t)W * ld1 * 4, (cuuint64_t)H * W * ld1 * 4};
-    const cuuint32_t box1[4] = {CP_CC, CP_TX, CP_TY, 1};
-    MapKey k1{f1, ld1, ((long long)H << 32) | (unsigned)W, ((long long)N << 32) | (unsigned)C, 7000 + D, 64};
-    int e = encode_cached(k1, &m1, 4, const_cast<float*>(f1), dims, str1, box1, estr, 64);
+    const cuuint32_t box1[4] = {CP_CC, CP_TX, (cuuint32_t)K::TY, 1};
+    MapKey k1{f1, ld1, ((long long)H << 32) | (unsigned)W, ((long long)N << 32) | (unsigned)C, 7000 + D, 32};
+    int e = encode_cached(k1, &m1, 4, const_cast<float*>(f1), dims, str1, box1, estr, 32);
     if (e) return e;
     const cuuint64_t str2[3] = {(cuuint64_t)ld2 * 4, (cuuint64_t)W * ld2 * 4, (cuuint64_t)H * W * ld2 * 4};
     const cuuint32_t box2[4] = {CP_CC, (cuuint32_t)K::HCOLS, (cuuint32_t)K::HROWS, 1};
-    MapKey k2{f2, ld2, ((long long)H << 32) | (unsigned)W, ((long long)N << 32) | (unsigned)C, 8000 + D, 64};
-    e = encode_cached(k2, &m2, 4, const_cast<float*>(f2), dims, str2, box2, estr, 64);
+    MapKey k2{f2, ld2, ((long long)H << 32) | (unsigned)W, ((long long)N << 32) | (unsigned)C, 8000 + D, 32};
+    e = encode_cached(k2, &m2, 4, const_cast<float*>(f2), dims, str2, box2, estr, 32);
     if (e) return e;
   }
+  // contiguous output whose tile rows are 16-byte aligned runs: shared -> global bulk copies instead of ld/st
+  const int bulk_out = (ldo == K::NOUT && W % 4 == 0 && aligned16(out)) ? 1 : 0;
   const unsigned grid = (unsigned)(tiles < UPF_NUM_SMS ? tiles : UPF_NUM_SMS);
   UPF_LAUNCH((corr_pipe_kernel<D>), grid, K::NT, K::SMEM_BYTES, st, m1, m2, out, ldo, H, W, C, s1, s2, slope, tiles_x, tiles_y, shift,
-                                                          N, (int)tiles);
+                                                          N, (int)tiles, bulk_out);
   return check_launch("corr_pipe");
 }
 
 static int g_corr_pipe_enabled = 1;
+// tiles PER IMAGE from which the pipelined kernel is used (never a function of N: an image must give the same bits
+// in any batch).  Measured (tools/time_corr.py, d=4, fused normalisation): 2x94x311 C=32 32.5 us vs 45.4 us tiled,
+// 2x47x156 C=64 (30 tiles per image) 29.3 vs 40.7
+static int g_corr_pipe_min_tiles = 25;
 
 // returns 1 in *taken when this kernel handled the call
 int launch_corr_pipe(const float* f1, int ld1, const float* f2, int ld2, float* out, int ldo,
@@ -310,22 +362,25 @@ int launch_corr_pipe(const float* f1, int ld1, const float* f2, int ld2, float* 
                      float slope, cudaStream_t st, int* taken) {
   *taken = 0;
   const bool vec = (C % 4 == 0) && (ld1 % 4 == 0) && (ld2 % 4 == 0) && aligned16(f1) && aligned16(f2);
-  const long long tiles = (long long)((W + CP_TX - 1) / CP_TX) * ((H + CP_TY - 1) / CP_TY) * N;
-  // persistent CTAs need several tiles each to amortise the pipeline fill and to balance the SMs: measured, at 240
-  // tiles (1/4-res KITTI, both directions) the two-CTA-per-SM tiled kernel of corr.cu is still ~10 % faster
-  if (!g_corr_pipe_enabled || !vec || D > 4 || C > 256 || tiles >= (1ll << 30) || tiles < 3 * UPF_NUM_SMS) return 0;
+  const int ty = D <= 4 ? 8 : 4;
+  const long long tiles_img = (long long)((W + CP_TX - 1) / CP_TX) * ((H + ty - 1) / ty);
+  if (!g_corr_pipe_enabled || !vec || D > 6 || C > 256 || tiles_img * N >= (1ll << 30) || tiles_img < g_corr_pipe_min_tiles) return 0;
   *taken = 1;
   switch (D) {
     case 1: return launch_corr_pipe_t<1>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, st);
     case 2: return launch_corr_pipe_t<2>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, st);
     case 3: return launch_corr_pipe_t<3>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, st);
-    default: return launch_corr_pipe_t<4>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, st);
+    case 4: return launch_corr_pipe_t<4>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, st);
+    case 5: return launch_corr_pipe_t<5>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, st);
+    default: return launch_corr_pipe_t<6>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, st);
   }
 }
 
 }  // namespace upf
 
+// enabled: 0 = never, 1 = default threshold, n > 1 = use the pipelined kernel from n tiles per image on (A/B runs)
 extern "C" int upf_debug_corr_pipe(int enabled) {
-  upf::g_corr_pipe_enabled = enabled;
+  upf::g_corr_pipe_enabled = enabled != 0;
+  upf::g_corr_pipe_min_tiles = enabled > 1 ? enabled : 25;
   return 0;
 }
