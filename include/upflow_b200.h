@@ -155,6 +155,47 @@ int upf_debug_corr_pipe(int enabled);
 /* debug: device buffer of 8 int64 receiving CTA 0's per-role wait / busy cycle counters of the halo kernel (NULL = off) */
 int upf_debug_probe(void* device_buffer_8x_int64);
 
+/* ---- a11: backward of the convolutions and of the small decoder ops (training step, BASELINE config 4) ----
+ * The INPUT gradient of conv() is upf_conv2d_fwd itself on flipped / transposed weights (stride 2: on the
+ * zero-interleaved output gradient); these entry points are the rest of what autograd asks of
+ * model/pwc_modules.py:10-31 (cuDNN wgrad + LeakyReLU backward), model/upflow.py:108-135 (torch.mean / torch.var
+ * are differentiated through), model/pwc_modules.py:77-90 and model/upflow.py:79-88.  All reductions are
+ * deterministic (fixed pixel ranges, fixed summation order, no floating-point atomics). */
+
+/* weight and bias gradient: grad_w [k*k][Cin][Cout] dense, grad_bias [Cout] (nullable), from the input x
+ * [N,H,W,>=Cin] and the gradient wrt the PRE-activation output grad_out [N,Ho,Wo,>=Cout].  workspace: at least
+ * upf_conv2d_wgrad_workspace_elems(...) floats. */
+long long upf_conv2d_wgrad_workspace_elems(int N, int H, int W, int Cin, int Cout, int ksize, int stride, int dilation);
+int upf_conv2d_wgrad(const float* x, int ldx, const float* grad_out, int ldg, float* grad_w, float* grad_bias,
+                     float* workspace, int N, int H, int W, int Cin, int Cout, int ksize, int stride, int dilation,
+                     void* stream);
+
+/* pointwise ops on [npix][C] pitched tensors.  op 0: out = b * (a > 0 ? 1 : slope)  (LeakyReLU backward from the
+ * saved output a and the incoming gradient b); op 1: out = sigmoid(a); op 2: out = b * a * (1 - a) (sigmoid
+ * backward from the saved output a). */
+#define UPF_PW_LRELU_BWD   0
+#define UPF_PW_SIGMOID     1
+#define UPF_PW_SIGMOID_BWD 2
+int upf_pointwise(int op, const float* a, int lda, const float* b, int ldb, float* out, int ldo, long long npix,
+                  int C, float slope, void* stream);
+
+/* sgu_model.forward's blend (model/upflow.py:88) as a differentiable piece: out_c = w_c*(1-m) + f_c*m, c in {0,1};
+ * backward: gw_c = g_c*(1-m), gf_c = g_c*m, gm = sum_c g_c*(f_c - w_c). */
+int upf_blend_fwd(const float* w, int ldw, const float* f, int ldf, const float* m, int ldm, float* out, int ldo,
+                  long long npix, void* stream);
+int upf_blend_bwd(const float* w, int ldw, const float* f, int ldf, const float* m, int ldm, const float* g, int ldg,
+                  float* gw, int ldgw, float* gf, int ldgf, float* gm, int ldgm, long long npix, void* stream);
+
+/* normalize_features backward through the moments: dx = (g - mean(g) - y*sum(g*y)/(n-1)) / std, y = (x-mean)/std.
+ * stats = the forward's (sum, sum^2) buffer; workspace: upf_featnorm_bwd_workspace_doubles(N, C) doubles. */
+long long upf_featnorm_bwd_workspace_doubles(int N, int C);
+int upf_featnorm_bwd(const float* x, int ldx, const double* stats, const float* grad_out, int ldg, float* grad_x,
+                     int ldgx, double* workspace, int N, int H, int W, int C, void* stream);
+
+/* adjoint of upf_resize_bilinear: grad_in [N,h,w,C] from grad_out [N,H,W,C] (same scale vector). */
+int upf_resize_bilinear_bwd(const float* grad_out, int ldgo, int H, int W, float* grad_in, int ldgi, int h, int w,
+                            int N, int C, const float* scale_host, void* stream);
+
 /* layout helpers for callers holding NCHW-contiguous tensors (the reference's
  * layout): strided copy between [N,C,H,W] planes and pixel-major rows. */
 int upf_nchw_to_nhwc(const float* in, float* out, int ldo, int N, int C, int H, int W, void* stream);

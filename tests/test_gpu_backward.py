@@ -1,0 +1,182 @@
+"""a11: backward kernels against torch autograd of the reference's own ops on CPU (fp64), and the
+whole training-path gradient of the drop-in UPFlow_net against autograd through the op-for-op port.  -m gpu."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import cpu_oracle as O
+from oracle import ref_port as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def upf():
+    from upflow_pytorch_b200 import _ext, ops
+    _ext.load()
+    return ops
+
+
+def _rand(seed, *shape):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def _check(name, val, tol):
+    if not val <= tol:
+        raise AssertionError("%s: %.3g > %.3g" % (name, val, tol)) from None
+    print("  %s %.3g (tol %.3g)" % (name, val, tol))
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("case", [(20, 12, 3, 1, 1, 13, 18), (16, 8, 3, 2, 1, 13, 18), (16, 8, 3, 2, 1, 14, 20),
+                                  (24, 6, 3, 1, 4, 17, 21), (10, 2, 1, 1, 1, 9, 11), (70, 130, 3, 1, 2, 20, 24),
+                                  (3, 16, 3, 1, 1, 16, 16), (36, 3, 3, 1, 1, 12, 40)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_conv_backward_fp32_vs_autograd(upf, case, relu):
+    """dgrad (forward kernel on flipped weights; stride 2 on the zero-interleaved gradient), wgrad, bias gradient and
+    the LeakyReLU derivative against F.conv2d + F.leaky_relu autograd in fp64.  Tolerance 2e-5 relative to the
+    largest gradient entry (fp32 sums over up to 70*9 products / 960 pixels)."""
+    from upflow_pytorch_b200 import _ext
+    Cin, Cout, k, stride, dil, H, W = case
+    x, w, b = _rand(1, 2, Cin, H, W), _rand(2, Cout, Cin, k, k) * 0.2, _rand(3, Cout) * 0.1
+    xd, wd, bd = (t.double().requires_grad_() for t in (x, w, b))
+    y = F.conv2d(xd, wd, bd, stride=stride, padding=((k - 1) * dil) // 2, dilation=dil)
+    y = F.leaky_relu(y, 0.1) if relu else y
+    gy = _rand(4, *y.shape)
+    y.backward(gy.double())
+    xc, wc, bc = (t.cuda().requires_grad_() for t in (x, w, b))
+    yc = upf.conv2d_autograd(xc, wc, bc, stride, dil, 0.1 if relu else 1.0, _ext.CONV_FP32)
+    _check("y", _rel(yc.detach().cpu(), y.detach()), 2e-5)
+    yc.backward(gy.cuda())
+    for got, ref, name in ((xc.grad, xd.grad, "dx"), (wc.grad, wd.grad, "dw"), (bc.grad, bd.grad, "db")):
+        assert got.shape == ref.shape
+        _check(name, _rel(got.cpu(), ref), 2e-5)
+
+
+@pytest.mark.parametrize("case", [(64, 32, 3, 1, 1, 24, 40), (96, 128, 3, 1, 2, 20, 33), (32, 32, 1, 1, 1, 17, 29), (16, 32, 3, 2, 1, 30, 44)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_conv_backward_tf32(upf, case, relu):
+    """tensor-core forward and dgrad (TF32 operands, fp32 accumulate), SIMT fp32 wgrad: 1e-2 relative."""
+    from upflow_pytorch_b200 import _ext
+    Cin, Cout, k, stride, dil, H, W = case
+    slope = 0.1 if relu else 1.0
+    x, w, b = _rand(1, 2, Cin, H, W), _rand(2, Cout, Cin, k, k) * 0.1, _rand(3, Cout) * 0.1
+    xc, wc, bc = (t.cuda().requires_grad_() for t in (x, w, b))
+    yc = upf.conv2d_autograd(xc, wc, bc, stride, dil, slope, _ext.CONV_TF32)
+    xd, wd, bd = (t.double().requires_grad_() for t in (x, w, b))
+    ypre = F.conv2d(xd, wd, bd, stride=stride, padding=((k - 1) * dil) // 2, dilation=dil)
+    # the activation pattern of the TF32 forward (a TF32-sized error flips the sign of ~0.1 % of the outputs; the
+    # gradient is checked for the pattern the kernel actually produced)
+    y = ypre * torch.where(yc.detach().cpu() > 0, 1.0, slope).double()
+    gy = _rand(4, *y.shape)
+    y.backward(gy.double())
+    yc.backward(gy.cuda())
+    _check("y", _rel(yc.detach().cpu(), F.leaky_relu(ypre.detach(), slope)), 1e-2)
+    _check("dx", _rel(xc.grad.cpu(), xd.grad), 1e-2)
+    _check("dw", _rel(wc.grad.cpu(), wd.grad), 1e-2)
+    _check("db", _rel(bc.grad.cpu(), bd.grad), 1e-2)
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 24, 39), (1, 196, 6, 20), (3, 7, 11, 13)])
+def test_normalize_features_backward(upf, shape):
+    x = _rand(5, *shape) * 1.7 + 0.4
+    g = _rand(6, *shape)
+    xd = x.double().requires_grad_()
+    P.normalize(xd).backward(g.double())
+    xc = x.cuda().requires_grad_()
+    upf.normalize_features(xc).backward(g.cuda())
+    _check("dx", _rel(xc.grad.cpu(), xd.grad), 1e-5)
+
+
+@pytest.mark.parametrize("case", [(2, 12, 39, 24, 78, True), (2, 94, 311, 375, 1242, True), (1, 47, 156, 188, 621, False),
+                                  (1, 1, 7, 5, 7, False), (2, 24, 78, 24, 78, True)])
+def test_resize_backward(upf, case):
+    C, h, w, H, W, rate = case
+    C = 2 if rate else 1
+    x = _rand(7, 2, C, h, w)
+    g = _rand(8, 2, C, H, W)
+    xd = x.double().requires_grad_()
+    P.upsample2d_flow_as(xd, H, W, if_rate=rate).backward(g.double())
+    xc = x.cuda().requires_grad_()
+    upf.resize_bilinear(xc, H, W, flow_rate=rate).backward(g.cuda())
+    _check("dx", _rel(xc.grad.cpu(), xd.grad), 3e-5)
+
+
+@pytest.mark.parametrize("lowres", [False, True])
+def test_sgu_blend_backward(upf, lowres):
+    """the differentiable chain (sigmoid, upsamples, un-masked warp, blend) against model/upflow.py:79-88 in autograd;
+    forward of the chain == the fused inference kernel."""
+    H, W = 36, 52
+    h, w = (9, 13) if lowres else (H, W)
+    flow_init, inter = _rand(9, 2, 2, H, W) * 2.0, _rand(10, 2, 3, h, w)
+    g = _rand(11, 2, 2, H, W)
+    fd, idd = flow_init.double().requires_grad_(), inter.double().requires_grad_()
+    inter_flow, mask = idd[:, :2], torch.sigmoid(idd[:, 2:3])
+    if lowres:
+        inter_flow = P.upsample2d_flow_as(inter_flow, H, W, if_rate=True)
+        mask = P.upsample2d_flow_as(mask, H, W)
+    ref = P.torch_warp(fd, inter_flow) * (1 - mask) + fd * mask
+    ref.backward(g.double())
+    fc, ic = flow_init.cuda().requires_grad_(), inter.cuda().requires_grad_()
+    out = upf.sgu_blend(fc, ic)
+    out.backward(g.cuda())
+    with torch.no_grad():
+        fused = upf.sgu_blend(flow_init.cuda(), inter.cuda())
+    _check("chain vs fused kernel", (out.detach() - fused).abs().max().item(), 2e-6)
+    _check("forward", _rel(out.detach().cpu(), ref.detach()), 1e-5)
+    # the warp gradient is discontinuous where a sample crosses a pixel boundary: compare away from fp32-vs-fp64 flips
+    for got, refg, name in ((fc.grad, fd.grad, "dflow_init"), (ic.grad, idd.grad, "dinter")):
+        bad = ((got.cpu().double() - refg).abs() > 1e-4 * refg.abs().max()).float().mean().item()
+        _check(name + " fraction of entries off by > 1e-4", bad, 2e-3)
+
+
+def test_training_path_gradients_vs_port():
+    """forward_2_frame_v3 with autograd (every op an autograd node on this library's kernels) against autograd through
+    the op-for-op CPU port of the reference, same weights, same smooth loss, robust-mask diagnostic on both sides
+    (tests/test_gpu_engine.py explains the `mask >= 1.0` noise).  All 80 parameter tensors receive a gradient."""
+    import upflow_pytorch_b200
+    from upflow_pytorch_b200 import ops
+    upflow_pytorch_b200.install_dropin()
+    from model.upflow import UPFlow_net
+    from model import pwc_modules
+    conf = UPFlow_net.config()
+    conf.update({"if_norm_before_cost_volume": True, "norm_moments_across_channels": False,
+                 "norm_moments_across_images": False, "if_sgu_upsample": True})
+    net = conf()
+    sd = P.det_state_dict(5)
+    net.load_state_dict(sd)
+    net = net.cuda().train()
+    pwc_modules.set_conv_precision("fp32")
+    im1, im2 = O.synthetic_pair(64, 96, seed=77)
+
+    def loss_of(f, b):
+        return (f ** 2).mean() + (b - 0.5).abs().mean() + (f[:, :, 1:] - f[:, :, :-1]).abs().mean()
+
+    P.MASK_THRESHOLD = 0.9999
+    ops.DIAG_MASK_THRESHOLD = 0.9999
+    try:
+        sdr = {k: v.clone().requires_grad_() for k, v in sd.items()}
+        rf, rb, _ = P.forward_2_frame(im1, im2, sdr)
+        ref_loss = loss_of(rf, rb)
+        ref_loss.backward()
+        f, b, flows = net.forward_2_frame_v3(im1.cuda(), im2.cuda())
+        loss = loss_of(f, b)
+        loss.backward()
+    finally:
+        P.MASK_THRESHOLD = 1.0
+        ops.DIAG_MASK_THRESHOLD = None
+    assert abs(loss.item() - ref_loss.item()) <= 1e-4 * abs(ref_loss.item())
+    worst = 0.0
+    n = 0
+    for name, p in net.named_parameters():
+        assert p.grad is not None, name
+        ref = sdr[name].grad
+        err = (p.grad.cpu() - ref).norm().item() / max(ref.norm().item(), 1e-12)
+        worst = max(worst, err)
+        n += 1
+    print("training-path gradient: %d tensors, worst relative L2 error %.3g" % (n, worst))
+    assert n == 80
+    assert worst <= 2e-2, worst

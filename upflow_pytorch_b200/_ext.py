@@ -34,6 +34,14 @@ SIGNATURES = {
     "upf_debug_probe": (_I, [_P]),
     "upf_debug_conv_win": (_I, [_I, _I, _I]),
     "upf_debug_corr_pipe": (_I, [_I]),
+    "upf_conv2d_wgrad_workspace_elems": (_LL, [_I, _I, _I, _I, _I, _I, _I, _I]),
+    "upf_conv2d_wgrad": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "upf_pointwise": (_I, [_I, _P, _I, _P, _I, _P, _I, _LL, _I, _F, _P]),
+    "upf_blend_fwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _LL, _P]),
+    "upf_blend_bwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _LL, _P]),
+    "upf_featnorm_bwd_workspace_doubles": (_LL, [_I, _I]),
+    "upf_featnorm_bwd": (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
+    "upf_resize_bilinear_bwd": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _c.POINTER(_F), _P]),
     "upf_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "upf_nhwc_to_nchw": (_I, [_P, _I, _P, _I, _I, _I, _I, _P]),
     "upf_copy_channels": (_I, [_P, _I, _P, _I, _LL, _I, _P]),
@@ -41,6 +49,7 @@ SIGNATURES = {
 
 CONV_FP32 = 0
 CONV_TF32 = 1
+PW_LRELU_BWD, PW_SIGMOID, PW_SIGMOID_BWD = 0, 1, 2
 
 _lib = None
 

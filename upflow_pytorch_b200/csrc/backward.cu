@@ -1,0 +1,371 @@
+// Backward kernels of the decoder path that are not a re-use of a forward kernel:
+//   * weight / bias gradient of conv() (replaces cuDNN wgrad behind nn.Conv2d, model/pwc_modules.py:10-31);
+//   * LeakyReLU backward taken from the saved OUTPUT (nn.LeakyReLU(0.1, inplace=True), :26-30);
+//   * normalize_features backward THROUGH the moments (model/upflow.py:108-135: torch.mean / torch.var are part
+//     of the graph);
+//   * upsample2d_flow_as backward (model/pwc_modules.py:77-90: bilinear, align_corners=True, per-channel scale);
+//   * the pointwise pieces of sgu_model.forward (model/upflow.py:79-88): sigmoid and the blend, both directions.
+// The input gradient of a convolution (cuDNN dgrad) is the FORWARD kernel run on the flipped, transposed weights
+// (ops.py: conv_dgrad), and the correlation / warp gradients live next to their forward kernels.
+//
+// Everything here is deterministic: reductions over pixels are split into fixed ranges whose partial results are
+// summed in a fixed order (no floating-point atomics).
+#include "upf_common.cuh"
+
+namespace upf {
+
+// ------------------------------------------------------------------------------------------------ wgrad
+// dW[tap][ci][co] = sum over output pixels p of X[p (+) tap][ci] * G[p][co]:  per tap a GEMM with the pixels as
+// the K dimension.  CTA tile 64 ci x 64 co, 16 pixels per shared-memory step, 4x4 register tile per thread.
+// grid = (ci tiles * co tiles, taps, pixel splits); split s writes part[s][tap][ci][co].
+constexpr int WG_BM = 64, WG_BN = 64, WG_KP = 16, WG_NT = 256;
+
+__global__ void __launch_bounds__(WG_NT)
+conv_wgrad_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ g, int ldg, float* __restrict__ part,
+                  int N, int H, int W, int Ho, int Wo, int Cin, int Cout, int ks, int stride, int dil, int pad,
+                  int co_tiles, long long pix_per_split, long long npix) {
+  __shared__ __align__(16) float Xs[WG_KP][WG_BM];
+  __shared__ __align__(16) float Gs[WG_KP][WG_BN];
+  const int tile = blockIdx.x, tap = blockIdx.y, split = blockIdx.z;
+  const int ci0 = (tile / co_tiles) * WG_BM, co0 = (tile % co_tiles) * WG_BN;
+  const int ky = tap / ks, kx = tap % ks;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int lrow = tid >> 4, lcol = (tid & 15) * 4;       // loader: pixel row of the step, 4 consecutive channels
+  const bool vx = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const bool vg = (ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
+  const long long p_begin = (long long)split * pix_per_split;
+  long long p_end = p_begin + pix_per_split;
+  if (p_end > npix) p_end = npix;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (long long p0 = p_begin; p0 < p_end; p0 += WG_KP) {
+    const long long p = p0 + lrow;
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
+    if (p < p_end) {
+      const int ox = (int)(p % Wo);
+      const long long t = p / Wo;
+      const int oy = (int)(t % Ho), n = (int)(t / Ho);
+      const int iy = oy * stride - pad + ky * dil, ix = ox * stride - pad + kx * dil;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        const float* xp = x + ((size_t)((size_t)n * H + iy) * W + ix) * ldx + ci0 + lcol;
+        if (vx && ci0 + lcol + 3 < Cin && (((ci0 + lcol) & 3) == 0)) xv = ldg4(xp);
+        else {
+          if (ci0 + lcol < Cin) xv.x = __ldg(xp);
+          if (ci0 + lcol + 1 < Cin) xv.y = __ldg(xp + 1);
+          if (ci0 + lcol + 2 < Cin) xv.z = __ldg(xp + 2);
+          if (ci0 + lcol + 3 < Cin) xv.w = __ldg(xp + 3);
+        }
+      }
+      const float* gp = g + (size_t)p * ldg + co0 + lcol;
+      if (vg && co0 + lcol + 3 < Cout) gv = ldg4(gp);
+      else {
+        if (co0 + lcol < Cout) gv.x = __ldg(gp);
+        if (co0 + lcol + 1 < Cout) gv.y = __ldg(gp + 1);
+        if (co0 + lcol + 2 < Cout) gv.z = __ldg(gp + 2);
+        if (co0 + lcol + 3 < Cout) gv.w = __ldg(gp + 3);
+      }
+    }
+    __syncthreads();                                      // the previous step's tiles have been consumed
+    *reinterpret_cast<float4*>(&Xs[lrow][lcol]) = xv;
+    *reinterpret_cast<float4*>(&Gs[lrow][lcol]) = gv;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < WG_KP; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&Xs[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Gs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+  const int taps = ks * ks;
+  float* dst = part + ((size_t)split * taps + tap) * Cin * Cout;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ci = ci0 + ty * 4 + i;
+    if (ci >= Cin) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tx * 4 + j;
+      if (co < Cout) dst[(size_t)ci * Cout + co] = acc[i][j];
+    }
+  }
+}
+
+// per-channel sum of G over a pixel range (bias gradient partials): part[split][co]
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ g, int ldg, float* __restrict__ part, int Cout, long long pix_per_split, long long npix) {
+  const int split = blockIdx.x;
+  const long long p_begin = (long long)split * pix_per_split;
+  long long p_end = p_begin + pix_per_split;
+  if (p_end > npix) p_end = npix;
+  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+    float s = 0.f;
+    for (long long p = p_begin; p < p_end; ++p) s += __ldg(g + (size_t)p * ldg + co);
+    part[(size_t)split * Cout + co] = s;
+  }
+}
+
+// out[i] = sum over splits (ascending) of part[s][i]
+__global__ void __launch_bounds__(256)
+reduce_splits_kernel(const float* __restrict__ part, float* __restrict__ out, long long n, int splits) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += part[(size_t)k * n + i];
+    out[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pointwise
+enum { PW_LRELU_BWD = 0, PW_SIGMOID = 1, PW_SIGMOID_BWD = 2 };
+
+// a, b, out: [npix][C] with pitches; LRELU_BWD: out = b * (a > 0 ? 1 : slope) (a = saved output, b = grad);
+// SIGMOID: out = 1/(1+exp(-a)); SIGMOID_BWD: out = b * a * (1 - a) (a = saved output)
+__global__ void __launch_bounds__(256)
+pointwise_kernel(int op, const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                 float* __restrict__ out, int ldo, long long npix, int C, float slope) {
+  const long long total = npix * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / C;
+    const int c = (int)(i - p * C);
+    const float av = a[(size_t)p * lda + c];
+    float r;
+    if (op == PW_LRELU_BWD) r = b[(size_t)p * ldb + c] * (av > 0.f ? 1.0f : slope);
+    else if (op == PW_SIGMOID) r = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-av)));
+    else r = b[(size_t)p * ldb + c] * av * (1.0f - av);
+    out[(size_t)p * ldo + c] = r;
+  }
+}
+
+// blend of sgu_model.forward (model/upflow.py:88): out_c = w_c * (1 - m) + f_c * m, c in {0,1}
+__global__ void __launch_bounds__(256)
+blend_fwd_kernel(const float* __restrict__ w, int ldw, const float* __restrict__ f, int ldf, const float* __restrict__ m,
+                 int ldm, float* __restrict__ out, int ldo, long long npix) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+    const float mv = m[(size_t)p * ldm];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+      out[(size_t)p * ldo + c] = __fadd_rn(__fmul_rn(w[(size_t)p * ldw + c], __fsub_rn(1.0f, mv)), __fmul_rn(f[(size_t)p * ldf + c], mv));
+  }
+}
+// gw_c = g_c (1 - m); gf_c = g_c m; gm = sum_c g_c (f_c - w_c)
+__global__ void __launch_bounds__(256)
+blend_bwd_kernel(const float* __restrict__ w, int ldw, const float* __restrict__ f, int ldf, const float* __restrict__ m,
+                 int ldm, const float* __restrict__ g, int ldg, float* __restrict__ gw, int ldgw, float* __restrict__ gf,
+                 int ldgf, float* __restrict__ gm, int ldgm, long long npix) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+    const float mv = m[(size_t)p * ldm];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float gv = g[(size_t)p * ldg + c];
+      gw[(size_t)p * ldgw + c] = gv * (1.0f - mv);
+      gf[(size_t)p * ldgf + c] = gv * mv;
+      s = fmaf(gv, f[(size_t)p * ldf + c] - w[(size_t)p * ldw + c], s);
+    }
+    gm[(size_t)p * ldgm] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ normalisation
+// y = (x - mean) / std with mean, std functions of x (unbiased variance, std = sqrt(var + 1e-16)):
+//   dx = ( g - mean(g) - y * sum(g*y) / (n-1) ) / std
+// pass 1: per split, per (image, channel): sum g and sum g*y over a pixel range -> part[split][n][c][2] (double)
+__global__ void __launch_bounds__(256)
+featnorm_bwd_sums_kernel(const float* __restrict__ x, int ldx, const double* __restrict__ stats, const float* __restrict__ g,
+                         int ldg, double* __restrict__ part, int N, int HW, int C, int splits) {
+  const int n = blockIdx.x / splits, split = blockIdx.x % splits;
+  const int per = (HW + splits - 1) / splits;
+  const int p_begin = split * per, p_end = min(HW, p_begin + per);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float m, s;
+    stats_to_mean_std(stats + ((size_t)n * C + c) * 2, (double)HW, m, s);
+    double sg = 0.0, sgy = 0.0;
+    for (int p = p_begin; p < p_end; ++p) {
+      const size_t pix = (size_t)n * HW + p;
+      const float gv = g[pix * ldg + c];
+      const float y = __fdiv_rn(__fsub_rn(x[pix * ldx + c], m), s);
+      sg += (double)gv;
+      sgy += (double)gv * (double)y;
+    }
+    double* d = part + (((size_t)split * N + n) * C + c) * 2;
+    d[0] = sg; d[1] = sgy;
+  }
+}
+__global__ void __launch_bounds__(256)
+featnorm_bwd_apply_kernel(const float* __restrict__ x, int ldx, const double* __restrict__ stats, const float* __restrict__ g,
+                          int ldg, const double* __restrict__ part, float* __restrict__ gx, int ldgx, int N, int HW, int C,
+                          int splits) {
+  const long long total = (long long)N * HW * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pix = i / C;
+    const int n = (int)(pix / HW);
+    float m, s;
+    stats_to_mean_std(stats + ((size_t)n * C + c) * 2, (double)HW, m, s);
+    double sg = 0.0, sgy = 0.0;
+    for (int k = 0; k < splits; ++k) {
+      const double* d = part + (((size_t)k * N + n) * C + c) * 2;
+      sg += d[0]; sgy += d[1];
+    }
+    const float y = __fdiv_rn(__fsub_rn(x[(size_t)pix * ldx + c], m), s);
+    const double v = ((double)g[(size_t)pix * ldg + c] - sg / (double)HW - (double)y * sgy / (double)(HW - 1)) / (double)s;
+    gx[(size_t)pix * ldgx + c] = (float)v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ resize backward
+// gather form of the adjoint of resize_bilinear_kernel: input pixel (iy, ix) collects every output pixel whose two
+// taps touch it (exact test with the forward's own tap computation), multiplied by the channel scale.
+__global__ void __launch_bounds__(256)
+resize_bilinear_bwd_kernel(const float* __restrict__ gout, int ldgo, int H, int W, float* __restrict__ gin, int ldgi,
+                           int h, int w, int N, int C, float sy, float sx, float4 scale) {
+  const long long total = (long long)N * h * w;
+  const float sc[4] = {scale.x, scale.y, scale.z, scale.w};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(i % w);
+    const long long t = i / w;
+    const int iy = (int)(t % h), n = (int)(t / h);
+    int oy_lo = 0, oy_hi = H - 1, ox_lo = 0, ox_hi = W - 1;
+    if (sy > 0.f) { oy_lo = max(0, (int)floorf((iy - 1) / sy) - 1); oy_hi = min(H - 1, (int)ceilf((iy + 1) / sy) + 1); }
+    if (sx > 0.f) { ox_lo = max(0, (int)floorf((ix - 1) / sx) - 1); ox_hi = min(W - 1, (int)ceilf((ix + 1) / sx) + 1); }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      const AxisTap ty = axis_tap(oy, h, sy);
+      if (ty.i0 != iy && ty.i1 != iy) continue;
+      const float wy = (ty.i0 == iy ? ty.l0 : 0.f) + (ty.i1 == iy ? ty.l1 : 0.f);
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        const AxisTap tx = axis_tap(ox, w, sx);
+        if (tx.i0 != ix && tx.i1 != ix) continue;
+        const float wx = (tx.i0 == ix ? tx.l0 : 0.f) + (tx.i1 == ix ? tx.l1 : 0.f);
+        const float* gp = gout + ((size_t)((size_t)n * H + oy) * W + ox) * ldgo;
+        const float wgt = wy * wx;
+        for (int c = 0; c < C; ++c) acc[c] = fmaf(gp[c], wgt, acc[c]);
+      }
+    }
+    float* o = gin + (size_t)i * ldgi;
+    for (int c = 0; c < C; ++c) o[c] = acc[c] * sc[c];
+  }
+}
+
+static unsigned grid_for(long long total) {
+  long long b = (total + 255) / 256;
+  if (b > UPF_NUM_SMS * 16) b = UPF_NUM_SMS * 16;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace upf
+
+// number of pixel splits the weight gradient uses for this shape (the caller sizes the workspace with it)
+static int wgrad_splits(int Cin, int Cout, int taps, long long npix) {
+  const long long tiles = (long long)((Cin + upf::WG_BM - 1) / upf::WG_BM) * ((Cout + upf::WG_BN - 1) / upf::WG_BN) * taps;
+  long long s = (4 * UPF_NUM_SMS + tiles - 1) / tiles;
+  const long long max_by_pix = (npix + 255) / 256;
+  if (s > max_by_pix) s = max_by_pix;
+  if (s > 128) s = 128;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+extern "C" long long upf_conv2d_wgrad_workspace_elems(int N, int H, int W, int Cin, int Cout, int ksize, int stride, int dilation) {
+  const int pad = ((ksize - 1) * dilation) / 2;
+  const int Ho = (H + 2 * pad - dilation * (ksize - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dilation * (ksize - 1) - 1) / stride + 1;
+  const int taps = ksize * ksize;
+  const int s = wgrad_splits(Cin, Cout, taps, (long long)N * Ho * Wo);
+  return (long long)s * ((long long)taps * Cin * Cout + Cout);
+}
+
+extern "C" int upf_conv2d_wgrad(const float* x, int ldx, const float* grad_out, int ldg, float* grad_w, float* grad_bias,
+                                float* workspace, int N, int H, int W, int Cin, int Cout, int ksize, int stride,
+                                int dilation, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(x && grad_out && grad_w && workspace, "wgrad: null tensor");
+  UPF_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "wgrad: bad shape");
+  UPF_REQUIRE(ksize == 1 || ksize == 3, "wgrad: kernel size %d not in {1,3}", ksize);
+  UPF_REQUIRE(stride >= 1 && dilation >= 1 && ldx >= Cin && ldg >= Cout, "wgrad: bad stride/dilation/pitch");
+  const int pad = ((ksize - 1) * dilation) / 2;
+  const int Ho = (H + 2 * pad - dilation * (ksize - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dilation * (ksize - 1) - 1) / stride + 1;
+  const int taps = ksize * ksize;
+  const long long npix = (long long)N * Ho * Wo;
+  const int splits = wgrad_splits(Cin, Cout, taps, npix);
+  const long long pps = ((npix + splits - 1) / splits + WG_KP - 1) / WG_KP * WG_KP;
+  const int ci_tiles = (Cin + WG_BM - 1) / WG_BM, co_tiles = (Cout + WG_BN - 1) / WG_BN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long wn = (long long)taps * Cin * Cout;
+  conv_wgrad_kernel<<<dim3(ci_tiles * co_tiles, taps, splits), WG_NT, 0, st>>>(x, ldx, grad_out, ldg, workspace, N, H, W, Ho, Wo, Cin,
+                                                                              Cout, ksize, stride, dilation, pad, co_tiles, pps, npix);
+  int e = check_launch("conv_wgrad");
+  if (e) return e;
+  reduce_splits_kernel<<<grid_for(wn), 256, 0, st>>>(workspace, grad_w, wn, splits);
+  e = check_launch("wgrad_reduce");
+  if (e) return e;
+  if (grad_bias) {
+    float* bpart = workspace + (size_t)splits * wn;
+    colsum_kernel<<<splits, 256, 0, st>>>(grad_out, ldg, bpart, Cout, pps, npix);
+    e = check_launch("bias_colsum");
+    if (e) return e;
+    reduce_splits_kernel<<<1, 256, 0, st>>>(bpart, grad_bias, Cout, splits);
+    e = check_launch("bias_reduce");
+  }
+  return e;
+}
+
+extern "C" int upf_pointwise(int op, const float* a, int lda, const float* b, int ldb, float* out, int ldo, long long npix,
+                             int C, float slope, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(a && out && (b || op == PW_SIGMOID), "pointwise: null tensor");
+  UPF_REQUIRE(op >= 0 && op <= 2 && npix > 0 && C > 0 && lda >= C && ldo >= C, "pointwise: bad argument");
+  pointwise_kernel<<<grid_for(npix * C), 256, 0, (cudaStream_t)stream>>>(op, a, lda, b, ldb, out, ldo, npix, C, slope);
+  return check_launch("pointwise");
+}
+
+extern "C" int upf_blend_fwd(const float* w, int ldw, const float* f, int ldf, const float* m, int ldm, float* out, int ldo,
+                             long long npix, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(w && f && m && out && npix > 0, "blend_fwd: bad argument");
+  blend_fwd_kernel<<<grid_for(npix), 256, 0, (cudaStream_t)stream>>>(w, ldw, f, ldf, m, ldm, out, ldo, npix);
+  return check_launch("blend_fwd");
+}
+extern "C" int upf_blend_bwd(const float* w, int ldw, const float* f, int ldf, const float* m, int ldm, const float* g, int ldg,
+                             float* gw, int ldgw, float* gf, int ldgf, float* gm, int ldgm, long long npix, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(w && f && m && g && gw && gf && gm && npix > 0, "blend_bwd: bad argument");
+  blend_bwd_kernel<<<grid_for(npix), 256, 0, (cudaStream_t)stream>>>(w, ldw, f, ldf, m, ldm, g, ldg, gw, ldgw, gf, ldgf, gm, ldgm, npix);
+  return check_launch("blend_bwd");
+}
+
+#define UPF_FEATNORM_BWD_SPLITS 32
+extern "C" long long upf_featnorm_bwd_workspace_doubles(int N, int C) { return (long long)UPF_FEATNORM_BWD_SPLITS * N * C * 2; }
+extern "C" int upf_featnorm_bwd(const float* x, int ldx, const double* stats, const float* grad_out, int ldg, float* grad_x,
+                                int ldgx, double* workspace, int N, int H, int W, int C, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(x && stats && grad_out && grad_x && workspace, "featnorm_bwd: null tensor");
+  UPF_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && ldx >= C && ldg >= C && ldgx >= C, "featnorm_bwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int splits = UPF_FEATNORM_BWD_SPLITS;
+  featnorm_bwd_sums_kernel<<<N * splits, 256, 0, st>>>(x, ldx, stats, grad_out, ldg, workspace, N, H * W, C, splits);
+  int e = check_launch("featnorm_bwd_sums");
+  if (e) return e;
+  featnorm_bwd_apply_kernel<<<grid_for((long long)N * H * W * C), 256, 0, st>>>(x, ldx, stats, grad_out, ldg, workspace, grad_x, ldgx,
+                                                                               N, H * W, C, splits);
+  return check_launch("featnorm_bwd_apply");
+}
+
+extern "C" int upf_resize_bilinear_bwd(const float* grad_out, int ldgo, int H, int W, float* grad_in, int ldgi, int h, int w,
+                                       int N, int C, const float* scale_host, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(grad_out && grad_in, "resize_bwd: null tensor");
+  UPF_REQUIRE(N > 0 && H > 0 && W > 0 && h > 0 && w > 0 && C > 0 && C <= 4 && ldgo >= C && ldgi >= C, "resize_bwd: bad shape");
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (scale_host) sc = make_float4(scale_host[0], scale_host[1], scale_host[2], scale_host[3]);
+  resize_bilinear_bwd_kernel<<<grid_for((long long)N * h * w), 256, 0, (cudaStream_t)stream>>>(
+      grad_out, ldgo, H, W, grad_in, ldgi, h, w, N, C, host_ac_scale(h, H), host_ac_scale(w, W), sc);
+  return check_launch("resize_bwd");
+}

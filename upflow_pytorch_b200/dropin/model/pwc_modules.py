@@ -44,10 +44,10 @@ class _ConvBlock(nn.Sequential):
 
     def forward(self, x):
         c = self[0]
-        if torch.is_grad_enabled() and (x.requires_grad or c.weight.requires_grad):
-            raise NotImplementedError(
-                "upflow_b200 conv: the backward kernels (a11, SURVEY.md section 8) are not built yet; "
-                "run under torch.no_grad()")
+        if torch.is_grad_enabled() and (x.requires_grad or c.weight.requires_grad or c.bias.requires_grad):
+            # training: autograd node whose backward is dgrad (forward kernel on flipped weights) + upf_conv2d_wgrad
+            return ops.conv2d_autograd(x, c.weight, c.bias, c.stride[0], c.dilation[0], 0.1 if self.is_relu else 1.0,
+                                       _PRECISION["mode"])
         w, b, tc = self.packed(_PRECISION["mode"])
         return ops.conv2d(x, w, b, c.out_channels, c.kernel_size[0], c.stride[0], c.dilation[0],
                           0.1 if self.is_relu else 1.0, _ext.CONV_TF32 if tc else _ext.CONV_FP32)
@@ -142,8 +142,11 @@ class _DenseBlock(tools.abstract_model):
 
     def forward(self, x):
         ops._require_cuda(x)
-        if torch.is_grad_enabled() and (x.requires_grad or self.conv_last[0].weight.requires_grad):
-            raise NotImplementedError("dense block backward is not built yet; run under torch.no_grad()")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # training: the reference's own data flow (model/pwc_modules.py:279-286), every conv an autograd node
+            for i in range(len(self._f)):
+                x = torch.cat([getattr(self, "conv%d" % (i + 1))(x), x], dim=1)
+            return x, self.conv_last(x)
         B, C, H, W = x.shape
         total = C + sum(self._f)
         ld = (total + 3) // 4 * 4

@@ -58,7 +58,7 @@ class network_tools():
             # sigmoid, the two upsamples, torch_warp and the blend are one kernel (upf_sgu_blend)
             flow_up = ops.sgu_blend(flow_init, x_out)
             inter_flow = x_out[:, :2, :, :]
-            inter_mask = torch.sigmoid(x_out[:, 2:3, :, :])
+            inter_mask = ops.sigmoid(x_out[:, 2:3, :, :])
             if output_level_flow is not None:
                 inter_flow = upsample2d_flow_as(inter_flow, output_level_flow, mode="bilinear", if_rate=True)
                 inter_mask = upsample2d_flow_as(inter_mask, output_level_flow, mode="bilinear")
@@ -188,9 +188,8 @@ class UPFlow_net(tools.abstract_model):
         if not x1_raw.is_cuda:
             raise RuntimeError("UPFlow_net (upflow_pytorch_b200) runs on CUDA only: move the model and the inputs "
                                "with .cuda(); there is no CPU path")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("training through the fused decoder needs the backward kernels (not built yet); "
-                                      "call under torch.no_grad()")
+        if torch.is_grad_enabled() and (x1_raw.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return self._forward_2_frame_modules(x1_raw, x2_raw)
         eng = self._get_engine()
         if self.use_cuda_graph:
             key = tuple(x1_raw.shape)
@@ -204,6 +203,35 @@ class UPFlow_net(tools.abstract_model):
         else:
             f, b, flows = eng.forward(x1_raw.float(), x2_raw.float())
         return f.clone(), b.clone(), [[a.clone(), c.clone()] for a, c in flows]
+
+    def _forward_2_frame_modules(self, x1_raw, x2_raw):
+        """Training path: model/upflow.py:494-533 module by module, every op an autograd node backed by the
+        library's forward AND backward kernels (ops.py)."""
+        x1_pyramid = self.feature_pyramid_extractor(x1_raw) + [x1_raw]
+        x2_pyramid = self.feature_pyramid_extractor(x2_raw) + [x2_raw]
+        b_size, _, h0, w0 = x1_pyramid[0].shape
+        flow_f = torch.zeros(b_size, 2, h0, w0, dtype=torch.float32, device=x1_raw.device)
+        flow_b = torch.zeros_like(flow_f)
+        levels = []
+        for l, (x1, x2) in enumerate(zip(x1_pyramid, x2_pyramid)):
+            levels.append((x1, self.conv_1x1[l](x1), x2, self.conv_1x1[l](x2)))
+            if l == self.output_level:
+                break
+        flows = []
+        for level, (x1, x1_1by1, x2, x2_1by1) in enumerate(levels):
+            flow_f, flow_b, res_f, res_b = self.decode_level_res(level, flow_f, flow_b, x1, x1_1by1, x2, x2_1by1,
+                                                                 x1_raw, x2_raw)
+            flow_f = flow_f + res_f
+            flow_b = flow_b + res_b
+            flows.append([flow_f, flow_b])
+        flow_f_out = upsample2d_flow_as(flow_f, x1_raw, mode="bilinear", if_rate=True)
+        flow_b_out = upsample2d_flow_as(flow_b, x1_raw, mode="bilinear", if_rate=True)
+        if self.conf.if_sgu_upsample:
+            f1 = self.sgi_model.output_conv(x1_raw)
+            f2 = self.sgi_model.output_conv(x2_raw)
+            flow_f_out = self.self_guided_upsample(flow_f, f1, f2, output_level_flow=flow_f_out)
+            flow_b_out = self.self_guided_upsample(flow_b, f2, f1, output_level_flow=flow_b_out)
+        return flow_f_out, flow_b_out, flows[::-1]
 
     def decode_level_res(self, level, flow_1, flow_2, feature_1, feature_1_1x1, feature_2, feature_2_1x1, img_ori_1,
                          img_ori_2):

@@ -21,6 +21,9 @@ import torch
 from . import _ext
 
 LRELU_SLOPE = 0.1
+# diagnostic only (tests): replaces the reference's `mask >= 1.0` threshold of every module-level warp, like
+# oracle/ref_port.MASK_THRESHOLD on the other side (see tests/test_gpu_engine.py for why)
+DIAG_MASK_THRESHOLD = None
 
 
 def _lib():
@@ -106,7 +109,7 @@ def k_corr_bwd(f1, f2, out, grad_out, grad_f1, grad_f2, max_disp=4, slope=1.0):
 def _mask_thr(use_mask):
     """True -> 1.0 (the reference's `mask >= 1.0`), False -> no mask, float -> that threshold (diagnostic)."""
     if use_mask is True:
-        return 1.0
+        return 1.0 if DIAG_MASK_THRESHOLD is None else float(DIAG_MASK_THRESHOLD)
     if use_mask is False or use_mask is None:
         return 0.0
     return float(use_mask)
@@ -165,6 +168,44 @@ def k_conv(x, weight, bias, out, ksize, stride=1, dilation=1, slope=LRELU_SLOPE,
     _ext.check(_lib().upf_conv2d_fwd(x.ptr(), x.ld, _p(weight), _p(bias), out.ptr(), out.ld, res.ptr() if res else None,
                                      res.ld if res else 0, x.N, x.H, x.W, x.C, out.C, ksize, stride, dilation,
                                      float(slope), int(precision), _stream()), "conv2d_fwd")
+
+
+def k_conv_wgrad(x, grad_out, ksize, stride=1, dilation=1, want_bias=True):
+    """Weight gradient [k*k, Cin, Cout] and bias gradient [Cout] of conv() from its input and the gradient wrt its
+    PRE-activation output (both pixel-major)."""
+    x, g = _as_slice(x), _as_slice(grad_out)
+    lib = _lib()
+    n = lib.upf_conv2d_wgrad_workspace_elems(x.N, x.H, x.W, x.C, g.C, ksize, stride, dilation)
+    ws = torch.empty(n, dtype=torch.float32, device=x.buf.device)
+    gw = torch.empty(ksize * ksize, x.C, g.C, dtype=torch.float32, device=x.buf.device)
+    gb = torch.empty(g.C, dtype=torch.float32, device=x.buf.device) if want_bias else None
+    _ext.check(lib.upf_conv2d_wgrad(x.ptr(), x.ld, g.ptr(), g.ld, _p(gw), _p(gb), _p(ws), x.N, x.H, x.W, x.C, g.C, ksize,
+                                    stride, dilation, _stream()), "conv2d_wgrad")
+    return gw, gb
+
+
+def k_pointwise(op, a, b, out, slope=LRELU_SLOPE):
+    a, out = _as_slice(a), _as_slice(out)
+    b = _as_slice(b) if b is not None else None
+    _ext.check(_lib().upf_pointwise(op, a.ptr(), a.ld, b.ptr() if b else None, b.ld if b else 0, out.ptr(), out.ld,
+                                    a.N * a.H * a.W, a.C, float(slope), _stream()), "pointwise")
+
+
+def k_featnorm_bwd(x, stats, grad_out, grad_x):
+    x, g, gx = _as_slice(x), _as_slice(grad_out), _as_slice(grad_x)
+    lib = _lib()
+    ws = torch.empty(lib.upf_featnorm_bwd_workspace_doubles(x.N, x.C), dtype=torch.float64, device=x.buf.device)
+    _ext.check(lib.upf_featnorm_bwd(x.ptr(), x.ld, ctypes.c_void_p(stats.data_ptr()), g.ptr(), g.ld, gx.ptr(), gx.ld,
+                                    ctypes.c_void_p(ws.data_ptr()), x.N, x.H, x.W, x.C, _stream()), "featnorm_bwd")
+
+
+def k_resize_bwd(grad_out, grad_in, scale=None):
+    g, gi = _as_slice(grad_out), _as_slice(grad_in)
+    sc = None
+    if scale is not None:
+        sc = (ctypes.c_float * 4)(*([float(v) for v in scale] + [1.0] * (4 - len(scale))))
+    _ext.check(_lib().upf_resize_bilinear_bwd(g.ptr(), g.ld, g.H, g.W, gi.ptr(), gi.ld, gi.H, gi.W, g.N, g.C, sc, _stream()),
+               "resize_bilinear_bwd")
 
 
 def k_copy(src, dst):
@@ -296,16 +337,53 @@ def warp(x, flow, align_corners=False, use_mask=True):
     return _WarpFn.apply(x, flow, bool(align_corners), use_mask)
 
 
+class _NormFn(torch.autograd.Function):
+    """normalize_features for one tensor; the backward differentiates through torch.mean / torch.var like autograd
+    does on the reference (model/upflow.py:108-135)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        a = to_pixel_major(x)
+        N, H, W, C = a.shape
+        stats = torch.zeros(N, C, 2, dtype=torch.float64, device=x.device)
+        k_stats(a, stats)
+        out = torch.empty_like(a)
+        k_norm_apply(a, stats, out)
+        ctx.save_for_backward(a, stats)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad):
+        a, stats = ctx.saved_tensors
+        g = to_pixel_major(grad)
+        gx = torch.empty_like(a)
+        k_featnorm_bwd(a, stats, g, gx)
+        return gx.permute(0, 3, 1, 2)
+
+
 def normalize_features(x):
     """Per-image per-channel (x-mean)/sqrt(var+1e-16), unbiased var (model/upflow.py:108-135)."""
     _require_cuda(x)
-    a = to_pixel_major(x)
-    N, H, W, C = a.shape
-    stats = torch.zeros(N, C, 2, dtype=torch.float64, device=x.device)
-    k_stats(a, stats)
-    out = torch.empty_like(a)
-    k_norm_apply(a, stats, out)
-    return out.permute(0, 3, 1, 2)
+    return _NormFn.apply(x)
+
+
+class _ResizeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, h, w, scale):
+        a = to_pixel_major(x)
+        N, hi, wi, C = a.shape
+        out = _new(N, h, w, C, x)
+        k_resize(a, out, scale)
+        ctx.cfg = (hi, wi, scale)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad):
+        hi, wi, scale = ctx.cfg
+        g = to_pixel_major(grad)
+        gi = _new(g.shape[0], hi, wi, g.shape[3], grad)
+        k_resize_bwd(g, gi, scale)
+        return gi.permute(0, 3, 1, 2), None, None, None
 
 
 def resize_bilinear(x, h, w, flow_rate=False):
@@ -315,24 +393,146 @@ def resize_bilinear(x, h, w, flow_rate=False):
     N, hi, wi, C = a.shape
     if C > 4:
         raise RuntimeError("resize_bilinear: at most 4 channels (flows and masks)")
-    out = _new(N, h, w, C, x)
     scale = None
     if flow_rate:
         if C != 2:
             raise RuntimeError("if_rate=True needs a 2-channel flow")
         scale = (w / wi, h / hi)
-    k_resize(a, out, scale)
-    return out.permute(0, 3, 1, 2)
+    return _ResizeFn.apply(x, h, w, scale)
+
+
+class _PointwiseFn(torch.autograd.Function):
+    """sigmoid with its backward taken from the saved output."""
+
+    @staticmethod
+    def forward(ctx, x):
+        a = to_pixel_major(x)
+        out = torch.empty_like(a)
+        k_pointwise(_ext.PW_SIGMOID, a, None, out)
+        ctx.save_for_backward(out)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (out,) = ctx.saved_tensors
+        g = to_pixel_major(grad)
+        gx = torch.empty_like(out)
+        k_pointwise(_ext.PW_SIGMOID_BWD, out, g, gx)
+        return gx.permute(0, 3, 1, 2)
+
+
+class _BlendFn(torch.autograd.Function):
+    """out = w*(1-m) + f*m (model/upflow.py:88) on [B,2,H,W], [B,2,H,W], [B,1,H,W]."""
+
+    @staticmethod
+    def forward(ctx, w, f, m):
+        wa, fa, ma = to_pixel_major(w), to_pixel_major(f), to_pixel_major(m)
+        out = torch.empty_like(fa)
+        npix = fa.shape[0] * fa.shape[1] * fa.shape[2]
+        _ext.check(_lib().upf_blend_fwd(_p(wa), 2, _p(fa), 2, _p(ma), 1, _p(out), 2, npix, _stream()), "blend_fwd")
+        ctx.save_for_backward(wa, fa, ma)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad):
+        wa, fa, ma = ctx.saved_tensors
+        g = to_pixel_major(grad)
+        gw, gf, gm = torch.empty_like(wa), torch.empty_like(fa), torch.empty_like(ma)
+        npix = fa.shape[0] * fa.shape[1] * fa.shape[2]
+        _ext.check(_lib().upf_blend_bwd(_p(wa), 2, _p(fa), 2, _p(ma), 1, _p(g), 2, _p(gw), 2, _p(gf), 2, _p(gm), 1, npix,
+                                        _stream()), "blend_bwd")
+        return gw.permute(0, 3, 1, 2), gf.permute(0, 3, 1, 2), gm.permute(0, 3, 1, 2)
+
+
+def sigmoid(x):
+    _require_cuda(x)
+    return _PointwiseFn.apply(x)
 
 
 def sgu_blend(flow_init, inter, align_corners=False):
     """flow_up of sgu_model.forward (model/upflow.py:79-88) from flow_init [B,2,H,W] at output resolution and the dense
-    block's raw 3-channel output ``inter`` (inter_flow u,v + mask logit), at the same or a lower resolution."""
+    block's raw 3-channel output ``inter`` (inter_flow u,v + mask logit), at the same or a lower resolution.
+    Without autograd this is ONE fused kernel; when a gradient is needed it is the same arithmetic as a chain of
+    differentiable pieces (sigmoid, the two upsamples, the un-masked warp, the blend), each with its own kernels."""
     _require_cuda(flow_init, inter)
+    if torch.is_grad_enabled() and (flow_init.requires_grad or inter.requires_grad):
+        H, W = flow_init.shape[2:]
+        inter_flow, mask = inter[:, :2], sigmoid(inter[:, 2:3])
+        if inter.shape[2:] != flow_init.shape[2:]:
+            inter_flow = resize_bilinear(inter_flow, H, W, flow_rate=True)
+            mask = resize_bilinear(mask, H, W)
+        return _BlendFn.apply(warp(flow_init, inter_flow, align_corners, use_mask=False), flow_init, mask)
     f, i = to_pixel_major(flow_init), to_pixel_major(inter)
     out = torch.empty_like(f)
     k_sgu_blend(f, i, out, align_corners)
     return out.permute(0, 3, 1, 2)
+
+
+class _ConvFn(torch.autograd.Function):
+    """conv() of model/pwc_modules.py:10-31 with autograd: the input gradient is the forward kernel on the flipped,
+    transposed weights (on the zero-interleaved gradient for stride 2), the weight / bias gradient is
+    upf_conv2d_wgrad, the LeakyReLU derivative comes from the saved output."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, dilation, slope, precision):
+        Cout, Cin, ks, _ = weight.shape
+        tc = precision == _ext.CONV_TF32
+        w_simt, w_tc = pack_conv_weight(weight, tc=tc)
+        a = Slice(to_pixel_major(x, ld=(Cin + 3) // 4 * 4), 0, Cin) if (tc and Cin % 4) else Slice(to_pixel_major(x))
+        pad = ((ks - 1) * dilation) // 2
+        Ho = (a.H + 2 * pad - dilation * (ks - 1) - 1) // stride + 1
+        Wo = (a.W + 2 * pad - dilation * (ks - 1) - 1) // stride + 1
+        out = _new(a.N, Ho, Wo, Cout, x)
+        k_conv(a, w_tc if tc else w_simt, bias.detach().float().contiguous(), out, ks, stride, dilation, slope, None, precision)
+        ctx.save_for_backward(a.buf, out, weight)
+        ctx.cfg = (Cin, stride, dilation, slope, precision)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad):
+        abuf, out, weight = ctx.saved_tensors
+        Cin, stride, dilation, slope, precision = ctx.cfg
+        Cout, _, ks, _ = weight.shape
+        a = Slice(abuf, 0, Cin)
+        tc = precision == _ext.CONV_TF32
+        N, Ho, Wo, _ = out.shape
+        g = to_pixel_major(grad)
+        ldg = (Cout + 3) // 4 * 4
+        if slope != 1.0 or ldg != Cout:
+            gp = torch.zeros(N, Ho, Wo, ldg, dtype=torch.float32, device=grad.device) if ldg != Cout else \
+                torch.empty(N, Ho, Wo, ldg, dtype=torch.float32, device=grad.device)
+            if slope != 1.0:
+                k_pointwise(_ext.PW_LRELU_BWD, out, g, Slice(gp, 0, Cout), slope)
+            else:
+                k_copy(Slice(g), Slice(gp, 0, Cout))
+        else:
+            gp = g
+        gps = Slice(gp, 0, Cout)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            gw_t, gb = k_conv_wgrad(a, gps, ks, stride, dilation, want_bias=True)
+            gw = gw_t.reshape(ks, ks, Cin, Cout).permute(3, 2, 0, 1).contiguous()
+        if ctx.needs_input_grad[0]:
+            w_d = weight.detach().flip(2, 3).transpose(0, 1).contiguous()         # [Cin, Cout, k, k]
+            w_simt, w_tc = pack_conv_weight(w_d, tc=tc)
+            if stride == 1:
+                src = gps
+            else:
+                # adjoint of a strided convolution = stride-1 convolution of the zero-interleaved gradient
+                up = torch.zeros(N, a.H, a.W, ldg, dtype=torch.float32, device=grad.device)
+                up[:, ::stride, ::stride, :][:, :Ho, :Wo] = gp
+                src = Slice(up, 0, Cout)
+            gxb = _new(a.N, a.H, a.W, Cin, grad)
+            zero_b = torch.zeros(Cin, dtype=torch.float32, device=grad.device)
+            k_conv(src, w_tc if tc else w_simt, zero_b, gxb, ks, 1, dilation, 1.0, None, precision)
+            gx = gxb.permute(0, 3, 1, 2)
+        return gx, gw, gb, None, None, None, None
+
+
+def conv2d_autograd(x, weight, bias, stride=1, dilation=1, slope=LRELU_SLOPE, precision=_ext.CONV_FP32):
+    """conv() + LeakyReLU with gradients wrt x, weight and bias (training path)."""
+    _require_cuda(x, weight)
+    return _ConvFn.apply(x, weight, bias, int(stride), int(dilation), float(slope), int(precision))
 
 
 def conv2d(x, w_packed, bias, cout, ksize, stride=1, dilation=1, slope=LRELU_SLOPE, precision=_ext.CONV_FP32):
