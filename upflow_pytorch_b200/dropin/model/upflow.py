@@ -6,10 +6,12 @@ the reference's names, signatures, output dictionary and state-dict keys
 
 Inference (`if_loss=False`, the path test.py drives, test.py:40-47) runs on
 `upflow_pytorch_b200.engine.DecoderEngine` -- both flow directions stacked,
-fused kernels, no torch.cat.  The per-level methods keep the reference's
-module-level semantics for callers that use them directly.  The loss branch
-(model/upflow.py:394-491) is outside the hot path (SURVEY.md section 2 rows
-12-14) and is not provided in this round.
+fused kernels, no torch.cat.  With autograd enabled (training,
+scripts/simple_train.py:140-146) the same forward runs module by module, every
+op an autograd node whose forward AND backward are this library's kernels
+(ops.py).  The loss branch (model/upflow.py:394-491) is elementwise torch around
+the library warp: smoothness, photometric and multi-scale-distillation terms;
+the boundary-dilated warp and the census term are rejected, not approximated.
 """
 from __future__ import absolute_import, division, print_function
 
@@ -76,6 +78,61 @@ class network_tools():
             raise NotImplementedError("only normalize=center=True with per-image per-channel moments "
                                       "(norm_moments_across_channels=False, norm_moments_across_images=False)")
         return [ops.normalize_features(f) for f in feature_list]
+
+    # ---- loss terms of the training step (model/upflow.py:198-290).  They run AFTER the decoder on full-resolution
+    # 2-/3-channel tensors: elementwise torch around the library's warp (loss kernels: SURVEY.md section 8f rank 2).
+    @classmethod
+    def edge_aware_smoothness_order1(cls, img, pred):
+        """model/upflow.py:198-218 (note the reference's naming: `gradient_x` differences ROWS)."""
+        def d_rows(t):
+            return t[:, :, :-1, :] - t[:, :, 1:, :]
+
+        def d_cols(t):
+            return t[:, :, :, :-1] - t[:, :, :, 1:]
+        w_r = torch.exp(-torch.mean(torch.abs(d_rows(img)), 1, keepdim=True))
+        w_c = torch.exp(-torch.mean(torch.abs(d_cols(img)), 1, keepdim=True))
+        return torch.mean(torch.abs(d_rows(pred)) * w_r) + torch.mean(torch.abs(d_cols(pred)) * w_c)
+
+    @classmethod
+    def edge_aware_smoothness_order2(cls, img, pred):
+        """model/upflow.py:220-245."""
+        def d_rows(t, s=1):
+            return t[:, :, :-s, :] - t[:, :, s:, :]
+
+        def d_cols(t, s=1):
+            return t[:, :, :, :-s] - t[:, :, :, s:]
+        w_r = torch.exp(-torch.mean(torch.abs(d_rows(img, 2)), 1, keepdim=True))
+        w_c = torch.exp(-torch.mean(torch.abs(d_cols(img, 2)), 1, keepdim=True))
+        return torch.mean(torch.abs(d_rows(d_rows(pred))) * w_r) + torch.mean(torch.abs(d_cols(d_cols(pred))) * w_c)
+
+    @classmethod
+    def flow_smooth_delta(cls, flow, if_second_order=False):
+        """model/upflow.py:247-266."""
+        def grad(x):
+            return x[:, :, :, 1:] - x[:, :, :, :-1], x[:, :, 1:] - x[:, :, :-1]
+        dx, dy = grad(flow)
+        loss = dx.abs().mean() + dy.abs().mean()
+        if if_second_order:
+            dx2, dxdy = grad(dx)
+            dydx, dy2 = grad(dy)
+            loss = loss + dx2.abs().mean() + dxdy.abs().mean() + dydx.abs().mean() + dy2.abs().mean()
+        return loss
+
+    @classmethod
+    def photo_loss_multi_type(cls, x, y, occ_mask, photo_loss_type='abs_robust', photo_loss_delta=0.4,
+                              photo_loss_use_occ=False):
+        """model/upflow.py:268-290 (the SSIM variant is not provided)."""
+        if photo_loss_type == 'abs_robust':
+            loss_diff = (torch.abs(x - y) + 0.01).pow(photo_loss_delta)
+        elif photo_loss_type == 'charbonnier':
+            loss_diff = ((x - y) ** 2 + 1e-6).pow(photo_loss_delta)
+        elif photo_loss_type == 'L1':
+            loss_diff = torch.abs(x - y + 1e-6)
+        else:
+            raise NotImplementedError('photo_loss type %s' % photo_loss_type)
+        if photo_loss_use_occ:
+            return torch.sum(loss_diff * occ_mask) / (torch.sum(occ_mask) + 1e-6)
+        return torch.mean(loss_diff)
 
 
 class UPFlow_net(tools.abstract_model):
@@ -170,18 +227,87 @@ class UPFlow_net(tools.abstract_model):
 
     def forward(self, input_dict: dict):
         """model/upflow.py:370-392 (inference branch)."""
-        if input_dict['if_loss']:
-            raise NotImplementedError("the unsupervised-loss branch (model/upflow.py:394-491) is outside the decoder "
-                                      "hot path and not part of this build yet")
-        im1, im2 = input_dict['im1'], input_dict['im2']
+        im1_ori, im2_ori = input_dict['im1'], input_dict['im2']
+        if input_dict['if_loss'] and self.conf.input_or_sp_input != 1:
+            im1, im2 = input_dict['im1_sp'], input_dict['im2_sp']
+        else:
+            im1, im2 = im1_ori, im2_ori
         output_dict = {}
-        flow_f, flow_b, flows = self.forward_2_frame_v3(im1, im2, if_loss=False)
+        flow_f, flow_b, flows = self.forward_2_frame_v3(im1, im2, if_loss=input_dict['if_loss'])
         occ_fw, occ_bw = self.occ_check_model(flow_f=flow_f, flow_b=flow_b)
         output_dict['flow_f_out'] = flow_f
         output_dict['flow_b_out'] = flow_b
         output_dict['occ_fw'] = occ_fw
         output_dict['occ_bw'] = occ_bw
+        if input_dict['if_loss']:
+            self._losses(input_dict, output_dict, im1_ori, im2_ori, flow_f, flow_b, flows, occ_fw, occ_bw)
         return output_dict
+
+    def _losses(self, input_dict, output_dict, im1_ori, im2_ori, flow_f, flow_b, flows, occ_fw, occ_bw):
+        """model/upflow.py:394-491: smoothness, photometric and multi-scale distillation terms.  Not provided (rejected,
+        not approximated): the boundary-dilated warp (`if_use_boundary_warp`, utils/tools.py:380-499) and the census
+        term (utils/loss.py:51-91) -- SURVEY.md section 8f rank 2."""
+        conf = self.conf
+        nt = network_tools
+        if conf.smooth_level == 'final':
+            s_flow_f, s_flow_b, s_im1, s_im2 = flow_f, flow_b, im1_ori, im2_ori
+        elif conf.smooth_level == '1/4':
+            s_flow_f, s_flow_b = flows[0]
+            th, tw = s_flow_f.shape[2:]
+            s_im1 = torch.nn.functional.interpolate(im1_ori, (th, tw), mode='area')
+            s_im2 = torch.nn.functional.interpolate(im2_ori, (th, tw), mode='area')
+        else:
+            raise ValueError('wrong smooth level choosed: %s' % conf.smooth_level)
+        smooth_loss = 0
+        for weight, second in ((conf.smooth_order_1_weight, False), (conf.smooth_order_2_weight, True)):
+            if weight > 0:
+                if conf.smooth_type == 'edge':
+                    fn = nt.edge_aware_smoothness_order2 if second else nt.edge_aware_smoothness_order1
+                    smooth_loss = smooth_loss + weight * fn(img=s_im1, pred=s_flow_f) + weight * fn(img=s_im2, pred=s_flow_b)
+                elif conf.smooth_type == 'delta':
+                    smooth_loss = smooth_loss + weight * nt.flow_smooth_delta(s_flow_f, second) \
+                        + weight * nt.flow_smooth_delta(s_flow_b, second)
+                else:
+                    raise ValueError('wrong smooth_type: %s' % conf.smooth_type)
+        output_dict['smooth_loss'] = smooth_loss
+        if conf.if_use_boundary_warp:
+            raise NotImplementedError("if_use_boundary_warp=True (tools.boundary_dilated_warp, utils/tools.py:380-499) is "
+                                      "not part of this build; set if_use_boundary_warp=False")
+        im1_warp = tools.torch_warp(im2_ori, flow_f)
+        im2_warp = tools.torch_warp(im1_ori, flow_b)
+        if conf.stop_occ_gradient:
+            occ_fw, occ_bw = occ_fw.clone().detach(), occ_bw.clone().detach()
+        kw = dict(photo_loss_type=conf.photo_loss_type, photo_loss_delta=conf.photo_loss_delta,
+                  photo_loss_use_occ=conf.photo_loss_use_occ)
+        output_dict['photo_loss'] = nt.photo_loss_multi_type(im1_ori, im1_warp, occ_fw, **kw) \
+            + nt.photo_loss_multi_type(im2_ori, im2_warp, occ_bw, **kw)
+        output_dict['im1_warp'] = im1_warp
+        output_dict['im2_warp'] = im2_warp
+        if conf.photo_loss_census_weight > 0:
+            raise NotImplementedError("the census term (utils/loss.py:51-91) is not part of this build")
+        output_dict['census_loss'] = None
+        if conf.multi_scale_distillation_weight > 0:
+            label_f, label_b = flow_f.clone().detach(), flow_b.clone().detach()
+            terms = []
+            for scale_fw, scale_bw in flows:
+                if conf.multi_scale_distillation_style == 'down':
+                    lf = upsample_flow(label_f, target_flow=scale_fw)
+                    of = torch.nn.functional.interpolate(occ_fw, list(scale_fw.shape[2:]), mode='nearest')
+                    lb = upsample_flow(label_b, target_flow=scale_bw)
+                    ob = torch.nn.functional.interpolate(occ_bw, list(scale_bw.shape[2:]), mode='nearest')
+                elif conf.multi_scale_distillation_style == 'upup':
+                    lf, of, lb, ob = label_f, occ_fw, label_b, occ_bw
+                    scale_fw = upsample_flow(scale_fw, target_flow=lf)
+                    scale_bw = upsample_flow(scale_bw, target_flow=lb)
+                else:
+                    raise ValueError('wrong multi_scale_distillation_style: %s' % conf.multi_scale_distillation_style)
+                terms.append(nt.photo_loss_multi_type(scale_fw, lf, of, 'abs_robust',
+                                                      photo_loss_use_occ=conf.multi_scale_distillation_occ))
+                terms.append(nt.photo_loss_multi_type(scale_bw, lb, ob, 'abs_robust',
+                                                      photo_loss_use_occ=conf.multi_scale_distillation_occ))
+            output_dict['msd_loss'] = conf.multi_scale_distillation_weight * sum(terms)
+        else:
+            output_dict['msd_loss'] = None
 
     def forward_2_frame_v3(self, x1_raw, x2_raw, if_loss=False):
         """model/upflow.py:494-533 on the fused engine; outputs are fresh tensors."""
@@ -207,6 +333,8 @@ class UPFlow_net(tools.abstract_model):
     def _forward_2_frame_modules(self, x1_raw, x2_raw):
         """Training path: model/upflow.py:494-533 module by module, every op an autograd node backed by the
         library's forward AND backward kernels (ops.py)."""
+        from model import pwc_modules
+        pwc_modules.set_conv_precision(self.conv_precision)
         x1_pyramid = self.feature_pyramid_extractor(x1_raw) + [x1_raw]
         x2_pyramid = self.feature_pyramid_extractor(x2_raw) + [x2_raw]
         b_size, _, h0, w0 = x1_pyramid[0].shape
