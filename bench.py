@@ -37,6 +37,7 @@ WORKLOADS = {  # name -> (H, W, batch per GPU)
     "sintel_436x1024_b8": (436, 1024, 8),
     "hd_1080x1920_b2": (1080, 1920, 2),
     "small_256x256_b1": (256, 256, 1),
+    "train_256x832_b4": (256, 832, 4),        # BASELINE config 4: unsupervised training step, 4 pairs per GPU
 }
 METRIC = "image_pairs_per_sec"
 UNIT = "pairs/s"
@@ -146,7 +147,79 @@ def run_reference(args, rank, world):
                              "sample": "%d forwards of one %dx%d batch-%d pair after %d warm-up" % (args.steps, H, W, B, max(1, args.warmup))},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(json.dumps(line))
+
+
+def run_train(args, rank, world, local, dist):
+    """--workload train_256x832_b4 (BASELINE config 4): one step = H2D of the local shard (pinned host), forward with
+    the loss branch (photometric + edge-aware smoothness + multi-scale distillation), backward on this library's
+    kernels, ONE all-reduce of the flat fp32 gradient buffer over NCCL, Adam(amsgrad) update, D2H of the loss."""
+    import upflow_pytorch_b200 as pkg
+    from upflow_pytorch_b200 import _ext
+    from upflow_pytorch_b200.train import Trainer
+    H, W, B = WORKLOADS[args.workload]
+    sd = make_weights()
+    net = pkg.build_model(params={"if_use_boundary_warp": False, "multi_scale_distillation_weight": 0.01},
+                          state_dict=sd, conv_precision=args.precision).train()
+    tr = Trainer(net)
+    im1_h, im2_h = synth_inputs(B, H, W, 1234 + rank)
+    im1_h, im2_h = im1_h.pin_memory(), im2_h.pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step():
+        loss = tr.train_step({"im1": im1_h.cuda(non_blocking=True), "im2": im2_h.cuda(non_blocking=True)})
+        return loss.item()                                   # D2H of the step's result
+
+    W_, K = max(3, args.warmup), args.steps
+    for _ in range(W_):
+        step()
+    sampler = ClockSampler(local)
+    sync_all()
+    sampler.start()
+    n0 = _ext.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = step()
+    e1.record()
+    sync_all()
+    clocks = sampler.stop()
+    launches = _ext.launch_count() - n0
+    ms = e0.elapsed_time(e1) / K
+    # the collective alone
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    a0.record()
+    for _ in range(5):
+        nbytes = tr.grads.all_reduce_mean()
+    a1.record()
+    sync_all()
+    ar_ms = a0.elapsed_time(a1) / 5
+    if dist is not None:
+        t = torch.tensor([ms, ar_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ar_ms = float(t[0].item()), float(t[1].item())
+    if rank == 0:
+        v = world * B / (ms * 1e-3)
+        emit(json.dumps({
+            "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": args.workload, "pairs_per_step_per_gpu": B, "image": [H, W],
+                       "step": "forward + loss (photo abs_robust, edge smooth, msd 0.01) + backward + gradient all-reduce + Adam(amsgrad)",
+                       "weights": "random-init (MSRA, seed 1234)", "l2": "per-step working set (> 1 GB of activations) exceeds the 126 MB L2",
+                       "parallelism": "data parallel x%d, one all-reduce of %d fp32 gradients per step" % (world, tr.grads.numel)},
+            "e2e": {"value": v, "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": 2 * im1_h.numel() * 4,
+                    "d2h_bytes_per_step": 4, "api": "upflow_pytorch_b200.train.Trainer.train_step(batch) with pinned host tensors"},
+            "allreduce": {"bytes": nbytes, "ms": ar_ms, "share_of_step": ar_ms / ms},
+            "gpu_launches": launches, "launches_per_step": launches // K, "clocks": clocks, "final_loss": loss}))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def corr_roofline(pk, iters=20):
@@ -173,12 +246,61 @@ def corr_roofline(pk, iters=20):
     ms = sum(ts) / len(ts)
     nbytes = 4 * N * h * w * (2 * C + 81)
     ach = nbytes / (ms * 1e-3) / 1e9
-    return {"kernel": "corr_fwd_kernel<4>", "shape": [N, C, h, w], "max_disp": d, "bound": "hbm", "achieved": ach,
-            "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None, "us_per_launch": ms * 1e3,
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("corr_pipe_kernel", {}).get("dram_bytes_per_launch_avg")
+    return {"kernel": "corr_pipe_kernel<4>", "shape": [N, C, h, w], "max_disp": d, "bound": "hbm", "achieved": ach,
+            "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": traffic, "us_per_launch": ms * 1e3,
             "best_us": min(ts) * 1e3, "algorithmic_bytes": nbytes, "l2": "flushed before every launch"}
 
 
+class _StdoutGuard:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    communicator creation), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to
+    the saved descriptor."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        self.out = os.fdopen(os.dup(self.saved), "w")
+        self._print = print
+        return self
+
+    def emit(self, text):
+        self.out.write(text + "\n")
+        self.out.flush()
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        self.out.close()
+        return False
+
+
+_GUARD = None
+
+
+def emit(text):
+    if _GUARD is not None:
+        _GUARD.emit(text)
+    else:
+        print(text)
+
+
 def main():
+    global _GUARD
+    with _StdoutGuard() as g:
+        _GUARD = g
+        try:
+            _main()
+        finally:
+            _GUARD = None
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -206,6 +328,11 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.workload.startswith("train"):
+        if args.steps > 20:
+            args.steps = 20
+        run_train(args, rank, world, local, dist)
+        return
     W_ = max(3, args.warmup)
     K = args.steps
     H, W, B = WORKLOADS[args.workload]
@@ -290,24 +417,33 @@ def main():
             eng.forward(im1_d, im2_d)
             with profiler.record() as rec:
                 eng.forward(im1_d, im2_d)
-        agg = rec.by_kernel()
+        agg = rec.by_kernel()           # keyed by the kernel family that ran (upf_last_kernel)
         total_ms = sum(a["ms"] for a in agg.values())
         dom = max(agg, key=lambda k: agg[k]["ms"])
         a = agg[dom]
-        if dom.startswith("conv"):
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")     # dram bytes per launch from committed ncu captures
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(dom + "_kernel", {}).get("dram_bytes_per_launch_avg")
+        if dom in ("conv_win", "conv_halo", "conv_tc"):
             tf32_peak = pk["bf16"] / 2.0
             ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
-            roof = {"kernel": "conv_tc_kernel" if dom == "conv_tc" else "conv_simt_kernel", "bound": "tensor",
-                    "achieved": ach, "peak": tf32_peak if dom == "conv_tc" else 74.4, "unit": "TFLOP/s",
-                    "frac": ach / (tf32_peak if dom == "conv_tc" else 74.4), "traffic": None,
-                    "peak_source": pk["source"] + ": bf16_tflops/2 (dense TF32 rate is half the bf16 rate)"
-                    if dom == "conv_tc" else "fp32 SIMT 148 SM x 128 lanes x 2 x 1.965 GHz",
+            roof = {"kernel": dom + "_kernel", "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": ach / tf32_peak, "traffic": traffic,
+                    "peak_source": pk["source"] + ": bf16_tflops/2 (dense TF32 rate is half the bf16 rate)",
+                    "launches_per_step": a["launches"], "ms_per_step": a["ms"], "share_of_step": a["ms"] / total_ms,
+                    "algorithmic_flops_per_step": a["flops"],
+                    "timing": "CUDA events around every launch of one eager forward (profiler.py), summed over this kernel's launches"}
+        elif dom.startswith("conv"):
+            ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
+            roof = {"kernel": dom + "_kernel", "bound": "tensor", "achieved": ach, "peak": 74.4, "unit": "TFLOP/s",
+                    "frac": ach / 74.4, "traffic": traffic, "peak_source": "fp32 SIMT 148 SM x 128 lanes x 2 x 1.965 GHz",
                     "launches_per_step": a["launches"], "ms_per_step": a["ms"], "share_of_step": a["ms"] / total_ms,
                     "algorithmic_flops_per_step": a["flops"]}
         else:
             ach = a["bytes"] / (a["ms"] * 1e-3) / 1e9
-            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                    "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["source"],
+            roof = {"kernel": dom + "_kernel", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": ach / pk["hbm"], "traffic": traffic, "peak_source": pk["source"],
                     "launches_per_step": a["launches"], "ms_per_step": a["ms"], "share_of_step": a["ms"] / total_ms}
         breakdown = {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
                          "GB/s": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
@@ -347,7 +483,7 @@ def main():
                 "wall_s_timed_region": wall}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -42,6 +42,10 @@ int         upf_abi_version(void);
 const char* upf_last_error(void);
 /* number of kernels this library has launched in the calling process */
 long long   upf_launch_count(void);
+/* name of the kernel family that served the calling thread's most recent launch ("conv_win", "conv_halo",
+ * "conv_tc", "conv_simt", "conv_c3", "corr_pipe", "corr_fwd", "corr_small", ...): entry points such as
+ * upf_conv2d_fwd and upf_corr_lrelu_fwd choose a kernel by shape, and measurements attribute time with this */
+const char* upf_last_kernel(void);
 
 /* a1+a2+a3 (+ apply half of a5): cost volume + LeakyReLU, optionally with the
  * per-image per-channel normalisation fused into the operand load.

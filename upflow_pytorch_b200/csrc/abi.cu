@@ -16,6 +16,9 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static thread_local const char* g_last_kernel = "";
+void note_kernel(const char* name) { g_last_kernel = name; }
+const char* last_kernel() { return g_last_kernel; }
 
 int conv2d_fwd_simt(const float* x, int ldx, const float* w, const float* bias, float* out, int ldo,
                     const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
@@ -28,6 +31,7 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
 
 extern "C" int upf_abi_version(void) { return UPF_ABI_VERSION; }
 extern "C" const char* upf_last_error(void) { return upf::g_err; }
+extern "C" const char* upf_last_kernel(void) { return upf::last_kernel(); }
 extern "C" long long upf_launch_count(void) { return upf::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int upf_conv2d_fwd(const float* x, int ldx, const float* w, const float* bias, float* out, int ldo,

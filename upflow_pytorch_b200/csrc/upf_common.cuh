@@ -12,6 +12,7 @@ namespace upf {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void note_kernel(const char* name);   // upf_last_kernel(): which kernel family served the calling thread's last launch
 
 // every launch goes through here so that a bad configuration is reported to
 // the caller as a return code (the reference printf's and AT_ERRORs instead:
@@ -23,6 +24,7 @@ inline int check_launch(const char* what) {
     return (int)e;
   }
   count_launch();
+  note_kernel(what);
   return 0;
 }
 

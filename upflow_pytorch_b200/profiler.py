@@ -9,7 +9,7 @@ import contextlib
 
 import torch
 
-from . import ops
+from . import _ext, ops
 
 
 def _npix(s):
@@ -60,11 +60,10 @@ class Recorder:
         return self.records
 
     def by_kernel(self):
+        """aggregate by the kernel family that actually ran (upf_last_kernel)"""
         agg = {}
         for r in self.records:
-            name = r["name"]
-            if name == "k_conv":
-                name = "conv_tc" if r.get("tc") else "conv_simt"
+            name = r.get("kernel") or r["name"]
             a = agg.setdefault(name, dict(launches=0, ms=0.0, bytes=0, flops=0))
             a["launches"] += 1
             a["ms"] += r["ms"]
@@ -85,7 +84,8 @@ def record(spin_cycles=20_000_000):
             e0.record()
             fn(*args, **kwargs)
             e1.record()
-            meta.update(name=name, e0=e0, e1=e1)
+            k = _ext.load().upf_last_kernel()
+            meta.update(name=name, e0=e0, e1=e1, kernel=k.decode() if k else name)
             rec.records.append(meta)
         return inner
 
