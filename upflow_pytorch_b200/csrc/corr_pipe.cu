@@ -7,15 +7,16 @@
 // loads, 25 % FMA-pipe utilisation).  Here the roles run concurrently:
 //   * (2d+1) COMPUTE warps run the register-tiled inner product (warp =
 //     horizontal displacement, lane = tile column, TY rows x (2d+1) vertical
-//     displacements per thread) on 8-channel chunks;
-//   * one ISSUER thread keeps a ring of four chunks in flight by TMA: two box
-//     loads per chunk (f2 search window {8 ch, TX+2d, TY+2d}, f1 tile {8 ch, TX, TY}),
-//     SWIZZLE_32B, out-of-bounds zero fill = the zero padding of the correlation.
-//     It runs up to three chunks ahead of the compute warps (first version: two
-//     16-channel stages, refilled only when drained -- ncu: 14 % of the compute
-//     warps' samples waited for the load, HBM latency under load is 2-3 us);
+//     displacements per thread) on 16-channel chunks;
+//   * one ISSUER thread keeps the ring of chunks in flight by TMA: two box loads
+//     per chunk (f2 search window {16 ch, TX+2d, TY+2d}, f1 tile {16 ch, TX, TY}),
+//     SWIZZLE_64B, out-of-bounds zero fill = the zero padding of the correlation,
+//     waiting only for the compute warps' "slot empty" arrivals;
 //   * with fused normalisation two NORMALISER warps apply (x-mean)*(1/std) in
 //     place to the in-image positions of a landed chunk and hand it on.
+// Ring geometry is a compile-time choice (UPF_CP_CC channels per chunk x
+// UPF_CP_STAGES slots, 114 KB either way): 16 x 2 measured 59.4 us on the HD
+// shape, 8 x 4 (32-byte box rows, deeper prefetch) 61.4 us.
 // Handshakes are mbarriers: full[s] (TMA bytes), ready[s] (normalised), empty[s]
 // (one arrival per compute warp).  The finished tile goes through a transpose
 // buffer (pitch = (2d+1)^2 floats, odd: conflict-free).  A contiguous output
@@ -24,17 +25,30 @@
 // channel slice of a wider buffer is written by the compute warps of schedulers
 // 1..3, a warp per pixel.  (first version: ONE storer warp copying 83 KB per tile
 // was busy 93 % of the time and the compute warps spent 14 % of theirs waiting
-// for it.  Also tried and measured slower, 67.6 vs 61.4 us: raw sums parked
-// column-minor and six finisher warps converting and storing them.)
-// Shared-memory rows are 32 bytes (8 channels); the 16-byte chunk index is
-// XOR-swizzled with (position >> 2) & 1 (= TMA's SWIZZLE_32B) so that 8
+// for it.  Also tried and measured slower: raw sums parked column-minor and six
+// finisher warps converting and storing them, 67.6 vs 61.4 us; the operands staged
+// by three service warps with 16-byte cp.async instead of TMA, 79.9 us -- the
+// copies share the LSU path with the compute warps' shared-memory loads.)
+// Where the 61 us go (debug builds, HD shape, d=4): without the 9th compute warp
+// (two warps per scheduler instead of 3/2/2/2) 51 us; without the store epilogue
+// 51 us; without both 41 us, and that remainder does not move when half of the
+// shared-memory loads or half of the FMAs are removed: it is the TMA unit
+// delivering 3584 32-byte box rows per tile (~3 cycles per row).
+// Shared-memory rows are 64 (32) bytes; the 16-byte chunk index is XOR-swizzled
+// with (position >> 1) & 3 (TMA's SWIZZLE_64B; (position >> 2) & 1 = SWIZZLE_32B) so that 8
 // consecutive lanes reading the same chunk of 8 consecutive positions hit 8
 // distinct 16-byte bank groups.
 #include "tc_common.cuh"
 
 namespace upf {
 
-constexpr int CP_TX = 32, CP_CC = 8, CP_STAGES = 4;   // tile width, channels per chunk, ring depth
+#ifndef UPF_CP_CC
+#define UPF_CP_CC 16
+#define UPF_CP_STAGES 2
+#endif
+constexpr int CP_TX = 32, CP_CC = UPF_CP_CC, CP_STAGES = UPF_CP_STAGES;   // tile width, channels per chunk, ring depth
+// XOR term of the 16-byte chunk index for position pos (= TMA SWIZZLE_32B for 8-channel rows, SWIZZLE_64B for 16)
+__device__ __forceinline__ int cp_sw(int pos) { return CP_CC == 8 ? ((pos >> 2) & 1) : ((pos >> 1) & 3); }
 
 template <int D>
 struct CPCfg {
@@ -119,9 +133,9 @@ corr_pipe_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant
     if (norm) {
       // ============================== NORMALISER WARPS ==============================
       const int lt = si * 32 + lane;
-      constexpr int NLT = K::NNORM * 32, PS = K::NNORM * 16;  // threads, position slots per pass
+      constexpr int NLT = K::NNORM * 32, PS = NLT / (CP_CC / 4);  // threads, position slots per pass
       const double npix = (double)H * (double)W;
-      const int ch = lt & 1, q0 = lt >> 1;                // a lane keeps one 16-byte channel quad
+      const int ch = lt & (CP_CC / 4 - 1), q0 = lt / (CP_CC / 4);   // a lane keeps one 16-byte channel quad
       int stat_n = -1;
       long long it = 0;
       for (int tloc = 0; tloc < my_tiles; ++tloc) {
@@ -162,7 +176,7 @@ corr_pipe_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant
                 const int r = pos / K::HCOLS, cc = pos - r * K::HCOLS;
                 const int y = y0 - D + r, x = x0 - D + cc;
                 qp[i] = (pos < K::HPOS && y >= 0 && y < H && x >= 0 && x < W)
-                            ? reinterpret_cast<float4*>(st2 + pos * CP_CC + (((ch ^ (pos >> 2)) & 1) << 2)) : nullptr;
+                            ? reinterpret_cast<float4*>(st2 + pos * CP_CC + (((ch ^ cp_sw(pos)) & (CP_CC / 4 - 1)) << 2)) : nullptr;
                 if (qp[i]) v[i] = *qp[i];
               }
 #pragma unroll
@@ -181,7 +195,7 @@ corr_pipe_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant
               for (int i = 0; i < U; ++i) {
                 const int pos = p0 + PS * i;                // CP_TX == 32: row = pos >> 5, column = pos & 31
                 qp[i] = (pos < K::F1POS && y0 + (pos >> 5) < H && x0 + (pos & 31) < W)
-                            ? reinterpret_cast<float4*>(st1 + pos * CP_CC + (((ch ^ (pos >> 2)) & 1) << 2)) : nullptr;
+                            ? reinterpret_cast<float4*>(st1 + pos * CP_CC + (((ch ^ cp_sw(pos)) & (CP_CC / 4 - 1)) << 2)) : nullptr;
                 if (qp[i]) v[i] = *qp[i];
               }
 #pragma unroll
@@ -204,7 +218,7 @@ corr_pipe_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant
     const int col2 = lane + dxi;
     constexpr int NCT = K::NCW * 32;                    // compute threads
     const int ct = threadIdx.x;                         // compute warps are warps 0 .. NCW-1
-    const int swa = (lane >> 2) & 1, swb = (col2 >> 2) & 1;
+    const int swa = cp_sw(lane), swb = cp_sw(col2);
     float acc[TY][K::WIN];
     long long it = 0;
     for (int tloc = 0; tloc < my_tiles; ++tloc) {
@@ -333,13 +347,13 @@ static int launch_corr_pipe_t(const float* f1, int ld1, const float* f2, int ld2
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const cuuint64_t str1[3] = {(cuuint64_t)ld1 * 4, (cuuint64_t)W * ld1 * 4, (cuuint64_t)H * W * ld1 * 4};
     const cuuint32_t box1[4] = {CP_CC, CP_TX, (cuuint32_t)K::TY, 1};
-    MapKey k1{f1, ld1, ((long long)H << 32) | (unsigned)W, ((long long)N << 32) | (unsigned)C, 7000 + D, 32};
-    int e = encode_cached(k1, &m1, 4, const_cast<float*>(f1), dims, str1, box1, estr, 32);
+    MapKey k1{f1, ld1, ((long long)H << 32) | (unsigned)W, ((long long)N << 32) | (unsigned)C, 7000 + D, CP_CC * 4};
+    int e = encode_cached(k1, &m1, 4, const_cast<float*>(f1), dims, str1, box1, estr, CP_CC * 4);
     if (e) return e;
     const cuuint64_t str2[3] = {(cuuint64_t)ld2 * 4, (cuuint64_t)W * ld2 * 4, (cuuint64_t)H * W * ld2 * 4};
     const cuuint32_t box2[4] = {CP_CC, (cuuint32_t)K::HCOLS, (cuuint32_t)K::HROWS, 1};
-    MapKey k2{f2, ld2, ((long long)H << 32) | (unsigned)W, ((long long)N << 32) | (unsigned)C, 8000 + D, 32};
-    e = encode_cached(k2, &m2, 4, const_cast<float*>(f2), dims, str2, box2, estr, 32);
+    MapKey k2{f2, ld2, ((long long)H << 32) | (unsigned)W, ((long long)N << 32) | (unsigned)C, 8000 + D, CP_CC * 4};
+    e = encode_cached(k2, &m2, 4, const_cast<float*>(f2), dims, str2, box2, estr, CP_CC * 4);
     if (e) return e;
   }
   // contiguous output whose tile rows are 16-byte aligned runs: shared -> global bulk copies instead of ld/st

@@ -81,6 +81,7 @@ class DecoderEngine:
         # 1.0 = the reference's `mask >= 1.0` (model/pwc_modules.py:206); 0.9999 = diagnostic robust mask
         self.mask = True if mask_threshold == 1.0 else float(mask_threshold)
         self._ws = {}
+        self.overlap = True        # image-only work on a side stream (forward())
         self.load_weights(state_dict)
 
     # ------------------------------------------------------------ weights
@@ -122,6 +123,11 @@ class DecoderEngine:
             self.outconv = [spec(f"sgi_model.upsample_output_conv.{i}", stride=s) for i, s in enumerate((1, 2, 1, 2))]
 
     # ------------------------------------------------------------ helpers
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def _conv(self, cs, x, out, residual=None):
         use_tc = self.tc and cs.w_tc is not None
         ops.k_conv(x, cs.w_tc if use_tc else cs.w, cs.bias, out, cs.k, cs.stride, cs.dil, cs.slope, residual,
@@ -204,6 +210,30 @@ class DecoderEngine:
         N = 2 * B
         ac = self.align_corners
         feats = self.encode(ws, im1, im2)              # index l -> 1/2^(l+1); decoder level L uses feats[5-L]
+        # Work that depends on the images only -- the 1x1 adapters and feature statistics of levels 1..4 and
+        # sgi_model.output_conv (two full-resolution convolutions) -- runs on a SIDE STREAM while the main stream
+        # walks the coarse levels, which are a latency-bound chain of small launches that leaves most SMs idle.
+        # Inside a captured graph the fork / join events become parallel branches.
+        main = torch.cuda.current_stream()
+        side = self._side_stream() if self.overlap else main     # overlap=False: one stream (per-kernel profiling)
+        ev_adapters, ev_outconv = torch.cuda.Event(), torch.cuda.Event()
+        if side is not main:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for L in range(1, 5):
+                d = ws["levels"][L]
+                F = Slice(feats[5 - L])
+                self._conv(self.conv1x1[L], F, Slice(d["X"], X_F1X1, 32))
+                d["stats_own"].zero_()
+                ops.k_stats(F, d["stats_own"])
+            ev_adapters.record(side)
+            if self.use_sgu:
+                # sgi_model.output_conv on both images (model/upflow.py:66-69, :527-528)
+                self._conv(self.outconv[0], Slice(ws["im"], 0, 3), Slice(ws["oc_a"]))
+                self._conv(self.outconv[1], Slice(ws["oc_a"]), Slice(ws["oc_b"]))
+                self._conv(self.outconv[2], Slice(ws["oc_b"]), Slice(ws["oc_c"]))
+                self._conv(self.outconv[3], Slice(ws["oc_c"]), Slice(ws["S_out"], 0, 32))
+            ev_outconv.record(side)
         prev_flow = None
         flows = []
         for L in range(5):
@@ -213,8 +243,13 @@ class DecoderEngine:
             C = NUM_CHS[L]
             X = d["X"]
             flow_up = Slice(X, X_FLOW, 2)
-            # 1x1 adapter (model/upflow.py:508-513) straight into its estimator slot
-            self._conv(self.conv1x1[L], F, Slice(X, X_F1X1, 32))
+            if L == 0:
+                # 1x1 adapter (model/upflow.py:508-513) straight into its estimator slot
+                self._conv(self.conv1x1[L], F, Slice(X, X_F1X1, 32))
+                d["stats_own"].zero_()
+                ops.k_stats(F, d["stats_own"])
+            elif L == 1:
+                main.wait_event(ev_adapters)
             if L == 0:
                 X[..., X_FLOW:X_FLOW + 2].zero_()      # upsampling a zero flow (model/upflow.py:504-505, :536)
             else:
@@ -229,9 +264,8 @@ class DecoderEngine:
                     ops.k_sgu_blend(bil, Slice(d["inter"], 0, 3), flow_up, ac)
                 else:
                     ops.k_resize(prev_flow, flow_up, (w / pw, h / ph))
-            # feature statistics (model/upflow.py:549-555), warp + its statistics (:546-547)
-            d["stats_own"].zero_()
-            ops.k_stats(F, d["stats_own"])
+            # feature statistics (model/upflow.py:549-555: computed above / on the side stream), warp + its
+            # statistics (:546-547)
             if L == 0:
                 ops.k_corr(F, F, Slice(X, X_CORR, 81), 4, d["stats_own"], d["stats_own"], f2_shift=B, slope=SLOPE)
             else:
@@ -264,18 +298,15 @@ class DecoderEngine:
         if self.use_sgu:
             bil = Slice(ws["flow_full_bil"])
             ops.k_resize(prev_flow, bil, (W / w4, H / h4))
-            # sgi_model.output_conv on both images (model/upflow.py:66-69, :527-528)
-            self._conv(self.outconv[0], Slice(ws["im"], 0, 3), Slice(ws["oc_a"]))
-            self._conv(self.outconv[1], Slice(ws["oc_a"]), Slice(ws["oc_b"]))
-            self._conv(self.outconv[2], Slice(ws["oc_b"]), Slice(ws["oc_c"]))
             S = ws["S_out"]
-            self._conv(self.outconv[3], Slice(ws["oc_c"]), Slice(S, 0, 32))
+            main.wait_event(ev_outconv)                # output_conv features (side stream)
             # the flow handed to sgu_model here is the 1/4-res flow itself (already at feature size, :73-75)
             ops.k_warp(Slice(S, 0, 32), prev_flow, Slice(S, 32, 32), ac, self.mask, x_shift=B)
             self._sgu_dense(S, ws["inter_out"])
             ops.k_sgu_blend(bil, Slice(ws["inter_out"], 0, 3), out, ac)
         else:
             ops.k_resize(prev_flow, out, (W / w4, H / h4))
+            main.wait_event(ev_outconv)
         fo = ws["flow_out"].permute(0, 3, 1, 2)
         lvl = [[f[:B].permute(0, 3, 1, 2), f[B:].permute(0, 3, 1, 2)] for f in flows]
         return fo[:B], fo[B:], lvl[::-1]
