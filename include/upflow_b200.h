@@ -143,6 +143,15 @@ int upf_conv2d_fwd(const float* x, int ldx, const float* w, const float* bias,
                    int N, int H, int W, int Cin, int Cout, int ksize, int stride, int dilation,
                    float slope, int precision, void* stream);
 
+/* Second half of a 3x3 convolution with very few output channels run as "expand, then combine the taps" (same
+ * reference routine as upf_conv2d_fwd: conv(), model/pwc_modules.py:10-31).  The first half is upf_conv2d_fwd with
+ * ksize 1 and 9*Cout output channels, Y[p][tap*Cout+co] = sum_ci X[p][ci]*W[co][ci][tap]; this gathers
+ *   out[n,y,x,co] = lrelu( bias[co] + sum_tap Y[n, y+(ky-1)*dil, x+(kx-1)*dil, tap*Cout+co] ) (+ residual),
+ * taps falling outside the image contributing nothing.  On the tensor cores a 3x3 conv with Cout <= 8 otherwise
+ * issues nine N=16 MMAs per K step for one N<=80 MMA's worth of products. */
+int upf_conv3x3_tap_combine(const float* y, int ldy, const float* bias, float* out, int ldo, const float* residual,
+                            int ldr, int N, int H, int W, int Cout, int dilation, float slope, void* stream);
+
 /* TF32 tensor-core path: weights packed as [tap][cout_pad16][cin_pad32] fp32
  * (K-major rows of 32 input channels), done on the device from the SIMT layout. */
 long long upf_conv_tc_packed_elems(int Cin, int Cout, int ksize);

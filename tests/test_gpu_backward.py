@@ -141,7 +141,6 @@ def test_training_path_gradients_vs_port():
     from upflow_pytorch_b200 import ops
     upflow_pytorch_b200.install_dropin()
     from model.upflow import UPFlow_net
-    from model import pwc_modules
     conf = UPFlow_net.config()
     conf.update({"if_norm_before_cost_volume": True, "norm_moments_across_channels": False,
                  "norm_moments_across_images": False, "if_sgu_upsample": True})
@@ -149,7 +148,7 @@ def test_training_path_gradients_vs_port():
     sd = P.det_state_dict(5)
     net.load_state_dict(sd)
     net = net.cuda().train()
-    pwc_modules.set_conv_precision("fp32")
+    net.conv_precision = "fp32"
     im1, im2 = O.synthetic_pair(64, 96, seed=77)
 
     def loss_of(f, b):

@@ -400,3 +400,25 @@ def test_conv_tf32_large_grid_kernels_agree(upf, case):
     finally:
         lib.upf_debug_conv_win(1, 0, 0)
         lib.upf_debug_conv_halo(1, (65 << 16) | (128 << 8))
+
+
+@pytest.mark.parametrize("case", [(576, 2, 1, 47, 60), (184, 3, 1, 33, 41), (176, 8, 1, 20, 50), (32, 2, 1, 64, 30), (64, 5, 4, 40, 44)])
+def test_conv3x3_expand_then_tap_combine(upf, case):
+    """3x3 conv with <= 8 outputs as a 1x1 tensor-core conv with 9*Cout outputs + upf_conv3x3_tap_combine (bias,
+    LeakyReLU, residual, dilation, zero padding) against the direct oracle on TF32-truncated operands."""
+    from upflow_pytorch_b200 import _ext
+    from upflow_pytorch_b200.ops import Slice
+    Cin, Cout, dil, H, W = case
+    x, w, b = _regen(70, (2, Cin, H, W)), _regen(71, (Cout, Cin, 3, 3)) * 0.05, _regen(72, (Cout,)) * 0.1
+    res = _regen(73, (2, Cout, H, W))
+    trunc = lambda t: (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    ref = O.conv2d_direct(trunc(x).double(), trunc(w).double(), b.double(), dilation=dil, leaky_slope=0.1).float() + res
+    a = upf.to_pixel_major(_cuda(x))
+    wexp = upf.pack_conv_weight(upf.expand_taps_weight(_cuda(w)), tc=True)[1]
+    Y = torch.zeros(2, H, W, 9 * 8, device="cuda")
+    ys = Slice(Y, 0, 9 * Cout)
+    upf.k_conv(a, wexp, torch.zeros(9 * Cout, device="cuda"), ys, 1, 1, 1, 1.0, None, _ext.CONV_TF32)
+    out = torch.full((2, H, W, Cout), float("nan"), device="cuda")
+    upf.k_tap_combine(ys, _cuda(b), out, dil, 0.1, upf.to_pixel_major(_cuda(res)))
+    err = (out.permute(0, 3, 1, 2).cpu() - ref).abs().max().item()
+    assert err <= 5e-4, err

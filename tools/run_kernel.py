@@ -21,7 +21,8 @@ if what == "corr":
 elif what == "conv":
     # estimator conv2 at KITTI 1/4 res: X[0:256] -> 128 channels, both directions stacked
     N, h, w = 2, 94, 311
-    cin, cout, dil = int(sys.argv[2]) if len(sys.argv) > 2 else 256, int(sys.argv[3]) if len(sys.argv) > 3 else 128, 1
+    cin, cout = int(sys.argv[2]) if len(sys.argv) > 2 else 256, int(sys.argv[3]) if len(sys.argv) > 3 else 128
+    dil = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     X = torch.randn(N, h, w, 576, generator=g).cuda()
     wt = torch.randn(cout, cin, 3, 3, generator=g).cuda() * 0.02
     b = torch.zeros(cout).cuda()

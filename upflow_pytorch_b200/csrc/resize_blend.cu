@@ -166,6 +166,44 @@ static unsigned grid_for(long long total, int per_block = 256) {
   return (unsigned)b;
 }
 
+
+// ---- 3x3 convolution with a handful of output channels as "expand, then combine the taps" ----------------------
+// A 3x3 conv with Cout <= 8 wastes the tensor pipe: every tap issues its own MMAs with N padded to 16, nine times
+// the instruction count of the products it needs.  Instead the tensor-core kernel runs it as a 1x1 convolution with
+// 9*Cout output channels, Y[p][tap*Cout+co] = sum_ci X[p][ci] * W[co][ci][tap]  (one pass over X, no halo), and this
+// kernel gathers the nine shifted partial results:
+//   out[n,y,x,co] = act( bias[co] + sum_tap Y[n, y+(ky-1)*dil, x+(kx-1)*dil, tap*Cout+co] ) (+ residual)
+// with taps whose source pixel lies outside the image contributing nothing (= the conv's zero padding).
+__global__ void __launch_bounds__(256)
+tap_combine_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ bias, float* __restrict__ out, int ldo,
+                   const float* __restrict__ res, int ldr, int N, int H, int W, int Cout, int dil, float slope) {
+  pdl_prologue();
+  const long long total = (long long)N * H * W * Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const long long pix = i / Cout;
+    const int x = (int)(pix % W);
+    const long long t = pix / W;
+    const int yy = (int)(t % H);
+    const long long n = t / H;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int sy = yy + (ky - 1) * dil;
+      if (sy < 0 || sy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int sx = x + (kx - 1) * dil;
+        if (sx < 0 || sx >= W) continue;
+        acc += __ldg(y + ((size_t)((size_t)n * H + sy) * W + sx) * ldy + (ky * 3 + kx) * Cout + co);
+      }
+    }
+    float v = lrelu(acc + __ldg(bias + co), slope);
+    if (res) v += __ldg(res + (size_t)pix * ldr + co);
+    out[(size_t)pix * ldo + co] = v;
+  }
+}
+
 }  // namespace upf
 
 extern "C" int upf_resize_bilinear(const float* in, int ldi, int h, int w, float* out, int ldo, int H, int W,
@@ -223,4 +261,15 @@ extern "C" int upf_copy_channels(const float* in, int ldi, float* out, int ldo, 
   const int vec = (C % 4 == 0) && (ldi % 4 == 0) && (ldo % 4 == 0) && aligned16(in) && aligned16(out);
   UPF_LAUNCH((copy_channels_kernel), grid_for(npix * (vec ? C / 4 : C)), 256, 0, (cudaStream_t)stream, in, ldi, out, ldo, npix, C, vec);
   return check_launch("copy_channels");
+}
+
+extern "C" int upf_conv3x3_tap_combine(const float* y, int ldy, const float* bias, float* out, int ldo, const float* residual,
+                                       int ldr, int N, int H, int W, int Cout, int dilation, float slope, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(y && bias && out, "tap_combine: null tensor");
+  UPF_REQUIRE(N > 0 && H > 0 && W > 0 && Cout > 0 && dilation >= 1 && ldy >= 9 * Cout && ldo >= Cout && (!residual || ldr >= Cout),
+              "tap_combine: bad shape");
+  UPF_LAUNCH((tap_combine_kernel), grid_for((long long)N * H * W * Cout), 256, 0, (cudaStream_t)stream, y, ldy, bias, out, ldo,
+             residual, ldr, N, H, W, Cout, dilation, slope);
+  return check_launch("tap_combine");
 }

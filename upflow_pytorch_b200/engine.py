@@ -53,8 +53,12 @@ def _dense_slots(x_width, x_slots, out_offsets, out_channels, k):
     return slots
 
 
+EXPAND_MAX_COUT = 8          # 3x3 convs with at most this many outputs run as 1x1-expand + tap-combine ...
+EXPAND_MIN_PIXELS = 5000     # ... on images with at least this many pixels (below, the extra launch costs more)
+
+
 class ConvSpec:
-    __slots__ = ("w", "w_tc", "bias", "cin", "cout", "k", "stride", "dil", "slope")
+    __slots__ = ("w", "w_tc", "bias", "cin", "cout", "k", "stride", "dil", "slope", "w_exp", "zero_bias")
 
     def __init__(self, weight, bias, stride=1, dil=1, relu=True, in_slots=None, cin_total=None, tc=True):
         self.cout, _, self.k, _ = weight.shape
@@ -64,6 +68,12 @@ class ConvSpec:
         # tensor cores for everything but the 3-channel image convs (K = 27: one quarter-empty K block per tap)
         self.w, self.w_tc = ops.pack_conv_weight(weight, in_slots, cin_total, tc=tc and stride in (1, 2) and self.cin >= 16)
         self.bias = bias.detach().float().contiguous()
+        # few output channels: Y = 1x1 conv with 9*Cout outputs (one N<=80 MMA per K step instead of nine N=16 ones),
+        # then upf_conv3x3_tap_combine gathers the nine shifted slices
+        self.w_exp = None
+        if self.w_tc is not None and self.k == 3 and stride == 1 and self.cout <= EXPAND_MAX_COUT:
+            self.w_exp = ops.pack_conv_weight(ops.expand_taps_weight(weight), in_slots, cin_total, tc=True)[1]
+            self.zero_bias = torch.zeros(9 * self.cout, dtype=torch.float32, device=weight.device)
 
 
 class DecoderEngine:
@@ -123,6 +133,15 @@ class DecoderEngine:
             self.outconv = [spec(f"sgi_model.upsample_output_conv.{i}", stride=s) for i, s in enumerate((1, 2, 1, 2))]
 
     # ------------------------------------------------------------ helpers
+    def _scratch(self, N, H, W, C):
+        side = getattr(self, "_side", None)
+        on_side = side is not None and torch.cuda.current_stream() == side
+        key = ("scratch", N, H, W, C, on_side)            # one per stream: the side stream overlaps the main one
+        buf = self._ws.get(key)
+        if buf is None:
+            buf = self._ws[key] = torch.zeros(N, H, W, C, dtype=torch.float32, device=self.device)
+        return buf
+
     def _side_stream(self):
         if getattr(self, "_side", None) is None:
             self._side = torch.cuda.Stream(device=self.device)
@@ -130,6 +149,12 @@ class DecoderEngine:
 
     def _conv(self, cs, x, out, residual=None):
         use_tc = self.tc and cs.w_tc is not None
+        if use_tc and cs.w_exp is not None and x.H * x.W >= EXPAND_MIN_PIXELS:
+            Y = self._scratch(x.N, x.H, x.W, 9 * EXPAND_MAX_COUT)
+            ys = Slice(Y, 0, 9 * cs.cout)
+            ops.k_conv(x, cs.w_exp, cs.zero_bias, ys, 1, 1, 1, 1.0, None, _ext.CONV_TF32)
+            ops.k_tap_combine(ys, cs.bias, out, cs.dil, cs.slope, residual)
+            return
         ops.k_conv(x, cs.w_tc if use_tc else cs.w, cs.bias, out, cs.k, cs.stride, cs.dil, cs.slope, residual,
                    _ext.CONV_TF32 if use_tc else _ext.CONV_FP32)
 

@@ -208,6 +208,23 @@ def k_resize_bwd(grad_out, grad_in, scale=None):
                "resize_bilinear_bwd")
 
 
+def k_tap_combine(y, bias, out, dilation=1, slope=LRELU_SLOPE, residual=None):
+    """out = lrelu(bias + sum of the nine shifted tap slices of y) (+ residual); y holds 9*Cout channels."""
+    y, out = _as_slice(y), _as_slice(out)
+    res = _as_slice(residual) if residual is not None else None
+    assert y.C == 9 * out.C
+    _ext.check(_lib().upf_conv3x3_tap_combine(y.ptr(), y.ld, _p(bias), out.ptr(), out.ld, res.ptr() if res else None,
+                                              res.ld if res else 0, out.N, out.H, out.W, out.C, dilation, float(slope),
+                                              _stream()), "conv3x3_tap_combine")
+
+
+def expand_taps_weight(weight):
+    """[Cout,Cin,3,3] -> [9*Cout,Cin,1,1] with row tap*Cout+co = weight[co,:,ky,kx], tap = ky*3+kx."""
+    Cout, Cin, k, _ = weight.shape
+    assert k == 3
+    return weight.detach().permute(2, 3, 0, 1).reshape(9 * Cout, Cin, 1, 1).contiguous()
+
+
 def k_copy(src, dst):
     src, dst = _as_slice(src), _as_slice(dst)
     assert src.C == dst.C
