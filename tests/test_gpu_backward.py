@@ -188,7 +188,7 @@ def _dropin_net(conf_dict, wseed, precision):
     conf = UPFlow_net.config()
     conf.update(conf_dict)
     net = conf()
-    net.load_state_dict(P.det_state_dict(wseed))
+    net.load_state_dict(P.det_state_dict(wseed), strict=bool(conf_dict.get("if_sgu_upsample")))   # no SGU: its 20 tensors are absent
     net.conv_precision = precision
     return net.cuda().train()
 
@@ -235,3 +235,27 @@ def test_trainer_steps_reduce_the_loss(precision):
     assert all(v == v for v in losses)
     assert losses[-1] < losses[0]
     assert tr.grads.numel == 3494549
+
+
+def test_training_step_default_loss_config_vs_reference_golden(golden):
+    """scripts/simple_train.py's default loss configuration -- boundary-dilated warp on the un-cropped frames plus the
+    census term -- against the reference's own step (tests/golden/train_step_boundary_census.pt)."""
+    g = golden("train_step_boundary_census")
+    net = _dropin_net(g["conf"], g["wseed"], "fp32")
+    hw, start = g["hw"], g["start"]
+    raw1, raw2 = O.synthetic_pair(hw[0] + 16, hw[1] + 16, seed=g["pair_seed"], batch=g["batch"])
+    crop = lambda t: torch.stack([t[b, :, int(start[b, 1]):int(start[b, 1]) + hw[0], int(start[b, 0]):int(start[b, 0]) + hw[1]]
+                                  for b in range(g["batch"])])
+    out = net({"im1": crop(raw1).cuda(), "im2": crop(raw2).cuda(), "im1_raw": raw1.cuda(), "im2_raw": raw2.cuda(),
+               "start": start.cuda(), "if_loss": True})
+    for k in ("photo_loss", "smooth_loss", "census_loss", "msd_loss"):
+        _check(k, abs(out[k].item() - g[k]) / abs(g[k]), 2e-2)
+    from upflow_pytorch_b200.train import total_loss
+    loss = total_loss(out)
+    _check("loss", abs(loss.item() - g["loss"]) / g["loss"], 2e-2)
+    loss.backward()
+    worst = 0.0
+    for name, p in net.named_parameters():
+        if name in g["grad_norm"]:
+            worst = max(worst, abs(p.grad.norm().item() - g["grad_norm"][name]) / max(g["grad_norm"][name], 1e-12))
+    _check("worst gradient-norm deviation", worst, 0.15)

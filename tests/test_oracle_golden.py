@@ -136,3 +136,19 @@ def test_end_to_end_restatement_within_noise_floor(golden):
     f, b, flows = O.forward_2_frame(im1, im2, sd)
     assert O.epe(flows[-1][0], g["flows"][-1][0]) < 1e-5      # coarsest level: no warp yet
     assert O.epe(f, g["flow_f_out"]) < 0.1
+
+
+def test_loss_side_ops_match_the_reference(golden):
+    """tools.boundary_dilated_warp.warp_im and loss_functions.census_loss_torch of the drop-in (plain torch, run on CPU
+    here) against the reference's own outputs (tests/golden/loss_ops.pt, oracle/make_golden_train.py)."""
+    import upflow_pytorch_b200
+    upflow_pytorch_b200.install_dropin()
+    from utils.tools import tools
+    from utils.loss import loss_functions
+    g = golden("loss_ops")
+    out = tools.boundary_dilated_warp.warp_im(g["I"], g["flow"], g["start"])
+    assert out.shape == g["warp"].shape
+    assert (out - g["warp"]).abs().max().item() <= 1e-6
+    for key, charb, occ in (("census_occ", False, True), ("census_noocc", False, False), ("census_charb", True, True)):
+        v = loss_functions.census_loss_torch(g["a"], g["b"], g["mask"], 0.4, charb, occ, True).item()
+        assert abs(v - g[key]) <= 1e-5 * abs(g[key]), (key, v, g[key])

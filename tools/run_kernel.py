@@ -20,7 +20,7 @@ if what == "corr":
         ops.k_corr(f1, f2, out, d, slope=0.1)
 elif what == "conv":
     # estimator conv2 at KITTI 1/4 res: X[0:256] -> 128 channels, both directions stacked
-    N, h, w = 2, 94, 311
+    N, h, w = 2, int(sys.argv[5]) if len(sys.argv) > 5 else 94, int(sys.argv[6]) if len(sys.argv) > 6 else 311
     cin, cout = int(sys.argv[2]) if len(sys.argv) > 2 else 256, int(sys.argv[3]) if len(sys.argv) > 3 else 128
     dil = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     X = torch.randn(N, h, w, 576, generator=g).cuda()

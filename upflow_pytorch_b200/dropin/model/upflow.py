@@ -10,8 +10,8 @@ fused kernels, no torch.cat.  With autograd enabled (training,
 scripts/simple_train.py:140-146) the same forward runs module by module, every
 op an autograd node whose forward AND backward are this library's kernels
 (ops.py).  The loss branch (model/upflow.py:394-491) is elementwise torch around
-the library warp: smoothness, photometric and multi-scale-distillation terms;
-the boundary-dilated warp and the census term are rejected, not approximated.
+the library warp: smoothness, photometric (plain or boundary-dilated warp), census
+and multi-scale-distillation terms.
 """
 from __future__ import absolute_import, division, print_function
 
@@ -25,6 +25,7 @@ from model.pwc_modules import (ContextNetwork_v2_, FeatureExtractor, FlowEstimat
                                _DenseBlock, conv, initialize_msra, upsample2d_flow_as, upsample_flow)
 from upflow_pytorch_b200 import ops
 from upflow_pytorch_b200.engine import DecoderEngine
+from utils.loss import loss_functions
 from utils.pytorch_correlation import Corr_pyTorch
 from utils.tools import tools
 
@@ -244,9 +245,8 @@ class UPFlow_net(tools.abstract_model):
         return output_dict
 
     def _losses(self, input_dict, output_dict, im1_ori, im2_ori, flow_f, flow_b, flows, occ_fw, occ_bw):
-        """model/upflow.py:394-491: smoothness, photometric and multi-scale distillation terms.  Not provided (rejected,
-        not approximated): the boundary-dilated warp (`if_use_boundary_warp`, utils/tools.py:380-499) and the census
-        term (utils/loss.py:51-91) -- SURVEY.md section 8f rank 2."""
+        """model/upflow.py:394-491: smoothness, photometric (plain or boundary-dilated warp), census and multi-scale
+        distillation terms -- elementwise torch around the library warp."""
         conf = self.conf
         nt = network_tools
         if conf.smooth_level == 'final':
@@ -271,10 +271,12 @@ class UPFlow_net(tools.abstract_model):
                     raise ValueError('wrong smooth_type: %s' % conf.smooth_type)
         output_dict['smooth_loss'] = smooth_loss
         if conf.if_use_boundary_warp:
-            raise NotImplementedError("if_use_boundary_warp=True (tools.boundary_dilated_warp, utils/tools.py:380-499) is "
-                                      "not part of this build; set if_use_boundary_warp=False")
-        im1_warp = tools.torch_warp(im2_ori, flow_f)
-        im2_warp = tools.torch_warp(im1_ori, flow_b)
+            im1_s, im2_s, start_s = input_dict['im1_raw'], input_dict['im2_raw'], input_dict['start']
+            im1_warp = tools.boundary_dilated_warp.warp_im(im2_s, flow_f, start_s)
+            im2_warp = tools.boundary_dilated_warp.warp_im(im1_s, flow_b, start_s)
+        else:
+            im1_warp = tools.torch_warp(im2_ori, flow_f)
+            im2_warp = tools.torch_warp(im1_ori, flow_b)
         if conf.stop_occ_gradient:
             occ_fw, occ_bw = occ_fw.clone().detach(), occ_bw.clone().detach()
         kw = dict(photo_loss_type=conf.photo_loss_type, photo_loss_delta=conf.photo_loss_delta,
@@ -284,8 +286,12 @@ class UPFlow_net(tools.abstract_model):
         output_dict['im1_warp'] = im1_warp
         output_dict['im2_warp'] = im2_warp
         if conf.photo_loss_census_weight > 0:
-            raise NotImplementedError("the census term (utils/loss.py:51-91) is not part of this build")
-        output_dict['census_loss'] = None
+            ckw = dict(q=conf.photo_loss_delta, charbonnier_or_abs_robust=False, if_use_occ=conf.photo_loss_use_occ, averge=True)
+            output_dict['census_loss'] = conf.photo_loss_census_weight * (
+                loss_functions.census_loss_torch(img1=im1_ori, img1_warp=im1_warp, mask=occ_fw, **ckw)
+                + loss_functions.census_loss_torch(img1=im2_ori, img1_warp=im2_warp, mask=occ_bw, **ckw))
+        else:
+            output_dict['census_loss'] = None
         if conf.multi_scale_distillation_weight > 0:
             label_f, label_b = flow_f.clone().detach(), flow_b.clone().detach()
             terms = []

@@ -1,7 +1,7 @@
 """Drop-in for the subset of the reference's utils/tools.py that the model, test.py
 and scripts/simple_train.py touch: `tools.abstract_config`,
 `tools.abstract_model`, `tools.abs_test_model`, `tools.torch_warp`,
-`tools.occ_check_model`, meters and timers.  Same names, arguments and
+`tools.occ_check_model`, `tools.boundary_dilated_warp`, meters and timers.  Same names, arguments and
 behaviour (citations per item); the warp runs on the library's kernel.
 
 I/O, visualisation, augmentation and data loading (utils/tools.py:166-252,
@@ -158,6 +158,48 @@ class tools():
     def torch_warp(cls, x, flo):
         """Warp x [B,C,H,W] by flo [B,2,H,W]; bilinear, zero padding, no validity mask (utils/tools.py:1274-1304)."""
         return ops.warp(x, flo, align_corners=False, use_mask=False)
+
+    class boundary_dilated_warp():
+        """Photometric-loss warp that samples the UN-CROPPED frame (utils/tools.py:350-499): the training crop starts
+        at `start` inside the full image, so flows pointing outside the crop still find real pixels.  Loss-side op on
+        3-channel images: index arithmetic and gathers in torch."""
+
+        @classmethod
+        def get_grid(cls, batch_size, H, W, start):
+            xx = torch.arange(0, W, device=start.device, dtype=torch.float32).view(1, 1, 1, W).expand(batch_size, 1, H, W)
+            yy = torch.arange(0, H, device=start.device, dtype=torch.float32).view(1, 1, H, 1).expand(batch_size, 1, H, W)
+            grid = torch.cat((xx, yy, torch.ones_like(xx)), 1)
+            grid[:, :2] = grid[:, :2] + start
+            return grid
+
+        @classmethod
+        def transformer(cls, I, vgrid, train=True):
+            """Bilinear lookup of I [B,C,Hf,Wf] at absolute pixel positions vgrid [B,2,h,w]; corner indices are clamped
+            to the image, weights are taken against the CLAMPED corners (utils/tools.py:383-470)."""
+            B, C, Hf, Wf = I.shape
+            x, y = vgrid[:, 0], vgrid[:, 1]                      # [B,h,w]
+            x0 = torch.floor(x)
+            y0 = torch.floor(y)
+            x0c, x1c = x0.clamp(0, Wf - 1), (x0 + 1).clamp(0, Wf - 1)
+            y0c, y1c = y0.clamp(0, Hf - 1), (y0 + 1).clamp(0, Hf - 1)
+            flat = I.float().reshape(B, C, Hf * Wf)
+
+            def take(yc, xc):
+                idx = (yc.long() * Wf + xc.long()).reshape(B, 1, -1).expand(B, C, -1)
+                return torch.gather(flat, 2, idx).reshape(B, C, *x.shape[1:])
+            wa = ((x1c - x) * (y1c - y)).unsqueeze(1)
+            wb = ((x1c - x) * (y - y0c)).unsqueeze(1)
+            wc = ((x - x0c) * (y1c - y)).unsqueeze(1)
+            wd = ((x - x0c) * (y - y0c)).unsqueeze(1)
+            out = wa * take(y0c, x0c) + wb * take(y1c, x0c) + wc * take(y0c, x1c) + wd * take(y1c, x1c)
+            return out if train else out.permute(0, 2, 3, 1)
+
+        @classmethod
+        def warp_im(cls, I_nchw, flow_nchw, start_n211):
+            batch_size = I_nchw.shape[0]
+            _, _, ph, pw = flow_nchw.shape
+            grid = cls.get_grid(batch_size, ph, pw, start_n211.to(flow_nchw.device).float())
+            return cls.transformer(I_nchw, grid[:, :2] + flow_nchw)
 
     class occ_check_model():
         """Forward/backward consistency occlusion masks (utils/tools.py:501-677); runs after the decoder on two
