@@ -97,6 +97,14 @@ int upf_warp_bwd(const float* x, int ldx, const float* flow, int ldf, const floa
                  float* grad_x, int ldgx, float* grad_flow, int ldgf,
                  int N, int H, int W, int C, int align_corners, float mask_threshold, void* stream);
 
+/* Forward/backward consistency masks returned by UPFlow_net.forward (model/upflow.py:386-392): replaces
+ * tools.occ_check_model('for_back_check', utils/tools.py:501-677) -- ~25 elementwise ATen kernels and two warps per
+ * forward -- by one launch.  flow [N,H,W,>=2]: forward flows in images 0..N/2-1, backward flows in N/2..N-1;
+ * occ [N,H,W,>=1] receives 1 = visible, 0 = occluded:  |own + torch_warp(other, own)|_1 < alpha_1*(|own|_1+|other|_1) + alpha_2.
+ * mode 0 = 'all', 1 = 'obj' (visible OR flow leaving the image), 2 = 'out' (flow stays inside the image). */
+int upf_occ_check(const float* flow, int ldf, float* occ, int ldo, int N, int H, int W, float alpha_1, float alpha_2,
+                  int mode, int align_corners, void* stream);
+
 /* a5: normalize_features (model/upflow.py:94-137) with
  * moments_across_channels=False, moments_across_images=False (test.py:24-26). */
 int upf_featnorm_stats(const float* x, int ldx, int N, int H, int W, int C, double* stats, void* stream);

@@ -162,3 +162,24 @@ def test_batch_and_repeatability():
     # swapping the two frames swaps forward and backward flow
     fw, bw, _ = eng.forward(im2.cuda(), im1.cuda())
     assert (fw - b1).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("mode", ["obj", "all", "out"])
+def test_fused_occlusion_check_vs_module(mode):
+    """upf_occ_check (one launch inside the graph) against tools.occ_check_model of the drop-in (the reference's
+    elementwise recipe, utils/tools.py:550-588, 641-677, around the library warp) on the same flows."""
+    import upflow_pytorch_b200
+    from upflow_pytorch_b200 import ops
+    upflow_pytorch_b200.install_dropin()
+    from utils.tools import tools
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 2, 37, 53
+    ff, fb = torch.randn(B, 2, H, W, generator=g).cuda() * 4, torch.randn(B, 2, H, W, generator=g).cuda() * 4
+    fb = -ff + fb * 0.05                                   # mostly consistent, so both classes occur
+    ref_f, ref_b = tools.occ_check_model(occ_type='for_back_check', occ_alpha_1=0.1, occ_alpha_2=0.5, obj_out_all=mode)(ff, fb)
+    stacked = torch.cat([ff, fb]).permute(0, 2, 3, 1).contiguous()
+    occ = torch.empty(2 * B, H, W, 1, device="cuda")
+    ops.k_occ_check(stacked, occ, 0.1, 0.5, mode)
+    got_f, got_b = occ[:B].permute(0, 3, 1, 2), occ[B:].permute(0, 3, 1, 2)
+    assert 0.02 < ref_f.mean().item() < 0.98
+    assert (got_f != ref_f).float().mean().item() <= 1e-3 and (got_b != ref_b).float().mean().item() <= 1e-3

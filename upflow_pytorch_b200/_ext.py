@@ -24,6 +24,7 @@ SIGNATURES = {
     "upf_corr_lrelu_bwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "upf_warp_fwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P]),
     "upf_warp_bwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "upf_occ_check": (_I, [_P, _I, _P, _I, _I, _I, _I, _F, _F, _I, _I, _P]),
     "upf_featnorm_stats": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "upf_featnorm_apply": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
     "upf_resize_bilinear": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _c.POINTER(_F), _P]),

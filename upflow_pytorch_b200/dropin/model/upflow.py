@@ -220,8 +220,11 @@ class UPFlow_net(tools.abstract_model):
                     "the fused decoder implements the shipped configuration (test.py:22-30): "
                     "if_norm_before_cost_volume=True, norm_moments_across_channels=False, "
                     "norm_moments_across_images=False")
+            occ = None
+            if self.conf.occ_type == 'for_back_check':
+                occ = (self.conf.alpha_1, self.conf.alpha_2, self.conf.occ_check_obj_out_all)
             self._engine = DecoderEngine(self.state_dict(), device=params[0].device, precision=self.conv_precision,
-                                         use_sgu=bool(self.conf.if_sgu_upsample))
+                                         use_sgu=bool(self.conf.if_sgu_upsample), occ=occ)
             self._engine_key = key
             self._graphs = {}
         return self._engine
@@ -234,8 +237,13 @@ class UPFlow_net(tools.abstract_model):
         else:
             im1, im2 = im1_ori, im2_ori
         output_dict = {}
-        flow_f, flow_b, flows = self.forward_2_frame_v3(im1, im2, if_loss=input_dict['if_loss'])
-        occ_fw, occ_bw = self.occ_check_model(flow_f=flow_f, flow_b=flow_b)
+        fused = self._infer(im1, im2, want_flows=False) if not input_dict['if_loss'] else None
+        if fused is not None:
+            # inference: flows AND occlusion masks come out of the fused engine (one captured graph)
+            flow_f, flow_b, flows, occ_fw, occ_bw = fused
+        else:
+            flow_f, flow_b, flows = self.forward_2_frame_v3(im1, im2, if_loss=input_dict['if_loss'])
+            occ_fw, occ_bw = self.occ_check_model(flow_f=flow_f, flow_b=flow_b)
         output_dict['flow_f_out'] = flow_f
         output_dict['flow_b_out'] = flow_b
         output_dict['occ_fw'] = occ_fw
@@ -322,6 +330,17 @@ class UPFlow_net(tools.abstract_model):
                                "with .cuda(); there is no CPU path")
         if torch.is_grad_enabled() and (x1_raw.requires_grad or any(p.requires_grad for p in self.parameters())):
             return self._forward_2_frame_modules(x1_raw, x2_raw)
+        f, b, flows, _, _ = self._infer(x1_raw, x2_raw, want_flows=True)
+        return f, b, flows
+
+    def _infer(self, x1_raw, x2_raw, want_flows):
+        """The fused engine (CUDA graph per input shape).  Returns fresh tensors (flow_f, flow_b, flows or None, occ_fw,
+        occ_bw), or None when autograd needs the module-level path."""
+        if not x1_raw.is_cuda:
+            raise RuntimeError("UPFlow_net (upflow_pytorch_b200) runs on CUDA only: move the model and the inputs "
+                               "with .cuda(); there is no CPU path")
+        if torch.is_grad_enabled() and (x1_raw.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return None
         eng = self._get_engine()
         if self.use_cuda_graph:
             key = tuple(x1_raw.shape)
@@ -331,10 +350,21 @@ class UPFlow_net(tools.abstract_model):
                     self._graphs.clear()
                 g = self._graphs[key] = eng.capture(x1_raw.shape[0], x1_raw.shape[2], x1_raw.shape[3])
             f, b = g(x1_raw, x2_raw)
-            flows = g.flows
+            flows, occ = g.flows, g.occ
         else:
             f, b, flows = eng.forward(x1_raw.float(), x2_raw.float())
-        return f.clone(), b.clone(), [[a.clone(), c.clone()] for a, c in flows]
+            occ = eng.last_occ
+        if occ is None:
+            f, b = f.clone(), b.clone()
+            occ_fw, occ_bw = self.occ_check_model(flow_f=f, flow_b=b)
+        else:
+            B = f.shape[0]
+            fo = eng.flow_out_buffer(x1_raw.shape).clone()          # ONE copy of [2B,H,W,2] instead of two
+            oc = occ.clone()
+            fo, oc = fo.permute(0, 3, 1, 2), oc.permute(0, 3, 1, 2)
+            f, b, occ_fw, occ_bw = fo[:B], fo[B:], oc[:B], oc[B:]
+        flows = [[a.clone(), c.clone()] for a, c in flows] if want_flows else None
+        return f, b, flows, occ_fw, occ_bw
 
     def _forward_2_frame_modules(self, x1_raw, x2_raw):
         """Training path: model/upflow.py:494-533 module by module, every op an autograd node backed by the

@@ -78,7 +78,7 @@ class ConvSpec:
 
 class DecoderEngine:
     def __init__(self, state_dict, device="cuda", precision="tf32", align_corners=False, use_sgu=True,
-                 mask_threshold=1.0):
+                 mask_threshold=1.0, occ=None):
         """state_dict: the reference's parameter names."""
         if not torch.cuda.is_available():
             raise RuntimeError("DecoderEngine needs a CUDA device: the decoder path has no CPU implementation")
@@ -91,6 +91,10 @@ class DecoderEngine:
         # 1.0 = the reference's `mask >= 1.0` (model/pwc_modules.py:206); 0.9999 = diagnostic robust mask
         self.mask = True if mask_threshold == 1.0 else float(mask_threshold)
         self._ws = {}
+        # (alpha_1, alpha_2, 'all'|'obj'|'out'): also produce the forward/backward consistency masks that
+        # UPFlow_net.forward returns (tools.occ_check_model, model/upflow.py:386) -- one more launch in the graph
+        self.occ = occ
+        self.last_occ = None
         self.overlap = True        # image-only work on a side stream (forward())
         self.load_weights(state_dict)
 
@@ -198,6 +202,8 @@ class DecoderEngine:
             ws["inter_out"] = z(N, h4, w4, 4)
             ws["flow_full_bil"] = z(N, H, W, 2)
         ws["flow_out"] = z(N, H, W, 2)
+        if self.occ is not None:
+            ws["occ"] = z(N, H, W, 1)
         self._ws[key] = ws
         return ws
 
@@ -332,9 +338,17 @@ class DecoderEngine:
         else:
             ops.k_resize(prev_flow, out, (W / w4, H / h4))
             main.wait_event(ev_outconv)
+        self.last_occ = None
+        if self.occ is not None:
+            ops.k_occ_check(out, Slice(ws["occ"]), self.occ[0], self.occ[1], self.occ[2], ac)
+            self.last_occ = ws["occ"]
         fo = ws["flow_out"].permute(0, 3, 1, 2)
         lvl = [[f[:B].permute(0, 3, 1, 2), f[B:].permute(0, 3, 1, 2)] for f in flows]
         return fo[:B], fo[B:], lvl[::-1]
+
+    def flow_out_buffer(self, shape):
+        """the [2B,H,W,2] buffer the last forward of this input shape wrote (forward flows first)"""
+        return self._workspace(shape[0], shape[2], shape[3])["flow_out"]
 
     # ------------------------------------------------------------ CUDA graph
     def capture(self, B, H, W):
@@ -348,14 +362,15 @@ class DecoderEngine:
         n0 = _ext.launch_count()
         with torch.cuda.graph(graph):
             out = self.forward(im1, im2)
-        return GraphedForward(graph, im1, im2, out, _ext.launch_count() - n0)
+        return GraphedForward(graph, im1, im2, out, _ext.launch_count() - n0, self.last_occ)
 
 
 class GraphedForward:
     """Replay handle: copy a pair into (im1, im2), call replay(), read flow_f / flow_b (views of the workspace)."""
 
-    def __init__(self, graph, im1, im2, out, launches):
+    def __init__(self, graph, im1, im2, out, launches, occ=None):
         self.graph, self.im1, self.im2 = graph, im1, im2
+        self.occ = occ                                 # [2B,H,W,1] visibility masks (forward directions first) or None
         self.flow_f, self.flow_b, self.flows = out
         self.launches = launches                       # library kernels per replay
 

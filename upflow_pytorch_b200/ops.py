@@ -132,6 +132,16 @@ def k_warp_bwd(x, flow, grad_out, grad_x, grad_flow, align_corners=False, use_ma
                "warp_bwd")
 
 
+OCC_MODES = {"all": 0, "obj": 1, "out": 2}
+
+
+def k_occ_check(flow, occ, alpha_1, alpha_2, mode="obj", align_corners=False):
+    """flow [2B,H,W,2] = [forward flows; backward flows] -> occ [2B,H,W,1] (1 = visible)."""
+    flow, occ = _as_slice(flow), _as_slice(occ)
+    _ext.check(_lib().upf_occ_check(flow.ptr(), flow.ld, occ.ptr(), occ.ld, flow.N, flow.H, flow.W, float(alpha_1),
+                                    float(alpha_2), OCC_MODES[mode], int(align_corners), _stream()), "occ_check")
+
+
 def k_stats(x, stats):
     x = _as_slice(x)
     assert stats.dtype == torch.float64 and stats.numel() >= x.N * x.C * 2

@@ -40,6 +40,9 @@ def _account(name, args, kwargs):
     if name == "k_sgu_blend":
         inter, out = S(args[1]), S(args[2])
         return dict(bytes=4 * (4 * _npix(out) + 3 * _npix(inter)), flops=40 * _npix(out), shape=(out.N, out.H, out.W))
+    if name == "k_occ_check":
+        f = S(args[0])
+        return dict(bytes=4 * _npix(f) * 7, flops=30 * _npix(f), shape=(f.N, f.H, f.W))
     if name == "k_tap_combine":
         y, out = S(args[0]), S(args[2])
         return dict(bytes=4 * _npix(out) * (y.C + out.C), flops=9 * _npix(out) * out.C, shape=(out.N, out.C, out.H, out.W))
@@ -49,7 +52,7 @@ def _account(name, args, kwargs):
     return dict(bytes=0, flops=0, shape=())
 
 
-NAMES = ("k_corr", "k_warp", "k_stats", "k_conv", "k_resize", "k_sgu_blend", "k_copy", "k_norm_apply", "k_tap_combine")
+NAMES = ("k_corr", "k_warp", "k_stats", "k_conv", "k_resize", "k_sgu_blend", "k_copy", "k_norm_apply", "k_tap_combine", "k_occ_check")
 
 
 def event_overhead_ms(n=200):
