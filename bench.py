@@ -473,6 +473,37 @@ def _main():
                    "sample": "%d forward(s) of the same %dx%d batch-%d pair after 1 warm-up, %d torch threads" % (reps, H, W, B, cores),
                    "epe_cuda_vs_cpu_port_px": O.epe(f.cpu(), rf)}
 
+        # ---------------- the reference's GPU path (the >= 10x target is against it): the op-for-op
+        # port of model/upflow.py (F.conv2d / cuDNN, F.grid_sample, unfold correlation) in eager PyTorch on this GPU,
+        # same weights, same inputs, host tensors in and out like e2e.  Reported next to the result, never part of it.
+        ref_gpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle import ref_port as P
+                sd_d = {k: v.cuda() for k, v in sd.items()}
+                with torch.no_grad():
+                    def ref_step():
+                        rf = P.forward_2_frame(im1_h.cuda(non_blocking=True), im2_h.cuda(non_blocking=True), sd_d)[0]
+                        out_h.copy_(rf, non_blocking=True)
+                        torch.cuda.current_stream().synchronize()
+                    for _ in range(3):
+                        ref_step()
+                    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    r0.record()
+                    for _ in range(10):
+                        ref_step()
+                    r1.record()
+                    torch.cuda.synchronize()
+                rms = r0.elapsed_time(r1) / 10
+                ref_gpu = {"value": B / (rms * 1e-3), "unit": UNIT, "ms_per_step": rms, "kind": "port",
+                           "path": "oracle/ref_port.py on cuda:0 (eager PyTorch %s, cuDNN, allow_tf32=%s), pinned host in / host out"
+                                   % (torch.__version__, torch.backends.cudnn.allow_tf32),
+                           "e2e_speedup_over_it": e2e["value"] / (B / (rms * 1e-3))}
+                del sd_d
+                torch.cuda.empty_cache()
+            except Exception as exc:   # pragma: no cover - the comparison leg must never break the bench line
+                ref_gpu = {"error": repr(exc)[:200]}
+
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic",
@@ -486,6 +517,8 @@ def _main():
                 "wall_s_timed_region": wall}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if ref_gpu is not None:
+            line["reference_gpu_path"] = ref_gpu
         emit(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -154,3 +154,33 @@ print("OK", type(tm.net_work).__module__)
     r = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, cwd=str(tmp_path))
     assert r.returncode == 0, r.stderr[-2000:]
     assert "OK model.upflow" in r.stdout
+
+
+def test_kitti_evaluation_helpers(tmp_path):
+    """metrics of dataset/kitti_dataset.py:464-499 on a case worked by hand, and the 16-bit KITTI PNG round trip
+    (write: utils/tools.py:1516-1525, read: dataset/kitti_dataset.py:130-149)."""
+    import numpy as np
+    import torch
+    from upflow_pytorch_b200 import evaluation as E
+    gt = torch.zeros(1, 2, 2, 3)
+    gt[0, 0] = torch.tensor([[10.0, 0.0, 100.0], [0.0, 0.0, 0.0]])
+    pred = gt.clone()
+    pred[0, 0, 0, 0] += 4.0          # error 4 > max(3, 0.5): outlier
+    pred[0, 1, 0, 2] += 4.0          # error 4 < max(3, 5): not an outlier
+    pred[0, 0, 1, 1] += 2.0          # error 2: not an outlier
+    pred[0, 0, 1, 2] += 50.0         # masked out
+    mask = torch.ones(1, 1, 2, 3)
+    mask[0, 0, 1, 2] = 0
+    assert abs(E.flow_error_avg(pred, gt, mask).item() - 10.0 / 5) < 1e-5
+    assert abs(E.outlier_pct(gt, pred, mask).item() - 100.0 / 5) < 1e-4
+    epe_all, f1, epe_noc, epe_occ = E.evaluate(pred, gt, mask, gt, mask * 0 + torch.tensor([[1.0, 1, 0], [1, 0, 0]]))
+    assert abs(epe_all - 2.0) < 1e-5 and abs(f1 - 20.0) < 1e-4
+    assert abs(epe_noc - 4.0 / 3) < 1e-5 and abs(epe_occ - 6.0 / 2) < 1e-5
+    rng = np.random.RandomState(0)
+    flow = np.round(rng.randn(7, 9, 2) * 20 * 64) / 64.0          # representable at 1/64 px
+    valid = (rng.rand(7, 9) > 0.3).astype(np.uint16)
+    p = str(tmp_path / "flow.png")
+    E.write_kitti_png_file(p, flow, valid)
+    f2, m2 = E.read_png_flow(p)
+    assert f2.shape == (2, 7, 9) and m2.shape == (1, 7, 9)
+    assert np.array_equal(np.transpose(f2, [1, 2, 0]), flow) and np.array_equal(m2[0], valid.astype(np.uint8))

@@ -52,3 +52,23 @@ def test_full_forward_port_is_bit_identical_with_checkpoint(ref):
     assert torch.equal(f, pf) and torch.equal(b, pb)
     # the checkpointed net recovers the synthetic (-3,+2) flow
     assert abs(f[:, 0].mean().item() + 3) < 0.3 and abs(f[:, 1].mean().item() - 2) < 0.3
+
+
+def test_evaluation_metrics_match_the_reference():
+    """upflow_pytorch_b200.evaluation against kitti_flow.Evaluation_bench.{flow_error_avg,outlier_pct} of the mounted
+    reference (dataset/kitti_dataset.py:464-499)."""
+    import importlib
+    import torch
+    from oracle import ref_shims
+    if not ref_shims.have_reference():
+        pytest.skip("reference not mounted")
+    ref_shims.install()
+    kd = importlib.import_module("dataset.kitti_dataset")
+    from upflow_pytorch_b200 import evaluation as E
+    g = torch.Generator().manual_seed(0)
+    gt, pred = torch.randn(2, 2, 9, 11, generator=g) * 30, torch.randn(2, 2, 9, 11, generator=g) * 30
+    pred = gt + (pred - gt) * 0.1
+    mask = (torch.rand(2, 1, 9, 11, generator=g) > 0.4).float()
+    bench = kd.kitti_flow.Evaluation_bench
+    assert torch.equal(E.flow_error_avg(pred, gt, mask), bench.flow_error_avg(pred, gt, mask))
+    assert torch.equal(E.outlier_pct(gt, pred, mask), bench.outlier_pct(gt, pred, mask))
