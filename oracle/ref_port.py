@@ -48,8 +48,9 @@ def corr_unfold(in1, in2, d=4):
 def _vgrid(flow):
     # mesh + flow -> [-1,1]   model/pwc_modules.py:186-199, utils/tools.py:1284-1299
     B, _, H, W = flow.shape
-    xx = torch.arange(0, W).view(1, -1).repeat(H, 1).view(1, 1, H, W).repeat(B, 1, 1, 1)
-    yy = torch.arange(0, H).view(-1, 1).repeat(1, W).view(1, 1, H, W).repeat(B, 1, 1, 1)
+    # (the reference builds the mesh on the host and moves it with .cuda() when x.is_cuda, pwc_modules.py:192-193)
+    xx = torch.arange(0, W, device=flow.device).view(1, -1).repeat(H, 1).view(1, 1, H, W).repeat(B, 1, 1, 1)
+    yy = torch.arange(0, H, device=flow.device).view(-1, 1).repeat(1, W).view(1, 1, H, W).repeat(B, 1, 1, 1)
     vgrid = torch.cat((xx, yy), 1).float() + flow
     vgrid[:, 0] = 2.0 * vgrid[:, 0] / max(W - 1, 1) - 1.0
     vgrid[:, 1] = 2.0 * vgrid[:, 1] / max(H - 1, 1) - 1.0
@@ -167,8 +168,8 @@ def forward_2_frame(im1, im2, sd, use_sgu=True, taps=None):
     p1 = pyramid(im1, sd) + [im1]
     p2 = pyramid(im2, sd) + [im2]
     B, _, h0, w0 = p1[0].shape
-    flow_f = torch.zeros(B, 2, h0, w0)
-    flow_b = torch.zeros(B, 2, h0, w0)
+    flow_f = torch.zeros(B, 2, h0, w0, device=im1.device)
+    flow_b = torch.zeros(B, 2, h0, w0, device=im1.device)
     levels = []
     for l in range(5):
         levels.append((p1[l], _conv(p1[l], sd, f"conv_1x1.{l}"), p2[l], _conv(p2[l], sd, f"conv_1x1.{l}")))

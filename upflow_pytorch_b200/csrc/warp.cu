@@ -78,14 +78,37 @@ warp_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ 
 #pragma unroll
     for (int t = 0; t < 4; ++t) sm[a][t] = sq[a][t] = 0.f;
 
-  for (int p = cta * ppc + pslot; p < npix; p += ctas_per_image * ppc) {
-    const int y = p / W, xpix = p - y * W;
-    const float* fl = flow + (img + p) * ldf;
-    const float u = __ldg(fl), v = __ldg(fl + 1);
-    const float ix = sample_coord((float)xpix, u, W, align_corners);
-    const float iy = sample_coord((float)y, v, H, align_corners);
-    const BilinearTaps t = bilinear_taps(ix, iy, H, W);
-    const bool keep = !(mask_thr > 0.f) || t.wsum >= mask_thr;      // mask = (grid_sample(ones) >= 1.0), pwc_modules.py:205-206
+  // The sampling coordinates, the four weights and the mask are a per-PIXEL computation (two IEEE divisions among
+  // ~100 instructions): one lane of the lpp lanes that share a pixel does it and broadcasts seven words.  (Every lane
+  // recomputing it made the kernel instruction-bound: 8x redundant at C=32, 32x at C=128.)
+  const int lane = threadIdx.x & 31;
+  const int leader = lane - (lpp < 32 ? sub : lane);       // lane of this pixel's sub == 0 inside the warp
+  for (int base = cta * ppc; base < npix; base += ctas_per_image * ppc) {   // uniform trip count per CTA (shuffles below)
+    const int p_raw = base + pslot;
+    const bool live = p_raw < npix;
+    const int p = live ? p_raw : npix - 1;
+    BilinearTaps t;
+    int flags = 0;
+    if (lane == leader) {
+      const int y = p / W, xpix = p - y * W;
+      const float* fl = flow + (img + p) * ldf;
+      const float u = __ldg(fl), v = __ldg(fl + 1);
+      const float ix = sample_coord((float)xpix, u, W, align_corners);
+      const float iy = sample_coord((float)y, v, H, align_corners);
+      t = bilinear_taps(ix, iy, H, W);
+      const bool k = !(mask_thr > 0.f) || t.wsum >= mask_thr;      // mask = (grid_sample(ones) >= 1.0), pwc_modules.py:205-206
+      flags = (t.in_nw ? 1 : 0) | (t.in_ne ? 2 : 0) | (t.in_sw ? 4 : 0) | (t.in_se ? 8 : 0) | (k ? 16 : 0);
+    }
+    t.x0 = __shfl_sync(0xffffffffu, t.x0, leader);
+    t.y0 = __shfl_sync(0xffffffffu, t.y0, leader);
+    t.w_nw = __shfl_sync(0xffffffffu, t.w_nw, leader);
+    t.w_ne = __shfl_sync(0xffffffffu, t.w_ne, leader);
+    t.w_sw = __shfl_sync(0xffffffffu, t.w_sw, leader);
+    t.w_se = __shfl_sync(0xffffffffu, t.w_se, leader);
+    flags = __shfl_sync(0xffffffffu, flags, leader);
+    t.in_nw = flags & 1; t.in_ne = flags & 2; t.in_sw = flags & 4; t.in_se = flags & 8;
+    const bool keep = (flags & 16) != 0;
+    if (!live) continue;
     const float* r_nw = x + (ximg + (long long)t.y0 * W + t.x0) * (long long)ldx;   // may point outside: only dereferenced when in_*
     const float* r_ne = r_nw + ldx;
     const float* r_sw = r_nw + (size_t)W * ldx;
@@ -325,7 +348,9 @@ extern "C" int upf_warp_fwd(const float* x, int ldx, const float* flow, int ldf,
   int per_image = (H * W + ppc - 1) / ppc;
   // the CTA count per image fixes how the fp32 partial moments are grouped: it must depend on the image
   // size only, never on N, so that an image gives the same bits in any batch (batch sharding relies on it)
-  const int cap = UPF_NUM_SMS * 4;
+  // (with the fused moments every CTA ends in one double atomic per channel and moment: measured, 914 CTAs per image
+  // cost 29 us at 2x32x94x311 where the warp alone takes 13.6 -- fewer, longer CTAs there)
+  const int cap = stats ? UPF_NUM_SMS * 2 : UPF_NUM_SMS * 8;
   if (per_image > cap) per_image = cap;
   if (per_image < 1) per_image = 1;
   const bool vec = (C % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(x) && aligned16(out);
@@ -360,7 +385,7 @@ extern "C" int upf_featnorm_stats(const float* x, int ldx, int N, int H, int W, 
   const int lpp = pick_lpp(C);
   const int ppc = WARP_NT / lpp;
   int per_image = (H * W + ppc * 8 - 1) / (ppc * 8);
-  const int cap = UPF_NUM_SMS * 4;                   // independent of N (see upf_warp_fwd)
+  const int cap = UPF_NUM_SMS * 8;                   // independent of N (see upf_warp_fwd)
   if (per_image > cap) per_image = cap;
   if (per_image < 1) per_image = 1;
   const int vec = (C % 4 == 0) && (ldx % 4 == 0) && aligned16(x);
