@@ -181,12 +181,18 @@ class DecoderEngine:
         ws["enc_a"] = [z(N, *sizes[l + 1], chs[l]) for l in range(6)]
         ws["enc_b"] = [z(N, *sizes[l + 1], chs[l]) for l in range(6)]
         lv = []
+        # every (sum, sum^2) accumulator of a forward lives in ONE arena, cleared by one memset per forward
+        arena = torch.zeros(2 * N * sum(NUM_CHS) * 2, dtype=torch.float64, device=dev)
+        ws["stats_arena"] = arena
+        off = 0
         for l in range(5):
             h, w = sizes[6 - l]
+            n = N * NUM_CHS[l] * 2
             d = {"hw": (h, w), "X": z(N, h, w, X_LD), "T0": z(N, h, w, 128), "T1": z(N, h, w, 128),
                  "flow": z(N, h, w, 2), "xw": z(N, h, w, NUM_CHS[l]),
-                 "stats_own": torch.zeros(N, NUM_CHS[l], 2, dtype=torch.float64, device=dev),
-                 "stats_w": torch.zeros(N, NUM_CHS[l], 2, dtype=torch.float64, device=dev)}
+                 "stats_own": arena[off:off + n].view(N, NUM_CHS[l], 2),
+                 "stats_w": arena[off + n:off + 2 * n].view(N, NUM_CHS[l], 2)}
+            off += 2 * n
             if self.use_sgu and l > 0:
                 d["S"] = z(N, h, w, S_LD)
                 d["inter"] = z(N, h, w, 4)
@@ -240,6 +246,7 @@ class DecoderEngine:
         ws = self._workspace(B, H, W)
         N = 2 * B
         ac = self.align_corners
+        ws["stats_arena"].zero_()                      # all feature / warp moment accumulators of this forward
         feats = self.encode(ws, im1, im2)              # index l -> 1/2^(l+1); decoder level L uses feats[5-L]
         # Work that depends on the images only -- the 1x1 adapters and feature statistics of levels 1..4 and
         # sgi_model.output_conv (two full-resolution convolutions) -- runs on a SIDE STREAM while the main stream
@@ -255,7 +262,6 @@ class DecoderEngine:
                 d = ws["levels"][L]
                 F = Slice(feats[5 - L])
                 self._conv(self.conv1x1[L], F, Slice(d["X"], X_F1X1, 32))
-                d["stats_own"].zero_()
                 ops.k_stats(F, d["stats_own"])
             ev_adapters.record(side)
             if self.use_sgu:
@@ -277,12 +283,12 @@ class DecoderEngine:
             if L == 0:
                 # 1x1 adapter (model/upflow.py:508-513) straight into its estimator slot
                 self._conv(self.conv1x1[L], F, Slice(X, X_F1X1, 32))
-                d["stats_own"].zero_()
                 ops.k_stats(F, d["stats_own"])
             elif L == 1:
                 main.wait_event(ev_adapters)
             if L == 0:
-                X[..., X_FLOW:X_FLOW + 2].zero_()      # upsampling a zero flow (model/upflow.py:504-505, :536)
+                pass       # upsampling a zero flow (model/upflow.py:504-505, :536): this slot of the level-0 buffer is
+                           # zero from allocation on and nothing ever writes it
             else:
                 ph, pw = ws["levels"][L - 1]["hw"]
                 if self.use_sgu:
@@ -300,7 +306,6 @@ class DecoderEngine:
             if L == 0:
                 ops.k_corr(F, F, Slice(X, X_CORR, 81), 4, d["stats_own"], d["stats_own"], f2_shift=B, slope=SLOPE)
             else:
-                d["stats_w"].zero_()
                 ops.k_warp(F, flow_up, Slice(d["xw"]), ac, self.mask, x_shift=B, stats=d["stats_w"])
                 ops.k_corr(F, Slice(d["xw"]), Slice(X, X_CORR, 81), 4, d["stats_own"], d["stats_w"], slope=SLOPE)
             # dense flow estimator (model/pwc_modules.py:279-286)
