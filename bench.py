@@ -448,9 +448,19 @@ def _main():
             roof = {"kernel": dom + "_kernel", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": ach / pk["hbm"], "traffic": traffic, "peak_source": pk["source"],
                     "launches_per_step": a["launches"], "ms_per_step": a["ms"], "share_of_step": a["ms"] / total_ms}
-        breakdown = {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
+        def _frac(k, v):
+            # fraction of the roofline that bounds the family: TF32 tensor peak for the tcgen05 convolutions, HBM otherwise
+            if v["ms"] <= 0:
+                return None
+            if k in ("conv_win", "conv_halo", "conv_tc"):
+                return round(v["flops"] / (v["ms"] * 1e-3) / 1e12 / (pk["bf16"] / 2.0), 4)
+            if k in ("conv_simt", "conv_c3"):
+                return round(v["flops"] / (v["ms"] * 1e-3) / 1e12 / 74.4, 4)
+            return round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm"], 4)
+        breakdown = {k: {"launches": v["launches"], "ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4),
                          "GB/s": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
-                         "TFLOP/s": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 else None}
+                         "TFLOP/s": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 else None,
+                         "roofline_frac": _frac(k, v)}
                      for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
         rc = corr_roofline(pk)
 
