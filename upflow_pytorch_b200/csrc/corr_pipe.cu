@@ -29,11 +29,17 @@
 // finisher warps converting and storing them, 67.6 vs 61.4 us; the operands staged
 // by three service warps with 16-byte cp.async instead of TMA, 79.9 us -- the
 // copies share the LSU path with the compute warps' shared-memory loads.)
-// Where the 61 us go (debug builds, HD shape, d=4): without the 9th compute warp
-// (two warps per scheduler instead of 3/2/2/2) 51 us; without the store epilogue
-// 51 us; without both 41 us, and that remainder does not move when half of the
-// shared-memory loads or half of the FMAs are removed: it is the TMA unit
-// delivering 3584 32-byte box rows per tile (~3 cycles per row).
+// Where the ~59 us go (clock64 around the phases of every compute warp, CTA 0, HD
+// shape, d=4, 7 tiles, 101k cycles): waiting for operands 6.6k in total -- the TMA
+// ring keeps up; FMA loop 10.3k cycles per tile for the three warps that share
+// scheduler 0 (issue-bound, IPC 0.73) and 7.2k for the two-warp schedulers, which
+// is the SHARED-MEMORY bound: 216 LDS.128 per channel quad = 6.9k wavefront cycles
+// per tile, the pipe is 96 % busy; epilogue (convert, transpose, two CTA barriers,
+// bulk store) ~4k per tile.  A variant that splits the last displacement column by
+// rows over four helper warps (one per scheduler) and replaces the CTA barriers by
+// per-half mbarriers measured 57.6 us: balanced, but the helpers' 2-row tiles read
+// 1 word per 1.5 FMA and every warp then runs at the shared-memory bound (10.2k).
+// The lever left is the FMA : shared-load ratio (3 with 8x9 blocking), not the pipeline.
 // Shared-memory rows are 64 (32) bytes; the 16-byte chunk index is XOR-swizzled
 // with (position >> 1) & 3 (TMA's SWIZZLE_64B; (position >> 2) & 1 = SWIZZLE_32B) so that 8
 // consecutive lanes reading the same chunk of 8 consecutive positions hit 8
