@@ -213,9 +213,11 @@ long long upf_featnorm_bwd_workspace_doubles(int N, int C);
 int upf_featnorm_bwd(const float* x, int ldx, const double* stats, const float* grad_out, int ldg, float* grad_x,
                      int ldgx, double* workspace, int N, int H, int W, int C, void* stream);
 
-/* adjoint of upf_resize_bilinear: grad_in [N,h,w,C] from grad_out [N,H,W,C] (same scale vector). */
+/* adjoint of upf_resize_bilinear: grad_in [N,h,w,C] from grad_out [N,H,W,C] (same scale vector); separable, two
+ * passes through workspace (upf_resize_bilinear_bwd_workspace_elems(N, H, w, C) floats). */
+long long upf_resize_bilinear_bwd_workspace_elems(int N, int H, int w, int C);
 int upf_resize_bilinear_bwd(const float* grad_out, int ldgo, int H, int W, float* grad_in, int ldgi, int h, int w,
-                            int N, int C, const float* scale_host, void* stream);
+                            int N, int C, const float* scale_host, float* workspace, void* stream);
 
 /* layout helpers for callers holding NCHW-contiguous tensors (the reference's
  * layout): strided copy between [N,C,H,W] planes and pixel-major rows. */

@@ -92,7 +92,7 @@ def test_normalize_features_backward(upf, shape):
 
 
 @pytest.mark.parametrize("case", [(2, 12, 39, 24, 78, True), (2, 94, 311, 375, 1242, True), (1, 47, 156, 188, 621, False),
-                                  (1, 1, 7, 5, 7, False), (2, 24, 78, 24, 78, True)])
+                                  (1, 1, 7, 5, 7, False), (2, 24, 78, 24, 78, True), (2, 4, 13, 256, 832, True), (2, 3, 5, 64, 96, False)])
 def test_resize_backward(upf, case):
     C, h, w, H, W, rate = case
     C = 2 if rate else 1

@@ -44,7 +44,8 @@ SIGNATURES = {
     "upf_blend_bwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _LL, _P]),
     "upf_featnorm_bwd_workspace_doubles": (_LL, [_I, _I]),
     "upf_featnorm_bwd": (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
-    "upf_resize_bilinear_bwd": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _c.POINTER(_F), _P]),
+    "upf_resize_bilinear_bwd_workspace_elems": (_LL, [_I, _I, _I, _I]),
+    "upf_resize_bilinear_bwd": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _c.POINTER(_F), _P, _P]),
     "upf_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "upf_nhwc_to_nchw": (_I, [_P, _I, _P, _I, _I, _I, _I, _P]),
     "upf_copy_channels": (_I, [_P, _I, _P, _I, _LL, _I, _P]),

@@ -18,97 +18,166 @@ namespace upf {
 // dW[tap][ci][co] = sum over output pixels p of X[p (+) tap][ci] * G[p][co]:  per tap a GEMM with the pixels as
 // the K dimension.  CTA tile 64 ci x 64 co, 16 pixels per shared-memory step, 4x4 register tile per thread.
 // grid = (ci tiles * co tiles, taps, pixel splits); split s writes part[s][tap][ci][co].
-constexpr int WG_BM = 64, WG_BN = 64, WG_KP = 16, WG_NT = 256;
+constexpr int WG_KP = 16, WG_NT = 256;
 
-__global__ void __launch_bounds__(WG_NT)
+// BM x BN CTA tile (ci x co), TM x TN register tile per thread, 256 threads = (BM/TM) x (BN/TN).
+// 128x128 / 8x8 reads one shared word per 4 FMAs (the first version, 64x64 / 4x4, one per 2: shared-memory bound).
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(WG_NT, 2)
 conv_wgrad_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ g, int ldg, float* __restrict__ part,
                   int N, int H, int W, int Ho, int Wo, int Cin, int Cout, int ks, int stride, int dil, int pad,
                   int co_tiles, long long pix_per_split, long long npix) {
-  __shared__ __align__(16) float Xs[WG_KP][WG_BM];
-  __shared__ __align__(16) float Gs[WG_KP][WG_BN];
+  static_assert((BM / TM) * (BN / TN) == WG_NT, "thread layout");
+  static_assert(TM % 4 == 0 && TN % 2 == 0, "vector widths");
+  __shared__ __align__(16) float Xs[WG_KP][BM];
+  __shared__ __align__(16) float Gs[WG_KP][BN];
   const int tile = blockIdx.x, tap = blockIdx.y, split = blockIdx.z;
-  const int ci0 = (tile / co_tiles) * WG_BM, co0 = (tile % co_tiles) * WG_BN;
+  const int ci0 = (tile / co_tiles) * BM, co0 = (tile % co_tiles) * BN;
   const int ky = tap / ks, kx = tap % ks;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int lrow = tid >> 4, lcol = (tid & 15) * 4;       // loader: pixel row of the step, 4 consecutive channels
+  const int tid = threadIdx.x;
+  constexpr int TXN = BN / TN;                               // threads along co
+  const int tx = tid % TXN, ty = tid / TXN;
   const bool vx = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   const bool vg = (ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
   const long long p_begin = (long long)split * pix_per_split;
   long long p_end = p_begin + pix_per_split;
   if (p_end > npix) p_end = npix;
-  float acc[4][4];
+  float acc[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  constexpr int XV = WG_KP * BM / 4, GV = WG_KP * BN / 4;    // float4 loads per step for each operand
 
-  for (long long p0 = p_begin; p0 < p_end; p0 += WG_KP) {
-    const long long p = p0 + lrow;
-    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
-    if (p < p_end) {
-      const int ox = (int)(p % Wo);
-      const long long t = p / Wo;
-      const int oy = (int)(t % Ho), n = (int)(t / Ho);
-      const int iy = oy * stride - pad + ky * dil, ix = ox * stride - pad + kx * dil;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-        const float* xp = x + ((size_t)((size_t)n * H + iy) * W + ix) * ldx + ci0 + lcol;
-        if (vx && ci0 + lcol + 3 < Cin && (((ci0 + lcol) & 3) == 0)) xv = ldg4(xp);
-        else {
-          if (ci0 + lcol < Cin) xv.x = __ldg(xp);
-          if (ci0 + lcol + 1 < Cin) xv.y = __ldg(xp + 1);
-          if (ci0 + lcol + 2 < Cin) xv.z = __ldg(xp + 2);
-          if (ci0 + lcol + 3 < Cin) xv.w = __ldg(xp + 3);
+  float4 xv[(XV + WG_NT - 1) / WG_NT], gv[(GV + WG_NT - 1) / WG_NT];
+  // global -> registers for the step starting at pixel p0 (issued one step ahead: the loads fly during the FMAs)
+  auto fetch = [&](long long p0) {
+#pragma unroll
+    for (int r = 0; r < (XV + WG_NT - 1) / WG_NT; ++r) {
+      const int v = tid + r * WG_NT;
+      xv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int lrow = v / (BM / 4), lcol = (v % (BM / 4)) * 4;
+      const long long p = p0 + lrow;
+      if (v < XV && p < p_end) {
+        const int ox = (int)(p % Wo);
+        const long long t = p / Wo;
+        const int oy = (int)(t % Ho), n = (int)(t / Ho);
+        const int iy = oy * stride - pad + ky * dil, ix = ox * stride - pad + kx * dil;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          const float* xp = x + ((size_t)((size_t)n * H + iy) * W + ix) * ldx + ci0 + lcol;
+          if (vx && ci0 + lcol + 3 < Cin) xv[r] = ldg4(xp);
+          else {
+            if (ci0 + lcol < Cin) xv[r].x = __ldg(xp);
+            if (ci0 + lcol + 1 < Cin) xv[r].y = __ldg(xp + 1);
+            if (ci0 + lcol + 2 < Cin) xv[r].z = __ldg(xp + 2);
+            if (ci0 + lcol + 3 < Cin) xv[r].w = __ldg(xp + 3);
+          }
         }
       }
-      const float* gp = g + (size_t)p * ldg + co0 + lcol;
-      if (vg && co0 + lcol + 3 < Cout) gv = ldg4(gp);
-      else {
-        if (co0 + lcol < Cout) gv.x = __ldg(gp);
-        if (co0 + lcol + 1 < Cout) gv.y = __ldg(gp + 1);
-        if (co0 + lcol + 2 < Cout) gv.z = __ldg(gp + 2);
-        if (co0 + lcol + 3 < Cout) gv.w = __ldg(gp + 3);
+    }
+#pragma unroll
+    for (int r = 0; r < (GV + WG_NT - 1) / WG_NT; ++r) {
+      const int v = tid + r * WG_NT;
+      gv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int lrow = v / (BN / 4), lcol = (v % (BN / 4)) * 4;
+      const long long p = p0 + lrow;
+      if (v < GV && p < p_end) {
+        const float* gp = g + (size_t)p * ldg + co0 + lcol;
+        if (vg && co0 + lcol + 3 < Cout) gv[r] = ldg4(gp);
+        else {
+          if (co0 + lcol < Cout) gv[r].x = __ldg(gp);
+          if (co0 + lcol + 1 < Cout) gv[r].y = __ldg(gp + 1);
+          if (co0 + lcol + 2 < Cout) gv[r].z = __ldg(gp + 2);
+          if (co0 + lcol + 3 < Cout) gv[r].w = __ldg(gp + 3);
+        }
       }
     }
+  };
+  fetch(p_begin);
+  for (long long p0 = p_begin; p0 < p_end; p0 += WG_KP) {
     __syncthreads();                                      // the previous step's tiles have been consumed
-    *reinterpret_cast<float4*>(&Xs[lrow][lcol]) = xv;
-    *reinterpret_cast<float4*>(&Gs[lrow][lcol]) = gv;
+#pragma unroll
+    for (int r = 0; r < (XV + WG_NT - 1) / WG_NT; ++r) {
+      const int v = tid + r * WG_NT;
+      if (v < XV) *reinterpret_cast<float4*>(&Xs[v / (BM / 4)][(v % (BM / 4)) * 4]) = xv[r];
+    }
+#pragma unroll
+    for (int r = 0; r < (GV + WG_NT - 1) / WG_NT; ++r) {
+      const int v = tid + r * WG_NT;
+      if (v < GV) *reinterpret_cast<float4*>(&Gs[v / (BN / 4)][(v % (BN / 4)) * 4]) = gv[r];
+    }
     __syncthreads();
+    if (p0 + WG_KP < p_end) fetch(p0 + WG_KP);
 #pragma unroll
     for (int k = 0; k < WG_KP; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&Xs[k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Gs[k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      float av[TM], bv[TN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; i += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(&Xs[k][ty * TM + i]);
+        av[i] = a.x; av[i + 1] = a.y; av[i + 2] = a.z; av[i + 3] = a.w;
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int j = 0; j < TN; j += 2) {
+        // a thread's TN output channels are pairs 2*TXN apart: consecutive lanes read consecutive 8-byte words
+        // (tx * TN + j made 16 lanes hit 4 bank groups: ncu, 38 % of the shared wavefronts were conflicts)
+        const float2 b = *reinterpret_cast<const float2*>(&Gs[k][(j / 2) * (2 * TXN) + tx * 2]);
+        bv[j] = b.x; bv[j + 1] = b.y;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
   }
   const int taps = ks * ks;
   float* dst = part + ((size_t)split * taps + tap) * Cin * Cout;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int ci = ci0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int ci = ci0 + ty * TM + i;
     if (ci >= Cin) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = co0 + tx * 4 + j;
+    for (int j = 0; j < TN; ++j) {
+      const int co = co0 + (j / 2) * (2 * TXN) + tx * 2 + (j & 1);
       if (co < Cout) dst[(size_t)ci * Cout + co] = acc[i][j];
     }
   }
 }
 
-// per-channel sum of G over a pixel range (bias gradient partials): part[split][co]
+// per-channel sum of G over a pixel range (bias gradient partials): part[split][co].  256 threads = `cw` channel lanes
+// x 256/cw pixel slots; the slots are summed through shared memory in slot order (deterministic).  (First version:
+// one thread per channel walking its pixel range alone -- 14 % of a training step.)
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ g, int ldg, float* __restrict__ part, int Cout, long long pix_per_split, long long npix) {
+colsum_kernel(const float* __restrict__ g, int ldg, float* __restrict__ part, int Cout, int cw, long long pix_per_split,
+              long long npix) {
+  __shared__ float s_part[256];
   const int split = blockIdx.x;
   const long long p_begin = (long long)split * pix_per_split;
   long long p_end = p_begin + pix_per_split;
   if (p_end > npix) p_end = npix;
-  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+  const int slots = 256 / cw, lane_c = threadIdx.x % cw, slot = threadIdx.x / cw;
+  for (int c0 = 0; c0 < Cout; c0 += cw) {
+    const int co = c0 + lane_c;
     float s = 0.f;
-    for (long long p = p_begin; p < p_end; ++p) s += __ldg(g + (size_t)p * ldg + co);
-    part[(size_t)split * Cout + co] = s;
+    if (co < Cout) {
+      float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      long long p = p_begin + slot;
+      for (; p + 3 * slots < p_end; p += 4 * slots) {       // four independent loads in flight
+        s += __ldg(g + (size_t)p * ldg + co);
+        s1 += __ldg(g + (size_t)(p + slots) * ldg + co);
+        s2 += __ldg(g + (size_t)(p + 2 * slots) * ldg + co);
+        s3 += __ldg(g + (size_t)(p + 3 * slots) * ldg + co);
+      }
+      for (; p < p_end; p += slots) s += __ldg(g + (size_t)p * ldg + co);
+      s = (s + s1) + (s2 + s3);
+    }
+    s_part[threadIdx.x] = s;
+    __syncthreads();
+    if (slot == 0 && co < Cout) {
+      float t = 0.f;
+      for (int k = 0; k < slots; ++k) t += s_part[k * cw + lane_c];
+      part[(size_t)split * Cout + co] = t;
+    }
+    __syncthreads();
   }
 }
 
@@ -221,33 +290,52 @@ featnorm_bwd_apply_kernel(const float* __restrict__ x, int ldx, const double* __
 }
 
 // ------------------------------------------------------------------------------------------------ resize backward
-// gather form of the adjoint of resize_bilinear_kernel: input pixel (iy, ix) collects every output pixel whose two
-// taps touch it (exact test with the forward's own tap computation), multiplied by the channel scale.
+// adjoint of resize_bilinear_kernel, separable and in gather form (exact tap test with the forward's own tap
+// computation, deterministic):  T[n,oy,ix] = sum_ox wx(ox,ix) g[n,oy,ox];  gin[n,iy,ix] = scale * sum_oy wy(oy,iy) T[n,oy,ix].
+// (First version: one thread per INPUT pixel scanning its whole 2-D footprint -- at the 64x upsampling of the
+// multi-scale distillation loss that is 416 threads walking 17k output pixels each, 0.86 ms per call.)
+__device__ __forceinline__ void resize_bwd_range(int i, float sc, int n_out, int& lo, int& hi) {
+  lo = 0; hi = n_out - 1;
+  if (sc > 0.f) { lo = max(0, (int)floorf((i - 1) / sc) - 1); hi = min(n_out - 1, (int)ceilf((i + 1) / sc) + 1); }
+}
 __global__ void __launch_bounds__(256)
-resize_bilinear_bwd_kernel(const float* __restrict__ gout, int ldgo, int H, int W, float* __restrict__ gin, int ldgi,
-                           int h, int w, int N, int C, float sy, float sx, float4 scale) {
+resize_bwd_x_kernel(const float* __restrict__ gout, int ldgo, int H, int W, float* __restrict__ tmp, int w, int N, int C, float sx) {
+  const long long total = (long long)N * H * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(i % w);
+    const long long row = i / w;                       // n * H + oy
+    int lo, hi;
+    resize_bwd_range(ix, sx, W, lo, hi);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ox = lo; ox <= hi; ++ox) {
+      const AxisTap tx = axis_tap(ox, w, sx);
+      const float wx = (tx.i0 == ix ? tx.l0 : 0.f) + (tx.i1 == ix ? tx.l1 : 0.f);
+      if (wx == 0.f) continue;
+      const float* gp = gout + ((size_t)row * W + ox) * ldgo;
+      for (int c = 0; c < C; ++c) acc[c] = fmaf(gp[c], wx, acc[c]);
+    }
+    float* o = tmp + (size_t)i * C;
+    for (int c = 0; c < C; ++c) o[c] = acc[c];
+  }
+}
+__global__ void __launch_bounds__(256)
+resize_bwd_y_kernel(const float* __restrict__ tmp, int H, float* __restrict__ gin, int ldgi, int h, int w, int N, int C, float sy,
+                    float4 scale) {
   const long long total = (long long)N * h * w;
   const float sc[4] = {scale.x, scale.y, scale.z, scale.w};
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ix = (int)(i % w);
     const long long t = i / w;
     const int iy = (int)(t % h), n = (int)(t / h);
-    int oy_lo = 0, oy_hi = H - 1, ox_lo = 0, ox_hi = W - 1;
-    if (sy > 0.f) { oy_lo = max(0, (int)floorf((iy - 1) / sy) - 1); oy_hi = min(H - 1, (int)ceilf((iy + 1) / sy) + 1); }
-    if (sx > 0.f) { ox_lo = max(0, (int)floorf((ix - 1) / sx) - 1); ox_hi = min(W - 1, (int)ceilf((ix + 1) / sx) + 1); }
+    int lo, hi;
+    resize_bwd_range(iy, sy, H, lo, hi);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+    for (int oy = lo; oy <= hi; ++oy) {
       const AxisTap ty = axis_tap(oy, h, sy);
-      if (ty.i0 != iy && ty.i1 != iy) continue;
       const float wy = (ty.i0 == iy ? ty.l0 : 0.f) + (ty.i1 == iy ? ty.l1 : 0.f);
-      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-        const AxisTap tx = axis_tap(ox, w, sx);
-        if (tx.i0 != ix && tx.i1 != ix) continue;
-        const float wx = (tx.i0 == ix ? tx.l0 : 0.f) + (tx.i1 == ix ? tx.l1 : 0.f);
-        const float* gp = gout + ((size_t)((size_t)n * H + oy) * W + ox) * ldgo;
-        const float wgt = wy * wx;
-        for (int c = 0; c < C; ++c) acc[c] = fmaf(gp[c], wgt, acc[c]);
-      }
+      if (wy == 0.f) continue;
+      const float* tp = tmp + ((size_t)((size_t)n * H + oy) * w + ix) * C;
+      for (int c = 0; c < C; ++c) acc[c] = fmaf(tp[c], wy, acc[c]);
     }
     float* o = gin + (size_t)i * ldgi;
     for (int c = 0; c < C; ++c) o[c] = acc[c] * sc[c];
@@ -265,7 +353,8 @@ static unsigned grid_for(long long total) {
 
 // number of pixel splits the weight gradient uses for this shape (the caller sizes the workspace with it)
 static int wgrad_splits(int Cin, int Cout, int taps, long long npix) {
-  const long long tiles = (long long)((Cin + upf::WG_BM - 1) / upf::WG_BM) * ((Cout + upf::WG_BN - 1) / upf::WG_BN) * taps;
+  const int bn = Cout > 64 ? 128 : 64;
+  const long long tiles = (long long)((Cin + 127) / 128) * ((Cout + bn - 1) / bn) * taps;
   long long s = (4 * UPF_NUM_SMS + tiles - 1) / tiles;
   const long long max_by_pix = (npix + 255) / 256;
   if (s > max_by_pix) s = max_by_pix;
@@ -274,12 +363,13 @@ static int wgrad_splits(int Cin, int Cout, int taps, long long npix) {
   return (int)s;
 }
 
+#define UPF_BIAS_SPLITS 1024
 extern "C" long long upf_conv2d_wgrad_workspace_elems(int N, int H, int W, int Cin, int Cout, int ksize, int stride, int dilation) {
   const int pad = ((ksize - 1) * dilation) / 2;
   const int Ho = (H + 2 * pad - dilation * (ksize - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dilation * (ksize - 1) - 1) / stride + 1;
   const int taps = ksize * ksize;
   const int s = wgrad_splits(Cin, Cout, taps, (long long)N * Ho * Wo);
-  return (long long)s * ((long long)taps * Cin * Cout + Cout);
+  return (long long)s * ((long long)taps * Cin * Cout) + (long long)UPF_BIAS_SPLITS * Cout;
 }
 
 extern "C" int upf_conv2d_wgrad(const float* x, int ldx, const float* grad_out, int ldg, float* grad_w, float* grad_bias,
@@ -296,11 +386,17 @@ extern "C" int upf_conv2d_wgrad(const float* x, int ldx, const float* grad_out, 
   const long long npix = (long long)N * Ho * Wo;
   const int splits = wgrad_splits(Cin, Cout, taps, npix);
   const long long pps = ((npix + splits - 1) / splits + WG_KP - 1) / WG_KP * WG_KP;
-  const int ci_tiles = (Cin + WG_BM - 1) / WG_BM, co_tiles = (Cout + WG_BN - 1) / WG_BN;
+  const int bn = Cout > 64 ? 128 : 64;
+  const int ci_tiles = (Cin + 127) / 128, co_tiles = (Cout + bn - 1) / bn;
   cudaStream_t st = (cudaStream_t)stream;
   const long long wn = (long long)taps * Cin * Cout;
-  conv_wgrad_kernel<<<dim3(ci_tiles * co_tiles, taps, splits), WG_NT, 0, st>>>(x, ldx, grad_out, ldg, workspace, N, H, W, Ho, Wo, Cin,
-                                                                              Cout, ksize, stride, dilation, pad, co_tiles, pps, npix);
+  const dim3 grid(ci_tiles * co_tiles, taps, splits);
+  if (bn == 128)
+    conv_wgrad_kernel<128, 128, 8, 8><<<grid, WG_NT, 0, st>>>(x, ldx, grad_out, ldg, workspace, N, H, W, Ho, Wo, Cin, Cout, ksize,
+                                                              stride, dilation, pad, co_tiles, pps, npix);
+  else
+    conv_wgrad_kernel<128, 64, 8, 4><<<grid, WG_NT, 0, st>>>(x, ldx, grad_out, ldg, workspace, N, H, W, Ho, Wo, Cin, Cout, ksize,
+                                                             stride, dilation, pad, co_tiles, pps, npix);
   int e = check_launch("conv_wgrad");
   if (e) return e;
   reduce_splits_kernel<<<grid_for(wn), 256, 0, st>>>(workspace, grad_w, wn, splits);
@@ -308,10 +404,16 @@ extern "C" int upf_conv2d_wgrad(const float* x, int ldx, const float* grad_out, 
   if (e) return e;
   if (grad_bias) {
     float* bpart = workspace + (size_t)splits * wn;
-    colsum_kernel<<<splits, 256, 0, st>>>(grad_out, ldg, bpart, Cout, pps, npix);
+    int cw = 1;
+    while (cw < Cout && cw < 256) cw <<= 1;               // channel lanes: power of two <= 256
+    int bs = (int)((npix + 255) / 256);                   // its own pixel split: the weight-gradient split can be 1
+    if (bs > UPF_BIAS_SPLITS) bs = UPF_BIAS_SPLITS;
+    if (bs < 1) bs = 1;
+    const long long bpps = (npix + bs - 1) / bs;
+    colsum_kernel<<<bs, 256, 0, st>>>(grad_out, ldg, bpart, Cout, cw, bpps, npix);
     e = check_launch("bias_colsum");
     if (e) return e;
-    reduce_splits_kernel<<<1, 256, 0, st>>>(bpart, grad_bias, Cout, splits);
+    reduce_splits_kernel<<<1, 256, 0, st>>>(bpart, grad_bias, Cout, bs);
     e = check_launch("bias_reduce");
   }
   return e;
@@ -358,14 +460,18 @@ extern "C" int upf_featnorm_bwd(const float* x, int ldx, const double* stats, co
   return check_launch("featnorm_bwd_apply");
 }
 
+extern "C" long long upf_resize_bilinear_bwd_workspace_elems(int N, int H, int w, int C) { return (long long)N * H * w * C; }
 extern "C" int upf_resize_bilinear_bwd(const float* grad_out, int ldgo, int H, int W, float* grad_in, int ldgi, int h, int w,
-                                       int N, int C, const float* scale_host, void* stream) {
+                                       int N, int C, const float* scale_host, float* workspace, void* stream) {
   using namespace upf;
-  UPF_REQUIRE(grad_out && grad_in, "resize_bwd: null tensor");
+  UPF_REQUIRE(grad_out && grad_in && workspace, "resize_bwd: null tensor");
   UPF_REQUIRE(N > 0 && H > 0 && W > 0 && h > 0 && w > 0 && C > 0 && C <= 4 && ldgo >= C && ldgi >= C, "resize_bwd: bad shape");
   float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
   if (scale_host) sc = make_float4(scale_host[0], scale_host[1], scale_host[2], scale_host[3]);
-  resize_bilinear_bwd_kernel<<<grid_for((long long)N * h * w), 256, 0, (cudaStream_t)stream>>>(
-      grad_out, ldgo, H, W, grad_in, ldgi, h, w, N, C, host_ac_scale(h, H), host_ac_scale(w, W), sc);
-  return check_launch("resize_bwd");
+  cudaStream_t st = (cudaStream_t)stream;
+  resize_bwd_x_kernel<<<grid_for((long long)N * H * w), 256, 0, st>>>(grad_out, ldgo, H, W, workspace, w, N, C, host_ac_scale(w, W));
+  int e = check_launch("resize_bwd_x");
+  if (e) return e;
+  resize_bwd_y_kernel<<<grid_for((long long)N * h * w), 256, 0, st>>>(workspace, H, grad_in, ldgi, h, w, N, C, host_ac_scale(h, H), sc);
+  return check_launch("resize_bwd_y");
 }

@@ -214,7 +214,9 @@ def k_resize_bwd(grad_out, grad_in, scale=None):
     sc = None
     if scale is not None:
         sc = (ctypes.c_float * 4)(*([float(v) for v in scale] + [1.0] * (4 - len(scale))))
-    _ext.check(_lib().upf_resize_bilinear_bwd(g.ptr(), g.ld, g.H, g.W, gi.ptr(), gi.ld, gi.H, gi.W, g.N, g.C, sc, _stream()),
+    lib = _lib()
+    ws = torch.empty(lib.upf_resize_bilinear_bwd_workspace_elems(g.N, g.H, gi.W, g.C), dtype=torch.float32, device=g.buf.device)
+    _ext.check(lib.upf_resize_bilinear_bwd(g.ptr(), g.ld, g.H, g.W, gi.ptr(), gi.ld, gi.H, gi.W, g.N, g.C, sc, _p(ws), _stream()),
                "resize_bilinear_bwd")
 
 
