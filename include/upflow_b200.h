@@ -191,6 +191,13 @@ int upf_conv2d_wgrad(const float* x, int ldx, const float* grad_out, int ldg, fl
                      float* workspace, int N, int H, int W, int Cin, int Cout, int ksize, int stride, int dilation,
                      void* stream);
 
+/* the same on the tensor cores (stride 1; TF32 operands, fp32 accumulation): both operands are transposed into planar,
+ * zero-padded form in `workspace` (upf_conv2d_wgrad_tc_workspace_elems floats, 16-byte aligned), where a tap is a
+ * constant shift of the K index, and the nine tap GEMMs run as one launch of the convolution kernel. */
+long long upf_conv2d_wgrad_tc_workspace_elems(int N, int H, int W, int Cin, int Cout, int ksize, int dilation);
+int upf_conv2d_wgrad_tc(const float* x, int ldx, const float* grad_out, int ldg, float* grad_w, float* grad_bias,
+                        float* workspace, int N, int H, int W, int Cin, int Cout, int ksize, int dilation, void* stream);
+
 /* pointwise ops on [npix][C] pitched tensors.  op 0: out = b * (a > 0 ? 1 : slope)  (LeakyReLU backward from the
  * saved output a and the incoming gradient b); op 1: out = sigmoid(a); op 2: out = b * a * (1 - a) (sigmoid
  * backward from the saved output a). */

@@ -342,6 +342,47 @@ resize_bwd_y_kernel(const float* __restrict__ tmp, int H, float* __restrict__ gi
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ tensor-core wgrad
+// Both operands of dW[tap][ci][co] = sum_p X[p (+) tap][ci] * G[p][co] are pixel-major, i.e. their K index (the pixel)
+// is the slow one.  They are transposed once per convolution into PLANAR, ZERO-PADDED form
+//     XT[ci][k], GT[co][k],  k = (n*(H+2pad) + y+pad)*(W+2pad) + x+pad,
+// where a tap is a constant shift of k (the padding absorbs it: GT is zero there), and the nine tap GEMMs run as ONE
+// launch of the tcgen05 kernel of conv_tc.cu with the taps as its "images" (M = Cin, N = Cout, K = k, cluster split-K).
+// A TMA box row must start 16-byte aligned, so only the VERTICAL part of the shift ((ky-1)*dil rows of W+2pad rounded
+// up to 4 elements) is applied to XT's coordinate; the horizontal part is baked into three copies of GT written at
+// k + (kx-1)*dil.
+__global__ void __launch_bounds__(256)
+nhwc_to_planar_padded_kernel(const float* __restrict__ src, int ld, int C, float* __restrict__ dst, long long Kp, long long P,
+                             int H, int W, int pad, int Wp, int shift) {
+  __shared__ float tile[32][33];
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const long long p = p0 + i;
+    const int c = c0 + tx;
+    tile[i][tx] = (p < P && c < C) ? __ldg(src + (size_t)p * ld + c) : 0.f;
+  }
+  __syncthreads();
+  const long long p = p0 + tx;
+  if (p < P) {
+    const int Hp = H + 2 * pad;
+    const long long hw = (long long)H * W;
+    const long long n = p / hw;
+    const int r = (int)(p - n * hw);
+    const int y = r / W, x = r - y * W;
+    const long long k = (n * Hp + y + pad) * Wp + x + pad + shift;
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i;
+      if (c < C) dst[(size_t)c * Kp + k] = tile[tx][i];
+    }
+  }
+}
+
+int conv_tc_wgrad_gemm(const float* xt, int ldk, const float* gt_packed, const float* zero_bias, float* gw, int taps,
+                       int Cin, int Cout, int K, const int* koffs, const int* wsel, cudaStream_t st);
+
 static unsigned grid_for(long long total) {
   long long b = (total + 255) / 256;
   if (b > UPF_NUM_SMS * 16) b = UPF_NUM_SMS * 16;
@@ -474,4 +515,70 @@ extern "C" int upf_resize_bilinear_bwd(const float* grad_out, int ldgo, int H, i
   if (e) return e;
   resize_bwd_y_kernel<<<grid_for((long long)N * h * w), 256, 0, st>>>(workspace, H, grad_in, ldgi, h, w, N, C, host_ac_scale(h, H), sc);
   return check_launch("resize_bwd_y");
+}
+
+// ---- tensor-core weight gradient (stride 1): see nhwc_to_planar_padded_kernel
+static int wgrad_tc_wp(int W, int ks, int dil) { return (W + (ks - 1) * dil + 3) / 4 * 4; }   // padded row, multiple of 4
+static long long wgrad_tc_kp(int N, int H, int W, int ks, int dil) {
+  const int pad = ((ks - 1) * dil) / 2;
+  const long long K = (long long)N * (H + 2 * pad) * wgrad_tc_wp(W, ks, dil);
+  return (K + 31) / 32 * 32;
+}
+extern "C" long long upf_conv2d_wgrad_tc_workspace_elems(int N, int H, int W, int Cin, int Cout, int ksize, int dilation) {
+  const long long Kp = wgrad_tc_kp(N, H, W, ksize, dilation);
+  const long long cout_pad = (Cout + 15) / 16 * 16;
+  return (long long)Cin * Kp + 3 * cout_pad * Kp + cout_pad + (long long)UPF_BIAS_SPLITS * Cout + 64;
+}
+extern "C" int upf_conv2d_wgrad_tc(const float* x, int ldx, const float* grad_out, int ldg, float* grad_w, float* grad_bias,
+                                   float* workspace, int N, int H, int W, int Cin, int Cout, int ksize, int dilation,
+                                   void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(x && grad_out && grad_w && workspace, "wgrad_tc: null tensor");
+  UPF_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (ksize == 1 || ksize == 3) && dilation >= 1, "wgrad_tc: bad shape");
+  UPF_REQUIRE(ldx >= Cin && ldg >= Cout && aligned16(workspace), "wgrad_tc: bad pitch / workspace alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pad = ((ksize - 1) * dilation) / 2, taps = ksize * ksize;
+  const int Wp = wgrad_tc_wp(W, ksize, dilation);
+  const long long Kp = wgrad_tc_kp(N, H, W, ksize, dilation);
+  UPF_REQUIRE(Kp < (1ll << 31), "wgrad_tc: padded pixel count too large");
+  const long long cout_pad = (Cout + 15) / 16 * 16;
+  const long long P = (long long)N * H * W;
+  const int ncopies = ksize == 1 ? 1 : 3;
+  float* xt = workspace;
+  float* gt = xt + (size_t)Cin * Kp;                      // [3][cout_pad][Kp]: G written at k + (kx-1)*dil
+  float* zb = gt + (size_t)3 * cout_pad * Kp;
+  float* bpart = zb + cout_pad;
+  cudaError_t ce = cudaMemsetAsync(workspace, 0, ((size_t)Cin * Kp + (size_t)3 * cout_pad * Kp + cout_pad) * sizeof(float), st);
+  if (ce != cudaSuccess) { set_error("wgrad_tc memset: %s", cudaGetErrorString(ce)); return (int)ce; }
+  const unsigned ptiles = (unsigned)((P + 31) / 32);
+  nhwc_to_planar_padded_kernel<<<dim3(ptiles, (Cin + 31) / 32), 256, 0, st>>>(x, ldx, Cin, xt, Kp, P, H, W, pad, Wp, 0);
+  int e = check_launch("wgrad_tc_transpose_x");
+  if (e) return e;
+  for (int c = 0; c < ncopies; ++c) {
+    nhwc_to_planar_padded_kernel<<<dim3(ptiles, (Cout + 31) / 32), 256, 0, st>>>(grad_out, ldg, Cout, gt + (size_t)c * cout_pad * Kp, Kp, P,
+                                                                                  H, W, pad, Wp, ksize == 1 ? 0 : (c - 1) * dilation);
+    e = check_launch("wgrad_tc_transpose_g");
+    if (e) return e;
+  }
+  int koffs[9], wsel[9];
+  for (int t = 0; t < taps; ++t) {
+    const int ky = t / ksize, kx = t % ksize;
+    koffs[t] = ksize == 1 ? 0 : (ky - 1) * dilation * Wp;          // multiple of 4
+    wsel[t] = ksize == 1 ? 0 : kx;
+  }
+  e = conv_tc_wgrad_gemm(xt, (int)Kp, gt, zb, grad_w, taps, Cin, Cout, (int)Kp, koffs, wsel, st);
+  if (e) return e;
+  if (grad_bias) {
+    int cw = 1;
+    while (cw < Cout && cw < 256) cw <<= 1;
+    int bs = (int)((P + 255) / 256);
+    if (bs > UPF_BIAS_SPLITS) bs = UPF_BIAS_SPLITS;
+    const long long bpps = (P + bs - 1) / bs;
+    colsum_kernel<<<bs, 256, 0, st>>>(grad_out, ldg, bpart, Cout, cw, bpps, P);
+    e = check_launch("bias_colsum");
+    if (e) return e;
+    reduce_splits_kernel<<<1, 256, 0, st>>>(bpart, grad_bias, Cout, bs);
+    e = check_launch("bias_reduce");
+  }
+  return e;
 }

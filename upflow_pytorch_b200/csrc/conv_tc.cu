@@ -59,6 +59,11 @@ struct TcParams {
   // one box is walked row by row (~10 ns per 128-byte row, measured), independent boxes proceed concurrently
   int bw, bh, nbx, nby, b_rows, nbb;
   float slope;
+  // weight-gradient mode (backward.cu): the "images" are the taps of ONE planar operand -- image n reads the same
+  // tensor with its K (channel) coordinate shifted by koffs[n]
+  int wgrad;
+  int koffs[9];               // multiples of 4 elements: a box row must start 16-byte aligned
+  int wsel[9];                // which of the (pre-shifted) copies of the other operand tap n multiplies
 };
 
 // bias + LeakyReLU (+ residual) and the store of 4 consecutive output channels of one pixel
@@ -156,12 +161,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const uint32_t b_dst = a_dst + TC_A_BYTES;
         const uint32_t fb = smem_u32(&full[s]);
         mbar_expect_tx(fb, TC_A_BYTES + b_bytes);
+        const int kc = kb * TC_KC + (p.wgrad ? p.koffs[n] : 0);
+        const int nn = p.wgrad ? 0 : n;
         for (int jy = 0; jy < p.nby; ++jy)
           for (int jx = 0; jx < p.nbx; ++jx)
-            tma_load_4d(a_dst + (uint32_t)((jy * p.bh * p.TW + jx * p.bw) * 128), &map_x, fb, kb * TC_KC,
-                        cx + jx * p.bw * p.stride, cy + jy * p.bh * p.stride, n);
+            tma_load_4d(a_dst + (uint32_t)((jy * p.bh * p.TW + jx * p.bw) * 128), &map_x, fb, kc,
+                        cx + jx * p.bw * p.stride, cy + jy * p.bh * p.stride, nn);
         for (int jb = 0; jb < p.nbb; ++jb)
-          tma_load_3d(b_dst + (uint32_t)(jb * p.b_rows * 128), &map_w, fb, kb * TC_KC, co0 + jb * p.b_rows, tap);
+          tma_load_3d(b_dst + (uint32_t)(jb * p.b_rows * 128), &map_w, fb, kb * TC_KC, co0 + jb * p.b_rows, p.wgrad ? p.wsel[n] : tap);
       }
     }
     __syncwarp();
@@ -357,12 +364,16 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
                    const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
                    float slope, cudaStream_t st, int* taken);
 
+static const int* g_tc_koffs = nullptr;      // set by conv_tc_wgrad_gemm around its call (host, single-threaded use)
+static const int* g_tc_wsel = nullptr;
+
 int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
                   const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
                   float slope, cudaStream_t st) {
+  const int* koffs = g_tc_koffs;
   UPF_REQUIRE((ldx % 4) == 0 && aligned16(x) && aligned16(w_packed), "conv_tc: input pitch/pointer must be 16-byte aligned");
   UPF_REQUIRE(stride == 1 || stride == 2, "conv_tc: stride %d not in {1,2}", stride);
-  {
+  if (!koffs) {
     // fine pyramid levels, 3x3 / dilation <= 4: the halo kernel loads the activation tile once for all nine taps
     int taken = 0;
     const int e0 = conv2d_fwd_win(x, ldx, w_packed, bias, out, ldo, res, ldr, N, H, W, Cin, Cout, ks, stride, dil, slope, st, &taken);
@@ -392,20 +403,21 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   while (BN % b_rows) b_rows -= 8;           // BN is a multiple of 16
   CUtensorMap mx, mw;
   {
-    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(koffs ? 1 : N)};
     const cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
     const cuuint32_t box[4] = {TC_KC, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), 1};
     const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    MapKey key{x, ldx, ((long long)H << 32) | (unsigned)W, ((long long)N << 32) | (unsigned)Cin, (bw * 1000 + bh) * 4 + stride, 4};
+    MapKey key{x, ldx, ((long long)H << 32) | (unsigned)W, ((long long)(koffs ? 1 : N) << 32) | (unsigned)Cin, (bw * 1000 + bh) * 4 + stride, 4};
     int e = encode_cached(key, &mx, 4, const_cast<float*>(x), dims, strides, box, estr);
     if (e) return e;
   }
   {
-    const cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)taps};
+    const int wtaps = koffs ? 3 : taps;      // weight-gradient mode: three pre-shifted copies of the second operand
+    const cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)wtaps};
     const cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 4, (cuuint64_t)cin_pad * cout_pad * 4};
     const cuuint32_t box[3] = {TC_KC, (cuuint32_t)b_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    MapKey key{w_packed, cin_pad, b_rows, taps, cout_pad, 3};
+    MapKey key{w_packed, cin_pad, b_rows, wtaps, cout_pad, 3};
     int e = encode_cached(key, &mw, 3, const_cast<float*>(w_packed), dims, strides, box, estr);
     if (e) return e;
   }
@@ -417,6 +429,8 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   p.ks = ks; p.dil = dil; p.stride = stride; p.kblocks = kblocks;
   p.bw = bw; p.bh = bh; p.nbx = TW / bw; p.nby = TH / bh; p.b_rows = b_rows; p.nbb = BN / b_rows;
   p.slope = slope;
+  p.wgrad = koffs ? 1 : 0;
+  for (int i = 0; i < 9; ++i) { p.koffs[i] = (koffs && i < N) ? koffs[i] : 0; p.wsel[i] = (koffs && g_tc_wsel && i < N) ? g_tc_wsel[i] : 0; }
   p.tmem_cols = BN <= 16 ? 32 : (BN <= 32 ? 64 : (BN <= 64 ? 128 : 256));   // two accumulators (one per MMA issuer)
   const int stage_bytes = TC_A_BYTES + ((BN * 128 + 1023) & ~1023);
   const long long tiles = (long long)p.tiles_x * p.tiles_y * N;
@@ -426,6 +440,7 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   const int iters_all = taps * kblocks;
   int splits = 1;
   while (splits < 8 && ctas * splits * 2 <= UPF_NUM_SMS && iters_all / (splits * 2) >= 3) splits *= 2;   // stay within one wave
+  if (koffs) { splits = 8; while (splits > 1 && iters_all / splits < 4) splits >>= 1; }   // weight gradient: K is the pixel index, 10^4..10^5 long
   int ips = (iters_all + splits - 1) / splits;
   while (splits > 1 && (splits - 1) * ips >= iters_all) { splits >>= 1; ips = (iters_all + splits - 1) / splits; }   // no empty CTA
   // stages: two CTAs per SM when the grid is large (epilogue/main-loop overlap across CTAs); a single
@@ -463,6 +478,16 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel, mx, mw, p);
   if (e != cudaSuccess) { set_error("conv_tc launch: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return (int)e; }
   return check_launch("conv_tc");
+}
+
+// dW[tap][ci][co] = sum_k XT[ci][k + koffs[tap]] * GT[wsel[tap]][co][k]  (backward.cu): the tensor-core GEMM of this file with the
+// taps as "images" (out is [taps][Cin][Cout]), M = Cin, K = the padded pixel index, cluster split-K
+int conv_tc_wgrad_gemm(const float* xt, int ldk, const float* gt_packed, const float* zero_bias, float* gw, int taps,
+                       int Cin, int Cout, int K, const int* koffs, const int* wsel, cudaStream_t st) {
+  g_tc_koffs = koffs; g_tc_wsel = wsel;
+  const int e = conv2d_fwd_tc(xt, ldk, gt_packed, zero_bias, gw, Cout, nullptr, 0, taps, 1, Cin, K, Cout, 1, 1, 1, 1.0f, st);
+  g_tc_koffs = nullptr; g_tc_wsel = nullptr;
+  return e;
 }
 
 }  // namespace upf

@@ -180,11 +180,19 @@ def k_conv(x, weight, bias, out, ksize, stride=1, dilation=1, slope=LRELU_SLOPE,
                                      float(slope), int(precision), _stream()), "conv2d_fwd")
 
 
-def k_conv_wgrad(x, grad_out, ksize, stride=1, dilation=1, want_bias=True):
+def k_conv_wgrad(x, grad_out, ksize, stride=1, dilation=1, want_bias=True, tensor_cores=False):
     """Weight gradient [k*k, Cin, Cout] and bias gradient [Cout] of conv() from its input and the gradient wrt its
-    PRE-activation output (both pixel-major)."""
+    PRE-activation output (both pixel-major).  tensor_cores: TF32 tcgen05 GEMM (stride 1), else fp32 SIMT."""
     x, g = _as_slice(x), _as_slice(grad_out)
     lib = _lib()
+    if tensor_cores and stride == 1:
+        n = lib.upf_conv2d_wgrad_tc_workspace_elems(x.N, x.H, x.W, x.C, g.C, ksize, dilation)
+        ws = torch.empty(n, dtype=torch.float32, device=x.buf.device)
+        gw = torch.empty(ksize * ksize, x.C, g.C, dtype=torch.float32, device=x.buf.device)
+        gb = torch.empty(g.C, dtype=torch.float32, device=x.buf.device) if want_bias else None
+        _ext.check(lib.upf_conv2d_wgrad_tc(x.ptr(), x.ld, g.ptr(), g.ld, _p(gw), _p(gb), _p(ws), x.N, x.H, x.W, x.C, g.C,
+                                           ksize, dilation, _stream()), "conv2d_wgrad_tc")
+        return gw, gb
     n = lib.upf_conv2d_wgrad_workspace_elems(x.N, x.H, x.W, x.C, g.C, ksize, stride, dilation)
     ws = torch.empty(n, dtype=torch.float32, device=x.buf.device)
     gw = torch.empty(ksize * ksize, x.C, g.C, dtype=torch.float32, device=x.buf.device)
@@ -539,7 +547,7 @@ class _ConvFn(torch.autograd.Function):
         gps = Slice(gp, 0, Cout)
         gx = gw = gb = None
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            gw_t, gb = k_conv_wgrad(a, gps, ks, stride, dilation, want_bias=True)
+            gw_t, gb = k_conv_wgrad(a, gps, ks, stride, dilation, want_bias=True, tensor_cores=tc)
             gw = gw_t.reshape(ks, ks, Cin, Cout).permute(3, 2, 0, 1).contiguous()
         if ctx.needs_input_grad[0]:
             w_d = weight.detach().flip(2, 3).transpose(0, 1).contiguous()         # [Cin, Cout, k, k]
