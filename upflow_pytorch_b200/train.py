@@ -74,23 +74,60 @@ def total_loss(output_dict):
 
 
 class Trainer:
-    """scripts/simple_train.py:118-146, data-parallel."""
+    """scripts/simple_train.py:118-146, data-parallel.
 
-    def __init__(self, net, lr=1e-4, weight_decay=1e-4, group=None):
+    use_cuda_graph=True captures zero-grad + forward + losses + backward of one batch SHAPE in a CUDA graph (the
+    eager step issues ~3300 launches from Python, 30 % of its wall time); the gradient all-reduce and the Adam update
+    stay outside the graph.  The batch tensors are copied into the graph's static inputs on every step."""
+
+    def __init__(self, net, lr=1e-4, weight_decay=1e-4, group=None, use_cuda_graph=False):
         self.net = net
         self.group = group
         self.grads = FlatGradients(net.parameters())
         self.optimizer = torch.optim.Adam(self.grads.params, lr=lr, amsgrad=True, weight_decay=weight_decay)
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
+        self.graph_launches = 0
+
+    def _forward_backward(self, batch):
+        self.grads.zero()
+        out = self.net(batch)
+        loss = total_loss(out)
+        loss.backward()
+        return loss.detach()
+
+    def _graphed(self, batch):
+        key = tuple((k, tuple(v.shape)) for k, v in sorted(batch.items()) if torch.is_tensor(v))
+        g = self._graphs.get(key)
+        if g is None:
+            static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                      # warm-up off the capture stream (torch.cuda.graphs recipe)
+                for _ in range(2):
+                    self._forward_backward(static)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            from . import _ext
+            graph = torch.cuda.CUDAGraph()
+            n0 = _ext.launch_count()
+            with torch.cuda.graph(graph):
+                loss = self._forward_backward(static)
+            self.graph_launches = _ext.launch_count() - n0     # library kernels inside one replay
+            g = self._graphs[key] = (graph, static, loss)
+        graph, static, loss = g
+        for k, v in batch.items():
+            if torch.is_tensor(v):
+                static[k].copy_(v, non_blocking=True)
+        graph.replay()
+        return loss
 
     def train_step(self, batch):
         """batch: the LOCAL shard (dict with im1, im2 [, im1_raw, im2_raw, start]).  Returns the local loss tensor."""
         self.net.train()
-        self.grads.zero()
         batch = dict(batch)
         batch["if_loss"] = True
-        out = self.net(batch)
-        loss = total_loss(out)
-        loss.backward()
+        loss = self._graphed(batch) if self.use_cuda_graph else self._forward_backward(batch)
         self.grads.all_reduce_mean(self.group)
         self.optimizer.step()
-        return loss.detach()
+        return loss.clone() if self.use_cuda_graph else loss
