@@ -446,17 +446,17 @@ extern "C" int upf_corr_lrelu_fwd(const float* f1, int ld1, const float* f2, int
   UPF_REQUIRE((stats1 == nullptr) == (stats2 == nullptr), "corr: give both stats or neither");
   cudaStream_t st = (cudaStream_t)stream;
   UPF_REQUIRE(max_disp >= 1 && max_disp <= 6, "corr: max_disp %d not in 1..6", max_disp);
-  // coarse pyramid levels: too few 8x32 tiles to occupy the chip (and up to 7 channel passes each)
-  // (the choice depends on the IMAGE size only, never on N: an image must give the same bits in any batch)
-  if ((long long)H * W <= CORR_SMALL_MAX_PIX / 2 && C <= 1024)
-    return launch_corr_small(f1, ld1, f2, ld2, out, ldo, N, H, W, C, max_disp, stats1, stats2, f2_batch_shift, slope, st);
   {
-    // large images, d <= 4: persistent warp-specialised kernel (loads overlap the FMA loop), corr_pipe.cu
+    // enough 32x8 tiles per image, d <= 6: persistent warp-specialised kernel (loads overlap the FMA loop), corr_pipe.cu
+    // (the choice depends on the IMAGE size only, never on N: an image must give the same bits in any batch)
     int taken = 0;
     const int e = launch_corr_pipe(f1, ld1, f2, ld2, out, ldo, N, H, W, C, max_disp, stats1, stats2, f2_batch_shift, slope,
                                    st, &taken);
     if (e != 0 || taken) return e;
   }
+  // coarse pyramid levels: too few tiles to occupy the chip (and up to 7 channel passes each)
+  if ((long long)H * W <= CORR_SMALL_MAX_PIX / 2 && C <= 1024)
+    return launch_corr_small(f1, ld1, f2, ld2, out, ldo, N, H, W, C, max_disp, stats1, stats2, f2_batch_shift, slope, st);
   switch (max_disp) {
     case 1: return launch_corr_fwd<1>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);
     case 2: return launch_corr_fwd<2>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);
