@@ -184,3 +184,22 @@ def test_kitti_evaluation_helpers(tmp_path):
     f2, m2 = E.read_png_flow(p)
     assert f2.shape == (2, 7, 9) and m2.shape == (1, 7, 9)
     assert np.array_equal(np.transpose(f2, [1, 2, 0]), flow) and np.array_equal(m2[0], valid.astype(np.uint8))
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py contract on the CPU tier: `--impl reference` runs the reference's CPU path (the port) and prints
+    exactly one JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload",
+                        "small_256x256_b1", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["value"] > 0 and d["config"]["workload"] == "small_256x256_b1"
