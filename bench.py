@@ -308,7 +308,7 @@ def _main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="kitti_375x1242_b1", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "tf32x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-graph", action="store_true", help="training workload: eager launches instead of a CUDA graph")
     args = ap.parse_args()

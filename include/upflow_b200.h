@@ -207,6 +207,13 @@ int upf_conv2d_wgrad_tc(const float* x, int ldx, const float* grad_out, int ldg,
 int upf_pointwise(int op, const float* a, int lda, const float* b, int ldb, float* out, int ldo, long long npix,
                   int C, float slope, void* stream);
 
+/* 3xTF32 convolutions (engine precision "tf32x3": fp32-class results on the tensor cores).  x = hi + lo with hi = x
+ * truncated to TF32 (what tcgen05 kind::tf32 reads from an fp32 operand) and lo = x - hi; the engine accumulates
+ * conv(lo, w) + conv(x, w_lo) + conv(x, w) + bias with upf_conv2d_fwd (slope 1, residual chaining) and finishes with
+ *   out = lrelu(t) (+ residual);  out_lo = out - trunc_tf32(out)        (t == NULL: only the split of `out`). */
+int upf_act_split(const float* t, int ldt, const float* residual, int ldr, float* out, int ldo, float* out_lo, int ldlo,
+                  long long npix, int C, float slope, void* stream);
+
 /* sgu_model.forward's blend (model/upflow.py:88) as a differentiable piece: out_c = w_c*(1-m) + f_c*m, c in {0,1};
  * backward: gw_c = g_c*(1-m), gf_c = g_c*m, gm = sum_c g_c*(f_c - w_c). */
 int upf_blend_fwd(const float* w, int ldw, const float* f, int ldf, const float* m, int ldm, float* out, int ldo,

@@ -5,6 +5,7 @@ python bench.py --steps 50 --warmup 5 > gpurun_out/final/bench_kitti_b1.json 2> 
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/final/bench_reference_arm.json 2> gpurun_out/final/bench_reference_arm.err
 python bench.py --steps 20 --warmup 3 --workload sintel_436x1024_b8 --no-cpu-baseline > gpurun_out/final/bench_sintel_b8.json 2> gpurun_out/final/bench_sintel_b8.err
 python bench.py --steps 10 --warmup 3 --workload hd_1080x1920_b2 --no-cpu-baseline > gpurun_out/final/bench_hd_b2.json 2> gpurun_out/final/bench_hd_b2.err
+python bench.py --steps 20 --warmup 3 --precision tf32x3 --no-cpu-baseline > gpurun_out/final/bench_kitti_b1_tf32x3.json 2> gpurun_out/final/bench_kitti_b1_tf32x3.err
 python bench.py --steps 8 --warmup 3 --workload train_256x832_b4 > gpurun_out/final/bench_train_b4.json 2> gpurun_out/final/bench_train_b4.err
 python tools/profile_step.py > gpurun_out/final/launch_table_kitti_events.txt 2>&1
 python tools/time_corr.py > gpurun_out/final/time_corr.txt 2>&1

@@ -383,6 +383,30 @@ nhwc_to_planar_padded_kernel(const float* __restrict__ src, int ld, int C, float
 int conv_tc_wgrad_gemm(const float* xt, int ldk, const float* gt_packed, const float* zero_bias, float* gw, int taps,
                        int Cin, int Cout, int K, const int* koffs, const int* wsel, cudaStream_t st);
 
+
+// ---- 3xTF32 support (engine precision "tf32x3"): an fp32 value x is hi + lo with hi = x truncated to TF32 (what
+// tcgen05 kind::tf32 reads) and lo = x - hi (13 significant bits).  conv(x,w) ~ hi*whi + lo*whi + hi*wlo, three
+// tensor-core passes accumulated before the activation.
+// out = lrelu(t) (+ res);  out_lo = out - trunc_tf32(out)   (t == nullptr: only the split of `out`)
+__global__ void __launch_bounds__(256)
+act_split_kernel(const float* __restrict__ t, int ldt, const float* __restrict__ res, int ldr, float* __restrict__ out, int ldo,
+                 float* __restrict__ lo, int ldlo, long long npix, int C, float slope) {
+  const long long total = npix * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / C;
+    const int c = (int)(i - p * C);
+    float v;
+    if (t) {
+      v = lrelu(t[(size_t)p * ldt + c], slope);
+      if (res) v += res[(size_t)p * ldr + c];
+      out[(size_t)p * ldo + c] = v;
+    } else {
+      v = out[(size_t)p * ldo + c];
+    }
+    if (lo) lo[(size_t)p * ldlo + c] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  }
+}
+
 static unsigned grid_for(long long total) {
   long long b = (total + 255) / 256;
   if (b > UPF_NUM_SMS * 16) b = UPF_NUM_SMS * 16;
@@ -581,4 +605,13 @@ extern "C" int upf_conv2d_wgrad_tc(const float* x, int ldx, const float* grad_ou
     e = check_launch("bias_reduce");
   }
   return e;
+}
+
+extern "C" int upf_act_split(const float* t, int ldt, const float* residual, int ldr, float* out, int ldo, float* out_lo, int ldlo,
+                             long long npix, int C, float slope, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(out && npix > 0 && C > 0 && ldo >= C && (!t || ldt >= C) && (!out_lo || ldlo >= C) && (!residual || ldr >= C),
+              "act_split: bad argument");
+  act_split_kernel<<<grid_for(npix * C), 256, 0, (cudaStream_t)stream>>>(t, ldt, residual, ldr, out, ldo, out_lo, ldlo, npix, C, slope);
+  return check_launch("act_split");
 }

@@ -20,7 +20,7 @@ _PRECISION = {"mode": _ext.CONV_FP32}
 
 def set_conv_precision(mode):
     """'fp32' (SIMT, strict) or 'tf32' (tcgen05 tensor cores) for module-level convs."""
-    _PRECISION["mode"] = {"fp32": _ext.CONV_FP32, "tf32": _ext.CONV_TF32}[mode]
+    _PRECISION["mode"] = {"fp32": _ext.CONV_FP32, "tf32": _ext.CONV_TF32, "tf32x3": _ext.CONV_TF32}[mode]
 
 
 class _ConvBlock(nn.Sequential):

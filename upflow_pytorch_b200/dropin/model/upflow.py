@@ -169,7 +169,8 @@ class UPFlow_net(tools.abstract_model):
             return UPFlow_net(self)
 
     # extra, non-reference knobs of the B200 build (class attributes so `config` stays identical)
-    conv_precision = "tf32"      # 'tf32' = tcgen05 tensor cores (what cuDNN does by default), 'fp32' = strict SIMT
+    conv_precision = "tf32"      # 'tf32' = tcgen05 tensor cores (what cuDNN does by default), 'tf32x3' = three TF32 passes
+                                 # per conv (fp32-class results, 3.8x the time), 'fp32' = strict SIMT (18x the time)
     use_cuda_graph = True        # replay one captured graph per input shape (inference has no host decisions)
 
     def __init__(self, conf: config):

@@ -58,9 +58,9 @@ EXPAND_MIN_PIXELS = 5000     # ... on images with at least this many pixels (bel
 
 
 class ConvSpec:
-    __slots__ = ("w", "w_tc", "bias", "cin", "cout", "k", "stride", "dil", "slope", "w_exp", "zero_bias")
+    __slots__ = ("w", "w_tc", "bias", "cin", "cout", "k", "stride", "dil", "slope", "w_exp", "zero_bias", "w_lo_tc", "zero_b")
 
-    def __init__(self, weight, bias, stride=1, dil=1, relu=True, in_slots=None, cin_total=None, tc=True):
+    def __init__(self, weight, bias, stride=1, dil=1, relu=True, in_slots=None, cin_total=None, tc=True, x3=False):
         self.cout, _, self.k, _ = weight.shape
         self.cin = cin_total or weight.shape[1]
         self.stride, self.dil = stride, dil
@@ -70,8 +70,15 @@ class ConvSpec:
         self.bias = bias.detach().float().contiguous()
         # few output channels: Y = 1x1 conv with 9*Cout outputs (one N<=80 MMA per K step instead of nine N=16 ones),
         # then upf_conv3x3_tap_combine gathers the nine shifted slices
+        # 3xTF32: the low part of the weights (w - w truncated to TF32), packed like w
+        self.w_lo_tc = None
+        if x3 and self.w_tc is not None:
+            w32 = weight.detach().float().contiguous()
+            w_hi = (w32.view(torch.int32) & ~0x1FFF).view(torch.float32)
+            self.w_lo_tc = ops.pack_conv_weight(w32 - w_hi, in_slots, cin_total, tc=True)[1]
+            self.zero_b = torch.zeros(self.cout, dtype=torch.float32, device=weight.device)
         self.w_exp = None
-        if self.w_tc is not None and self.k == 3 and stride == 1 and self.cout <= EXPAND_MAX_COUT:
+        if not x3 and self.w_tc is not None and self.k == 3 and stride == 1 and self.cout <= EXPAND_MAX_COUT:
             self.w_exp = ops.pack_conv_weight(ops.expand_taps_weight(weight), in_slots, cin_total, tc=True)[1]
             self.zero_bias = torch.zeros(9 * self.cout, dtype=torch.float32, device=weight.device)
 
@@ -84,8 +91,15 @@ class DecoderEngine:
             raise RuntimeError("DecoderEngine needs a CUDA device: the decoder path has no CPU implementation")
         _ext.load()
         self.device = torch.device(device)
+        if precision not in ("tf32", "fp32", "tf32x3"):
+            raise ValueError("precision must be 'tf32', 'tf32x3' or 'fp32'")
         self.precision = precision
-        self.tc = precision == "tf32"
+        self.tc = precision in ("tf32", "tf32x3")
+        # 'tf32x3': every tensor-core convolution as three TF32 passes (hi*hi + lo*hi + hi*lo) accumulated before the
+        # activation -- fp32-class results (2^-21) at a third of the tensor-core rate; every convolution input keeps a
+        # "low part" twin buffer (x - x truncated to TF32) that the producing kernel's output is split into
+        self.x3 = precision == "tf32x3"
+        self._lo_bufs = {}
         self.align_corners = bool(align_corners)
         self.use_sgu = use_sgu
         # 1.0 = the reference's `mask >= 1.0` (model/pwc_modules.py:206); 0.9999 = diagnostic robust mask
@@ -104,7 +118,7 @@ class DecoderEngine:
         tc = self.tc
 
         def spec(key, **kw):
-            return ConvSpec(g(key + ".0.weight"), g(key + ".0.bias"), tc=tc, **kw)
+            return ConvSpec(g(key + ".0.weight"), g(key + ".0.bias"), tc=tc, x3=self.x3, **kw)
 
         self.enc = []
         for l in range(6):
@@ -151,8 +165,35 @@ class DecoderEngine:
             self._side = torch.cuda.Stream(device=self.device)
         return self._side
 
+    def _lo(self, buf):
+        """the low-part twin of a buffer (tf32x3 mode)"""
+        lo = self._lo_bufs.get(id(buf))
+        if lo is None:
+            lo = torch.zeros_like(buf)
+            self._lo_bufs[id(buf)] = (lo, buf)            # keep `buf` alive: the key is its id
+            return lo
+        return lo[0]
+
+    def _split(self, sl):
+        """tf32x3: refresh the low part of a slice some non-convolution kernel just wrote"""
+        if self.x3:
+            ops.k_act_split(None, sl, Slice(self._lo(sl.buf), sl.c0, sl.C))
+
     def _conv(self, cs, x, out, residual=None):
         use_tc = self.tc and cs.w_tc is not None
+        if self.x3 and use_tc:
+            xlo = Slice(self._lo(x.buf), x.c0, x.C)
+            tmp = Slice(self._scratch(out.N, out.H, out.W, (cs.cout + 3) // 4 * 4), 0, cs.cout)
+            args = (cs.k, cs.stride, cs.dil, 1.0)
+            ops.k_conv(xlo, cs.w_tc, cs.zero_b, tmp, *args, None, _ext.CONV_TF32)          # lo * w_hi
+            ops.k_conv(x, cs.w_lo_tc, cs.zero_b, tmp, *args, tmp, _ext.CONV_TF32)          # + hi * w_lo
+            ops.k_conv(x, cs.w_tc, cs.bias, tmp, *args, tmp, _ext.CONV_TF32)               # + hi * w_hi + bias
+            ops.k_act_split(tmp, out, Slice(self._lo(out.buf), out.c0, out.C), cs.slope, residual)
+            return
+        if self.x3:
+            ops.k_conv(x, cs.w, cs.bias, out, cs.k, cs.stride, cs.dil, cs.slope, residual, _ext.CONV_FP32)   # exact SIMT
+            self._split(out)
+            return
         if use_tc and cs.w_exp is not None and x.H * x.W >= EXPAND_MIN_PIXELS:
             Y = self._scratch(x.N, x.H, x.W, 9 * EXPAND_MAX_COUT)
             ys = Slice(Y, 0, 9 * cs.cout)
@@ -297,17 +338,21 @@ class DecoderEngine:
                     S = d["S"]
                     ops.k_copy(Slice(X, X_F1X1, 32), Slice(S, 0, 32))
                     ops.k_warp(Slice(X, X_F1X1, 32), bil, Slice(S, 32, 32), ac, self.mask, x_shift=B)
+                    self._split(Slice(S, 0, 64))
                     self._sgu_dense(S, d["inter"])
                     ops.k_sgu_blend(bil, Slice(d["inter"], 0, 3), flow_up, ac)
                 else:
                     ops.k_resize(prev_flow, flow_up, (w / pw, h / ph))
+                self._split(flow_up)
             # feature statistics (model/upflow.py:549-555: computed above / on the side stream), warp + its
             # statistics (:546-547)
             if L == 0:
                 ops.k_corr(F, F, Slice(X, X_CORR, 81), 4, d["stats_own"], d["stats_own"], f2_shift=B, slope=SLOPE)
+                self._split(Slice(X, X_CORR, 81))
             else:
                 ops.k_warp(F, flow_up, Slice(d["xw"]), ac, self.mask, x_shift=B, stats=d["stats_w"])
                 ops.k_corr(F, Slice(d["xw"]), Slice(X, X_CORR, 81), 4, d["stats_own"], d["stats_w"], slope=SLOPE)
+                self._split(Slice(X, X_CORR, 81))
             # dense flow estimator (model/pwc_modules.py:279-286)
             for k in range(5):
                 self._conv(self.est[k], Slice(X, 0, self.est[k].cin), Slice(X, X_OFF[k], EST_CH[k]))
@@ -338,6 +383,7 @@ class DecoderEngine:
             main.wait_event(ev_outconv)                # output_conv features (side stream)
             # the flow handed to sgu_model here is the 1/4-res flow itself (already at feature size, :73-75)
             ops.k_warp(Slice(S, 0, 32), prev_flow, Slice(S, 32, 32), ac, self.mask, x_shift=B)
+            self._split(Slice(S, 32, 32))
             self._sgu_dense(S, ws["inter_out"])
             ops.k_sgu_blend(bil, Slice(ws["inter_out"], 0, 3), out, ac)
         else:

@@ -245,6 +245,17 @@ def expand_taps_weight(weight):
     return weight.detach().permute(2, 3, 0, 1).reshape(9 * Cout, Cin, 1, 1).contiguous()
 
 
+def k_act_split(t, out, out_lo=None, slope=1.0, residual=None):
+    """out = lrelu(t) (+ residual); out_lo = out - trunc_tf32(out).  t=None: only split `out` into out_lo."""
+    out = _as_slice(out)
+    t = _as_slice(t) if t is not None else None
+    lo = _as_slice(out_lo) if out_lo is not None else None
+    res = _as_slice(residual) if residual is not None else None
+    _ext.check(_lib().upf_act_split(t.ptr() if t else None, t.ld if t else 0, res.ptr() if res else None, res.ld if res else 0,
+                                    out.ptr(), out.ld, lo.ptr() if lo else None, lo.ld if lo else 0, out.N * out.H * out.W,
+                                    out.C, float(slope), _stream()), "act_split")
+
+
 def k_copy(src, dst):
     src, dst = _as_slice(src), _as_slice(dst)
     assert src.C == dst.C
