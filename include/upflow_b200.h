@@ -233,6 +233,31 @@ long long upf_resize_bilinear_bwd_workspace_elems(int N, int H, int w, int C);
 int upf_resize_bilinear_bwd(const float* grad_out, int ldgo, int H, int W, float* grad_in, int ldgi, int h, int w,
                             int N, int C, const float* scale_host, float* workspace, void* stream);
 
+/* Loss terms of the training step on pixel-major tensors, each ONE reduction pass forward
+ * (deterministic: per-CTA partials summed in a fixed order) and one elementwise pass backward.
+ * workspace: upf_loss_workspace_elems() floats.  out: 2 floats, out[0] = the term (out[1] is kept for backward).
+ *
+ * upf_robust_loss_*: photo_loss_multi_type (model/upflow.py:268-290; the photometric term :436-437 and the multi-scale
+ * distillation terms :461-487).  d = x - y over [npix][C]; kind 0 abs_robust (|d|+0.01)^q, 1 charbonnier (d^2+1e-6)^q,
+ * 2 L1 |d+1e-6|; mask == NULL: mean over npix*C; mask [npix] (photo_loss_use_occ): sum(v*mask)/(sum(mask)+1e-6).
+ * Backward: grad_x = grad_out[0] * d(term)/dx, grad_y = -grad_x (either may be NULL); no gradient reaches the mask. */
+#define UPF_LOSS_ABS_ROBUST  0
+#define UPF_LOSS_CHARBONNIER 1
+#define UPF_LOSS_L1          2
+long long upf_loss_workspace_elems(void);
+int upf_robust_loss_fwd(const float* x, int ldx, const float* y, int ldy, const float* mask, int ldm, float* workspace,
+                        float* out, long long npix, int C, int kind, float q, void* stream);
+int upf_robust_loss_bwd(const float* x, int ldx, const float* y, int ldy, const float* mask, int ldm, const float* out,
+                        const float* grad_out, float* grad_x, int ldgx, float* grad_y, int ldgy, long long npix, int C,
+                        int kind, float q, void* stream);
+/* upf_edge_smooth1_*: edge_aware_smoothness_order1 (model/upflow.py:198-218): mean(|d_rows pred| * exp(-mean_c|d_rows
+ * img|)) + mean(|d_cols pred| * exp(-mean_c|d_cols img|)); img [N,H,W,Ci], pred [N,H,W,Cp], H, W >= 2.  Backward gives
+ * the gradient of pred only (the image is data). */
+int upf_edge_smooth1_fwd(const float* img, int ldi, int Ci, const float* pred, int ldp, int Cp, float* workspace,
+                         float* out, int N, int H, int W, void* stream);
+int upf_edge_smooth1_bwd(const float* img, int ldi, int Ci, const float* pred, int ldp, int Cp, const float* grad_out,
+                         float* grad_pred, int ldg, int N, int H, int W, void* stream);
+
 /* layout helpers for callers holding NCHW-contiguous tensors (the reference's
  * layout): strided copy between [N,C,H,W] planes and pixel-major rows. */
 int upf_nchw_to_nhwc(const float* in, float* out, int ldo, int N, int C, int H, int W, void* stream);

@@ -279,3 +279,104 @@ def test_trainer_cuda_graph_matches_eager():
     # training itself amplifies last-bit differences (measured 8e-6, 6e-4, 3e-4 relative on steps 2-4)
     for i, (a, b) in enumerate(zip(*losses)):
         _check("loss difference, step %d" % (i + 1), abs(a - b) / abs(a), 1e-5 if i == 0 else 2e-2)
+
+
+def _torch_loss_terms():
+    """The drop-in's torch expressions of the two loss terms (the kernels' A/B partner; pinned to the reference by
+    the golden training steps above)."""
+    import upflow_pytorch_b200
+    upflow_pytorch_b200.install_dropin()
+    from model.upflow import network_tools
+    return network_tools
+
+
+@pytest.mark.parametrize("kind", ["abs_robust", "charbonnier", "L1"])
+@pytest.mark.parametrize("masked", [False, True])
+@pytest.mark.parametrize("shape", [(2, 3, 37, 53), (1, 2, 6, 20), (4, 2, 256, 832)])
+def test_robust_loss_kernels_vs_torch(upf, kind, masked, shape):
+    """upf_robust_loss_fwd/bwd (csrc/loss.cu) against the torch expression of photo_loss_multi_type
+    (model/upflow.py:268-290) in fp64: value to 5e-6 relative, both gradients to 2e-5 of their largest entry.
+    Inputs arrive channels_last and NCHW-contiguous, like the training path's."""
+    nt = _torch_loss_terms()
+    N, C, H, W = shape
+    x = _rand(1, N, C, H, W).cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    y = _rand(2, N, C, H, W).cuda().requires_grad_()
+    mask = (torch.rand(N, 1, H, W, generator=torch.Generator().manual_seed(3)) > 0.4).float().cuda()
+    got = upf.robust_loss(x, y, mask if masked else None, kind, 0.4)
+    gx, gy = torch.autograd.grad(got * 3.0, (x, y))
+    xd, yd = x.detach().double().requires_grad_(), y.detach().double().requires_grad_()
+    nt.use_loss_kernels = False
+    try:
+        want = nt.photo_loss_multi_type(xd, yd, mask.double(), kind, 0.4, photo_loss_use_occ=masked)
+    finally:
+        nt.use_loss_kernels = True
+    wx, wy = torch.autograd.grad(want * 3.0, (xd, yd))
+    _check("value", abs(got.item() - want.item()) / abs(want.item()), 5e-6)
+    _check("grad x", _rel(gx, wx), 2e-5)
+    _check("grad y", _rel(gy, wy), 2e-5)
+    # only one side needs a gradient (the distillation label, the source image)
+    (gy2,) = torch.autograd.grad(upf.robust_loss(x.detach(), y, mask if masked else None, kind, 0.4) * 3.0, (y,))
+    assert torch.equal(gy2, gy)
+    # deterministic
+    assert upf.robust_loss(x, y, mask if masked else None, kind, 0.4).item() == got.item()
+
+
+@pytest.mark.parametrize("shape", [(2, 37, 53), (1, 2, 2), (4, 256, 832), (1, 375, 1242)])
+def test_edge_smooth1_kernels_vs_torch(upf, shape):
+    """upf_edge_smooth1_fwd/bwd against the torch expression of edge_aware_smoothness_order1 (model/upflow.py:198-218)
+    in fp64.  The flow is quantised so that some neighbouring differences are exactly zero (sign(0) = 0)."""
+    nt = _torch_loss_terms()
+    N, H, W = shape
+    img = torch.rand(N, 3, H, W, generator=torch.Generator().manual_seed(4)).cuda()
+    flow = (_rand(5, N, 2, H, W) * 2).round().div(2).cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    got = upf.edge_smooth1(img, flow)
+    (gf,) = torch.autograd.grad(got * 2.0, (flow,))
+    fd = flow.detach().double().requires_grad_()
+    nt.use_loss_kernels = False
+    try:
+        want = nt.edge_aware_smoothness_order1(img.double(), fd)
+    finally:
+        nt.use_loss_kernels = True
+    (wf,) = torch.autograd.grad(want * 2.0, (fd,))
+    _check("value", abs(got.item() - want.item()) / abs(want.item()), 5e-6)
+    _check("grad", _rel(gf, wf), 2e-5)
+    assert upf.edge_smooth1(img, flow).item() == got.item()
+
+
+def test_loss_kernels_reject_bad_arguments(upf):
+    x = torch.zeros(1, 2, 4, 4, device="cuda")
+    with pytest.raises(ValueError):
+        upf.robust_loss(x, torch.zeros(1, 2, 4, 5, device="cuda"))
+    with pytest.raises(KeyError):
+        upf.robust_loss(x, x, None, "SSIM")
+    with pytest.raises(RuntimeError):
+        upf.edge_smooth1(torch.zeros(1, 3, 1, 4, device="cuda"), torch.zeros(1, 2, 1, 4, device="cuda"))
+    with pytest.raises(RuntimeError):
+        upf.robust_loss(x.cpu(), x.cpu())
+
+
+def test_training_step_loss_kernels_match_torch_terms():
+    """The whole training step with the fused loss kernels against the same step with the torch expressions: every
+    loss term to 1e-5 relative, every parameter gradient to 1e-3 of its norm (same forward, same backward kernels;
+    only the loss branch differs)."""
+    nt = _torch_loss_terms()
+    from upflow_pytorch_b200.train import total_loss
+    conf = {"if_norm_before_cost_volume": True, "norm_moments_across_channels": False, "norm_moments_across_images": False,
+            "if_sgu_upsample": True, "if_use_boundary_warp": False, "multi_scale_distillation_weight": 0.01,
+            "photo_loss_use_occ": True}
+    im1, im2 = O.synthetic_pair(64, 96, seed=8, batch=2)
+    res = {}
+    for use in (True, False):
+        net = _dropin_net(conf, 13, "fp32")
+        nt.use_loss_kernels = use
+        try:
+            out = net({"im1": im1.cuda(), "im2": im2.cuda(), "if_loss": True})
+            total_loss(out).backward()
+        finally:
+            nt.use_loss_kernels = True
+        res[use] = ({k: out[k].item() for k in ("photo_loss", "smooth_loss", "msd_loss")},
+                    {n: p.grad.clone() for n, p in net.named_parameters()})
+    for k, v in res[False][0].items():
+        _check(k, abs(res[True][0][k] - v) / abs(v), 1e-5)
+    worst = max(((res[True][1][n] - g).norm() / g.norm().clamp_min(1e-20)).item() for n, g in res[False][1].items())
+    _check("worst relative gradient difference", worst, 1e-3)

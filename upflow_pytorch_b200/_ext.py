@@ -49,6 +49,11 @@ SIGNATURES = {
     "upf_featnorm_bwd": (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
     "upf_resize_bilinear_bwd_workspace_elems": (_LL, [_I, _I, _I, _I]),
     "upf_resize_bilinear_bwd": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _c.POINTER(_F), _P, _P]),
+    "upf_loss_workspace_elems": (_LL, []),
+    "upf_robust_loss_fwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _LL, _I, _I, _F, _P]),
+    "upf_robust_loss_bwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _P, _I, _LL, _I, _I, _F, _P]),
+    "upf_edge_smooth1_fwd": (_I, [_P, _I, _I, _P, _I, _I, _P, _P, _I, _I, _I, _P]),
+    "upf_edge_smooth1_bwd": (_I, [_P, _I, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P]),
     "upf_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "upf_nhwc_to_nchw": (_I, [_P, _I, _P, _I, _I, _I, _I, _P]),
     "upf_copy_channels": (_I, [_P, _I, _P, _I, _LL, _I, _P]),
@@ -57,6 +62,7 @@ SIGNATURES = {
 CONV_FP32 = 0
 CONV_TF32 = 1
 PW_LRELU_BWD, PW_SIGMOID, PW_SIGMOID_BWD = 0, 1, 2
+LOSS_KINDS = {"abs_robust": 0, "charbonnier": 1, "L1": 2}
 
 _lib = None
 

@@ -81,7 +81,12 @@ class network_tools():
         return [ops.normalize_features(f) for f in feature_list]
 
     # ---- loss terms of the training step (model/upflow.py:198-290).  They run AFTER the decoder on full-resolution
-    # 2-/3-channel tensors: elementwise torch around the library's warp (loss kernels: SURVEY.md section 8f rank 2).
+    # 2-/3-channel tensors.  The photometric / distillation term and the first-order smoothness term are fused kernels
+    # (csrc/loss.cu); the torch expressions below remain for what the kernels do not take
+    # (a mask or an image that itself needs a gradient, the second-order term) and as the A/B partner
+    # (`network_tools.use_loss_kernels = False`, tests/test_gpu_backward.py).
+    use_loss_kernels = True
+
     @classmethod
     def edge_aware_smoothness_order1(cls, img, pred):
         """model/upflow.py:198-218 (note the reference's naming: `gradient_x` differences ROWS)."""
@@ -90,6 +95,8 @@ class network_tools():
 
         def d_cols(t):
             return t[:, :, :, :-1] - t[:, :, :, 1:]
+        if cls.use_loss_kernels and pred.is_cuda and not img.requires_grad and min(pred.shape[2:]) >= 2:
+            return ops.edge_smooth1(img.float(), pred)           # one kernel forward, one backward (csrc/loss.cu)
         w_r = torch.exp(-torch.mean(torch.abs(d_rows(img)), 1, keepdim=True))
         w_c = torch.exp(-torch.mean(torch.abs(d_cols(img)), 1, keepdim=True))
         return torch.mean(torch.abs(d_rows(pred)) * w_r) + torch.mean(torch.abs(d_cols(pred)) * w_c)
@@ -123,6 +130,12 @@ class network_tools():
     def photo_loss_multi_type(cls, x, y, occ_mask, photo_loss_type='abs_robust', photo_loss_delta=0.4,
                               photo_loss_use_occ=False):
         """model/upflow.py:268-290 (the SSIM variant is not provided)."""
+        if photo_loss_type not in ('abs_robust', 'charbonnier', 'L1'):
+            raise NotImplementedError('photo_loss type %s' % photo_loss_type)
+        mask = occ_mask if photo_loss_use_occ else None
+        if cls.use_loss_kernels and x.is_cuda and x.shape == y.shape and (mask is None or (
+                not mask.requires_grad and mask.numel() == x.shape[0] * x.shape[2] * x.shape[3])):
+            return ops.robust_loss(x, y, mask, photo_loss_type, photo_loss_delta)   # csrc/loss.cu
         if photo_loss_type == 'abs_robust':
             loss_diff = (torch.abs(x - y) + 0.01).pow(photo_loss_delta)
         elif photo_loss_type == 'charbonnier':

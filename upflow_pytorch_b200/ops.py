@@ -516,6 +516,89 @@ def sgu_blend(flow_init, inter, align_corners=False):
     return out.permute(0, 3, 1, 2)
 
 
+# ---------------------------------------------------------------- loss terms of the training step
+def _loss_buffers(like):
+    ws = torch.empty(int(_lib().upf_loss_workspace_elems()), dtype=torch.float32, device=like.device)
+    return ws, torch.empty(2, dtype=torch.float32, device=like.device)
+
+
+class _RobustLossFn(torch.autograd.Function):
+    """photo_loss_multi_type (model/upflow.py:268-290) as one reduction kernel forward, one elementwise kernel
+    backward; the mask (if any) gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, y, mask, kind, q):
+        xa, ya = to_pixel_major(x), to_pixel_major(y)
+        ma = mask.reshape(-1).contiguous() if mask is not None else None
+        N, H, W, C = xa.shape
+        ws, out = _loss_buffers(xa)
+        _ext.check(_lib().upf_robust_loss_fwd(_p(xa), C, _p(ya), C, _p(ma), 1, _p(ws), _p(out), N * H * W, C, kind,
+                                              float(q), _stream()), "robust_loss_fwd")
+        ctx.save_for_backward(xa, ya, out, *([ma] if ma is not None else []))
+        ctx.kind, ctx.q = kind, float(q)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad):
+        xa, ya, out = ctx.saved_tensors[:3]
+        ma = ctx.saved_tensors[3] if len(ctx.saved_tensors) > 3 else None
+        N, H, W, C = xa.shape
+        g = grad.reshape(1).contiguous()
+        _require_cuda(g)
+        gx = torch.empty_like(xa) if ctx.needs_input_grad[0] else None
+        gy = torch.empty_like(ya) if ctx.needs_input_grad[1] else None
+        if gx is None and gy is None:
+            return None, None, None, None, None
+        _ext.check(_lib().upf_robust_loss_bwd(_p(xa), C, _p(ya), C, _p(ma), 1, _p(out), _p(g), _p(gx), C, _p(gy), C,
+                                              N * H * W, C, ctx.kind, ctx.q, _stream()), "robust_loss_bwd")
+        return (gx.permute(0, 3, 1, 2) if gx is not None else None, gy.permute(0, 3, 1, 2) if gy is not None else None,
+                None, None, None)
+
+
+def robust_loss(x, y, mask=None, kind="abs_robust", q=0.4):
+    """The reference's photometric / distillation term (model/upflow.py:268-290) of x, y [N,C,H,W]: mean of
+    (|x-y|+0.01)^q ('abs_robust'), ((x-y)^2+1e-6)^q ('charbonnier') or |x-y+1e-6| ('L1'); with mask [N,1,H,W]:
+    sum(v*mask)/(sum(mask)+1e-6).  Returns a 0-dim tensor."""
+    _require_cuda(x, y, mask)
+    if x.shape != y.shape or (mask is not None and mask.numel() != x.shape[0] * x.shape[2] * x.shape[3]):
+        raise ValueError("robust_loss: x %s, y %s, mask %s" % (tuple(x.shape), tuple(y.shape),
+                                                                None if mask is None else tuple(mask.shape)))
+    return _RobustLossFn.apply(x, y, mask, _ext.LOSS_KINDS[kind], q)
+
+
+class _EdgeSmooth1Fn(torch.autograd.Function):
+    """edge_aware_smoothness_order1 (model/upflow.py:198-218); gradient for `pred` only."""
+
+    @staticmethod
+    def forward(ctx, img, pred):
+        ia, pa = to_pixel_major(img), to_pixel_major(pred)
+        N, H, W, Cp = pa.shape
+        ws, out = _loss_buffers(pa)
+        _ext.check(_lib().upf_edge_smooth1_fwd(_p(ia), ia.shape[3], ia.shape[3], _p(pa), Cp, Cp, _p(ws), _p(out),
+                                               N, H, W, _stream()), "edge_smooth1_fwd")
+        ctx.save_for_backward(ia, pa)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad):
+        ia, pa = ctx.saved_tensors
+        N, H, W, Cp = pa.shape
+        g = grad.reshape(1).contiguous()
+        _require_cuda(g)
+        gp = torch.empty_like(pa)
+        _ext.check(_lib().upf_edge_smooth1_bwd(_p(ia), ia.shape[3], ia.shape[3], _p(pa), Cp, Cp, _p(g), _p(gp), Cp,
+                                               N, H, W, _stream()), "edge_smooth1_bwd")
+        return None, gp.permute(0, 3, 1, 2)
+
+
+def edge_smooth1(img, pred):
+    """First-order edge-aware smoothness of pred [N,Cp,H,W] under image img [N,Ci,H,W] (model/upflow.py:198-218)."""
+    _require_cuda(img, pred)
+    if img.shape[0] != pred.shape[0] or img.shape[2:] != pred.shape[2:]:
+        raise ValueError("edge_smooth1: img %s, pred %s" % (tuple(img.shape), tuple(pred.shape)))
+    return _EdgeSmooth1Fn.apply(img, pred)
+
+
 class _ConvFn(torch.autograd.Function):
     """conv() of model/pwc_modules.py:10-31 with autograd: the input gradient is the forward kernel on the flipped,
     transposed weights (on the zero-interleaved gradient for stride 2), the weight / bias gradient is
