@@ -233,6 +233,12 @@ long long upf_resize_bilinear_bwd_workspace_elems(int N, int H, int w, int C);
 int upf_resize_bilinear_bwd(const float* grad_out, int ldgo, int H, int W, float* grad_in, int ldgi, int h, int w,
                             int N, int C, const float* scale_host, float* workspace, void* stream);
 
+/* nn.Conv2d weight [A][B][k][k] (the reference's parameter layout, model/pwc_modules.py:10-31) -> this library's
+ * [k*k][Cin][cout_pad] (cout_pad = Cout rounded up to 4, padding zeroed) in one launch.  flip_transpose 0: the forward
+ * convolution (Cout = A, Cin = B).  flip_transpose 1: the weights of the input-gradient convolution -- taps flipped,
+ * channel roles exchanged (Cin = A, Cout = B). */
+int upf_repack_conv_weight(const float* weight, float* out, int A, int B, int ksize, int flip_transpose, void* stream);
+
 /* Loss terms of the training step on pixel-major tensors, each ONE reduction pass forward
  * (deterministic: per-CTA partials summed in a fixed order) and one elementwise pass backward.
  * workspace: upf_loss_workspace_elems() floats.  out: 2 floats, out[0] = the term (out[1] is kept for backward).

@@ -380,3 +380,21 @@ def test_training_step_loss_kernels_match_torch_terms():
         _check(k, abs(res[True][0][k] - v) / abs(v), 1e-5)
     worst = max(((res[True][1][n] - g).norm() / g.norm().clamp_min(1e-20)).item() for n, g in res[False][1].items())
     _check("worst relative gradient difference", worst, 1e-3)
+
+
+@pytest.mark.parametrize("shape", [(20, 12, 3), (2, 3, 3), (16, 3, 3), (7, 5, 1), (196, 128, 3)])
+def test_repack_conv_weight_kernel(upf, shape):
+    """upf_repack_conv_weight (one launch per convolution call of the training path) against the permute / flip /
+    transpose it replaces: bit-exact, padding columns zero."""
+    Cout, Cin, k = shape
+    w = _rand(9, Cout, Cin, k, k).cuda()
+    got, _ = upf.pack_conv_weight(w)
+    pad = lambda c: (c + 3) // 4 * 4
+    want = torch.zeros(k * k, Cin, pad(Cout), device="cuda")
+    want[:, :, :Cout] = w.permute(2, 3, 1, 0).reshape(k * k, Cin, Cout)
+    assert torch.equal(got, want)
+    got_d, _ = upf.pack_conv_weight(w, flip_transpose=True)
+    w_d = w.flip(2, 3).transpose(0, 1).contiguous()                    # [Cin, Cout, k, k]: Cout and Cin exchanged
+    want_d = torch.zeros(k * k, Cout, pad(Cin), device="cuda")
+    want_d[:, :, :Cin] = w_d.permute(2, 3, 1, 0).reshape(k * k, Cout, Cin)
+    assert torch.equal(got_d, want_d)

@@ -26,5 +26,5 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 rows = [(e.key, e.count, e.device_time_total) for e in prof.key_averages() if e.device_time_total > 0]
 tot = sum(r[2] for r in rows)
 print("# one training step, %d pairs of %dx%d: %.1f ms of kernel time" % (B, H, W, tot / 1e3))
-for k, n, t in sorted(rows, key=lambda r: -r[2])[:25]:
+for k, n, t in sorted(rows, key=lambda r: -r[2])[:45]:
     print("%6.2f%%  %8.2f ms  %5d  %s" % (100 * t / tot, t / 1e3, n, k[:110]))

@@ -354,7 +354,7 @@ resize_bwd_y_kernel(const float* __restrict__ tmp, int H, float* __restrict__ gi
 // k + (kx-1)*dil.
 __global__ void __launch_bounds__(256)
 nhwc_to_planar_padded_kernel(const float* __restrict__ src, int ld, int C, float* __restrict__ dst, long long Kp, long long P,
-                             int H, int W, int pad, int Wp, int shift) {
+                             int H, int W, int pad, int Wp, int shift, int ncopies, long long copy_stride, int copy_shift) {
   __shared__ float tile[32][33];
   const long long p0 = (long long)blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
@@ -375,7 +375,11 @@ nhwc_to_planar_padded_kernel(const float* __restrict__ src, int ld, int C, float
     const long long k = (n * Hp + y + pad) * Wp + x + pad + shift;
     for (int i = ty; i < 32; i += 8) {
       const int c = c0 + i;
-      if (c < C) dst[(size_t)c * Kp + k] = tile[tx][i];
+      if (c < C) {
+        const float v = tile[tx][i];
+        for (int q = 0; q < ncopies; ++q)                  // copy q lives at dst + q*copy_stride, shifted by q*copy_shift
+          dst[(size_t)q * copy_stride + (size_t)c * Kp + k + q * copy_shift] = v;
+      }
     }
   }
 }
@@ -417,9 +421,13 @@ static unsigned grid_for(long long total) {
 }  // namespace upf
 
 // number of pixel splits the weight gradient uses for this shape (the caller sizes the workspace with it)
+// CTA tile (ci x co) by shape: 32 x 64 for the few-channel convolutions of the image pyramid and output_conv, whose
+// pixel count is what is large (a 128 x 64 tile spent 5.9 ms of a 71 ms training step on ten such launches, 1/32 of
+// its FMAs useful)
+static int wgrad_bm(int Cin, int Cout) { return (Cin <= 32 && Cout <= 64) ? 32 : 128; }
 static int wgrad_splits(int Cin, int Cout, int taps, long long npix) {
-  const int bn = Cout > 64 ? 128 : 64;
-  const long long tiles = (long long)((Cin + 127) / 128) * ((Cout + bn - 1) / bn) * taps;
+  const int bn = Cout > 64 ? 128 : 64, bm = wgrad_bm(Cin, Cout);
+  const long long tiles = (long long)((Cin + bm - 1) / bm) * ((Cout + bn - 1) / bn) * taps;
   long long s = (4 * UPF_NUM_SMS + tiles - 1) / tiles;
   const long long max_by_pix = (npix + 255) / 256;
   if (s > max_by_pix) s = max_by_pix;
@@ -451,14 +459,17 @@ extern "C" int upf_conv2d_wgrad(const float* x, int ldx, const float* grad_out, 
   const long long npix = (long long)N * Ho * Wo;
   const int splits = wgrad_splits(Cin, Cout, taps, npix);
   const long long pps = ((npix + splits - 1) / splits + WG_KP - 1) / WG_KP * WG_KP;
-  const int bn = Cout > 64 ? 128 : 64;
-  const int ci_tiles = (Cin + 127) / 128, co_tiles = (Cout + bn - 1) / bn;
+  const int bn = Cout > 64 ? 128 : 64, bm = wgrad_bm(Cin, Cout);
+  const int ci_tiles = (Cin + bm - 1) / bm, co_tiles = (Cout + bn - 1) / bn;
   cudaStream_t st = (cudaStream_t)stream;
   const long long wn = (long long)taps * Cin * Cout;
   const dim3 grid(ci_tiles * co_tiles, taps, splits);
   if (bn == 128)
     conv_wgrad_kernel<128, 128, 8, 8><<<grid, WG_NT, 0, st>>>(x, ldx, grad_out, ldg, workspace, N, H, W, Ho, Wo, Cin, Cout, ksize,
                                                               stride, dilation, pad, co_tiles, pps, npix);
+  else if (bm == 32)
+    conv_wgrad_kernel<32, 64, 4, 2><<<grid, WG_NT, 0, st>>>(x, ldx, grad_out, ldg, workspace, N, H, W, Ho, Wo, Cin, Cout, ksize,
+                                                            stride, dilation, pad, co_tiles, pps, npix);
   else
     conv_wgrad_kernel<128, 64, 8, 4><<<grid, WG_NT, 0, st>>>(x, ldx, grad_out, ldg, workspace, N, H, W, Ho, Wo, Cin, Cout, ksize,
                                                              stride, dilation, pad, co_tiles, pps, npix);
@@ -541,6 +552,35 @@ extern "C" int upf_resize_bilinear_bwd(const float* grad_out, int ldgo, int H, i
   return check_launch("resize_bwd_y");
 }
 
+// ---- nn.Conv2d weight [A][B][k][k] -> the library's [k*k][Cin][cout_pad] (cout_pad = Cout rounded up to 4, padding
+// zero), one launch per convolution call of the training path (was: fill + permute copy + slice copy, and for the
+// input-gradient convolution a flip and a transposing copy before those).
+// flip_transpose 0: the forward convolution, Cout = A, Cin = B:          out[t][ci][co] = w[co][ci][t]
+// flip_transpose 1: the input-gradient convolution, Cin = A, Cout = B:  out[t][ci][co] = w[ci][co][taps-1-t]
+__global__ void __launch_bounds__(256)
+repack_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int Cin, int Cout, int cout_pad, int taps, int flip_transpose) {
+  const long long total = (long long)taps * Cin * cout_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % cout_pad);
+    const long long r = i / cout_pad;
+    const int ci = (int)(r % Cin), t = (int)(r / Cin);
+    float v = 0.f;
+    if (co < Cout)
+      v = flip_transpose ? __ldg(w + ((size_t)ci * Cout + co) * taps + (taps - 1 - t)) : __ldg(w + ((size_t)co * Cin + ci) * taps + t);
+    out[i] = v;
+  }
+}
+
+extern "C" int upf_repack_conv_weight(const float* weight, float* out, int A, int B, int ksize, int flip_transpose, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(weight && out && A > 0 && B > 0 && ksize > 0, "repack_conv_weight: bad argument");
+  const int Cin = flip_transpose ? A : B, Cout = flip_transpose ? B : A, taps = ksize * ksize;
+  const int cout_pad = (Cout + 3) / 4 * 4;
+  repack_weight_kernel<<<grid_for((long long)taps * Cin * cout_pad), 256, 0, (cudaStream_t)stream>>>(weight, out, Cin, Cout, cout_pad,
+                                                                                                   taps, flip_transpose ? 1 : 0);
+  return check_launch("repack_weight");
+}
+
 // ---- tensor-core weight gradient (stride 1): see nhwc_to_planar_padded_kernel
 static int wgrad_tc_wp(int W, int ks, int dil) { return (W + (ks - 1) * dil + 3) / 4 * 4; }   // padded row, multiple of 4
 static long long wgrad_tc_kp(int N, int H, int W, int ks, int dil) {
@@ -575,15 +615,15 @@ extern "C" int upf_conv2d_wgrad_tc(const float* x, int ldx, const float* grad_ou
   cudaError_t ce = cudaMemsetAsync(workspace, 0, ((size_t)Cin * Kp + (size_t)3 * cout_pad * Kp + cout_pad) * sizeof(float), st);
   if (ce != cudaSuccess) { set_error("wgrad_tc memset: %s", cudaGetErrorString(ce)); return (int)ce; }
   const unsigned ptiles = (unsigned)((P + 31) / 32);
-  nhwc_to_planar_padded_kernel<<<dim3(ptiles, (Cin + 31) / 32), 256, 0, st>>>(x, ldx, Cin, xt, Kp, P, H, W, pad, Wp, 0);
+  nhwc_to_planar_padded_kernel<<<dim3(ptiles, (Cin + 31) / 32), 256, 0, st>>>(x, ldx, Cin, xt, Kp, P, H, W, pad, Wp, 0, 1, 0, 0);
   int e = check_launch("wgrad_tc_transpose_x");
   if (e) return e;
-  for (int c = 0; c < ncopies; ++c) {
-    nhwc_to_planar_padded_kernel<<<dim3(ptiles, (Cout + 31) / 32), 256, 0, st>>>(grad_out, ldg, Cout, gt + (size_t)c * cout_pad * Kp, Kp, P,
-                                                                                  H, W, pad, Wp, ksize == 1 ? 0 : (c - 1) * dilation);
-    e = check_launch("wgrad_tc_transpose_g");
-    if (e) return e;
-  }
+  // the three horizontally shifted copies of G in one pass: one read, three writes
+  nhwc_to_planar_padded_kernel<<<dim3(ptiles, (Cout + 31) / 32), 256, 0, st>>>(grad_out, ldg, Cout, gt, Kp, P, H, W, pad, Wp,
+                                                                                ksize == 1 ? 0 : -dilation, ncopies,
+                                                                                cout_pad * Kp, dilation);
+  e = check_launch("wgrad_tc_transpose_g");
+  if (e) return e;
   int koffs[9], wsel[9];
   for (int t = 0; t < taps; ++t) {
     const int ky = t / ksize, kx = t % ksize;

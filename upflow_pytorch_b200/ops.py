@@ -264,8 +264,10 @@ def k_copy(src, dst):
 
 
 # ---------------------------------------------------------------- weights
-def pack_conv_weight(weight, in_slots=None, cin_total=None, tc=False):
+def pack_conv_weight(weight, in_slots=None, cin_total=None, tc=False, flip_transpose=False):
     """nn.Conv2d weight [Cout,Cin,k,k] -> library layouts.
+
+    flip_transpose: the weights of the input-gradient convolution instead (taps flipped, Cin and Cout exchanged).
 
     in_slots[i] = position, inside the input slice the kernel reads, of the
     reference's input channel i (identity when None); cin_total = width of that
@@ -273,6 +275,21 @@ def pack_conv_weight(weight, in_slots=None, cin_total=None, tc=False):
     prepend-concatenation order (model/pwc_modules.py:280-284) is mapped onto
     append-only buffers).  Returns (w_simt [taps,cin_total,cout_pad4], w_tc or None)."""
     Cout, Cin, k, _ = weight.shape
+    if flip_transpose or (in_slots is None and cin_total in (None, Cin) and weight.is_cuda):
+        if in_slots is not None or cin_total not in (None, Cin):
+            raise ValueError("flip_transpose packs the plain layout only")
+        src = weight.detach().float().contiguous()
+        _require_cuda(src)
+        if flip_transpose:
+            Cout, Cin = Cin, Cout
+        w = torch.empty(k * k, Cin, (Cout + 3) // 4 * 4, dtype=torch.float32, device=weight.device)
+        _ext.check(_lib().upf_repack_conv_weight(_p(src), _p(w), weight.shape[0], weight.shape[1], k,
+                                                 1 if flip_transpose else 0, _stream()), "repack_conv_weight")
+        w_tc = None
+        if tc:
+            w_tc = torch.empty(_lib().upf_conv_tc_packed_elems(Cin, Cout, k), dtype=torch.float32, device=weight.device)
+            _ext.check(_lib().upf_conv_tc_pack_weights(_p(w), _p(w_tc), Cin, Cout, k, _stream()), "conv_tc_pack_weights")
+        return w, w_tc
     cin_total = cin_total or Cin
     cout_pad = (Cout + 3) // 4 * 4
     w = torch.zeros(k * k, cin_total, cout_pad, dtype=torch.float32, device=weight.device)
@@ -319,6 +336,17 @@ def to_nchw_contiguous(buf, C=None):
     out = torch.empty(s.N, s.C, s.H, s.W, dtype=torch.float32, device=s.buf.device)
     _ext.check(_lib().upf_nhwc_to_nchw(s.ptr(), s.ld, _p(out), s.N, s.C, s.H, s.W, _stream()), "nhwc_to_nchw")
     return out
+
+
+_ZERO_BIAS = {}
+
+
+def _zero_bias(n, device):
+    """A read-only all-zero bias vector (never written, kept alive: one fill per device instead of one per call)."""
+    z = _ZERO_BIAS.get(device)
+    if z is None or z.numel() < n:
+        z = _ZERO_BIAS[device] = torch.zeros(max(1024, n), dtype=torch.float32, device=device)
+    return z[:n]
 
 
 def _new(N, H, W, C, like):
@@ -644,8 +672,7 @@ class _ConvFn(torch.autograd.Function):
             gw_t, gb = k_conv_wgrad(a, gps, ks, stride, dilation, want_bias=True, tensor_cores=tc)
             gw = gw_t.reshape(ks, ks, Cin, Cout).permute(3, 2, 0, 1).contiguous()
         if ctx.needs_input_grad[0]:
-            w_d = weight.detach().flip(2, 3).transpose(0, 1).contiguous()         # [Cin, Cout, k, k]
-            w_simt, w_tc = pack_conv_weight(w_d, tc=tc)
+            w_simt, w_tc = pack_conv_weight(weight, tc=tc, flip_transpose=True)   # flipped taps, [Cin, Cout] roles exchanged
             if stride == 1:
                 src = gps
             else:
@@ -654,7 +681,7 @@ class _ConvFn(torch.autograd.Function):
                 up[:, ::stride, ::stride, :][:, :Ho, :Wo] = gp
                 src = Slice(up, 0, Cout)
             gxb = _new(a.N, a.H, a.W, Cin, grad)
-            zero_b = torch.zeros(Cin, dtype=torch.float32, device=grad.device)
+            zero_b = _zero_bias(Cin, grad.device)
             k_conv(src, w_tc if tc else w_simt, zero_b, gxb, ks, 1, dilation, 1.0, None, precision)
             gx = gxb.permute(0, 3, 1, 2)
         return gx, gw, gb, None, None, None, None
