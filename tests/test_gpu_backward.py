@@ -398,3 +398,46 @@ def test_repack_conv_weight_kernel(upf, shape):
     want_d = torch.zeros(k * k, Cout, pad(Cin), device="cuda")
     want_d[:, :, :Cin] = w_d.permute(2, 3, 1, 0).reshape(k * k, Cout, Cin)
     assert torch.equal(got_d, want_d)
+
+
+@pytest.mark.parametrize("case", [("fp32", 115, (128, 128, 96, 64, 32), 2, 2, 24, 40), ("tf32", 115, (128, 128, 96, 64, 32), 2, 2, 24, 40),
+                                  ("fp32", 64, (32, 32, 32, 16, 8), 3, 2, 20, 28), ("tf32", 64, (32, 32, 32, 16, 8), 3, 1, 64, 96),
+                                  ("fp32", 13, (8, 6), 2, 1, 9, 11)])
+def test_dense_block_node_vs_reference_data_flow(case):
+    """ops.dense_block (one autograd node on an append-only buffer; backward: one K-concatenated input-gradient
+    convolution per channel block) against the reference's own data flow -- torch.cat after every conv (model/pwc_modules.py:279-286)
+    with one autograd node per conv: same forward values, gradients of the input and of all 2(n+1) parameters to 2e-5
+    (fp32) / 3e-3 (TF32: the two paths sum the same products in a different order) of their largest entry."""
+    import upflow_pytorch_b200
+    upflow_pytorch_b200.install_dropin()
+    from model import pwc_modules
+    precision, ch_in, f, cout, B, H, W = case
+    pwc_modules.set_conv_precision(precision)
+    torch.manual_seed(3)
+    blk = pwc_modules.FlowEstimatorDense_v2(ch_in, f_channels=f, out_channel=cout).cuda().train()
+    for p_ in blk.parameters():
+        if p_.dim() == 1:
+            torch.nn.init.normal_(p_, std=0.1)
+    x = _rand(1, B, ch_in, H, W).cuda().requires_grad_()
+    total = ch_in + sum(f)
+    r5, ro = _rand(2, B, total, H, W).cuda(), _rand(3, B, cout, H, W).cuda()
+    res = {}
+    try:
+        for fused in (True, False):
+            pwc_modules._DenseBlock.fused_training_block = fused
+            blk.zero_grad(set_to_none=True)
+            x5, out = blk(x)
+            assert x5.shape == (B, total, H, W) and out.shape == (B, cout, H, W)
+            ((x5 * r5).sum() + (out * ro).sum()).backward()
+            res[fused] = (x5.detach().clone(), out.detach().clone(), x.grad.clone(),
+                          {n: p_.grad.clone() for n, p_ in blk.named_parameters()})
+            x.grad = None
+    finally:
+        pwc_modules._DenseBlock.fused_training_block = True
+        pwc_modules.set_conv_precision("fp32")
+    tol_f, tol_g = (1e-6, 2e-5) if precision == "fp32" else (1e-5, 3e-3)
+    _check("x5", _rel(res[True][0], res[False][0]), tol_f)
+    _check("conv_last", _rel(res[True][1], res[False][1]), tol_f)
+    _check("grad x", _rel(res[True][2], res[False][2]), tol_g)
+    for n in res[False][3]:
+        _check("grad " + n, _rel(res[True][3][n], res[False][3][n]), tol_g)

@@ -131,6 +131,8 @@ class _DenseBlock(tools.abstract_model):
     (model/upflow.py:24-60): convs run into one append-only pixel-major buffer, then x5 is assembled in the
     reference's channel order [conv5, conv4, conv3, conv2, conv1, x]."""
 
+    fused_training_block = True
+
     def _build(self, ch_in, f_channels, out_channel):
         N = ch_in
         for i, c in enumerate(f_channels):
@@ -143,10 +145,16 @@ class _DenseBlock(tools.abstract_model):
     def forward(self, x):
         ops._require_cuda(x)
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            # training: the reference's own data flow (model/pwc_modules.py:279-286), every conv an autograd node
-            for i in range(len(self._f)):
-                x = torch.cat([getattr(self, "conv%d" % (i + 1))(x), x], dim=1)
-            return x, self.conv_last(x)
+            # training: one autograd node over the same append-only buffer as below (ops.dense_block); the reference's
+            # own data flow, torch.cat after every conv (model/pwc_modules.py:279-286), stays as the A/B partner
+            if not self.fused_training_block:
+                for i in range(len(self._f)):
+                    x = torch.cat([getattr(self, "conv%d" % (i + 1))(x), x], dim=1)
+                return x, self.conv_last(x)
+            params = []
+            for blk in [getattr(self, "conv%d" % (i + 1)) for i in range(len(self._f))] + [self.conv_last]:
+                params += [blk[0].weight, blk[0].bias]
+            return ops.dense_block(x, self._f, params, _PRECISION["mode"])
         B, C, H, W = x.shape
         total = C + sum(self._f)
         ld = (total + 3) // 4 * 4

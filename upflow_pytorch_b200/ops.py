@@ -651,40 +651,142 @@ class _ConvFn(torch.autograd.Function):
     def backward(ctx, grad):
         abuf, out, weight = ctx.saved_tensors
         Cin, stride, dilation, slope, precision = ctx.cfg
-        Cout, _, ks, _ = weight.shape
-        a = Slice(abuf, 0, Cin)
-        tc = precision == _ext.CONV_TF32
-        N, Ho, Wo, _ = out.shape
-        g = to_pixel_major(grad)
-        ldg = (Cout + 3) // 4 * 4
-        if slope != 1.0 or ldg != Cout:
-            gp = torch.zeros(N, Ho, Wo, ldg, dtype=torch.float32, device=grad.device) if ldg != Cout else \
-                torch.empty(N, Ho, Wo, ldg, dtype=torch.float32, device=grad.device)
-            if slope != 1.0:
-                k_pointwise(_ext.PW_LRELU_BWD, out, g, Slice(gp, 0, Cout), slope)
-            else:
-                k_copy(Slice(g), Slice(gp, 0, Cout))
+        gxb, gw, gb = _conv_backward(Slice(abuf, 0, Cin), Slice(out), weight, Slice(to_pixel_major(grad)), stride, dilation,
+                                     slope, precision, ctx.needs_input_grad[1] or ctx.needs_input_grad[2],
+                                     ctx.needs_input_grad[0])
+        return gxb.permute(0, 3, 1, 2) if gxb is not None else None, gw, gb, None, None, None, None
+
+
+def _conv_backward(a, act, weight, g, stride, dilation, slope, precision, need_w, need_x):
+    """Backward of one conv() call on pixel-major slices.  a: the input slice; act: the saved OUTPUT slice (LeakyReLU
+    derivative); g: gradient wrt the output.  Returns (gx buffer or None, grad weight [Cout,Cin,k,k] or None, grad
+    bias or None)."""
+    Cout, Cin, ks, _ = weight.shape
+    tc = precision == _ext.CONV_TF32
+    N, Ho, Wo = g.N, g.H, g.W
+    ldg = (Cout + 3) // 4 * 4
+    if slope != 1.0 or ldg != Cout or g.ld != Cout:
+        gp = torch.zeros(N, Ho, Wo, ldg, dtype=torch.float32, device=g.buf.device) if ldg != Cout else \
+            torch.empty(N, Ho, Wo, ldg, dtype=torch.float32, device=g.buf.device)
+        if slope != 1.0:
+            k_pointwise(_ext.PW_LRELU_BWD, act, g, Slice(gp, 0, Cout), slope)
         else:
-            gp = g
-        gps = Slice(gp, 0, Cout)
-        gx = gw = gb = None
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            gw_t, gb = k_conv_wgrad(a, gps, ks, stride, dilation, want_bias=True, tensor_cores=tc)
-            gw = gw_t.reshape(ks, ks, Cin, Cout).permute(3, 2, 0, 1).contiguous()
-        if ctx.needs_input_grad[0]:
-            w_simt, w_tc = pack_conv_weight(weight, tc=tc, flip_transpose=True)   # flipped taps, [Cin, Cout] roles exchanged
-            if stride == 1:
-                src = gps
+            k_copy(g, Slice(gp, 0, Cout))
+    else:
+        gp = g.buf
+    gps = Slice(gp, 0, Cout)
+    gxb = gw = gb = None
+    if need_w:
+        gw_t, gb = k_conv_wgrad(a, gps, ks, stride, dilation, want_bias=True, tensor_cores=tc)
+        gw = gw_t.reshape(ks, ks, Cin, Cout).permute(3, 2, 0, 1).contiguous()
+    if need_x:
+        w_simt, w_tc = pack_conv_weight(weight, tc=tc, flip_transpose=True)   # flipped taps, [Cin, Cout] roles exchanged
+        if stride == 1:
+            src = gps
+        else:
+            # adjoint of a strided convolution = stride-1 convolution of the zero-interleaved gradient
+            up = torch.zeros(N, a.H, a.W, ldg, dtype=torch.float32, device=g.buf.device)
+            up[:, ::stride, ::stride, :][:, :Ho, :Wo] = gp
+            src = Slice(up, 0, Cout)
+        gxb = _new(a.N, a.H, a.W, Cin, g.buf)
+        k_conv(src, w_tc if tc else w_simt, _zero_bias(Cin, g.buf.device), Slice(gxb), ks, 1, dilation, 1.0, None, precision)
+    return gxb, gw, gb
+
+
+class _DenseBlockFn(torch.autograd.Function):
+    """FlowEstimatorDense_v2.forward (model/pwc_modules.py:279-286) and the SGU dense block (model/upflow.py:52-60) as
+    ONE autograd node on an append-only pixel-major buffer [conv_n | ... | conv1 | x]: convolution i reads the suffix
+    that exists so far and writes its output in front of it, so the reference's torch.cat calls (and, backward, the
+    slice / add kernels autograd makes of them) disappear.  Backward: see there.  params = (w1, b1, ..., wn, bn, w_last, b_last).  Returns (x_n, conv_last(x_n)) in NCHW views."""
+
+    @staticmethod
+    def forward(ctx, x, f_channels, precision, *params):
+        B, C, H, W = x.shape
+        n = len(f_channels)
+        total = C + sum(f_channels)
+        ld = (total + 3) // 4 * 4
+        buf = torch.zeros(B, H, W, ld, dtype=torch.float32, device=x.device)
+        lo = total - C
+        k_copy(Slice(to_pixel_major(x)), Slice(buf, lo, C))
+        los, precs = [], []
+        for i in range(n + 1):
+            weight, bias = params[2 * i], params[2 * i + 1]
+            prec = _ext.CONV_FP32 if (lo % 4) else precision      # the tensor-core kernels read 16-byte aligned slices
+            tc = prec == _ext.CONV_TF32
+            w_simt, w_tc = pack_conv_weight(weight, tc=tc)
+            bvec = bias.detach().float().contiguous()
+            los.append(lo)
+            precs.append(prec)
+            if i < n:
+                c = f_channels[i]
+                k_conv(Slice(buf, lo, total - lo), w_tc if tc else w_simt, bvec, Slice(buf, lo - c, c), 3, 1, 1, LRELU_SLOPE,
+                       None, prec)
+                lo -= c
             else:
-                # adjoint of a strided convolution = stride-1 convolution of the zero-interleaved gradient
-                up = torch.zeros(N, a.H, a.W, ldg, dtype=torch.float32, device=grad.device)
-                up[:, ::stride, ::stride, :][:, :Ho, :Wo] = gp
-                src = Slice(up, 0, Cout)
-            gxb = _new(a.N, a.H, a.W, Cin, grad)
-            zero_b = _zero_bias(Cin, grad.device)
-            k_conv(src, w_tc if tc else w_simt, zero_b, gxb, ks, 1, dilation, 1.0, None, precision)
-            gx = gxb.permute(0, 3, 1, 2)
-        return gx, gw, gb, None, None, None, None
+                cout = weight.shape[0]
+                out = torch.empty(B, H, W, cout, dtype=torch.float32, device=x.device)
+                k_conv(Slice(buf, 0, total), w_tc if tc else w_simt, bvec, Slice(out), 3, 1, 1, 1.0, None, prec)
+        ctx.save_for_backward(buf, *params[0::2])
+        ctx.cfg = (C, tuple(f_channels), total, tuple(los), tuple(precs), precision)
+        return buf[..., :total].permute(0, 3, 1, 2), out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g_x5, g_out):
+        # Each channel block of the buffer is read by every LATER convolution, so its gradient is a sum over those
+        # convolutions.  Instead of accumulating n nested input gradients (every convolution writing the whole suffix
+        # it read: 3x the bytes, and the accumulate is an uncoalesced read in the tensor-core epilogue), the
+        # pre-activation output gradients live in a second append-only buffer GP = [gp_1 | ... | gp_n | gp_last], and
+        # the gradient of block i is ONE convolution of the suffix behind gp_i with the consumers' weight slices
+        # concatenated along K (flipped / transposed), written once, with the incoming x_n gradient as its residual.
+        buf, *weights = ctx.saved_tensors
+        C, f, total, los, precs, precision = ctx.cfg
+        n = len(f)
+        B, H, W, _ = buf.shape
+        cout = weights[n].shape[0]
+        need = ctx.needs_input_grad
+        offs = [sum(f[:i]) for i in range(n + 1)]              # offs[i]: where gp of convolution i starts (i == n: conv_last)
+        gp_w = offs[n] + cout
+        GP = torch.zeros(B, H, W, (gp_w + 3) // 4 * 4, dtype=torch.float32, device=buf.device)
+        g5 = to_pixel_major(g_x5) if g_x5 is not None else None
+        if g_out is not None:
+            k_copy(Slice(to_pixel_major(g_out)), Slice(GP, offs[n], cout))
+        grads = [None] * (2 * n + 2)
+
+        def param_grads(i, c):
+            if need[3 + 2 * i] or need[4 + 2 * i]:
+                gw_t, gb = k_conv_wgrad(Slice(buf, los[i], total - los[i]), Slice(GP, offs[i], c), 3, 1, 1, want_bias=True,
+                                        tensor_cores=precs[i] == _ext.CONV_TF32)
+                grads[2 * i] = gw_t.reshape(3, 3, total - los[i], c).permute(3, 2, 0, 1).contiguous()
+                grads[2 * i + 1] = gb
+
+        def block_grad(first, s, c):
+            """Gradient of buffer channels [s, s+c): consumers are convolutions first..n."""
+            wcat = torch.cat([weights[m][:, s - los[m]:s - los[m] + c] for m in range(first, n + 1)], dim=0)
+            prec = _ext.CONV_FP32 if (offs[first] % 4) else precision
+            tc = prec == _ext.CONV_TF32
+            w_simt, w_tc = pack_conv_weight(wcat, tc=tc, flip_transpose=True)
+            gblk = _new(B, H, W, c, buf)
+            k_conv(Slice(GP, offs[first], gp_w - offs[first]), w_tc if tc else w_simt, _zero_bias(c, buf.device), Slice(gblk), 3, 1,
+                   1, 1.0, Slice(g5, s, c) if g5 is not None else None, prec)
+            return gblk
+
+        param_grads(n, cout)
+        for i in range(n - 1, -1, -1):
+            c, s = f[i], los[i] - f[i]
+            gblk = block_grad(i + 1, s, c)
+            k_pointwise(_ext.PW_LRELU_BWD, Slice(buf, s, c), Slice(gblk), Slice(GP, offs[i], c), LRELU_SLOPE)
+            param_grads(i, c)
+        gx = block_grad(0, total - C, C).permute(0, 3, 1, 2) if need[0] else None
+        return (gx, None, None) + tuple(grads)
+
+
+def dense_block(x, f_channels, params, precision=_ext.CONV_FP32):
+    """The dense estimator block with autograd (training path): x [B,C,H,W], params = (w1, b1, ..., wn, bn, w_last,
+    b_last) as nn.Conv2d parameters.  Returns (x_n [B, C+sum(f), H, W] in the reference's order, conv_last(x_n))."""
+    _require_cuda(x, *params)
+    if len(params) != 2 * len(f_channels) + 2:
+        raise ValueError("dense_block: %d parameters for %d convolutions" % (len(params), len(f_channels) + 1))
+    return _DenseBlockFn.apply(x, tuple(int(c) for c in f_channels), int(precision), *params)
 
 
 def conv2d_autograd(x, weight, bias, stride=1, dilation=1, slope=LRELU_SLOPE, precision=_ext.CONV_FP32):
