@@ -197,6 +197,16 @@ int upf_conv2d_wgrad(const float* x, int ldx, const float* grad_out, int ldg, fl
 long long upf_conv2d_wgrad_tc_workspace_elems(int N, int H, int W, int Cin, int Cout, int ksize, int dilation);
 int upf_conv2d_wgrad_tc(const float* x, int ldx, const float* grad_out, int ldg, float* grad_w, float* grad_bias,
                         float* workspace, int N, int H, int W, int Cin, int Cout, int ksize, int dilation, void* stream);
+/* The same with the input transposed once for several convolutions that read nested channel ranges of one buffer
+ * (the dense blocks): upf_wgrad_tc_transpose_input writes xt [C][pitch] (pitch = upf_wgrad_tc_planar_pitch, planar,
+ * zero-padded); a convolution whose input is channels [c0, c0+Cin) of that buffer passes xt + c0*pitch.  All of them
+ * must share ksize and dilation.  workspace as for upf_conv2d_wgrad_tc. */
+long long upf_wgrad_tc_planar_pitch(int N, int H, int W, int ksize, int dilation);
+int upf_wgrad_tc_transpose_input(const float* x, int ldx, int C, float* xt, int N, int H, int W, int ksize, int dilation,
+                                 void* stream);
+int upf_conv2d_wgrad_tc_planar(const float* xt, const float* grad_out, int ldg, float* grad_w, float* grad_bias,
+                               float* workspace, int N, int H, int W, int Cin, int Cout, int ksize, int dilation,
+                               void* stream);
 
 /* pointwise ops on [npix][C] pitched tensors.  op 0: out = b * (a > 0 ? 1 : slope)  (LeakyReLU backward from the
  * saved output a and the incoming gradient b); op 1: out = sigmoid(a); op 2: out = b * a * (1 - a) (sigmoid

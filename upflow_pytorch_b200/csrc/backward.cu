@@ -593,14 +593,17 @@ extern "C" long long upf_conv2d_wgrad_tc_workspace_elems(int N, int H, int W, in
   const long long cout_pad = (Cout + 15) / 16 * 16;
   return (long long)Cin * Kp + 3 * cout_pad * Kp + cout_pad + (long long)UPF_BIAS_SPLITS * Cout + 64;
 }
-extern "C" int upf_conv2d_wgrad_tc(const float* x, int ldx, const float* grad_out, int ldg, float* grad_w, float* grad_bias,
-                                   float* workspace, int N, int H, int W, int Cin, int Cout, int ksize, int dilation,
-                                   void* stream) {
+// x != NULL: transpose the input here; xt_pre != NULL: the caller already holds the planar padded input (rows of
+// upf_wgrad_tc_transpose_input's output -- a dense block transposes its whole buffer ONCE and every convolution of the
+// block reads its own suffix of rows)
+static int wgrad_tc_impl(const float* x, int ldx, const float* xt_pre, const float* grad_out, int ldg, float* grad_w,
+                         float* grad_bias, float* workspace, int N, int H, int W, int Cin, int Cout, int ksize, int dilation,
+                         cudaStream_t st) {
   using namespace upf;
-  UPF_REQUIRE(x && grad_out && grad_w && workspace, "wgrad_tc: null tensor");
+  UPF_REQUIRE((x || xt_pre) && grad_out && grad_w && workspace, "wgrad_tc: null tensor");
   UPF_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (ksize == 1 || ksize == 3) && dilation >= 1, "wgrad_tc: bad shape");
-  UPF_REQUIRE(ldx >= Cin && ldg >= Cout && aligned16(workspace), "wgrad_tc: bad pitch / workspace alignment");
-  cudaStream_t st = (cudaStream_t)stream;
+  UPF_REQUIRE((xt_pre || ldx >= Cin) && ldg >= Cout && aligned16(workspace) && (!xt_pre || aligned16(xt_pre)),
+              "wgrad_tc: bad pitch / workspace alignment");
   const int pad = ((ksize - 1) * dilation) / 2, taps = ksize * ksize;
   const int Wp = wgrad_tc_wp(W, ksize, dilation);
   const long long Kp = wgrad_tc_kp(N, H, W, ksize, dilation);
@@ -609,15 +612,18 @@ extern "C" int upf_conv2d_wgrad_tc(const float* x, int ldx, const float* grad_ou
   const long long P = (long long)N * H * W;
   const int ncopies = ksize == 1 ? 1 : 3;
   float* xt = workspace;
-  float* gt = xt + (size_t)Cin * Kp;                      // [3][cout_pad][Kp]: G written at k + (kx-1)*dil
+  float* gt = xt + (xt_pre ? 0 : (size_t)Cin * Kp);       // [3][cout_pad][Kp]: G written at k + (kx-1)*dil
   float* zb = gt + (size_t)3 * cout_pad * Kp;
   float* bpart = zb + cout_pad;
-  cudaError_t ce = cudaMemsetAsync(workspace, 0, ((size_t)Cin * Kp + (size_t)3 * cout_pad * Kp + cout_pad) * sizeof(float), st);
+  cudaError_t ce = cudaMemsetAsync(workspace, 0, (size_t)((char*)(zb + cout_pad) - (char*)workspace), st);
   if (ce != cudaSuccess) { set_error("wgrad_tc memset: %s", cudaGetErrorString(ce)); return (int)ce; }
   const unsigned ptiles = (unsigned)((P + 31) / 32);
-  nhwc_to_planar_padded_kernel<<<dim3(ptiles, (Cin + 31) / 32), 256, 0, st>>>(x, ldx, Cin, xt, Kp, P, H, W, pad, Wp, 0, 1, 0, 0);
-  int e = check_launch("wgrad_tc_transpose_x");
-  if (e) return e;
+  int e = 0;
+  if (!xt_pre) {
+    nhwc_to_planar_padded_kernel<<<dim3(ptiles, (Cin + 31) / 32), 256, 0, st>>>(x, ldx, Cin, xt, Kp, P, H, W, pad, Wp, 0, 1, 0, 0);
+    e = check_launch("wgrad_tc_transpose_x");
+    if (e) return e;
+  }
   // the three horizontally shifted copies of G in one pass: one read, three writes
   nhwc_to_planar_padded_kernel<<<dim3(ptiles, (Cout + 31) / 32), 256, 0, st>>>(grad_out, ldg, Cout, gt, Kp, P, H, W, pad, Wp,
                                                                                 ksize == 1 ? 0 : -dilation, ncopies,
@@ -630,7 +636,7 @@ extern "C" int upf_conv2d_wgrad_tc(const float* x, int ldx, const float* grad_ou
     koffs[t] = ksize == 1 ? 0 : (ky - 1) * dilation * Wp;          // multiple of 4
     wsel[t] = ksize == 1 ? 0 : kx;
   }
-  e = conv_tc_wgrad_gemm(xt, (int)Kp, gt, zb, grad_w, taps, Cin, Cout, (int)Kp, koffs, wsel, st);
+  e = conv_tc_wgrad_gemm(xt_pre ? xt_pre : xt, (int)Kp, gt, zb, grad_w, taps, Cin, Cout, (int)Kp, koffs, wsel, st);
   if (e) return e;
   if (grad_bias) {
     int cw = 1;
@@ -645,6 +651,41 @@ extern "C" int upf_conv2d_wgrad_tc(const float* x, int ldx, const float* grad_ou
     e = check_launch("bias_reduce");
   }
   return e;
+}
+
+extern "C" int upf_conv2d_wgrad_tc(const float* x, int ldx, const float* grad_out, int ldg, float* grad_w, float* grad_bias,
+                                   float* workspace, int N, int H, int W, int Cin, int Cout, int ksize, int dilation,
+                                   void* stream) {
+  UPF_REQUIRE(x, "wgrad_tc: null input");
+  return wgrad_tc_impl(x, ldx, nullptr, grad_out, ldg, grad_w, grad_bias, workspace, N, H, W, Cin, Cout, ksize, dilation,
+                       (cudaStream_t)stream);
+}
+
+extern "C" long long upf_wgrad_tc_planar_pitch(int N, int H, int W, int ksize, int dilation) {
+  return wgrad_tc_kp(N, H, W, ksize, dilation);
+}
+
+extern "C" int upf_wgrad_tc_transpose_input(const float* x, int ldx, int C, float* xt, int N, int H, int W, int ksize,
+                                            int dilation, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(x && xt && N > 0 && H > 0 && W > 0 && C > 0 && ldx >= C && (ksize == 1 || ksize == 3) && dilation >= 1 &&
+                  aligned16(xt), "wgrad_tc_transpose_input: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pad = ((ksize - 1) * dilation) / 2;
+  const long long Kp = wgrad_tc_kp(N, H, W, ksize, dilation), P = (long long)N * H * W;
+  cudaError_t ce = cudaMemsetAsync(xt, 0, (size_t)C * Kp * sizeof(float), st);
+  if (ce != cudaSuccess) { set_error("wgrad_tc_transpose_input memset: %s", cudaGetErrorString(ce)); return (int)ce; }
+  nhwc_to_planar_padded_kernel<<<dim3((unsigned)((P + 31) / 32), (C + 31) / 32), 256, 0, st>>>(
+      x, ldx, C, xt, Kp, P, H, W, pad, wgrad_tc_wp(W, ksize, dilation), 0, 1, 0, 0);
+  return check_launch("wgrad_tc_transpose_x");
+}
+
+extern "C" int upf_conv2d_wgrad_tc_planar(const float* xt, const float* grad_out, int ldg, float* grad_w, float* grad_bias,
+                                          float* workspace, int N, int H, int W, int Cin, int Cout, int ksize, int dilation,
+                                          void* stream) {
+  UPF_REQUIRE(xt, "wgrad_tc_planar: null input");
+  return wgrad_tc_impl(nullptr, 0, xt, grad_out, ldg, grad_w, grad_bias, workspace, N, H, W, Cin, Cout, ksize, dilation,
+                       (cudaStream_t)stream);
 }
 
 extern "C" int upf_act_split(const float* t, int ldt, const float* residual, int ldr, float* out, int ldo, float* out_lo, int ldlo,

@@ -180,9 +180,22 @@ def k_conv(x, weight, bias, out, ksize, stride=1, dilation=1, slope=LRELU_SLOPE,
                                      float(slope), int(precision), _stream()), "conv2d_fwd")
 
 
-def k_conv_wgrad(x, grad_out, ksize, stride=1, dilation=1, want_bias=True, tensor_cores=False):
+def k_wgrad_planar_input(x, ksize, dilation=1):
+    """The planar, zero-padded transpose of slice x that the tensor-core weight gradient reads, made ONCE for several
+    convolutions whose inputs are nested channel ranges of x (same ksize / dilation).  Returns (xt, pitch): the rows
+    of channel c start at xt[c * pitch]."""
+    x = _as_slice(x)
+    pitch = int(_lib().upf_wgrad_tc_planar_pitch(x.N, x.H, x.W, ksize, dilation))
+    xt = torch.empty(x.C * pitch, dtype=torch.float32, device=x.buf.device)
+    _ext.check(_lib().upf_wgrad_tc_transpose_input(x.ptr(), x.ld, x.C, _p(xt), x.N, x.H, x.W, ksize, dilation, _stream()),
+               "wgrad_tc_transpose_input")
+    return xt, pitch
+
+
+def k_conv_wgrad(x, grad_out, ksize, stride=1, dilation=1, want_bias=True, tensor_cores=False, planar=None):
     """Weight gradient [k*k, Cin, Cout] and bias gradient [Cout] of conv() from its input and the gradient wrt its
-    PRE-activation output (both pixel-major).  tensor_cores: TF32 tcgen05 GEMM (stride 1), else fp32 SIMT."""
+    PRE-activation output (both pixel-major).  tensor_cores: TF32 tcgen05 GEMM (stride 1), else fp32 SIMT.
+    planar = (xt, pitch, c0): k_wgrad_planar_input's transpose of a buffer whose channels [c0, c0 + x.C) are x."""
     x, g = _as_slice(x), _as_slice(grad_out)
     lib = _lib()
     if tensor_cores and stride == 1:
@@ -190,8 +203,13 @@ def k_conv_wgrad(x, grad_out, ksize, stride=1, dilation=1, want_bias=True, tenso
         ws = torch.empty(n, dtype=torch.float32, device=x.buf.device)
         gw = torch.empty(ksize * ksize, x.C, g.C, dtype=torch.float32, device=x.buf.device)
         gb = torch.empty(g.C, dtype=torch.float32, device=x.buf.device) if want_bias else None
-        _ext.check(lib.upf_conv2d_wgrad_tc(x.ptr(), x.ld, g.ptr(), g.ld, _p(gw), _p(gb), _p(ws), x.N, x.H, x.W, x.C, g.C,
-                                           ksize, dilation, _stream()), "conv2d_wgrad_tc")
+        if planar is not None:
+            xt, pitch, c0 = planar
+            _ext.check(lib.upf_conv2d_wgrad_tc_planar(_p(xt, c0 * pitch), g.ptr(), g.ld, _p(gw), _p(gb), _p(ws), x.N, x.H, x.W,
+                                                      x.C, g.C, ksize, dilation, _stream()), "conv2d_wgrad_tc_planar")
+        else:
+            _ext.check(lib.upf_conv2d_wgrad_tc(x.ptr(), x.ld, g.ptr(), g.ld, _p(gw), _p(gb), _p(ws), x.N, x.H, x.W, x.C, g.C,
+                                               ksize, dilation, _stream()), "conv2d_wgrad_tc")
         return gw, gb
     n = lib.upf_conv2d_wgrad_workspace_elems(x.N, x.H, x.W, x.C, g.C, ksize, stride, dilation)
     ws = torch.empty(n, dtype=torch.float32, device=x.buf.device)
@@ -752,10 +770,14 @@ class _DenseBlockFn(torch.autograd.Function):
             k_copy(Slice(to_pixel_major(g_out)), Slice(GP, offs[n], cout))
         grads = [None] * (2 * n + 2)
 
+        # the convolutions' inputs are nested suffixes of buf: transpose it once for all the tensor-core weight gradients
+        xt = k_wgrad_planar_input(Slice(buf, 0, total), 3, 1) if any(p == _ext.CONV_TF32 for p in precs) else None
+
         def param_grads(i, c):
             if need[3 + 2 * i] or need[4 + 2 * i]:
                 gw_t, gb = k_conv_wgrad(Slice(buf, los[i], total - los[i]), Slice(GP, offs[i], c), 3, 1, 1, want_bias=True,
-                                        tensor_cores=precs[i] == _ext.CONV_TF32)
+                                        tensor_cores=precs[i] == _ext.CONV_TF32,
+                                        planar=(xt[0], xt[1], los[i]) if xt is not None else None)
                 grads[2 * i] = gw_t.reshape(3, 3, total - los[i], c).permute(3, 2, 0, 1).contiguous()
                 grads[2 * i + 1] = gb
 
