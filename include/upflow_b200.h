@@ -248,6 +248,9 @@ int upf_resize_bilinear_bwd(const float* grad_out, int ldgo, int H, int W, float
  * convolution (Cout = A, Cin = B).  flip_transpose 1: the weights of the input-gradient convolution -- taps flipped,
  * channel roles exchanged (Cin = A, Cout = B). */
 int upf_repack_conv_weight(const float* weight, float* out, int A, int B, int ksize, int flip_transpose, void* stream);
+/* the same straight into the tensor-core layout of upf_conv_tc_pack_weights (upf_conv_tc_packed_elems floats) */
+int upf_repack_conv_weight_tc(const float* weight, float* w_packed, int A, int B, int ksize, int flip_transpose,
+                              void* stream);
 
 /* Loss terms of the training step on pixel-major tensors, each ONE reduction pass forward
  * (deterministic: per-CTA partials summed in a fixed order) and one elementwise pass backward.

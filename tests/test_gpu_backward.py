@@ -441,3 +441,14 @@ def test_dense_block_node_vs_reference_data_flow(case):
     _check("grad x", _rel(res[True][2], res[False][2]), tol_g)
     for n in res[False][3]:
         _check("grad " + n, _rel(res[True][3][n], res[False][3][n]), tol_g)
+
+
+@pytest.mark.parametrize("shape", [(20, 12, 3), (2, 3, 3), (7, 5, 1), (196, 128, 3), (115, 226, 3)])
+@pytest.mark.parametrize("flip", [False, True])
+def test_repack_conv_weight_tc_kernel_matches_two_step_packing(upf, shape, flip):
+    """upf_repack_conv_weight_tc (one launch) == upf_repack_conv_weight followed by upf_conv_tc_pack_weights, bit-exact."""
+    Cout, Cin, k = shape
+    w = _rand(10, Cout, Cin, k, k).cuda()
+    _, two_step = upf.pack_conv_weight(w, tc=True, flip_transpose=flip)
+    none, one = upf.pack_conv_weight(w, tc=True, flip_transpose=flip, tc_only=True)
+    assert none is None and torch.equal(one, two_step)

@@ -53,6 +53,7 @@ SIGNATURES = {
     "upf_resize_bilinear_bwd_workspace_elems": (_LL, [_I, _I, _I, _I]),
     "upf_resize_bilinear_bwd": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _c.POINTER(_F), _P, _P]),
     "upf_repack_conv_weight": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "upf_repack_conv_weight_tc": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "upf_loss_workspace_elems": (_LL, []),
     "upf_robust_loss_fwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _LL, _I, _I, _F, _P]),
     "upf_robust_loss_bwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _P, _I, _LL, _I, _I, _F, _P]),

@@ -298,6 +298,22 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
   }
 }
 
+// nn.Conv2d weight [A][B][k][k] -> packed [tap][cout_pad16][cin_pad32] in one launch (upf_repack_conv_weight followed
+// by pack_weights_kernel, fused: the training path packs every weight twice per step).  flip_transpose as there.
+__global__ void repack_weights_tc_kernel(const float* __restrict__ w, float* __restrict__ wp, int Cin, int Cout, int taps,
+                                         int cout_pad16, int cin_pad32, int flip_transpose) {
+  const long long total = (long long)taps * cout_pad16 * cin_pad32;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin_pad32);
+    const int co = (int)((i / cin_pad32) % cout_pad16);
+    const int tap = (int)(i / ((long long)cin_pad32 * cout_pad16));
+    float v = 0.f;
+    if (ci < Cin && co < Cout)
+      v = flip_transpose ? __ldg(w + ((size_t)ci * Cout + co) * taps + (taps - 1 - tap)) : __ldg(w + ((size_t)co * Cin + ci) * taps + tap);
+    wp[i] = v;
+  }
+}
+
 // ---------------------------------------------------------------- tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -508,4 +524,18 @@ extern "C" int upf_conv_tc_pack_weights(const float* w_simt, float* w_packed, in
   pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w_simt, w_packed, Cin, Cout, taps, cout_pad4,
                                                                          cout_pad16, cin_pad32);
   return check_launch("pack_weights");
+}
+
+extern "C" int upf_repack_conv_weight_tc(const float* weight, float* w_packed, int A, int B, int ksize, int flip_transpose,
+                                         void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(weight && w_packed && A > 0 && B > 0 && (ksize == 1 || ksize == 3), "repack_conv_weight_tc: bad argument");
+  const int Cin = flip_transpose ? A : B, Cout = flip_transpose ? B : A, taps = ksize * ksize;
+  const int cout_pad16 = (Cout + 15) & ~15, cin_pad32 = (Cin + 31) / 32 * 32;
+  const long long total = (long long)taps * cout_pad16 * cin_pad32;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  repack_weights_tc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(weight, w_packed, Cin, Cout, taps, cout_pad16,
+                                                                              cin_pad32, flip_transpose ? 1 : 0);
+  return check_launch("repack_weights_tc");
 }

@@ -282,10 +282,11 @@ def k_copy(src, dst):
 
 
 # ---------------------------------------------------------------- weights
-def pack_conv_weight(weight, in_slots=None, cin_total=None, tc=False, flip_transpose=False):
+def pack_conv_weight(weight, in_slots=None, cin_total=None, tc=False, flip_transpose=False, tc_only=False):
     """nn.Conv2d weight [Cout,Cin,k,k] -> library layouts.
 
     flip_transpose: the weights of the input-gradient convolution instead (taps flipped, Cin and Cout exchanged).
+    tc_only (with tc): only the tensor-core layout, in one launch; the first element of the result is None.
 
     in_slots[i] = position, inside the input slice the kernel reads, of the
     reference's input channel i (identity when None); cin_total = width of that
@@ -300,6 +301,11 @@ def pack_conv_weight(weight, in_slots=None, cin_total=None, tc=False, flip_trans
         _require_cuda(src)
         if flip_transpose:
             Cout, Cin = Cin, Cout
+        if tc and tc_only:
+            w_tc = torch.empty(_lib().upf_conv_tc_packed_elems(Cin, Cout, k), dtype=torch.float32, device=weight.device)
+            _ext.check(_lib().upf_repack_conv_weight_tc(_p(src), _p(w_tc), weight.shape[0], weight.shape[1], k,
+                                                        1 if flip_transpose else 0, _stream()), "repack_conv_weight_tc")
+            return None, w_tc
         w = torch.empty(k * k, Cin, (Cout + 3) // 4 * 4, dtype=torch.float32, device=weight.device)
         _ext.check(_lib().upf_repack_conv_weight(_p(src), _p(w), weight.shape[0], weight.shape[1], k,
                                                  1 if flip_transpose else 0, _stream()), "repack_conv_weight")
@@ -654,7 +660,7 @@ class _ConvFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, stride, dilation, slope, precision):
         Cout, Cin, ks, _ = weight.shape
         tc = precision == _ext.CONV_TF32
-        w_simt, w_tc = pack_conv_weight(weight, tc=tc)
+        w_simt, w_tc = pack_conv_weight(weight, tc=tc, tc_only=True)
         a = Slice(to_pixel_major(x, ld=(Cin + 3) // 4 * 4), 0, Cin) if (tc and Cin % 4) else Slice(to_pixel_major(x))
         pad = ((ks - 1) * dilation) // 2
         Ho = (a.H + 2 * pad - dilation * (ks - 1) - 1) // stride + 1
@@ -698,7 +704,7 @@ def _conv_backward(a, act, weight, g, stride, dilation, slope, precision, need_w
         gw_t, gb = k_conv_wgrad(a, gps, ks, stride, dilation, want_bias=True, tensor_cores=tc)
         gw = gw_t.reshape(ks, ks, Cin, Cout).permute(3, 2, 0, 1).contiguous()
     if need_x:
-        w_simt, w_tc = pack_conv_weight(weight, tc=tc, flip_transpose=True)   # flipped taps, [Cin, Cout] roles exchanged
+        w_simt, w_tc = pack_conv_weight(weight, tc=tc, flip_transpose=True, tc_only=True)   # flipped taps, [Cin, Cout] roles exchanged
         if stride == 1:
             src = gps
         else:
@@ -731,7 +737,7 @@ class _DenseBlockFn(torch.autograd.Function):
             weight, bias = params[2 * i], params[2 * i + 1]
             prec = _ext.CONV_FP32 if (lo % 4) else precision      # the tensor-core kernels read 16-byte aligned slices
             tc = prec == _ext.CONV_TF32
-            w_simt, w_tc = pack_conv_weight(weight, tc=tc)
+            w_simt, w_tc = pack_conv_weight(weight, tc=tc, tc_only=True)
             bvec = bias.detach().float().contiguous()
             los.append(lo)
             precs.append(prec)
@@ -786,7 +792,7 @@ class _DenseBlockFn(torch.autograd.Function):
             wcat = torch.cat([weights[m][:, s - los[m]:s - los[m] + c] for m in range(first, n + 1)], dim=0)
             prec = _ext.CONV_FP32 if (offs[first] % 4) else precision
             tc = prec == _ext.CONV_TF32
-            w_simt, w_tc = pack_conv_weight(wcat, tc=tc, flip_transpose=True)
+            w_simt, w_tc = pack_conv_weight(wcat, tc=tc, flip_transpose=True, tc_only=True)
             gblk = _new(B, H, W, c, buf)
             k_conv(Slice(GP, offs[first], gp_w - offs[first]), w_tc if tc else w_simt, _zero_bias(c, buf.device), Slice(gblk), 3, 1,
                    1, 1.0, Slice(g5, s, c) if g5 is not None else None, prec)
