@@ -56,10 +56,12 @@ def test_conv_backward_fp32_vs_autograd(upf, case, relu):
         _check(name, _rel(got.cpu(), ref), 2e-5)
 
 
-@pytest.mark.parametrize("case", [(64, 32, 3, 1, 1, 24, 40), (96, 128, 3, 1, 2, 20, 33), (32, 32, 1, 1, 1, 17, 29), (16, 32, 3, 2, 1, 30, 44)])
+@pytest.mark.parametrize("case", [(64, 32, 3, 1, 1, 24, 40), (96, 128, 3, 1, 2, 20, 33), (32, 32, 1, 1, 1, 17, 29), (16, 32, 3, 2, 1, 30, 44),
+                                  # few channels, many pixels (K = 65k..68k per cluster of 8)
+                                  (8, 16, 3, 1, 1, 128, 256), (16, 8, 1, 1, 1, 160, 200), (3, 16, 3, 1, 2, 96, 320)])
 @pytest.mark.parametrize("relu", [False, True])
 def test_conv_backward_tf32(upf, case, relu):
-    """tensor-core forward and dgrad (TF32 operands, fp32 accumulate), SIMT fp32 wgrad: 1e-2 relative."""
+    """tensor-core forward, dgrad and wgrad (TF32 operands, fp32 accumulate; stride 2: SIMT fp32 wgrad): 1e-2 relative."""
     from upflow_pytorch_b200 import _ext
     Cin, Cout, k, stride, dil, H, W = case
     slope = 0.1 if relu else 1.0

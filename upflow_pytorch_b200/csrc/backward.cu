@@ -582,6 +582,9 @@ extern "C" int upf_repack_conv_weight(const float* weight, float* out, int A, in
 }
 
 // ---- tensor-core weight gradient (stride 1): see nhwc_to_planar_padded_kernel
+// (Tried: cutting K into up to 8 grid-level parts on top of the cluster split for the few-channel convolutions at fine
+// resolution, 72 -> 576 CTAs, partials summed by reduce_splits_kernel -- parity-green, training step 57.19 vs 57.00 ms:
+// those launches are not bound by the GEMM's CTA count; removed.)
 static int wgrad_tc_wp(int W, int ks, int dil) { return (W + (ks - 1) * dil + 3) / 4 * 4; }   // padded row, multiple of 4
 static long long wgrad_tc_kp(int N, int H, int W, int ks, int dil) {
   const int pad = ((ks - 1) * dil) / 2;
