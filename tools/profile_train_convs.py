@@ -1,5 +1,8 @@
 """Which convolution calls of one (eager) training step cost what: CUDA events around every ops.k_conv (forward and
 input-gradient convolutions) and ops.k_conv_wgrad call, summed by (kind, kernel family, shape).
+CAVEAT: the step runs eagerly, so an event pair also spans the host's launch gaps (allocator, tensor-map encoding,
+5 launches per weight gradient: ~0.1-0.25 ms per call at this problem size) -- the ranking of the LARGE entries is
+usable, the absolute times are upper bounds; the graph-replayed step (bench.py) has none of these gaps.
     python tools/profile_train_convs.py > gpurun_out/train_convs.txt"""
 import collections
 import os
