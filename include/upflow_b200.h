@@ -277,6 +277,18 @@ int upf_edge_smooth1_fwd(const float* img, int ldi, int Ci, const float* pred, i
 int upf_edge_smooth1_bwd(const float* img, int ldi, int Ci, const float* pred, int ldp, int Cp, const float* grad_out,
                          float* grad_pred, int ldg, int N, int H, int W, void* stream);
 
+/* upf_census_loss_*: census_loss_torch (utils/loss.py:51-91) with the abs_robust penalty: grey = 0.2989 R + 0.5870 G +
+ * 0.1140 B of both 3-channel images, soft ternary transform over the (2*max_distance+1)^2 patch (zero padding), soft
+ * Hamming distance `dist`, then (|dist|+0.01)^q: mask == NULL mean over the pixels; mask [npix]: masked by mask * (border
+ * of max_distance pixels removed), sum / (2*sum(mask') + 1e-6) -- the reference's factor 2 (utils/loss.py:44-46).
+ * grey: 2*npix floats, dist: npix floats (both kept for backward).  Backward: gradient of the SECOND image only. */
+int upf_census_loss_fwd(const float* img1, int ld1, const float* img2, int ld2, const float* mask, int ldm, float* grey,
+                        float* dist, float* workspace, float* out, int N, int H, int W, int max_distance, float q,
+                        void* stream);
+int upf_census_loss_bwd(const float* grey, const float* dist, const float* mask, int ldm, const float* out,
+                        const float* grad_out, float* grad_img2, int ldg, int N, int H, int W, int max_distance, float q,
+                        void* stream);
+
 /* layout helpers for callers holding NCHW-contiguous tensors (the reference's
  * layout): strided copy between [N,C,H,W] planes and pixel-major rows. */
 int upf_nchw_to_nhwc(const float* in, float* out, int ldo, int N, int C, int H, int W, void* stream);

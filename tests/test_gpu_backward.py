@@ -454,3 +454,31 @@ def test_repack_conv_weight_tc_kernel_matches_two_step_packing(upf, shape, flip)
     _, two_step = upf.pack_conv_weight(w, tc=True, flip_transpose=flip)
     none, one = upf.pack_conv_weight(w, tc=True, flip_transpose=flip, tc_only=True)
     assert none is None and torch.equal(one, two_step)
+
+
+@pytest.mark.parametrize("masked", [False, True])
+@pytest.mark.parametrize("shape", [(2, 20, 31, 3), (1, 64, 96, 3), (1, 9, 12, 1)])
+def test_census_loss_kernels_vs_torch(upf, masked, shape):
+    """upf_census_loss_fwd/bwd (csrc/loss.cu) against the torch expression of census_loss_torch (utils/loss.py:51-91,
+    pinned to the reference by tests/golden/loss_ops.pt) in fp64: value to 1e-5 relative, gradient of the warped image
+    to 1e-4 of its largest entry."""
+    import upflow_pytorch_b200
+    upflow_pytorch_b200.install_dropin()
+    from utils.loss import loss_functions
+    N, H, W, d = shape
+    gen = torch.Generator().manual_seed(6)
+    a = torch.rand(N, 3, H, W, generator=gen).cuda()
+    b = (a.cpu() + 0.1 * torch.randn(N, 3, H, W, generator=gen)).cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    mask = (torch.rand(N, 1, H, W, generator=gen) > 0.3).float().cuda()
+    got = upf.census_loss(a, b, mask if masked else None, 0.4, d)
+    (gb,) = torch.autograd.grad(got * 2.0, (b,))
+    bd = b.detach().double().requires_grad_()
+    loss_functions.use_loss_kernels = False
+    try:
+        want = loss_functions.census_loss_torch(a.double(), bd, mask.double(), 0.4, False, masked, True, max_distance=d)
+    finally:
+        loss_functions.use_loss_kernels = True
+    (wb,) = torch.autograd.grad(want * 2.0, (bd,))
+    _check("value", abs(got.item() - want.item()) / abs(want.item()), 1e-5)
+    _check("grad", _rel(gb, wb), 1e-4)
+    assert upf.census_loss(a, b, mask if masked else None, 0.4, d).item() == got.item()

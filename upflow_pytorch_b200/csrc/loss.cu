@@ -58,10 +58,12 @@ robust_loss_fwd_kernel(const float* __restrict__ x, int ldx, const float* __rest
   block_sum2(sd, sm, part);
 }
 
-// out[0] = the term, out[1] = 1/denominator (what backward scales by).  mode 0: mean over npix*C; mode 1: masked,
-// sum(d*mask)/(sum(mask)+1e-6).
+// out[0] = the term, out[1] = 1/denominator (what backward scales by).  masked 0: mean over `count` elements;
+// masked 1: sum(d*mask)/(mask_scale*sum(mask)+1e-6) (mask_scale 2: the reference's census normalisation,
+// utils/loss.py:44-46).
 __global__ void __launch_bounds__(LOSS_THREADS)
-robust_loss_finish_kernel(const float* __restrict__ part, int blocks, float* __restrict__ out, double count, int masked) {
+robust_loss_finish_kernel(const float* __restrict__ part, int blocks, float* __restrict__ out, double count, int masked,
+                          double mask_scale) {
   __shared__ double s_a[LOSS_THREADS], s_b[LOSS_THREADS];
   double a = 0.0, b = 0.0;
   for (int k = threadIdx.x; k < blocks; k += LOSS_THREADS) { a += part[k]; b += part[blocks + k]; }
@@ -71,7 +73,7 @@ robust_loss_finish_kernel(const float* __restrict__ part, int blocks, float* __r
   if (threadIdx.x == 0) {
     double ta = 0.0, tb = 0.0;
     for (int k = 0; k < LOSS_THREADS; ++k) { ta += s_a[k]; tb += s_b[k]; }
-    const double inv = masked ? 1.0 / (tb + 1e-6) : 1.0 / count;
+    const double inv = masked ? 1.0 / (tb * mask_scale + 1e-6) : 1.0 / count;
     out[0] = (float)(ta * inv);
     out[1] = (float)inv;
   }
@@ -170,6 +172,103 @@ edge_smooth1_bwd_kernel(const float* __restrict__ img, int ldi, int Ci, const fl
   }
 }
 
+// ---- census term (utils/loss.py:51-91): soft ternary census transform of the grey images over a (2d+1)^2 patch
+// (zero padding), soft Hamming distance, robust penalty.  The reference materialises two 49-channel tensors with a
+// one-hot convolution; here a pixel walks its patch in registers over a 2-channel grey buffer (L1-resident).
+__global__ void __launch_bounds__(LOSS_THREADS)
+census_grey_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb, float2* __restrict__ grey,
+                   long long npix) {
+  for (long long p = blockIdx.x * (long long)LOSS_THREADS + threadIdx.x; p < npix; p += (long long)gridDim.x * LOSS_THREADS) {
+    const float* ap = a + (size_t)p * lda;
+    const float* bp = b + (size_t)p * ldb;
+    grey[p] = make_float2(0.2989f * __ldg(ap) + 0.5870f * __ldg(ap + 1) + 0.1140f * __ldg(ap + 2),
+                          0.2989f * __ldg(bp) + 0.5870f * __ldg(bp + 1) + 0.1140f * __ldg(bp + 2));
+  }
+}
+
+// h'(u) * tau'(v2) for the pair (neighbour value g, centre value c): u = tau(g.x-c.x) - tau(g.y-c.y),
+// tau(v) = v / sqrt(0.81 + v^2), h(u) = u^2 / (0.1 + u^2)
+__device__ __forceinline__ float census_pair_grad(float2 g, float2 c) {
+  const float v1 = g.x - c.x, v2 = g.y - c.y;
+  const float r1 = 1.f / sqrtf(0.81f + v1 * v1), r2 = 1.f / sqrtf(0.81f + v2 * v2);
+  const float u = v1 * r1 - v2 * r2;
+  const float den = 0.1f + u * u;
+  return (0.2f * u / (den * den)) * (0.81f * r2 * r2 * r2);
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS)
+census_fwd_kernel(const float2* __restrict__ grey, const float* __restrict__ mask, int ldm, float* __restrict__ dist,
+                  float* __restrict__ part, int N, int H, int W, int d, float q) {
+  const long long npix = (long long)N * H * W;
+  float sd = 0.f, sm = 0.f;
+  for (long long p = blockIdx.x * (long long)LOSS_THREADS + threadIdx.x; p < npix; p += (long long)gridDim.x * LOSS_THREADS) {
+    const int x = (int)(p % W), y = (int)((p / W) % H);
+    const long long img = p - ((long long)y * W + x);
+    const float2 c = grey[p];
+    float ds = 0.f;
+    for (int dy = -d; dy <= d; ++dy)
+      for (int dx = -d; dx <= d; ++dx) {
+        const int yy = y + dy, xx = x + dx;
+        float2 g = make_float2(0.f, 0.f);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) g = grey[img + (long long)yy * W + xx];
+        const float v1 = g.x - c.x, v2 = g.y - c.y;
+        const float u = v1 / sqrtf(0.81f + v1 * v1) - v2 / sqrtf(0.81f + v2 * v2);
+        const float uu = u * u;
+        ds += uu / (0.1f + uu);
+      }
+    dist[p] = ds;
+    float m = 1.f;
+    if (mask) m = (y >= d && y < H - d && x >= d && x < W - d) ? __ldg(mask + (size_t)p * ldm) : 0.f;
+    sd += powf(fabsf(ds) + 0.01f, q) * m;
+    sm += m;
+  }
+  block_sum2(sd, sm, part);
+}
+
+// gradient wrt the SECOND image (the warped one), gather form: pixel p collects its role as the centre of its own patch
+// and as a neighbour in the (2d+1)^2 patches around it
+__global__ void __launch_bounds__(LOSS_THREADS)
+census_bwd_kernel(const float2* __restrict__ grey, const float* __restrict__ mask, int ldm, const float* __restrict__ dist,
+                  const float* __restrict__ out, const float* __restrict__ gout, float* __restrict__ gimg, int ldg, int N, int H,
+                  int W, int d, float q) {
+  const long long npix = (long long)N * H * W;
+  const float s = __ldg(gout) * __ldg(out + 1) * q;
+  for (long long p = blockIdx.x * (long long)LOSS_THREADS + threadIdx.x; p < npix; p += (long long)gridDim.x * LOSS_THREADS) {
+    const int x = (int)(p % W), y = (int)((p / W) % H);
+    const long long img = p - ((long long)y * W + x);
+    const float2 c = grey[p];
+    // d(term)/d(dist) at pixel (yy, xx)
+    auto coef = [&](int yy, int xx) -> float {
+      const long long pc = img + (long long)yy * W + xx;
+      float m = 1.f;
+      if (mask) m = (yy >= d && yy < H - d && xx >= d && xx < W - d) ? __ldg(mask + (size_t)pc * ldm) : 0.f;
+      if (m == 0.f) return 0.f;
+      const float ds = __ldg(dist + pc);
+      return s * m * powf(fabsf(ds) + 0.01f, q - 1.f) * sgn(ds);
+    };
+    const float a_own = coef(y, x);
+    float acc = 0.f;
+    for (int dy = -d; dy <= d; ++dy)
+      for (int dx = -d; dx <= d; ++dx) {
+        if (a_own != 0.f) {                                  // centre of its own patch: neighbour p+o (zero outside)
+          const int yy = y + dy, xx = x + dx;
+          float2 g = make_float2(0.f, 0.f);
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) g = grey[img + (long long)yy * W + xx];
+          acc += a_own * census_pair_grad(g, c);
+        }
+        const int cy = y - dy, cx = x - dx;                  // neighbour in the patch centred at p-o
+        if (cy >= 0 && cy < H && cx >= 0 && cx < W) {
+          const float a_c = coef(cy, cx);
+          if (a_c != 0.f) acc -= a_c * census_pair_grad(c, grey[img + (long long)cy * W + cx]);
+        }
+      }
+    float* gp = gimg + (size_t)p * ldg;
+    gp[0] = 0.2989f * acc;
+    gp[1] = 0.5870f * acc;
+    gp[2] = 0.1140f * acc;
+  }
+}
+
 static int loss_blocks(long long npix) {
   long long b = (npix + LOSS_THREADS - 1) / LOSS_THREADS;
   if (b > LOSS_MAX_BLOCKS) b = LOSS_MAX_BLOCKS;
@@ -192,7 +291,7 @@ extern "C" int upf_robust_loss_fwd(const float* x, int ldx, const float* y, int 
   robust_loss_fwd_kernel<<<blocks, LOSS_THREADS, 0, st>>>(x, ldx, y, ldy, mask, ldm, workspace, npix, C, kind, q);
   int e = check_launch("robust_loss_fwd");
   if (e) return e;
-  robust_loss_finish_kernel<<<1, LOSS_THREADS, 0, st>>>(workspace, blocks, out, (double)npix * C, mask != nullptr);
+  robust_loss_finish_kernel<<<1, LOSS_THREADS, 0, st>>>(workspace, blocks, out, (double)npix * C, mask != nullptr, 1.0);
   return check_launch("robust_loss_finish");
 }
 
@@ -235,4 +334,38 @@ extern "C" int upf_edge_smooth1_bwd(const float* img, int ldi, int Ci, const flo
       img, ldi, Ci, pred, ldp, Cp, grad_out, grad_pred, ldg, N, H, W, (float)(1.0 / ((double)N * Cp * (H - 1) * W)),
       (float)(1.0 / ((double)N * Cp * H * (W - 1))));
   return check_launch("edge_smooth1_bwd");
+}
+
+extern "C" int upf_census_loss_fwd(const float* img1, int ld1, const float* img2, int ld2, const float* mask, int ldm,
+                                   float* grey, float* dist, float* workspace, float* out, int N, int H, int W,
+                                   int max_distance, float q, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(img1 && img2 && grey && dist && workspace && out, "census_loss_fwd: null tensor");
+  UPF_REQUIRE(N > 0 && H > 0 && W > 0 && ld1 >= 3 && ld2 >= 3 && (!mask || ldm >= 1) && max_distance >= 1 && max_distance <= 8,
+              "census_loss_fwd: bad shape (3-channel images, patch radius 1..8)");
+  UPF_REQUIRE((reinterpret_cast<uintptr_t>(grey) & 7) == 0, "census_loss_fwd: grey buffer must be 8-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long npix = (long long)N * H * W;
+  const int blocks = loss_blocks(npix);
+  census_grey_kernel<<<blocks, LOSS_THREADS, 0, st>>>(img1, ld1, img2, ld2, reinterpret_cast<float2*>(grey), npix);
+  int e = check_launch("census_grey");
+  if (e) return e;
+  census_fwd_kernel<<<blocks, LOSS_THREADS, 0, st>>>(reinterpret_cast<const float2*>(grey), mask, ldm, dist, workspace, N, H, W,
+                                                     max_distance, q);
+  e = check_launch("census_fwd");
+  if (e) return e;
+  robust_loss_finish_kernel<<<1, LOSS_THREADS, 0, st>>>(workspace, blocks, out, (double)npix, mask != nullptr, 2.0);
+  return check_launch("census_finish");
+}
+
+extern "C" int upf_census_loss_bwd(const float* grey, const float* dist, const float* mask, int ldm, const float* out,
+                                   const float* grad_out, float* grad_img2, int ldg, int N, int H, int W, int max_distance,
+                                   float q, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(grey && dist && out && grad_out && grad_img2, "census_loss_bwd: null tensor");
+  UPF_REQUIRE(N > 0 && H > 0 && W > 0 && ldg >= 3 && (!mask || ldm >= 1) && max_distance >= 1 && max_distance <= 8,
+              "census_loss_bwd: bad shape");
+  census_bwd_kernel<<<loss_blocks((long long)N * H * W), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(grey), mask, ldm, dist, out, grad_out, grad_img2, ldg, N, H, W, max_distance, q);
+  return check_launch("census_bwd");
 }

@@ -1,11 +1,14 @@
 """Drop-in for the part of the reference's utils/loss.py the model uses (model/upflow.py:447-455):
 `loss_functions.photo_loss_function` and `loss_functions.census_loss_torch`.  Loss-side ops on 3-channel images
-(SURVEY.md section 8f rank 2), elementwise torch."""
+(SURVEY.md section 8f rank 2): the census term runs as fused kernels (csrc/loss.cu) for CUDA tensors; the torch
+expressions are what the kernels are tested against (`loss_functions.use_loss_kernels = False`) and serve the cases the
+kernels do not take (charbonnier penalty, a first image or mask that needs a gradient, CPU tensors in the oracle tests)."""
 import torch
 import torch.nn.functional as F
 
 
 class loss_functions():
+    use_loss_kernels = True
 
     @classmethod
     def photo_loss_function(cls, diff, mask, q, charbonnier_or_abs_robust, if_use_occ, averge=True):
@@ -27,6 +30,10 @@ class loss_functions():
         """utils/loss.py:51-91: soft ternary census transform over a (2d+1)^2 patch of the grey image, soft Hamming
         distance, border mask.  The reference extracts the patch with a one-hot 49-channel conv2d; here the 49 shifted
         copies are slices of the zero-padded grey image (same values)."""
+        if cls.use_loss_kernels and img1.is_cuda and not charbonnier_or_abs_robust and averge and not img1.requires_grad \
+                and mask is not None and not mask.requires_grad and img1.shape[1] == 3 and 1 <= max_distance <= 8:
+            from upflow_pytorch_b200 import ops
+            return ops.census_loss(img1.float(), img1_warp, mask if if_use_occ else None, q, max_distance)   # csrc/loss.cu
         d = max_distance
         n = 2 * d + 1
 

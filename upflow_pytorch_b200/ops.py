@@ -651,6 +651,51 @@ def edge_smooth1(img, pred):
     return _EdgeSmooth1Fn.apply(img, pred)
 
 
+class _CensusLossFn(torch.autograd.Function):
+    """census_loss_torch (utils/loss.py:51-91, abs_robust penalty): grey conversion + one patch-walking reduction
+    kernel forward, one gather kernel backward; gradient for the second (warped) image only."""
+
+    @staticmethod
+    def forward(ctx, img1, img2, mask, q, max_distance):
+        a, b = to_pixel_major(img1), to_pixel_major(img2)
+        ma = mask.reshape(-1).contiguous() if mask is not None else None
+        N, H, W, _ = a.shape
+        grey = torch.empty(N * H * W, 2, dtype=torch.float32, device=a.device)
+        dist = torch.empty(N * H * W, dtype=torch.float32, device=a.device)
+        ws, out = _loss_buffers(a)
+        _ext.check(_lib().upf_census_loss_fwd(_p(a), a.shape[3], _p(b), b.shape[3], _p(ma), 1, _p(grey), _p(dist), _p(ws),
+                                              _p(out), N, H, W, int(max_distance), float(q), _stream()), "census_loss_fwd")
+        ctx.save_for_backward(grey, dist, out, *([ma] if ma is not None else []))
+        ctx.cfg = (N, H, W, float(q), int(max_distance))
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad):
+        grey, dist, out = ctx.saved_tensors[:3]
+        ma = ctx.saved_tensors[3] if len(ctx.saved_tensors) > 3 else None
+        N, H, W, q, d = ctx.cfg
+        if not ctx.needs_input_grad[1]:
+            return None, None, None, None, None
+        g = grad.reshape(1).contiguous()
+        _require_cuda(g)
+        gimg = torch.empty(N, H, W, 3, dtype=torch.float32, device=grey.device)
+        _ext.check(_lib().upf_census_loss_bwd(_p(grey), _p(dist), _p(ma), 1, _p(out), _p(g), _p(gimg), 3, N, H, W, d, q,
+                                              _stream()), "census_loss_bwd")
+        return None, gimg.permute(0, 3, 1, 2), None, None, None
+
+
+def census_loss(img1, img1_warp, mask=None, q=0.4, max_distance=3):
+    """The reference's census term (utils/loss.py:51-91, abs_robust penalty) of two RGB images [N,3,H,W]; with mask
+    [N,1,H,W] (if_use_occ): masked, border of max_distance pixels excluded, normalised by 2*sum(mask)+1e-6; without:
+    the mean over all pixels.  Differentiable in img1_warp."""
+    _require_cuda(img1, img1_warp, mask)
+    if img1.shape != img1_warp.shape or img1.shape[1] != 3 or \
+            (mask is not None and mask.numel() != img1.shape[0] * img1.shape[2] * img1.shape[3]):
+        raise ValueError("census_loss: img1 %s, img1_warp %s, mask %s" % (tuple(img1.shape), tuple(img1_warp.shape),
+                                                                         None if mask is None else tuple(mask.shape)))
+    return _CensusLossFn.apply(img1, img1_warp, mask, q, max_distance)
+
+
 class _ConvFn(torch.autograd.Function):
     """conv() of model/pwc_modules.py:10-31 with autograd: the input gradient is the forward kernel on the flipped,
     transposed weights (on the zero-interleaved gradient for stride 2), the weight / bias gradient is
