@@ -289,6 +289,16 @@ int upf_census_loss_bwd(const float* grey, const float* dist, const float* mask,
                         const float* grad_out, float* grad_img2, int ldg, int N, int H, int W, int max_distance, float q,
                         void* stream);
 
+/* upf_boundary_warp_*: tools.boundary_dilated_warp.warp_im (utils/tools.py:350-499): the photometric loss samples the
+ * UN-CROPPED frame image [N,Hf,Wf,C] at (x + start[n][0] + u, y + start[n][1] + v) for every pixel of the crop [N,h,w];
+ * corner indices are clamped to the frame and the bilinear weights are taken against the clamped corners, like the
+ * reference.  start: [N][2] floats on the device.  Backward: gradient of the flow (the frame is data). */
+int upf_boundary_warp_fwd(const float* image, int ldi, int C, int Hf, int Wf, const float* flow, int ldf,
+                          const float* start, float* out, int ldo, int N, int h, int w, void* stream);
+int upf_boundary_warp_bwd(const float* image, int ldi, int C, int Hf, int Wf, const float* flow, int ldf,
+                          const float* start, const float* grad_out, int ldg, float* grad_flow, int ldgf, int N, int h,
+                          int w, void* stream);
+
 /* layout helpers for callers holding NCHW-contiguous tensors (the reference's
  * layout): strided copy between [N,C,H,W] planes and pixel-major rows. */
 int upf_nchw_to_nhwc(const float* in, float* out, int ldo, int N, int C, int H, int W, void* stream);

@@ -482,3 +482,36 @@ def test_census_loss_kernels_vs_torch(upf, masked, shape):
     _check("value", abs(got.item() - want.item()) / abs(want.item()), 1e-5)
     _check("grad", _rel(gb, wb), 1e-4)
     assert upf.census_loss(a, b, mask if masked else None, 0.4, d).item() == got.item()
+
+
+def test_boundary_warp_kernels_vs_torch(upf):
+    """upf_boundary_warp_fwd/bwd against the torch expression of tools.boundary_dilated_warp.warp_im (utils/tools.py:350-499,
+    pinned to the reference by tests/golden/loss_ops.pt) in fp64, with samples inside, on the border of and far outside
+    the un-cropped frame.  The flow is a multiple of 1/64 plus 1/128: exact in fp32 and never on a pixel boundary, so
+    both sides pick the same corners."""
+    import upflow_pytorch_b200
+    upflow_pytorch_b200.install_dropin()
+    from utils.tools import tools
+    N, Hf, Wf, h, w = 2, 40, 56, 24, 32
+    gen = torch.Generator().manual_seed(12)
+    frame = torch.rand(N, 3, Hf, Wf, generator=gen).cuda()
+    start = torch.tensor([[5.0, 7.0], [16.0, 9.0]]).reshape(N, 2, 1, 1).cuda()
+    flow = ((torch.randn(N, 2, h, w, generator=gen) * 10 * 64).round() / 64 + 1.0 / 128).cuda()
+    flow = flow.contiguous(memory_format=torch.channels_last).requires_grad_()
+    got = upf.boundary_warp(frame, flow, start)
+    r = _rand(13, N, 3, h, w).cuda()
+    (gf,) = torch.autograd.grad((got * r).sum(), (flow,))
+    fd = flow.detach().double().requires_grad_()
+    tools.boundary_dilated_warp.use_kernel = False
+    try:
+        want = tools.boundary_dilated_warp.warp_im(frame, fd, start.double())
+    finally:
+        tools.boundary_dilated_warp.use_kernel = True
+    (wf,) = torch.autograd.grad((want * r.double()).sum(), (fd,))
+    outside = ((fd[:, 0] + start[:, 0].double() + torch.arange(w, device="cuda")) < 0).float().mean().item()
+    assert 0.02 < outside < 0.5, outside                       # the clamped-corner branch is exercised
+    _check("warp", _rel(got, want), 2e-5)
+    _check("grad flow", _rel(gf, wf), 2e-4)
+    # through the drop-in entry point
+    again = tools.boundary_dilated_warp.warp_im(frame, flow, start)
+    assert torch.equal(again, got)

@@ -61,6 +61,8 @@ SIGNATURES = {
     "upf_edge_smooth1_bwd": (_I, [_P, _I, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P]),
     "upf_census_loss_fwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "upf_census_loss_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
+    "upf_boundary_warp_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
+    "upf_boundary_warp_bwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _P]),
     "upf_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "upf_nhwc_to_nchw": (_I, [_P, _I, _P, _I, _I, _I, _I, _P]),
     "upf_copy_channels": (_I, [_P, _I, _P, _I, _LL, _I, _P]),

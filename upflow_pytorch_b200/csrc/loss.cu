@@ -269,6 +269,66 @@ census_bwd_kernel(const float2* __restrict__ grey, const float* __restrict__ mas
   }
 }
 
+// ---- boundary-dilated warp (utils/tools.py:350-499): bilinear lookup of the UN-CROPPED frame I [N,Hf,Wf,C] at
+// (x + start_x + u, y + start_y + v); corner indices clamped to the frame, weights taken against the CLAMPED corners
+// (so a sample outside the frame extrapolates from the border pixels: that is the reference's arithmetic).
+struct BdCorners { float fx, fy, x0c, x1c, y0c, y1c; long long ia, ib, ic, id; };
+__device__ __forceinline__ BdCorners bd_corners(const float* __restrict__ flow, int ldf, const float* __restrict__ start, long long p,
+                                                int h, int w, int Hf, int Wf) {
+  const int x = (int)(p % w), y = (int)((p / w) % h);
+  const long long n = p / ((long long)h * w);
+  BdCorners c;
+  c.fx = ((float)x + __ldg(start + 2 * n)) + __ldg(flow + (size_t)p * ldf);
+  c.fy = ((float)y + __ldg(start + 2 * n + 1)) + __ldg(flow + (size_t)p * ldf + 1);
+  const float x0 = floorf(c.fx), y0 = floorf(c.fy);
+  c.x0c = fminf(fmaxf(x0, 0.f), (float)(Wf - 1));
+  c.x1c = fminf(fmaxf(x0 + 1.f, 0.f), (float)(Wf - 1));
+  c.y0c = fminf(fmaxf(y0, 0.f), (float)(Hf - 1));
+  c.y1c = fminf(fmaxf(y0 + 1.f, 0.f), (float)(Hf - 1));
+  const long long base = n * Hf;
+  c.ia = (base + (long long)c.y0c) * Wf + (long long)c.x0c;
+  c.ib = (base + (long long)c.y1c) * Wf + (long long)c.x0c;
+  c.ic = (base + (long long)c.y0c) * Wf + (long long)c.x1c;
+  c.id = (base + (long long)c.y1c) * Wf + (long long)c.x1c;
+  return c;
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS)
+bdwarp_fwd_kernel(const float* __restrict__ I, int ldi, int C, int Hf, int Wf, const float* __restrict__ flow, int ldf,
+                  const float* __restrict__ start, float* __restrict__ out, int ldo, int N, int h, int w) {
+  const long long npix = (long long)N * h * w;
+  for (long long p = blockIdx.x * (long long)LOSS_THREADS + threadIdx.x; p < npix; p += (long long)gridDim.x * LOSS_THREADS) {
+    const BdCorners c = bd_corners(flow, ldf, start, p, h, w, Hf, Wf);
+    const float wa = (c.x1c - c.fx) * (c.y1c - c.fy), wb = (c.x1c - c.fx) * (c.fy - c.y0c);
+    const float wc = (c.fx - c.x0c) * (c.y1c - c.fy), wd = (c.fx - c.x0c) * (c.fy - c.y0c);
+    for (int k = 0; k < C; ++k)
+      out[(size_t)p * ldo + k] = wa * __ldg(I + (size_t)c.ia * ldi + k) + wb * __ldg(I + (size_t)c.ib * ldi + k) +
+                                 wc * __ldg(I + (size_t)c.ic * ldi + k) + wd * __ldg(I + (size_t)c.id * ldi + k);
+  }
+}
+
+// gradient wrt the flow (floor and clamp are piecewise constant): d/du = sum_k g_k [(y1c-y)(Ic-Ia) + (y-y0c)(Id-Ib)],
+// d/dv = sum_k g_k [(x1c-x)(Ib-Ia) + (x-x0c)(Id-Ic)]
+__global__ void __launch_bounds__(LOSS_THREADS)
+bdwarp_bwd_kernel(const float* __restrict__ I, int ldi, int C, int Hf, int Wf, const float* __restrict__ flow, int ldf,
+                  const float* __restrict__ start, const float* __restrict__ g, int ldg, float* __restrict__ gflow, int ldgf,
+                  int N, int h, int w) {
+  const long long npix = (long long)N * h * w;
+  for (long long p = blockIdx.x * (long long)LOSS_THREADS + threadIdx.x; p < npix; p += (long long)gridDim.x * LOSS_THREADS) {
+    const BdCorners c = bd_corners(flow, ldf, start, p, h, w, Hf, Wf);
+    float gu = 0.f, gv = 0.f;
+    for (int k = 0; k < C; ++k) {
+      const float a = __ldg(I + (size_t)c.ia * ldi + k), b = __ldg(I + (size_t)c.ib * ldi + k);
+      const float cc = __ldg(I + (size_t)c.ic * ldi + k), d = __ldg(I + (size_t)c.id * ldi + k);
+      const float gk = __ldg(g + (size_t)p * ldg + k);
+      gu += gk * ((c.y1c - c.fy) * (cc - a) + (c.fy - c.y0c) * (d - b));
+      gv += gk * ((c.x1c - c.fx) * (b - a) + (c.fx - c.x0c) * (d - cc));
+    }
+    gflow[(size_t)p * ldgf] = gu;
+    gflow[(size_t)p * ldgf + 1] = gv;
+  }
+}
+
 static int loss_blocks(long long npix) {
   long long b = (npix + LOSS_THREADS - 1) / LOSS_THREADS;
   if (b > LOSS_MAX_BLOCKS) b = LOSS_MAX_BLOCKS;
@@ -368,4 +428,26 @@ extern "C" int upf_census_loss_bwd(const float* grey, const float* dist, const f
   census_bwd_kernel<<<loss_blocks((long long)N * H * W), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float2*>(grey), mask, ldm, dist, out, grad_out, grad_img2, ldg, N, H, W, max_distance, q);
   return check_launch("census_bwd");
+}
+
+extern "C" int upf_boundary_warp_fwd(const float* image, int ldi, int C, int Hf, int Wf, const float* flow, int ldf,
+                                     const float* start, float* out, int ldo, int N, int h, int w, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(image && flow && start && out, "boundary_warp_fwd: null tensor");
+  UPF_REQUIRE(N > 0 && h > 0 && w > 0 && Hf > 0 && Wf > 0 && C > 0 && ldi >= C && ldo >= C && ldf >= 2, "boundary_warp_fwd: bad shape");
+  bdwarp_fwd_kernel<<<loss_blocks((long long)N * h * w), LOSS_THREADS, 0, (cudaStream_t)stream>>>(image, ldi, C, Hf, Wf, flow, ldf,
+                                                                                             start, out, ldo, N, h, w);
+  return check_launch("boundary_warp_fwd");
+}
+
+extern "C" int upf_boundary_warp_bwd(const float* image, int ldi, int C, int Hf, int Wf, const float* flow, int ldf,
+                                     const float* start, const float* grad_out, int ldg, float* grad_flow, int ldgf, int N,
+                                     int h, int w, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(image && flow && start && grad_out && grad_flow, "boundary_warp_bwd: null tensor");
+  UPF_REQUIRE(N > 0 && h > 0 && w > 0 && Hf > 0 && Wf > 0 && C > 0 && ldi >= C && ldg >= C && ldf >= 2 && ldgf >= 2,
+              "boundary_warp_bwd: bad shape");
+  bdwarp_bwd_kernel<<<loss_blocks((long long)N * h * w), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
+      image, ldi, C, Hf, Wf, flow, ldf, start, grad_out, ldg, grad_flow, ldgf, N, h, w);
+  return check_launch("boundary_warp_bwd");
 }

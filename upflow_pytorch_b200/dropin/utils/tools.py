@@ -162,7 +162,10 @@ class tools():
     class boundary_dilated_warp():
         """Photometric-loss warp that samples the UN-CROPPED frame (utils/tools.py:350-499): the training crop starts
         at `start` inside the full image, so flows pointing outside the crop still find real pixels.  Loss-side op on
-        3-channel images: index arithmetic and gathers in torch."""
+        3-channel images (SURVEY.md section 8f rank 2): one gather kernel each way for CUDA tensors (ops.boundary_warp);
+        the index arithmetic and gathers in torch below are its A/B partner (`use_kernel = False`) and the CPU path of
+        the oracle tests."""
+        use_kernel = True
 
         @classmethod
         def get_grid(cls, batch_size, H, W, start):
@@ -196,6 +199,9 @@ class tools():
 
         @classmethod
         def warp_im(cls, I_nchw, flow_nchw, start_n211):
+            if cls.use_kernel and flow_nchw.is_cuda and not I_nchw.requires_grad and flow_nchw.shape[1] == 2:
+                return ops.boundary_warp(I_nchw.float().to(flow_nchw.device), flow_nchw,
+                                         start_n211.to(flow_nchw.device).float())               # csrc/loss.cu
             batch_size = I_nchw.shape[0]
             _, _, ph, pw = flow_nchw.shape
             grid = cls.get_grid(batch_size, ph, pw, start_n211.to(flow_nchw.device).float())

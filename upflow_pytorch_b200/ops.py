@@ -696,6 +696,47 @@ def census_loss(img1, img1_warp, mask=None, q=0.4, max_distance=3):
     return _CensusLossFn.apply(img1, img1_warp, mask, q, max_distance)
 
 
+class _BoundaryWarpFn(torch.autograd.Function):
+    """tools.boundary_dilated_warp.warp_im (utils/tools.py:350-499): one gather kernel forward, one backward (gradient
+    of the flow only)."""
+
+    @staticmethod
+    def forward(ctx, image, flow, start):
+        im, fl = to_pixel_major(image), to_pixel_major(flow)
+        st = start.reshape(-1, 2).float().contiguous()
+        N, Hf, Wf, C = im.shape
+        _, h, w, _ = fl.shape
+        out = torch.empty(N, h, w, C, dtype=torch.float32, device=im.device)
+        _ext.check(_lib().upf_boundary_warp_fwd(_p(im), C, C, Hf, Wf, _p(fl), 2, _p(st), _p(out), C, N, h, w, _stream()),
+                   "boundary_warp_fwd")
+        ctx.save_for_backward(im, fl, st)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad):
+        im, fl, st = ctx.saved_tensors
+        if not ctx.needs_input_grad[1]:
+            return None, None, None
+        N, Hf, Wf, C = im.shape
+        _, h, w, _ = fl.shape
+        g = to_pixel_major(grad)
+        gf = torch.empty(N, h, w, 2, dtype=torch.float32, device=im.device)
+        _ext.check(_lib().upf_boundary_warp_bwd(_p(im), C, C, Hf, Wf, _p(fl), 2, _p(st), _p(g), C, _p(gf), 2, N, h, w,
+                                                _stream()), "boundary_warp_bwd")
+        return None, gf.permute(0, 3, 1, 2), None
+
+
+def boundary_warp(image, flow, start):
+    """The reference's boundary-dilated warp (utils/tools.py:350-499): image [N,C,Hf,Wf] (the un-cropped frame), flow
+    [N,2,h,w] (of the crop), start [N,2,1,1] (the crop's origin inside the frame, x then y).  Differentiable in flow."""
+    _require_cuda(image, flow)
+    if not start.is_cuda:
+        raise RuntimeError("boundary_warp: start must be a CUDA tensor")
+    if image.shape[0] != flow.shape[0] or flow.shape[1] != 2 or start.numel() != 2 * flow.shape[0]:
+        raise ValueError("boundary_warp: image %s, flow %s, start %s" % (tuple(image.shape), tuple(flow.shape), tuple(start.shape)))
+    return _BoundaryWarpFn.apply(image, flow, start)
+
+
 class _ConvFn(torch.autograd.Function):
     """conv() of model/pwc_modules.py:10-31 with autograd: the input gradient is the forward kernel on the flipped,
     transposed weights (on the zero-interleaved gradient for stride 2), the weight / bias gradient is
