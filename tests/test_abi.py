@@ -61,6 +61,24 @@ def test_bad_arguments_return_codes_not_crashes(lib_path):
     rc = lib.upf_conv2d_fwd(ctypes.c_void_p(16), 32, ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), 32,
                             None, 0, 1, 8, 8, 32, 32, 5, 1, 1, 0.1, 0, None)
     assert rc == -1 and b"kernel size" in lib.upf_last_error()
+    # the training-side entry points validate the same way
+    P = ctypes.c_void_p(64)
+    rc = lib.upf_robust_loss_fwd(P, 2, P, 2, None, 0, P, P, 100, 2, 7, 0.4, None)
+    assert rc == -1 and b"kind" in lib.upf_last_error()
+    rc = lib.upf_robust_loss_bwd(P, 2, P, 2, None, 0, P, P, None, 2, None, 2, 100, 2, 0, 0.4, None)
+    assert rc == -1 and b"null" in lib.upf_last_error()          # neither gradient requested
+    rc = lib.upf_edge_smooth1_fwd(P, 3, 3, P, 2, 2, P, P, 1, 1, 8, None)
+    assert rc == -1 and b"H, W >= 2" in lib.upf_last_error()
+    rc = lib.upf_census_loss_fwd(P, 3, P, 3, None, 0, P, P, P, P, 1, 8, 8, 9, 0.4, None)
+    assert rc == -1 and b"radius" in lib.upf_last_error()
+    rc = lib.upf_boundary_warp_fwd(P, 3, 3, 8, 8, P, 1, P, P, 3, 1, 4, 4, None)
+    assert rc == -1 and b"bad shape" in lib.upf_last_error()     # a flow needs two channels
+    rc = lib.upf_repack_conv_weight_tc(P, P, 8, 8, 5, 0, None)
+    assert rc == -1 and b"repack" in lib.upf_last_error()
+    rc = lib.upf_conv2d_wgrad_tc_planar(None, P, 8, P, P, P, 1, 8, 8, 8, 8, 3, 1, None)
+    assert rc == -1 and b"null" in lib.upf_last_error()
+    assert lib.upf_loss_workspace_elems() >= 2 * 148
+    assert lib.upf_wgrad_tc_planar_pitch(2, 8, 8, 3, 1) % 32 == 0
 
 
 def test_sass_has_blackwell_tensor_and_tma_instructions(lib_path):
