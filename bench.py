@@ -159,11 +159,30 @@ def run_train(args, rank, world, local, dist):
     from upflow_pytorch_b200.train import Trainer
     H, W, B = WORKLOADS[args.workload]
     sd = make_weights()
-    net = pkg.build_model(params={"if_use_boundary_warp": False, "multi_scale_distillation_weight": 0.01},
-                          state_dict=sd, conv_precision=args.precision).train()
+    default_losses = args.train_losses == "all"
+    params = {"if_use_boundary_warp": default_losses, "multi_scale_distillation_weight": 0.01}
+    if default_losses:
+        params["photo_loss_census_weight"] = 1.0
+    net = pkg.build_model(params=params, state_dict=sd, conv_precision=args.precision).train()
+    if args.torch_losses:
+        from model.upflow import network_tools
+        from utils.loss import loss_functions
+        from utils.tools import tools
+        network_tools.use_loss_kernels = loss_functions.use_loss_kernels = tools.boundary_dilated_warp.use_kernel = False
     tr = Trainer(net, use_cuda_graph=not args.no_train_graph)
-    im1_h, im2_h = synth_inputs(B, H, W, 1234 + rank)
+    host = {}
+    if default_losses:
+        # the crop of a full KITTI frame, like dataset/kitti_dataset.py's random crop: the frames travel too
+        RH, RW, y0, x0 = 375, 1242, 60, 200
+        raw1, raw2 = synth_inputs(B, RH, RW, 1234 + rank)
+        im1_h, im2_h = raw1[:, :, y0:y0 + H, x0:x0 + W].contiguous(), raw2[:, :, y0:y0 + H, x0:x0 + W].contiguous()
+        host = {"im1_raw": raw1.pin_memory(), "im2_raw": raw2.pin_memory(),
+                "start": torch.tensor([[x0, y0]] * B, dtype=torch.float32).reshape(B, 2, 1, 1).pin_memory()}
+    else:
+        im1_h, im2_h = synth_inputs(B, H, W, 1234 + rank)
     im1_h, im2_h = im1_h.pin_memory(), im2_h.pin_memory()
+    host.update({"im1": im1_h, "im2": im2_h})
+    h2d_bytes = sum(t.numel() * 4 for t in host.values())
 
     def sync_all():
         torch.cuda.synchronize()
@@ -172,7 +191,7 @@ def run_train(args, rank, world, local, dist):
             torch.cuda.synchronize()
 
     def step():
-        loss = tr.train_step({"im1": im1_h.cuda(non_blocking=True), "im2": im2_h.cuda(non_blocking=True)})
+        loss = tr.train_step({k: t.cuda(non_blocking=True) for k, t in host.items()})
         return loss.item()                                   # D2H of the step's result
 
     W_, K = max(3, args.warmup), args.steps
@@ -210,11 +229,14 @@ def run_train(args, rank, world, local, dist):
             "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": args.workload, "pairs_per_step_per_gpu": B, "image": [H, W],
-                       "step": "forward + loss (photo abs_robust, edge smooth, msd 0.01) + backward + gradient all-reduce + Adam(amsgrad)",
+                       "step": "forward + loss (%s) + backward + gradient all-reduce + Adam(amsgrad)" % (
+                           "boundary-dilated-warp photo abs_robust on the 375x1242 frames, census 1.0, edge smooth, msd 0.01"
+                           if default_losses else "photo abs_robust, edge smooth, msd 0.01"),
+                       "losses": "torch expressions (A/B)" if args.torch_losses else "loss kernels (csrc/loss.cu)",
                        "launch": "eager" if args.no_train_graph else "zero-grad + forward + losses + backward replayed as one CUDA graph; all-reduce and Adam eager",
                        "weights": "random-init (MSRA, seed 1234)", "l2": "per-step working set (> 1 GB of activations) exceeds the 126 MB L2",
                        "parallelism": "data parallel x%d, one all-reduce of %d fp32 gradients per step" % (world, tr.grads.numel)},
-            "e2e": {"value": v, "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": 2 * im1_h.numel() * 4,
+            "e2e": {"value": v, "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "api": "upflow_pytorch_b200.train.Trainer.train_step(batch) with pinned host tensors"},
             "allreduce": {"bytes": nbytes, "ms": ar_ms, "share_of_step": ar_ms / ms},
             "gpu_launches": launches, "launches_per_step": launches // K, "clocks": clocks, "final_loss": loss}))
@@ -311,6 +333,12 @@ def _main():
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "tf32x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-graph", action="store_true", help="training workload: eager launches instead of a CUDA graph")
+    ap.add_argument("--train-losses", default="plain", choices=["plain", "all"],
+                    help="training workload: 'plain' = photo + smooth + msd (the line BASELINE config 4 is measured on); "
+                         "'all' = every loss term of model/upflow.py:394-491: the boundary-dilated warp on the un-cropped 375x1242 frames "
+                         "(the model's default if_use_boundary_warp=True) + census weight 1")
+    ap.add_argument("--torch-losses", action="store_true",
+                    help="training workload: the loss branch as torch expressions instead of the loss kernels (A/B)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
