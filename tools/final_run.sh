@@ -7,6 +7,8 @@ python bench.py --steps 20 --warmup 3 --workload sintel_436x1024_b8 --no-cpu-bas
 python bench.py --steps 10 --warmup 3 --workload hd_1080x1920_b2 --no-cpu-baseline > gpurun_out/final/bench_hd_b2.json 2> gpurun_out/final/bench_hd_b2.err
 python bench.py --steps 20 --warmup 3 --precision tf32x3 --no-cpu-baseline > gpurun_out/final/bench_kitti_b1_tf32x3.json 2> gpurun_out/final/bench_kitti_b1_tf32x3.err
 python bench.py --steps 8 --warmup 3 --workload train_256x832_b4 > gpurun_out/final/bench_train_b4.json 2> gpurun_out/final/bench_train_b4.err
+python bench.py --steps 8 --warmup 3 --workload train_256x832_b4 --train-losses all > gpurun_out/final/bench_train_b4_all_losses.json 2> gpurun_out/final/bench_train_b4_all_losses.err
+python bench.py --steps 8 --warmup 3 --workload train_256x832_b4 --train-losses all --torch-losses > gpurun_out/final/bench_train_b4_all_losses_torch.json 2> gpurun_out/final/bench_train_b4_all_losses_torch.err
 python tools/profile_train.py > gpurun_out/final/train_breakdown.txt 2> gpurun_out/final/train_breakdown.err
 python tools/profile_step.py > gpurun_out/final/launch_table_kitti_events.txt 2>&1
 python tools/time_corr.py > gpurun_out/final/time_corr.txt 2>&1
