@@ -203,3 +203,20 @@ def test_bench_reference_arm_prints_one_json_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["value"] > 0 and d["config"]["workload"] == "small_256x256_b1"
+
+
+def test_bench_reference_arm_under_torchrun_prints_once():
+    """The driver launches the reference arm like the product arm, torchrun included: with two ranks, rank 0 alone
+    runs and prints the line, the other rank exits 0 without work."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--workload", "small_256x256_b1", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-800:]
+    lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1, r.stdout[-800:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["value"] > 0
