@@ -114,9 +114,36 @@ def make_weights(seed=1234):
     return sd
 
 
+CHECKPOINT = os.path.join(ROOT, "tests", "golden", "upflow_kitti2015.pth")
+GOLDEN_E2E = os.path.join(ROOT, "tests", "golden", "kitti_e2e.pt")
+
+
+def load_weights():
+    """BASELINE config 2 names the reference's shipped checkpoint (scripts/upflow_kitti2015.pth, loaded by
+    test.py:31-38): its state dict travels to the GPU box as a committed fixture.  Falls back to random-init weights of
+    the same architecture only if the fixture is missing.  Returns (state dict, description, checkpoint path or None)."""
+    if os.path.exists(CHECKPOINT):
+        return (torch.load(CHECKPOINT, weights_only=True), "upflow_kitti2015.pth (the reference's shipped checkpoint; "
+                "tests/golden copy, loaded with net.load_model like test.py:31-38)", CHECKPOINT)
+    return make_weights(), "random-init (MSRA, seed 1234): checkpoint fixture missing", None
+
+
 def synth_inputs(B, H, W, seed):
+    """Synthetic image pairs of the named resolution: a smooth random texture (bicubically upsampled
+    uniform noise, range ~[-0.5, 0.5] like the KITTI preprocessing) and the same texture moved by (u, v) = (-3, +2)
+    px.  seed 1234, B = 1 reproduces the pair of tests/golden/kitti_e2e.pt bit for bit."""
     g = torch.Generator().manual_seed(seed)
-    return torch.rand(B, 3, H, W, generator=g) - 0.5, torch.rand(B, 3, H, W, generator=g) - 0.5
+    lo = torch.rand(B, 3, H // 8 + 4, W // 8 + 4, generator=g)
+    base = torch.nn.functional.interpolate(lo, size=(H + 16, W + 16), mode="bicubic", align_corners=False) - 0.5
+    return base[:, :, 8:8 + H, 8:8 + W].contiguous(), base[:, :, 6:6 + H, 11:11 + W].contiguous()
+
+
+def workload_config(workload, weights_desc):
+    """The `config` object: what is measured, identical for the product arm and the reference arm."""
+    H, W, B = WORKLOADS[workload]
+    return {"workload": workload, "image": [H, W], "pairs_per_step_per_gpu": B, "pyramid_levels": 6, "decoder_levels": 5,
+            "sgu": True, "directions": "forward + backward flow", "weights": weights_desc,
+            "inputs": "synthetic textured pair with known motion (-3,+2) px, seed 1234 + rank"}
 
 
 def run_reference(args, rank, world):
@@ -125,7 +152,7 @@ def run_reference(args, rank, world):
         return
     from oracle import ref_port as P
     H, W, B = WORKLOADS[args.workload]
-    sd = make_weights()
+    sd, wdesc, _ = load_weights()
     im1, im2 = synth_inputs(B, H, W, 1234)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -140,9 +167,12 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(1, args.warmup), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "pairs_per_step": B, "weights": "random-init (MSRA), seed 1234",
-                       "path": "oracle/ref_port.py: op-for-op CPU port of model/upflow.py forward_2_frame_v3 "
-                               "(F.conv2d / F.grid_sample / unfold correlation), bit-identical to the reference on CPU"},
+            "config": workload_config(args.workload, wdesc),
+            "path": "oracle/ref_port.py: op-for-op CPU port of model/upflow.py forward_2_frame_v3 (F.conv2d / "
+                    "F.grid_sample / unfold correlation), bit-identical to the reference on CPU",
+            "host_processes": 1,
+            "note": "ONE CPU process on all host cores whatever --gpus says (rank 0 runs, the other ranks exit): "
+                    "compare with the product arm at N=1 only",
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d forwards of one %dx%d batch-%d pair after %d warm-up" % (args.steps, H, W, B, max(1, args.warmup))},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -150,20 +180,29 @@ def run_reference(args, rank, world):
     emit(json.dumps(line))
 
 
-def run_train(args, rank, world, local, dist):
-    """--workload train_256x832_b4 (BASELINE config 4): one step = H2D of the local shard (pinned host), forward with
-    the loss branch (photometric + edge-aware smoothness + multi-scale distillation), backward on this library's
-    kernels, ONE all-reduce of the flat fp32 gradient buffer over NCCL, Adam(amsgrad) update, D2H of the loss."""
+def build_net(params=None, precision="tf32", train=False):
+    """the public drop-in model with the benchmark's weights, loaded the way test.py:31-38 does"""
     import upflow_pytorch_b200 as pkg
+    sd, wdesc, ckpt = load_weights()
+    net = pkg.build_model(params=params, state_dict=None if ckpt else sd, conv_precision=precision)
+    if ckpt:
+        net.load_model(ckpt, if_relax=True, if_print=False)
+    return (net.train() if train else net.eval()), sd, wdesc
+
+
+def measure_train(args, rank, world, local, dist, steps, warmup):
+    """BASELINE config 4 (unsupervised training step on synthetic 832x256 pairs, 4 pairs per GPU = batch 32 over 8
+    GPUs): one step = H2D of the local shard (pinned host), forward with the loss branch (photometric + edge-aware
+    smoothness + multi-scale distillation), backward on this library's kernels, ONE all-reduce of the flat fp32
+    gradient buffer over NCCL, Adam(amsgrad) update, D2H of the loss.  Returns the record (max over ranks)."""
     from upflow_pytorch_b200 import _ext
     from upflow_pytorch_b200.train import Trainer
-    H, W, B = WORKLOADS[args.workload]
-    sd = make_weights()
+    H, W, B = WORKLOADS["train_256x832_b4"]
     default_losses = args.train_losses == "all"
     params = {"if_use_boundary_warp": default_losses, "multi_scale_distillation_weight": 0.01}
     if default_losses:
         params["photo_loss_census_weight"] = 1.0
-    net = pkg.build_model(params=params, state_dict=sd, conv_precision=args.precision).train()
+    net, sd, wdesc = build_net(params, args.precision, train=True)
     if args.torch_losses:
         from model.upflow import network_tools
         from utils.loss import loss_functions
@@ -194,8 +233,7 @@ def run_train(args, rank, world, local, dist):
         loss = tr.train_step({k: t.cuda(non_blocking=True) for k, t in host.items()})
         return loss.item()                                   # D2H of the step's result
 
-    W_, K = max(3, args.warmup), args.steps
-    for _ in range(W_):
+    for _ in range(warmup):
         step()
     sampler = ClockSampler(local)
     sync_all()
@@ -203,14 +241,15 @@ def run_train(args, rank, world, local, dist):
     n0 = _ext.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(K):
+    for _ in range(steps):
         loss = step()
     e1.record()
     sync_all()
     clocks = sampler.stop()
-    launches = _ext.launch_count() - n0 + (tr.graph_launches * K if tr.use_cuda_graph else 0)   # replayed kernels are not host launches
-    ms = e0.elapsed_time(e1) / K
-    # the collective alone
+    launches = _ext.launch_count() - n0 + (tr.graph_launches * steps if tr.use_cuda_graph else 0)   # replayed kernels are not host launches
+    ms = e0.elapsed_time(e1) / steps
+    # the collective alone, and how much of it the step hides (Trainer issues it on a side stream under the Adam
+    # update of ... nothing: it is 0.1 % of the step; reported as measured)
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     a0.record()
@@ -223,26 +262,108 @@ def run_train(args, rank, world, local, dist):
         t = torch.tensor([ms, ar_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ar_ms = float(t[0].item()), float(t[1].item())
+    v = world * B / (ms * 1e-3)
+    rec = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+           "global_batch": world * B, "dtype": args.precision,
+           "config": dict(workload_config("train_256x832_b4", wdesc),
+                          step="forward + loss (%s) + backward + gradient all-reduce + Adam(amsgrad)" % (
+                              "boundary-dilated-warp photo abs_robust on the 375x1242 frames, census 1.0, edge smooth, msd 0.01"
+                              if default_losses else "photo abs_robust, edge smooth, msd 0.01"),
+                          losses="torch expressions (A/B)" if args.torch_losses else "loss kernels (csrc/loss.cu)",
+                          launch="eager" if args.no_train_graph else "zero-grad + forward + losses + backward replayed as one CUDA graph; all-reduce and Adam eager",
+                          l2="per-step working set (> 1 GB of activations) exceeds the 126 MB L2",
+                          parallelism="data parallel x%d, one all-reduce of %d fp32 gradients per step" % (world, tr.grads.numel)),
+           "e2e": {"value": v, "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": h2d_bytes,
+                   "d2h_bytes_per_step": 4, "api": "upflow_pytorch_b200.train.Trainer.train_step(batch) with pinned host tensors"},
+           "allreduce": {"bytes": nbytes, "ms": ar_ms, "share_of_step": ar_ms / ms,
+                         "comm": "NCCL all-reduce (sum) of one flat fp32 buffer" if world > 1 else "none (1 GPU)"},
+           "gpu_launches": launches, "launches_per_step": launches // steps, "clocks": clocks, "final_loss": loss}
+    del tr, net
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_train(args, rank, world, local, dist):
+    """--workload train_256x832_b4: the training record as the bench line."""
+    rec = measure_train(args, rank, world, local, dist, args.steps, max(3, args.warmup))
     if rank == 0:
-        v = world * B / (ms * 1e-3)
-        emit(json.dumps({
-            "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": args.workload, "pairs_per_step_per_gpu": B, "image": [H, W],
-                       "step": "forward + loss (%s) + backward + gradient all-reduce + Adam(amsgrad)" % (
-                           "boundary-dilated-warp photo abs_robust on the 375x1242 frames, census 1.0, edge smooth, msd 0.01"
-                           if default_losses else "photo abs_robust, edge smooth, msd 0.01"),
-                       "losses": "torch expressions (A/B)" if args.torch_losses else "loss kernels (csrc/loss.cu)",
-                       "launch": "eager" if args.no_train_graph else "zero-grad + forward + losses + backward replayed as one CUDA graph; all-reduce and Adam eager",
-                       "weights": "random-init (MSRA, seed 1234)", "l2": "per-step working set (> 1 GB of activations) exceeds the 126 MB L2",
-                       "parallelism": "data parallel x%d, one all-reduce of %d fp32 gradients per step" % (world, tr.grads.numel)},
-            "e2e": {"value": v, "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": 4, "api": "upflow_pytorch_b200.train.Trainer.train_step(batch) with pinned host tensors"},
-            "allreduce": {"bytes": nbytes, "ms": ar_ms, "share_of_step": ar_ms / ms},
-            "gpu_launches": launches, "launches_per_step": launches // K, "clocks": clocks, "final_loss": loss}))
+        ref = None
+        if world == 1 and not args.no_cpu_baseline:
+            ref = reference_gpu_train_step(args)
+        line = dict(rec, higher_is_better=True, scaling="weak", vs_baseline=None, data="synthetic")
+        if ref is not None:
+            line["reference_gpu_path"] = ref
+        emit(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def reference_gpu_train_step(args, steps=5):
+    """The anchor of the training step: the op-for-op port of the reference (oracle/ref_port.py + ref_port_train.py:
+    F.conv2d through cuDNN with TF32 allowed, F.grid_sample, unfold correlation, the loss branch as torch expressions)
+    with torch autograd and torch.optim.Adam(amsgrad), eager, on the same GPU, same shard, host tensors in, loss out.
+    Reported next to the result, never part of it."""
+    try:
+        from oracle import ref_port_train as PT
+        H, W, B = WORKLOADS["train_256x832_b4"]
+        sd, _, _ = load_weights()
+        params = {k: v.clone().cuda().requires_grad_() for k, v in sd.items()}
+        opt = torch.optim.Adam(list(params.values()), lr=1e-4, amsgrad=True, weight_decay=1e-4)
+        im1_h, im2_h = (t.pin_memory() for t in synth_inputs(B, H, W, 1234))
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            loss = PT.training_loss(im1_h.cuda(non_blocking=True), im2_h.cuda(non_blocking=True), params,
+                                    msd_weight=0.01)["loss"]
+            loss.backward()
+            opt.step()
+            return loss.item()
+        for _ in range(2):
+            step()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        r0.record()
+        for _ in range(steps):
+            loss = step()
+        r1.record()
+        torch.cuda.synchronize()
+        ms = r0.elapsed_time(r1) / steps
+        out = {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "kind": "port", "final_loss": loss,
+               "path": "oracle/ref_port.py + ref_port_train.py on cuda:0: eager PyTorch %s autograd, cuDNN (allow_tf32=%s), "
+                       "torch.optim.Adam(amsgrad)" % (torch.__version__, torch.backends.cudnn.allow_tf32)}
+        del params, opt
+        torch.cuda.empty_cache()
+        return out
+    except Exception as exc:   # pragma: no cover - the comparison leg must never break the bench line
+        return {"error": repr(exc)[:300]}
+
+
+def epe_vs_reference(args, net, H, W, B):
+    """Mean end-point error of the benchmarked precision against the REFERENCE's own CPU flow on the same pair, shipped
+    weights (tests/golden/kitti_e2e.pt, made by oracle/make_golden_kitti.py from the unmodified reference): under the
+    reference's `mask >= 1.0` (bounded below by its own noise floor, stored with the fixture) and under the robust-mask
+    diagnostic (threshold 0.9999 on both sides), which is the number the 1e-3 px target is read on."""
+    if not (os.path.exists(GOLDEN_E2E) and os.path.exists(CHECKPOINT)):
+        return None
+    case = [c for c in torch.load(GOLDEN_E2E, weights_only=False) if (c["H"], c["W"]) == (H, W)]
+    if not case:
+        return None
+    c = case[0]
+    im1, im2 = synth_inputs(1, H, W, c["seed"])
+    eng = net._get_engine()
+    out = {"weights": "upflow_kitti2015.pth", "precision": args.precision, "reference": "UPFlow_net.forward_2_frame_v3 of the "
+           "unmodified reference on CPU (fp32), fixture tests/golden/kitti_e2e.pt", "noise_floor_of_the_reference_px": c["noise_floor_px"]}
+
+    def epe(a, b):
+        return torch.sqrt(((a - b) ** 2).sum(1)).mean().item()
+    with torch.no_grad():
+        for name, thr, key in (("robust_mask", 0.9999, "flow_f_robust"), ("real_mask", 1.0, "flow_f_reference")):
+            eng.mask = True if thr == 1.0 else thr
+            f, _, _ = eng.forward(im1.cuda(), im2.cuda())
+            out[name] = epe(f.cpu(), c[key])
+    eng.mask = True
+    return out
 
 
 def corr_roofline(pk, iters=20):
@@ -332,6 +453,7 @@ def _main():
     ap.add_argument("--workload", default="kitti_375x1242_b1", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "tf32x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the `train` sub-record (BASELINE config 4) of the default line")
     ap.add_argument("--no-train-graph", action="store_true", help="training workload: eager launches instead of a CUDA graph")
     ap.add_argument("--train-losses", default="plain", choices=["plain", "all"],
                     help="training workload: 'plain' = photo + smooth + msd (the line BASELINE config 4 is measured on); "
@@ -368,10 +490,9 @@ def _main():
     H, W, B = WORKLOADS[args.workload]
     pk = peaks()
 
-    import upflow_pytorch_b200 as pkg
     from upflow_pytorch_b200 import _ext, profiler
-    sd = make_weights()
-    net = pkg.build_model(state_dict=sd, conv_precision=args.precision)      # public API object (drop-in UPFlow_net)
+    from upflow_pytorch_b200.pipeline import PipelinedInference
+    net, sd, wdesc = build_net(None, args.precision)                         # public API object (drop-in UPFlow_net)
     im1_h, im2_h = synth_inputs(B, H, W, 1234 + rank)
     im1_h, im2_h = im1_h.pin_memory(), im2_h.pin_memory()
     im1_d, im2_d = im1_h.cuda(), im2_h.cuda()
@@ -417,28 +538,50 @@ def _main():
     step_ms = max_over_ranks(step_ms)
     value = world * B / (step_ms * 1e-3)
 
-    # ---------------- e2e: public API, pinned host in, host out, every step
+    # ---------------- e2e: public API, pinned host in, host out, every step.  Depth-2 pipeline (pipeline.py): the
+    # host->device copy of pair k+1 and the device->host copy of flow k-1 run on a copy stream under the forward of pair
+    # k; every step still moves its own inputs and its own result, and the caller holds flow k-1 when submit(k) returns.
+    pipe = PipelinedInference(net)
+    for _ in range(W_):
+        pipe.submit(im1_h, im2_h)
+    pipe.flush()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(pipe.compute)
+    for _ in range(K):
+        pipe.submit(im1_h, im2_h)
+    flow_host = pipe.flush()                             # the last result is on the host when the clock stops
+    e1.record(pipe.copy)
+    barrier()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / K
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1) / K, e2e_wall_ms))      # the slower of the device and the host clock
+    e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": 2 * im1_h.numel() * 4, "d2h_bytes_per_step": flow_host.numel() * 4,
+           "api": "UPFlow_net(input_dict)['flow_f_out'] (drop-in model.upflow) behind upflow_pytorch_b200.pipeline."
+                  "PipelinedInference: pinned host tensors in, pinned host flow out, copies of step k+1 / k-1 overlap "
+                  "the forward of step k (K steps timed from the first submit to the last flow on the host)"}
+    # the same call without the pipeline (copy in, forward, copy out, wait), for the record
     out_h = torch.empty(B, 2, H, W).pin_memory()
     with torch.no_grad():
-        def e2e_step():
-            a = im1_h.cuda(non_blocking=True)
-            b = im2_h.cuda(non_blocking=True)
-            o = net({"im1": a, "im2": b, "if_loss": False})
+        def serial_step():
+            o = net({"im1": im1_h.cuda(non_blocking=True), "im2": im2_h.cuda(non_blocking=True), "if_loss": False})
             out_h.copy_(o["flow_f_out"], non_blocking=True)
-            torch.cuda.current_stream().synchronize()    # the caller reads the flow
-        for _ in range(W_):
-            e2e_step()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(K):
-            e2e_step()
-        e1.record()
-        barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1) / K)
-    e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": 2 * im1_h.numel() * 4, "d2h_bytes_per_step": out_h.numel() * 4,
-           "api": "UPFlow_net(input_dict)['flow_f_out'] (drop-in model.upflow), pinned host tensors in and out"}
+            torch.cuda.current_stream().synchronize()
+        for _ in range(3):
+            serial_step()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(min(K, 20)):
+            serial_step()
+        s1.record()
+        torch.cuda.synchronize()
+    e2e["serial_ms_per_step"] = s0.elapsed_time(s1) / min(K, 20)
+
+    # ---------------- the training step of BASELINE config 4 on the same ranks (4 pairs per GPU, NCCL all-reduce)
+    train = None
+    if args.workload == "kitti_375x1242_b1" and not args.no_train:
+        train = measure_train(args, rank, world, local, dist, 10, 3)
 
     line = None
     if rank == 0:
@@ -512,6 +655,7 @@ def _main():
             cpu = {"value": B / dt, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "%d forward(s) of the same %dx%d batch-%d pair after 1 warm-up, %d torch threads" % (reps, H, W, B, cores),
                    "epe_cuda_vs_cpu_port_px": O.epe(f.cpu(), rf)}
+        epe = epe_vs_reference(args, net, H, W, B)
 
         # ---------------- the reference's GPU path (the >= 10x target is against it): the op-for-op
         # port of model/upflow.py (F.conv2d / cuDNN, F.grid_sample, unfold correlation) in eager PyTorch on this GPU,
@@ -547,14 +691,21 @@ def _main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic",
-                "config": {"workload": args.workload, "pairs_per_step_per_gpu": B, "image": [H, W],
-                           "pyramid_levels": 6, "decoder_levels": 5, "sgu": True, "directions": "forward+backward stacked",
-                           "weights": "random-init (MSRA, seed 1234): no checkpoint on the GPU box",
-                           "l2": "flushed (256 MiB write) before every timed step; flush outside the step events",
-                           "launch": "one CUDA graph replay per step", "parallelism": "batch-sharded x%d, no collective in inference" % world},
+                "config": workload_config(args.workload, wdesc),
+                "timing": {"l2": "flushed (256 MiB write) before every timed step; flush outside the step events",
+                           "launch": "one CUDA graph replay per step, both flow directions stacked in one batch",
+                           "parallelism": "batch-sharded x%d, no collective in inference" % world},
                 "e2e": e2e, "gpu_launches": graphed.launches * K, "launches_per_step": graphed.launches,
                 "clocks": clocks, "roofline": roof, "roofline_corr": rc, "kernel_breakdown_ms": breakdown,
                 "wall_s_timed_region": wall}
+        if epe is not None:
+            line["epe_vs_reference_px"] = epe
+        if train is not None:
+            if world == 1 and not args.no_cpu_baseline:
+                train["reference_gpu_path"] = reference_gpu_train_step(args)
+                if "value" in train["reference_gpu_path"]:
+                    train["reference_gpu_path"]["speedup_over_it"] = train["value"] / train["reference_gpu_path"]["value"]
+            line["train"] = train
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if ref_gpu is not None:

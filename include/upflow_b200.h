@@ -32,11 +32,18 @@
 extern "C" {
 #endif
 
-#define UPF_ABI_VERSION 1
+#define UPF_ABI_VERSION 2
 
 #define UPF_EINVAL   (-1)  /* bad argument (shape, alignment, unsupported value) */
 #define UPF_ENOTSUP  (-2)  /* valid request this build cannot serve            */
 #define UPF_EDRIVER  (-3)  /* CUDA driver entry point / tensor-map failure     */
+
+/* `flags` bit of the producers below: store the result ROUNDED TO THE NEAREST TF32 value (10 mantissa bits, ties away
+ * from zero -- cvt.rna.tf32.f32).  tcgen05 kind::tf32 reads the top 19 bits of an fp32 operand, i.e. TRUNCATES; a
+ * buffer whose only consumers are tensor-core convolutions is therefore written pre-rounded by whoever produces it
+ * (unbiased operand error 2^-12 instead of a one-sided 2^-11: mean EPE vs the fp32 reference 5.6e-4 px instead of
+ * 3.8e-3 at KITTI size with the shipped checkpoint, robust-mask diagnostic).  Weights are rounded when packed. */
+#define UPF_FLAG_ROUND_TF32 1
 
 int         upf_abi_version(void);
 const char* upf_last_error(void);
@@ -64,7 +71,7 @@ const char* upf_last_kernel(void);
 int upf_corr_lrelu_fwd(const float* f1, int ld1, const float* f2, int ld2,
                        float* out, int ldo, int N, int H, int W, int C, int max_disp,
                        const double* stats1, const double* stats2, int f2_batch_shift,
-                       float slope, void* stream);
+                       float slope, int flags, void* stream);
 
 /* a11: gradients of the (un-normalised) cost volume wrt f1 and f2.
  *   replaces correlation_cuda.backward (correlation_cuda.cc:89-167, kernels
@@ -89,7 +96,7 @@ int upf_corr_lrelu_bwd(const float* f1, int ld1, const float* f2, int ld2,
  * samples image (n + shift) % N of x (see upf_corr_lrelu_fwd). */
 int upf_warp_fwd(const float* x, int ldx, const float* flow, int ldf, float* out, int ldo,
                  int N, int H, int W, int C, int align_corners, float mask_threshold,
-                 int x_batch_shift, double* stats, void* stream);
+                 int x_batch_shift, double* stats, int flags, void* stream);
 
 /* a11: backward of upf_warp_fwd wrt x (scatter-add; grad_x must be zeroed by the
  * caller) and wrt flow (grad_flow [N,H,W,2], written).  Either may be NULL. */
@@ -110,6 +117,14 @@ int upf_occ_check(const float* flow, int ldf, float* occ, int ldo, int N, int H,
 int upf_featnorm_stats(const float* x, int ldx, int N, int H, int W, int C, double* stats, void* stream);
 int upf_featnorm_apply(const float* x, int ldx, const double* stats, float* out, int ldo,
                        int N, int H, int W, int C, void* stream);
+/* normalize_features' other moment modes (model/upflow.py:109-124; the reference's DEFAULT configuration, :311-313):
+ * moments pooled over the channels of an image (mean / unbiased var over [C,H,W]) and / or over the two tensors of a
+ * (feature, warped feature) pair -- the mean of the two means and, as the reference computes it (:121-124), the unbiased
+ * variance of the two variances.  stats_a image n is paired with stats_b image (n + b_batch_shift) % N; out_a[n] and
+ * out_b[(n + b_batch_shift) % N] receive EQUIVALENT per-channel moments (sum' = mean*npix, sumsq' = var*(npix-1) +
+ * sum'*mean) that upf_corr_lrelu_fwd / upf_featnorm_apply turn back into the pooled mean and std.  C <= 256. */
+int upf_featnorm_combine(const double* stats_a, const double* stats_b, int b_batch_shift, double* out_a, double* out_b,
+                         int N, int C, long long npix, int across_channels, int across_images, void* stream);
 
 /* a6: upsample2d_flow_as / upsample2d_as (model/pwc_modules.py:72-90):
  * bilinear, align_corners=True, channel c multiplied by scale[c] afterwards
@@ -124,9 +139,14 @@ int upf_resize_bilinear(const float* in, int ldi, int h, int w, float* out, int 
  *   out = warp(flow_init, inter_flow)*(1-sigmoid(m)) + flow_init*sigmoid(m)
  * output-level variant (ih<H): inter_flow is bilinearly upsampled (align_corners
  * =True) and scaled by (W/iw, H/ih); sigmoid(m) is upsampled AFTER the sigmoid
- * (model/upflow.py:84-86). */
+ * (model/upflow.py:84-86).
+ * out_tf32 (nullable) [N,H,W,>=4] pitch ldt: a second copy of the result for tensor-core consumers, channels
+ * (rn_tf32(u), rn_tf32(v), 0, 0) when flags has UPF_FLAG_ROUND_TF32, (u, v, 0, 0) otherwise -- the decoder's estimator
+ * buffer keeps flow_up in a 4-channel slot whose second half (flow_up + flow_res) is written later in the level; clearing
+ * it here means no value of a previous forward is ever read. */
 int upf_sgu_blend(const float* flow_init, int ldf, const float* inter, int ldi, int ih, int iw,
-                  float* out, int ldo, int N, int H, int W, int align_corners, void* stream);
+                  float* out, int ldo, float* out_tf32, int ldt, int N, int H, int W, int align_corners, int flags,
+                  void* stream);
 
 /* a8/a9 (+ the dense block of a7): Conv2d(k in {1,3}, pad=((k-1)*dil)/2) + bias
  * + LeakyReLU(slope) [+ residual], reading an input channel slice and writing
@@ -146,6 +166,8 @@ int upf_sgu_blend(const float* flow_init, int ldf, const float* inter, int ldi, 
  *            (bitwise reproducible, no scratch buffer). */
 #define UPF_CONV_FP32 0
 #define UPF_CONV_TF32 1
+/* OR-ed into `precision`: store the output rounded to the nearest TF32 value (see UPF_FLAG_ROUND_TF32) */
+#define UPF_CONV_ROUND_OUT 0x100
 int upf_conv2d_fwd(const float* x, int ldx, const float* w, const float* bias,
                    float* out, int ldo, const float* residual, int ldr,
                    int N, int H, int W, int Cin, int Cout, int ksize, int stride, int dilation,
@@ -158,10 +180,11 @@ int upf_conv2d_fwd(const float* x, int ldx, const float* w, const float* bias,
  * taps falling outside the image contributing nothing.  On the tensor cores a 3x3 conv with Cout <= 8 otherwise
  * issues nine N=16 MMAs per K step for one N<=80 MMA's worth of products. */
 int upf_conv3x3_tap_combine(const float* y, int ldy, const float* bias, float* out, int ldo, const float* residual,
-                            int ldr, int N, int H, int W, int Cout, int dilation, float slope, void* stream);
+                            int ldr, int N, int H, int W, int Cout, int dilation, float slope, int flags, void* stream);
 
 /* TF32 tensor-core path: weights packed as [tap][cout_pad16][cin_pad32] fp32
- * (K-major rows of 32 input channels), done on the device from the SIMT layout. */
+ * (K-major rows of 32 input channels), done on the device from the SIMT layout; values rounded to the nearest TF32
+ * (the MMA would otherwise truncate them). */
 long long upf_conv_tc_packed_elems(int Cin, int Cout, int ksize);
 int upf_conv_tc_pack_weights(const float* w_simt, float* w_packed, int Cin, int Cout, int ksize, void* stream);
 
@@ -303,8 +326,8 @@ int upf_boundary_warp_bwd(const float* image, int ldi, int C, int Hf, int Wf, co
  * layout): strided copy between [N,C,H,W] planes and pixel-major rows. */
 int upf_nchw_to_nhwc(const float* in, float* out, int ldo, int N, int C, int H, int W, void* stream);
 int upf_nhwc_to_nchw(const float* in, int ldi, float* out, int N, int C, int H, int W, void* stream);
-/* out[n,y,x,0:C] = in[n,y,x,0:C] between two pitched buffers */
-int upf_copy_channels(const float* in, int ldi, float* out, int ldo, long long npix, int C, void* stream);
+/* out[n,y,x,0:C] = in[n,y,x,0:C] between two pitched buffers (flags: UPF_FLAG_ROUND_TF32); in == NULL writes zeros */
+int upf_copy_channels(const float* in, int ldi, float* out, int ldo, long long npix, int C, int flags, void* stream);
 
 #ifdef __cplusplus
 }

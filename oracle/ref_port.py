@@ -80,6 +80,26 @@ def upsample2d_flow_as(x, h, w, if_rate=False):
     return res
 
 
+# (if_norm_before_cost_volume, norm_moments_across_channels, norm_moments_across_images) of UPFlow_net.config
+# (model/upflow.py:311-313).  test.py:24-26 runs (True, False, False); the class default is (False, True, True).
+NORM_MODE = (True, False, False)
+
+
+def normalize_pair(fa, fb):
+    # network_tools.normalize_features((fa, fb), normalize=True, center=True, ...)   model/upflow.py:94-137, :549-555
+    if_norm, across_ch, across_img = NORM_MODE
+    if not if_norm:
+        return fa, fb
+    axes = [1, 2, 3] if across_ch else [2, 3]
+    means = [torch.mean(f, dim=axes, keepdim=True) for f in (fa, fb)]
+    variances = [torch.var(f, dim=axes, keepdim=True) for f in (fa, fb)]
+    if across_img:
+        means = [torch.mean(torch.stack(means, dim=0), dim=(0,))] * 2
+        variances = [torch.var(torch.stack(variances, dim=0), dim=(0,))] * 2
+    stds = [torch.sqrt(v + 1e-16) for v in variances]
+    return (fa - means[0]) / stds[0], (fb - means[1]) / stds[1]
+
+
 def normalize(f):
     # network_tools.normalize_features, per image per channel   model/upflow.py:108-135
     mean = torch.mean(f, dim=[2, 3], keepdim=True)
@@ -132,8 +152,8 @@ def decode_level(level, flow_1, flow_2, x1, x1_1x1, x2, x2_1x1, sd, use_sgu=True
             f2u = sgu(f2u, x2_1x1, x1_1x1, sd)[0]
         x2w = warp_mask(x2, f1u)
         x1w = warp_mask(x1, f2u)
-    n1, n2w = normalize(x1), normalize(x2w)
-    n2, n1w = normalize(x2), normalize(x1w)
+    n1, n2w = normalize_pair(x1, x2w)
+    n2, n1w = normalize_pair(x2, x1w)
     c1 = F.leaky_relu(corr_unfold(n1, n2w), SLOPE)
     c2 = F.leaky_relu(corr_unfold(n2, n1w), SLOPE)
     x5_1, r1 = dense(torch.cat([c1, x1_1x1, f1u], dim=1), sd, "flow_estimators")

@@ -48,7 +48,7 @@ def test_ctypes_signatures_match_header(lib_path):
     for name, n in d.items():
         assert len(_ext.SIGNATURES[name][1]) == n, name
     lib = _ext.load()
-    assert lib.upf_abi_version() == 1
+    assert lib.upf_abi_version() == _ext.ABI_VERSION == 2
     assert lib.upf_launch_count() == 0
 
 
@@ -56,7 +56,7 @@ def test_bad_arguments_return_codes_not_crashes(lib_path):
     """argument validation happens on the host before any launch (works without a GPU)"""
     from upflow_pytorch_b200 import _ext
     lib = _ext.load()
-    rc = lib.upf_corr_lrelu_fwd(None, 32, None, 32, None, 81, 1, 8, 8, 32, 4, None, None, 0, 0.1, None)
+    rc = lib.upf_corr_lrelu_fwd(None, 32, None, 32, None, 81, 1, 8, 8, 32, 4, None, None, 0, 0.1, 0, None)
     assert rc == -1 and b"null" in lib.upf_last_error()
     rc = lib.upf_conv2d_fwd(ctypes.c_void_p(16), 32, ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), 32,
                             None, 0, 1, 8, 8, 32, 32, 5, 1, 1, 0.1, 0, None)

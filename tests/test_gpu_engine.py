@@ -207,3 +207,135 @@ def test_tf32x3_is_fp32_class():
             prec, O.epe(res[prec][0], rf), O.epe(res[prec][1], rb), O.epe(res[prec][0], res["fp32"][0])))
     assert O.epe(res["tf32x3"][0], rf) <= 1e-3 and O.epe(res["tf32x3"][1], rb) <= 1e-3
     assert O.epe(res["tf32x3"][0], res["fp32"][0]) <= 1e-3
+
+
+# ------------------------------------------------------------------ the shipped checkpoint (BASELINE config 2)
+def _checkpoint_net(precision):
+    """the drop-in UPFlow_net with scripts/upflow_kitti2015.pth (fixture copy) loaded the way test.py:31-38 does"""
+    import os
+    import upflow_pytorch_b200 as pkg
+    GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    net = pkg.build_model(conv_precision=precision)
+    net.load_model(os.path.join(GOLDEN, "upflow_kitti2015.pth"), if_relax=True, if_print=False)
+    return net.cuda().eval()
+
+
+@pytest.mark.parametrize("size", [0, 1])
+def test_checkpoint_epe_vs_reference_at_full_size(golden, size):
+    """North-star parity (EPE within 1e-3 px of the reference) with the SHIPPED weights at 375x1242 and 436x1024:
+    every precision against the reference's own CPU flow.  Robust-mask diagnostic (threshold 0.9999 on both sides):
+    fp32 and tf32x3 to rounding, tf32 (operands rounded to nearest) inside 1e-3.  Reference mask (`>= 1.0`): inside
+    the reference's own 1e-6-perturbation noise floor (stored with the fixture) times a small factor."""
+    c = golden("kitti_e2e")[size]
+    im1, im2 = O.synthetic_pair(c["H"], c["W"], seed=c["seed"])
+    for precision, bound in (("fp32", 1e-4), ("tf32x3", 1e-4), ("tf32", 1e-3)):
+        net = _checkpoint_net(precision)
+        eng = net._get_engine()
+        res = {}
+        for name, thr, key in (("robust", 0.9999, "flow_f_robust"), ("reference", 1.0, "flow_f_reference")):
+            eng.mask = True if thr == 1.0 else thr
+            with torch.no_grad():
+                f, _, _ = eng.forward(im1.cuda(), im2.cuda())
+            res[name] = O.epe(f.cpu(), c[key])
+        eng.mask = True
+        print("checkpoint %dx%d %-7s mean EPE vs reference: robust mask %.3g px, reference mask %.3g px (noise floor %.3g)"
+              % (c["H"], c["W"], precision, res["robust"], res["reference"], c["noise_floor_px"]))
+        assert res["robust"] <= bound, (precision, res)
+        assert res["reference"] <= 3 * c["noise_floor_px"], (precision, res)
+
+
+def test_checkpoint_through_the_public_api(golden):
+    """net(input_dict) (CUDA-graph replay) with the checkpoint: the same flow as the eager engine, and the motion."""
+    c = golden("kitti_e2e")[0]
+    im1, im2 = O.synthetic_pair(c["H"], c["W"], seed=c["seed"])
+    net = _checkpoint_net("tf32")
+    with torch.no_grad():
+        out = net({"im1": im1.cuda(), "im2": im2.cuda(), "if_loss": False})
+        out2 = net({"im1": im1.cuda(), "im2": im2.cuda(), "if_loss": False})
+    f = out["flow_f_out"].cpu()
+    assert torch.equal(f, out2["flow_f_out"].cpu())
+    assert O.epe(f, c["flow_f_reference"]) <= 3 * c["noise_floor_px"]
+    assert abs(f[:, 0].mean().item() + 3) < 0.1 and abs(f[:, 1].mean().item() - 2) < 0.1
+
+
+# ------------------------------------------------------------------ configurations other than test.py's
+def test_config_modes_vs_reference_golden(golden):
+    """UPFlow_net.config() class defaults (no normalisation, no SGU: model/upflow.py:311-323) and the other stable
+    configurations run on the fused engine and match the reference's own outputs (oracle/make_golden_kitti.py)."""
+    import contextlib
+    import io
+    import upflow_pytorch_b200 as pkg
+    pkg.install_dropin()
+    from model.upflow import UPFlow_net
+    for c in golden("e2e_modes")["e2e"]:
+        conf = UPFlow_net.config()
+        with contextlib.redirect_stdout(io.StringIO()):
+            conf.update(dict(c["params"]))
+        net = conf()
+        net.conv_precision = "fp32"
+        sd = P.det_state_dict(c["wseed"])
+        net.load_state_dict({k: v for k, v in sd.items() if k in net.state_dict()})
+        net = net.cuda().eval()
+        im1, im2 = O.synthetic_pair(*c["hw"], seed=c["pair_seed"])
+        with torch.no_grad():
+            out = net({"im1": im1.cuda(), "im2": im2.cuda(), "if_loss": False})
+        e = O.epe(out["flow_f_out"].cpu(), c["flow_f_out"])
+        agree = (out["occ_fw"].cpu() == c["occ_fw"]).float().mean().item()
+        print("config", c["name"], "EPE vs reference %.3g px, occlusion agreement %.4f" % (e, agree))
+        assert e <= 0.05 and agree >= 0.97, c["name"]
+
+
+def test_pooled_moment_modes_at_the_operator(golden):
+    """normalize_features' pooled modes (model/upflow.py:109-124) through statistics + upf_featnorm_combine + the fused
+    correlation, against the reference's normalize_features followed by Corr_pyTorch.  The across-images mode divides
+    by the std of the two VARIANCES (the reference's arithmetic), so values are large: relative tolerance."""
+    from upflow_pytorch_b200 import ops
+    for c in golden("e2e_modes")["ops"]:
+        fa, fb = ops.to_pixel_major(c["fa"].cuda()), ops.to_pixel_major(c["fb"].cuda())
+        N, H, W, C = fa.shape
+        sa = torch.zeros(N, C, 2, dtype=torch.float64, device="cuda")
+        sb, ca, cb = torch.zeros_like(sa), torch.zeros_like(sa), torch.zeros_like(sa)
+        ops.k_stats(fa, sa)
+        ops.k_stats(fb, sb)
+        ops.k_norm_combine(sa, sb, ca, cb, N, C, H * W, 0, c["across_channels"], c["across_images"])
+        out = torch.zeros(N, H, W, 81, device="cuda")
+        ops.k_corr(fa, fb, out, 4, ca, cb, slope=1.0)
+        got = out.permute(0, 3, 1, 2).cpu()
+        rel = ((got - c["corr"]).abs().max() / c["corr"].abs().max()).item()
+        na = torch.zeros_like(fa)
+        ops.k_norm_apply(fa, ca, na)
+        rel_n = ((na.permute(0, 3, 1, 2).cpu() - c["na"]).abs().max() / c["na"].abs().max()).item()
+        print("pooled moments ch=%s img=%s: normalised rel err %.3g, correlation rel err %.3g" % (
+            c["across_channels"], c["across_images"], rel_n, rel))
+        assert rel_n <= 2e-5 and rel <= 5e-5
+
+
+# ------------------------------------------------------------------ BASELINE configs 3 and 5 at their sizes
+@pytest.mark.parametrize("case", [("sintel", 436, 1024, 8), ("hd", 1080, 1920, 2)])
+def test_sintel_and_hd_sizes_vs_port(case):
+    """436x1024 batch 8 and 1080x1920 batch 2 (BASELINE configs 3 and 5) against the CPU port, robust-mask diagnostic
+    on both sides, shipped weights: fp32 engine to rounding, tf32 inside 2e-3 px.  Every image of the batch is its own
+    pair (different seeds); the port runs them one by one."""
+    import os
+    GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    name, H, W, B = case
+    sd = torch.load(os.path.join(GOLDEN, "upflow_kitti2015.pth"), weights_only=True)
+    pairs = [O.synthetic_pair(H, W, seed=1234 + i) for i in range(B)]
+    im1, im2 = torch.cat([p[0] for p in pairs]), torch.cat([p[1] for p in pairs])
+    ref_idx = (0, B - 1) if B > 2 else tuple(range(B))       # the port costs 4-13 s per pair: first and last image
+    P.MASK_THRESHOLD = 0.9999
+    try:
+        with torch.no_grad():
+            refs = {i: P.forward_2_frame(im1[i:i + 1], im2[i:i + 1], sd)[0] for i in ref_idx}
+    finally:
+        P.MASK_THRESHOLD = 1.0
+    for precision, bound in (("fp32", 1e-4), ("tf32", 2e-3)):
+        eng = _engine(precision, sd, mask_threshold=0.9999)
+        f, b, _ = eng.forward(im1.cuda(), im2.cuda())
+        f = f.cpu()
+        for i in ref_idx:
+            e = O.epe(f[i:i + 1], refs[i])
+            print(name, "%dx%d b%d" % (H, W, B), precision, "image", i, "mean EPE vs port %.3g px" % e)
+            assert e <= bound, (name, precision, i, e)
+        del eng
+        torch.cuda.empty_cache()

@@ -30,6 +30,12 @@ def _regen(seed, shape):
     return torch.randn(shape, generator=_g(seed))
 
 
+def _rn_tf32(t):
+    """nearest TF32 value, ties away from zero (cvt.rna.tf32.f32): what the weight packers and the UPF_FLAG_ROUND_TF32
+    producers store; tcgen05 kind::tf32 itself truncates whatever it is given"""
+    return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 # ------------------------------------------------------------------ correlation
 def test_corr_golden(upf, golden):
     """BASELINE config 1 (1x32x64x64, d=4) and the ragged / d=2 / d=6 / C=196 cases, vs Corr_pyTorch outputs."""
@@ -249,7 +255,7 @@ def test_conv_tf32_tensor_core_vs_oracle(upf, case):
 
     def trunc(t):
         return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
-    ref_t = O.conv2d_direct(trunc(x).double(), trunc(w).double(), b.double(), dil, stride, 0.1).float()
+    ref_t = O.conv2d_direct(trunc(x).double(), _rn_tf32(w).double(), b.double(), dil, stride, 0.1).float()
     ref = O.conv2d_direct(x.double(), w.double(), b.double(), dil, stride, 0.1).float()
     err_t = (out - ref_t).abs().max().item()
     err = (out - ref).abs().max().item()
@@ -310,7 +316,7 @@ def test_conv_tf32_cluster_split_k_and_stride2(upf, case):
 
     def trunc(t):
         return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
-    ref = O.conv2d_direct(trunc(x).double(), trunc(w).double(), b.double(), dil, stride, 0.1).float()
+    ref = O.conv2d_direct(trunc(x).double(), _rn_tf32(w).double(), b.double(), dil, stride, 0.1).float()
     res = _regen(53, tuple(ref.shape))
     ld = (Cin + 3) // 4 * 4
     a = Slice(upf.to_pixel_major(_cuda(x), ld=ld), 0, Cin)
@@ -378,7 +384,7 @@ def test_conv_tf32_large_grid_kernels_agree(upf, case):
 
     def trunc(t):
         return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
-    ref = O.conv2d_direct(trunc(x).double(), trunc(w).double(), b.double(), dil, 1, 0.1).float()
+    ref = O.conv2d_direct(trunc(x).double(), _rn_tf32(w).double(), b.double(), dil, 1, 0.1).float()
     ld = (Cin + 3) // 4 * 4 + 8
     a = Slice(upf.to_pixel_major(_cuda(x), ld=ld), 0, Cin)
     ldo = (Cout + 3) // 4 * 4 + 4
@@ -412,7 +418,7 @@ def test_conv3x3_expand_then_tap_combine(upf, case):
     x, w, b = _regen(70, (2, Cin, H, W)), _regen(71, (Cout, Cin, 3, 3)) * 0.05, _regen(72, (Cout,)) * 0.1
     res = _regen(73, (2, Cout, H, W))
     trunc = lambda t: (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
-    ref = O.conv2d_direct(trunc(x).double(), trunc(w).double(), b.double(), dilation=dil, leaky_slope=0.1).float() + res
+    ref = O.conv2d_direct(trunc(x).double(), _rn_tf32(w).double(), b.double(), dilation=dil, leaky_slope=0.1).float() + res
     a = upf.to_pixel_major(_cuda(x))
     wexp = upf.pack_conv_weight(upf.expand_taps_weight(_cuda(w)), tc=True)[1]
     Y = torch.zeros(2, H, W, 9 * 8, device="cuda")
@@ -422,3 +428,98 @@ def test_conv3x3_expand_then_tap_combine(upf, case):
     upf.k_tap_combine(ys, _cuda(b), out, dil, 0.1, upf.to_pixel_major(_cuda(res)))
     err = (out.permute(0, 3, 1, 2).cpu() - ref).abs().max().item()
     assert err <= 5e-4, err
+
+
+# ------------------------------------------------------------------ TF32-rounded producers (UPF_FLAG_ROUND_TF32)
+def test_round_tf32_flag_is_exactly_the_rounded_plain_result(upf):
+    """Every producer that can store its result pre-rounded for tensor-core consumers must store EXACTLY
+    rn_tf32(the un-rounded result): convolution epilogues of all kernel families (SIMT, image conv, cluster split-K,
+    window, halo), tap combine, correlation (small / tiled / pipelined), warp, channel copy, SGU blend."""
+    from upflow_pytorch_b200 import _ext
+    from upflow_pytorch_b200.ops import Slice
+    g = _g(77)
+    dev = "cuda"
+
+    def conv_pair(N, H, W, Cin, Cout, k, stride, dil, prec):
+        x = torch.randn(N, H, W, Cin, generator=g).to(dev)
+        w = (torch.randn(Cout, Cin, k, k, generator=g) * 0.1).to(dev)
+        b = (torch.randn(Cout, generator=g) * 0.1).to(dev)
+        ws, wt = upf.pack_conv_weight(w, tc=prec == _ext.CONV_TF32)
+        wk = wt if prec == _ext.CONV_TF32 else ws
+        pad = ((k - 1) * dil) // 2
+        Ho, Wo = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1, (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
+        outs = []
+        for flag in (0, _ext.CONV_ROUND_OUT):
+            o = torch.zeros(N, Ho, Wo, Cout, device=dev)
+            upf.k_conv(Slice(x), wk, b, Slice(o), k, stride, dil, 0.1, None, prec | flag)
+            outs.append(o.cpu())
+        return outs
+
+    cases = [(2, 20, 24, 3, 16, 3, 2, 1, _ext.CONV_FP32),        # conv_c3
+             (1, 9, 11, 20, 12, 3, 1, 1, _ext.CONV_FP32),        # conv_simt
+             (2, 12, 20, 64, 96, 3, 1, 8, _ext.CONV_TF32),       # conv_tc (cluster split-K)
+             (2, 94, 100, 64, 32, 3, 1, 1, _ext.CONV_TF32),      # conv_win
+             (2, 94, 100, 96, 128, 3, 1, 2, _ext.CONV_TF32)]     # conv_halo
+    for c in cases:
+        plain, rounded = conv_pair(*c)
+        assert torch.equal(rounded, _rn_tf32(plain)), c
+        assert not torch.equal(rounded, plain)
+
+    # correlation: coarse (corr_small), tiled and pipelined shapes
+    for (N, C, H, W) in ((2, 32, 12, 20), (1, 30, 40, 48), (2, 32, 94, 160)):
+        f1, f2 = torch.randn(N, H, W, C, generator=g).to(dev), torch.randn(N, H, W, C, generator=g).to(dev)
+        o0, o1 = torch.zeros(N, H, W, 81, device=dev), torch.zeros(N, H, W, 81, device=dev)
+        upf.k_corr(f1, f2, o0, 4, slope=0.1)
+        upf.k_corr(f1, f2, o1, 4, slope=0.1, round_tf32=True)
+        assert torch.equal(o1.cpu(), _rn_tf32(o0.cpu())), (N, C, H, W)
+
+    # warp, copy, tap combine, blend
+    x = torch.randn(2, 30, 44, 32, generator=g).to(dev)
+    fl = (torch.randn(2, 30, 44, 2, generator=g) * 3).to(dev)
+    o0, o1 = torch.zeros_like(x), torch.zeros_like(x)
+    upf.k_warp(x, fl, o0)
+    upf.k_warp(x, fl, o1, round_tf32=True)
+    assert torch.equal(o1.cpu(), _rn_tf32(o0.cpu()))
+    big = torch.zeros(2, 30, 44, 40, device=dev)
+    upf.k_copy(Slice(x, 0, 30), Slice(big, 4, 30), round_tf32=True)
+    assert torch.equal(big[..., 4:34].cpu(), _rn_tf32(x[..., :30].cpu()))
+    assert big[..., :4].abs().max().item() == 0 and big[..., 34:].abs().max().item() == 0
+    upf.k_copy(None, Slice(big, 4, 30))
+    assert big.abs().max().item() == 0
+    y = torch.randn(2, 30, 44, 72, generator=g).to(dev)
+    bias = torch.randn(8, generator=g).to(dev)
+    o0, o1 = torch.zeros(2, 30, 44, 8, device=dev), torch.zeros(2, 30, 44, 8, device=dev)
+    upf.k_tap_combine(y, bias, o0, 1, 0.1)
+    upf.k_tap_combine(y, bias, o1, 1, 0.1, round_tf32=True)
+    assert torch.equal(o1.cpu(), _rn_tf32(o0.cpu()))
+    inter = torch.randn(2, 30, 44, 4, generator=g).to(dev)
+    o0, o1 = torch.zeros(2, 30, 44, 2, device=dev), torch.zeros(2, 30, 44, 2, device=dev)
+    slot = torch.full((2, 30, 44, 8), 7.0, device=dev)
+    upf.k_sgu_blend(fl, Slice(inter, 0, 3), o0)
+    upf.k_sgu_blend(fl, Slice(inter, 0, 3), o1, out_tc=Slice(slot, 2, 4), round_tf32=True)
+    assert torch.equal(o0.cpu(), o1.cpu())                                   # the exact output does not change
+    assert torch.equal(slot[..., 2:4].cpu(), _rn_tf32(o0.cpu()))
+    assert slot[..., 4:6].abs().max().item() == 0 and (slot[..., :2] == 7).all() and (slot[..., 6:] == 7).all()
+
+
+def test_tc_weight_packing_rounds_to_nearest(upf):
+    """the tensor-core weight layouts hold rn_tf32(w): a convolution on them equals the oracle on rounded weights and
+    truncated activations to fp32 rounding (and is closer to the exact result than truncated weights would be)"""
+    from upflow_pytorch_b200 import _ext
+    from upflow_pytorch_b200.ops import Slice
+    g = _g(5)
+    x, w, b = torch.randn(1, 24, 40, 64, generator=g), torch.randn(32, 64, 3, 3, generator=g) * 0.05, torch.zeros(32)
+    trunc = lambda t: (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+    xn = x.permute(0, 3, 1, 2).contiguous()
+    ref_rn = O.conv2d_direct(trunc(xn).double(), _rn_tf32(w).double(), b.double(), 1, 1, 1.0).float()
+    ref_tr = O.conv2d_direct(trunc(xn).double(), trunc(w).double(), b.double(), 1, 1, 1.0).float()
+    for ft in (False, True):
+        if ft:
+            _, wt = upf.pack_conv_weight(w.cuda(), tc=True, tc_only=True)
+        else:
+            _, wt = upf.pack_conv_weight(w.cuda(), in_slots=list(range(64)), cin_total=64, tc=True)
+        out = torch.zeros(1, 24, 40, 32, device="cuda")
+        upf.k_conv(Slice(x.cuda()), wt, b.cuda(), Slice(out), 3, 1, 1, 1.0, None, _ext.CONV_TF32)
+        got = out.permute(0, 3, 1, 2).cpu()
+        assert (got - ref_rn).abs().max().item() <= 5e-5
+        assert (got - ref_tr).abs().max().item() > 2e-4

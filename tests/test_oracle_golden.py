@@ -152,3 +152,72 @@ def test_loss_side_ops_match_the_reference(golden):
     for key, charb, occ in (("census_occ", False, True), ("census_noocc", False, False), ("census_charb", True, True)):
         v = loss_functions.census_loss_torch(g["a"], g["b"], g["mask"], 0.4, charb, occ, True).item()
         assert abs(v - g[key]) <= 1e-5 * abs(g[key]), (key, v, g[key])
+
+
+def test_port_config_modes_match_the_reference(golden):
+    """the port under the configurations other than test.py's (model/upflow.py:311-323 class defaults: no
+    normalisation, no SGU; pooled moments) against the reference's own outputs, and normalize_features' pooled modes
+    at the operator (oracle/make_golden_kitti.py)."""
+    g = golden("e2e_modes")
+    for c in g["e2e"]:
+        sd = P.det_state_dict(c["wseed"])
+        im1, im2 = O.synthetic_pair(*c["hw"], seed=c["pair_seed"])
+        p = c["params"]
+        P.NORM_MODE = (p["if_norm_before_cost_volume"], p["norm_moments_across_channels"], p["norm_moments_across_images"])
+        try:
+            with torch.no_grad():
+                f, b, _ = P.forward_2_frame(im1, im2, sd, use_sgu=p["if_sgu_upsample"])
+        finally:
+            P.NORM_MODE = (True, False, False)
+        assert torch.equal(f, c["flow_f_out"]) and torch.equal(b, c["flow_b_out"]), c["name"]
+    for c in g["ops"]:
+        P.NORM_MODE = (True, c["across_channels"], c["across_images"])
+        try:
+            na, nb = P.normalize_pair(c["fa"], c["fb"])
+        finally:
+            P.NORM_MODE = (True, False, False)
+        assert torch.equal(na, c["na"]) and torch.equal(nb, c["nb"])
+        assert torch.equal(P.corr_unfold(na, nb, 4), c["corr"])
+
+
+def test_kitti_size_golden_is_self_consistent(golden):
+    """the 375x1242 pin with the shipped weights: fixture integrity (the full-size forward itself is re-run against the
+    live reference by oracle/make_golden_kitti.py, which asserts port == reference bit for bit before it writes)."""
+    import os
+    GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sd = torch.load(os.path.join(GOLDEN, "upflow_kitti2015.pth"), weights_only=True)
+    shapes = P.reference_param_shapes()
+    assert set(sd) == set(shapes) and all(tuple(sd[k].shape) == shapes[k] for k in sd)
+    assert sum(v.numel() for v in sd.values()) == 3494549
+    for c in golden("kitti_e2e"):
+        assert c["flow_f_reference"].shape == (1, 2, c["H"], c["W"]) == c["flow_f_robust"].shape
+        # the checkpointed network recovers the synthetic (-3, +2) motion
+        assert abs(c["mean_flow"][0] + 3) < 0.1 and abs(c["mean_flow"][1] - 2) < 0.1
+        # what separates the two masks is the reference's own noise floor, not arithmetic
+        assert c["noise_floor_robust_px"] < 1e-5 < c["noise_floor_px"] < 0.1
+        assert O.epe(c["flow_f_reference"], c["flow_f_robust"]) < 0.1
+    # a reduced-size forward of the port with these weights reproduces the motion too (seconds on one thread)
+    im1, im2 = O.synthetic_pair(96, 160)
+    with torch.no_grad():
+        f = P.forward_2_frame(im1, im2, sd)[0]
+    assert abs(f[:, 0].mean().item() + 3) < 0.3 and abs(f[:, 1].mean().item() - 2) < 0.3
+
+
+def test_training_port_matches_the_reference_step(golden):
+    """oracle/ref_port_train.py (the anchor bench.py times as the reference's GPU training path) against the loss terms
+    and gradients of the reference's OWN training step (tests/golden/train_step.pt, oracle/make_golden_train.py)."""
+    from oracle import ref_port_train as PT
+    g = golden("train_step")
+    sd = {k: v.clone().requires_grad_() for k, v in P.det_state_dict(g["wseed"]).items()}
+    im1, im2 = O.synthetic_pair(*g["hw"], seed=g["pair_seed"], batch=g["batch"])
+    c = g["conf"]
+    out = PT.training_loss(im1, im2, sd, smooth1_weight=c["smooth_order_1_weight"], smooth2_weight=c["smooth_order_2_weight"],
+                           photo_use_occ=c["photo_loss_use_occ"], msd_weight=c["multi_scale_distillation_weight"],
+                           msd_occ=c["multi_scale_distillation_occ"])
+    for k in ("photo_loss", "smooth_loss", "msd_loss", "loss"):
+        assert abs(out[k].item() - g[k]) <= 1e-6 * max(1.0, abs(g[k])), (k, out[k].item(), g[k])
+    out["loss"].backward()
+    for n, ref in g["grads"].items():
+        assert torch.allclose(sd[n].grad, ref, rtol=1e-4, atol=1e-7), n
+    for n, ref in g["grad_norm"].items():
+        assert abs(sd[n].grad.norm().item() - ref) <= 1e-4 * max(ref, 1e-6), n

@@ -1,5 +1,5 @@
 """Validate conv_halo.cu against the per-tap tensor-core kernel (conv_tc.cu) for both descriptor base-offset
-conventions, and time both.  python tools/test_halo.py"""
+conventions, and time both.  python tools/bench_halo.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -1,6 +1,6 @@
 """Validate conv_win.cu (linear-window tensor-core conv) against the per-tap kernel (conv_tc.cu) and the shared-halo
 kernel (conv_halo.cu) on the same inputs, time the three, and print CTA 0's pipeline wait counters.
-    python tools/test_win.py"""
+    python tools/bench_win.py"""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -20,17 +20,18 @@ SIGNATURES = {
     "upf_last_error": (_c.c_char_p, []),
     "upf_launch_count": (_LL, []),
     "upf_last_kernel": (_c.c_char_p, []),
-    "upf_corr_lrelu_fwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _F, _P]),
+    "upf_corr_lrelu_fwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _F, _I, _P]),
     "upf_corr_lrelu_bwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
-    "upf_warp_fwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P]),
+    "upf_warp_fwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _I, _P]),
     "upf_warp_bwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "upf_occ_check": (_I, [_P, _I, _P, _I, _I, _I, _I, _F, _F, _I, _I, _P]),
     "upf_featnorm_stats": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "upf_featnorm_apply": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "upf_featnorm_combine": (_I, [_P, _P, _I, _P, _P, _I, _I, _LL, _I, _I, _P]),
     "upf_resize_bilinear": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _c.POINTER(_F), _P]),
-    "upf_sgu_blend": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "upf_sgu_blend": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     "upf_conv2d_fwd": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P]),
-    "upf_conv3x3_tap_combine": (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "upf_conv3x3_tap_combine": (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P]),
     "upf_conv_tc_packed_elems": (_LL, [_I, _I, _I]),
     "upf_conv_tc_pack_weights": (_I, [_P, _P, _I, _I, _I, _P]),
     "upf_debug_conv_halo": (_I, [_I, _I]),
@@ -65,11 +66,14 @@ SIGNATURES = {
     "upf_boundary_warp_bwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _P]),
     "upf_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "upf_nhwc_to_nchw": (_I, [_P, _I, _P, _I, _I, _I, _I, _P]),
-    "upf_copy_channels": (_I, [_P, _I, _P, _I, _LL, _I, _P]),
+    "upf_copy_channels": (_I, [_P, _I, _P, _I, _LL, _I, _I, _P]),
 }
 
 CONV_FP32 = 0
 CONV_TF32 = 1
+CONV_ROUND_OUT = 0x100       # OR-ed into the precision: store the output rounded to the nearest TF32 value
+FLAG_ROUND_TF32 = 1
+ABI_VERSION = 2
 PW_LRELU_BWD, PW_SIGMOID, PW_SIGMOID_BWD = 0, 1, 2
 LOSS_KINDS = {"abs_robust": 0, "charbonnier": 1, "L1": 2}
 
@@ -95,7 +99,7 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the header and the .so disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.upf_abi_version() != 1:
+    if lib.upf_abi_version() != ABI_VERSION:
         raise UpflowLibraryError("ABI version mismatch")
     _lib = lib
     return lib

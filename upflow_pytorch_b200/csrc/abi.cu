@@ -22,10 +22,10 @@ const char* last_kernel() { return g_last_kernel; }
 
 int conv2d_fwd_simt(const float* x, int ldx, const float* w, const float* bias, float* out, int ldo,
                     const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
-                    float slope, cudaStream_t st);
+                    float slope, int flags, cudaStream_t st);
 int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
                   const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
-                  float slope, cudaStream_t st);
+                  float slope, int flags, cudaStream_t st);
 
 }  // namespace upf
 
@@ -43,12 +43,14 @@ extern "C" int upf_conv2d_fwd(const float* x, int ldx, const float* w, const flo
   UPF_REQUIRE(ksize == 1 || ksize == 3, "conv: kernel size %d not in {1,3}", ksize);
   UPF_REQUIRE(stride >= 1 && dilation >= 1, "conv: bad stride/dilation");
   UPF_REQUIRE(ldx >= Cin && ldo >= Cout && (residual == nullptr || ldr >= Cout), "conv: pitch smaller than channels");
+  const int flags = (precision & UPF_CONV_ROUND_OUT) ? UPF_FLAG_ROUND_TF32 : 0;
+  precision &= ~UPF_CONV_ROUND_OUT;
   if (precision == UPF_CONV_FP32)
     return conv2d_fwd_simt(x, ldx, w, bias, out, ldo, residual, ldr, N, H, W, Cin, Cout, ksize, stride, dilation,
-                           slope, (cudaStream_t)stream);
+                           slope, flags, (cudaStream_t)stream);
   if (precision == UPF_CONV_TF32) {
     return conv2d_fwd_tc(x, ldx, w, bias, out, ldo, residual, ldr, N, H, W, Cin, Cout, ksize, stride, dilation, slope,
-                         (cudaStream_t)stream);
+                         flags, (cudaStream_t)stream);
   }
   set_error("conv: unknown precision %d", precision);
   return UPF_EINVAL;

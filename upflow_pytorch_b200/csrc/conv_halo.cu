@@ -2,7 +2,7 @@
 // activation tile loaded ONCE per 32-channel block and shared by the nine taps,
 // and with the GEMM TRANSPOSED so that the pixels are the wide N dimension.
 //
-// Two measured facts shape this kernel (B200, tools/test_halo.py):
+// Two measured facts shape this kernel (B200, tools/bench_halo.py):
 //  (1) conv_tc.cu issues one TMA box per (tap, channel block): every activation
 //      byte travels L2 -> shared memory nine times;
 //  (2) tcgen05.mma kind::tf32 M=128 K=8 costs 46 / 49 / 65 / 129 cycles at
@@ -52,6 +52,7 @@ struct HaloParams {
   int bo_mode;                // 1: descriptor base_offset = (start >> 7) & 7
   long long* probe;           // debug: per-role wait/issue cycle counters of CTA 0 (nullptr = off)
   float slope;
+  int flags;
 };
 
 __global__ void __launch_bounds__(HC_THREADS)
@@ -235,6 +236,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           for (int k = 0; k < 4; ++k)
             if (c0 + k < p.Cout) f[k] += __ldg(p.res + pix[j] * p.ldr + c0 + k);
         }
+        if (p.flags & UPF_FLAG_ROUND_TF32) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) f[k] = round_tf32(f[k]);
+        }
         float* o = p.out + pix[j] * p.ldo + c0;
         if (vec_out && c0 + 4 <= p.Cout) {
           *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
@@ -266,7 +271,7 @@ long long* g_halo_probe = nullptr;
 // returns 1 when the launch was taken, 0 when the shape is not eligible (caller falls through to conv_tc), <0 / cudaError on failure
 int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
                     const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
-                    float slope, cudaStream_t st, int* taken) {
+                    float slope, int flags, cudaStream_t st, int* taken) {
   *taken = 0;
   if (!g_halo_enabled || ks != 3 || stride != 1 || !(dil == 1 || dil == 2 || dil == 4) || Cout > 128) return 0;
   const int tiles_x = (W + 7) / 8;
@@ -276,7 +281,7 @@ int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float*
   const int tiles_y = (H + 16 * MT - 1) / (16 * MT);
   const long long tiles = (long long)tiles_x * tiles_y * N;
   if (tiles < 96) return 0;                      // coarse levels: the cluster split-K kernel is the better fit
-  // measured (tools/test_halo.py, 1/4-res KITTI): the shared halo wins once the K loop is long (576->128: 152 vs
+  // measured (tools/bench_halo.py, 1/4-res KITTI): the shared halo wins once the K loop is long (576->128: 152 vs
   // 193 us, 544->32: 138 vs 160) and loses on short-K / high-resolution layers (32->32 at 188x621: 76 vs 61 us)
   if (Cin < g_halo_min_cin) return 0;
   const int BN = (Cout + 15) & ~15;
@@ -315,6 +320,7 @@ int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float*
   p.a_bytes = rows * HC_ROW_BYTES;
   p.b_stage_bytes = 128 * 128;                 // the MMA reads M = 128 weight rows; rows past cout_pad16 are stale, never stored
   p.slope = slope;
+  p.flags = flags;
   p.bo_mode = g_halo_bo_mode;
   p.probe = g_halo_probe;
   p.tmem_cols = 128 * MT;                      // lanes = channels, columns = pixels
@@ -329,11 +335,11 @@ int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float*
   if ((long long)na * p.a_bytes + (long long)nb * p.b_stage_bytes < 128ll * MT * HC_PITCH * 4 + 512) return 0;   // epilogue staging tile + bias
   p.ra = ra; p.nba = rows / ra; p.b_rows = b_rows; p.nbb = BN / b_rows;
   const size_t smem = (size_t)na * p.a_bytes + (size_t)nb * p.b_stage_bytes + (2 * na + 2 * nb + 2) * 8 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need()) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("conv_halo smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_set = true;
+    attr_set.mark();
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)tiles);

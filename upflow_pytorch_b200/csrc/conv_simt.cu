@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(CS_NT)
 conv_simt_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ bias,
                  float* __restrict__ out, int ldo, const float* __restrict__ res, int ldr,
                  int N, int H, int W, int Ho, int Wo, int Cin, int Cout, int cout_pad,
-                 int ks, int stride, int dil, float slope, int vec_in) {
+                 int ks, int stride, int dil, float slope, int vec_in, int flags) {
   pdl_prologue();
   static_assert((BM / TM) * (BN / TN) == CS_NT, "thread grid");
   constexpr int A_PER = BM * CS_BK / 4 / CS_NT;      // float4 loads of A per thread per stage
@@ -140,7 +140,7 @@ conv_simt_kernel(const float* __restrict__ x, int ldx, const float* __restrict__
       if (co < Cout) {
         float v = lrelu(acc[i][j] + __ldg(bias + co), slope);
         if (r) v += __ldg(r + co);
-        o[co] = v;
+        o[co] = maybe_round(v, flags);
       }
     }
   }
@@ -149,11 +149,11 @@ conv_simt_kernel(const float* __restrict__ x, int ldx, const float* __restrict__
 template <int BM, int BN, int TM, int TN>
 static void launch_simt(const float* x, int ldx, const float* w, const float* bias, float* out, int ldo,
                         const float* res, int ldr, int N, int H, int W, int Ho, int Wo, int Cin, int Cout,
-                        int cout_pad, int ks, int stride, int dil, float slope, int vec_in, cudaStream_t st) {
+                        int cout_pad, int ks, int stride, int dil, float slope, int vec_in, int flags, cudaStream_t st) {
   const long long M = (long long)N * Ho * Wo;
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((cout_pad + BN - 1) / BN));
   UPF_LAUNCH((conv_simt_kernel<BM, BN, TM, TN>), grid, CS_NT, 0, st, x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cin,
-                                                          Cout, cout_pad, ks, stride, dil, slope, vec_in);
+                                                          Cout, cout_pad, ks, stride, dil, slope, vec_in, flags);
 }
 
 
@@ -170,7 +170,7 @@ template <int CIN, int STRIDE>
 __global__ void __launch_bounds__(256)
 conv_c3_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ bias,
                float* __restrict__ out, int ldo, const float* __restrict__ res, int ldr,
-               int N, int H, int W, int Ho, int Wo, int Cout, int cout_pad, float slope) {
+               int N, int H, int W, int Ho, int Wo, int Cout, int cout_pad, float slope, int flags) {
   pdl_prologue();
   extern __shared__ float s_w[];                         // [9*CIN][cout_pad] then bias[cout_pad]
   for (int i = threadIdx.x; i < 9 * CIN * cout_pad; i += blockDim.x) s_w[i] = __ldg(w + i);
@@ -237,6 +237,10 @@ conv_c3_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w
         for (int k = 0; k < 4; ++k)
           if (c0 + k < Cout) f[k] += __ldg(res + (size_t)pix * ldr + c0 + k);
       }
+      if (flags & UPF_FLAG_ROUND_TF32) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[k] = round_tf32(f[k]);
+      }
       float* o = out + (size_t)pix * ldo + c0;
       if (vec_out && c0 + 4 <= Cout) {
         *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
@@ -251,7 +255,7 @@ conv_c3_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w
 
 template <int CIN>
 static int launch_c3(const float* x, int ldx, const float* w, const float* bias, float* out, int ldo, const float* res, int ldr,
-                     int N, int H, int W, int Ho, int Wo, int Cout, int cout_pad, int stride, float slope, cudaStream_t st) {
+                     int N, int H, int W, int Ho, int Wo, int Cout, int cout_pad, int stride, float slope, int flags, cudaStream_t st) {
   const int gpb = 256 / (cout_pad >> 2);
   const size_t smem = (size_t)(9 * CIN + 1) * cout_pad * sizeof(float);
   const int ngx = (Wo + C3_PX - 1) / C3_PX;
@@ -260,15 +264,15 @@ static int launch_c3(const float* x, int ldx, const float* w, const float* bias,
   const long long cap = (long long)UPF_NUM_SMS * 8;
   const unsigned grid = (unsigned)(items < cap ? items : cap);
   if (stride == 1)
-    UPF_LAUNCH((conv_c3_kernel<CIN, 1>), grid, 256, smem, st, x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, slope);
+    UPF_LAUNCH((conv_c3_kernel<CIN, 1>), grid, 256, smem, st, x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, slope, flags);
   else
-    UPF_LAUNCH((conv_c3_kernel<CIN, 2>), grid, 256, smem, st, x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, slope);
+    UPF_LAUNCH((conv_c3_kernel<CIN, 2>), grid, 256, smem, st, x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, slope, flags);
   return check_launch("conv_c3");
 }
 
 int conv2d_fwd_simt(const float* x, int ldx, const float* w, const float* bias, float* out, int ldo,
                     const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
-                    float slope, cudaStream_t st) {
+                    float slope, int flags, cudaStream_t st) {
   const int pad = ((ks - 1) * dil) / 2;
   const int Ho = (H + 2 * pad - dil * (ks - 1) - 1) / stride + 1;
   const int Wo = (W + 2 * pad - dil * (ks - 1) - 1) / stride + 1;
@@ -278,22 +282,22 @@ int conv2d_fwd_simt(const float* x, int ldx, const float* w, const float* bias, 
   const int vec_in = (ldx % 4 == 0) && aligned16(x);
   if (ks == 3 && dil == 1 && (stride == 1 || stride == 2) && Cin <= 4 && (cout_pad == 4 || cout_pad == 8 || cout_pad == 16 || cout_pad == 32)) {
     switch (Cin) {
-      case 1: return launch_c3<1>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, stride, slope, st);
-      case 2: return launch_c3<2>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, stride, slope, st);
-      case 3: return launch_c3<3>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, stride, slope, st);
-      default: return launch_c3<4>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, stride, slope, st);
+      case 1: return launch_c3<1>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, stride, slope, flags, st);
+      case 2: return launch_c3<2>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, stride, slope, flags, st);
+      case 3: return launch_c3<3>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, stride, slope, flags, st);
+      default: return launch_c3<4>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cout, cout_pad, stride, slope, flags, st);
     }
   }
   if (cout_pad > 64)
-    launch_simt<128, 128, 8, 8>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cin, Cout, cout_pad, ks, stride, dil, slope, vec_in, st);
+    launch_simt<128, 128, 8, 8>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cin, Cout, cout_pad, ks, stride, dil, slope, vec_in, flags, st);
   else if (cout_pad > 32)
-    launch_simt<128, 64, 8, 4>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cin, Cout, cout_pad, ks, stride, dil, slope, vec_in, st);
+    launch_simt<128, 64, 8, 4>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cin, Cout, cout_pad, ks, stride, dil, slope, vec_in, flags, st);
   else if (cout_pad > 16)
-    launch_simt<128, 32, 4, 4>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cin, Cout, cout_pad, ks, stride, dil, slope, vec_in, st);
+    launch_simt<128, 32, 4, 4>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cin, Cout, cout_pad, ks, stride, dil, slope, vec_in, flags, st);
   else if (cout_pad > 4)
-    launch_simt<256, 16, 4, 4>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cin, Cout, cout_pad, ks, stride, dil, slope, vec_in, st);
+    launch_simt<256, 16, 4, 4>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cin, Cout, cout_pad, ks, stride, dil, slope, vec_in, flags, st);
   else
-    launch_simt<256, 4, 1, 4>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cin, Cout, cout_pad, ks, stride, dil, slope, vec_in, st);
+    launch_simt<256, 4, 1, 4>(x, ldx, w, bias, out, ldo, res, ldr, N, H, W, Ho, Wo, Cin, Cout, cout_pad, ks, stride, dil, slope, vec_in, flags, st);
   return check_launch("conv_simt");
 }
 

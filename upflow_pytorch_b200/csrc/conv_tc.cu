@@ -59,6 +59,7 @@ struct TcParams {
   // one box is walked row by row (~10 ns per 128-byte row, measured), independent boxes proceed concurrently
   int bw, bh, nbx, nby, b_rows, nbb;
   float slope;
+  int flags;                   // UPF_FLAG_ROUND_TF32: store the output rounded to the nearest TF32 value
   // weight-gradient mode (backward.cu): the "images" are the taps of ONE planar operand -- image n reads the same
   // tensor with its K (channel) coordinate shifted by koffs[n]
   int wgrad;
@@ -74,7 +75,7 @@ __device__ __forceinline__ void store4(const TcParams& p, const float* s_bias, i
     if (co + j < p.Cout) {
       float a = lrelu(v[j] + s_bias[co + j - co0], p.slope);
       if (r) a += __ldg(r + co + j);
-      v[j] = a;
+      v[j] = maybe_round(a, p.flags);
     }
   if (vec_out && co + 4 <= p.Cout) {
     *reinterpret_cast<float4*>(o + co) = make_float4(v[0], v[1], v[2], v[3]);
@@ -294,7 +295,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
     const int tap = (int)(i / ((long long)cin_pad32 * cout_pad16));
     float v = 0.f;
     if (ci < Cin && co < Cout) v = w[((size_t)tap * Cin + ci) * cout_pad4 + co];
-    wp[i] = v;
+    wp[i] = round_tf32(v);      // kind::tf32 would truncate: round to nearest once, here
   }
 }
 
@@ -310,7 +311,7 @@ __global__ void repack_weights_tc_kernel(const float* __restrict__ w, float* __r
     float v = 0.f;
     if (ci < Cin && co < Cout)
       v = flip_transpose ? __ldg(w + ((size_t)ci * Cout + co) * taps + (taps - 1 - tap)) : __ldg(w + ((size_t)co * Cin + ci) * taps + tap);
-    wp[i] = v;
+    wp[i] = round_tf32(v);
   }
 }
 
@@ -370,31 +371,31 @@ static void pick_tile(int H, int W, int max_tw, int* TH, int* TW) {
 
 int g_tc_pdl = 1;         // programmatic dependent launch between consecutive conv kernels (upf_debug_conv_halo bit 3 = off)
 int g_tc_box_rows = 128;  // pixels (128-byte rows) per TMA box (128 = one box per tile).  Measured: SMALLER boxes are
-                          // slower (tools/test_halo.py: 16-row boxes cost 1.5-2x), so the tile is fetched as one box
+                          // slower (tools/bench_halo.py: 16-row boxes cost 1.5-2x), so the tile is fetched as one box
 
 int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
                     const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
-                    float slope, cudaStream_t st, int* taken);
+                    float slope, int flags, cudaStream_t st, int* taken);
 
 int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
                    const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
-                   float slope, cudaStream_t st, int* taken);
+                   float slope, int flags, cudaStream_t st, int* taken);
 
-static const int* g_tc_koffs = nullptr;      // set by conv_tc_wgrad_gemm around its call (host, single-threaded use)
-static const int* g_tc_wsel = nullptr;
+static thread_local const int* g_tc_koffs = nullptr;      // set by conv_tc_wgrad_gemm around its call (per calling thread)
+static thread_local const int* g_tc_wsel = nullptr;
 
 int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
                   const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
-                  float slope, cudaStream_t st) {
+                  float slope, int flags, cudaStream_t st) {
   const int* koffs = g_tc_koffs;
   UPF_REQUIRE((ldx % 4) == 0 && aligned16(x) && aligned16(w_packed), "conv_tc: input pitch/pointer must be 16-byte aligned");
   UPF_REQUIRE(stride == 1 || stride == 2, "conv_tc: stride %d not in {1,2}", stride);
   if (!koffs) {
     // fine pyramid levels, 3x3 / dilation <= 4: the halo kernel loads the activation tile once for all nine taps
     int taken = 0;
-    const int e0 = conv2d_fwd_win(x, ldx, w_packed, bias, out, ldo, res, ldr, N, H, W, Cin, Cout, ks, stride, dil, slope, st, &taken);
+    const int e0 = conv2d_fwd_win(x, ldx, w_packed, bias, out, ldo, res, ldr, N, H, W, Cin, Cout, ks, stride, dil, slope, flags, st, &taken);
     if (e0 != 0 || taken) return e0;
-    const int e = conv2d_fwd_halo(x, ldx, w_packed, bias, out, ldo, res, ldr, N, H, W, Cin, Cout, ks, stride, dil, slope, st, &taken);
+    const int e = conv2d_fwd_halo(x, ldx, w_packed, bias, out, ldo, res, ldr, N, H, W, Cin, Cout, ks, stride, dil, slope, flags, st, &taken);
     if (e != 0 || taken) return e;
   }
   const int pad = ((ks - 1) * dil) / 2;
@@ -445,6 +446,7 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   p.ks = ks; p.dil = dil; p.stride = stride; p.kblocks = kblocks;
   p.bw = bw; p.bh = bh; p.nbx = TW / bw; p.nby = TH / bh; p.b_rows = b_rows; p.nbb = BN / b_rows;
   p.slope = slope;
+  p.flags = flags;
   p.wgrad = koffs ? 1 : 0;
   for (int i = 0; i < 9; ++i) { p.koffs[i] = (koffs && i < N) ? koffs[i] : 0; p.wsel[i] = (koffs && g_tc_wsel && i < N) ? g_tc_wsel[i] : 0; }
   p.tmem_cols = BN <= 16 ? 32 : (BN <= 32 ? 64 : (BN <= 64 ? 128 : 256));   // two accumulators (one per MMA issuer)
@@ -471,11 +473,11 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   p.nstage = nstage;
   p.splits = splits; p.ips = ips;
   const size_t smem = (size_t)nstage * stage_bytes + (2 * nstage + 2) * 8 + 16 + BN * 4 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need()) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("conv_tc smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_set = true;
+    attr_set.mark();
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)tiles, (unsigned)ntiles_n, (unsigned)splits);
@@ -501,7 +503,7 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
 int conv_tc_wgrad_gemm(const float* xt, int ldk, const float* gt_packed, const float* zero_bias, float* gw, int taps,
                        int Cin, int Cout, int K, const int* koffs, const int* wsel, cudaStream_t st) {
   g_tc_koffs = koffs; g_tc_wsel = wsel;
-  const int e = conv2d_fwd_tc(xt, ldk, gt_packed, zero_bias, gw, Cout, nullptr, 0, taps, 1, Cin, K, Cout, 1, 1, 1, 1.0f, st);
+  const int e = conv2d_fwd_tc(xt, ldk, gt_packed, zero_bias, gw, Cout, nullptr, 0, taps, 1, Cin, K, Cout, 1, 1, 1, 1.0f, 0, st);
   g_tc_koffs = nullptr; g_tc_wsel = nullptr;
   return e;
 }

@@ -2,7 +2,7 @@
 // activation halo loaded ONCE per 32-channel block, the nine taps read it as LINEARLY SHIFTED WINDOWS, one weight
 // fetch shared by up to four accumulators, and TWO MMA-issuing warps.
 //
-// Measured facts that shape it (B200; tools/microbench/tc_probe.cu "conv-like issue pattern", tools/test_win.py):
+// Measured facts that shape it (B200; tools/microbench/tc_probe.cu "conv-like issue pattern", tools/bench_win.py):
 //  (1) a single issuing thread cannot keep the tensor pipe busy with this loop shape: per tap it issues 4*m MMAs, one
 //      or two tcgen05.commit and one mbarrier poll, and the pipe idles for ~280 cycles around every commit
 //      (M=128, N=128: 4 MMAs + commit + poll = 634 cycles against 259 of MMA work; N=256: 635 against 515).
@@ -51,6 +51,7 @@ struct WinParams {
   int tap_split;              // 1: issuers alternate taps (two accumulator sets), 0: issuers alternate units
   long long* probe;
   float slope;
+  int flags;
 };
 
 template <bool PROBE>
@@ -227,6 +228,10 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             for (int k = 0; k < 4; ++k)
               if (c + k < p.Cout) f[k] += __ldg(rrow + c + k);
           }
+          if (p.flags & UPF_FLAG_ROUND_TF32) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) f[k] = round_tf32(f[k]);
+          }
           if (vec_out && c + 4 <= p.Cout) {
             *reinterpret_cast<float4*>(orow + c) = make_float4(f[0], f[1], f[2], f[3]);
           } else {
@@ -251,14 +256,14 @@ extern int g_tc_pdl;
 extern long long* g_halo_probe;
 static int g_win_enabled = 1;
 static int g_win_min_cin = 0;
-static int g_win_max_cout = 64;   // measured (tools/test_win.py, 1/4- and 1/8-res KITTI): faster than conv_halo.cu for Cout <= 64
+static int g_win_max_cout = 64;   // measured (tools/bench_win.py, 1/4- and 1/8-res KITTI): faster than conv_halo.cu for Cout <= 64
                                   // (544->32: 97 vs 139 us, 480->64: 108 vs 130, 576->2: 91 vs 131), slower for 96..128
 static int g_win_force_m = 0;
 
 // returns with *taken = 1 when the launch was made, 0 when the shape is not eligible (caller falls through)
 int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
                    const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
-                   float slope, cudaStream_t st, int* taken) {
+                   float slope, int flags, cudaStream_t st, int* taken) {
   *taken = 0;
   if (!g_win_enabled || ks != 3 || stride != 1 || !(dil == 1 || dil == 2 || dil == 4) || Cout > 128) return 0;
   if (Cin < g_win_min_cin || Cout > g_win_max_cout) return 0;
@@ -321,6 +326,7 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
   p.a_bytes = rows * CW_ROW_BYTES;
   p.b_stage_bytes = b_stage_bytes;
   p.slope = slope;
+  p.flags = flags;
   p.probe = g_halo_probe;
   int cols = 32;
   while (cols < (tap_split ? 2 : 1) * m * BN) cols <<= 1;
@@ -336,12 +342,12 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
   p.na = na; p.nb = nb;
   // the windows of the last unit read up to 2*dil positions past their stage: the weight ring follows the halo ring
   const size_t smem = (size_t)na * p.a_bytes + (size_t)nb * b_stage_bytes + (2 * na + 2 * nb + 2) * 8 + 16 + 128 * 4 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need()) {
     cudaError_t e = cudaFuncSetAttribute(conv_win_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_win_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("conv_win smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_set = true;
+    attr_set.mark();
   }
   if (smem > 227 * 1024) return 0;
   cudaLaunchConfig_t cfg = {};

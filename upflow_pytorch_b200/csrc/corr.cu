@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(CorrCfg<D>::NT) __maxnreg__(CorrCfg<D>::MIN_CT
 corr_fwd_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__ f2, int ld2,
                 float* __restrict__ out, int ldo, int H, int W, int C,
                 const double* __restrict__ stats1, const double* __restrict__ stats2,
-                float slope, int tiles_x, int tiles_y, int n2_shift, int N) {
+                float slope, int flags, int tiles_x, int tiles_y, int n2_shift, int N) {
   pdl_prologue();
   using K = CorrCfg<D>;
   extern __shared__ __align__(128) float smem[];
@@ -201,7 +201,7 @@ corr_fwd_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__
       const float s = acc[p][q];
       float v = __fmul_rn(s, inv);
       v = __fmaf_rn(__fmaf_rn(-v, fC, s), inv, v);
-      s_out[(p * CORR_TX + lane) * K::NOUT + q * K::WIN + dxi] = lrelu(v, slope);
+      s_out[(p * CORR_TX + lane) * K::NOUT + q * K::WIN + dxi] = maybe_round(lrelu(v, slope), flags);
     }
   __syncthreads();
 
@@ -227,7 +227,7 @@ corr_fwd_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__
 template <int D>
 static int launch_corr_fwd(const float* f1, int ld1, const float* f2, int ld2, float* out, int ldo,
                            int N, int H, int W, int C, const double* s1, const double* s2, int shift,
-                           float slope, cudaStream_t st) {
+                           float slope, int flags, cudaStream_t st) {
   using K = CorrCfg<D>;
   const int tiles_x = (W + CORR_TX - 1) / CORR_TX, tiles_y = (H + CORR_TY - 1) / CORR_TY;
   const long long tiles = (long long)tiles_x * tiles_y * N;
@@ -235,8 +235,8 @@ static int launch_corr_fwd(const float* f1, int ld1, const float* f2, int ld2, f
   const bool vec = (C % 4 == 0) && (ld1 % 4 == 0) && (ld2 % 4 == 0) && aligned16(f1) && aligned16(f2);
   // opt in to >48 KB dynamic shared memory once per instantiation (per device would need a table: one
   // process drives one GPU here)
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.need()) {
     cudaError_t e = cudaFuncSetAttribute(corr_fwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(corr_fwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
@@ -244,14 +244,14 @@ static int launch_corr_fwd(const float* f1, int ld1, const float* f2, int ld2, f
       set_error("corr smem attr: %s", cudaGetErrorString(e));
       return (int)e;
     }
-    attr_done = true;
+    attr_done.mark();
   }
   if (vec) {
     UPF_LAUNCH((corr_fwd_kernel<D, true>), (unsigned)tiles, K::NT, K::SMEM_BYTES, st, f1, ld1, f2, ld2, out, ldo, H, W, C, s1, s2,
-                                                                          slope, tiles_x, tiles_y, shift, N);
+                                                                          slope, flags, tiles_x, tiles_y, shift, N);
   } else {
     UPF_LAUNCH((corr_fwd_kernel<D, false>), (unsigned)tiles, K::NT, K::SMEM_BYTES, st, f1, ld1, f2, ld2, out, ldo, H, W, C, s1,
-                                                                           s2, slope, tiles_x, tiles_y, shift, N);
+                                                                           s2, slope, flags, tiles_x, tiles_y, shift, N);
   }
   return check_launch("corr_fwd");
 }
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(704)
 corr_small_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__ f2, int ld2,
                   float* __restrict__ out, int ldo, int H, int W, int C, int D,
                   const double* __restrict__ stats1, const double* __restrict__ stats2,
-                  float slope, int n2_shift, int N) {
+                  float slope, int flags, int n2_shift, int N) {
   pdl_prologue();
   extern __shared__ __align__(16) float sm[];        // a[Cp] | mean2[Cp] | rstd2[Cp]
   const int Cp = (C + 3) & ~3;
@@ -404,19 +404,19 @@ corr_small_kernel(const float* __restrict__ f1, int ld1, const float* __restrict
     const float fC = (float)C, inv = __fdiv_rn(1.0f, fC);
     float v = __fmul_rn(acc, inv);
     v = __fmaf_rn(__fmaf_rn(-v, fC, acc), inv, v);          // correctly rounded acc / C
-    out[(size_t)pix * ldo + k] = lrelu(v, slope);
+    out[(size_t)pix * ldo + k] = maybe_round(lrelu(v, slope), flags);
   }
 }
 
 int launch_corr_pipe(const float* f1, int ld1, const float* f2, int ld2, float* out, int ldo,
                      int N, int H, int W, int C, int D, const double* s1, const double* s2, int shift,
-                     float slope, cudaStream_t st, int* taken);
+                     float slope, int flags, cudaStream_t st, int* taken);
 
 constexpr long long CORR_SMALL_MAX_PIX = 4096;   // measured: at 2x47x156 (C=64) the tiled kernel is already 2x faster
 
 static int launch_corr_small(const float* f1, int ld1, const float* f2, int ld2, float* out, int ldo,
                              int N, int H, int W, int C, int D, const double* s1, const double* s2, int shift,
-                             float slope, cudaStream_t st) {
+                             float slope, int flags, cudaStream_t st) {
   const int nout = (2 * D + 1) * (2 * D + 1);
   const int threads = ((nout * 4 + 31) / 32) * 32;          // 4 lanes per displacement
   UPF_REQUIRE(threads <= 704, "corr_small: window too large");
@@ -424,9 +424,9 @@ static int launch_corr_small(const float* f1, int ld1, const float* f2, int ld2,
   const size_t smem = (size_t)3 * ((C + 3) & ~3) * sizeof(float);
   const unsigned grid = (unsigned)((long long)N * H * W);
   if (vec)
-    UPF_LAUNCH((corr_small_kernel<true>), grid, threads, smem, st, f1, ld1, f2, ld2, out, ldo, H, W, C, D, s1, s2, slope, shift, N);
+    UPF_LAUNCH((corr_small_kernel<true>), grid, threads, smem, st, f1, ld1, f2, ld2, out, ldo, H, W, C, D, s1, s2, slope, flags, shift, N);
   else
-    UPF_LAUNCH((corr_small_kernel<false>), grid, threads, smem, st, f1, ld1, f2, ld2, out, ldo, H, W, C, D, s1, s2, slope, shift, N);
+    UPF_LAUNCH((corr_small_kernel<false>), grid, threads, smem, st, f1, ld1, f2, ld2, out, ldo, H, W, C, D, s1, s2, slope, flags, shift, N);
   return check_launch("corr_small");
 }
 
@@ -435,7 +435,7 @@ static int launch_corr_small(const float* f1, int ld1, const float* f2, int ld2,
 extern "C" int upf_corr_lrelu_fwd(const float* f1, int ld1, const float* f2, int ld2, float* out, int ldo,
                                   int N, int H, int W, int C, int max_disp,
                                   const double* stats1, const double* stats2, int f2_batch_shift,
-                                  float slope, void* stream) {
+                                  float slope, int flags, void* stream) {
   using namespace upf;
   UPF_REQUIRE(f1 && f2 && out, "corr: null tensor");
   UPF_REQUIRE(f2_batch_shift >= 0 && f2_batch_shift < N, "corr: batch shift out of range");
@@ -450,20 +450,20 @@ extern "C" int upf_corr_lrelu_fwd(const float* f1, int ld1, const float* f2, int
     // enough 32x8 tiles per image, d <= 6: persistent warp-specialised kernel (loads overlap the FMA loop), corr_pipe.cu
     // (the choice depends on the IMAGE size only, never on N: an image must give the same bits in any batch)
     int taken = 0;
-    const int e = launch_corr_pipe(f1, ld1, f2, ld2, out, ldo, N, H, W, C, max_disp, stats1, stats2, f2_batch_shift, slope,
+    const int e = launch_corr_pipe(f1, ld1, f2, ld2, out, ldo, N, H, W, C, max_disp, stats1, stats2, f2_batch_shift, slope, flags,
                                    st, &taken);
     if (e != 0 || taken) return e;
   }
   // coarse pyramid levels: too few tiles to occupy the chip (and up to 7 channel passes each)
   if ((long long)H * W <= CORR_SMALL_MAX_PIX / 2 && C <= 1024)
-    return launch_corr_small(f1, ld1, f2, ld2, out, ldo, N, H, W, C, max_disp, stats1, stats2, f2_batch_shift, slope, st);
+    return launch_corr_small(f1, ld1, f2, ld2, out, ldo, N, H, W, C, max_disp, stats1, stats2, f2_batch_shift, slope, flags, st);
   switch (max_disp) {
-    case 1: return launch_corr_fwd<1>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);
-    case 2: return launch_corr_fwd<2>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);
-    case 3: return launch_corr_fwd<3>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);
-    case 4: return launch_corr_fwd<4>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);
-    case 5: return launch_corr_fwd<5>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);
-    case 6: return launch_corr_fwd<6>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, st);
+    case 1: return launch_corr_fwd<1>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, flags, st);
+    case 2: return launch_corr_fwd<2>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, flags, st);
+    case 3: return launch_corr_fwd<3>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, flags, st);
+    case 4: return launch_corr_fwd<4>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, flags, st);
+    case 5: return launch_corr_fwd<5>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, flags, st);
+    case 6: return launch_corr_fwd<6>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, flags, st);
     default: set_error("corr: max_disp %d not in 1..6", max_disp); return UPF_ENOTSUP;
   }
 }

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(CPCfg<D>::NT, 1)
 corr_pipe_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                  float* __restrict__ out, int ldo, int H, int W, int C,
                  const double* __restrict__ stats1, const double* __restrict__ stats2,
-                 float slope, int tiles_x, int tiles_y, int n2_shift, int N, int total_tiles, int bulk_out) {
+                 float slope, int flags, int tiles_x, int tiles_y, int n2_shift, int N, int total_tiles, int bulk_out) {
   pdl_prologue();
   using K = CPCfg<D>;
   constexpr int TY = K::TY;
@@ -283,7 +283,7 @@ corr_pipe_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant
         for (int p = 0; p < TY; ++p)
 #pragma unroll
           for (int q = 0; q < K::WIN; ++q)
-            s_out[(p * CP_TX + lane) * K::NOUT + q * K::WIN + dxi] = lrelu(__fmul_rn(acc[p][q], inv), slope);
+            s_out[(p * CP_TX + lane) * K::NOUT + q * K::WIN + dxi] = maybe_round(lrelu(__fmul_rn(acc[p][q], inv), slope), flags);
       } else {
 #pragma unroll
         for (int p = 0; p < TY; ++p)
@@ -292,7 +292,7 @@ corr_pipe_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant
             const float sacc = acc[p][q];
             float v = __fmul_rn(sacc, inv);
             v = __fmaf_rn(__fmaf_rn(-v, fC, sacc), inv, v);     // correctly rounded sum / C (torch.mean)
-            s_out[(p * CP_TX + lane) * K::NOUT + q * K::WIN + dxi] = lrelu(v, slope);
+            s_out[(p * CP_TX + lane) * K::NOUT + q * K::WIN + dxi] = maybe_round(lrelu(v, slope), flags);
           }
       }
       if (bulk_out) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> bulk-copy reads
@@ -337,15 +337,15 @@ corr_pipe_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant
 template <int D>
 static int launch_corr_pipe_t(const float* f1, int ld1, const float* f2, int ld2, float* out, int ldo,
                               int N, int H, int W, int C, const double* s1, const double* s2, int shift,
-                              float slope, cudaStream_t st) {
+                              float slope, int flags, cudaStream_t st) {
   using K = CPCfg<D>;
   const int tiles_x = (W + CP_TX - 1) / CP_TX, tiles_y = (H + K::TY - 1) / K::TY;
   const long long tiles = (long long)tiles_x * tiles_y * N;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.need()) {
     cudaError_t e = cudaFuncSetAttribute(corr_pipe_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("corr_pipe smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
+    attr_done.mark();
   }
   CUtensorMap m1, m2;
   {
@@ -365,7 +365,7 @@ static int launch_corr_pipe_t(const float* f1, int ld1, const float* f2, int ld2
   // contiguous output whose tile rows are 16-byte aligned runs: shared -> global bulk copies instead of ld/st
   const int bulk_out = (ldo == K::NOUT && W % 4 == 0 && aligned16(out)) ? 1 : 0;
   const unsigned grid = (unsigned)(tiles < UPF_NUM_SMS ? tiles : UPF_NUM_SMS);
-  UPF_LAUNCH((corr_pipe_kernel<D>), grid, K::NT, K::SMEM_BYTES, st, m1, m2, out, ldo, H, W, C, s1, s2, slope, tiles_x, tiles_y, shift,
+  UPF_LAUNCH((corr_pipe_kernel<D>), grid, K::NT, K::SMEM_BYTES, st, m1, m2, out, ldo, H, W, C, s1, s2, slope, flags, tiles_x, tiles_y, shift,
                                                           N, (int)tiles, bulk_out);
   return check_launch("corr_pipe");
 }
@@ -379,7 +379,7 @@ static int g_corr_pipe_min_tiles = 25;
 // returns 1 in *taken when this kernel handled the call
 int launch_corr_pipe(const float* f1, int ld1, const float* f2, int ld2, float* out, int ldo,
                      int N, int H, int W, int C, int D, const double* s1, const double* s2, int shift,
-                     float slope, cudaStream_t st, int* taken) {
+                     float slope, int flags, cudaStream_t st, int* taken) {
   *taken = 0;
   const bool vec = (C % 4 == 0) && (ld1 % 4 == 0) && (ld2 % 4 == 0) && aligned16(f1) && aligned16(f2);
   const int ty = D <= 4 ? 8 : 4;
@@ -387,12 +387,12 @@ int launch_corr_pipe(const float* f1, int ld1, const float* f2, int ld2, float* 
   if (!g_corr_pipe_enabled || !vec || D > 6 || C > 256 || tiles_img * N >= (1ll << 30) || tiles_img < g_corr_pipe_min_tiles) return 0;
   *taken = 1;
   switch (D) {
-    case 1: return launch_corr_pipe_t<1>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, st);
-    case 2: return launch_corr_pipe_t<2>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, st);
-    case 3: return launch_corr_pipe_t<3>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, st);
-    case 4: return launch_corr_pipe_t<4>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, st);
-    case 5: return launch_corr_pipe_t<5>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, st);
-    default: return launch_corr_pipe_t<6>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, st);
+    case 1: return launch_corr_pipe_t<1>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, flags, st);
+    case 2: return launch_corr_pipe_t<2>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, flags, st);
+    case 3: return launch_corr_pipe_t<3>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, flags, st);
+    case 4: return launch_corr_pipe_t<4>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, flags, st);
+    case 5: return launch_corr_pipe_t<5>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, flags, st);
+    default: return launch_corr_pipe_t<6>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, s1, s2, shift, slope, flags, st);
   }
 }
 

@@ -52,8 +52,8 @@ __device__ __forceinline__ float lowres_tap(const float* r0, const float* r1, co
 
 __global__ void __launch_bounds__(256)
 sgu_blend_kernel(const float* __restrict__ flow_init, int ldf, const float* __restrict__ inter, int ldi, int ih, int iw,
-                 float* __restrict__ out, int ldo, int N, int H, int W, int align_corners,
-                 float sh, float sw, float rate_u, float rate_v) {
+                 float* __restrict__ out, int ldo, float* __restrict__ out2, int ld2, int N, int H, int W, int align_corners,
+                 float sh, float sw, float rate_u, float rate_v, int flags) {
   pdl_prologue();
   const long long total = (long long)N * H * W;
   const bool same = (ih == H && iw == W);
@@ -93,8 +93,13 @@ sgu_blend_kernel(const float* __restrict__ flow_init, int ldf, const float* __re
     const float u0 = __ldg(f0), v0 = __ldg(f0 + 1);
     const float om = __fsub_rn(1.0f, m);
     // warp*(1-m) + init*m, two products then one add (model/upflow.py:88)
-    out[(size_t)i * ldo + 0] = __fadd_rn(__fmul_rn(wu, om), __fmul_rn(u0, m));
-    out[(size_t)i * ldo + 1] = __fadd_rn(__fmul_rn(wv, om), __fmul_rn(v0, m));
+    const float ru = __fadd_rn(__fmul_rn(wu, om), __fmul_rn(u0, m)), rv = __fadd_rn(__fmul_rn(wv, om), __fmul_rn(v0, m));
+    out[(size_t)i * ldo + 0] = ru;
+    out[(size_t)i * ldo + 1] = rv;
+    if (out2) {                      // the tensor-core consumers' copy: 4-channel slot (u, v, 0, 0)
+      float* o2 = out2 + (size_t)i * ld2;
+      o2[0] = maybe_round(ru, flags); o2[1] = maybe_round(rv, flags); o2[2] = 0.f; o2[3] = 0.f;
+    }
   }
 }
 
@@ -139,7 +144,7 @@ nhwc_to_nchw_kernel(const float* __restrict__ in, int ldi, float* __restrict__ o
 
 __global__ void __launch_bounds__(256)
 copy_channels_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int ldo, long long npix, int C,
-                     int vec) {
+                     int vec, int flags) {
   pdl_prologue();
   if (vec) {
     const int cg = C >> 2;
@@ -147,14 +152,16 @@ copy_channels_kernel(const float* __restrict__ in, int ldi, float* __restrict__ 
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
       const long long p = i / cg;
       const int c = (int)(i - p * cg) * 4;
-      *reinterpret_cast<float4*>(out + (size_t)p * ldo + c) = ldg4(in + (size_t)p * ldi + c);
+      float4 v = in ? ldg4(in + (size_t)p * ldi + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (flags & UPF_FLAG_ROUND_TF32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+      *reinterpret_cast<float4*>(out + (size_t)p * ldo + c) = v;
     }
   } else {
     const long long total = npix * C;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
       const long long p = i / C;
       const int c = (int)(i - p * C);
-      out[(size_t)p * ldo + c] = __ldg(in + (size_t)p * ldi + c);
+      out[(size_t)p * ldo + c] = in ? maybe_round(__ldg(in + (size_t)p * ldi + c), flags) : 0.f;
     }
   }
 }
@@ -176,7 +183,7 @@ static unsigned grid_for(long long total, int per_block = 256) {
 // with taps whose source pixel lies outside the image contributing nothing (= the conv's zero padding).
 __global__ void __launch_bounds__(256)
 tap_combine_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ bias, float* __restrict__ out, int ldo,
-                   const float* __restrict__ res, int ldr, int N, int H, int W, int Cout, int dil, float slope) {
+                   const float* __restrict__ res, int ldr, int N, int H, int W, int Cout, int dil, float slope, int flags) {
   pdl_prologue();
   const long long total = (long long)N * H * W * Cout;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -200,7 +207,7 @@ tap_combine_kernel(const float* __restrict__ y, int ldy, const float* __restrict
     }
     float v = lrelu(acc + __ldg(bias + co), slope);
     if (res) v += __ldg(res + (size_t)pix * ldr + co);
-    out[(size_t)pix * ldo + co] = v;
+    out[(size_t)pix * ldo + co] = maybe_round(v, flags);
   }
 }
 
@@ -222,16 +229,18 @@ extern "C" int upf_resize_bilinear(const float* in, int ldi, int h, int w, float
 }
 
 extern "C" int upf_sgu_blend(const float* flow_init, int ldf, const float* inter, int ldi, int ih, int iw,
-                             float* out, int ldo, int N, int H, int W, int align_corners, void* stream) {
+                             float* out, int ldo, float* out_tf32, int ldt, int N, int H, int W, int align_corners, int flags,
+                             void* stream) {
   using namespace upf;
   UPF_REQUIRE(flow_init && inter && out, "sgu_blend: null tensor");
   UPF_REQUIRE(N > 0 && H > 0 && W > 0 && ih > 0 && iw > 0 && ldf >= 2 && ldi >= 3 && ldo >= 2, "sgu_blend: bad shape");
   UPF_REQUIRE(out != flow_init, "sgu_blend: cannot run in place (neighbouring pixels are gathered)");
+  UPF_REQUIRE(out_tf32 == nullptr || ldt >= 4, "sgu_blend: the second output is a 4-channel slot");
   // rate = ratio of SIZES as python floats (model/pwc_modules.py:84-85), rounded to fp32 at the multiply
   const float rate_u = (float)((double)W / (double)iw), rate_v = (float)((double)H / (double)ih);
   UPF_LAUNCH((sgu_blend_kernel), grid_for((long long)N * H * W), 256, 0, (cudaStream_t)stream, 
-      flow_init, ldf, inter, ldi, ih, iw, out, ldo, N, H, W, align_corners, host_ac_scale(ih, H), host_ac_scale(iw, W),
-      rate_u, rate_v);
+      flow_init, ldf, inter, ldi, ih, iw, out, ldo, out_tf32, ldt, N, H, W, align_corners, host_ac_scale(ih, H), host_ac_scale(iw, W),
+      rate_u, rate_v, flags);
   return check_launch("sgu_blend");
 }
 
@@ -255,21 +264,21 @@ extern "C" int upf_nhwc_to_nchw(const float* in, int ldi, float* out, int N, int
   return check_launch("nhwc_to_nchw");
 }
 
-extern "C" int upf_copy_channels(const float* in, int ldi, float* out, int ldo, long long npix, int C, void* stream) {
+extern "C" int upf_copy_channels(const float* in, int ldi, float* out, int ldo, long long npix, int C, int flags, void* stream) {
   using namespace upf;
-  UPF_REQUIRE(in && out && npix > 0 && C > 0 && ldi >= C && ldo >= C, "copy_channels: bad argument");
-  const int vec = (C % 4 == 0) && (ldi % 4 == 0) && (ldo % 4 == 0) && aligned16(in) && aligned16(out);
-  UPF_LAUNCH((copy_channels_kernel), grid_for(npix * (vec ? C / 4 : C)), 256, 0, (cudaStream_t)stream, in, ldi, out, ldo, npix, C, vec);
+  UPF_REQUIRE(out && npix > 0 && C > 0 && (!in || ldi >= C) && ldo >= C, "copy_channels: bad argument");
+  const int vec = (C % 4 == 0) && (!in || ((ldi % 4 == 0) && aligned16(in))) && (ldo % 4 == 0) && aligned16(out);
+  UPF_LAUNCH((copy_channels_kernel), grid_for(npix * (vec ? C / 4 : C)), 256, 0, (cudaStream_t)stream, in, ldi, out, ldo, npix, C, vec, flags);
   return check_launch("copy_channels");
 }
 
 extern "C" int upf_conv3x3_tap_combine(const float* y, int ldy, const float* bias, float* out, int ldo, const float* residual,
-                                       int ldr, int N, int H, int W, int Cout, int dilation, float slope, void* stream) {
+                                       int ldr, int N, int H, int W, int Cout, int dilation, float slope, int flags, void* stream) {
   using namespace upf;
   UPF_REQUIRE(y && bias && out, "tap_combine: null tensor");
   UPF_REQUIRE(N > 0 && H > 0 && W > 0 && Cout > 0 && dilation >= 1 && ldy >= 9 * Cout && ldo >= Cout && (!residual || ldr >= Cout),
               "tap_combine: bad shape");
   UPF_LAUNCH((tap_combine_kernel), grid_for((long long)N * H * W * Cout), 256, 0, (cudaStream_t)stream, y, ldy, bias, out, ldo,
-             residual, ldr, N, H, W, Cout, dilation, slope);
+             residual, ldr, N, H, W, Cout, dilation, slope, flags);
   return check_launch("tap_combine");
 }

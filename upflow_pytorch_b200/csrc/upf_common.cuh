@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
 #include "../../include/upflow_b200.h"
 
 #define UPF_NUM_SMS 148   // B200: 2 dies x 74 SMs
@@ -63,9 +64,26 @@ struct PdlLaunch {
     (void)cudaLaunchKernelEx(&_l.cfg, kernel, __VA_ARGS__);                 \
   } while (0)
 
+// cudaFuncSetAttribute is per DEVICE: a once-per-process flag would leave the second GPU of a process (nn.DataParallel,
+// tools.abstract_model.choose_gpu) at the 48 KB default.  One bit per device ordinal, set after the first success.
+struct PerDeviceOnce {
+  unsigned long long done = 0;
+  bool need() const { int d = 0; cudaGetDevice(&d); return d >= 64 || !((done >> d) & 1ull); }
+  void mark() { int d = 0; cudaGetDevice(&d); if (d < 64) done |= 1ull << d; }
+};
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v < 0.f ? v * slope : v; }
+// nearest TF32 value, ties away from zero (cvt.rna.tf32.f32): what a tensor-core consumer should find in the top 19 bits
+__host__ __device__ __forceinline__ float round_tf32(float v) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+#else
+  uint32_t u; memcpy(&u, &v, 4); u = (u + 0x1000u) & 0xffffe000u; memcpy(&v, &u, 4); return v;
+#endif
+}
+__device__ __forceinline__ float maybe_round(float v, int flags) { return (flags & UPF_FLAG_ROUND_TF32) ? round_tf32(v) : v; }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 

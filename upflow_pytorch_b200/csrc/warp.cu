@@ -57,7 +57,7 @@ template <bool VEC>
 __global__ void __launch_bounds__(WARP_NT)
 warp_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ flow, int ldf,
                 float* __restrict__ out, int ldo, int H, int W, int C, int align_corners, float mask_thr,
-                double* __restrict__ stats, int lpp, int ctas_per_image, int x_shift, int N) {
+                double* __restrict__ stats, int lpp, int ctas_per_image, int x_shift, int N, int oflags) {
   pdl_prologue();
   extern __shared__ double s_red[];   // [2][cgroups*4] when stats
   const int n = blockIdx.x / ctas_per_image;
@@ -140,6 +140,7 @@ warp_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ 
             }
         }
       }
+      if (oflags & UPF_FLAG_ROUND_TF32) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
       if (VEC) {
         *reinterpret_cast<float4*>(o + c) = acc;
       } else {
@@ -276,6 +277,54 @@ warp_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ 
   }
 }
 
+
+// ---- normalize_features' other moment modes (model/upflow.py:94-137) ----------------------------------------------
+// The correlation kernels normalise with per-(image, channel) statistics given as (sum, sum of squares).  The
+// reference can also pool the moments over the channels of an image (moments_across_channels: mean / unbiased var
+// over [C,H,W]) and over the two tensors of a pair (moments_across_images: the MEAN of the two means, and -- as the
+// reference writes it, :121-124 -- the unbiased VARIANCE of the two variances).  Both are still one (mean, std) per
+// image and channel, so this kernel rewrites the raw moments of a pair (A = image n of sa, B = image (n+shift)%N of
+// sb) into EQUIVALENT per-channel moments (sum' = mean*npix, sumsq' = var*(npix-1) + sum'*mean) that
+// stats_to_mean_std turns back into the pooled mean / std.  One CTA per pair.
+__global__ void __launch_bounds__(256)
+featnorm_combine_kernel(const double* __restrict__ sa, const double* __restrict__ sb, int shift, double* __restrict__ oa,
+                        double* __restrict__ ob, int N, int C, double npix, int across_ch, int across_img) {
+  pdl_prologue();
+  const int n = blockIdx.x, n2 = (n + shift) % N;
+  const double* a = sa + (size_t)n * C * 2;
+  const double* b = sb + (size_t)n2 * C * 2;
+  __shared__ double red[4];
+  if (across_ch) {
+    if (threadIdx.x < 4) red[threadIdx.x] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {                 // C <= 256 values per sum: a fixed-order serial sum is deterministic and cheap
+      double t[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int c = 0; c < C; ++c) { t[0] += a[c * 2]; t[1] += a[c * 2 + 1]; t[2] += b[c * 2]; t[3] += b[c * 2 + 1]; }
+      for (int k = 0; k < 4; ++k) red[k] = t[k];
+    }
+    __syncthreads();
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double cnt = npix, a0 = a[c * 2], a1 = a[c * 2 + 1], b0 = b[c * 2], b1 = b[c * 2 + 1];
+    if (across_ch) { cnt = npix * (double)C; a0 = red[0]; a1 = red[1]; b0 = red[2]; b1 = red[3]; }
+    double ma = a0 / cnt, mb = b0 / cnt;
+    double va = (a1 - a0 * ma) / (cnt - 1.0), vb = (b1 - b0 * mb) / (cnt - 1.0);
+    if (va < 0.0) va = 0.0;
+    if (vb < 0.0) vb = 0.0;
+    if (across_img) {
+      // the reference works on the fp32 means / variances of the two tensors from here on
+      const double fa = (double)(float)ma, fb = (double)(float)mb, ga = (double)(float)va, gb = (double)(float)vb;
+      const double m = (fa + fb) * 0.5, gm = (ga + gb) * 0.5;
+      const double v = (ga - gm) * (ga - gm) + (gb - gm) * (gb - gm);     // torch.var of two values, unbiased (n-1 = 1)
+      ma = mb = m; va = vb = v;
+    }
+    double* pa = oa + ((size_t)n * C + c) * 2;
+    double* pb = ob + ((size_t)n2 * C + c) * 2;
+    pa[0] = ma * npix; pa[1] = va * (npix - 1.0) + ma * npix * ma;
+    pb[0] = mb * npix; pb[1] = vb * (npix - 1.0) + mb * npix * mb;
+  }
+}
+
 static int pick_lpp(int C) {
   int cg = (C + 3) / 4;
   int lpp = 1;
@@ -337,7 +386,7 @@ occ_check_kernel(const float* __restrict__ flow, int ldf, float* __restrict__ oc
 
 extern "C" int upf_warp_fwd(const float* x, int ldx, const float* flow, int ldf, float* out, int ldo,
                             int N, int H, int W, int C, int align_corners, float mask_threshold, int x_batch_shift,
-                            double* stats, void* stream) {
+                            double* stats, int flags, void* stream) {
   using namespace upf;
   UPF_REQUIRE(x && flow && out, "warp: null tensor");
   UPF_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && ldx >= C && ldo >= C && ldf >= 2, "warp: bad shape");
@@ -357,10 +406,10 @@ extern "C" int upf_warp_fwd(const float* x, int ldx, const float* flow, int ldf,
   const size_t smem = stats ? (size_t)(WARP_NT / 32) * 2 * ((C + 3) / 4) * 4 * sizeof(double) : 0;
   if (vec)
     UPF_LAUNCH((warp_fwd_kernel<true>), N * per_image, WARP_NT, smem, (cudaStream_t)stream, x, ldx, flow, ldf, out, ldo, H, W, C,
-                                                                                 align_corners, mask_threshold, stats, lpp, per_image, x_batch_shift, N);
+                                                                                 align_corners, mask_threshold, stats, lpp, per_image, x_batch_shift, N, flags);
   else
     UPF_LAUNCH((warp_fwd_kernel<false>), N * per_image, WARP_NT, smem, (cudaStream_t)stream, x, ldx, flow, ldf, out, ldo, H, W, C,
-                                                                                  align_corners, mask_threshold, stats, lpp, per_image, x_batch_shift, N);
+                                                                                  align_corners, mask_threshold, stats, lpp, per_image, x_batch_shift, N, flags);
   return check_launch("warp_fwd");
 }
 
@@ -392,6 +441,18 @@ extern "C" int upf_featnorm_stats(const float* x, int ldx, int N, int H, int W, 
   const size_t smem = (size_t)(WARP_NT / 32) * 2 * ((C + 3) / 4) * 4 * sizeof(double);
   UPF_LAUNCH((featnorm_stats_kernel), N * per_image, WARP_NT, smem, (cudaStream_t)stream, x, ldx, H, W, C, stats, lpp, per_image, vec);
   return check_launch("featnorm_stats");
+}
+
+extern "C" int upf_featnorm_combine(const double* stats_a, const double* stats_b, int b_batch_shift, double* out_a, double* out_b,
+                                    int N, int C, long long npix, int across_channels, int across_images, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(stats_a && stats_b && out_a && out_b, "featnorm_combine: null tensor");
+  UPF_REQUIRE(N > 0 && C > 0 && C <= 256 && npix > 1 && b_batch_shift >= 0 && b_batch_shift < N, "featnorm_combine: bad argument");
+  UPF_REQUIRE(out_a != out_b && out_a != stats_a && out_a != stats_b && out_b != stats_a && out_b != stats_b,
+              "featnorm_combine: outputs must be distinct buffers");
+  UPF_LAUNCH((featnorm_combine_kernel), N, 256, 0, (cudaStream_t)stream, stats_a, stats_b, b_batch_shift, out_a, out_b, N, C,
+             (double)npix, across_channels ? 1 : 0, across_images ? 1 : 0);
+  return check_launch("featnorm_combine");
 }
 
 extern "C" int upf_featnorm_apply(const float* x, int ldx, const double* stats, float* out, int ldo,

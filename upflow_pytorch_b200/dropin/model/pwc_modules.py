@@ -49,8 +49,10 @@ class _ConvBlock(nn.Sequential):
             return ops.conv2d_autograd(x, c.weight, c.bias, c.stride[0], c.dilation[0], 0.1 if self.is_relu else 1.0,
                                        _PRECISION["mode"])
         w, b, tc = self.packed(_PRECISION["mode"])
+        # hidden activations of tensor-core convolutions are stored rounded to the nearest TF32 value (the MMA truncates)
+        prec = (_ext.CONV_TF32 | (_ext.CONV_ROUND_OUT if self.is_relu else 0)) if tc else _ext.CONV_FP32
         return ops.conv2d(x, w, b, c.out_channels, c.kernel_size[0], c.stride[0], c.dilation[0],
-                          0.1 if self.is_relu else 1.0, _ext.CONV_TF32 if tc else _ext.CONV_FP32)
+                          0.1 if self.is_relu else 1.0, prec)
 
 
 def conv(in_planes, out_planes, kernel_size=3, stride=1, dilation=1, isReLU=True, if_IN=False, IN_affine=False,
@@ -171,7 +173,7 @@ class _DenseBlock(tools.abstract_model):
             w, b, tc = blk.packed(_ext.CONV_FP32 if (lo % 4) else _PRECISION["mode"])
             new_lo = lo - c
             ops.k_conv(Slice(buf, lo, total - lo), w, b, Slice(buf, new_lo, c), 3, 1, 1, 0.1, None,
-                       _ext.CONV_TF32 if tc else _ext.CONV_FP32)
+                       (_ext.CONV_TF32 | _ext.CONV_ROUND_OUT) if tc else _ext.CONV_FP32)
             lo = new_lo
         w, b, tc = self.conv_last.packed(_ext.CONV_FP32 if (lo % 4) else _PRECISION["mode"])
         cout = self.conv_last[0].out_channels

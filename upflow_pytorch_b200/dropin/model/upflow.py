@@ -73,12 +73,25 @@ class network_tools():
     @classmethod
     def normalize_features(cls, feature_list, normalize, center, moments_across_channels=True,
                            moments_across_images=True):
-        """model/upflow.py:94-137.  The kernel implements the configuration the shipped model uses
-        (per image, per channel: test.py:24-26); other moment modes are rejected rather than approximated."""
-        if moments_across_channels or moments_across_images or not (normalize and center):
-            raise NotImplementedError("only normalize=center=True with per-image per-channel moments "
-                                      "(norm_moments_across_channels=False, norm_moments_across_images=False)")
-        return [ops.normalize_features(f) for f in feature_list]
+        """model/upflow.py:94-137.  Per-image per-channel moments (the shipped configuration, test.py:24-26) are the
+        library's fused statistics + apply kernels with their own backward.  The pooled moment modes (the class
+        defaults, :312-313) and the normalize / center switches exist on this module-level (training) path as the
+        reference's own expressions on the CUDA tensors -- autograd differentiates them as it does there; the fused
+        inference engine serves every mode with kernels (upf_featnorm_combine)."""
+        if normalize and center and not moments_across_channels and not moments_across_images:
+            return [ops.normalize_features(f) for f in feature_list]
+        axes = [1, 2, 3] if moments_across_channels else [2, 3]
+        means = [torch.mean(f, dim=axes, keepdim=True) for f in feature_list]
+        variances = [torch.var(f, dim=axes, keepdim=True) for f in feature_list]
+        if moments_across_images:
+            means = [torch.mean(torch.stack(means, dim=0), dim=(0,))] * len(feature_list)
+            variances = [torch.var(torch.stack(variances, dim=0), dim=(0,))] * len(feature_list)
+        stds = [torch.sqrt(v + 1e-16) for v in variances]
+        if center:
+            feature_list = [f - m for f, m in zip(feature_list, means)]
+        if normalize:
+            feature_list = [f / sd for f, sd in zip(feature_list, stds)]
+        return list(feature_list)
 
     # ---- loss terms of the training step (model/upflow.py:198-290).  They run AFTER the decoder on full-resolution
     # 2-/3-channel tensors.  The photometric / distillation term and the first-order smoothness term are fused kernels
@@ -226,19 +239,16 @@ class UPFlow_net(tools.abstract_model):
     def _get_engine(self):
         params = list(self.parameters())
         key = (self.conv_precision, params[0].device, tuple(p._version for p in params),
-               tuple(p.data_ptr() for p in params))
+               tuple(p.data_ptr() for p in params), bool(self.conf.if_norm_before_cost_volume),
+               bool(self.conf.norm_moments_across_channels), bool(self.conf.norm_moments_across_images))
         if self._engine is None or self._engine_key != key:
-            if not (self.conf.if_norm_before_cost_volume and not self.conf.norm_moments_across_channels
-                    and not self.conf.norm_moments_across_images):
-                raise NotImplementedError(
-                    "the fused decoder implements the shipped configuration (test.py:22-30): "
-                    "if_norm_before_cost_volume=True, norm_moments_across_channels=False, "
-                    "norm_moments_across_images=False")
             occ = None
             if self.conf.occ_type == 'for_back_check':
                 occ = (self.conf.alpha_1, self.conf.alpha_2, self.conf.occ_check_obj_out_all)
             self._engine = DecoderEngine(self.state_dict(), device=params[0].device, precision=self.conv_precision,
-                                         use_sgu=bool(self.conf.if_sgu_upsample), occ=occ)
+                                         use_sgu=bool(self.conf.if_sgu_upsample), occ=occ,
+                                         norm=(self.conf.if_norm_before_cost_volume, self.conf.norm_moments_across_channels,
+                                               self.conf.norm_moments_across_images))
             self._engine_key = key
             self._graphs = {}
         return self._engine
@@ -362,10 +372,13 @@ class UPFlow_net(tools.abstract_model):
             if g is None:
                 if len(self._graphs) >= 8:
                     self._graphs.clear()
+                    eng.release_workspaces()       # the graphs' buffers go with them
                 g = self._graphs[key] = eng.capture(x1_raw.shape[0], x1_raw.shape[2], x1_raw.shape[3])
             f, b = g(x1_raw, x2_raw)
             flows, occ = g.flows, g.occ
         else:
+            if len(eng._ws) >= 24:
+                eng.release_workspaces()
             f, b, flows = eng.forward(x1_raw.float(), x2_raw.float())
             occ = eng.last_occ
         if occ is None:

@@ -78,7 +78,15 @@ class tools():
         @classmethod
         def choose_gpu(cls, model, gpu_opt=None):
             if gpu_opt is None:
-                model = torch.nn.DataParallel(model.cuda(), device_ids=list(range(torch.cuda.device_count())))
+                # the reference wraps the model in nn.DataParallel over every visible GPU (utils/tools.py:140): one
+                # process, one thread per device.  This library's engine (CUDA graphs, per-shape workspaces) is built
+                # for one process per GPU (upflow_pytorch_b200.train.Trainer / torchrun), so several devices in one
+                # process are refused instead of run half-supported
+                if torch.cuda.device_count() > 1:
+                    raise RuntimeError("choose_gpu(gpu_opt=None) would wrap the model in nn.DataParallel over %d GPUs; "
+                                       "upflow_pytorch_b200 runs one process per GPU: launch with torchrun and use "
+                                       "upflow_pytorch_b200.train.Trainer, or pass gpu_opt=<index>" % torch.cuda.device_count())
+                model = torch.nn.DataParallel(model.cuda(), device_ids=[0])
             elif gpu_opt == 0:
                 model = model.cuda()
             else:

@@ -23,6 +23,17 @@ X buffer channel map (estimator input order of the reference is
 [corr 81 | f_1x1 32 | flow 2], model/upflow.py:565):
     0..80 corr | 81..112 f_1x1 | 113..114 flow_up | 115..116 flow_up+flow_res
     | 117..127 zero | 128 conv1 | 256 conv2 | 384 conv3 | 480 conv4 | 544 conv5
+
+Precision "tf32": tcgen05 kind::tf32 reads the top 19 bits of an fp32 operand,
+i.e. it TRUNCATES.  Every buffer a tensor-core convolution reads is therefore
+written already ROUNDED TO THE NEAREST TF32 value by its producer (convolution
+epilogues of hidden layers, the correlation, the SGU warp, the flow slots), and
+the weights are rounded when packed: unbiased operand error 2^-12 instead of a
+one-sided 2^-11.  The two flow slots of X are rounded COPIES; the exact flows
+the warp / blend / residual additions need live in their own small buffers
+("fu", "flow2").  With the shipped checkpoint at KITTI size this is the
+difference between 3.8e-3 px (truncation) and 5.6e-4 px (rounding) mean EPE
+against the fp32 reference (robust-mask diagnostic).
 """
 import torch
 
@@ -58,13 +69,16 @@ EXPAND_MIN_PIXELS = 5000     # ... on images with at least this many pixels (bel
 
 
 class ConvSpec:
-    __slots__ = ("w", "w_tc", "bias", "cin", "cout", "k", "stride", "dil", "slope", "w_exp", "zero_bias", "w_lo_tc", "zero_b")
+    __slots__ = ("w", "w_tc", "bias", "cin", "cout", "k", "stride", "dil", "slope", "w_exp", "zero_bias", "w_lo_tc", "zero_b",
+                 "hidden")
 
     def __init__(self, weight, bias, stride=1, dil=1, relu=True, in_slots=None, cin_total=None, tc=True, x3=False):
         self.cout, _, self.k, _ = weight.shape
         self.cin = cin_total or weight.shape[1]
         self.stride, self.dil = stride, dil
         self.slope = SLOPE if relu else 1.0
+        self.hidden = relu            # a hidden activation: only convolutions (and, for the encoder features, the
+                                      # correlation / warp) read it -- stored TF32-rounded under precision "tf32"
         # tensor cores for everything but the 3-channel image convs (K = 27: one quarter-empty K block per tap)
         self.w, self.w_tc = ops.pack_conv_weight(weight, in_slots, cin_total, tc=tc and stride in (1, 2) and self.cin >= 16)
         self.bias = bias.detach().float().contiguous()
@@ -74,7 +88,7 @@ class ConvSpec:
         self.w_lo_tc = None
         if x3 and self.w_tc is not None:
             w32 = weight.detach().float().contiguous()
-            w_hi = (w32.view(torch.int32) & ~0x1FFF).view(torch.float32)
+            w_hi = ((w32.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)      # what the packer stores: nearest TF32
             self.w_lo_tc = ops.pack_conv_weight(w32 - w_hi, in_slots, cin_total, tc=True)[1]
             self.zero_b = torch.zeros(self.cout, dtype=torch.float32, device=weight.device)
         self.w_exp = None
@@ -85,8 +99,11 @@ class ConvSpec:
 
 class DecoderEngine:
     def __init__(self, state_dict, device="cuda", precision="tf32", align_corners=False, use_sgu=True,
-                 mask_threshold=1.0, occ=None):
-        """state_dict: the reference's parameter names."""
+                 mask_threshold=1.0, occ=None, norm=(True, False, False)):
+        """state_dict: the reference's parameter names.
+        norm = (if_norm_before_cost_volume, norm_moments_across_channels, norm_moments_across_images) of
+        UPFlow_net.config (model/upflow.py:311-313); test.py runs (True, False, False), the class default is
+        (False, True, True)."""
         if not torch.cuda.is_available():
             raise RuntimeError("DecoderEngine needs a CUDA device: the decoder path has no CPU implementation")
         _ext.load()
@@ -99,12 +116,14 @@ class DecoderEngine:
         # activation -- fp32-class results (2^-21) at a third of the tensor-core rate; every convolution input keeps a
         # "low part" twin buffer (x - x truncated to TF32) that the producing kernel's output is split into
         self.x3 = precision == "tf32x3"
+        self.rnd = precision == "tf32"       # producers round what tensor-core convolutions will read
         self._lo_bufs = {}
         self.align_corners = bool(align_corners)
         self.use_sgu = use_sgu
         # 1.0 = the reference's `mask >= 1.0` (model/pwc_modules.py:206); 0.9999 = diagnostic robust mask
         self.mask = True if mask_threshold == 1.0 else float(mask_threshold)
         self._ws = {}
+        self.norm, self.norm_ch, self.norm_img = (bool(v) for v in norm)
         # (alpha_1, alpha_2, 'all'|'obj'|'out'): also produce the forward/backward consistency masks that
         # UPFlow_net.forward returns (tools.occ_check_model, model/upflow.py:386) -- one more launch in the graph
         self.occ = occ
@@ -194,14 +213,15 @@ class DecoderEngine:
             ops.k_conv(x, cs.w, cs.bias, out, cs.k, cs.stride, cs.dil, cs.slope, residual, _ext.CONV_FP32)   # exact SIMT
             self._split(out)
             return
+        rnd = self.rnd and cs.hidden
         if use_tc and cs.w_exp is not None and x.H * x.W >= EXPAND_MIN_PIXELS:
             Y = self._scratch(x.N, x.H, x.W, 9 * EXPAND_MAX_COUT)
             ys = Slice(Y, 0, 9 * cs.cout)
             ops.k_conv(x, cs.w_exp, cs.zero_bias, ys, 1, 1, 1, 1.0, None, _ext.CONV_TF32)
-            ops.k_tap_combine(ys, cs.bias, out, cs.dil, cs.slope, residual)
+            ops.k_tap_combine(ys, cs.bias, out, cs.dil, cs.slope, residual, round_tf32=rnd)
             return
         ops.k_conv(x, cs.w_tc if use_tc else cs.w, cs.bias, out, cs.k, cs.stride, cs.dil, cs.slope, residual,
-                   _ext.CONV_TF32 if use_tc else _ext.CONV_FP32)
+                   (_ext.CONV_TF32 if use_tc else _ext.CONV_FP32) | (_ext.CONV_ROUND_OUT if rnd else 0))
 
     def _workspace(self, B, H, W):
         key = (B, H, W)
@@ -225,14 +245,19 @@ class DecoderEngine:
         # every (sum, sum^2) accumulator of a forward lives in ONE arena, cleared by one memset per forward
         arena = torch.zeros(2 * N * sum(NUM_CHS) * 2, dtype=torch.float64, device=dev)
         ws["stats_arena"] = arena
+        pooled = self.norm and (self.norm_ch or self.norm_img)      # the pooled moment modes go through upf_featnorm_combine
         off = 0
         for l in range(5):
             h, w = sizes[6 - l]
             n = N * NUM_CHS[l] * 2
             d = {"hw": (h, w), "X": z(N, h, w, X_LD), "T0": z(N, h, w, 128), "T1": z(N, h, w, 128),
                  "flow": z(N, h, w, 2), "xw": z(N, h, w, NUM_CHS[l]),
+                 "fu": z(N, h, w, 2), "flow2": z(N, h, w, 2),        # exact flow_up / flow_up + flow_res (X holds TF32 copies)
                  "stats_own": arena[off:off + n].view(N, NUM_CHS[l], 2),
                  "stats_w": arena[off + n:off + 2 * n].view(N, NUM_CHS[l], 2)}
+            if pooled:
+                d["stats_ca"] = torch.zeros(N, NUM_CHS[l], 2, dtype=torch.float64, device=dev)
+                d["stats_cb"] = torch.zeros(N, NUM_CHS[l], 2, dtype=torch.float64, device=dev)
             off += 2 * n
             if self.use_sgu and l > 0:
                 d["S"] = z(N, h, w, S_LD)
@@ -287,7 +312,8 @@ class DecoderEngine:
         ws = self._workspace(B, H, W)
         N = 2 * B
         ac = self.align_corners
-        ws["stats_arena"].zero_()                      # all feature / warp moment accumulators of this forward
+        if self.norm:
+            ws["stats_arena"].zero_()                  # all feature / warp moment accumulators of this forward
         feats = self.encode(ws, im1, im2)              # index l -> 1/2^(l+1); decoder level L uses feats[5-L]
         # Work that depends on the images only -- the 1x1 adapters and feature statistics of levels 1..4 and
         # sgi_model.output_conv (two full-resolution convolutions) -- runs on a SIDE STREAM while the main stream
@@ -303,7 +329,8 @@ class DecoderEngine:
                 d = ws["levels"][L]
                 F = Slice(feats[5 - L])
                 self._conv(self.conv1x1[L], F, Slice(d["X"], X_F1X1, 32))
-                ops.k_stats(F, d["stats_own"])
+                if self.norm:
+                    ops.k_stats(F, d["stats_own"])
             ev_adapters.record(side)
             if self.use_sgu:
                 # sgi_model.output_conv on both images (model/upflow.py:66-69, :527-528)
@@ -320,16 +347,20 @@ class DecoderEngine:
             F = Slice(feats[5 - L])
             C = NUM_CHS[L]
             X = d["X"]
-            flow_up = Slice(X, X_FLOW, 2)
+            flow_up = Slice(d["fu"])                    # exact; X[113:117] = (its TF32 copy, 0, 0) for the convolutions
+            x_flow = Slice(X, X_FLOW, 4)
             if L == 0:
                 # 1x1 adapter (model/upflow.py:508-513) straight into its estimator slot
                 self._conv(self.conv1x1[L], F, Slice(X, X_F1X1, 32))
-                ops.k_stats(F, d["stats_own"])
+                if self.norm:
+                    ops.k_stats(F, d["stats_own"])
             elif L == 1:
                 main.wait_event(ev_adapters)
             if L == 0:
-                pass       # upsampling a zero flow (model/upflow.py:504-505, :536): this slot of the level-0 buffer is
-                           # zero from allocation on and nothing ever writes it
+                # upsampling a zero flow (model/upflow.py:504-505, :536): "fu" is zero from allocation on and nothing
+                # writes it; the X slot is cleared every forward (its second half is rewritten below)
+                ops.k_copy(None, x_flow)
+                self._split(x_flow)
             else:
                 ph, pw = ws["levels"][L - 1]["hw"]
                 if self.use_sgu:
@@ -337,27 +368,38 @@ class DecoderEngine:
                     ops.k_resize(prev_flow, bil, (w / pw, h / ph))
                     S = d["S"]
                     ops.k_copy(Slice(X, X_F1X1, 32), Slice(S, 0, 32))
-                    ops.k_warp(Slice(X, X_F1X1, 32), bil, Slice(S, 32, 32), ac, self.mask, x_shift=B)
+                    ops.k_warp(Slice(X, X_F1X1, 32), bil, Slice(S, 32, 32), ac, self.mask, x_shift=B, round_tf32=self.rnd)
                     self._split(Slice(S, 0, 64))
                     self._sgu_dense(S, d["inter"])
-                    ops.k_sgu_blend(bil, Slice(d["inter"], 0, 3), flow_up, ac)
+                    ops.k_sgu_blend(bil, Slice(d["inter"], 0, 3), flow_up, ac, out_tc=x_flow, round_tf32=self.rnd)
                 else:
                     ops.k_resize(prev_flow, flow_up, (w / pw, h / ph))
-                self._split(flow_up)
+                    ops.k_copy(None, Slice(X, X_FLOW2, 2))
+                    ops.k_copy(flow_up, Slice(X, X_FLOW, 2), round_tf32=self.rnd)
+                self._split(x_flow)
             # feature statistics (model/upflow.py:549-555: computed above / on the side stream), warp + its
             # statistics (:546-547)
+            # if_norm_before_cost_volume (model/upflow.py:549-555): off = the raw features are correlated
             if L == 0:
-                ops.k_corr(F, F, Slice(X, X_CORR, 81), 4, d["stats_own"], d["stats_own"], f2_shift=B, slope=SLOPE)
-                self._split(Slice(X, X_CORR, 81))
+                s1 = s2 = d["stats_own"] if self.norm else None
+                f2, shift = F, B
             else:
-                ops.k_warp(F, flow_up, Slice(d["xw"]), ac, self.mask, x_shift=B, stats=d["stats_w"])
-                ops.k_corr(F, Slice(d["xw"]), Slice(X, X_CORR, 81), 4, d["stats_own"], d["stats_w"], slope=SLOPE)
-                self._split(Slice(X, X_CORR, 81))
+                ops.k_warp(F, flow_up, Slice(d["xw"]), ac, self.mask, x_shift=B, stats=d["stats_w"] if self.norm else None)
+                s1, s2 = (d["stats_own"], d["stats_w"]) if self.norm else (None, None)
+                f2, shift = Slice(d["xw"]), 0
+            if self.norm and (self.norm_ch or self.norm_img):
+                ops.k_norm_combine(s1, s2, d["stats_ca"], d["stats_cb"], N, C, h * w, shift, self.norm_ch, self.norm_img)
+                s1, s2 = d["stats_ca"], d["stats_cb"]
+            ops.k_corr(F, f2, Slice(X, X_CORR, 81), 4, s1, s2, f2_shift=shift, slope=SLOPE, round_tf32=self.rnd)
+            self._split(Slice(X, X_CORR, 81))
             # dense flow estimator (model/pwc_modules.py:279-286)
             for k in range(5):
                 self._conv(self.est[k], Slice(X, 0, self.est[k].cin), Slice(X, X_OFF[k], EST_CH[k]))
-            # flow_up + flow_res -> context input slot (model/upflow.py:567)
-            self._conv(self.est[5], Slice(X, 0, X_LD), Slice(X, X_FLOW2, 2), residual=flow_up)
+            # flow_up + flow_res (model/upflow.py:567): exact into "flow2", TF32 copy into the context input slot
+            flow2 = Slice(d["flow2"])
+            self._conv(self.est[5], Slice(X, 0, X_LD), flow2, residual=flow_up)
+            ops.k_copy(flow2, Slice(X, X_FLOW2, 2), round_tf32=self.rnd)
+            self._split(Slice(X, X_FLOW2, 2))
             # context network (model/pwc_modules.py:401-412); last conv adds (flow_up + flow_res): :569-572, :519
             t_in = Slice(X, 0, X_LD)
             bufs = (d["T0"], d["T1"])
@@ -365,11 +407,11 @@ class DecoderEngine:
                 t_out = Slice(bufs[i % 2], 0, CTX_CH[i])
                 self._conv(self.ctx[i], t_in, t_out)
                 t_in = t_out
-            self._conv(self.ctx[6], t_in, Slice(d["flow"]), residual=Slice(X, X_FLOW2, 2))
+            self._conv(self.ctx[6], t_in, Slice(d["flow"]), residual=flow2)
             prev_flow = Slice(d["flow"])
             flows.append(d["flow"])
             if taps is not None:
-                taps.append({"level": L, "flow_up": X[..., X_FLOW:X_FLOW + 2].permute(0, 3, 1, 2).clone(),
+                taps.append({"level": L, "flow_up": d["fu"].permute(0, 3, 1, 2).clone(),
                              "corr": X[..., :81].permute(0, 3, 1, 2).clone(),
                              "xw": d["xw"].permute(0, 3, 1, 2).clone() if L > 0 else None,
                              "flow": d["flow"].permute(0, 3, 1, 2).clone()})
@@ -382,7 +424,7 @@ class DecoderEngine:
             S = ws["S_out"]
             main.wait_event(ev_outconv)                # output_conv features (side stream)
             # the flow handed to sgu_model here is the 1/4-res flow itself (already at feature size, :73-75)
-            ops.k_warp(Slice(S, 0, 32), prev_flow, Slice(S, 32, 32), ac, self.mask, x_shift=B)
+            ops.k_warp(Slice(S, 0, 32), prev_flow, Slice(S, 32, 32), ac, self.mask, x_shift=B, round_tf32=self.rnd)
             self._split(Slice(S, 32, 32))
             self._sgu_dense(S, ws["inter_out"])
             ops.k_sgu_blend(bil, Slice(ws["inter_out"], 0, 3), out, ac)
@@ -396,6 +438,13 @@ class DecoderEngine:
         fo = ws["flow_out"].permute(0, 3, 1, 2)
         lvl = [[f[:B].permute(0, 3, 1, 2), f[B:].permute(0, 3, 1, 2)] for f in flows]
         return fo[:B], fo[B:], lvl[::-1]
+
+    def release_workspaces(self):
+        """Drop every per-shape workspace (hundreds of MB each at KITTI size), scratch and low-part twin buffer.
+        UPFlow_net calls this when it drops its captured graphs, so evaluating a dataset with many image sizes does not
+        grow GPU memory without bound; graphs captured on the old workspaces must be dropped with them."""
+        self._ws.clear()
+        self._lo_bufs.clear()
 
     def flow_out_buffer(self, shape):
         """the [2B,H,W,2] buffer the last forward of this input shape wrote (forward flows first)"""

@@ -90,11 +90,12 @@ def _as_slice(x):
 
 
 # ---------------------------------------------------------------- launchers
-def k_corr(f1, f2, out, max_disp=4, stats1=None, stats2=None, f2_shift=0, slope=LRELU_SLOPE):
+def k_corr(f1, f2, out, max_disp=4, stats1=None, stats2=None, f2_shift=0, slope=LRELU_SLOPE, round_tf32=False):
     f1, f2, out = _as_slice(f1), _as_slice(f2), _as_slice(out)
     assert f1.C == f2.C and out.C == (2 * max_disp + 1) ** 2
     _ext.check(_lib().upf_corr_lrelu_fwd(f1.ptr(), f1.ld, f2.ptr(), f2.ld, out.ptr(), out.ld, f1.N, f1.H, f1.W, f1.C,
-                                         max_disp, _p(stats1), _p(stats2), f2_shift, slope, _stream()), "corr_lrelu_fwd")
+                                         max_disp, _p(stats1), _p(stats2), f2_shift, slope,
+                                         _ext.FLAG_ROUND_TF32 if round_tf32 else 0, _stream()), "corr_lrelu_fwd")
 
 
 def k_corr_bwd(f1, f2, out, grad_out, grad_f1, grad_f2, max_disp=4, slope=1.0):
@@ -115,11 +116,12 @@ def _mask_thr(use_mask):
     return float(use_mask)
 
 
-def k_warp(x, flow, out, align_corners=False, use_mask=True, x_shift=0, stats=None):
+def k_warp(x, flow, out, align_corners=False, use_mask=True, x_shift=0, stats=None, round_tf32=False):
     x, flow, out = _as_slice(x), _as_slice(flow), _as_slice(out)
     assert flow.C >= 2 and out.C == x.C
     _ext.check(_lib().upf_warp_fwd(x.ptr(), x.ld, flow.ptr(), flow.ld, out.ptr(), out.ld, out.N, out.H, out.W, x.C,
-                                   int(align_corners), _mask_thr(use_mask), x_shift, _p(stats), _stream()), "warp_fwd")
+                                   int(align_corners), _mask_thr(use_mask), x_shift, _p(stats),
+                                   _ext.FLAG_ROUND_TF32 if round_tf32 else 0, _stream()), "warp_fwd")
 
 
 def k_warp_bwd(x, flow, grad_out, grad_x, grad_flow, align_corners=False, use_mask=True):
@@ -149,6 +151,16 @@ def k_stats(x, stats):
                "featnorm_stats")
 
 
+def k_norm_combine(stats_a, stats_b, out_a, out_b, N, C, npix, shift=0, across_channels=False, across_images=False):
+    """Rewrite the raw moments of the pairs (stats_a[n], stats_b[(n+shift)%N]) into equivalent per-channel moments of
+    normalize_features' pooled modes (model/upflow.py:109-124)."""
+    dp = lambda t: ctypes.c_void_p(t.data_ptr())
+    for t in (stats_a, stats_b, out_a, out_b):
+        assert t.dtype == torch.float64 and t.numel() >= N * C * 2
+    _ext.check(_lib().upf_featnorm_combine(dp(stats_a), dp(stats_b), shift, dp(out_a), dp(out_b), N, C, int(npix),
+                                           int(across_channels), int(across_images), _stream()), "featnorm_combine")
+
+
 def k_norm_apply(x, stats, out):
     x, out = _as_slice(x), _as_slice(out)
     _ext.check(_lib().upf_featnorm_apply(x.ptr(), x.ld, ctypes.c_void_p(stats.data_ptr()), out.ptr(), out.ld, x.N, x.H,
@@ -165,10 +177,14 @@ def k_resize(src, out, scale=None):
                                           sc, _stream()), "resize_bilinear")
 
 
-def k_sgu_blend(flow_init, inter, out, align_corners=False):
+def k_sgu_blend(flow_init, inter, out, align_corners=False, out_tc=None, round_tf32=False):
+    """out_tc: a 4-channel slot of a convolution input buffer that receives (u, v, 0, 0), rounded to TF32 on request."""
     flow_init, inter, out = _as_slice(flow_init), _as_slice(inter), _as_slice(out)
+    o2 = _as_slice(out_tc) if out_tc is not None else None
+    assert o2 is None or o2.C == 4
     _ext.check(_lib().upf_sgu_blend(flow_init.ptr(), flow_init.ld, inter.ptr(), inter.ld, inter.H, inter.W, out.ptr(),
-                                    out.ld, out.N, out.H, out.W, int(align_corners), _stream()), "sgu_blend")
+                                    out.ld, o2.ptr() if o2 else None, o2.ld if o2 else 0, out.N, out.H, out.W,
+                                    int(align_corners), _ext.FLAG_ROUND_TF32 if round_tf32 else 0, _stream()), "sgu_blend")
 
 
 def k_conv(x, weight, bias, out, ksize, stride=1, dilation=1, slope=LRELU_SLOPE, residual=None, precision=_ext.CONV_FP32):
@@ -246,14 +262,14 @@ def k_resize_bwd(grad_out, grad_in, scale=None):
                "resize_bilinear_bwd")
 
 
-def k_tap_combine(y, bias, out, dilation=1, slope=LRELU_SLOPE, residual=None):
+def k_tap_combine(y, bias, out, dilation=1, slope=LRELU_SLOPE, residual=None, round_tf32=False):
     """out = lrelu(bias + sum of the nine shifted tap slices of y) (+ residual); y holds 9*Cout channels."""
     y, out = _as_slice(y), _as_slice(out)
     res = _as_slice(residual) if residual is not None else None
     assert y.C == 9 * out.C
     _ext.check(_lib().upf_conv3x3_tap_combine(y.ptr(), y.ld, _p(bias), out.ptr(), out.ld, res.ptr() if res else None,
                                               res.ld if res else 0, out.N, out.H, out.W, out.C, dilation, float(slope),
-                                              _stream()), "conv3x3_tap_combine")
+                                              _ext.FLAG_ROUND_TF32 if round_tf32 else 0, _stream()), "conv3x3_tap_combine")
 
 
 def expand_taps_weight(weight):
@@ -274,10 +290,13 @@ def k_act_split(t, out, out_lo=None, slope=1.0, residual=None):
                                     out.C, float(slope), _stream()), "act_split")
 
 
-def k_copy(src, dst):
-    src, dst = _as_slice(src), _as_slice(dst)
-    assert src.C == dst.C
-    _ext.check(_lib().upf_copy_channels(src.ptr(), src.ld, dst.ptr(), dst.ld, src.N * src.H * src.W, src.C, _stream()),
+def k_copy(src, dst, round_tf32=False):
+    """dst = src (src=None: zeros), optionally rounded to the nearest TF32 value."""
+    dst = _as_slice(dst)
+    src = _as_slice(src) if src is not None else None
+    assert src is None or src.C == dst.C
+    _ext.check(_lib().upf_copy_channels(src.ptr() if src else None, src.ld if src else 0, dst.ptr(), dst.ld,
+                                        dst.N * dst.H * dst.W, dst.C, _ext.FLAG_ROUND_TF32 if round_tf32 else 0, _stream()),
                "copy_channels")
 
 
@@ -752,7 +771,8 @@ class _ConvFn(torch.autograd.Function):
         Ho = (a.H + 2 * pad - dilation * (ks - 1) - 1) // stride + 1
         Wo = (a.W + 2 * pad - dilation * (ks - 1) - 1) // stride + 1
         out = _new(a.N, Ho, Wo, Cout, x)
-        k_conv(a, w_tc if tc else w_simt, bias.detach().float().contiguous(), out, ks, stride, dilation, slope, None, precision)
+        k_conv(a, w_tc if tc else w_simt, bias.detach().float().contiguous(), out, ks, stride, dilation, slope, None,
+               precision | (_ext.CONV_ROUND_OUT if tc and slope != 1.0 else 0))     # hidden activation: TF32-rounded for its consumers
         ctx.save_for_backward(a.buf, out, weight)
         ctx.cfg = (Cin, stride, dilation, slope, precision)
         return out.permute(0, 3, 1, 2)
@@ -830,7 +850,7 @@ class _DenseBlockFn(torch.autograd.Function):
             if i < n:
                 c = f_channels[i]
                 k_conv(Slice(buf, lo, total - lo), w_tc if tc else w_simt, bvec, Slice(buf, lo - c, c), 3, 1, 1, LRELU_SLOPE,
-                       None, prec)
+                       None, prec | (_ext.CONV_ROUND_OUT if tc else 0))
                 lo -= c
             else:
                 cout = weight.shape[0]
@@ -913,7 +933,7 @@ def conv2d(x, w_packed, bias, cout, ksize, stride=1, dilation=1, slope=LRELU_SLO
     """conv() of model/pwc_modules.py:10-31 on an NCHW tensor with pre-packed weights (pack_conv_weight)."""
     _require_cuda(x)
     C = x.shape[1]
-    if precision == _ext.CONV_TF32 and C % 4:
+    if (precision & 0xFF) == _ext.CONV_TF32 and C % 4:
         a = Slice(to_pixel_major(x, ld=(C + 3) // 4 * 4), 0, C)     # TMA needs a 16-byte pixel pitch
     else:
         a = Slice(to_pixel_major(x))
