@@ -523,3 +523,69 @@ def test_tc_weight_packing_rounds_to_nearest(upf):
         got = out.permute(0, 3, 1, 2).cpu()
         assert (got - ref_rn).abs().max().item() <= 5e-5
         assert (got - ref_tr).abs().max().item() > 2e-4
+
+
+# ------------------------------------------------------------------ the `correlation_cuda` stub (native boundary b1)
+class _RefCorrelationFunction(torch.autograd.Function):
+    """model/correlation_package/correlation.py:6-44 restated with static methods (the legacy instance-style Function of
+    the reference is rejected by torch >= 1.5): the same calls into `correlation_cuda`, the same empty tensors."""
+
+    @staticmethod
+    def forward(ctx, input1, input2, pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply):
+        import correlation_cuda
+        ctx.save_for_backward(input1, input2)
+        ctx.cfg = (pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply)
+        with torch.cuda.device_of(input1):
+            rbot1, rbot2, output = input1.new(), input2.new(), input1.new()
+            correlation_cuda.forward(input1, input2, rbot1, rbot2, output, *ctx.cfg)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        import correlation_cuda
+        input1, input2 = ctx.saved_tensors
+        with torch.cuda.device_of(input1):
+            rbot1, rbot2 = input1.new(), input2.new()
+            grad_input1, grad_input2 = input1.new(), input2.new()
+            correlation_cuda.backward(input1, input2, rbot1, rbot2, grad_output.contiguous(), grad_input1, grad_input2, *ctx.cfg)
+        return (grad_input1, grad_input2) + (None,) * 6
+
+
+def test_correlation_cuda_stub_matches_reference_golden(golden):
+    """`import correlation_cuda` (upflow_pytorch_b200/dropin/correlation_cuda.py, the file INTEGRATION.md section 2
+    installs next to the reference's correlation.py) driven exactly as correlation.py drives the pybind module, against
+    the reference's own outputs (tests/golden/corr.pt incl. BASELINE config 1)."""
+    import upflow_pytorch_b200
+    upflow_pytorch_b200.install_dropin()
+    import correlation_cuda
+    for c in golden("corr"):
+        f1 = c["f1"] if c["f1"] is not None else _regen(c["seed"], c["shape"])
+        f2 = c["f2"] if c["f2"] is not None else _regen(c["seed"] + 100, c["shape"])
+        d = c["d"]
+        out = _RefCorrelationFunction.apply(f1.cuda(), f2.cuda(), d, 1, d, 1, 1, 1)
+        assert out.shape == c["out"].shape and out.is_contiguous()
+        assert (out.cpu() - c["out"]).abs().max().item() <= 1e-5
+    # conventions: returns 1, sizes the caller's empty tensors, rejects what the kernel does not implement
+    a, b = torch.randn(1, 8, 6, 7).cuda(), torch.randn(1, 8, 6, 7).cuda()
+    o = a.new()
+    assert correlation_cuda.forward(a, b, a.new(), b.new(), o, 4, 1, 4, 1, 1, 1) == 1 and o.shape == (1, 81, 6, 7)
+    with pytest.raises(RuntimeError):
+        correlation_cuda.forward(a, b, a.new(), b.new(), a.new(), 3, 3, 20, 1, 2, 1)      # FlowNet2's setting, not UPFlow's
+    with pytest.raises(RuntimeError):
+        correlation_cuda.forward(a.cpu(), b.cpu(), a.new(), b.new(), a.new(), 4, 1, 4, 1, 1, 1)
+
+
+def test_correlation_cuda_stub_backward_vs_autograd():
+    """correlation_cuda.backward through the restated CorrelationFunction against autograd of Corr_pyTorch's expression
+    (oracle port) in fp64."""
+    import upflow_pytorch_b200
+    upflow_pytorch_b200.install_dropin()
+    g = _g(11)
+    f1, f2 = torch.randn(2, 12, 9, 13, generator=g), torch.randn(2, 12, 9, 13, generator=g)
+    go = torch.randn(2, 81, 9, 13, generator=g)
+    r1, r2 = f1.double().requires_grad_(), f2.double().requires_grad_()
+    P.corr_unfold(r1, r2, 4).backward(go.double())
+    c1, c2 = f1.cuda().requires_grad_(), f2.cuda().requires_grad_()
+    _RefCorrelationFunction.apply(c1, c2, 4, 1, 4, 1, 1, 1).backward(go.cuda())
+    assert (c1.grad.cpu().double() - r1.grad).abs().max().item() <= 1e-5
+    assert (c2.grad.cpu().double() - r2.grad).abs().max().item() <= 1e-5

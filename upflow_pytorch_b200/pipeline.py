@@ -9,8 +9,9 @@ idea for the drop-in model, both directions:
         done = pipe.submit(im1_host, im2_host)   # -> the PREVIOUS pair's flow (pinned host tensor) or None
     last = pipe.flush()
 
-* copy stream: H2D of pair k+1 while the compute stream runs pair k; D2H of pair k's flow into one of two pinned
-  staging buffers while pair k+1 computes;
+* two copy streams (an in-order stream would park the H2D of pair k+1 behind the D2H of flow k, which waits for forward
+  k): H2D of pair k+1 while the compute stream runs pair k; D2H of pair k's flow into one of two pinned staging buffers
+  while pair k+1 computes;
 * compute stream: ``net({'im1','im2','if_loss': False})`` -- the public call, unchanged (one CUDA-graph replay);
 * the caller receives a result one submit later (depth-2 pipeline) and may read it until the next-but-one submit.
 
@@ -23,7 +24,8 @@ class PipelinedInference:
     def __init__(self, net, device=None):
         self.net = net
         self.device = torch.device(device) if device is not None else next(net.parameters()).device
-        self.copy = torch.cuda.Stream(device=self.device)
+        self.h2d = torch.cuda.Stream(device=self.device)
+        self.copy = torch.cuda.Stream(device=self.device)          # device -> host
         self.compute = torch.cuda.Stream(device=self.device)
         self._dev_in = [None, None]         # two device input slots (im1, im2)
         self._host_out = [None, None]       # two pinned result slots
@@ -47,12 +49,12 @@ class PipelinedInference:
         (valid until the next-but-one submit), or None for the first call."""
         s = self._k & 1
         a, b = self._slot(s, im1_host, im2_host)
-        with torch.cuda.stream(self.copy):
+        with torch.cuda.stream(self.h2d):
             if self._k >= 2:
-                self.copy.wait_event(self._free[s])            # the forward that read this input slot has finished with it
+                self.h2d.wait_event(self._free[s])             # the forward that read this input slot has finished with it
             a.copy_(im1_host, non_blocking=True)
             b.copy_(im2_host, non_blocking=True)
-            self._h2d[s].record(self.copy)
+            self._h2d[s].record(self.h2d)
         with torch.cuda.stream(self.compute), torch.no_grad():
             self.compute.wait_event(self._h2d[s])
             if self._k >= 2:

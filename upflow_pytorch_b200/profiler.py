@@ -33,7 +33,7 @@ def _account(name, args, kwargs):
         k = args[4]
         n = _npix(out)
         return dict(bytes=4 * (_npix(x) * x.C + n * out.C) + 4 * k * k * x.C * out.C, flops=2 * n * k * k * x.C * out.C,
-                    shape=(x.N, x.C, x.H, x.W, out.C, k), tc=(kwargs.get("precision", args[9] if len(args) > 9 else 0) == 1))
+                    shape=(x.N, x.C, x.H, x.W, out.C, k), tc=((kwargs.get("precision", args[9] if len(args) > 9 else 0) & 0xFF) == 1))
     if name == "k_resize":
         a, out = S(args[0]), S(args[1])
         return dict(bytes=4 * a.C * (_npix(a) + _npix(out)), flops=8 * a.C * _npix(out), shape=(out.N, a.C, out.H, out.W))
@@ -47,12 +47,13 @@ def _account(name, args, kwargs):
         y, out = S(args[0]), S(args[2])
         return dict(bytes=4 * _npix(out) * (y.C + out.C), flops=9 * _npix(out) * out.C, shape=(out.N, out.C, out.H, out.W))
     if name == "k_copy":
-        a = S(args[0])
-        return dict(bytes=8 * _npix(a) * a.C, flops=0, shape=(a.N, a.C, a.H, a.W))
+        a = S(args[1])                                    # the destination (the source may be None: zero fill)
+        return dict(bytes=(8 if args[0] is not None else 4) * _npix(a) * a.C, flops=0, shape=(a.N, a.C, a.H, a.W))
     return dict(bytes=0, flops=0, shape=())
 
 
-NAMES = ("k_corr", "k_warp", "k_stats", "k_conv", "k_resize", "k_sgu_blend", "k_copy", "k_norm_apply", "k_tap_combine", "k_occ_check")
+NAMES = ("k_corr", "k_warp", "k_stats", "k_conv", "k_resize", "k_sgu_blend", "k_copy", "k_norm_apply", "k_tap_combine", "k_occ_check",
+         "k_norm_combine")
 
 
 def event_overhead_ms(n=200):
