@@ -196,7 +196,8 @@ int upf_debug_conv_halo(int enabled, int bo_mode);
 int upf_debug_conv_win(int enabled, int min_cin, int force_m);
 /* test / tuning hook: 0 routes large-image correlations to the non-pipelined tiled kernel (corr.cu) */
 int upf_debug_corr_pipe(int enabled);
-/* debug: device buffer of 8 int64 receiving CTA 0's per-role wait / busy cycle counters of the halo kernel (NULL = off) */
+/* debug: device buffer of 64 int64 receiving CTA 0's per-role wait / busy cycle counters of the halo / window /
+ * pipelined-correlation kernels (NULL = off) */
 int upf_debug_probe(void* device_buffer_8x_int64);
 
 /* ---- a11: backward of the convolutions and of the small decoder ops (training step, BASELINE config 4) ----
