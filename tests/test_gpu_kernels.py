@@ -302,7 +302,9 @@ def test_cpu_tensors_fail_loudly(upf):
 
 @pytest.mark.parametrize("case", [(576, 128, 3, 1, 1, 6, 20), (128, 96, 3, 1, 8, 12, 39), (184, 3, 3, 1, 1, 24, 78),
                                   (196, 32, 1, 1, 1, 6, 20), (96, 128, 3, 2, 1, 24, 78), (16, 32, 3, 2, 1, 47, 61),
-                                  (128, 196, 3, 2, 1, 12, 39)])
+                                  (128, 196, 3, 2, 1, 12, 39), (128, 128, 3, 1, 2, 6, 20), (64, 32, 3, 1, 1, 12, 39),
+                                  (576, 2, 3, 1, 1, 12, 39), (544, 32, 3, 1, 1, 24, 78), (96, 64, 3, 1, 16, 7, 16),
+                                  (32, 32, 1, 1, 1, 3, 5)])
 def test_conv_tf32_cluster_split_k_and_stride2(upf, case):
     """small grids split the K loop over a thread-block cluster (DSMEM reduction in rank order): same bits on every
     run, fp32-rounding agreement with the TF32-truncated oracle; stride 2 is walked by TMA element strides."""
@@ -329,6 +331,16 @@ def test_conv_tf32_cluster_split_k_and_stride2(upf, case):
     assert torch.equal(outs[0], outs[1])
     err = (outs[0].permute(0, 3, 1, 2).cpu() - (ref + res)).abs().max().item()
     assert err <= 5e-4, err
+    # the experimental small-grid policies (N narrowing + clusters of <= 8 / <= 16 CTAs, whole-row tiles) give the same result
+    # to rounding (another, equally fixed, summation order)
+    for cap in (8, 16):
+        _ext.load().upf_debug_conv_tc(cap)
+        try:
+            outc = torch.full((2, ref.shape[2], ref.shape[3], Cout), float("nan"), device="cuda")
+            upf.k_conv(a, wtc, _cuda(b), outc, k, stride, dil, 0.1, r, _ext.CONV_TF32)
+        finally:
+            _ext.load().upf_debug_conv_tc(0)
+        assert (outc - outs[0]).abs().max().item() <= 1e-4
 
 
 @pytest.mark.parametrize("shape,d", [((2, 32, 270, 480), 4), ((1, 16, 256, 512), 3), ((1, 36, 250, 480), 1), ((1, 64, 272, 448), 2),

@@ -14,7 +14,7 @@ from upflow_pytorch_b200.engine import DecoderEngine
 workload = sys.argv[1] if len(sys.argv) > 1 else "kitti_375x1242_b1"
 precision = sys.argv[2] if len(sys.argv) > 2 else "tf32"
 H, W, B = bench.WORKLOADS[workload]
-sd = bench.make_weights()
+sd = bench.load_weights()[0]
 eng = DecoderEngine({k: v.cuda() for k, v in sd.items()}, precision=precision)
 eng.overlap = False   # single stream: clean per-launch times
 im1, im2 = bench.synth_inputs(B, H, W, 1234)

@@ -58,6 +58,7 @@ struct TcParams {
   // every operand tile is fetched as several small TMA boxes (bw x bh output pixels / b_rows weight rows each):
   // one box is walked row by row (~10 ns per 128-byte row, measured), independent boxes proceed concurrently
   int bw, bh, nbx, nby, b_rows, nbb;
+  int a_bytes;                 // bytes one activation tile really brings in: TH * TW pixels x 128 B (<= TC_A_BYTES)
   float slope;
   int flags;                   // UPF_FLAG_ROUND_TF32: store the output rounded to the nearest TF32 value
   // weight-gradient mode (backward.cu): the "images" are the taps of ONE planar operand -- image n reads the same
@@ -161,7 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const uint32_t a_dst = smem_u32(base + (size_t)s * stage_bytes);
         const uint32_t b_dst = a_dst + TC_A_BYTES;
         const uint32_t fb = smem_u32(&full[s]);
-        mbar_expect_tx(fb, TC_A_BYTES + b_bytes);
+        mbar_expect_tx(fb, (uint32_t)p.a_bytes + b_bytes);
         const int kc = kb * TC_KC + (p.wgrad ? p.koffs[n] : 0);
         const int nn = p.wgrad ? 0 : n;
         for (int jy = 0; jy < p.nby; ++jy)
@@ -205,7 +206,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (p.splits == 1) {
       const int py = y0 + row / p.TW, px = x0 + row % p.TW;
-      const bool valid = (py < p.Ho) && (px < p.Wo);
+      const bool valid = (row < p.TH * p.TW) && (py < p.Ho) && (px < p.Wo);   // a tile may hold fewer than 128 pixels
       const size_t pix = ((size_t)n * p.Ho + py) * p.Wo + px;
       float* o = p.out + pix * p.ldo;
       const float* r = p.res ? p.res + pix * p.ldr : nullptr;
@@ -270,7 +271,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
       }
       const int py = y0 + row / p.TW, px = x0 + row % p.TW;
-      if (py < p.Ho && px < p.Wo) {
+      if (row < p.TH * p.TW && py < p.Ho && px < p.Wo) {
         const size_t pix = ((size_t)n * p.Ho + py) * p.Wo + px;
         store4(p, s_bias, co0, p.out + pix * p.ldo, p.res ? p.res + pix * p.ldr : nullptr, co0 + c4 * 4, acc, vec_out);
       }
@@ -359,13 +360,27 @@ int encode_cached(const MapKey& key, CUtensorMap* out, cuuint32_t rank, void* pt
   return 0;
 }
 
+// Small-grid policy.  0 (default) = K split over a cluster of <= 8 only.  8 / 16 = additionally narrow N tiles and whole-row
+// pixel tiles chosen by an operand-traffic cost model, clusters up to that size -- measured SLOWER on the KITTI forward
+// (2.855 vs 2.77 ms, tools/ab_conv_tc.py, profiles/r2_ab_conv_tc.txt): the coarse levels are bound by the serial
+// launch -> prologue -> first TMA -> commit -> epilogue chain, not by operand bandwidth.  Kept as an A/B switch.
+static int g_tc_cluster_cap = 0;
 static void pick_tile(int H, int W, int max_tw, int* TH, int* TW) {
-  // 128 pixels per tile; pick the shape (TW multiple of 8) wasting the fewest pixels
+  // <= 128 pixels per tile; pick the shape wasting the fewest pixels
   long long best = -1;
   for (int tw = 8; tw <= max_tw; tw <<= 1) {
     const int th = 128 / tw;
     const long long cover = (long long)((H + th - 1) / th) * ((W + tw - 1) / tw);
     if (best < 0 || cover < best || (cover == best && tw == 16)) { best = cover; *TH = th; *TW = tw; }
+  }
+  // whole image rows (TW = W, any width): the box is dense, so its pixels are consecutive 128-byte rows of the stage like
+  // any other tile's; the MMA reads 128 rows, the rows past TH*TW are never stored.  6x20 (the 1/64 level of a KITTI
+  // frame) is ONE tile per image instead of two half-empty ones.
+  if (W <= max_tw && W >= 4 && g_tc_cluster_cap != 0) {
+    int th = 128 / W;
+    if (th > H) th = H;
+    const long long cover = (H + th - 1) / th;
+    if (cover < best) { *TH = th; *TW = W; }
   }
 }
 
@@ -380,6 +395,34 @@ int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float*
 int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
                    const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
                    float slope, int flags, cudaStream_t st, int* taken);
+
+// Largest cluster the K split may use: 16 (non-portable size, opt-in per kernel) when the device schedules it, else 8.
+static int tc_max_cluster() {
+  static PerDeviceOnce once;
+  static int allowed[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 64) return 8;
+  if (once.need()) {
+    allowed[dev] = 8;
+    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(1, 1, 16);
+      cfg.blockDim = dim3(TC_THREADS);
+      cfg.dynamicSmemBytes = 210 * 1024;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 16;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, conv_tc_kernel, &cfg) == cudaSuccess && nclusters >= 8) allowed[dev] = 16;
+    }
+    (void)cudaGetLastError();
+    once.mark();
+  }
+  return allowed[dev] < g_tc_cluster_cap ? allowed[dev] : g_tc_cluster_cap;
+}
 
 static thread_local const int* g_tc_koffs = nullptr;      // set by conv_tc_wgrad_gemm around its call (per calling thread)
 static thread_local const int* g_tc_wsel = nullptr;
@@ -403,13 +446,51 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   const int Wo = (W + 2 * pad - dil * (ks - 1) - 1) / stride + 1;
   UPF_REQUIRE(Ho > 0 && Wo > 0, "conv_tc: empty output");
   const int cout_pad = (Cout + 15) & ~15;
-  const int ntiles_n = (cout_pad + 127) / 128;
-  const int BN = ((cout_pad + ntiles_n - 1) / ntiles_n + 15) & ~15;   // equal N tiles <= 128 wide (rows past cout_pad: TMA zero fill)
   const int kblocks = (Cin + TC_KC - 1) / TC_KC;
   const int cin_pad = kblocks * TC_KC;
   const int taps = ks * ks;
   int TH = 8, TW = 16;
   pick_tile(Ho, Wo, 256 / stride > 128 ? 128 : 256 / stride, &TH, &TW);   // TMA box extents are <= 256 elements
+  const int tiles_x = (Wo + TW - 1) / TW, tiles_y = (Ho + TH - 1) / TH;
+  const long long tiles = (long long)tiles_x * tiles_y * N;
+  const int iters_all = taps * kblocks;
+  const int a_bytes = TH * TW * 128;
+
+  // N tiling and K split.  Large grids: equal N tiles <= 128 wide, no split.  Small grids (the coarse pyramid levels: 2..30
+  // pixel tiles for 148 SMs) are bound by how fast ONE SM can pull its operands out of L2 (~58 B/clk measured,
+  // tools/microbench/tc_probe.cu): a CTA that walks `ips` K iterations receives ips * (activation tile + BN weight rows)
+  // bytes.  So the work is cut along N (narrow weight tiles: the activation tile is re-fetched per N tile, but by another
+  // SM) and along K (a thread-block cluster of up to 16 CTAs reduces its partial tiles through distributed shared memory
+  // in rank order), choosing the (N tiles, splits) pair with the smallest per-CTA cost that still fits one wave.
+  int ntiles_n = (cout_pad + 127) / 128;
+  int BN = ((cout_pad + ntiles_n - 1) / ntiles_n + 15) & ~15;   // rows past cout_pad: TMA zero fill
+  int splits = 1;
+  if (koffs) {
+    splits = 8;                                                   // weight gradient: K is the pixel index, 10^4..10^5 long
+    while (splits > 1 && iters_all / splits < 4) splits >>= 1;
+  } else if (g_tc_cluster_cap == 0) {
+    while (splits < 8 && tiles * ntiles_n * splits * 2 <= UPF_NUM_SMS && iters_all / (splits * 2) >= 3) splits *= 2;
+  } else if (tiles * ntiles_n * 2 <= UPF_NUM_SMS) {
+    const int max_cluster = tc_max_cluster();
+    double best = 1e30;
+    const int base_nt = ntiles_n;
+    const int cand_nt[4] = {base_nt, 2, 4, 8};
+    for (int ci = 0; ci < 4; ++ci) {
+      const int nt = cand_nt[ci];
+      if (ci > 0 && nt <= base_nt) continue;
+      const int bn = ((cout_pad + nt - 1) / nt + 15) & ~15;
+      if (nt > base_nt && (nt - 1) * bn >= cout_pad) break;     // an N tile would be empty
+      for (int sp = 1; sp <= max_cluster; sp <<= 1) {
+        if (tiles * nt * sp > UPF_NUM_SMS && !(nt == base_nt && sp == 1)) break;
+        const int ips_c = (iters_all + sp - 1) / sp;
+        if (sp > 1 && (ips_c < 2 || (sp - 1) * ips_c >= iters_all)) break;
+        const double load = (double)ips_c * (a_bytes + bn * 128) / 58.0;                 // cycles to receive the operands
+        const double reduce = sp > 1 ? 1500.0 + 40.0 * sp * (((128 / sp) * (bn / 4) + TC_THREADS - 1) / TC_THREADS) : 0.0;
+        const double cost = load + reduce;
+        if (cost < best * 0.97) { best = cost; ntiles_n = nt; BN = bn; splits = sp; }
+      }
+    }
+  }
 
   // sub-boxes: `box_rows` pixels each, either whole tile rows (TW <= box_rows) or a segment of one row
   const int box_rows = (g_tc_box_rows >= 8 && g_tc_box_rows <= 128) ? g_tc_box_rows : 128;
@@ -442,23 +523,17 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   TcParams p;
   p.out = out; p.ldo = ldo; p.res = res; p.ldr = ldr; p.bias = bias;
   p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.BN = BN;
-  p.TH = TH; p.TW = TW; p.tiles_x = (Wo + TW - 1) / TW; p.tiles_y = (Ho + TH - 1) / TH;
+  p.TH = TH; p.TW = TW; p.tiles_x = tiles_x; p.tiles_y = tiles_y;
   p.ks = ks; p.dil = dil; p.stride = stride; p.kblocks = kblocks;
   p.bw = bw; p.bh = bh; p.nbx = TW / bw; p.nby = TH / bh; p.b_rows = b_rows; p.nbb = BN / b_rows;
+  p.a_bytes = a_bytes;
   p.slope = slope;
   p.flags = flags;
   p.wgrad = koffs ? 1 : 0;
   for (int i = 0; i < 9; ++i) { p.koffs[i] = (koffs && i < N) ? koffs[i] : 0; p.wsel[i] = (koffs && g_tc_wsel && i < N) ? g_tc_wsel[i] : 0; }
   p.tmem_cols = BN <= 16 ? 32 : (BN <= 32 ? 64 : (BN <= 64 ? 128 : 256));   // two accumulators (one per MMA issuer)
   const int stage_bytes = TC_A_BYTES + ((BN * 128 + 1023) & ~1023);
-  const long long tiles = (long long)p.tiles_x * p.tiles_y * N;
   const long long ctas = tiles * ntiles_n;
-  // split-K over a cluster when the grid cannot fill the chip: the K loop (taps x channel blocks) is the only
-  // parallelism left at the coarse pyramid levels
-  const int iters_all = taps * kblocks;
-  int splits = 1;
-  while (splits < 8 && ctas * splits * 2 <= UPF_NUM_SMS && iters_all / (splits * 2) >= 3) splits *= 2;   // stay within one wave
-  if (koffs) { splits = 8; while (splits > 1 && iters_all / splits < 4) splits >>= 1; }   // weight gradient: K is the pixel index, 10^4..10^5 long
   int ips = (iters_all + splits - 1) / splits;
   while (splits > 1 && (splits - 1) * ips >= iters_all) { splits >>= 1; ips = (iters_all + splits - 1) / splits; }   // no empty CTA
   // stages: two CTAs per SM when the grid is large (epilogue/main-loop overlap across CTAs); a single
@@ -509,6 +584,12 @@ int conv_tc_wgrad_gemm(const float* xt, int ldk, const float* gt_packed, const f
 }
 
 }  // namespace upf
+
+// test / tuning hook: small-grid policy of conv_tc (0 = default, 8 / 16 = cost-model policy with that cluster cap)
+extern "C" int upf_debug_conv_tc(int max_cluster) {
+  upf::g_tc_cluster_cap = (max_cluster >= 0 && max_cluster <= 16) ? max_cluster : 0;
+  return 0;
+}
 
 extern "C" long long upf_conv_tc_packed_elems(int Cin, int Cout, int ksize) {
   const long long cin_pad = (Cin + 31) / 32 * 32, cout_pad = (Cout + 15) / 16 * 16;
