@@ -73,6 +73,18 @@ int upf_corr_lrelu_fwd(const float* f1, int ld1, const float* f2, int ld2,
                        const double* stats1, const double* stats2, int f2_batch_shift,
                        float slope, int flags, void* stream);
 
+/* a1+a2+a3 in the reference operator's OWN layout: planar ("NCHW") feature maps in, planar cost volume out
+ * (correlation_cuda.forward: input1, input2 [B,C,H,W] -> output [B,(2d+1)^2,H,W], correlation_cuda.cc:10-87;
+ * Corr_pyTorch.forward, utils/pytorch_correlation.py:27-50) -- no layout conversion on either side.
+ * pitch*[3] = {row pitch, plane (channel) pitch, image pitch} in ELEMENTS; a contiguous [N,C,H,W] tensor has
+ * {W, H*W, C*H*W}.  The operands travel by TMA: the pitches of f1 / f2 must be multiples of 4 elements and their base
+ * pointers 16-byte aligned (else UPF_ENOTSUP: convert to pixel-major and call upf_corr_lrelu_fwd); the output may have
+ * any pitches.
+ * out[n,(dy+d)*(2d+1)+(dx+d),y,x] = lrelu( (1/C) sum_c f1[n,c,y,x] * f2[(n+shift)%N,c,y+dy,x+dx] ), f2 zero outside. */
+int upf_corr_lrelu_fwd_planar(const float* f1, const long long* pitch1, const float* f2, const long long* pitch2,
+                              float* out, const long long* pitch_out, int N, int H, int W, int C, int max_disp,
+                              int f2_batch_shift, float slope, int flags, void* stream);
+
 /* a11: gradients of the (un-normalised) cost volume wrt f1 and f2.
  *   replaces correlation_cuda.backward (correlation_cuda.cc:89-167, kernels
  *   correlation_cuda_kernel.cu:116-300).  `out` is the saved forward output;

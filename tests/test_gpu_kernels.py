@@ -70,6 +70,41 @@ def test_corr_vs_oracle(upf, shape, d, layout):
     assert (out - ref).abs().max().item() <= 1e-5
 
 
+@pytest.mark.parametrize("shape,d", [((2, 32, 64, 96), 4), ((1, 32, 270, 480), 4), ((1, 7, 33, 36), 4), ((2, 196, 12, 40), 4),
+                                     ((1, 32, 50, 100), 1), ((1, 20, 70, 132), 2), ((1, 32, 45, 64), 3), ((1, 33, 31, 124), 3),
+                                     ((1, 32, 29, 248), 2), ((1, 4, 8, 4), 4), ((3, 64, 47, 156), 4), ((1, 5, 13, 244), 1)])
+def test_corr_planar_vs_oracle(upf, shape, d):
+    """corr_planar.cu: planar (NCHW) operands by TMA, outer-product register blocking, planar output by TMA stores --
+    vs the fp64 oracle; every displacement range it serves (d <= 4), ragged tiles, widths around the 120-column tile, channel counts that are not a multiple of the ring chunk,
+    LeakyReLU, the batch shift, and pitched (non-contiguous) operands and output."""
+    from upflow_pytorch_b200 import ops
+    f1, f2 = _regen(11, shape), _regen(12, shape)
+    N, C, H, W = shape
+    n = (2 * d + 1) ** 2
+    a, b = _cuda(f1), _cuda(f2)
+    out = torch.full((N, n, H, W), float("nan"), device="cuda")
+    ops.k_corr_planar(a, b, out, d, slope=0.1)
+    assert upf.last_kernel() == "corr_planar"
+    ref = O.correlation(f1.double(), f2.double(), d, 0.1).float()
+    assert (out.cpu() - ref).abs().max().item() <= 1e-5
+    # the public operator takes the same route for NCHW inputs (no layout conversion)
+    out2 = upf.correlation(a, b, d, leaky_slope=0.1)
+    if H * W >= ops.PLANAR_CORR_MIN_PIXELS:
+        assert upf.last_kernel() == "corr_planar" and out2.is_contiguous()
+        assert torch.equal(out2, out)
+    # pitched operands (a window of a larger buffer: row / plane / image pitches all differ from the dense ones) and a
+    # pitched output, image n against image (n + 1) % N
+    big1 = torch.zeros(N, C + 1, H + 2, W + 8, device="cuda"); big2 = torch.zeros_like(big1)
+    bigo = torch.full((N, n + 2, H + 1, W + 8), 7.0, device="cuda")
+    v1, v2, vo = big1[:, :C, 1:H + 1, 4:W + 4], big2[:, :C, 1:H + 1, 4:W + 4], bigo[:, 1:n + 1, :H, 4:W + 4]
+    v1.copy_(a); v2.copy_(b)
+    ops.k_corr_planar(v1, v2, vo, d, f2_shift=1 % N, slope=1.0)
+    ref = O.correlation(f1.double(), f2.double()[[(i + 1) % N for i in range(N)]], d).float()
+    assert (vo.cpu() - ref).abs().max().item() <= 1e-5
+    bigo[:, 1:n + 1, :H, 4:W + 4] = 7.0
+    assert (bigo == 7.0).all()          # nothing outside the window was written
+
+
 def test_corr_fused_norm_matches_two_step(upf):
     """normalize_features + correlation + LeakyReLU fused (what the engine runs) vs the oracle chain."""
     from upflow_pytorch_b200.ops import Slice

@@ -1,5 +1,5 @@
 """Run ONE kernel configuration a few times (target for `ncu --set full -k regex:...`).
-    python tools/run_kernel.py corr|conv [args]"""
+    python tools/run_kernel.py corr|corr_planar|conv [args]"""
 import os
 import sys
 
@@ -18,6 +18,13 @@ if what == "corr":
     out = torch.empty(N, h, w, 81, device="cuda")
     for _ in range(3):
         ops.k_corr(f1, f2, out, d, slope=0.1)
+elif what == "corr_planar":
+    N, C, h, w, d = 2, 32, 270, 480, int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    f1 = torch.randn(N, C, h, w, generator=g).cuda()
+    f2 = torch.randn(N, C, h, w, generator=g).cuda()
+    out = torch.empty(N, (2 * d + 1) ** 2, h, w, device="cuda")
+    for _ in range(3):
+        ops.k_corr_planar(f1, f2, out, d, slope=0.1)
 elif what == "conv":
     # estimator conv2 at KITTI 1/4 res: X[0:256] -> 128 channels, both directions stacked
     N, h, w = 2, int(sys.argv[5]) if len(sys.argv) > 5 else 94, int(sys.argv[6]) if len(sys.argv) > 6 else 311

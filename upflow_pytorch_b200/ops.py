@@ -89,6 +89,9 @@ def _as_slice(x):
     return x if isinstance(x, Slice) else Slice(x)
 
 
+PLANAR_CORR = True              # NCHW inputs with 16-byte pitches go to the planar kernel (False: always pixel-major)
+PLANAR_CORR_MIN_PIXELS = 16384  # smaller images: too few 120x4 tiles for 148 CTAs (measured: 47x156 29 vs 22 us pixel-major)
+
 # ---------------------------------------------------------------- launchers
 def k_corr(f1, f2, out, max_disp=4, stats1=None, stats2=None, f2_shift=0, slope=LRELU_SLOPE, round_tf32=False):
     f1, f2, out = _as_slice(f1), _as_slice(f2), _as_slice(out)
@@ -96,6 +99,29 @@ def k_corr(f1, f2, out, max_disp=4, stats1=None, stats2=None, f2_shift=0, slope=
     _ext.check(_lib().upf_corr_lrelu_fwd(f1.ptr(), f1.ld, f2.ptr(), f2.ld, out.ptr(), out.ld, f1.N, f1.H, f1.W, f1.C,
                                          max_disp, _p(stats1), _p(stats2), f2_shift, slope,
                                          _ext.FLAG_ROUND_TF32 if round_tf32 else 0, _stream()), "corr_lrelu_fwd")
+
+
+def last_kernel():
+    """kernel family that served this thread's most recent library call (upf_last_kernel)"""
+    return _lib().upf_last_kernel().decode()
+
+
+def _planar_ok(t):
+    """dense planar [N,C,H,W] whose row / plane / image pitches TMA can walk (multiples of 16 bytes)"""
+    return (t.dim() == 4 and t.dtype == torch.float32 and t.stride(3) == 1 and all(st % 4 == 0 for st in t.stride()[:3])
+            and t.stride(2) >= t.shape[3] and t.stride(1) >= t.stride(2) * t.shape[2] and t.stride(0) >= t.stride(1) * t.shape[1]
+            and t.data_ptr() % 16 == 0)
+
+
+def k_corr_planar(f1, f2, out, max_disp=4, f2_shift=0, slope=LRELU_SLOPE, round_tf32=False):
+    """planar (NCHW) feature maps -> planar cost volume [N,(2d+1)^2,H,W], no layout conversion (corr_planar.cu)."""
+    N, C, H, W = f1.shape
+    assert f2.shape == f1.shape and tuple(out.shape) == (N, (2 * max_disp + 1) ** 2, H, W)
+    assert _planar_ok(f1) and _planar_ok(f2) and _planar_ok(out) and max_disp <= 4
+    pit = [(_ext.ctypes.c_longlong * 3)(t.stride(2), t.stride(1), t.stride(0)) for t in (f1, f2, out)]
+    _ext.check(_lib().upf_corr_lrelu_fwd_planar(f1.data_ptr(), pit[0], f2.data_ptr(), pit[1], out.data_ptr(), pit[2],
+                                                N, H, W, C, max_disp, f2_shift, slope,
+                                                _ext.FLAG_ROUND_TF32 if round_tf32 else 0, _stream()), "corr_lrelu_fwd_planar")
 
 
 def k_corr_bwd(f1, f2, out, grad_out, grad_f1, grad_f2, max_disp=4, slope=1.0):
@@ -424,6 +450,12 @@ def correlation(in1, in2, max_disp=4, leaky_slope=None):
     _require_cuda(in1, in2)
     if in1.shape != in2.shape:
         raise RuntimeError("correlation: shape mismatch %s vs %s" % (tuple(in1.shape), tuple(in2.shape)))
+    if (PLANAR_CORR and max_disp in (3, 4) and not (torch.is_grad_enabled() and (in1.requires_grad or in2.requires_grad))
+            and _planar_ok(in1) and _planar_ok(in2) and in1.shape[2] * in1.shape[3] >= PLANAR_CORR_MIN_PIXELS):
+        # the reference operator's own layout, inference: planar in, planar out, no transposes (corr_planar.cu)
+        out = torch.empty(in1.shape[0], (2 * max_disp + 1) ** 2, in1.shape[2], in1.shape[3], device=in1.device, dtype=in1.dtype)
+        k_corr_planar(in1, in2, out, max_disp, slope=1.0 if leaky_slope is None else float(leaky_slope))
+        return out
     return _CorrelationFn.apply(in1, in2, max_disp, 1.0 if leaky_slope is None else float(leaky_slope))
 
 
