@@ -78,9 +78,11 @@ int upf_corr_lrelu_fwd(const float* f1, int ld1, const float* f2, int ld2,
  * Corr_pyTorch.forward, utils/pytorch_correlation.py:27-50) -- no layout conversion on either side.
  * pitch*[3] = {row pitch, plane (channel) pitch, image pitch} in ELEMENTS; a contiguous [N,C,H,W] tensor has
  * {W, H*W, C*H*W}.  The operands travel by TMA: the pitches of f1 / f2 must be multiples of 4 elements and their base
- * pointers 16-byte aligned (else UPF_ENOTSUP: convert to pixel-major and call upf_corr_lrelu_fwd); the output may have
- * any pitches.
- * out[n,(dy+d)*(2d+1)+(dx+d),y,x] = lrelu( (1/C) sum_c f1[n,c,y,x] * f2[(n+shift)%N,c,y+dy,x+dx] ), f2 zero outside. */
+ * pointers 16-byte aligned, and so must the output's (it leaves by TMA tensor stores); else UPF_ENOTSUP: convert to
+ * pixel-major and call upf_corr_lrelu_fwd.
+ * out[n,(dy+d)*(2d+1)+(dx+d),y,x] = lrelu( (1/C) sum_c f1[n,c,y,x] * f2[(n+shift)%N,c,y+dy,x+dx] ), f2 zero outside.
+ * max_disp <= 4 (5, 6: UPF_ENOTSUP, use the pixel-major entry point).  Bits 8..13 of `flags` are ablation switches of
+ * this kernel for tools/dbg_planar_time.py (they skip phases; never set them in production). */
 int upf_corr_lrelu_fwd_planar(const float* f1, const long long* pitch1, const float* f2, const long long* pitch2,
                               float* out, const long long* pitch_out, int N, int H, int W, int C, int max_disp,
                               int f2_batch_shift, float slope, int flags, void* stream);

@@ -43,6 +43,8 @@ namespace upf {
 #ifndef UPF_PL_CC4
 #define UPF_PL_CC4 4
 #endif
+// ablation switches in `flags` (tools/dbg_planar_time.py; results are garbage with any of them set)
+constexpr int PL_DBG_NO_FMA = 0x100, PL_DBG_NO_LOADS = 0x200, PL_DBG_NO_STORE = 0x800, PL_DBG_NO_EPILOGUE = 0x2000;
 constexpr int PL_COLS = 128;   // f2 columns per warp row: 32 lanes x one 16-byte column quad
 
 template <int D>
@@ -144,7 +146,7 @@ corr_planar_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
   // requesting warp does not wait (refilling the slot of chunk it-1 would make it wait for the slowest warp and then be the
   // slowest itself: request + compute in series again).  S-2 chunks are in flight.
   constexpr int AHEAD = S - 2;
-  if (!(flags & 0x200) && lane == 0 && warp < AHEAD && warp < total_chunks) issue(warp);
+  if (!(flags & PL_DBG_NO_LOADS) && lane == 0 && warp < AHEAD && warp < total_chunks) issue(warp);
   int next_issue = AHEAD;                                // chunk requested at the top of the next iteration ...
   int turn = AHEAD % K::NW;                              // ... by this warp
 
@@ -161,15 +163,15 @@ corr_planar_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
         for (int j = 0; j < 4; ++j) acc[r][q][j] = 0.f;
     for (int chunk = 0; chunk < nchunks; ++chunk) {
       // refill: the chunk S-1 ahead goes to the slot the previous chunk has just left
-      if (turn == warp && lane == 0 && next_issue < total_chunks && !(flags & 0x200)) issue(next_issue);
+      if (turn == warp && lane == 0 && next_issue < total_chunks && !(flags & PL_DBG_NO_LOADS)) issue(next_issue);
       ++next_issue;
       if (++turn == K::NW) turn = 0;
       __syncwarp();
-      if (!(flags & 0x200)) mbar_wait(full0 + slot * 8, phase);
+      if (!(flags & PL_DBG_NO_LOADS)) mbar_wait(full0 + slot * 8, phase);
       const float* st = smem + slot * K::STAGE_FLOATS;
       const float* st2 = st + off2;
       const float* st1 = st + off1;
-      if (!(flags & 0x100))
+      if (!(flags & PL_DBG_NO_FMA))
 #pragma unroll
       for (int c = 0; c < CC; ++c) {
         float a[12];                                     // f1 columns q-4 .. q+7 of this thread's row
@@ -253,12 +255,12 @@ corr_planar_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
     const bool fast = pow2 && slope >= 0.f && slope <= 1.f && !(flags & UPF_FLAG_ROUND_TF32);
     // two stores per tile (the staging tile holds half of the horizontal displacements): the first is read by the copy
     // engine while the warp converts the second half, the second under the next tile's FMA loop
-    if (flags & 0x2000) continue;
+    if (flags & PL_DBG_NO_EPILOGUE) continue;
     if (fast) epilogue(std::true_type{}, std::false_type{}); else epilogue(std::false_type{}, std::false_type{});
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic writes -> TMA store reads
     __syncwarp();
     if (lane == 0) {
-      if (row_ok && !(flags & 0x800)) tma_store_5d(&mapo, smem_u32(wst), x0, y0 + yy, 0, g * R, n);
+      if (row_ok && !(flags & PL_DBG_NO_STORE)) tma_store_5d(&mapo, smem_u32(wst), x0, y0 + yy, 0, g * R, n);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
@@ -266,7 +268,7 @@ corr_planar_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
     if (fast) epilogue(std::true_type{}, std::true_type{}); else epilogue(std::false_type{}, std::true_type{});
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
-    if (lane == 0 && row_ok && !(flags & 0x800)) {
+    if (lane == 0 && row_ok && !(flags & PL_DBG_NO_STORE)) {
       tma_store_5d(&mapo2, smem_u32(wst), x0, y0 + yy, K::QA, g * R, n);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
