@@ -87,6 +87,19 @@ int upf_corr_lrelu_fwd_planar(const float* f1, const long long* pitch1, const fl
                               float* out, const long long* pitch_out, int N, int H, int W, int C, int max_disp,
                               int f2_batch_shift, float slope, int flags, void* stream);
 
+/* fp16 / bf16 STORAGE variants (the reference dispatches its correlation on Half too,
+ * correlation_cuda_kernel.cu:352; F.grid_sample takes half tensors).  Tensors are pixel-major 2-byte elements (pitches in
+ * ELEMENTS), every product and sum is fp32, one rounding at the store.  dtype: UPF_DTYPE_F16 / UPF_DTYPE_BF16.
+ * Same semantics as upf_corr_lrelu_fwd / upf_warp_fwd otherwise (the flow, the mask arithmetic and the moments are fp32). */
+#define UPF_DTYPE_F16 1
+#define UPF_DTYPE_BF16 2
+int upf_corr_lrelu_fwd_lp(const void* f1, int ld1, const void* f2, int ld2, void* out, int ldo, int dtype,
+                          int N, int H, int W, int C, int max_disp, const double* stats1, const double* stats2,
+                          int f2_batch_shift, float slope, void* stream);
+int upf_warp_fwd_lp(const void* x, int ldx, const float* flow, int ldf, void* out, int ldo, int dtype,
+                    int N, int H, int W, int C, int align_corners, float mask_threshold, int x_batch_shift,
+                    double* stats, void* stream);
+
 /* a11: gradients of the (un-normalised) cost volume wrt f1 and f2.
  *   replaces correlation_cuda.backward (correlation_cuda.cc:89-167, kernels
  *   correlation_cuda_kernel.cu:116-300).  `out` is the saved forward output;

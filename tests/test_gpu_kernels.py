@@ -105,6 +105,45 @@ def test_corr_planar_vs_oracle(upf, shape, d):
     assert (bigo == 7.0).all()          # nothing outside the window was written
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape,d", [((2, 32, 40, 100), 4), ((1, 64, 24, 78), 4), ((1, 7, 9, 33), 3), ((1, 32, 37, 65), 6),
+                                     ((1, 36, 30, 40), 2), ((2, 196, 6, 20), 4)])
+def test_corr_warp_low_precision_storage(upf, shape, d, dtype):
+    """SURVEY 8f rank 4 (the reference dispatches its correlation on Half, correlation_cuda_kernel.cu:352): fp16 / bf16
+    STORAGE of the correlation's operands and result and of the warp's source and result, fp32 arithmetic.  Oracle: the
+    fp64 routine on the SAME rounded operands; stated tolerance: one rounding of the result to the storage type
+    (2^-11 relative for fp16, 2^-8 for bf16) plus the fp32 accumulation error."""
+    from upflow_pytorch_b200 import ops
+    eps = 2.0 ** -11 if dtype == torch.float16 else 2.0 ** -8
+    f1, f2 = _regen(21, shape).to(dtype), _regen(22, shape).to(dtype)
+    out = upf.correlation(_cuda(f1), _cuda(f2), d, leaky_slope=0.1)
+    assert out.dtype == dtype and upf.last_kernel() == "corr_fwd"
+    ref = O.correlation(f1.double(), f2.double(), d, 0.1)
+    err = (out.cpu().double() - ref).abs()
+    assert (err <= eps * ref.abs() + 2e-6).all(), err.max().item()
+    # channels_last input (no layout copy), a channel slice of a wider buffer as the output, the batch shift
+    N, C, H, W = shape
+    a = _cuda(f1).contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+    b = _cuda(f2).contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+    n = (2 * d + 1) ** 2
+    X = torch.full((N, H, W, n + 7), 3.0, device="cuda", dtype=dtype)
+    ops.k_corr_lp(a, b, X[..., :n], d, f2_shift=N - 1, slope=1.0)
+    ref = O.correlation(f1.double(), f2.double()[[(i + N - 1) % N for i in range(N)]], d)
+    err = (X[..., :n].permute(0, 3, 1, 2).cpu().double() - ref).abs()
+    assert (err <= eps * ref.abs() + 2e-6).all(), err.max().item()
+    assert (X[..., n:] == 3.0).all()
+    # warp: fp32 flow, half source and result; the mask is the fp32 kernel's (same coordinates), values within one rounding
+    flow = (torch.randn(N, 2, H, W, generator=torch.Generator().manual_seed(5)) * 3.0)
+    w_lp = upf.warp(_cuda(f1), _cuda(flow))
+    w_32 = upf.warp(_cuda(f1.float()), _cuda(flow))
+    assert w_lp.dtype == dtype
+    assert torch.equal(w_lp == 0, (w_32 == 0) | (w_lp == 0)) and torch.equal((w_32 == 0), (w_32 == 0) & (w_lp == 0))
+    err = (w_lp.float() - w_32).abs()
+    assert (err <= eps * w_32.abs() + 1e-7).all(), err.max().item()
+    with pytest.raises(RuntimeError):
+        upf.correlation(_cuda(f1), _cuda(f2.float()), d)
+
+
 def test_corr_fused_norm_matches_two_step(upf):
     """normalize_features + correlation + LeakyReLU fused (what the engine runs) vs the oracle chain."""
     from upflow_pytorch_b200.ops import Slice

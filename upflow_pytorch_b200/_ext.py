@@ -22,6 +22,8 @@ SIGNATURES = {
     "upf_last_kernel": (_c.c_char_p, []),
     "upf_corr_lrelu_fwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _F, _I, _P]),
     "upf_corr_lrelu_fwd_planar": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P]),
+    "upf_corr_lrelu_fwd_lp": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _F, _P]),
+    "upf_warp_fwd_lp": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P]),
     "upf_corr_lrelu_bwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "upf_warp_fwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _I, _P]),
     "upf_warp_bwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
@@ -75,6 +77,7 @@ CONV_FP32 = 0
 CONV_TF32 = 1
 CONV_ROUND_OUT = 0x100       # OR-ed into the precision: store the output rounded to the nearest TF32 value
 FLAG_ROUND_TF32 = 1
+DTYPE_F16, DTYPE_BF16 = 1, 2      # UPF_DTYPE_* (low-precision storage variants)
 ABI_VERSION = 2
 PW_LRELU_BWD, PW_SIGMOID, PW_SIGMOID_BWD = 0, 1, 2
 LOSS_KINDS = {"abs_robust": 0, "charbonnier": 1, "L1": 2}

@@ -56,13 +56,13 @@ __device__ __forceinline__ int swz(int pos, int chunk) { return pos * 32 + (((ch
 // is applied in registers; out-of-image positions and channels >= C are written as zeros (= the zero
 // padding of the correlation AFTER normalisation, as in the reference).
 constexpr int CORR_LB = 4;
-template <int NT, int COLS, bool VEC>
-__device__ __forceinline__ void corr_stage(float* __restrict__ dst, const float* __restrict__ src, int ld,
+template <int NT, int COLS, bool VEC, typename T>
+__device__ __forceinline__ void corr_stage(float* __restrict__ dst, const T* __restrict__ src, int ld,
                                            int n, int H, int W, int C, int c0, int y_org, int x_org,
                                            int npos, const float* __restrict__ mean, const float* __restrict__ rstd,
                                            bool norm) {
   const int units = npos * 8;
-  const float* img = src + (size_t)n * H * W * ld;
+  const T* img = src + (size_t)n * H * W * ld;
   for (int u0 = threadIdx.x; u0 < units; u0 += NT * CORR_LB) {
     float4 v[CORR_LB];
     bool ok[CORR_LB];
@@ -76,14 +76,14 @@ __device__ __forceinline__ void corr_stage(float* __restrict__ dst, const float*
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       ok[i] = u < units && y >= 0 && y < H && x >= 0 && x < W && c < C;
       if (ok[i]) {
-        const float* p = img + ((size_t)y * W + x) * ld + c;
+        const T* p = img + ((size_t)y * W + x) * ld + c;
         if (VEC) {
-          v[i] = ldg4(p);
+          v[i] = ld4(p);
         } else {
-          v[i].x = __ldg(p);
-          if (c + 1 < C) v[i].y = __ldg(p + 1);
-          if (c + 2 < C) v[i].z = __ldg(p + 2);
-          if (c + 3 < C) v[i].w = __ldg(p + 3);
+          v[i].x = ld1(p);
+          if (c + 1 < C) v[i].y = ld1(p + 1);
+          if (c + 2 < C) v[i].z = ld1(p + 2);
+          if (c + 3 < C) v[i].w = ld1(p + 3);
         }
       }
     }
@@ -104,14 +104,14 @@ __device__ __forceinline__ void corr_stage(float* __restrict__ dst, const float*
   }
 }
 
-template <int D, bool VEC>
+template <int D, bool VEC, typename T>
 // (__maxnreg__ instead of a min-blocks hint: ptxas otherwise settles on 96 registers and spills accumulators
 // inside the channel loop; 112 x 288 threads x 2 CTAs = 64512 registers still fits the SM; registers are granted per warp in units of 512,
 // so the single-CTA 13-warp variant (d = 6) gets 144, not 152)
 // (measured: the 13-warp d = 6 variant launches with 128 registers and fails with 144)
 __global__ void __launch_bounds__(CorrCfg<D>::NT) __maxnreg__(CorrCfg<D>::MIN_CTAS == 2 ? 112 : 128)
-corr_fwd_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__ f2, int ld2,
-                float* __restrict__ out, int ldo, int H, int W, int C,
+corr_fwd_kernel(const T* __restrict__ f1, int ld1, const T* __restrict__ f2, int ld2,
+                T* __restrict__ out, int ldo, int H, int W, int C,
                 const double* __restrict__ stats1, const double* __restrict__ stats2,
                 float slope, int flags, int tiles_x, int tiles_y, int n2_shift, int N) {
   pdl_prologue();
@@ -157,9 +157,9 @@ corr_fwd_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__
       }
       __syncthreads();
     }
-    corr_stage<K::NT, K::HCOLS, VEC>(s_f2, f2, ld2, n2, H, W, C, c0, y0 - D, x0 - D, K::HPOS,
+    corr_stage<K::NT, K::HCOLS, VEC, T>(s_f2, f2, ld2, n2, H, W, C, c0, y0 - D, x0 - D, K::HPOS,
                                      s_stat + 2 * CORR_CC, s_stat + 3 * CORR_CC, norm);
-    corr_stage<K::NT, CORR_TX, VEC>(s_f1, f1, ld1, n, H, W, C, c0, y0, x0, K::F1POS, s_stat, s_stat + CORR_CC, norm);
+    corr_stage<K::NT, CORR_TX, VEC, T>(s_f1, f1, ld1, n, H, W, C, c0, y0, x0, K::F1POS, s_stat, s_stat + CORR_CC, norm);
     __syncthreads();
 
     const int cend = (C - c0 < CORR_CC ? C - c0 : CORR_CC);
@@ -211,35 +211,35 @@ corr_fwd_kernel(const float* __restrict__ f1, int ld1, const float* __restrict__
   for (int r = 0; r < CORR_TY; ++r) {
     const int y = y0 + r;
     if (y >= H) break;
-    float* orow = out + ((size_t)((size_t)n * H + y) * W + x0) * ldo;
+    T* orow = out + ((size_t)((size_t)n * H + y) * W + x0) * ldo;
     const float* srow = s_out + r * CORR_TX * K::NOUT;
     if (ldo == K::NOUT) {
-      for (int e = threadIdx.x; e < total; e += K::NT) orow[e] = srow[e];       // one contiguous run
+      for (int e = threadIdx.x; e < total; e += K::NT) st1(orow + e, srow[e]);       // one contiguous run
     } else {
       for (int e = threadIdx.x; e < total; e += K::NT) {
         const int px = e / K::NOUT, k = e - px * K::NOUT;
-        orow[(size_t)px * ldo + k] = srow[e];
+        st1(orow + (size_t)px * ldo + k, srow[e]);
       }
     }
   }
 }
 
-template <int D>
-static int launch_corr_fwd(const float* f1, int ld1, const float* f2, int ld2, float* out, int ldo,
+template <int D, typename T = float>
+static int launch_corr_fwd(const T* f1, int ld1, const T* f2, int ld2, T* out, int ldo,
                            int N, int H, int W, int C, const double* s1, const double* s2, int shift,
                            float slope, int flags, cudaStream_t st) {
   using K = CorrCfg<D>;
   const int tiles_x = (W + CORR_TX - 1) / CORR_TX, tiles_y = (H + CORR_TY - 1) / CORR_TY;
   const long long tiles = (long long)tiles_x * tiles_y * N;
   UPF_REQUIRE(tiles > 0 && tiles < (1ll << 31), "corr: bad tile count %lld", tiles);
-  const bool vec = (C % 4 == 0) && (ld1 % 4 == 0) && (ld2 % 4 == 0) && aligned16(f1) && aligned16(f2);
+  const bool vec = (C % 4 == 0) && (ld1 % 4 == 0) && (ld2 % 4 == 0) && aligned_vec4<T>(f1) && aligned_vec4<T>(f2);
   // opt in to >48 KB dynamic shared memory once per instantiation (per device would need a table: one
   // process drives one GPU here)
   static PerDeviceOnce attr_done;
   if (attr_done.need()) {
-    cudaError_t e = cudaFuncSetAttribute(corr_fwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(corr_fwd_kernel<D, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(corr_fwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
+      e = cudaFuncSetAttribute(corr_fwd_kernel<D, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("corr smem attr: %s", cudaGetErrorString(e));
       return (int)e;
@@ -247,10 +247,10 @@ static int launch_corr_fwd(const float* f1, int ld1, const float* f2, int ld2, f
     attr_done.mark();
   }
   if (vec) {
-    UPF_LAUNCH((corr_fwd_kernel<D, true>), (unsigned)tiles, K::NT, K::SMEM_BYTES, st, f1, ld1, f2, ld2, out, ldo, H, W, C, s1, s2,
+    UPF_LAUNCH((corr_fwd_kernel<D, true, T>), (unsigned)tiles, K::NT, K::SMEM_BYTES, st, f1, ld1, f2, ld2, out, ldo, H, W, C, s1, s2,
                                                                           slope, flags, tiles_x, tiles_y, shift, N);
   } else {
-    UPF_LAUNCH((corr_fwd_kernel<D, false>), (unsigned)tiles, K::NT, K::SMEM_BYTES, st, f1, ld1, f2, ld2, out, ldo, H, W, C, s1,
+    UPF_LAUNCH((corr_fwd_kernel<D, false, T>), (unsigned)tiles, K::NT, K::SMEM_BYTES, st, f1, ld1, f2, ld2, out, ldo, H, W, C, s1,
                                                                            s2, slope, flags, tiles_x, tiles_y, shift, N);
   }
   return check_launch("corr_fwd");
@@ -466,6 +466,42 @@ extern "C" int upf_corr_lrelu_fwd(const float* f1, int ld1, const float* f2, int
     case 6: return launch_corr_fwd<6>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, stats1, stats2, f2_batch_shift, slope, flags, st);
     default: set_error("corr: max_disp %d not in 1..6", max_disp); return UPF_ENOTSUP;
   }
+}
+
+// fp16 / bf16 STORAGE: the tiled kernel with T -> fp32 conversion while staging and fp32 -> T at the
+// store; every product and sum is fp32, as in the reference's Half dispatch (accumulation in float,
+// correlation_cuda_kernel.cu:15-114 with scalar_t = Half)
+template <typename T>
+static int corr_fwd_lp(const void* f1, int ld1, const void* f2, int ld2, void* out, int ldo, int N, int H, int W, int C, int max_disp,
+                       const double* s1, const double* s2, int shift, float slope, cudaStream_t st) {
+  using namespace upf;
+  const T *a = static_cast<const T*>(f1), *b = static_cast<const T*>(f2);
+  T* o = static_cast<T*>(out);
+  switch (max_disp) {
+    case 1: return launch_corr_fwd<1, T>(a, ld1, b, ld2, o, ldo, N, H, W, C, s1, s2, shift, slope, 0, st);
+    case 2: return launch_corr_fwd<2, T>(a, ld1, b, ld2, o, ldo, N, H, W, C, s1, s2, shift, slope, 0, st);
+    case 3: return launch_corr_fwd<3, T>(a, ld1, b, ld2, o, ldo, N, H, W, C, s1, s2, shift, slope, 0, st);
+    case 4: return launch_corr_fwd<4, T>(a, ld1, b, ld2, o, ldo, N, H, W, C, s1, s2, shift, slope, 0, st);
+    case 5: return launch_corr_fwd<5, T>(a, ld1, b, ld2, o, ldo, N, H, W, C, s1, s2, shift, slope, 0, st);
+    default: return launch_corr_fwd<6, T>(a, ld1, b, ld2, o, ldo, N, H, W, C, s1, s2, shift, slope, 0, st);
+  }
+}
+
+extern "C" int upf_corr_lrelu_fwd_lp(const void* f1, int ld1, const void* f2, int ld2, void* out, int ldo, int dtype,
+                                     int N, int H, int W, int C, int max_disp, const double* stats1, const double* stats2,
+                                     int f2_batch_shift, float slope, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(f1 && f2 && out, "corr_lp: null tensor");
+  UPF_REQUIRE(dtype == UPF_DTYPE_F16 || dtype == UPF_DTYPE_BF16, "corr_lp: dtype must be UPF_DTYPE_F16 or UPF_DTYPE_BF16");
+  UPF_REQUIRE(f2_batch_shift >= 0 && f2_batch_shift < N, "corr_lp: batch shift out of range");
+  UPF_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "corr_lp: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
+  UPF_REQUIRE(max_disp >= 1 && max_disp <= 6, "corr_lp: max_disp %d not in 1..6", max_disp);
+  UPF_REQUIRE(ld1 >= C && ld2 >= C && ldo >= (2 * max_disp + 1) * (2 * max_disp + 1), "corr_lp: pitch too small");
+  UPF_REQUIRE((stats1 == nullptr) == (stats2 == nullptr), "corr_lp: give both stats or neither");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == UPF_DTYPE_F16)
+    return corr_fwd_lp<__half>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, max_disp, stats1, stats2, f2_batch_shift, slope, st);
+  return corr_fwd_lp<__nv_bfloat16>(f1, ld1, f2, ld2, out, ldo, N, H, W, C, max_disp, stats1, stats2, f2_batch_shift, slope, st);
 }
 
 extern "C" int upf_corr_lrelu_bwd(const float* f1, int ld1, const float* f2, int ld2, const float* out, int ldo,

@@ -1,6 +1,8 @@
 // Shared host/device helpers for the upflow_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -86,6 +88,40 @@ __host__ __device__ __forceinline__ float round_tf32(float v) {
 __device__ __forceinline__ float maybe_round(float v, int flags) { return (flags & UPF_FLAG_ROUND_TF32) ? round_tf32(v) : v; }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// ---- storage types of the low-precision variants (fp16 / bf16 STORAGE, fp32 arithmetic; the reference
+// dispatches its correlation kernels on Half too, correlation_cuda_kernel.cu:352).  ld4 / st4: four consecutive elements
+// (16-byte aligned for float, 8-byte for the 2-byte types); ld1 / st1: one element.
+__device__ __forceinline__ float4 ld4(const float* p) { return ldg4(p); }
+__device__ __forceinline__ float4 ld4(const __half* p) {
+  const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));      // bf16 -> fp32 is a 16-bit shift
+  return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                     __uint_as_float(r.y & 0xffff0000u));
+}
+__device__ __forceinline__ float ld1(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld1(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ float ld1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(__half* p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__half* p, float4 v) {
+  const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  uint2 r; r.x = *reinterpret_cast<const unsigned*>(&a); r.y = *reinterpret_cast<const unsigned*>(&b);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 r; r.x = *reinterpret_cast<const unsigned*>(&a); r.y = *reinterpret_cast<const unsigned*>(&b);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+// vector accesses of T need 4 * sizeof(T) alignment
+template <typename T> inline bool aligned_vec4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & (4 * sizeof(T) - 1)) == 0; }
 
 // mean / rstd of one (image, channel) from accumulated double sums; the
 // reference uses torch.mean and the UNBIASED torch.var (model/upflow.py:113-114)

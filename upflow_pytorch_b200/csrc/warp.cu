@@ -53,10 +53,10 @@ __device__ __forceinline__ void cta_reduce_moments(const float (&sm)[2][4], cons
 // thread layout: `lpp` lanes per pixel (each lane owns 4 consecutive channels
 // per pass), WARP_NT/lpp pixels per CTA step; a CTA strides over the pixels of
 // ONE image so the moment reduction stays per image.
-template <bool VEC>
+template <bool VEC, typename T = float>
 __global__ void __launch_bounds__(WARP_NT)
-warp_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ flow, int ldf,
-                float* __restrict__ out, int ldo, int H, int W, int C, int align_corners, float mask_thr,
+warp_fwd_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ flow, int ldf,
+                T* __restrict__ out, int ldo, int H, int W, int C, int align_corners, float mask_thr,
                 double* __restrict__ stats, int lpp, int ctas_per_image, int x_shift, int N, int oflags) {
   pdl_prologue();
   extern __shared__ double s_red[];   // [2][cgroups*4] when stats
@@ -109,11 +109,11 @@ warp_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ 
     t.in_nw = flags & 1; t.in_ne = flags & 2; t.in_sw = flags & 4; t.in_se = flags & 8;
     const bool keep = (flags & 16) != 0;
     if (!live) continue;
-    const float* r_nw = x + (ximg + (long long)t.y0 * W + t.x0) * (long long)ldx;   // may point outside: only dereferenced when in_*
-    const float* r_ne = r_nw + ldx;
-    const float* r_sw = r_nw + (size_t)W * ldx;
-    const float* r_se = r_sw + ldx;
-    float* o = out + (img + p) * ldo;
+    const T* r_nw = x + (ximg + (long long)t.y0 * W + t.x0) * (long long)ldx;   // may point outside: only dereferenced when in_*
+    const T* r_ne = r_nw + ldx;
+    const T* r_sw = r_nw + (size_t)W * ldx;
+    const T* r_se = r_sw + ldx;
+    T* o = out + (img + p) * ldo;
 #pragma unroll 2
     for (int pass = 0; pass < passes; ++pass) {
       const int c = (pass * lpp + sub) * 4;
@@ -122,32 +122,32 @@ warp_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ 
       if (keep) {
         // same accumulation order as ATen's grid_sampler_2d: nw, ne, sw, se
         if (VEC) {
-          if (t.in_nw) { float4 q = ldg4(r_nw + c); acc.x = fmaf(q.x, t.w_nw, acc.x); acc.y = fmaf(q.y, t.w_nw, acc.y); acc.z = fmaf(q.z, t.w_nw, acc.z); acc.w = fmaf(q.w, t.w_nw, acc.w); }
-          if (t.in_ne) { float4 q = ldg4(r_ne + c); acc.x = fmaf(q.x, t.w_ne, acc.x); acc.y = fmaf(q.y, t.w_ne, acc.y); acc.z = fmaf(q.z, t.w_ne, acc.z); acc.w = fmaf(q.w, t.w_ne, acc.w); }
-          if (t.in_sw) { float4 q = ldg4(r_sw + c); acc.x = fmaf(q.x, t.w_sw, acc.x); acc.y = fmaf(q.y, t.w_sw, acc.y); acc.z = fmaf(q.z, t.w_sw, acc.z); acc.w = fmaf(q.w, t.w_sw, acc.w); }
-          if (t.in_se) { float4 q = ldg4(r_se + c); acc.x = fmaf(q.x, t.w_se, acc.x); acc.y = fmaf(q.y, t.w_se, acc.y); acc.z = fmaf(q.z, t.w_se, acc.z); acc.w = fmaf(q.w, t.w_se, acc.w); }
+          if (t.in_nw) { float4 q = ld4(r_nw + c); acc.x = fmaf(q.x, t.w_nw, acc.x); acc.y = fmaf(q.y, t.w_nw, acc.y); acc.z = fmaf(q.z, t.w_nw, acc.z); acc.w = fmaf(q.w, t.w_nw, acc.w); }
+          if (t.in_ne) { float4 q = ld4(r_ne + c); acc.x = fmaf(q.x, t.w_ne, acc.x); acc.y = fmaf(q.y, t.w_ne, acc.y); acc.z = fmaf(q.z, t.w_ne, acc.z); acc.w = fmaf(q.w, t.w_ne, acc.w); }
+          if (t.in_sw) { float4 q = ld4(r_sw + c); acc.x = fmaf(q.x, t.w_sw, acc.x); acc.y = fmaf(q.y, t.w_sw, acc.y); acc.z = fmaf(q.z, t.w_sw, acc.z); acc.w = fmaf(q.w, t.w_sw, acc.w); }
+          if (t.in_se) { float4 q = ld4(r_se + c); acc.x = fmaf(q.x, t.w_se, acc.x); acc.y = fmaf(q.y, t.w_se, acc.y); acc.z = fmaf(q.z, t.w_se, acc.z); acc.w = fmaf(q.w, t.w_se, acc.w); }
         } else {
           float* a = &acc.x;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             if (c + k < C) {
               float s = 0.f;
-              if (t.in_nw) s = fmaf(__ldg(r_nw + c + k), t.w_nw, s);
-              if (t.in_ne) s = fmaf(__ldg(r_ne + c + k), t.w_ne, s);
-              if (t.in_sw) s = fmaf(__ldg(r_sw + c + k), t.w_sw, s);
-              if (t.in_se) s = fmaf(__ldg(r_se + c + k), t.w_se, s);
+              if (t.in_nw) s = fmaf(ld1(r_nw + c + k), t.w_nw, s);
+              if (t.in_ne) s = fmaf(ld1(r_ne + c + k), t.w_ne, s);
+              if (t.in_sw) s = fmaf(ld1(r_sw + c + k), t.w_sw, s);
+              if (t.in_se) s = fmaf(ld1(r_se + c + k), t.w_se, s);
               a[k] = s;
             }
         }
       }
       if (oflags & UPF_FLAG_ROUND_TF32) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
       if (VEC) {
-        *reinterpret_cast<float4*>(o + c) = acc;
+        st4(o + c, acc);
       } else {
         const float* a = &acc.x;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (c + k < C) o[c + k] = a[k];
+          if (c + k < C) st1(o + c + k, a[k]);
       }
       if (stats && pass < 2) {
         sm[pass][0] += acc.x; sm[pass][1] += acc.y; sm[pass][2] += acc.z; sm[pass][3] += acc.w;
@@ -384,10 +384,11 @@ occ_check_kernel(const float* __restrict__ flow, int ldf, float* __restrict__ oc
 
 }  // namespace upf
 
-extern "C" int upf_warp_fwd(const float* x, int ldx, const float* flow, int ldf, float* out, int ldo,
-                            int N, int H, int W, int C, int align_corners, float mask_threshold, int x_batch_shift,
-                            double* stats, int flags, void* stream) {
-  using namespace upf;
+namespace upf {
+template <typename T>
+static int warp_fwd_launch(const T* x, int ldx, const float* flow, int ldf, T* out, int ldo,
+                           int N, int H, int W, int C, int align_corners, float mask_threshold, int x_batch_shift,
+                           double* stats, int flags, void* stream) {
   UPF_REQUIRE(x && flow && out, "warp: null tensor");
   UPF_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && ldx >= C && ldo >= C && ldf >= 2, "warp: bad shape");
   UPF_REQUIRE(stats == nullptr || C <= 256, "warp: fused moments need C <= 256");
@@ -402,15 +403,38 @@ extern "C" int upf_warp_fwd(const float* x, int ldx, const float* flow, int ldf,
   const int cap = stats ? UPF_NUM_SMS * 2 : UPF_NUM_SMS * 8;
   if (per_image > cap) per_image = cap;
   if (per_image < 1) per_image = 1;
-  const bool vec = (C % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(x) && aligned16(out);
+  const bool vec = (C % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned_vec4<T>(x) && aligned_vec4<T>(out);
   const size_t smem = stats ? (size_t)(WARP_NT / 32) * 2 * ((C + 3) / 4) * 4 * sizeof(double) : 0;
   if (vec)
-    UPF_LAUNCH((warp_fwd_kernel<true>), N * per_image, WARP_NT, smem, (cudaStream_t)stream, x, ldx, flow, ldf, out, ldo, H, W, C,
+    UPF_LAUNCH((warp_fwd_kernel<true, T>), N * per_image, WARP_NT, smem, (cudaStream_t)stream, x, ldx, flow, ldf, out, ldo, H, W, C,
                                                                                  align_corners, mask_threshold, stats, lpp, per_image, x_batch_shift, N, flags);
   else
-    UPF_LAUNCH((warp_fwd_kernel<false>), N * per_image, WARP_NT, smem, (cudaStream_t)stream, x, ldx, flow, ldf, out, ldo, H, W, C,
+    UPF_LAUNCH((warp_fwd_kernel<false, T>), N * per_image, WARP_NT, smem, (cudaStream_t)stream, x, ldx, flow, ldf, out, ldo, H, W, C,
                                                                                   align_corners, mask_threshold, stats, lpp, per_image, x_batch_shift, N, flags);
   return check_launch("warp_fwd");
+}
+}  // namespace upf
+
+extern "C" int upf_warp_fwd(const float* x, int ldx, const float* flow, int ldf, float* out, int ldo,
+                            int N, int H, int W, int C, int align_corners, float mask_threshold, int x_batch_shift,
+                            double* stats, int flags, void* stream) {
+  return upf::warp_fwd_launch<float>(x, ldx, flow, ldf, out, ldo, N, H, W, C, align_corners, mask_threshold, x_batch_shift, stats,
+                                     flags, stream);
+}
+
+// fp16 / bf16 STORAGE of the warped tensor and its source: taps are converted to fp32, blended in
+// fp32 in ATen's order, rounded once at the store; the flow and the mask arithmetic stay fp32 (so the mask is the same
+// bit-faithful one); the fused moments are those of the ROUNDED output's fp32 pre-image.
+extern "C" int upf_warp_fwd_lp(const void* x, int ldx, const float* flow, int ldf, void* out, int ldo, int dtype,
+                               int N, int H, int W, int C, int align_corners, float mask_threshold, int x_batch_shift,
+                               double* stats, void* stream) {
+  using namespace upf;
+  UPF_REQUIRE(dtype == UPF_DTYPE_F16 || dtype == UPF_DTYPE_BF16, "warp_lp: dtype must be UPF_DTYPE_F16 or UPF_DTYPE_BF16");
+  if (dtype == UPF_DTYPE_F16)
+    return warp_fwd_launch<__half>(static_cast<const __half*>(x), ldx, flow, ldf, static_cast<__half*>(out), ldo, N, H, W, C,
+                                   align_corners, mask_threshold, x_batch_shift, stats, 0, stream);
+  return warp_fwd_launch<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), ldx, flow, ldf, static_cast<__nv_bfloat16*>(out), ldo,
+                                        N, H, W, C, align_corners, mask_threshold, x_batch_shift, stats, 0, stream);
 }
 
 extern "C" int upf_warp_bwd(const float* x, int ldx, const float* flow, int ldf, const float* grad_out, int ldg,

@@ -40,12 +40,14 @@ def _p(t, offset_elems=0):
     return ctypes.c_void_p(t.data_ptr() + 4 * offset_elems)
 
 
-def _require_cuda(*ts):
+def _require_cuda(*ts, lp_ok=False):
     for t in ts:
         if t is None:
             continue
         if not t.is_cuda:
             raise RuntimeError("upflow_pytorch_b200 ops need CUDA tensors (no CPU path exists); got %s" % t.device)
+        if lp_ok and t.dtype in (torch.float16, torch.bfloat16):
+            continue                     # correlation / warp have fp16 / bf16 storage variants
         if t.dtype != torch.float32:
             raise RuntimeError("upflow_pytorch_b200 ops are fp32; got %s" % t.dtype)
 
@@ -122,6 +124,34 @@ def k_corr_planar(f1, f2, out, max_disp=4, f2_shift=0, slope=LRELU_SLOPE, round_
     _ext.check(_lib().upf_corr_lrelu_fwd_planar(f1.data_ptr(), pit[0], f2.data_ptr(), pit[1], out.data_ptr(), pit[2],
                                                 N, H, W, C, max_disp, f2_shift, slope,
                                                 _ext.FLAG_ROUND_TF32 if round_tf32 else 0, _stream()), "corr_lrelu_fwd_planar")
+
+
+_LP_DTYPES = {torch.float16: _ext.DTYPE_F16, torch.bfloat16: _ext.DTYPE_BF16}
+
+
+def k_corr_lp(f1, f2, out, max_disp=4, stats1=None, stats2=None, f2_shift=0, slope=LRELU_SLOPE):
+    """fp16 / bf16 storage variant: pixel-major [N,H,W,C] half tensors in, [N,H,W,(2d+1)^2] of the same dtype out, fp32
+    arithmetic (upf_corr_lrelu_fwd_lp).  Pitches may exceed C (channel slices of a wider buffer)."""
+    assert f1.dtype in _LP_DTYPES and f2.dtype == f1.dtype and out.dtype == f1.dtype
+    N, H, W, C = f1.shape
+    assert f1.stride(3) == 1 and f2.stride(3) == 1 and out.stride(3) == 1 and out.shape[3] == (2 * max_disp + 1) ** 2
+    dp = lambda t: ctypes.c_void_p(t.data_ptr())
+    _ext.check(_lib().upf_corr_lrelu_fwd_lp(dp(f1), f1.stride(2), dp(f2), f2.stride(2), dp(out), out.stride(2), _LP_DTYPES[f1.dtype],
+                                            N, H, W, C, max_disp, _p(stats1), _p(stats2), f2_shift, slope, _stream()), "corr_lrelu_fwd_lp")
+
+
+def k_warp_lp(x, flow, out, align_corners=False, use_mask=True, x_shift=0, stats=None):
+    """fp16 / bf16 storage variant of k_warp: x, out pixel-major half tensors, flow fp32 [N,H,W,>=2]."""
+    assert x.dtype in _LP_DTYPES and out.dtype == x.dtype and flow.dtype == torch.float32
+    N, H, W, C = out.shape
+    dp = lambda t: ctypes.c_void_p(t.data_ptr())
+    _ext.check(_lib().upf_warp_fwd_lp(dp(x), x.stride(2), dp(flow), flow.stride(2), dp(out), out.stride(2), _LP_DTYPES[x.dtype],
+                                      N, H, W, C, int(align_corners), _mask_thr(use_mask), x_shift, _p(stats), _stream()), "warp_fwd_lp")
+
+
+def _pixel_major_any(x):
+    """[N,C,H,W] of any dtype -> contiguous pixel-major [N,H,W,C] (a view when x is channels_last)"""
+    return x.permute(0, 2, 3, 1).contiguous()
 
 
 def k_corr_bwd(f1, f2, out, grad_out, grad_f1, grad_f2, max_disp=4, slope=1.0):
@@ -447,9 +477,19 @@ class _CorrelationFn(torch.autograd.Function):
 
 def correlation(in1, in2, max_disp=4, leaky_slope=None):
     """Cost volume [B,(2d+1)^2,H,W]; ``leaky_slope`` fuses the LeakyReLU of model/upflow.py:563-564."""
-    _require_cuda(in1, in2)
+    _require_cuda(in1, in2, lp_ok=True)
     if in1.shape != in2.shape:
         raise RuntimeError("correlation: shape mismatch %s vs %s" % (tuple(in1.shape), tuple(in2.shape)))
+    if in1.dtype in _LP_DTYPES:
+        # fp16 / bf16 storage (the reference's Half dispatch): inference only -- train in fp32
+        if in2.dtype != in1.dtype:
+            raise RuntimeError("correlation: dtype mismatch %s vs %s" % (in1.dtype, in2.dtype))
+        if torch.is_grad_enabled() and (in1.requires_grad or in2.requires_grad):
+            raise RuntimeError("correlation: the fp16 / bf16 storage variant has no backward; train in fp32")
+        a, b = _pixel_major_any(in1), _pixel_major_any(in2)
+        out = torch.empty(a.shape[0], a.shape[1], a.shape[2], (2 * max_disp + 1) ** 2, device=a.device, dtype=a.dtype)
+        k_corr_lp(a, b, out, max_disp, slope=1.0 if leaky_slope is None else float(leaky_slope))
+        return out.permute(0, 3, 1, 2)
     if (PLANAR_CORR and max_disp in (3, 4) and not (torch.is_grad_enabled() and (in1.requires_grad or in2.requires_grad))
             and _planar_ok(in1) and _planar_ok(in2) and in1.shape[2] * in1.shape[3] >= PLANAR_CORR_MIN_PIXELS):
         # the reference operator's own layout, inference: planar in, planar out, no transposes (corr_planar.cu)
@@ -482,9 +522,16 @@ class _WarpFn(torch.autograd.Function):
 
 def warp(x, flow, align_corners=False, use_mask=True):
     """WarpingLayer_no_div (model/pwc_modules.py:184-207); use_mask=False = tools.torch_warp (utils/tools.py:1274-1304)."""
-    _require_cuda(x, flow)
+    _require_cuda(x, flow, lp_ok=True)
     if flow.shape[1] != 2 or flow.shape[0] != x.shape[0] or flow.shape[2:] != x.shape[2:]:
         raise RuntimeError("warp: flow must be [B,2,H,W] matching x")
+    if x.dtype in _LP_DTYPES:
+        if torch.is_grad_enabled() and (x.requires_grad or flow.requires_grad):
+            raise RuntimeError("warp: the fp16 / bf16 storage variant has no backward; train in fp32")
+        a, f = _pixel_major_any(x), _pixel_major_any(flow.float())
+        out = torch.empty_like(a)
+        k_warp_lp(a, f, out, bool(align_corners), use_mask)
+        return out.permute(0, 3, 1, 2)
     return _WarpFn.apply(x, flow, bool(align_corners), use_mask)
 
 
