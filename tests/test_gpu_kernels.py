@@ -418,7 +418,9 @@ def test_conv_tf32_cluster_split_k_and_stride2(upf, case):
 
 
 @pytest.mark.parametrize("shape,d", [((2, 32, 270, 480), 4), ((1, 16, 256, 512), 3), ((1, 36, 250, 480), 1), ((1, 64, 272, 448), 2),
-                                     ((1, 32, 135, 470), 6), ((1, 20, 200, 333), 5), ((2, 32, 94, 311), 4)])
+                                     ((1, 32, 135, 470), 6), ((1, 20, 200, 333), 5), ((2, 32, 94, 311), 4),
+                                     # BASELINE config 5's sweep d in {2, 4, 6} at the HD 1/4-res shape
+                                     ((1, 32, 270, 480), 2), ((1, 32, 270, 480), 6)])
 def test_corr_pipelined_persistent_kernel(upf, shape, d):
     """>= 25 tiles per image: the persistent TMA / warp-specialised kernel (corr_pipe.cu), raw and with fused normalisation +
     LeakyReLU, into a channel slice; and bit-for-bit agreement with the tiled kernel is NOT required (different
