@@ -394,9 +394,37 @@ def corr_roofline(pk, iters=20):
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("corr_pipe_kernel", {}).get("dram_bytes_per_launch_avg")
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        tt = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            tt.append(e0.elapsed_time(e1))
+        return sum(tt) / len(tt) * 1e3
+    # the same cost volume through the other entry points: the reference operator's own layout (NCHW in, NCHW out,
+    # corr_planar.cu) and the fp16 / bf16 storage variants (half the bytes, fp32 arithmetic)
+    variants = {}
+    try:
+        p1, p2 = f1.permute(0, 3, 1, 2).contiguous(), f2.permute(0, 3, 1, 2).contiguous()
+        po = torch.empty(N, 81, h, w, device="cuda")
+        us = timed(lambda: ops.k_corr_planar(p1, p2, po, d, slope=0.1))
+        variants["planar_nchw_fp32"] = {"kernel": "corr_planar_kernel<4>", "us_per_launch": us, "algorithmic_bytes": nbytes,
+                                        "frac": nbytes / us / 1e3 / pk["hbm"]}
+        for name, dt in (("bf16_storage", torch.bfloat16), ("fp16_storage", torch.float16)):
+            a, b, o = f1.to(dt), f2.to(dt), torch.empty(N, h, w, 81, device="cuda", dtype=dt)
+            us = timed(lambda: ops.k_corr_lp(a, b, o, d, slope=0.1))
+            variants[name] = {"kernel": "corr_fwd_kernel<4, %s>" % str(dt).split(".")[1], "us_per_launch": us,
+                              "algorithmic_bytes": nbytes // 2, "frac": nbytes / 2 / us / 1e3 / pk["hbm"]}
+    except Exception as exc:   # pragma: no cover - side measurements must never break the bench line
+        variants["error"] = repr(exc)[:200]
     return {"kernel": "corr_pipe_kernel<4>", "shape": [N, C, h, w], "max_disp": d, "bound": "hbm", "achieved": ach,
             "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": traffic, "us_per_launch": ms * 1e3,
-            "best_us": min(ts) * 1e3, "algorithmic_bytes": nbytes, "l2": "flushed before every launch"}
+            "best_us": min(ts) * 1e3, "algorithmic_bytes": nbytes, "l2": "flushed before every launch", "variants": variants}
 
 
 class _StdoutGuard:

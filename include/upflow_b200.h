@@ -247,20 +247,27 @@ int upf_conv2d_wgrad(const float* x, int ldx, const float* grad_out, int ldg, fl
 
 /* the same on the tensor cores (stride 1; TF32 operands, fp32 accumulation): both operands are transposed into planar,
  * zero-padded form in `workspace` (upf_conv2d_wgrad_tc_workspace_elems floats, 16-byte aligned), where a tap is a
- * constant shift of the K index, and the nine tap GEMMs run as one launch of the convolution kernel. */
+ * constant shift of the K index (the padded pixel index), and the nine tap GEMMs run as one launch of the convolution
+ * kernel.  The planar form is BLOCKED and PRE-SWIZZLED, [K / 32][row][32] with the 16-byte chunk index XOR (row & 7): a
+ * GEMM operand tile (rows x 32 k) is then one contiguous run that ONE bulk copy (cp.async.bulk) lands in the K-major
+ * SWIZZLE_128B form the tensor-core descriptors expect -- as TMA tensor boxes the same tiles cost ~6 ns per 128-byte row
+ * (measured: 1.95 ms for the 576->128 GEMM at 8x64x208).  The padded row length is a multiple of 32 so that a tap's
+ * vertical shift is a whole number of blocks. */
 long long upf_conv2d_wgrad_tc_workspace_elems(int N, int H, int W, int Cin, int Cout, int ksize, int dilation);
 int upf_conv2d_wgrad_tc(const float* x, int ldx, const float* grad_out, int ldg, float* grad_w, float* grad_bias,
                         float* workspace, int N, int H, int W, int Cin, int Cout, int ksize, int dilation, void* stream);
 /* The same with the input transposed once for several convolutions that read nested channel ranges of one buffer
- * (the dense blocks): upf_wgrad_tc_transpose_input writes xt [C][pitch] (pitch = upf_wgrad_tc_planar_pitch, planar,
- * zero-padded); a convolution whose input is channels [c0, c0+Cin) of that buffer passes xt + c0*pitch.  All of them
- * must share ksize and dilation.  workspace as for upf_conv2d_wgrad_tc. */
-long long upf_wgrad_tc_planar_pitch(int N, int H, int W, int ksize, int dilation);
+ * (the dense blocks): upf_wgrad_tc_transpose_input writes xt (upf_wgrad_tc_planar_elems floats, 16-byte aligned:
+ * blocked planar [k blocks][C][32], pre-swizzled, zero-padded in k on both sides); a convolution whose input is
+ * channels [row0, row0+Cin) of that buffer (row0 a multiple of 8) passes xt, xt_rows = C and row0.  All of them must
+ * share ksize and dilation.  workspace as for upf_conv2d_wgrad_tc. */
+long long upf_wgrad_tc_planar_pitch(int N, int H, int W, int ksize, int dilation);   /* padded pixel count K (multiple of 32) */
+long long upf_wgrad_tc_planar_elems(int N, int H, int W, int C, int ksize, int dilation);
 int upf_wgrad_tc_transpose_input(const float* x, int ldx, int C, float* xt, int N, int H, int W, int ksize, int dilation,
                                  void* stream);
-int upf_conv2d_wgrad_tc_planar(const float* xt, const float* grad_out, int ldg, float* grad_w, float* grad_bias,
-                               float* workspace, int N, int H, int W, int Cin, int Cout, int ksize, int dilation,
-                               void* stream);
+int upf_conv2d_wgrad_tc_planar(const float* xt, int xt_rows, int row0, const float* grad_out, int ldg, float* grad_w,
+                               float* grad_bias, float* workspace, int N, int H, int W, int Cin, int Cout, int ksize,
+                               int dilation, void* stream);
 
 /* pointwise ops on [npix][C] pitched tensors.  op 0: out = b * (a > 0 ? 1 : slope)  (LeakyReLU backward from the
  * saved output a and the incoming gradient b); op 1: out = sigmoid(a); op 2: out = b * a * (1 - a) (sigmoid

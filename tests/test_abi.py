@@ -75,7 +75,7 @@ def test_bad_arguments_return_codes_not_crashes(lib_path):
     assert rc == -1 and b"bad shape" in lib.upf_last_error()     # a flow needs two channels
     rc = lib.upf_repack_conv_weight_tc(P, P, 8, 8, 5, 0, None)
     assert rc == -1 and b"repack" in lib.upf_last_error()
-    rc = lib.upf_conv2d_wgrad_tc_planar(None, P, 8, P, P, P, 1, 8, 8, 8, 8, 3, 1, None)
+    rc = lib.upf_conv2d_wgrad_tc_planar(None, 8, 0, P, 8, P, P, P, 1, 8, 8, 8, 8, 3, 1, None)
     assert rc == -1 and b"null" in lib.upf_last_error()
     assert lib.upf_loss_workspace_elems() >= 2 * 148
     assert lib.upf_wgrad_tc_planar_pitch(2, 8, 8, 3, 1) % 32 == 0

@@ -37,6 +37,8 @@ LEVELS = [("KITTI 1/4 (2x94x311)", 2, 94, 311, True), ("KITTI 1/8 (2x47x156)", 2
           ("train 1/4 (8x64x208)", 8, 64, 208, False), ("train 1/8 (8x32x104)", 8, 32, 104, False)]
 if len(sys.argv) > 1 and sys.argv[1] == "quick":
     LEVELS = LEVELS[:1]; EST = EST[:2]; CTX = CTX[:1]; SGU = SGU[:1]; ADP = ADP[:1]
+if len(sys.argv) > 1 and sys.argv[1] == "train":
+    LEVELS = LEVELS[2:]
 
 print("# Convolutions: this library vs cuDNN on the same B200 (tools/conv_vs_cudnn.py)\n")
 print("cuDNN %s, torch %s, TF32 allowed, `cudnn.benchmark=True`, channels_last; CUDA events, L2 flushed before every launch, best of 6; µs.\n" % (torch.backends.cudnn.version(), torch.__version__))

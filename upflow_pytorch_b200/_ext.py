@@ -47,8 +47,9 @@ SIGNATURES = {
     "upf_conv2d_wgrad_tc_workspace_elems": (_LL, [_I, _I, _I, _I, _I, _I, _I]),
     "upf_conv2d_wgrad_tc": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "upf_wgrad_tc_planar_pitch": (_LL, [_I, _I, _I, _I, _I]),
+    "upf_wgrad_tc_planar_elems": (_LL, [_I, _I, _I, _I, _I, _I]),
     "upf_wgrad_tc_transpose_input": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
-    "upf_conv2d_wgrad_tc_planar": (_I, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "upf_conv2d_wgrad_tc_planar": (_I, [_P, _I, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "upf_pointwise": (_I, [_I, _P, _I, _P, _I, _P, _I, _LL, _I, _F, _P]),
     "upf_act_split": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _LL, _I, _F, _P]),
     "upf_blend_fwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _LL, _P]),

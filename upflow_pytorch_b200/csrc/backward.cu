@@ -354,7 +354,8 @@ resize_bwd_y_kernel(const float* __restrict__ tmp, int H, float* __restrict__ gi
 // k + (kx-1)*dil.
 __global__ void __launch_bounds__(256)
 nhwc_to_planar_padded_kernel(const float* __restrict__ src, int ld, int C, float* __restrict__ dst, long long Kp, long long P,
-                             int H, int W, int pad, int Wp, int shift, int ncopies, long long copy_stride, int copy_shift) {
+                             int H, int W, int pad, int Wp, int shift, int ncopies, long long copy_stride, int copy_shift,
+                             int rows) {
   __shared__ float tile[32][33];
   const long long p0 = (long long)blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
@@ -377,15 +378,21 @@ nhwc_to_planar_padded_kernel(const float* __restrict__ src, int ld, int C, float
       const int c = c0 + i;
       if (c < C) {
         const float v = tile[tx][i];
-        for (int q = 0; q < ncopies; ++q)                  // copy q lives at dst + q*copy_stride, shifted by q*copy_shift
-          dst[(size_t)q * copy_stride + (size_t)c * Kp + k + q * copy_shift] = v;
+        for (int q = 0; q < ncopies; ++q) {                // copy q lives at dst + q*copy_stride, shifted by q*copy_shift
+          // BLOCKED planar [k / 32][row][k % 32], `rows` rows per k block, with the 16-byte chunk index XOR-ed by
+          // (row & 7): the image of TMA's SWIZZLE_128B, so that a plain bulk copy of rows x 128 bytes lands the K-major
+          // operand tile the tcgen05 descriptors expect (tile rows start at multiples of 8)
+          const long long kk = k + q * copy_shift;
+          const int j = (int)(kk & 31);
+          dst[(size_t)q * copy_stride + ((size_t)(kk >> 5) * rows + c) * 32 + ((((j >> 2) ^ (c & 7)) << 2) | (j & 3))] = v;
+        }
       }
     }
   }
 }
 
 int conv_tc_wgrad_gemm(const float* xt, int ldk, const float* gt_packed, const float* zero_bias, float* gw, int taps,
-                       int Cin, int Cout, int K, const int* koffs, const int* wsel, cudaStream_t st);
+                       int Cin, int Cout, int K, const int* koffs, const int* wsel, int xt_rows, int kpad, cudaStream_t st);
 
 
 // ---- 3xTF32 support (engine precision "tf32x3"): an fp32 value x is hi + lo with hi = x truncated to TF32 (what
@@ -585,21 +592,32 @@ extern "C" int upf_repack_conv_weight(const float* weight, float* out, int A, in
 // (Tried: cutting K into up to 8 grid-level parts on top of the cluster split for the few-channel convolutions at fine
 // resolution, 72 -> 576 CTAs, partials summed by reduce_splits_kernel -- parity-green, training step 57.19 vs 57.00 ms:
 // those launches are not bound by the GEMM's CTA count; removed.)
-static int wgrad_tc_wp(int W, int ks, int dil) { return (W + (ks - 1) * dil + 3) / 4 * 4; }   // padded row, multiple of 4
+// padded row: a multiple of 32, so that a tap's vertical shift (dil * Wp pixels) is a whole number of 32-pixel k blocks
+static int wgrad_tc_wp(int W, int ks, int dil) { return ks == 1 ? W : (W + (ks - 1) * dil + 31) / 32 * 32; }
 static long long wgrad_tc_kp(int N, int H, int W, int ks, int dil) {
   const int pad = ((ks - 1) * dil) / 2;
   const long long K = (long long)N * (H + 2 * pad) * wgrad_tc_wp(W, ks, dil);
   return (K + 31) / 32 * 32;
 }
+// zero k blocks in front of / behind the blocked XT buffer: a tap's vertical shift, dil * Wp pixels
+static int wgrad_tc_kpad(int W, int ks, int dil) { return ks == 1 ? 0 : dil * wgrad_tc_wp(W, ks, dil) / 32; }
+constexpr long long WGRAD_SLACK = 128 * 32;      // a 128-row tile may start at the buffer's last rows: one tile of slack
+static long long wgrad_tc_xt_elems(int N, int H, int W, int C, int ks, int dil) {
+  return (wgrad_tc_kp(N, H, W, ks, dil) / 32 + 2 * wgrad_tc_kpad(W, ks, dil)) * (long long)C * 32 + WGRAD_SLACK;
+}
+extern "C" long long upf_wgrad_tc_planar_elems(int N, int H, int W, int C, int ksize, int dilation) {
+  return wgrad_tc_xt_elems(N, H, W, C, ksize, dilation);
+}
 extern "C" long long upf_conv2d_wgrad_tc_workspace_elems(int N, int H, int W, int Cin, int Cout, int ksize, int dilation) {
   const long long Kp = wgrad_tc_kp(N, H, W, ksize, dilation);
   const long long cout_pad = (Cout + 15) / 16 * 16;
-  return (long long)Cin * Kp + 3 * cout_pad * Kp + cout_pad + (long long)UPF_BIAS_SPLITS * Cout + 64;
+  return wgrad_tc_xt_elems(N, H, W, Cin, ksize, dilation) + 3 * cout_pad * Kp + WGRAD_SLACK + cout_pad +
+         (long long)UPF_BIAS_SPLITS * Cout + 64;
 }
 // x != NULL: transpose the input here; xt_pre != NULL: the caller already holds the planar padded input (rows of
 // upf_wgrad_tc_transpose_input's output -- a dense block transposes its whole buffer ONCE and every convolution of the
 // block reads its own suffix of rows)
-static int wgrad_tc_impl(const float* x, int ldx, const float* xt_pre, const float* grad_out, int ldg, float* grad_w,
+static int wgrad_tc_impl(const float* x, int ldx, const float* xt_pre, int xt_rows, int row0, const float* grad_out, int ldg, float* grad_w,
                          float* grad_bias, float* workspace, int N, int H, int W, int Cin, int Cout, int ksize, int dilation,
                          cudaStream_t st) {
   using namespace upf;
@@ -614,32 +632,36 @@ static int wgrad_tc_impl(const float* x, int ldx, const float* xt_pre, const flo
   const long long cout_pad = (Cout + 15) / 16 * 16;
   const long long P = (long long)N * H * W;
   const int ncopies = ksize == 1 ? 1 : 3;
+  const int kpad = wgrad_tc_kpad(W, ksize, dilation);
+  UPF_REQUIRE(!xt_pre || (row0 % 8) == 0, "wgrad_tc_planar: row0 must be a multiple of 8 (swizzle phase of the operand tiles)");
   float* xt = workspace;
-  float* gt = xt + (xt_pre ? 0 : (size_t)Cin * Kp);       // [3][cout_pad][Kp]: G written at k + (kx-1)*dil
-  float* zb = gt + (size_t)3 * cout_pad * Kp;
+  float* gt = xt + (xt_pre ? 0 : (size_t)wgrad_tc_xt_elems(N, H, W, Cin, ksize, dilation));   // [3][Kp / 32][cout_pad][32]: G written at k + (kx-1)*dil
+  float* zb = gt + (size_t)3 * cout_pad * Kp + WGRAD_SLACK;
   float* bpart = zb + cout_pad;
   cudaError_t ce = cudaMemsetAsync(workspace, 0, (size_t)((char*)(zb + cout_pad) - (char*)workspace), st);
   if (ce != cudaSuccess) { set_error("wgrad_tc memset: %s", cudaGetErrorString(ce)); return (int)ce; }
   const unsigned ptiles = (unsigned)((P + 31) / 32);
   int e = 0;
   if (!xt_pre) {
-    nhwc_to_planar_padded_kernel<<<dim3(ptiles, (Cin + 31) / 32), 256, 0, st>>>(x, ldx, Cin, xt, Kp, P, H, W, pad, Wp, 0, 1, 0, 0);
+    nhwc_to_planar_padded_kernel<<<dim3(ptiles, (Cin + 31) / 32), 256, 0, st>>>(x, ldx, Cin, xt + (size_t)kpad * Cin * 32, Kp, P, H, W,
+                                                                                pad, Wp, 0, 1, 0, 0, Cin);
     e = check_launch("wgrad_tc_transpose_x");
     if (e) return e;
   }
   // the three horizontally shifted copies of G in one pass: one read, three writes
   nhwc_to_planar_padded_kernel<<<dim3(ptiles, (Cout + 31) / 32), 256, 0, st>>>(grad_out, ldg, Cout, gt, Kp, P, H, W, pad, Wp,
                                                                                 ksize == 1 ? 0 : -dilation, ncopies,
-                                                                                cout_pad * Kp, dilation);
+                                                                                cout_pad * Kp, dilation, (int)cout_pad);
   e = check_launch("wgrad_tc_transpose_g");
   if (e) return e;
   int koffs[9], wsel[9];
   for (int t = 0; t < taps; ++t) {
     const int ky = t / ksize, kx = t % ksize;
-    koffs[t] = ksize == 1 ? 0 : (ky - 1) * dilation * Wp;          // multiple of 4
+    koffs[t] = ksize == 1 ? 0 : (ky - 1) * dilation * (Wp / 32);   // in k blocks of 32 (Wp is a multiple of 32)
     wsel[t] = ksize == 1 ? 0 : kx;
   }
-  e = conv_tc_wgrad_gemm(xt_pre ? xt_pre : xt, (int)Kp, gt, zb, grad_w, taps, Cin, Cout, (int)Kp, koffs, wsel, st);
+  e = conv_tc_wgrad_gemm(xt_pre ? xt_pre + (size_t)row0 * 32 : xt, (int)Kp, gt, zb, grad_w, taps, Cin, Cout, (int)Kp, koffs, wsel,
+                         xt_pre ? xt_rows : Cin, kpad, st);
   if (e) return e;
   if (grad_bias) {
     int cw = 1;
@@ -660,7 +682,7 @@ extern "C" int upf_conv2d_wgrad_tc(const float* x, int ldx, const float* grad_ou
                                    float* workspace, int N, int H, int W, int Cin, int Cout, int ksize, int dilation,
                                    void* stream) {
   UPF_REQUIRE(x, "wgrad_tc: null input");
-  return wgrad_tc_impl(x, ldx, nullptr, grad_out, ldg, grad_w, grad_bias, workspace, N, H, W, Cin, Cout, ksize, dilation,
+  return wgrad_tc_impl(x, ldx, nullptr, 0, 0, grad_out, ldg, grad_w, grad_bias, workspace, N, H, W, Cin, Cout, ksize, dilation,
                        (cudaStream_t)stream);
 }
 
@@ -676,18 +698,19 @@ extern "C" int upf_wgrad_tc_transpose_input(const float* x, int ldx, int C, floa
   cudaStream_t st = (cudaStream_t)stream;
   const int pad = ((ksize - 1) * dilation) / 2;
   const long long Kp = wgrad_tc_kp(N, H, W, ksize, dilation), P = (long long)N * H * W;
-  cudaError_t ce = cudaMemsetAsync(xt, 0, (size_t)C * Kp * sizeof(float), st);
+  cudaError_t ce = cudaMemsetAsync(xt, 0, (size_t)wgrad_tc_xt_elems(N, H, W, C, ksize, dilation) * sizeof(float), st);
   if (ce != cudaSuccess) { set_error("wgrad_tc_transpose_input memset: %s", cudaGetErrorString(ce)); return (int)ce; }
   nhwc_to_planar_padded_kernel<<<dim3((unsigned)((P + 31) / 32), (C + 31) / 32), 256, 0, st>>>(
-      x, ldx, C, xt, Kp, P, H, W, pad, wgrad_tc_wp(W, ksize, dilation), 0, 1, 0, 0);
+      x, ldx, C, xt + (size_t)wgrad_tc_kpad(W, ksize, dilation) * C * 32, Kp, P, H, W, pad, wgrad_tc_wp(W, ksize, dilation), 0, 1, 0, 0, C);
   return check_launch("wgrad_tc_transpose_x");
 }
 
-extern "C" int upf_conv2d_wgrad_tc_planar(const float* xt, const float* grad_out, int ldg, float* grad_w, float* grad_bias,
-                                          float* workspace, int N, int H, int W, int Cin, int Cout, int ksize, int dilation,
-                                          void* stream) {
+extern "C" int upf_conv2d_wgrad_tc_planar(const float* xt, int xt_rows, int row0, const float* grad_out, int ldg, float* grad_w,
+                                          float* grad_bias, float* workspace, int N, int H, int W, int Cin, int Cout, int ksize,
+                                          int dilation, void* stream) {
   UPF_REQUIRE(xt, "wgrad_tc_planar: null input");
-  return wgrad_tc_impl(nullptr, 0, xt, grad_out, ldg, grad_w, grad_bias, workspace, N, H, W, Cin, Cout, ksize, dilation,
+  UPF_REQUIRE(row0 >= 0 && Cin > 0 && row0 + Cin <= xt_rows, "wgrad_tc_planar: rows [%d, %d) outside the %d-row buffer", row0, row0 + Cin, xt_rows);
+  return wgrad_tc_impl(nullptr, 0, xt, xt_rows, row0, grad_out, ldg, grad_w, grad_bias, workspace, N, H, W, Cin, Cout, ksize, dilation,
                        (cudaStream_t)stream);
 }
 

@@ -64,9 +64,20 @@ struct TcParams {
   // weight-gradient mode (backward.cu): the "images" are the taps of ONE planar operand -- image n reads the same
   // tensor with its K (channel) coordinate shifted by koffs[n]
   int wgrad;
-  int koffs[9];               // multiples of 4 elements: a box row must start 16-byte aligned
+  int koffs[9];               // in k BLOCKS of 32 (the blocked planar layout of backward.cu)
   int wsel[9];                // which of the (pre-shifted) copies of the other operand tap n multiplies
+  // the blocked, PRE-SWIZZLED planar operands of the weight gradient: [k block][row][32 k], `kpad` zero blocks before
+  // block 0 of xg (a tap's vertical shift may reach that far); an operand tile is one contiguous run -> one bulk copy
+  const float* xg; const float* wg;
+  int xrows, wrows, kpad;
+  long long wcopy;            // elements between the pre-shifted copies of wg
 };
+
+// contiguous global -> shared bulk copy completing on an mbarrier (no tensor map: no per-row cost)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 
 // bias + LeakyReLU (+ residual) and the store of 4 consecutive output channels of one pixel
 __device__ __forceinline__ void store4(const TcParams& p, const float* s_bias, int co0, float* o, const float* r, int co, float4 f, bool vec_out) {
@@ -163,14 +174,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const uint32_t b_dst = a_dst + TC_A_BYTES;
         const uint32_t fb = smem_u32(&full[s]);
         mbar_expect_tx(fb, (uint32_t)p.a_bytes + b_bytes);
-        const int kc = kb * TC_KC + (p.wgrad ? p.koffs[n] : 0);
-        const int nn = p.wgrad ? 0 : n;
-        for (int jy = 0; jy < p.nby; ++jy)
-          for (int jx = 0; jx < p.nbx; ++jx)
-            tma_load_4d(a_dst + (uint32_t)((jy * p.bh * p.TW + jx * p.bw) * 128), &map_x, fb, kc,
-                        cx + jx * p.bw * p.stride, cy + jy * p.bh * p.stride, nn);
-        for (int jb = 0; jb < p.nbb; ++jb)
-          tma_load_3d(b_dst + (uint32_t)(jb * p.b_rows * 128), &map_w, fb, kb * TC_KC, co0 + jb * p.b_rows, p.wgrad ? p.wsel[n] : tap);
+        if (p.wgrad) {
+          // weight gradient: both operands are BLOCKED planar tensors [k block][row][32 k] (backward.cu), so a box of
+          // `rows` x 32 k is one contiguous run of rows x 128 bytes; the tap's vertical shift is a whole number of k blocks
+          // (as TMA tensor boxes these tiles cost ~6 ns per 128-byte row whatever the layout: 1.95 ms for the 576->128
+          // gradient at 8x64x208; the data is written pre-swizzled by nhwc_to_planar_padded_kernel)
+          const int kblk = kb + p.koffs[n] + p.kpad;
+          bulk_g2s(a_dst, p.xg + ((size_t)kblk * p.xrows + cx) * 32, (uint32_t)p.a_bytes, fb);
+          bulk_g2s(b_dst, p.wg + (size_t)p.wsel[n] * p.wcopy + ((size_t)kb * p.wrows + co0) * 32, b_bytes, fb);
+        } else {
+          const int kc = kb * TC_KC;
+          for (int jy = 0; jy < p.nby; ++jy)
+            for (int jx = 0; jx < p.nbx; ++jx)
+              tma_load_4d(a_dst + (uint32_t)((jy * p.bh * p.TW + jx * p.bw) * 128), &map_x, fb, kc,
+                          cx + jx * p.bw * p.stride, cy + jy * p.bh * p.stride, n);
+          for (int jb = 0; jb < p.nbb; ++jb)
+            tma_load_3d(b_dst + (uint32_t)(jb * p.b_rows * 128), &map_w, fb, kb * TC_KC, co0 + jb * p.b_rows, tap);
+        }
       }
     }
     __syncwarp();
@@ -426,6 +446,8 @@ static int tc_max_cluster() {
 
 static thread_local const int* g_tc_koffs = nullptr;      // set by conv_tc_wgrad_gemm around its call (per calling thread)
 static thread_local const int* g_tc_wsel = nullptr;
+static thread_local int g_tc_xrows = 0;                   // rows per k block of the blocked planar XT buffer
+static thread_local int g_tc_kpad = 0;                    // zero k blocks in front of XT's block 0
 
 int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
                   const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
@@ -451,6 +473,11 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   const int taps = ks * ks;
   int TH = 8, TW = 16;
   pick_tile(Ho, Wo, 256 / stride > 128 ? 128 : 256 / stride, &TH, &TW);   // TMA box extents are <= 256 elements
+  if (koffs) {                 // weight gradient: the "image" is one row of Cin operand rows; one box of TW rows per k block
+    TH = 1;
+    TW = 8;
+    while (TW < 128 && TW < Wo) TW <<= 1;
+  }
   const int tiles_x = (Wo + TW - 1) / TW, tiles_y = (Ho + TH - 1) / TH;
   const long long tiles = (long long)tiles_x * tiles_y * N;
   const int iters_all = taps * kblocks;
@@ -500,6 +527,25 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   int b_rows = BN < box_rows ? BN : box_rows;
   while (BN % b_rows) b_rows -= 8;           // BN is a multiple of 16
   CUtensorMap mx, mw;
+  if (koffs) {
+    // weight gradient: x = XT blocked [Cin / 32 k blocks][g_tc_xrows rows][32], this call's rows start at x; w = GT blocked
+    // [3 copies][k blocks][cout_pad rows][32]
+    UPF_REQUIRE(H == 1 && stride == 1 && ks == 1 && Cin % 32 == 0 && g_tc_xrows >= W, "conv_tc: bad weight-gradient call");
+    const cuuint64_t kblk = (cuuint64_t)(Cin / 32);
+    const cuuint64_t dims[4] = {32, (cuuint64_t)W, kblk, 1};
+    const cuuint64_t strides[3] = {128, (cuuint64_t)g_tc_xrows * 128, (cuuint64_t)g_tc_xrows * 128 * kblk};
+    const cuuint32_t box[4] = {TC_KC, (cuuint32_t)bw, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    MapKey key{x, g_tc_xrows, (long long)W, (long long)kblk, bw, 41};
+    int e = encode_cached(key, &mx, 4, const_cast<float*>(x), dims, strides, box, estr);
+    if (e) return e;
+    const cuuint64_t wdims[4] = {32, (cuuint64_t)cout_pad, kblk, 3};
+    const cuuint64_t wstrides[3] = {128, (cuuint64_t)cout_pad * 128, (cuuint64_t)cout_pad * 128 * kblk};
+    const cuuint32_t wbox[4] = {TC_KC, (cuuint32_t)b_rows, 1, 1};
+    MapKey wkey{w_packed, cout_pad, (long long)kblk, b_rows, 3, 42};
+    e = encode_cached(wkey, &mw, 4, const_cast<float*>(w_packed), wdims, wstrides, wbox, estr);
+    if (e) return e;
+  } else {
   {
     const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(koffs ? 1 : N)};
     const cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
@@ -519,6 +565,7 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
     int e = encode_cached(key, &mw, 3, const_cast<float*>(w_packed), dims, strides, box, estr);
     if (e) return e;
   }
+  }
 
   TcParams p;
   p.out = out; p.ldo = ldo; p.res = res; p.ldr = ldr; p.bias = bias;
@@ -530,6 +577,8 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   p.slope = slope;
   p.flags = flags;
   p.wgrad = koffs ? 1 : 0;
+  p.xg = x; p.wg = w_packed; p.xrows = g_tc_xrows; p.wrows = cout_pad; p.kpad = g_tc_kpad;
+  p.wcopy = (long long)cout_pad * cin_pad;
   for (int i = 0; i < 9; ++i) { p.koffs[i] = (koffs && i < N) ? koffs[i] : 0; p.wsel[i] = (koffs && g_tc_wsel && i < N) ? g_tc_wsel[i] : 0; }
   p.tmem_cols = BN <= 16 ? 32 : (BN <= 32 ? 64 : (BN <= 64 ? 128 : 256));   // two accumulators (one per MMA issuer)
   const int stage_bytes = TC_A_BYTES + ((BN * 128 + 1023) & ~1023);
@@ -576,8 +625,8 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
 // dW[tap][ci][co] = sum_k XT[ci][k + koffs[tap]] * GT[wsel[tap]][co][k]  (backward.cu): the tensor-core GEMM of this file with the
 // taps as "images" (out is [taps][Cin][Cout]), M = Cin, K = the padded pixel index, cluster split-K
 int conv_tc_wgrad_gemm(const float* xt, int ldk, const float* gt_packed, const float* zero_bias, float* gw, int taps,
-                       int Cin, int Cout, int K, const int* koffs, const int* wsel, cudaStream_t st) {
-  g_tc_koffs = koffs; g_tc_wsel = wsel;
+                       int Cin, int Cout, int K, const int* koffs, const int* wsel, int xt_rows, int kpad, cudaStream_t st) {
+  g_tc_koffs = koffs; g_tc_wsel = wsel; g_tc_xrows = xt_rows; g_tc_kpad = kpad;
   const int e = conv2d_fwd_tc(xt, ldk, gt_packed, zero_bias, gw, Cout, nullptr, 0, taps, 1, Cin, K, Cout, 1, 1, 1, 1.0f, 0, st);
   g_tc_koffs = nullptr; g_tc_wsel = nullptr;
   return e;

@@ -32,6 +32,7 @@ def _load():
             raise RuntimeError("correlation_cuda: %s not found (build it with `python -m upflow_pytorch_b200.build`)" % _LIB_PATH)
         lib = ctypes.CDLL(_LIB_PATH)
         lib.upf_corr_lrelu_fwd.argtypes = [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _F, _I, _P]
+        lib.upf_corr_lrelu_fwd_planar.argtypes = [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P]
         lib.upf_corr_lrelu_bwd.argtypes = [_P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _P]
         lib.upf_nchw_to_nhwc.argtypes = [_P, _P, _I, _I, _I, _I, _I, _P]
         lib.upf_nhwc_to_nchw.argtypes = [_P, _I, _P, _I, _I, _I, _I, _P]
@@ -77,6 +78,14 @@ def forward(input1, input2, rbot1, rbot2, output, pad_size, kernel_size, max_dis
         st = torch.cuda.current_stream().cuda_stream
         B, C, H, W = input1.shape
         D2 = (2 * max_displacement + 1) ** 2
+        if (max_displacement in (3, 4) and W % 4 == 0 and H * W >= 16384 and input1.is_contiguous() and input2.is_contiguous()
+                and input1.data_ptr() % 16 == 0 and input2.data_ptr() % 16 == 0):
+            # the reference's own layout end to end: NCHW operands and NCHW result through TMA, no conversion (corr_planar.cu)
+            output.resize_(B, D2, H, W)
+            pit = lambda c: (ctypes.c_longlong * 3)(W, H * W, c * H * W)
+            _chk(lib.upf_corr_lrelu_fwd_planar(input1.data_ptr(), pit(C), input2.data_ptr(), pit(C), output.data_ptr(), pit(D2),
+                                               B, H, W, C, max_displacement, 0, 1.0, 0, st))
+            return 1
         a, b = _nhwc(input1, st), _nhwc(input2, st)
         o = torch.empty(B, H, W, D2, dtype=torch.float32, device=input1.device)
         _chk(lib.upf_corr_lrelu_fwd(a.data_ptr(), C, b.data_ptr(), C, o.data_ptr(), D2, B, H, W, C, max_displacement,

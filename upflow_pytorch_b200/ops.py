@@ -254,20 +254,20 @@ def k_conv(x, weight, bias, out, ksize, stride=1, dilation=1, slope=LRELU_SLOPE,
 
 def k_wgrad_planar_input(x, ksize, dilation=1):
     """The planar, zero-padded transpose of slice x that the tensor-core weight gradient reads, made ONCE for several
-    convolutions whose inputs are nested channel ranges of x (same ksize / dilation).  Returns (xt, pitch): the rows
-    of channel c start at xt[c * pitch]."""
+    convolutions whose inputs are nested channel ranges of x (same ksize / dilation).  Returns (xt, rows): blocked planar
+    [pitch / 32][rows = x.C][32]; a convolution reading channels [c0, c0 + Cin) passes planar=(xt, rows, c0)."""
     x = _as_slice(x)
-    pitch = int(_lib().upf_wgrad_tc_planar_pitch(x.N, x.H, x.W, ksize, dilation))
-    xt = torch.empty(x.C * pitch, dtype=torch.float32, device=x.buf.device)
+    xt = torch.empty(int(_lib().upf_wgrad_tc_planar_elems(x.N, x.H, x.W, x.C, ksize, dilation)), dtype=torch.float32,
+                     device=x.buf.device)
     _ext.check(_lib().upf_wgrad_tc_transpose_input(x.ptr(), x.ld, x.C, _p(xt), x.N, x.H, x.W, ksize, dilation, _stream()),
                "wgrad_tc_transpose_input")
-    return xt, pitch
+    return xt, x.C
 
 
 def k_conv_wgrad(x, grad_out, ksize, stride=1, dilation=1, want_bias=True, tensor_cores=False, planar=None):
     """Weight gradient [k*k, Cin, Cout] and bias gradient [Cout] of conv() from its input and the gradient wrt its
     PRE-activation output (both pixel-major).  tensor_cores: TF32 tcgen05 GEMM (stride 1), else fp32 SIMT.
-    planar = (xt, pitch, c0): k_wgrad_planar_input's transpose of a buffer whose channels [c0, c0 + x.C) are x."""
+    planar = (xt, rows, c0): k_wgrad_planar_input's transpose of a `rows`-channel buffer whose channels [c0, c0 + x.C) are x."""
     x, g = _as_slice(x), _as_slice(grad_out)
     lib = _lib()
     if tensor_cores and stride == 1:
@@ -276,8 +276,8 @@ def k_conv_wgrad(x, grad_out, ksize, stride=1, dilation=1, want_bias=True, tenso
         gw = torch.empty(ksize * ksize, x.C, g.C, dtype=torch.float32, device=x.buf.device)
         gb = torch.empty(g.C, dtype=torch.float32, device=x.buf.device) if want_bias else None
         if planar is not None:
-            xt, pitch, c0 = planar
-            _ext.check(lib.upf_conv2d_wgrad_tc_planar(_p(xt, c0 * pitch), g.ptr(), g.ld, _p(gw), _p(gb), _p(ws), x.N, x.H, x.W,
+            xt, rows, c0 = planar
+            _ext.check(lib.upf_conv2d_wgrad_tc_planar(_p(xt), rows, c0, g.ptr(), g.ld, _p(gw), _p(gb), _p(ws), x.N, x.H, x.W,
                                                       x.C, g.C, ksize, dilation, _stream()), "conv2d_wgrad_tc_planar")
         else:
             _ext.check(lib.upf_conv2d_wgrad_tc(x.ptr(), x.ld, g.ptr(), g.ld, _p(gw), _p(gb), _p(ws), x.N, x.H, x.W, x.C, g.C,
