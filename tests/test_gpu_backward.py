@@ -515,3 +515,27 @@ def test_boundary_warp_kernels_vs_torch(upf):
     # through the drop-in entry point
     again = tools.boundary_dilated_warp.warp_im(frame, flow, start)
     assert torch.equal(again, got)
+
+
+@pytest.mark.parametrize("level", [(4, 128, 416), (8, 64, 208), (8, 16, 52), (8, 4, 13)])
+def test_wgrad_tensor_core_operand_geometry_vs_simt(upf, level):
+    """The tensor-core weight gradient over the training step's convolution shapes: blocked, pre-swizzled planar operands
+    landed by bulk copies, 1..8 k blocks per ring slot (small operand tiles travel several at a time), one resident CTA
+    with a deep ring for 128-wide N tiles -- against the fp32 SIMT weight gradient (TF32 operands: 2e-3 relative L2).
+    (32 -> 2 at 4x128x416 is the shape whose last A block read past its ring slot before the slot was sized for it.)"""
+    from upflow_pytorch_b200.ops import Slice
+    N, h, w = level
+    g = torch.Generator().manual_seed(3)
+    convs = [(16, 16, 3, 1), (32, 2, 3, 1), (32, 32, 1, 1), (64, 32, 3, 1), (565, 128, 3, 1), (128, 96, 3, 8), (96, 64, 3, 16),
+             (243, 128, 3, 1), (531, 32, 3, 1), (184, 3, 3, 1)]
+    for (cin, cout, ks, dil) in convs:
+        if h * w > 30000 and cin > 32:
+            continue
+        X = torch.randn(N, h, w, (cin + 3) // 4 * 4, generator=g).cuda()
+        G = torch.randn(N, h, w, (cout + 3) // 4 * 4, generator=g).cuda()
+        xs, gs = Slice(X, 0, cin), Slice(G, 0, cout)
+        gw, gb = upf.k_conv_wgrad(xs, gs, ks, 1, dil, want_bias=True, tensor_cores=True)
+        rw, rb = upf.k_conv_wgrad(xs, gs, ks, 1, dil, want_bias=True, tensor_cores=False)
+        rel = ((gw - rw).norm() / rw.norm()).item()
+        assert rel <= 2e-3, ((cin, cout, ks, dil), rel)
+        assert (gb - rb).abs().max().item() <= 1e-3 * rb.abs().max().item() + 1e-4

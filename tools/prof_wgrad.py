@@ -12,6 +12,9 @@ g = torch.Generator().manual_seed(0)
 X = torch.randn(N, h, w, (cin + 31) // 32 * 32, generator=g).cuda()
 G = torch.randn(N, h, w, (cout + 3) // 4 * 4, generator=g).cuda()
 xs, gs = Slice(X, 0, cin), Slice(G, 0, cout)
+import os as _os
+from upflow_pytorch_b200 import _ext as _e
+_e.load().upf_debug_conv_tc(int(_os.environ.get('UPF_TC_DEBUG', '0')))
 for _ in range(3):
     ops.k_conv_wgrad(xs, gs, ks, 1, 1, want_bias=True, tensor_cores=True)
 torch.cuda.synchronize()

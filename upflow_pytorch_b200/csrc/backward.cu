@@ -602,8 +602,9 @@ static long long wgrad_tc_kp(int N, int H, int W, int ks, int dil) {
 // zero k blocks in front of / behind the blocked XT buffer: a tap's vertical shift, dil * Wp pixels
 static int wgrad_tc_kpad(int W, int ks, int dil) { return ks == 1 ? 0 : dil * wgrad_tc_wp(W, ks, dil) / 32; }
 constexpr long long WGRAD_SLACK = 128 * 32;      // a 128-row tile may start at the buffer's last rows: one tile of slack
+constexpr int WGRAD_TAIL = 7;                    // zero k blocks behind the last one: a ring slot of the GEMM holds up to 8 blocks
 static long long wgrad_tc_xt_elems(int N, int H, int W, int C, int ks, int dil) {
-  return (wgrad_tc_kp(N, H, W, ks, dil) / 32 + 2 * wgrad_tc_kpad(W, ks, dil)) * (long long)C * 32 + WGRAD_SLACK;
+  return (wgrad_tc_kp(N, H, W, ks, dil) / 32 + 2 * wgrad_tc_kpad(W, ks, dil) + WGRAD_TAIL) * (long long)C * 32 + WGRAD_SLACK;
 }
 extern "C" long long upf_wgrad_tc_planar_elems(int N, int H, int W, int C, int ksize, int dilation) {
   return wgrad_tc_xt_elems(N, H, W, C, ksize, dilation);
@@ -611,7 +612,7 @@ extern "C" long long upf_wgrad_tc_planar_elems(int N, int H, int W, int C, int k
 extern "C" long long upf_conv2d_wgrad_tc_workspace_elems(int N, int H, int W, int Cin, int Cout, int ksize, int dilation) {
   const long long Kp = wgrad_tc_kp(N, H, W, ksize, dilation);
   const long long cout_pad = (Cout + 15) / 16 * 16;
-  return wgrad_tc_xt_elems(N, H, W, Cin, ksize, dilation) + 3 * cout_pad * Kp + WGRAD_SLACK + cout_pad +
+  return wgrad_tc_xt_elems(N, H, W, Cin, ksize, dilation) + 3 * cout_pad * (Kp + WGRAD_TAIL * 32) + WGRAD_SLACK + cout_pad +
          (long long)UPF_BIAS_SPLITS * Cout + 64;
 }
 // x != NULL: transpose the input here; xt_pre != NULL: the caller already holds the planar padded input (rows of
@@ -636,7 +637,7 @@ static int wgrad_tc_impl(const float* x, int ldx, const float* xt_pre, int xt_ro
   UPF_REQUIRE(!xt_pre || (row0 % 8) == 0, "wgrad_tc_planar: row0 must be a multiple of 8 (swizzle phase of the operand tiles)");
   float* xt = workspace;
   float* gt = xt + (xt_pre ? 0 : (size_t)wgrad_tc_xt_elems(N, H, W, Cin, ksize, dilation));   // [3][Kp / 32][cout_pad][32]: G written at k + (kx-1)*dil
-  float* zb = gt + (size_t)3 * cout_pad * Kp + WGRAD_SLACK;
+  float* zb = gt + (size_t)3 * cout_pad * (Kp + WGRAD_TAIL * 32) + WGRAD_SLACK;
   float* bpart = zb + cout_pad;
   cudaError_t ce = cudaMemsetAsync(workspace, 0, (size_t)((char*)(zb + cout_pad) - (char*)workspace), st);
   if (ce != cudaSuccess) { set_error("wgrad_tc memset: %s", cudaGetErrorString(ce)); return (int)ce; }
@@ -651,7 +652,7 @@ static int wgrad_tc_impl(const float* x, int ldx, const float* xt_pre, int xt_ro
   // the three horizontally shifted copies of G in one pass: one read, three writes
   nhwc_to_planar_padded_kernel<<<dim3(ptiles, (Cout + 31) / 32), 256, 0, st>>>(grad_out, ldg, Cout, gt, Kp, P, H, W, pad, Wp,
                                                                                 ksize == 1 ? 0 : -dilation, ncopies,
-                                                                                cout_pad * Kp, dilation, (int)cout_pad);
+                                                                                cout_pad * (Kp + WGRAD_TAIL * 32), dilation, (int)cout_pad);
   e = check_launch("wgrad_tc_transpose_g");
   if (e) return e;
   int koffs[9], wsel[9];

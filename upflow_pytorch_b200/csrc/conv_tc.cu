@@ -70,6 +70,8 @@ struct TcParams {
   // block 0 of xg (a tap's vertical shift may reach that far); an operand tile is one contiguous run -> one bulk copy
   const float* xg; const float* wg;
   int xrows, wrows, kpad;
+  int stage_bytes;            // bytes of one ring slot: [A blocks: 16 KB][B blocks]
+  int kbs;                    // k blocks per ring slot in weight-gradient mode (1 otherwise): small operand tiles travel 2..8 at a time
   long long wcopy;            // elements between the pre-shifted copies of wg
 };
 
@@ -106,7 +108,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   // access into a generic-address load: measured 4x slower epilogue)
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t b_bytes = (uint32_t)p.BN * 128u;
-  const uint32_t stage_bytes = TC_A_BYTES + ((b_bytes + 1023u) & ~1023u);
+  const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)p.nstage * stage_bytes);
   uint64_t* full = bars;                       // [nstage]
   uint64_t* empty = bars + p.nstage;           // [nstage]
@@ -173,15 +175,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const uint32_t a_dst = smem_u32(base + (size_t)s * stage_bytes);
         const uint32_t b_dst = a_dst + TC_A_BYTES;
         const uint32_t fb = smem_u32(&full[s]);
-        mbar_expect_tx(fb, (uint32_t)p.a_bytes + b_bytes);
+        mbar_expect_tx(fb, (uint32_t)p.kbs * ((uint32_t)p.a_bytes + b_bytes));
         if (p.wgrad) {
           // weight gradient: both operands are BLOCKED planar tensors [k block][row][32 k] (backward.cu), so a box of
           // `rows` x 32 k is one contiguous run of rows x 128 bytes; the tap's vertical shift is a whole number of k blocks
           // (as TMA tensor boxes these tiles cost ~6 ns per 128-byte row whatever the layout: 1.95 ms for the 576->128
           // gradient at 8x64x208; the data is written pre-swizzled by nhwc_to_planar_padded_kernel)
-          const int kblk = kb + p.koffs[n] + p.kpad;
-          bulk_g2s(a_dst, p.xg + ((size_t)kblk * p.xrows + cx) * 32, (uint32_t)p.a_bytes, fb);
-          bulk_g2s(b_dst, p.wg + (size_t)p.wsel[n] * p.wcopy + ((size_t)kb * p.wrows + co0) * 32, b_bytes, fb);
+          // a ring slot holds p.kbs consecutive k blocks of both operands (a K loop of small tiles is bound by its ~0.35 us
+          // hand-off chain per slot, not by bytes: measured 1.4 ms for the 3->16 full-resolution gradient, one block per slot)
+          for (int j = 0; j < p.kbs; ++j) {
+            const int kq = kb * p.kbs + j;
+            bulk_g2s(a_dst + (uint32_t)(j * p.a_bytes), p.xg + ((size_t)(kq + p.koffs[n] + p.kpad) * p.xrows + cx) * 32, (uint32_t)p.a_bytes, fb);
+            bulk_g2s(b_dst + (uint32_t)j * b_bytes, p.wg + (size_t)p.wsel[n] * p.wcopy + ((size_t)kq * p.wrows + co0) * 32, b_bytes, fb);
+          }
         } else {
           const int kc = kb * TC_KC;
           for (int jy = 0; jy < p.nby; ++jy)
@@ -207,11 +213,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
         const uint32_t a_addr = smem_u32(base + (size_t)s * stage_bytes);
-        const uint64_t da = umma_desc_sw128(a_addr);
-        const uint64_t db = umma_desc_sw128(a_addr + TC_A_BYTES);
+        for (int j = 0; j < p.kbs; ++j) {
+          const uint64_t da = umma_desc_sw128(a_addr + (uint32_t)(j * p.a_bytes));
+          const uint64_t db = umma_desc_sw128(a_addr + TC_A_BYTES + (uint32_t)j * b_bytes);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 bytes): advance the start address inside the swizzle atom
-          umma_tf32(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > wi || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 bytes): advance the start address inside the swizzle atom
+            umma_tf32(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > wi || j > 0 || k > 0) ? 1u : 0u);
+        }
         umma_commit(smem_u32(&empty[s]));                      // frees the stage when these MMAs retire
         if (it + 2 >= iters) umma_commit(smem_u32(accum_full));
       }
@@ -385,6 +393,8 @@ int encode_cached(const MapKey& key, CUtensorMap* out, cuuint32_t rank, void* pt
 // (2.855 vs 2.77 ms, tools/ab_conv_tc.py, profiles/r2_ab_conv_tc.txt): the coarse levels are bound by the serial
 // launch -> prologue -> first TMA -> commit -> epilogue chain, not by operand bandwidth.  Kept as an A/B switch.
 static int g_tc_cluster_cap = 0;
+static int g_tc_wgrad_kbs1 = 0;        // 1: one k block per ring slot in the weight-gradient GEMM (A/B switch, upf_debug_conv_tc bit 9)
+static int g_tc_wgrad_one_cta = 1;     // weight-gradient GEMM: one resident CTA with a deep ring (0: two CTAs, two slots each)
 static void pick_tile(int H, int W, int max_tw, int* TH, int* TW) {
   // <= 128 pixels per tile; pick the shape wasting the fewest pixels
   long long best = -1;
@@ -480,8 +490,16 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   }
   const int tiles_x = (Wo + TW - 1) / TW, tiles_y = (Ho + TH - 1) / TH;
   const long long tiles = (long long)tiles_x * tiles_y * N;
-  const int iters_all = taps * kblocks;
   const int a_bytes = TH * TW * 128;
+  // weight gradient: k blocks per ring slot (the blocked operands carry 7 zero blocks of slack behind the last one)
+  int kbs = 1;
+  if (koffs) {
+    const int cpad = (Cout + 15) & ~15;
+    const int bn0 = ((cpad + (cpad + 127) / 128 - 1) / ((cpad + 127) / 128) + 15) & ~15;
+    while (kbs < 8 && 2 * kbs * TW <= 128 && 2 * kbs * (a_bytes + bn0 * 128) <= 32 * 1024) kbs <<= 1;
+    if (g_tc_wgrad_kbs1) kbs = 1;
+  }
+  const int iters_all = taps * ((kblocks + kbs - 1) / kbs);
 
   // N tiling and K split.  Large grids: equal N tiles <= 128 wide, no split.  Small grids (the coarse pyramid levels: 2..30
   // pixel tiles for 148 SMs) are bound by how fast ONE SM can pull its operands out of L2 (~58 B/clk measured,
@@ -571,23 +589,29 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   p.out = out; p.ldo = ldo; p.res = res; p.ldr = ldr; p.bias = bias;
   p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.BN = BN;
   p.TH = TH; p.TW = TW; p.tiles_x = tiles_x; p.tiles_y = tiles_y;
-  p.ks = ks; p.dil = dil; p.stride = stride; p.kblocks = kblocks;
+  p.ks = ks; p.dil = dil; p.stride = stride; p.kblocks = (kblocks + kbs - 1) / kbs;   // ring slots per tap
+  p.kbs = kbs;
   p.bw = bw; p.bh = bh; p.nbx = TW / bw; p.nby = TH / bh; p.b_rows = b_rows; p.nbb = BN / b_rows;
   p.a_bytes = a_bytes;
   p.slope = slope;
   p.flags = flags;
   p.wgrad = koffs ? 1 : 0;
   p.xg = x; p.wg = w_packed; p.xrows = g_tc_xrows; p.wrows = cout_pad; p.kpad = g_tc_kpad;
-  p.wcopy = (long long)cout_pad * cin_pad;
+  p.wcopy = (long long)cout_pad * (cin_pad + 7 * 32);     // copies of GT are (K / 32 + 7) blocks apart
   for (int i = 0; i < 9; ++i) { p.koffs[i] = (koffs && i < N) ? koffs[i] : 0; p.wsel[i] = (koffs && g_tc_wsel && i < N) ? g_tc_wsel[i] : 0; }
   p.tmem_cols = BN <= 16 ? 32 : (BN <= 32 ? 64 : (BN <= 64 ? 128 : 256));   // two accumulators (one per MMA issuer)
-  const int stage_bytes = TC_A_BYTES + ((BN * 128 + 1023) & ~1023);
+  // an MMA reads 128 rows of A from its block's start whatever TW is: the LAST block of a slot must still end inside the slot
+  int stage_bytes = TC_A_BYTES + ((kbs * BN * 128 + 1023) & ~1023);
+  if (stage_bytes < (kbs - 1) * a_bytes + TC_A_BYTES) stage_bytes = (kbs - 1) * a_bytes + TC_A_BYTES;
   const long long ctas = tiles * ntiles_n;
   int ips = (iters_all + splits - 1) / splits;
   while (splits > 1 && (splits - 1) * ips >= iters_all) { splits >>= 1; ips = (iters_all + splits - 1) / splits; }   // no empty CTA
   // stages: two CTAs per SM when the grid is large (epilogue/main-loop overlap across CTAs); a single
   // resident CTA gets the whole shared memory so that more TMA loads are in flight (latency-bound regime)
-  const bool one_cta = ctas * splits <= UPF_NUM_SMS;
+  // (weight gradient with 128-wide N tiles: its operands stream from HBM and two resident CTAs get only two 32 KB slots
+  // each -- measured 1913 us for 576->128 at 8x64x208 against 505 us with ONE resident CTA and a six-slot ring; for
+  // N <= 96 two CTAs stay ahead (257 vs 327 us at 384->96, 333 vs 482 at 480->64).  upf_debug_conv_tc bit 8: A/B switch)
+  const bool one_cta = ctas * splits <= UPF_NUM_SMS || (koffs && BN > 96 && g_tc_wgrad_one_cta);
   int nstage = ((one_cta ? 200 : 108) * 1024) / stage_bytes;
   if (nstage > (one_cta ? 12 : 6)) nstage = one_cta ? 12 : 6;
   nstage &= ~1;        // EVEN: issuer w then owns the stages of parity w and sees every phase of their barriers -- with an odd
@@ -595,6 +619,7 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   if (nstage < 2) nstage = 2;
   if (splits > 1 && (long long)nstage * stage_bytes < 128ll * (BN + 4) * 4) { splits = 1; ips = iters_all; }
   p.nstage = nstage;
+  p.stage_bytes = stage_bytes;
   p.splits = splits; p.ips = ips;
   const size_t smem = (size_t)nstage * stage_bytes + (2 * nstage + 2) * 8 + 16 + BN * 4 + 1024;
   static PerDeviceOnce attr_set;
@@ -636,7 +661,9 @@ int conv_tc_wgrad_gemm(const float* xt, int ldk, const float* gt_packed, const f
 
 // test / tuning hook: small-grid policy of conv_tc (0 = default, 8 / 16 = cost-model policy with that cluster cap)
 extern "C" int upf_debug_conv_tc(int max_cluster) {
-  upf::g_tc_cluster_cap = (max_cluster >= 0 && max_cluster <= 16) ? max_cluster : 0;
+  upf::g_tc_wgrad_one_cta = (max_cluster >= 0 && (max_cluster & 0x100)) ? 0 : 1;
+  upf::g_tc_wgrad_kbs1 = (max_cluster >= 0 && (max_cluster & 0x200)) ? 1 : 0;
+  upf::g_tc_cluster_cap = (max_cluster >= 0 && (max_cluster & 0xff) <= 16) ? (max_cluster & 0xff) : 0;
   return 0;
 }
 
