@@ -213,7 +213,10 @@ corr_fwd_kernel(const T* __restrict__ f1, int ld1, const T* __restrict__ f2, int
     if (y >= H) break;
     T* orow = out + ((size_t)((size_t)n * H + y) * W + x0) * ldo;
     const float* srow = s_out + r * CORR_TX * K::NOUT;
-    if (ldo == K::NOUT) {
+    if (ldo == K::NOUT && sizeof(T) == 2 && ((total | (int)(((size_t)(orow - out)) & 1)) & 1) == 0) {
+      // 2-byte storage: two outputs per 4-byte store (the run starts on an even element and has an even length)
+      for (int e = 2 * threadIdx.x; e < total; e += 2 * K::NT) st2(orow + e, srow[e], srow[e + 1]);
+    } else if (ldo == K::NOUT) {
       for (int e = threadIdx.x; e < total; e += K::NT) st1(orow + e, srow[e]);       // one contiguous run
     } else {
       for (int e = threadIdx.x; e < total; e += K::NT) {

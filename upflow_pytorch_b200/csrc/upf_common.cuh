@@ -109,6 +109,10 @@ __device__ __forceinline__ float ld1(const __nv_bfloat16* p) { return __bfloat16
 __device__ __forceinline__ void st1(float* p, float v) { *p = v; }
 __device__ __forceinline__ void st1(__half* p, float v) { *p = __float2half_rn(v); }
 __device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+// two consecutive elements (4-byte aligned for the 2-byte types)
+__device__ __forceinline__ void st2(float* p, float a, float b) { p[0] = a; p[1] = b; }
+__device__ __forceinline__ void st2(__half* p, float a, float b) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b); }
+__device__ __forceinline__ void st2(__nv_bfloat16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void st4(__half* p, float4 v) {
   const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
