@@ -42,6 +42,7 @@ SIGNATURES = {
     "upf_debug_conv_win": (_I, [_I, _I, _I]),
     "upf_debug_corr_pipe": (_I, [_I]),
     "upf_debug_conv_tc": (_I, [_I]),
+    "upf_debug_wgrad_taps": (_I, [_I]),
     "upf_conv2d_wgrad_workspace_elems": (_LL, [_I, _I, _I, _I, _I, _I, _I, _I]),
     "upf_conv2d_wgrad": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "upf_conv2d_wgrad_tc_workspace_elems": (_LL, [_I, _I, _I, _I, _I, _I, _I]),

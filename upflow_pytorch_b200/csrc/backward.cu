@@ -191,6 +191,12 @@ reduce_splits_kernel(const float* __restrict__ part, float* __restrict__ out, lo
   }
 }
 
+static unsigned grid_for(long long n);
+int launch_reduce_splits(const float* part, float* out, long long n, int splits, cudaStream_t st) {
+  reduce_splits_kernel<<<grid_for(n), 256, 0, st>>>(part, out, n, splits);
+  return check_launch("reduce_splits");
+}
+
 // ------------------------------------------------------------------------------------------------ pointwise
 enum { PW_LRELU_BWD = 0, PW_SIGMOID = 1, PW_SIGMOID_BWD = 2 };
 
@@ -392,7 +398,10 @@ nhwc_to_planar_padded_kernel(const float* __restrict__ src, int ld, int C, float
 }
 
 int conv_tc_wgrad_gemm(const float* xt, int ldk, const float* gt_packed, const float* zero_bias, float* gw, int taps,
-                       int Cin, int Cout, int K, const int* koffs, const int* wsel, int xt_rows, int kpad, cudaStream_t st);
+                       int Cin, int Cout, int K, const int* koffs, const int* wsel, int xt_rows, int kpad, long long gcopy, cudaStream_t st);
+int wgrad_taps_gemm(const float* xt, int xt_rows, const float* gt, long long gcopy, int cout_pad, float* part, float* gw,
+                    int Cin, int Cout, int kblocks, const int* koff3, cudaStream_t st, int* taken);
+long long wgrad_taps_part_elems(int Cin, int Cout);
 
 
 // ---- 3xTF32 support (engine precision "tf32x3"): an fp32 value x is hi + lo with hi = x truncated to TF32 (what
@@ -606,14 +615,18 @@ constexpr int WGRAD_TAIL = 7;                    // zero k blocks behind the las
 static long long wgrad_tc_xt_elems(int N, int H, int W, int C, int ks, int dil) {
   return (wgrad_tc_kp(N, H, W, ks, dil) / 32 + 2 * wgrad_tc_kpad(W, ks, dil) + WGRAD_TAIL) * (long long)C * 32 + WGRAD_SLACK;
 }
+// one pre-shifted copy of GT: [kpad zero blocks][K / 32 blocks][kpad + tail zero blocks] x cout_pad rows x 32
+static long long wgrad_tc_gt_copy_elems(int N, int H, int W, long long cout_pad, int ks, int dil) {
+  return (wgrad_tc_kp(N, H, W, ks, dil) / 32 + 2 * wgrad_tc_kpad(W, ks, dil) + WGRAD_TAIL) * cout_pad * 32;
+}
 extern "C" long long upf_wgrad_tc_planar_elems(int N, int H, int W, int C, int ksize, int dilation) {
   return wgrad_tc_xt_elems(N, H, W, C, ksize, dilation);
 }
 extern "C" long long upf_conv2d_wgrad_tc_workspace_elems(int N, int H, int W, int Cin, int Cout, int ksize, int dilation) {
   const long long Kp = wgrad_tc_kp(N, H, W, ksize, dilation);
   const long long cout_pad = (Cout + 15) / 16 * 16;
-  return wgrad_tc_xt_elems(N, H, W, Cin, ksize, dilation) + 3 * cout_pad * (Kp + WGRAD_TAIL * 32) + WGRAD_SLACK + cout_pad +
-         (long long)UPF_BIAS_SPLITS * Cout + 64;
+  return wgrad_tc_xt_elems(N, H, W, Cin, ksize, dilation) + 3 * wgrad_tc_gt_copy_elems(N, H, W, cout_pad, ksize, dilation) +
+         WGRAD_SLACK + cout_pad + (long long)UPF_BIAS_SPLITS * Cout + (cout_pad <= 32 && ksize == 3 ? upf::wgrad_taps_part_elems(Cin, Cout) : 0) + 64;
 }
 // x != NULL: transpose the input here; xt_pre != NULL: the caller already holds the planar padded input (rows of
 // upf_wgrad_tc_transpose_input's output -- a dense block transposes its whole buffer ONCE and every convolution of the
@@ -637,8 +650,11 @@ static int wgrad_tc_impl(const float* x, int ldx, const float* xt_pre, int xt_ro
   UPF_REQUIRE(!xt_pre || (row0 % 8) == 0, "wgrad_tc_planar: row0 must be a multiple of 8 (swizzle phase of the operand tiles)");
   float* xt = workspace;
   float* gt = xt + (xt_pre ? 0 : (size_t)wgrad_tc_xt_elems(N, H, W, Cin, ksize, dilation));   // [3][Kp / 32][cout_pad][32]: G written at k + (kx-1)*dil
-  float* zb = gt + (size_t)3 * cout_pad * (Kp + WGRAD_TAIL * 32) + WGRAD_SLACK;
+  const long long gcopy = wgrad_tc_gt_copy_elems(N, H, W, cout_pad, ksize, dilation);
+  float* gt0 = gt + (size_t)kpad * cout_pad * 32;           // block 0 of copy 0 (kpad zero blocks in front of every copy)
+  float* zb = gt + (size_t)3 * gcopy + WGRAD_SLACK;
   float* bpart = zb + cout_pad;
+  float* tpart = bpart + (size_t)UPF_BIAS_SPLITS * Cout;    // partial sums of the taps-along-N kernel (Cout <= 32)
   cudaError_t ce = cudaMemsetAsync(workspace, 0, (size_t)((char*)(zb + cout_pad) - (char*)workspace), st);
   if (ce != cudaSuccess) { set_error("wgrad_tc memset: %s", cudaGetErrorString(ce)); return (int)ce; }
   const unsigned ptiles = (unsigned)((P + 31) / 32);
@@ -650,9 +666,9 @@ static int wgrad_tc_impl(const float* x, int ldx, const float* xt_pre, int xt_ro
     if (e) return e;
   }
   // the three horizontally shifted copies of G in one pass: one read, three writes
-  nhwc_to_planar_padded_kernel<<<dim3(ptiles, (Cout + 31) / 32), 256, 0, st>>>(grad_out, ldg, Cout, gt, Kp, P, H, W, pad, Wp,
+  nhwc_to_planar_padded_kernel<<<dim3(ptiles, (Cout + 31) / 32), 256, 0, st>>>(grad_out, ldg, Cout, gt0, Kp, P, H, W, pad, Wp,
                                                                                 ksize == 1 ? 0 : -dilation, ncopies,
-                                                                                cout_pad * (Kp + WGRAD_TAIL * 32), dilation, (int)cout_pad);
+                                                                                gcopy, dilation, (int)cout_pad);
   e = check_launch("wgrad_tc_transpose_g");
   if (e) return e;
   int koffs[9], wsel[9];
@@ -661,9 +677,21 @@ static int wgrad_tc_impl(const float* x, int ldx, const float* xt_pre, int xt_ro
     koffs[t] = ksize == 1 ? 0 : (ky - 1) * dilation * (Wp / 32);   // in k blocks of 32 (Wp is a multiple of 32)
     wsel[t] = ksize == 1 ? 0 : kx;
   }
-  e = conv_tc_wgrad_gemm(xt_pre ? xt_pre + (size_t)row0 * 32 : xt, (int)Kp, gt, zb, grad_w, taps, Cin, Cout, (int)Kp, koffs, wsel,
-                         xt_pre ? xt_rows : Cin, kpad, st);
-  if (e) return e;
+  {
+    // few output channels: the nine taps along N, the input tile loaded once (wgrad_taps.cu)
+    int taken = 0;
+    if (ksize == 3) {
+      const int koff3[3] = {-dilation * (Wp / 32), 0, dilation * (Wp / 32)};
+      const float* xt0 = xt_pre ? xt_pre + (size_t)row0 * 32 + (size_t)kpad * xt_rows * 32 : xt + (size_t)kpad * Cin * 32;
+      e = wgrad_taps_gemm(xt0, xt_pre ? xt_rows : Cin, gt0, gcopy, (int)cout_pad, tpart, grad_w, Cin, Cout, (int)(Kp / 32), koff3, st, &taken);
+      if (e) return e;
+    }
+    if (!taken) {
+      e = conv_tc_wgrad_gemm(xt_pre ? xt_pre + (size_t)row0 * 32 : xt, (int)Kp, gt0, zb, grad_w, taps, Cin, Cout, (int)Kp, koffs, wsel,
+                             xt_pre ? xt_rows : Cin, kpad, gcopy, st);
+      if (e) return e;
+    }
+  }
   if (grad_bias) {
     int cw = 1;
     while (cw < Cout && cw < 256) cw <<= 1;

@@ -458,6 +458,7 @@ static thread_local const int* g_tc_koffs = nullptr;      // set by conv_tc_wgra
 static thread_local const int* g_tc_wsel = nullptr;
 static thread_local int g_tc_xrows = 0;                   // rows per k block of the blocked planar XT buffer
 static thread_local int g_tc_kpad = 0;                    // zero k blocks in front of XT's block 0
+static thread_local long long g_tc_gcopy = 0;             // elements between the pre-shifted copies of GT
 
 int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
                   const float* res, int ldr, int N, int H, int W, int Cin, int Cout, int ks, int stride, int dil,
@@ -597,7 +598,7 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
   p.flags = flags;
   p.wgrad = koffs ? 1 : 0;
   p.xg = x; p.wg = w_packed; p.xrows = g_tc_xrows; p.wrows = cout_pad; p.kpad = g_tc_kpad;
-  p.wcopy = (long long)cout_pad * (cin_pad + 7 * 32);     // copies of GT are (K / 32 + 7) blocks apart
+  p.wcopy = g_tc_gcopy;
   for (int i = 0; i < 9; ++i) { p.koffs[i] = (koffs && i < N) ? koffs[i] : 0; p.wsel[i] = (koffs && g_tc_wsel && i < N) ? g_tc_wsel[i] : 0; }
   p.tmem_cols = BN <= 16 ? 32 : (BN <= 32 ? 64 : (BN <= 64 ? 128 : 256));   // two accumulators (one per MMA issuer)
   // an MMA reads 128 rows of A from its block's start whatever TW is: the LAST block of a slot must still end inside the slot
@@ -650,8 +651,8 @@ int conv2d_fwd_tc(const float* x, int ldx, const float* w_packed, const float* b
 // dW[tap][ci][co] = sum_k XT[ci][k + koffs[tap]] * GT[wsel[tap]][co][k]  (backward.cu): the tensor-core GEMM of this file with the
 // taps as "images" (out is [taps][Cin][Cout]), M = Cin, K = the padded pixel index, cluster split-K
 int conv_tc_wgrad_gemm(const float* xt, int ldk, const float* gt_packed, const float* zero_bias, float* gw, int taps,
-                       int Cin, int Cout, int K, const int* koffs, const int* wsel, int xt_rows, int kpad, cudaStream_t st) {
-  g_tc_koffs = koffs; g_tc_wsel = wsel; g_tc_xrows = xt_rows; g_tc_kpad = kpad;
+                       int Cin, int Cout, int K, const int* koffs, const int* wsel, int xt_rows, int kpad, long long gcopy, cudaStream_t st) {
+  g_tc_koffs = koffs; g_tc_wsel = wsel; g_tc_xrows = xt_rows; g_tc_kpad = kpad; g_tc_gcopy = gcopy;
   const int e = conv2d_fwd_tc(xt, ldk, gt_packed, zero_bias, gw, Cout, nullptr, 0, taps, 1, Cin, K, Cout, 1, 1, 1, 1.0f, 0, st);
   g_tc_koffs = nullptr; g_tc_wsel = nullptr;
   return e;
