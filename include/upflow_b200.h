@@ -224,9 +224,9 @@ int upf_debug_conv_win(int enabled, int min_cin, int force_m);
 /* test / tuning hook: small-grid policy of conv_tc.cu: 0 = default (K split over <= 8 CTAs); 8 / 16 = experimental cost-model
  * policy (narrow N tiles, whole-row pixel tiles, clusters up to that size; measured slower, profiles/r2_ab_conv_tc.txt) */
 int upf_debug_conv_tc(int max_cluster);
-/* test / tuning hook: 0 routes the few-output-channel weight gradients (Cout <= 32, 3x3) back to conv_tc.cu's per-tap GEMMs
- * instead of the taps-along-N kernel (wgrad_taps.cu) */
-int upf_debug_wgrad_taps(int enabled);
+/* test / tuning hook: largest padded Cout whose 3x3 weight gradient takes the taps-along-N kernel (wgrad_taps.cu); 0 routes
+ * every shape to conv_tc.cu's per-tap GEMMs, < 0 restores the default */
+int upf_debug_wgrad_taps(int max_cout_pad);
 /* test / tuning hook: 0 routes large-image correlations to the non-pipelined tiled kernel (corr.cu) */
 int upf_debug_corr_pipe(int enabled);
 /* debug: device buffer of 64 int64 receiving CTA 0's per-role wait / busy cycle counters of the halo / window /

@@ -15,6 +15,7 @@ xs, gs = Slice(X, 0, cin), Slice(G, 0, cout)
 import os as _os
 from upflow_pytorch_b200 import _ext as _e
 _e.load().upf_debug_conv_tc(int(_os.environ.get('UPF_TC_DEBUG', '0')))
+if _os.environ.get('UPF_TAPS'): _e.load().upf_debug_wgrad_taps(int(_os.environ['UPF_TAPS']))
 for _ in range(3):
     ops.k_conv_wgrad(xs, gs, ks, 1, 1, want_bias=True, tensor_cores=True)
 torch.cuda.synchronize()

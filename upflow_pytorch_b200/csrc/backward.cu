@@ -626,7 +626,7 @@ extern "C" long long upf_conv2d_wgrad_tc_workspace_elems(int N, int H, int W, in
   const long long Kp = wgrad_tc_kp(N, H, W, ksize, dilation);
   const long long cout_pad = (Cout + 15) / 16 * 16;
   return wgrad_tc_xt_elems(N, H, W, Cin, ksize, dilation) + 3 * wgrad_tc_gt_copy_elems(N, H, W, cout_pad, ksize, dilation) +
-         WGRAD_SLACK + cout_pad + (long long)UPF_BIAS_SPLITS * Cout + (cout_pad <= 32 && ksize == 3 ? upf::wgrad_taps_part_elems(Cin, Cout) : 0) + 64;
+         WGRAD_SLACK + cout_pad + (long long)UPF_BIAS_SPLITS * Cout + (ksize == 3 ? upf::wgrad_taps_part_elems(Cin, Cout) : 0) + 64;
 }
 // x != NULL: transpose the input here; xt_pre != NULL: the caller already holds the planar padded input (rows of
 // upf_wgrad_tc_transpose_input's output -- a dense block transposes its whole buffer ONCE and every convolution of the

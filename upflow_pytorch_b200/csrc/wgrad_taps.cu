@@ -1,4 +1,4 @@
-// Tensor-core weight gradient of a 3x3 convolution with FEW output channels (Cout <= 32): the nine taps along N.
+// Tensor-core weight gradient of a 3x3 convolution: the nine taps along N, output channels in parts of <= 32.
 //
 // conv_tc.cu's weight-gradient mode runs the nine tap GEMMs dW[tap] = XT(shifted by the tap) . GT^T as nine sets of CTAs:
 // every tap streams its own 128-row tile of the planar input, 162 KB of operand tiles per 32 pixels of K for an M tile, and
@@ -10,6 +10,9 @@
 // pre-shifted copies GT_kx, as in backward.cu) into NINE accumulators side by side in tensor memory (9 x BN <= 288
 // columns): 16 KB + 9 x BN x 128 B per 32 pixels of K and M tile.  K is split over the GRID (not a cluster: the split can be
 // as wide as the chip), partial sums go to a workspace and are added in split order by reduce_splits_kernel (deterministic).
+// Wider layers run as N parts of 32 channels in separate CTAs (nine 32-column accumulators each): measured against the
+// per-tap GEMMs at 8x64x208 -- 128->128 139 vs 192 us, 96->64 80 vs 187, 480->64 244 vs 378, 256->128 246 vs 377,
+// 576->128 573 vs 580, 384->96 285 vs 271.
 // Operands are the blocked, pre-swizzled planar tensors of backward.cu ([k block][row][32]: one bulk copy per tile).
 // Roles: warp 0 = producer (one thread), warp 1 = MMA issuer (one thread, 36 MMAs per ring slot into nine independent
 // accumulators), warps 2..5 = epilogue.
@@ -51,6 +54,7 @@ wgrad_taps_kernel(const WtParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;                                      // first input channel (row of XT) of this M tile
   const int split = blockIdx.y;
+  const int co0 = blockIdx.z * p.BN;                                    // first output channel of this N part
   const int kb0 = split * p.bps;
   const int iters = (p.kblocks - kb0 < p.bps ? p.kblocks - kb0 : p.bps);   // >= 1 by construction
 
@@ -87,7 +91,7 @@ wgrad_taps_kernel(const WtParams p) {
         for (int t = 0; t < 9; ++t) {
           const int ky = t / 3, kx = t - ky * 3;
           wt_bulk_g2s(a_dst + WT_A_BYTES + (uint32_t)t * b_bytes,
-                      p.gg + (size_t)kx * p.gcopy + (long long)(j - p.koff[ky]) * p.grows * 32, b_bytes, fb);
+                      p.gg + (size_t)kx * p.gcopy + ((long long)(j - p.koff[ky]) * p.grows + co0) * 32, b_bytes, fb);
         }
       }
     }
@@ -132,7 +136,7 @@ wgrad_taps_kernel(const WtParams p) {
           float* o = dst + ((size_t)t * p.Cin + ci) * p.Cout;
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj)
-            if (c0 + jj < p.Cout) o[c0 + jj] = __uint_as_float(v[jj]);
+            if (co0 + c0 + jj < p.Cout) o[co0 + c0 + jj] = __uint_as_float(v[jj]);
         }
       }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -146,7 +150,7 @@ wgrad_taps_kernel(const WtParams p) {
 
 int launch_reduce_splits(const float* part, float* out, long long n, int splits, cudaStream_t st);   // backward.cu
 
-static int g_wgrad_taps = 1;          // upf_debug_wgrad_taps: 0 routes every shape back to conv_tc's weight-gradient mode
+static int g_wgrad_taps = 128;        // largest padded Cout served here (upf_debug_wgrad_taps; 0 routes every shape to conv_tc's weight-gradient mode)
 
 // xt: block 0 of the blocked input (rows [row0, row0 + Cin) of a buffer with xt_rows rows per block: pass xt + row0 * 32);
 // gt: block 0 of copy 0 (the caller guarantees max|koff| zero blocks in front of and behind every copy).
@@ -154,19 +158,19 @@ static int g_wgrad_taps = 1;          // upf_debug_wgrad_taps: 0 routes every sh
 int wgrad_taps_gemm(const float* xt, int xt_rows, const float* gt, long long gcopy, int cout_pad, float* part, float* gw,
                     int Cin, int Cout, int kblocks, const int* koff3, cudaStream_t st, int* taken) {
   *taken = 0;
-  if (!g_wgrad_taps || cout_pad > 32 || kblocks < 8) return 0;
+  if (cout_pad > g_wgrad_taps || kblocks < 8) return 0;
   *taken = 1;
   WtParams p;
   p.xg = xt; p.xrows = xt_rows; p.gg = gt; p.grows = cout_pad; p.gcopy = gcopy;
   for (int i = 0; i < 3; ++i) p.koff[i] = koff3[i];
   p.kblocks = kblocks;
   p.Cin = Cin; p.Cout = Cout; p.BN = cout_pad <= 16 ? 16 : 32;
-  if (p.BN != cout_pad) { set_error("wgrad_taps: cout_pad %d is not 16 or 32", cout_pad); return UPF_EINVAL; }
+  const int nparts = (cout_pad + p.BN - 1) / p.BN;             // N parts of 32 channels: nine accumulators of 32 columns each per CTA
   int tw = 8;
   while (tw < 128 && tw < Cin) tw <<= 1;
   p.a_bytes = tw * 128;
   const int mtiles = (Cin + 127) / 128;
-  int splits = UPF_NUM_SMS / mtiles;
+  int splits = UPF_NUM_SMS / (mtiles * nparts);
   if (splits > kblocks / 8) splits = kblocks / 8;              // at least 8 k blocks per split
   if (splits < 1) splits = 1;
   p.bps = (kblocks + splits - 1) / splits;
@@ -184,7 +188,7 @@ int wgrad_taps_gemm(const float* xt, int xt_rows, const float* gt, long long gco
     if (e != cudaSuccess) { set_error("wgrad_taps smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     attr_set.mark();
   }
-  wgrad_taps_kernel<<<dim3((unsigned)mtiles, (unsigned)splits), WT_THREADS, smem, st>>>(p);
+  wgrad_taps_kernel<<<dim3((unsigned)mtiles, (unsigned)splits, (unsigned)nparts), WT_THREADS, smem, st>>>(p);
   int e = check_launch("wgrad_taps");
   if (e) return e;
   return launch_reduce_splits(part, gw, 9ll * Cin * Cout, splits, st);
@@ -194,7 +198,7 @@ long long wgrad_taps_part_elems(int Cin, int Cout) { return (long long)UPF_NUM_S
 
 }  // namespace upf
 
-extern "C" int upf_debug_wgrad_taps(int enabled) {
-  upf::g_wgrad_taps = enabled ? 1 : 0;
+extern "C" int upf_debug_wgrad_taps(int max_cout_pad) {
+  upf::g_wgrad_taps = max_cout_pad < 0 ? 128 : max_cout_pad;
   return 0;
 }
