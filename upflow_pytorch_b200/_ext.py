@@ -108,6 +108,8 @@ def load():
         fn.argtypes = args
     if lib.upf_abi_version() != ABI_VERSION:
         raise UpflowLibraryError("ABI version mismatch")
+    if os.environ.get("UPF_WGRAD_TAPS"):          # A/B runs: largest padded Cout served by the taps-along-N weight gradient
+        lib.upf_debug_wgrad_taps(int(os.environ["UPF_WGRAD_TAPS"]))
     _lib = lib
     return lib
 

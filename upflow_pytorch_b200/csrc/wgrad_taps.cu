@@ -12,7 +12,8 @@
 // as wide as the chip), partial sums go to a workspace and are added in split order by reduce_splits_kernel (deterministic).
 // Wider layers run as N parts of 32 channels in separate CTAs (nine 32-column accumulators each): measured against the
 // per-tap GEMMs at 8x64x208 -- 128->128 139 vs 192 us, 96->64 80 vs 187, 480->64 244 vs 378, 256->128 246 vs 377,
-// 576->128 573 vs 580, 384->96 285 vs 271.
+// 576->128 573 vs 580, 384->96 285 vs 271.  INSIDE the training step, though, serving the 96- and 128-wide layers here costs
+// 2 ms (49.5 vs 46.7-48.1 ms per step, same process, UPF_WGRAD_TAPS = 128 / 64 / 32): the default limit is 64.
 // Operands are the blocked, pre-swizzled planar tensors of backward.cu ([k block][row][32]: one bulk copy per tile).
 // Roles: warp 0 = producer (one thread), warp 1 = MMA issuer (one thread, 36 MMAs per ring slot into nine independent
 // accumulators), warps 2..5 = epilogue.
@@ -150,7 +151,7 @@ wgrad_taps_kernel(const WtParams p) {
 
 int launch_reduce_splits(const float* part, float* out, long long n, int splits, cudaStream_t st);   // backward.cu
 
-static int g_wgrad_taps = 128;        // largest padded Cout served here (upf_debug_wgrad_taps; 0 routes every shape to conv_tc's weight-gradient mode)
+static int g_wgrad_taps = 64;         // largest padded Cout served here (upf_debug_wgrad_taps; 0 routes every shape to conv_tc's weight-gradient mode)
 
 // xt: block 0 of the blocked input (rows [row0, row0 + Cin) of a buffer with xt_rows rows per block: pass xt + row0 * 32);
 // gt: block 0 of copy 0 (the caller guarantees max|koff| zero blocks in front of and behind every copy).
@@ -199,6 +200,6 @@ long long wgrad_taps_part_elems(int Cin, int Cout) { return (long long)UPF_NUM_S
 }  // namespace upf
 
 extern "C" int upf_debug_wgrad_taps(int max_cout_pad) {
-  upf::g_wgrad_taps = max_cout_pad < 0 ? 128 : max_cout_pad;
+  upf::g_wgrad_taps = max_cout_pad < 0 ? 64 : max_cout_pad;
   return 0;
 }
