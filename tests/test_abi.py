@@ -78,6 +78,20 @@ def test_bad_arguments_return_codes_not_crashes(lib_path):
     rc = lib.upf_conv2d_wgrad_tc_planar(None, 8, 0, P, 8, P, P, P, 1, 8, 8, 8, 8, 3, 1, None)
     assert rc == -1 and b"null" in lib.upf_last_error()
     assert lib.upf_loss_workspace_elems() >= 2 * 148
+    # round 2: the planar (NCHW) correlation and the fp16 / bf16 storage variants
+    L3 = ctypes.c_longlong * 3
+    dense = lambda c: L3(8, 64, c * 64)
+    rc = lib.upf_corr_lrelu_fwd_planar(P, dense(32), P, dense(32), P, dense(81), 1, 8, 8, 32, 5, 0, 0.1, 0, None)
+    assert rc == -2 and b"max_disp > 4" in lib.upf_last_error()            # UPF_ENOTSUP: the pixel-major kernel serves d = 5, 6
+    rc = lib.upf_corr_lrelu_fwd_planar(P, L3(6, 48, 1536), P, L3(6, 48, 1536), P, L3(8, 64, 5184), 1, 8, 6, 32, 4, 0, 0.1, 0, None)
+    assert rc == -2 and b"multiples of 4" in lib.upf_last_error()           # TMA needs 16-byte pitches
+    rc = lib.upf_corr_lrelu_fwd_planar(P, dense(32), P, dense(32), P, dense(81), 1, 8, 8, 32, 4, 3, 0.1, 0, None)
+    assert rc == -1 and b"batch shift" in lib.upf_last_error()
+    rc = lib.upf_corr_lrelu_fwd_lp(P, 32, P, 32, P, 81, 7, 1, 8, 8, 32, 4, None, None, 0, 0.1, None)
+    assert rc == -1 and b"dtype" in lib.upf_last_error()
+    rc = lib.upf_warp_fwd_lp(P, 32, P, 2, P, 32, 0, 1, 8, 8, 32, 0, 1.0, 0, None, None)
+    assert rc == -1 and b"dtype" in lib.upf_last_error()
+    assert lib.upf_wgrad_tc_planar_elems(2, 8, 8, 16, 3, 1) > 16 * lib.upf_wgrad_tc_planar_pitch(2, 8, 8, 3, 1)   # k padding + slack
     assert lib.upf_wgrad_tc_planar_pitch(2, 8, 8, 3, 1) % 32 == 0
 
 
