@@ -200,6 +200,32 @@ int upf_conv2d_fwd(const float* x, int ldx, const float* w, const float* bias,
                    int N, int H, int W, int Cin, int Cout, int ksize, int stride, int dilation,
                    float slope, int precision, void* stream);
 
+/* A CHAIN of dependent stride-1 convolutions on ONE small feature map [N,H,W] in one persistent launch (conv_chain.cu):
+ * the 19 convolutions a coarse pyramid level runs back to back -- FlowEstimatorDense_v2.forward
+ * (model/pwc_modules.py:279-286), ContextNetwork_v2_.forward (:401-412), sgu_model's dense block
+ * (model/upflow.py:52-60), as called from UPFlow_net.decode_level_res (model/upflow.py:565-572) -- each of which is
+ * 0.1-5 GFLOP and costs 7-18 us as a launch of its own.  Layer l is exactly upf_conv2d_fwd(UPF_CONV_TF32) with
+ * stride 1 on the same packed weights: out = lrelu(conv(x) + bias) (+ residual), `flags` as there
+ * (UPF_FLAG_ROUND_TF32); layer l may read what layers < l wrote (and nothing a later layer writes).  out2 (nullable):
+ * a second copy of the result rounded to TF32 (decode_level_res feeds flow_up + flow_res to the context network, :567-569).
+ * Results equal upf_conv2d_fwd's up to the order of the fp32 partial sums over K (bitwise reproducible run to run).
+ * The launch occupies most SMs with a co-resident grid (layers are separated by a grid-wide barrier): issue chains
+ * of one device from ONE stream at a time.  1 <= n_layers <= 16, Cout <= 1024. */
+typedef struct {
+  const float* x; int ldx;            /* input [N,H,W,>=Cin], pitch ldx (multiple of 4, 16-byte aligned base) */
+  const float* w_packed;              /* upf_conv_tc_pack_weights layout */
+  const float* bias;
+  float* out; int ldo;
+  const float* residual; int ldr;     /* nullable, added after the activation */
+  float* out2; int ldo2;              /* nullable */
+  int Cin, Cout, ksize, dilation;
+  float slope;
+  int flags;
+} upf_chain_layer;
+int upf_conv_chain_fwd(const upf_chain_layer* layers, int n_layers, int N, int H, int W, void* stream);
+/* test / tuning hook: cluster size (K split, 1/2/4/8) and number of clusters (0 = as many as are co-resident) of conv_chain.cu */
+int upf_debug_conv_chain(int cluster_size, int n_clusters);
+
 /* Second half of a 3x3 convolution with very few output channels run as "expand, then combine the taps" (same
  * reference routine as upf_conv2d_fwd: conv(), model/pwc_modules.py:10-31).  The first half is upf_conv2d_fwd with
  * ksize 1 and 9*Cout output channels, Y[p][tap*Cout+co] = sum_ci X[p][ci]*W[co][ci][tap]; this gathers

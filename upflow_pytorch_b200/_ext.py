@@ -34,6 +34,8 @@ SIGNATURES = {
     "upf_resize_bilinear": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _c.POINTER(_F), _P]),
     "upf_sgu_blend": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     "upf_conv2d_fwd": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P]),
+    "upf_conv_chain_fwd": (_I, [_P, _I, _I, _I, _I, _P]),
+    "upf_debug_conv_chain": (_I, [_I, _I]),
     "upf_conv3x3_tap_combine": (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P]),
     "upf_conv_tc_packed_elems": (_LL, [_I, _I, _I]),
     "upf_conv_tc_pack_weights": (_I, [_P, _P, _I, _I, _I, _P]),
@@ -74,6 +76,14 @@ SIGNATURES = {
     "upf_nhwc_to_nchw": (_I, [_P, _I, _P, _I, _I, _I, _I, _P]),
     "upf_copy_channels": (_I, [_P, _I, _P, _I, _LL, _I, _I, _P]),
 }
+
+
+
+class ChainLayer(ctypes.Structure):
+    """upf_chain_layer (include/upflow_b200.h)"""
+    _fields_ = [("x", _P), ("ldx", _I), ("w_packed", _P), ("bias", _P), ("out", _P), ("ldo", _I), ("residual", _P), ("ldr", _I),
+                ("out2", _P), ("ldo2", _I), ("Cin", _I), ("Cout", _I), ("ksize", _I), ("dilation", _I), ("slope", _F), ("flags", _I)]
+
 
 CONV_FP32 = 0
 CONV_TF32 = 1

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "lib", "libupflow_b200.so")
-SOURCES = ["abi.cu", "corr.cu", "corr_pipe.cu", "corr_planar.cu", "warp.cu", "resize_blend.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu", "conv_win.cu", "backward.cu", "wgrad_taps.cu", "loss.cu"]
+SOURCES = ["abi.cu", "corr.cu", "corr_pipe.cu", "corr_planar.cu", "warp.cu", "resize_blend.cu", "conv_simt.cu", "conv_tc.cu", "conv_chain.cu", "conv_halo.cu", "conv_win.cu", "backward.cu", "wgrad_taps.cu", "loss.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

@@ -265,6 +265,7 @@ static int g_halo_bo_mode = 0;   // measured on B200: the 128-byte swizzle is ap
 extern int g_tc_box_rows;
 extern int g_tc_pdl;
 static int g_halo_enabled = 1;
+static int g_halo_two_cta = 0;     // A/B (upf_debug_conv_halo enabled bit 1): 8x16-pixel tiles with ~108 KB rings, two resident CTAs per SM
 static int g_halo_min_cin = 64;    // A/B on the whole KITTI forward (tools/ab_forward.py): off 3.83 ms, >=192 3.72, >=64 3.60, all 3.61
 long long* g_halo_probe = nullptr;
 
@@ -278,6 +279,10 @@ int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float*
   // two M-tiles per CTA when that still gives every SM work; else one
   int MT = 2;
   if ((long long)tiles_x * ((H + 31) / 32) * N < UPF_NUM_SMS) MT = 1;
+  // two resident CTAs per SM (small tiles, short rings): one CTA's prologue / epilogue and commit bubbles run under the
+  // other's MMAs, and the hardware balances the tail at 128-pixel granularity
+  bool two_cta = g_halo_two_cta && MT == 2 && (16 + 2 * dil) * HC_ROW_BYTES * 2 + 2 * 128 * 128 <= 108 * 1024;
+  if (two_cta) MT = 1;
   const int tiles_y = (H + 16 * MT - 1) / (16 * MT);
   const long long tiles = (long long)tiles_x * tiles_y * N;
   if (tiles < 96) return 0;                      // coarse levels: the cluster split-K kernel is the better fit
@@ -325,7 +330,7 @@ int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float*
   p.probe = g_halo_probe;
   p.tmem_cols = 128 * MT;                      // lanes = channels, columns = pixels
   // ring depths within ~212 KB: at least 2 A stages, then as many B stages as fit (3..8)
-  const int budget = 212 * 1024;
+  const int budget = two_cta ? 108 * 1024 : 212 * 1024;
   int na = (kblocks >= 3 && 3 * p.a_bytes + 4 * p.b_stage_bytes <= budget) ? 3 : 2;
   if (na > kblocks) na = kblocks < 1 ? 1 : kblocks;
   int nb = (budget - na * p.a_bytes) / p.b_stage_bytes;
@@ -370,6 +375,7 @@ extern "C" int upf_debug_probe(void* device_buffer_8x_int64) {
 
 extern "C" int upf_debug_conv_halo(int enabled, int bo_mode) {
   upf::g_halo_enabled = enabled & 1;
+  upf::g_halo_two_cta = (enabled >> 1) & 1;
   upf::g_halo_bo_mode = bo_mode & 7;
   upf::g_tc_pdl = (bo_mode & 8) ? 0 : 1;
   if ((bo_mode >> 8) & 0xff) upf::g_tc_box_rows = (bo_mode >> 8) & 0xff;     // tuning: rows per TMA box in bits 8..15 (0 = keep)

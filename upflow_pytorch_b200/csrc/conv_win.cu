@@ -273,7 +273,8 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
   const int useful = CW_POS - 2 * dil;
   const int tiles_x = (W + useful - 1) / useful;
   const int b_stage_bytes = BN * 128;                        // multiple of 2048
-  const int budget = 224 * 1024;
+  const bool two_cta = (g_win_force_m & 16) != 0;              // A/B: ~108 KB rings, two resident CTAs per SM
+  const int budget = two_cta ? 108 * 1024 : 224 * 1024;
   // units per CTA and issuer split: minimise waves x (time of one tap), modelled from the microbenchmark --
   // one issuer needs ~(490 + 145 m) cycles per tap (4m MMAs + commit + poll), two run in parallel, and the tensor
   // pipe needs 4 m T(N) cycles per tap, T = 40 / 49 / 57 / 65 cycles at N <= 32 / 64 / 96 / 128.
@@ -287,11 +288,13 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
     if (g_win_force_m & 8) split = 0;
     if (!split && (cand * BN > 512 || cand < 2)) continue;
     const int a_bytes = (4 * cand + 2 * dil) * CW_ROW_BYTES;
-    if (2 * a_bytes + 3 * b_stage_bytes > budget) continue;
+    if (2 * a_bytes + (two_cta ? 2 : 3) * b_stage_bytes > budget) continue;
+    if (two_cta && (split ? 2 : 1) * cand * BN > 256) continue;          // both CTAs' accumulators must fit the 512 TMEM columns
     const long long t = (long long)tiles_x * ((H + 4 * cand - 1) / (4 * cand)) * N;
     const double issuer = split ? (490. + 145. * cand) / 2 : (490. + 145. * cand / 2);
     const double tap_time = issuer > 4. * cand * T ? issuer : 4. * cand * T;
-    const double cost = (double)((t + UPF_NUM_SMS - 1) / UPF_NUM_SMS) * tap_time;
+    const int slots = two_cta ? 2 * UPF_NUM_SMS : UPF_NUM_SMS;
+    const double cost = (double)((t + slots - 1) / slots) * tap_time * (two_cta ? 2 : 1);
     if (cost < best * 0.97) { best = cost; m = cand; tap_split = split; }
   }
   if (m == 0) return 0;

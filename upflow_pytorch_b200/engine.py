@@ -35,6 +35,8 @@ the warp / blend / residual additions need live in their own small buffers
 difference between 3.8e-3 px (truncation) and 5.6e-4 px (rounding) mean EPE
 against the fp32 reference (robust-mask diagnostic).
 """
+import os
+
 import torch
 
 from . import _ext, ops
@@ -64,6 +66,7 @@ def _dense_slots(x_width, x_slots, out_offsets, out_channels, k):
     return slots
 
 
+CHAIN_MAX_PIXELS = 4096      # feature maps (N*h*w) up to this size run their dense blocks as ONE persistent launch (conv_chain.cu)
 EXPAND_MAX_COUT = 8          # 3x3 convs with at most this many outputs run as 1x1-expand + tap-combine ...
 EXPAND_MIN_PIXELS = 5000     # ... on images with at least this many pixels (below, the extra launch costs more)
 
@@ -129,6 +132,8 @@ class DecoderEngine:
         self.occ = occ
         self.last_occ = None
         self.overlap = True        # image-only work on a side stream (forward())
+        # coarse levels: estimator + context network (13 convolutions) and the SGU block (6) as one launch each
+        self.chain = precision == "tf32" and os.environ.get("UPF_CHAIN", "1") != "0"
         self.load_weights(state_dict)
 
     # ------------------------------------------------------------ weights
@@ -279,8 +284,19 @@ class DecoderEngine:
         self._ws[key] = ws
         return ws
 
+    def _use_chain(self, buf):
+        return self.chain and buf.shape[0] * buf.shape[1] * buf.shape[2] <= CHAIN_MAX_PIXELS
+
+    def _chain_layer(self, cs, x, out, residual=None, out2=None):
+        return ops.chain_layer(x, cs.w_tc, cs.bias, out, cs.k, cs.dil, cs.slope, residual, self.rnd and cs.hidden, out2)
+
     def _sgu_dense(self, S, inter):
         """FlowEstimatorDense_temp (model/upflow.py:24-60) on the S buffer."""
+        if self._use_chain(S):
+            layers = [self._chain_layer(self.sgu[k], Slice(S, 0, self.sgu[k].cin), Slice(S, S_OFF[k], SGU_CH[k])) for k in range(5)]
+            layers.append(self._chain_layer(self.sgu[5], Slice(S, 0, self.sgu[5].cin), Slice(inter, 0, 3)))
+            ops.k_conv_chain(layers)
+            return
         for k in range(5):
             self._conv(self.sgu[k], Slice(S, 0, self.sgu[k].cin), Slice(S, S_OFF[k], SGU_CH[k]))
         self._conv(self.sgu[5], Slice(S, 0, self.sgu[5].cin), Slice(inter, 0, 3))
@@ -392,22 +408,35 @@ class DecoderEngine:
                 s1, s2 = d["stats_ca"], d["stats_cb"]
             ops.k_corr(F, f2, Slice(X, X_CORR, 81), 4, s1, s2, f2_shift=shift, slope=SLOPE, round_tf32=self.rnd)
             self._split(Slice(X, X_CORR, 81))
-            # dense flow estimator (model/pwc_modules.py:279-286)
-            for k in range(5):
-                self._conv(self.est[k], Slice(X, 0, self.est[k].cin), Slice(X, X_OFF[k], EST_CH[k]))
-            # flow_up + flow_res (model/upflow.py:567): exact into "flow2", TF32 copy into the context input slot
             flow2 = Slice(d["flow2"])
-            self._conv(self.est[5], Slice(X, 0, X_LD), flow2, residual=flow_up)
-            ops.k_copy(flow2, Slice(X, X_FLOW2, 2), round_tf32=self.rnd)
-            self._split(Slice(X, X_FLOW2, 2))
-            # context network (model/pwc_modules.py:401-412); last conv adds (flow_up + flow_res): :569-572, :519
-            t_in = Slice(X, 0, X_LD)
             bufs = (d["T0"], d["T1"])
-            for i in range(6):
-                t_out = Slice(bufs[i % 2], 0, CTX_CH[i])
-                self._conv(self.ctx[i], t_in, t_out)
-                t_in = t_out
-            self._conv(self.ctx[6], t_in, Slice(d["flow"]), residual=flow2)
+            if self._use_chain(X):
+                # estimator, flow_up + flow_res (exact into "flow2", TF32 copy into the context input slot) and the context
+                # network: 13 dependent convolutions, one persistent launch
+                layers = [self._chain_layer(self.est[k], Slice(X, 0, self.est[k].cin), Slice(X, X_OFF[k], EST_CH[k])) for k in range(5)]
+                layers.append(self._chain_layer(self.est[5], Slice(X, 0, X_LD), flow2, residual=flow_up, out2=Slice(X, X_FLOW2, 2)))
+                t_in = Slice(X, 0, X_LD)
+                for i in range(6):
+                    t_out = Slice(bufs[i % 2], 0, CTX_CH[i])
+                    layers.append(self._chain_layer(self.ctx[i], t_in, t_out))
+                    t_in = t_out
+                layers.append(self._chain_layer(self.ctx[6], t_in, Slice(d["flow"]), residual=flow2))
+                ops.k_conv_chain(layers)
+            else:
+                # dense flow estimator (model/pwc_modules.py:279-286)
+                for k in range(5):
+                    self._conv(self.est[k], Slice(X, 0, self.est[k].cin), Slice(X, X_OFF[k], EST_CH[k]))
+                # flow_up + flow_res (model/upflow.py:567): exact into "flow2", TF32 copy into the context input slot
+                self._conv(self.est[5], Slice(X, 0, X_LD), flow2, residual=flow_up)
+                ops.k_copy(flow2, Slice(X, X_FLOW2, 2), round_tf32=self.rnd)
+                self._split(Slice(X, X_FLOW2, 2))
+                # context network (model/pwc_modules.py:401-412); last conv adds (flow_up + flow_res): :569-572, :519
+                t_in = Slice(X, 0, X_LD)
+                for i in range(6):
+                    t_out = Slice(bufs[i % 2], 0, CTX_CH[i])
+                    self._conv(self.ctx[i], t_in, t_out)
+                    t_in = t_out
+                self._conv(self.ctx[6], t_in, Slice(d["flow"]), residual=flow2)
             prev_flow = Slice(d["flow"])
             flows.append(d["flow"])
             if taps is not None:

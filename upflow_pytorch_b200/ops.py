@@ -252,6 +252,31 @@ def k_conv(x, weight, bias, out, ksize, stride=1, dilation=1, slope=LRELU_SLOPE,
                                      float(slope), int(precision), _stream()), "conv2d_fwd")
 
 
+def chain_layer(x, weight_tc, bias, out, ksize, dilation=1, slope=LRELU_SLOPE, residual=None, round_tf32=False, out2=None):
+    """One layer of k_conv_chain: k_conv(..., precision=CONV_TF32) with stride 1; out2 = optional TF32-rounded second copy."""
+    x, out = _as_slice(x), _as_slice(out)
+    res = _as_slice(residual) if residual is not None else None
+    o2 = _as_slice(out2) if out2 is not None else None
+    L = _ext.ChainLayer()
+    L.x, L.ldx, L.w_packed, L.bias = x.ptr(), x.ld, _p(weight_tc), _p(bias)
+    L.out, L.ldo = out.ptr(), out.ld
+    L.residual, L.ldr = (res.ptr(), res.ld) if res else (None, 0)
+    L.out2, L.ldo2 = (o2.ptr(), o2.ld) if o2 else (None, 0)
+    L.Cin, L.Cout, L.ksize, L.dilation = x.C, out.C, ksize, dilation
+    L.slope, L.flags = float(slope), (_ext.FLAG_ROUND_TF32 if round_tf32 else 0)
+    L._shape = (x.N, x.H, x.W)
+    L._keep = (x.buf, weight_tc, bias, out.buf, res.buf if res else None, o2.buf if o2 else None)
+    return L
+
+
+def k_conv_chain(layers):
+    """Dependent stride-1 tensor-core convolutions on one small feature map in ONE persistent launch (conv_chain.cu)."""
+    N, H, W = layers[0]._shape
+    assert all(L._shape == (N, H, W) for L in layers), "every layer of a chain works on the same [N,H,W] map"
+    arr = (_ext.ChainLayer * len(layers))(*layers)
+    _ext.check(_lib().upf_conv_chain_fwd(ctypes.cast(arr, ctypes.c_void_p), len(layers), N, H, W, _stream()), "conv_chain_fwd")
+
+
 def k_wgrad_planar_input(x, ksize, dilation=1):
     """The planar, zero-padded transpose of slice x that the tensor-core weight gradient reads, made ONCE for several
     convolutions whose inputs are nested channel ranges of x (same ksize / dilation).  Returns (xt, rows): blocked planar
