@@ -223,8 +223,11 @@ typedef struct {
   int flags;
 } upf_chain_layer;
 int upf_conv_chain_fwd(const upf_chain_layer* layers, int n_layers, int N, int H, int W, void* stream);
-/* test / tuning hook: cluster size (K split, 1/2/4/8) and number of clusters (0 = as many as are co-resident) of conv_chain.cu */
+/* test / tuning hook: cluster size (K split, 1/2/4/8) and number of clusters (0 = as many as are co-resident) of conv_chain.cu;
+ * bits 8..15 of cluster_size: rows per TMA box (0 = 128, one box per operand tile) */
 int upf_debug_conv_chain(int cluster_size, int n_clusters);
+/* debug: device buffer of 16 x 16 int64 receiving CTA 0's per-layer clock64 stamps of conv_chain.cu's roles (NULL = off) */
+int upf_debug_conv_chain_probe(void* device_buffer_256x_int64);
 
 /* Second half of a 3x3 convolution with very few output channels run as "expand, then combine the taps" (same
  * reference routine as upf_conv2d_fwd: conv(), model/pwc_modules.py:10-31).  The first half is upf_conv2d_fwd with

@@ -179,6 +179,7 @@ def test_engine_with_and_without_chains():
     assert epe.mean().item() <= 2e-3
     # the graph replays it bit-identically
     eng = DecoderEngine(sd, precision="tf32", mask_threshold=0.9999)
+    eng.chain = True
     with torch.no_grad():
         g = eng.capture(B, H, W)
     outs = []

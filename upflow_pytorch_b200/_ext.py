@@ -36,6 +36,7 @@ SIGNATURES = {
     "upf_conv2d_fwd": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P]),
     "upf_conv_chain_fwd": (_I, [_P, _I, _I, _I, _I, _P]),
     "upf_debug_conv_chain": (_I, [_I, _I]),
+    "upf_debug_conv_chain_probe": (_I, [_P]),
     "upf_conv3x3_tap_combine": (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P]),
     "upf_conv_tc_packed_elems": (_LL, [_I, _I, _I]),
     "upf_conv_tc_pack_weights": (_I, [_P, _P, _I, _I, _I, _P]),

@@ -33,7 +33,7 @@
 
 namespace upf {
 
-constexpr int HC_THREADS = 224;                   // warps: 0 weights TMA, 1 MMA, 2-5 epilogue, 6 halo TMA
+constexpr int HC_THREADS = 256;                   // warps: 0 weights TMA, 1 and 7 MMA issuers, 2-5 epilogue, 6 halo TMA
 constexpr int HC_PITCH = 132;                     // floats per pixel row of the epilogue staging tile
 constexpr int HC_COLS = 16;                       // halo positions per row (2048 B)
 constexpr int HC_ROW_BYTES = HC_COLS * 128;
@@ -49,11 +49,26 @@ struct HaloParams {
   int ra, nba, b_rows, nbb;   // halo rows per TMA box / boxes per halo tile; weight rows per box / boxes per tile
   int a_bytes, b_stage_bytes; // per stage (multiples of 1024)
   int tmem_cols;
+  int two_issuers;            // 1: two MMA-issuing warps, two accumulators (2 * 128 * MT TMEM columns)
+  int mc;                     // 1: launched as clusters of two CTAs that share every weight tile (each loads half, TMA multicast)
   int bo_mode;                // 1: descriptor base_offset = (start >> 7) & 7
   long long* probe;           // debug: per-role wait/issue cycle counters of CTA 0 (nullptr = off)
   float slope;
   int flags;
 };
+
+// half a weight tile, delivered to the same shared-memory offset (and counted on the same mbarrier offset) of BOTH CTAs of the pair
+__device__ __forceinline__ void tma_load_3d_mc2(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at this offset in BOTH CTAs of the pair (a shared weight slot is free when both have read it)
+__device__ __forceinline__ void umma_commit_mc2(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
 
 __global__ void __launch_bounds__(HC_THREADS)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const HaloParams p) {
@@ -84,9 +99,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    for (int s = 0; s < p.na; ++s) { mbar_init(smem_u32(&fullA[s]), 1); mbar_init(smem_u32(&emptyA[s]), 1); }
-    for (int s = 0; s < p.nb; ++s) { mbar_init(smem_u32(&fullB[s]), 1); mbar_init(smem_u32(&emptyB[s]), 1); }
-    mbar_init(smem_u32(accum_full), 1);
+    for (int s = 0; s < p.na; ++s) { mbar_init(smem_u32(&fullA[s]), 1); mbar_init(smem_u32(&emptyA[s]), p.two_issuers ? 2 : 1); }
+    for (int s = 0; s < p.nb; ++s) { mbar_init(smem_u32(&fullB[s]), 1); mbar_init(smem_u32(&emptyB[s]), p.mc ? 2 : 1); }
+    mbar_init(smem_u32(accum_full), p.two_issuers ? 2 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -94,9 +109,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (p.mc) cluster_sync_all();        // the peer's barriers exist before anything is multicast into this CTA
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  const int crank = p.mc ? (int)cluster_ctarank() : 0;
   // programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, bias) touched
   // only this CTA's own state and constant weights, and may overlap the tail of the previous kernel in the stream;
   // from here on we read activations / write outputs, so wait for the upstream grid to complete and flush.
@@ -114,10 +131,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         mbar_wait(smem_u32(&emptyB[sb]), (((uint32_t)(ib / p.nb)) & 1u) ^ 1u);
         w_eb += clock64() - t0;
         const uint32_t fb = smem_u32(&fullB[sb]);
-        mbar_expect_tx(fb, b_bytes);
         const uint32_t b_dst = smem_u32(b_ring + (size_t)sb * p.b_stage_bytes);
-        for (int jb = 0; jb < p.nbb; ++jb)
-          tma_load_3d(b_dst + (uint32_t)(jb * p.b_rows * 128), &map_w, fb, kb * 32, jb * p.b_rows, tap);
+        if (p.mc) {
+          // this CTA fetches weight rows [64 rank, +64) for both CTAs; the peer's half arrives on the same barrier
+          mbar_expect_tx(fb, 2u * 64u * 128u);
+          tma_load_3d_mc2(b_dst + (uint32_t)(crank * 64 * 128), &map_w, fb, kb * 32, crank * 64, tap);
+        } else {
+          mbar_expect_tx(fb, b_bytes);
+          for (int jb = 0; jb < p.nbb; ++jb)
+            tma_load_3d(b_dst + (uint32_t)(jb * p.b_rows * 128), &map_w, fb, kb * 32, jb * p.b_rows, tap);
+        }
       }
       if (p.probe && blockIdx.x == 0) { p.probe[1] = w_eb; p.probe[2] = clock64() - t_start; }
     }
@@ -141,20 +164,31 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       if (p.probe && blockIdx.x == 0) p.probe[0] = w_ea;
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // M = 128 (output channels, rows past Cout are never stored), N = 128*MT pixels
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((128 * p.MT) >> 3) << 17) | ((128u >> 4) << 24);
-    int ib = 0;
-    long long w_fa = 0, w_fb = 0, t_start = clock64();
-    for (int kb = 0; kb < p.kblocks; ++kb) {
-      const int sa = kb % p.na;
-      long long t0 = clock64();
-      mbar_wait(smem_u32(&fullA[sa]), ((uint32_t)(kb / p.na)) & 1u);
-      w_fa += clock64() - t0;
-      const uint32_t a_base = smem_u32(a_ring + (size_t)sa * p.a_bytes);
-      for (int tap = 0; tap < 9; ++tap, ++ib) {
-        const int sb = ib % p.nb;
+  } else if (warp == 1 || warp == 7) {
+    // ===================== MMA issuers =====================
+    // M = 128 (output channels, rows past Cout are never stored), N = 128*MT pixels.  One thread needs ~635 cycles to issue a
+    // tap (4 MMAs + commits + the next mbarrier poll, tools/microbench/tc_probe.cu) against 516 cycles of tensor work at
+    // N = 256: measured 730-790 cycles per tap with ONE issuer (tools/probe_fine.py).  TWO issuers: issuer w takes the taps
+    // with (kb*9 + tap) % 2 == w into its OWN accumulator (fixed order each: bitwise reproducible), the epilogue adds the two.
+    const int wi = warp == 1 ? 0 : 1;
+    if (wi == 0 || p.two_issuers) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((128 * p.MT) >> 3) << 17) | ((128u >> 4) << 24);
+      const int total = p.kblocks * 9;
+      const int step = p.two_issuers ? 2 : 1;
+      const uint32_t tacc = tmem_base + (uint32_t)(wi * 128 * p.MT);
+      long long w_fa = 0, w_fb = 0, t_start = clock64();
+      int kb_ready = -1;
+      uint32_t acc = 0;
+      for (int ib = wi; ib < total; ib += step) {
+        const int kb = ib / 9, tap = ib - kb * 9;
+        const int sa = kb % p.na, sb = ib % p.nb;
+        long long t0 = clock64();
+        if (kb != kb_ready) {
+          mbar_wait(smem_u32(&fullA[sa]), ((uint32_t)(kb / p.na)) & 1u);
+          kb_ready = kb;
+        }
+        w_fa += clock64() - t0;
+        const uint32_t a_base = smem_u32(a_ring + (size_t)sa * p.a_bytes);
         t0 = clock64();
         mbar_wait(smem_u32(&fullB[sb]), ((uint32_t)(ib / p.nb)) & 1u);
         w_fb += clock64() - t0;
@@ -166,15 +200,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           const uint64_t dx = umma_desc_sw128_ex(x_addr, HC_ROW_BYTES, (p.bo_mode & 1) ? (x_addr >> 7) : 0u);     // pixels: B
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_tf32(tmem_base, dw + (uint64_t)(k * 2), dx + (uint64_t)(k * 2), idesc, (kb > 0 || tap > 0 || k > 0) ? 1u : 0u);
-          umma_commit(smem_u32(&emptyB[sb]));
-          if (tap == 8) umma_commit(smem_u32(&emptyA[sa]));
-          if (kb == p.kblocks - 1 && tap == 8) umma_commit(smem_u32(accum_full));
+            umma_tf32(tacc, dw + (uint64_t)(k * 2), dx + (uint64_t)(k * 2), idesc, acc | (uint32_t)k);
+          if (p.mc) umma_commit_mc2(smem_u32(&emptyB[sb]));
+          else umma_commit(smem_u32(&emptyB[sb]));
+          if ((ib + step) / 9 != kb) umma_commit(smem_u32(&emptyA[sa]));      // this issuer's last tap of the channel block
+          if (ib + step >= total) umma_commit(smem_u32(accum_full));
         }
         __syncwarp();
+        acc = 1;
       }
+      if (p.probe && blockIdx.x == 0 && lane == 0 && wi == 0) { p.probe[3] = w_fa; p.probe[4] = w_fb; p.probe[5] = clock64() - t_start; }
     }
-    if (p.probe && blockIdx.x == 0 && lane == 0) { p.probe[3] = w_fa; p.probe[4] = w_fb; p.probe[5] = clock64() - t_start; }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                                    // TMEM lane quarter = 32 output channels
@@ -191,7 +227,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       for (int n0 = 0; n0 < npx; n0 += 16) {                   // 16 pixels = 2 tile rows of 8
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (p.two_issuers) {
+          uint32_t v2[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(npx + n0), v2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        } else {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) stage[(n0 + j) * HC_PITCH + c] = __uint_as_float(v[j]);
       }
@@ -253,7 +297,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     if (p.probe && blockIdx.x == 0 && threadIdx.x == 64) { p.probe[6] = t_e2 - t_e1; p.probe[7] = clock64() - t_e2; }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
-  __syncthreads();
+  if (p.mc) cluster_sync_all();        // nobody leaves while the peer may still multicast into it or arrive on its barriers
+  else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -265,6 +310,9 @@ static int g_halo_bo_mode = 0;   // measured on B200: the 128-byte swizzle is ap
 extern int g_tc_box_rows;
 extern int g_tc_pdl;
 static int g_halo_enabled = 1;
+static int g_halo_mc = 1;          // pairs of CTAs share every weight tile by TMA multicast (upf_debug_conv_halo enabled bit 2 = OFF): with ONE MMA
+                                   // issuer no faster (2.765 vs 2.764 ms per KITTI forward), with two 2.657 vs 2.672 ms
+static int g_halo_two_issuers = 1; // upf_debug_conv_halo enabled bit 3 = one issuer (A/B)
 static int g_halo_two_cta = 0;     // A/B (upf_debug_conv_halo enabled bit 1): 8x16-pixel tiles with ~108 KB rings, two resident CTAs per SM
 static int g_halo_min_cin = 64;    // A/B on the whole KITTI forward (tools/ab_forward.py): off 3.83 ms, >=192 3.72, >=64 3.60, all 3.61
 long long* g_halo_probe = nullptr;
@@ -298,6 +346,11 @@ int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float*
   while (rows % ra) --ra;
   int b_rows = (g_tc_box_rows >= 8 && g_tc_box_rows <= 128 && g_tc_box_rows < BN) ? g_tc_box_rows : BN;
   while (BN % b_rows) b_rows -= 8;
+  // weight tiles shared by a pair of CTAs: the kernel's operand traffic (16 KB of weights per tap + the halo) runs at ~47 of the
+  // ~58 B/clk an SM can pull out of L2 and its MMA thread waits for weight slots 19 % of the time (tools/probe_fine.py);
+  // with each CTA fetching half of every tile for both, the weight traffic per SM halves
+  const bool mc = g_halo_mc && !two_cta && (tiles % 2 == 0) && BN > 64;
+  if (mc) b_rows = 64;
 
   CUtensorMap mx, mw;
   {
@@ -314,7 +367,7 @@ int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float*
     const cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 4, (cuuint64_t)cin_pad * BN * 4};
     const cuuint32_t box[3] = {32, (cuuint32_t)b_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    MapKey key{w_packed, cin_pad, b_rows, 9, BN, 3};
+    MapKey key{w_packed, cin_pad, b_rows, 9, BN, mc ? 33 : 3};
     int e = encode_cached(key, &mw, 3, const_cast<float*>(w_packed), dims, strides, box, estr);
     if (e) return e;
   }
@@ -327,14 +380,18 @@ int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float*
   p.slope = slope;
   p.flags = flags;
   p.bo_mode = g_halo_bo_mode;
+  p.mc = mc ? 1 : 0;
   p.probe = g_halo_probe;
-  p.tmem_cols = 128 * MT;                      // lanes = channels, columns = pixels
+  const bool two_issuers = g_halo_two_issuers && !two_cta;
+  p.two_issuers = two_issuers ? 1 : 0;
+  p.tmem_cols = (two_issuers ? 2 : 1) * 128 * MT;   // lanes = channels, columns = pixels; one accumulator per issuer
   // ring depths within ~212 KB: at least 2 A stages, then as many B stages as fit (3..8)
   const int budget = two_cta ? 108 * 1024 : 212 * 1024;
   int na = (kblocks >= 3 && 3 * p.a_bytes + 4 * p.b_stage_bytes <= budget) ? 3 : 2;
   if (na > kblocks) na = kblocks < 1 ? 1 : kblocks;
   int nb = (budget - na * p.a_bytes) / p.b_stage_bytes;
   if (nb > 8) nb = 8;
+  if (two_issuers) nb &= ~1;     // EVEN: each issuer owns the weight slots of its parity and sees every phase of their barriers
   if (nb < 2) return 0;
   p.na = na; p.nb = nb;
   if ((long long)na * p.a_bytes + (long long)nb * p.b_stage_bytes < 128ll * MT * HC_PITCH * 4 + 512) return 0;   // epilogue staging tile + bias
@@ -351,11 +408,20 @@ int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float*
   cfg.blockDim = dim3(HC_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na_ = 0;
+  if (mc) {
+    attr[na_].id = cudaLaunchAttributeClusterDimension;
+    attr[na_].val.clusterDim.x = 2; attr[na_].val.clusterDim.y = 1; attr[na_].val.clusterDim.z = 1;
+    ++na_;
+  }
+  if (g_tc_pdl) {
+    attr[na_].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na_].val.programmaticStreamSerializationAllowed = 1;
+    ++na_;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = g_tc_pdl ? 1 : 0;
+  cfg.numAttrs = na_;
   {
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo_kernel, mx, mw, p);
     if (e != cudaSuccess) { set_error("conv_halo launch: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return (int)e; }
@@ -376,6 +442,8 @@ extern "C" int upf_debug_probe(void* device_buffer_8x_int64) {
 extern "C" int upf_debug_conv_halo(int enabled, int bo_mode) {
   upf::g_halo_enabled = enabled & 1;
   upf::g_halo_two_cta = (enabled >> 1) & 1;
+  upf::g_halo_mc = ((enabled >> 2) & 1) ? 0 : 1;
+  upf::g_halo_two_issuers = ((enabled >> 3) & 1) ? 0 : 1;
   upf::g_halo_bo_mode = bo_mode & 7;
   upf::g_tc_pdl = (bo_mode & 8) ? 0 : 1;
   if ((bo_mode >> 8) & 0xff) upf::g_tc_box_rows = (bo_mode >> 8) & 0xff;     // tuning: rows per TMA box in bits 8..15 (0 = keep)

@@ -133,7 +133,7 @@ class DecoderEngine:
         self.last_occ = None
         self.overlap = True        # image-only work on a side stream (forward())
         # coarse levels: estimator + context network (13 convolutions) and the SGU block (6) as one launch each
-        self.chain = precision == "tf32" and os.environ.get("UPF_CHAIN", "1") != "0"
+        self.chain = precision == "tf32" and os.environ.get("UPF_CHAIN", "0") == "1"
         self.load_weights(state_dict)
 
     # ------------------------------------------------------------ weights

@@ -34,6 +34,13 @@ def _account(name, args, kwargs):
         n = _npix(out)
         return dict(bytes=4 * (_npix(x) * x.C + n * out.C) + 4 * k * k * x.C * out.C, flops=2 * n * k * k * x.C * out.C,
                     shape=(x.N, x.C, x.H, x.W, out.C, k), tc=((kwargs.get("precision", args[9] if len(args) > 9 else 0) & 0xFF) == 1))
+    if name == "k_conv_chain":
+        layers = args[0]
+        N, H, W = layers[0]._shape
+        n = N * H * W
+        return dict(bytes=sum(4 * n * (L.Cin + L.Cout) + 4 * L.ksize * L.ksize * L.Cin * L.Cout for L in layers),
+                    flops=sum(2 * n * L.ksize * L.ksize * L.Cin * L.Cout for L in layers), shape=(N, H, W, "%d layers" % len(layers)),
+                    tc=True)
     if name == "k_resize":
         a, out = S(args[0]), S(args[1])
         return dict(bytes=4 * a.C * (_npix(a) + _npix(out)), flops=8 * a.C * _npix(out), shape=(out.N, a.C, out.H, out.W))
@@ -52,7 +59,7 @@ def _account(name, args, kwargs):
     return dict(bytes=0, flops=0, shape=())
 
 
-NAMES = ("k_corr", "k_warp", "k_stats", "k_conv", "k_resize", "k_sgu_blend", "k_copy", "k_norm_apply", "k_tap_combine", "k_occ_check",
+NAMES = ("k_corr", "k_warp", "k_stats", "k_conv", "k_conv_chain", "k_resize", "k_sgu_blend", "k_copy", "k_norm_apply", "k_tap_combine", "k_occ_check",
          "k_norm_combine")
 
 
