@@ -276,7 +276,9 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
   // two resident CTAs per SM (~108 KB rings each): one CTA's epilogue -- 4-8 us of stores per tile with the tensor pipe idle --
   // runs under the other's MMAs.  Measured on whole forwards (tools/ab_win2.py): KITTI b1 2.813 -> 2.790 ms, Sintel b8
   // 15.10 -> 14.56 ms, HD b2 16.39 -> 15.94 ms.  force_m bit 4 (16): one CTA with 224 KB rings (A/B switch)
-  const bool two_cta = (g_win_force_m & 16) == 0;
+  // Only where a CTA still gets >= 4 weight slots: at BN = 64 it gets two, the MMA threads then wait for weights 30 % of the
+  // time and the layer is no faster than with one CTA (480->64 at 94x311: 101.4 vs 99.3 us; 544->32: 81.9 vs 93.2 us).
+  const bool two_cta = (g_win_force_m & 16) == 0 && (108 * 1024 - 2 * (8 + 2 * dil) * CW_ROW_BYTES) / b_stage_bytes >= 4;
   const int budget = two_cta ? 108 * 1024 : 224 * 1024;
   // units per CTA and issuer split: minimise waves x (time of one tap), modelled from the microbenchmark --
   // one issuer needs ~(490 + 145 m) cycles per tap (4m MMAs + commit + poll), two run in parallel, and the tensor

@@ -15,13 +15,16 @@
 // 576->128 573 vs 580, 384->96 285 vs 271.  INSIDE the training step, though, serving the 96- and 128-wide layers here costs
 // 2 ms (49.5 vs 46.7-48.1 ms per step, same process, UPF_WGRAD_TAPS = 128 / 64 / 32): the default limit is 64.
 // Operands are the blocked, pre-swizzled planar tensors of backward.cu ([k block][row][32]: one bulk copy per tile).
-// Roles: warp 0 = producer (one thread), warp 1 = MMA issuer (one thread, 36 MMAs per ring slot into nine independent
-// accumulators), warps 2..5 = epilogue.
+// Roles: warp 0 = producer (one thread), warps 1, 6, 7 = MMA issuers (one thread each: a thread issues ~one tcgen05 instruction
+// per 100 cycles, 36 MMAs per ring slot would take it 3700 cycles against 1440 of tensor work at N = 32; issuer i takes the
+// three taps of kernel row i -- 12 MMAs per slot into its own three accumulators, so every accumulator keeps ONE issuer and a
+// fixed order), warps 2..5 = epilogue.
 #include "tc_common.cuh"
 
 namespace upf {
 
-constexpr int WT_THREADS = 192;
+constexpr int WT_THREADS = 256;
+constexpr int WT_ISSUERS = 3;
 constexpr int WT_A_BYTES = 128 * 128;
 
 struct WtParams {
@@ -62,9 +65,9 @@ wgrad_taps_kernel(const WtParams p) {
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nstage; ++s) {
       mbar_init(smem_u32(&full[s]), 1);
-      mbar_init(smem_u32(&empty[s]), 1);
+      mbar_init(smem_u32(&empty[s]), WT_ISSUERS);
     }
-    mbar_init(smem_u32(accum_full), 1);
+    mbar_init(smem_u32(accum_full), WT_ISSUERS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -97,8 +100,9 @@ wgrad_taps_kernel(const WtParams p) {
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp >= 6) {
+    // ===================== MMA issuers =====================
+    const int ky = warp == 1 ? 0 : warp - 5;                  // kernel row whose three taps this warp accumulates
     // instruction descriptor: D=f32 (bit4), A=B=TF32 (2<<7, 2<<10), K-major both, N>>3 @17, M>>4 @24
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
     for (int it = 0; it < iters; ++it) {
@@ -112,7 +116,8 @@ wgrad_taps_kernel(const WtParams p) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)        // K steps outside, the nine accumulators inside: independent MMAs back to back
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
+          for (int tx = 0; tx < 3; ++tx) {
+            const int t = ky * 3 + tx;
             const uint64_t db = umma_desc_sw128(a_addr + WT_A_BYTES + (uint32_t)t * b_bytes);
             umma_tf32(tmem_base + (uint32_t)(t * p.BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
