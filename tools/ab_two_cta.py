@@ -14,7 +14,8 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 HALO = (65 << 16) | (128 << 8)
 # (name, halo `enabled` word (bit 1 = two CTAs), win force_m word (16 = two CTAs))
 # halo word: bit 1 = two CTAs per SM, bit 2 = weight multicast OFF, bit 3 = ONE MMA issuer; win word: 16 = ONE CTA per SM
-variants = [("default", 1, 0), ("halo one issuer", 9, 0), ("halo multicast off", 5, 0), ("win one CTA", 1, 16)]
+# bits 4..7 of the halo word = TMA boxes per halo tile
+variants = [("default", 1, 0), ("halo A in 2 boxes", 1 | (2 << 4), 0), ("halo one issuer", 9, 0), ("halo multicast off", 5, 0), ("win one CTA", 1, 16)]
 ref = None
 for rep in range(2):
     for name, hen, wforce in variants:

@@ -312,6 +312,7 @@ extern int g_tc_pdl;
 static int g_halo_enabled = 1;
 static int g_halo_mc = 1;          // pairs of CTAs share every weight tile by TMA multicast (upf_debug_conv_halo enabled bit 2 = OFF): with ONE MMA
                                    // issuer no faster (2.765 vs 2.764 ms per KITTI forward), with two 2.657 vs 2.672 ms
+static int g_halo_a_boxes = 1;     // TMA boxes per halo tile (upf_debug_conv_halo enabled bits 4..7; must divide the halo rows)
 static int g_halo_two_issuers = 1; // upf_debug_conv_halo enabled bit 3 = one issuer (A/B)
 static int g_halo_two_cta = 0;     // A/B (upf_debug_conv_halo enabled bit 1): 8x16-pixel tiles with ~108 KB rings, two resident CTAs per SM
 static int g_halo_min_cin = 64;    // A/B on the whole KITTI forward (tools/ab_forward.py): off 3.83 ms, >=192 3.72, >=64 3.60, all 3.61
@@ -343,6 +344,7 @@ int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float*
   const int rows = 16 * MT + 2 * dil;
   // TMA sub-boxes: `ra` halo rows (16 positions each) per box, must divide rows (rows is even)
   int ra = (g_tc_box_rows >= 16 && g_tc_box_rows <= 128) ? g_tc_box_rows / 16 : rows;
+  if (g_halo_a_boxes > 1 && rows % g_halo_a_boxes == 0) ra = rows / g_halo_a_boxes;   // the halo as several concurrent boxes
   while (rows % ra) --ra;
   int b_rows = (g_tc_box_rows >= 8 && g_tc_box_rows <= 128 && g_tc_box_rows < BN) ? g_tc_box_rows : BN;
   while (BN % b_rows) b_rows -= 8;
@@ -444,6 +446,7 @@ extern "C" int upf_debug_conv_halo(int enabled, int bo_mode) {
   upf::g_halo_two_cta = (enabled >> 1) & 1;
   upf::g_halo_mc = ((enabled >> 2) & 1) ? 0 : 1;
   upf::g_halo_two_issuers = ((enabled >> 3) & 1) ? 0 : 1;
+  upf::g_halo_a_boxes = ((enabled >> 4) & 15) ? ((enabled >> 4) & 15) : 1;
   upf::g_halo_bo_mode = bo_mode & 7;
   upf::g_tc_pdl = (bo_mode & 8) ? 0 : 1;
   if ((bo_mode >> 8) & 0xff) upf::g_tc_box_rows = (bo_mode >> 8) & 0xff;     // tuning: rows per TMA box in bits 8..15 (0 = keep)
