@@ -361,3 +361,20 @@ def test_pipelined_inference_returns_every_flow_in_order(golden):
     assert pipe.flush() is None and len(got) == len(want)
     for g, w in zip(got, want):
         assert torch.equal(g, w)
+    # two and three lanes: graphs of consecutive pairs replay concurrently on their own workspaces; same bits, same order
+    for lanes in (2, 3):
+        pipe = PipelinedInference(net, lanes=lanes)
+        got = []
+        for rep in range(2):
+            for a, b in pairs:
+                r = pipe.submit(a, b)
+                assert (r is None) == (len(got) == 0 and pipe._k <= lanes)
+                if r is not None:
+                    got.append(r.clone())
+        got += [r.clone() for r in pipe.drain()]
+        assert pipe.drain() == [] and len(got) == 2 * len(want)
+        for g, w in zip(got, want + want):
+            assert torch.equal(g, w), lanes
+    # the plain call still works after a pipeline put the engine back on lane 0
+    with torch.no_grad():
+        assert torch.equal(net({"im1": pairs[0][0].cuda(), "im2": pairs[0][1].cuda(), "if_loss": False})["flow_f_out"].cpu(), want[0])

@@ -253,6 +253,11 @@ class UPFlow_net(tools.abstract_model):
             self._graphs = {}
         return self._engine
 
+    def set_lane(self, lane: int):
+        """Select the workspace / graph set the next inference calls use (engine.DecoderEngine.lane).  Calls on different
+        lanes may be in flight on different CUDA streams at the same time (pipeline.PipelinedInference(lanes=2))."""
+        self._get_engine().lane = int(lane)
+
     def forward(self, input_dict: dict):
         """model/upflow.py:370-392 (inference branch)."""
         im1_ori, im2_ori = input_dict['im1'], input_dict['im2']
@@ -367,7 +372,7 @@ class UPFlow_net(tools.abstract_model):
             return None
         eng = self._get_engine()
         if self.use_cuda_graph:
-            key = tuple(x1_raw.shape)
+            key = tuple(x1_raw.shape) + (eng.lane,)
             g = self._graphs.get(key)
             if g is None:
                 if len(self._graphs) >= 8:

@@ -132,6 +132,10 @@ class DecoderEngine:
         self.occ = occ
         self.last_occ = None
         self.overlap = True        # image-only work on a side stream (forward())
+        # Workspace set in use.  Two forwards whose graphs replay CONCURRENTLY (pipeline.PipelinedInference(lanes=2):
+        # one pair's latency-bound coarse levels fill the SMs another pair's fine levels leave idle) must not share
+        # buffers: each lane has its own workspaces, scratch and captured graphs.
+        self.lane = 0
         # coarse levels: estimator + context network (13 convolutions) and the SGU block (6) as one launch each
         self.chain = precision == "tf32" and os.environ.get("UPF_CHAIN", "0") == "1"
         self.load_weights(state_dict)
@@ -178,7 +182,7 @@ class DecoderEngine:
     def _scratch(self, N, H, W, C):
         side = getattr(self, "_side", None)
         on_side = side is not None and torch.cuda.current_stream() == side
-        key = ("scratch", N, H, W, C, on_side)            # one per stream: the side stream overlaps the main one
+        key = ("scratch", N, H, W, C, on_side, self.lane)  # one per stream: the side stream overlaps the main one
         buf = self._ws.get(key)
         if buf is None:
             buf = self._ws[key] = torch.zeros(N, H, W, C, dtype=torch.float32, device=self.device)
@@ -229,7 +233,7 @@ class DecoderEngine:
                    (_ext.CONV_TF32 if use_tc else _ext.CONV_FP32) | (_ext.CONV_ROUND_OUT if rnd else 0))
 
     def _workspace(self, B, H, W):
-        key = (B, H, W)
+        key = (B, H, W, self.lane)
         ws = self._ws.get(key)
         if ws is not None:
             return ws
