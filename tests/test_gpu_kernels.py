@@ -455,12 +455,14 @@ def test_corr_pipelined_persistent_kernel(upf, shape, d):
     assert (out2 - out).abs().max().item() <= 1e-5
 
 
-@pytest.mark.parametrize("case", [(200, 128, 1, 70, 200), (168, 24, 2, 66, 150), (96, 64, 4, 64, 130), (40, 3, 1, 90, 95)])
+@pytest.mark.parametrize("case", [(200, 128, 1, 70, 200), (168, 24, 2, 66, 150), (96, 64, 4, 64, 130), (40, 3, 1, 90, 95),
+                                  (16, 32, 1, 50, 70), (100, 48, 1, 40, 61), (544, 32, 1, 47, 156), (160, 16, 2, 47, 100)])
 def test_conv_tf32_large_grid_kernels_agree(upf, case):
     """Fine pyramid levels: the same 3x3 convolution through the per-tap kernel (conv_tc.cu, two CTAs per SM), the
     shared-halo kernel (conv_halo.cu) and the linear-window kernel (conv_win.cu; 1, 2 and 4 units per CTA, two MMA
-    issuers) -- each must match the TF32-truncated oracle to fp32 rounding, repeat bit for bit, and leave the
-    neighbouring channels of the output buffer alone."""
+    issuers; one MMA per kernel row with the horizontal taps along N -- the default for Cout <= 64 -- and one per tap)
+    -- each must match the TF32-truncated oracle to fp32 rounding, repeat bit for bit, and leave the neighbouring
+    channels of the output buffer alone."""
     from upflow_pytorch_b200 import _ext
     from upflow_pytorch_b200.ops import Slice
     lib = _ext.load()
@@ -477,7 +479,9 @@ def test_conv_tf32_large_grid_kernels_agree(upf, case):
     a = Slice(upf.to_pixel_major(_cuda(x), ld=ld), 0, Cin)
     ldo = (Cout + 3) // 4 * 4 + 4
     HALO = (1 << 16) | (128 << 8)
-    modes = {"tap": (0, 0, 0), "halo": (0, 0, 1), "win": (3, 0, 0), "win m1": (3, 1, 0), "win m2": (3, 2, 0), "win m4": (3, 4, 0)}
+    modes = {"tap": (0, 0, 0), "halo": (0, 0, 1), "win": (3, 0, 0), "win m1": (3, 1, 0), "win m2": (3, 2, 0), "win m4": (3, 4, 0),
+             "win one CTA": (3, 16, 0), "win unit split": (3, 8, 0), "win four epilogue warps": (3, 32, 0),
+             "win9": (7, 0, 0), "win9 m1": (7, 1, 0), "win9 m2": (7, 2, 0), "win9 m4": (7, 4, 0)}
     try:
         for name, (wen, fm, hen) in modes.items():
             lib.upf_debug_conv_win(wen, 0, fm)

@@ -13,7 +13,9 @@ probe = torch.zeros(8, dtype=torch.int64, device="cuda")
 lib.upf_debug_probe(ctypes.c_void_p(probe.data_ptr()))
 
 # name -> (win enabled, force_m, halo enabled)
-MODES = (("tap", (0, 0, 0)), ("halo", (0, 0, 1)), ("win", (3, 0, 0)), ("win m1", (3, 1, 0)), ("win m2", (3, 2, 0)), ("win m4", (3, 4, 0)))
+MODES = (("tap", (0, 0, 0)), ("halo", (0, 0, 1)), ("win9", (7, 0, 0)), ("win", (3, 0, 0)), ("win4w", (3, 32, 0)), ("win9 4w", (7, 32, 0)), ("win m1", (3, 1, 0)), ("win m2", (3, 2, 0)), ("win m4", (3, 4, 0)))
+if os.environ.get("BW_MODES"):
+    MODES = tuple(m for m in MODES if m[0] in os.environ["BW_MODES"].split(",") or m[0] == "tap")
 
 
 def run(N, h, w, cin, cout, dil, ld=576, resid=False):
@@ -60,8 +62,12 @@ SHAPES = ((2, 94, 311, 576, 128, 1), (2, 94, 311, 544, 32, 1), (2, 94, 311, 480,
           (2, 94, 311, 32, 2, 1, 576, True),
           (2, 47, 156, 576, 128, 1), (2, 47, 156, 256, 128, 1), (2, 47, 156, 544, 32, 1), (2, 47, 156, 128, 96, 4),
           (2, 188, 621, 32, 32, 1, 32), (2, 375, 1242, 16, 16, 1, 16), (2, 24, 78, 576, 128, 1), (1, 37, 61, 100, 50, 2, 100))
+SHAPES += ((2, 94, 311, 96, 32, 1), (2, 94, 311, 128, 32, 1), (2, 94, 311, 160, 16, 1), (2, 47, 156, 480, 64, 1), (2, 47, 156, 160, 16, 1),
+           (2, 188, 621, 16, 32, 1, 16), (2, 94, 311, 64, 32, 2), (2, 94, 311, 64, 48, 4), (1, 37, 61, 100, 50, 1, 100), (1, 33, 45, 40, 20, 1, 44, True))
 if len(sys.argv) > 1:
     SHAPES = SHAPES[:int(sys.argv[1])]
+if os.environ.get("BW_MAXCOUT"):
+    SHAPES = tuple(a for a in SHAPES if a[4] <= int(os.environ["BW_MAXCOUT"]))
 for args in SHAPES:
     run(*args)
 lib.upf_debug_conv_win(1, 0, 0)

@@ -29,7 +29,7 @@
 //   unit split (m = 4, BN > 64): issuer w takes units w, w+2 of every tap; a weight slot is released by both.
 //   accumulators: [128 positions x BN channels] fp32 tiles in TMEM; TMEM lane = position, so the epilogue thread of
 //   lane j owns one pixel and stores its channels as 16-byte vectors straight from registers.
-//   warps: 0 = weight TMA, 1 and 7 = MMA issuers, 2-5 = epilogue, 6 = halo TMA.
+//   warps: 0 = weight TMA, 1 and 7 = MMA issuers, 2-5 = epilogue, 6 = halo TMA; all eight in the epilogue when m >= 2.
 #include "tc_common.cuh"
 
 namespace upf {
@@ -49,6 +49,8 @@ struct WinParams {
   int a_bytes, b_stage_bytes;
   int tmem_cols;
   int tap_split;              // 1: issuers alternate taps (two accumulator sets), 0: issuers alternate units
+  int epi_helpers;            // 1: warps 0, 1, 6, 7 take the odd units of the epilogue
+  int kxn;                    // 1: the three horizontal taps along N (one MMA per ky and K step, N = 3*BN; header note (4))
   long long* probe;
   float slope;
   int flags;
@@ -79,7 +81,9 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int d = p.dil;
   const int useful = CW_POS - 2 * d;
   const int x0 = tx * useful, y0 = ty * 4 * p.m;
-  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const int ntap = p.kxn ? 3 : 9;                                     // ring items per channel block: kernel rows / taps
+  const int NB = p.kxn ? 3 * p.BN : p.BN;                             // accumulator width of one unit
+  const uint32_t b_bytes = (uint32_t)NB * 128u;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -108,16 +112,17 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // ===================== TMA producer: weight tiles (one per tap and channel block) =====================
     if (elect_one()) {
       long long w_eb = 0, t_start = PROBE ? clock64() : 0;
-      const int total = p.kblocks * 9;
+      const int total = p.kblocks * ntap;
       for (int ib = 0; ib < total; ++ib) {
-        const int kb = ib / 9, tap = ib - kb * 9;
+        const int kb = ib / ntap, tap = ib - kb * ntap;
         const int sb = ib % p.nb;
         const long long t0 = PROBE ? clock64() : 0;
         mbar_wait(smem_u32(&emptyB[sb]), (((uint32_t)(ib / p.nb)) & 1u) ^ 1u);
         if (PROBE) w_eb += clock64() - t0;
         const uint32_t fb = smem_u32(&fullB[sb]);
         mbar_expect_tx(fb, b_bytes);
-        tma_load_3d(smem_u32(b_ring + (size_t)sb * p.b_stage_bytes), &map_w, fb, kb * 32, 0, tap);
+        // kxn: the box holds the three taps of kernel row `tap`, rows (kx, co) -- 3*BN operand rows of 128 bytes
+        tma_load_3d(smem_u32(b_ring + (size_t)sb * p.b_stage_bytes), &map_w, fb, kb * 32, 0, p.kxn ? tap * 3 : tap);
       }
       if (PROBE && p.probe && blockIdx.x == 0) { p.probe[1] = w_eb; p.probe[2] = clock64() - t_start; }
     }
@@ -141,16 +146,16 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   } else if (warp == 1 || warp == 7) {
     // ===================== MMA issuers: M = 128 positions, N = BN output channels =====================
     const int wi = warp == 1 ? 0 : 1;
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
-    const int total = p.kblocks * 9;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
+    const int total = p.kblocks * ntap;
     const int step = p.tap_split ? 2 : 1;
     const int u0 = p.tap_split ? 0 : wi, ustep = p.tap_split ? 1 : 2;
-    const uint32_t tset = tmem_base + (uint32_t)(p.tap_split ? wi * p.m * p.BN : 0);
+    const uint32_t tset = tmem_base + (uint32_t)(p.tap_split ? wi * p.m * NB : 0);
     int kb_ready = -1;
     uint32_t acc = 0;
     long long w_fa = 0, w_fb = 0, t_start = PROBE ? clock64() : 0;
     for (int ib = p.tap_split ? wi : 0; ib < total; ib += step) {
-      const int kb = ib / 9, tap = ib - kb * 9;
+      const int kb = ib / ntap, tap = ib - kb * ntap;
       const int sa = kb % p.na, sb = ib % p.nb;
       if (kb != kb_ready) {
         const long long t0 = PROBE ? clock64() : 0;
@@ -165,42 +170,80 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
-        const int ky = tap / 3, kx = tap - ky * 3;
+        const int ky = p.kxn ? tap : tap / 3, kx = p.kxn ? 0 : tap - ky * 3;
         const uint64_t dw = umma_desc_sw128(smem_u32(b_ring + (size_t)sb * p.b_stage_bytes));
         const uint64_t dx = umma_desc_sw128(smem_u32(a_ring + (size_t)sa * p.a_bytes) + (uint32_t)(((ky * d) * CW_POS + kx * d) * 128));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           for (int u = u0; u < p.m; u += ustep)      // unit u: 4 halo rows = 16 KB further (1024 descriptor units)
-            umma_tf32(tset + (uint32_t)(u * p.BN), dx + (uint64_t)(u * 1024 + k * 2), dw + (uint64_t)(k * 2), idesc, acc | (uint32_t)k);
+            umma_tf32(tset + (uint32_t)(u * NB), dx + (uint64_t)(u * 1024 + k * 2), dw + (uint64_t)(k * 2), idesc, acc | (uint32_t)k);
         }
         umma_commit(smem_u32(&emptyB[sb]));
-        if ((ib + step) / 9 != kb) umma_commit(smem_u32(&emptyA[sa]));     // this issuer's last tap of the channel block
+        if ((ib + step) / ntap != kb) umma_commit(smem_u32(&emptyA[sa]));  // this issuer's last tap of the channel block
         if (ib + step >= total) umma_commit(smem_u32(accum_full));
       }
       __syncwarp();
       acc = 1;
     }
     if (PROBE && p.probe && blockIdx.x == 0 && lane == 0 && wi == 0) { p.probe[3] = w_fa; p.probe[4] = w_fb; p.probe[5] = clock64() - t_start; }
-  } else {
-    // ===================== epilogue (warps 2..5): lane = position, one pixel per thread and unit =====================
+  }
+  // ===================== epilogue: lane = position, one pixel per thread and unit =====================
+  // warps 2..5 from the start; the producer and issuer warps (0, 1, 6, 7 -- one per TMEM lane quarter as well) join when
+  // their loops are done and take every other unit: the phase is a chain of TMEM-load / store latencies per unit, two
+  // groups of four warps run two such chains at once
+  const bool primary = warp >= 2 && warp < 6;
+  const bool helpers = p.epi_helpers && p.m >= 2;
+  if (primary || helpers) {
     const int q = warp & 3;                                    // TMEM lane quarter = row h of the unit
+    const int u_first = (helpers && !primary) ? 1 : 0, u_step = helpers ? 2 : 1;
     const bool vec_out = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     const size_t img = (size_t)n * p.H * p.W;
     const int x = x0 + lane;
     const bool col_ok = lane < useful && x < p.W;
-    const uint32_t set2 = (uint32_t)(p.m * p.BN);
+    const uint32_t set2 = (uint32_t)(p.m * NB);
     mbar_wait(smem_u32(accum_full), 0);
     const long long t_e1 = PROBE ? clock64() : 0;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int u = 0; u < p.m; ++u) {
+    for (int u = u_first; u < p.m; u += u_step) {
       const int y = y0 + 4 * u + q;
       const bool ok = col_ok && y < p.H;
       const size_t pix = img + (size_t)y * p.W + x;
       float* orow = p.out + pix * p.ldo;
       const float* rrow = p.res ? p.res + pix * p.ldr : nullptr;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * p.BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * NB);
       for (int c0 = 0; c0 < p.Cout; c0 += 32) {
         uint32_t v[32];
+        const int nv = (c0 + 16 < p.BN) ? 32 : 16;                               // warp-uniform
+        if (p.kxn) {
+          // column group kx of lane j holds the products of tap (., kx) with the input at position j: the output at
+          // position j needs them from position j + kx*d -- lane + kx*d of the same warp (a unit row is one warp's 32
+          // lanes, and the lanes whose neighbour would wrap, w >= 32 - 2d, are the ones never stored)
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            uint32_t t[32];
+            const uint32_t ta = taddr + (uint32_t)(g * p.BN + c0);
+            tmem_ld16(ta, t);
+            if (nv == 32) tmem_ld16(ta + 16, t + 16);
+            if (p.tap_split) {
+              uint32_t t2[32];
+              tmem_ld16(ta + set2, t2);
+              if (nv == 32) tmem_ld16(ta + set2 + 16, t2 + 16);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) t[j] = __float_as_uint(__uint_as_float(t[j]) + __uint_as_float(t2[j]));
+            } else {
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < nv) {
+                if (g == 0) v[j] = t[j];
+                else v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(t[j]), g * d));
+              }
+            }
+          }
+        } else {
         tmem_ld16(taddr + (uint32_t)c0, v);
         if (c0 + 16 < p.BN) tmem_ld16(taddr + (uint32_t)(c0 + 16), v + 16);      // warp-uniform
         if (p.tap_split) {                                                       // second accumulator set (odd taps)
@@ -208,12 +251,12 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           tmem_ld16(taddr + set2 + (uint32_t)c0, v2);
           if (c0 + 16 < p.BN) tmem_ld16(taddr + set2 + (uint32_t)(c0 + 16), v2 + 16);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const int nv = (c0 + 16 < p.BN) ? 32 : 16;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (j < nv) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
         } else {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
         }
         if (!ok) continue;
 #pragma unroll
@@ -259,6 +302,7 @@ static int g_win_min_cin = 0;
 static int g_win_max_cout = 64;   // measured (tools/bench_win.py, 1/4- and 1/8-res KITTI): faster than conv_halo.cu for Cout <= 64
                                   // (544->32: 97 vs 139 us, 480->64: 108 vs 130, 576->2: 91 vs 131), slower for 96..128
 static int g_win_force_m = 0;
+static int g_win_kxn = 1;         // the three horizontal taps along N (header note (4)); upf_debug_conv_win bit 2 switches it off
 
 // returns with *taken = 1 when the launch was made, 0 when the shape is not eligible (caller falls through)
 int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
@@ -272,7 +316,17 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
   const int cin_pad = kblocks * 32;
   const int useful = CW_POS - 2 * dil;
   const int tiles_x = (W + useful - 1) / useful;
-  const int b_stage_bytes = BN * 128;                        // multiple of 2048
+  // (4) kxn: one MMA per kernel ROW and K step, N = 3*BN -- column group kx of the accumulator holds the products of tap
+  // (ky, kx) with the UNSHIFTED window, and the epilogue adds group kx of lane + kx*d (a warp shuffle: a unit row is one
+  // warp).  A third of the MMAs, each above the ~40-cycle floor that N <= 32 instructions pay (note (3)), and a third of
+  // the window descriptors / commits / polls per channel block.  The same packed weights serve both forms: the three
+  // taps of a kernel row are consecutive [BN][cin_pad] slabs, one {32, BN, 3} box.
+  // Measured (tools/bench_win.py, 2x94x311): 544->32 85 -> 64 us, 480->64 104 -> 91, 160->16 35 -> 23, 184->3 37 -> 22; at
+  // 1/8 resolution 544->32 49 -> 27, 480->64 47 -> 29.  With one or two channel blocks at BN >= 32 the longer epilogue (three
+  // column groups to read and shift) outweighs the shorter K loop (64->32 22.5 -> 24.5, 32->32 at 1/2 res 47 -> 58).
+  const bool kxn = g_win_kxn && BN <= 64 && (BN <= 16 || kblocks >= 3);
+  const int NB = kxn ? 3 * BN : BN;                          // accumulator columns per unit
+  const int b_stage_bytes = NB * 128;                        // multiple of 2048
   // two resident CTAs per SM (~108 KB rings each): one CTA's epilogue -- 4-8 us of stores per tile with the tensor pipe idle --
   // runs under the other's MMAs.  Measured on whole forwards (tools/ab_win2.py): KITTI b1 2.813 -> 2.790 ms, Sintel b8
   // 15.10 -> 14.56 ms, HD b2 16.39 -> 15.94 ms.  force_m bit 4 (16): one CTA with 224 KB rings (A/B switch)
@@ -280,21 +334,21 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
   // time and the layer is no faster than with one CTA (480->64 at 94x311: 101.4 vs 99.3 us; 544->32: 81.9 vs 93.2 us).
   const bool two_cta = (g_win_force_m & 16) == 0 && (108 * 1024 - 2 * (8 + 2 * dil) * CW_ROW_BYTES) / b_stage_bytes >= 4;
   const int budget = two_cta ? 108 * 1024 : 224 * 1024;
-  // units per CTA and issuer split: minimise waves x (time of one tap), modelled from the microbenchmark --
-  // one issuer needs ~(490 + 145 m) cycles per tap (4m MMAs + commit + poll), two run in parallel, and the tensor
-  // pipe needs 4 m T(N) cycles per tap, T = 40 / 49 / 57 / 65 cycles at N <= 32 / 64 / 96 / 128.
+  // units per CTA and issuer split: minimise waves x (time of one ring item), modelled from the microbenchmark --
+  // one issuer needs ~(490 + 145 m) cycles per item (4m MMAs + commit + poll), two run in parallel, and the tensor
+  // pipe needs 4 m T(N) cycles per item, T = 40 / 49 / 57 / 65 cycles at N <= 32 / 64 / 96 / 128, ~N/2 above.
   // Ties go to the larger tile (fewer weight fetches per pixel).  force_m: +8 forces the unit split.
-  const double T = BN <= 32 ? 40. : BN <= 64 ? 49. : BN <= 96 ? 57. : 65.;
+  const double T = NB <= 32 ? 40. : NB <= 64 ? 49. : NB <= 96 ? 57. : NB <= 128 ? 65. : NB * 0.5;
   int m = 0, tap_split = 1;
   double best = 1e30;
   for (int cand = 4; cand >= 1; cand >>= 1) {
     if ((g_win_force_m & 7) && cand != (g_win_force_m & 7)) continue;
-    int split = (2 * cand * BN <= 512) ? 1 : 0;
+    int split = (2 * cand * NB <= 512) ? 1 : 0;
     if (g_win_force_m & 8) split = 0;
-    if (!split && (cand * BN > 512 || cand < 2)) continue;
+    if (!split && (cand * NB > 512 || cand < 2)) continue;
     const int a_bytes = (4 * cand + 2 * dil) * CW_ROW_BYTES;
     if (2 * a_bytes + (two_cta ? 2 : 3) * b_stage_bytes > budget) continue;
-    if (two_cta && (split ? 2 : 1) * cand * BN > 256) continue;          // both CTAs' accumulators must fit the 512 TMEM columns
+    if (two_cta && (split ? 2 : 1) * cand * NB > 256) continue;          // both CTAs' accumulators must fit the 512 TMEM columns
     const long long t = (long long)tiles_x * ((H + 4 * cand - 1) / (4 * cand)) * N;
     const double issuer = split ? (490. + 145. * cand) / 2 : (490. + 145. * cand / 2);
     const double tap_time = issuer > 4. * cand * T ? issuer : 4. * cand * T;
@@ -321,9 +375,9 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
   {
     const cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)BN, 9};
     const cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 4, (cuuint64_t)cin_pad * BN * 4};
-    const cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
+    const cuuint32_t box[3] = {32, (cuuint32_t)BN, kxn ? 3u : 1u};
     const cuuint32_t estr[3] = {1, 1, 1};
-    MapKey key{w_packed, cin_pad, BN, 9, BN, 3};
+    MapKey key{w_packed, cin_pad, BN, 9, kxn ? 3000 + BN : BN, 3};
     int e = encode_cached(key, &mw, 3, const_cast<float*>(w_packed), dims, strides, box, estr);
     if (e) return e;
   }
@@ -337,9 +391,11 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
   p.flags = flags;
   p.probe = g_halo_probe;
   int cols = 32;
-  while (cols < (tap_split ? 2 : 1) * m * BN) cols <<= 1;
+  while (cols < (tap_split ? 2 : 1) * m * NB) cols <<= 1;
   p.tmem_cols = cols;
   p.tap_split = tap_split;
+  p.kxn = kxn ? 1 : 0;
+  p.epi_helpers = (g_win_force_m & 32) ? 0 : 1;
   int na = (kblocks >= 3 && 3 * p.a_bytes + 4 * b_stage_bytes <= budget) ? 3 : 2;
   if (na > kblocks) na = kblocks;
   int nb = (budget - na * p.a_bytes) / b_stage_bytes;
@@ -383,6 +439,7 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
 extern "C" int upf_debug_conv_win(int enabled, int min_cin, int force_m) {
   upf::g_win_enabled = enabled & 1;
   upf::g_win_max_cout = (enabled & 2) ? 128 : 64;      // bit 1: take every Cout <= 128 (A/B runs)
+  upf::g_win_kxn = (enabled & 4) ? 0 : 1;              // bit 2: one MMA per TAP (N = BN) instead of per kernel row (N = 3 BN)
   if (min_cin >= 0) upf::g_win_min_cin = min_cin;
   upf::g_win_force_m = force_m;
   return 0;
