@@ -483,9 +483,11 @@ def test_conv_tf32_large_grid_kernels_agree(upf, case):
              "win one CTA": (3, 16, 0), "win unit split": (3, 8, 0), "win four epilogue warps": (3, 32, 0),
              "win9": (7, 0, 0), "win9 m1": (7, 1, 0), "win9 m2": (7, 2, 0), "win9 m4": (7, 4, 0)}
     try:
-        for name, (wen, fm, hen) in modes.items():
+        modes["halo four epilogue warps"] = (0, 0, 1, 16)
+        for name, mode in modes.items():
+            wen, fm, hen = mode[:3]
             lib.upf_debug_conv_win(wen, 0, fm)
-            lib.upf_debug_conv_halo(hen, HALO)
+            lib.upf_debug_conv_halo(hen, HALO | (mode[3] if len(mode) > 3 else 0))
             outs = []
             for _ in range(3):
                 buf = torch.full((2, H, W, ldo), 7.0, device="cuda")

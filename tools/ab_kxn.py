@@ -6,18 +6,26 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 from upflow_pytorch_b200 import _ext
+from upflow_pytorch_b200 import engine as E
 from upflow_pytorch_b200.engine import DecoderEngine
 lib = _ext.load()
 sd = bench.make_weights()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-VARIANTS = (("default (kxn, 8 epilogue warps)", 1, 0), ("kxn, 4 epilogue warps", 1, 32), ("per tap, 8 warps", 5, 0), ("per tap, 4 warps (before)", 5, 32))
+# name, conv_win mode, conv_win force bits, largest Cout that runs as 1x1-expand + tap-combine
+VARIANTS = (("default", 1, 0, E.EXPAND_MAX_COUT), ("conv_halo: 4 epilogue warps", 1, 0, E.EXPAND_MAX_COUT, 16), ("expand Cout<=8", 1, 0, 8),
+            ("per tap, 4 epilogue warps, expand (before)", 5, 32, 8, 16))
+if os.environ.get("AB_FULL"):
+    VARIANTS += (("kxn, 4 epilogue warps", 1, 32, E.EXPAND_MAX_COUT), ("per tap, 8 warps", 5, 0, E.EXPAND_MAX_COUT))
 for wl in (sys.argv[1:] or ["kitti_375x1242_b1"]):
     H, W, B = bench.WORKLOADS[wl]
     im1, im2 = bench.synth_inputs(B, H, W, 1234)
     ref = None
     for rep in range(2):
-        for name, wmode, wforce in VARIANTS:
+        for var in VARIANTS:
+            name, wmode, wforce, exp_cout = var[:4]
             lib.upf_debug_conv_win(wmode, 0, wforce)
+            lib.upf_debug_conv_halo(1, (65 << 16) | (128 << 8) | (var[4] if len(var) > 4 else 0))
+            E.EXPAND_MAX_COUT = exp_cout
             eng = DecoderEngine({k: v.cuda() for k, v in sd.items()}, precision="tf32")
             with torch.no_grad():
                 g = eng.capture(B, H, W)
@@ -39,3 +47,4 @@ for wl in (sys.argv[1:] or ["kitti_375x1242_b1"]):
             del g, eng
             torch.cuda.empty_cache()
 lib.upf_debug_conv_win(1, 0, 0)
+lib.upf_debug_conv_halo(1, (65 << 16) | (128 << 8))

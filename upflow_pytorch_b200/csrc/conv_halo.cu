@@ -49,6 +49,7 @@ struct HaloParams {
   int ra, nba, b_rows, nbb;   // halo rows per TMA box / boxes per halo tile; weight rows per box / boxes per tile
   int a_bytes, b_stage_bytes; // per stage (multiples of 1024)
   int tmem_cols;
+  int epi_helpers;            // 1: warps 0, 1, 6, 7 take half of the epilogue
   int two_issuers;            // 1: two MMA-issuing warps, two accumulators (2 * 128 * MT TMEM columns)
   int mc;                     // 1: launched as clusters of two CTAs that share every weight tile (each loads half, TMA multicast)
   int bo_mode;                // 1: descriptor base_offset = (start >> 7) & 7
@@ -211,8 +212,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       }
       if (p.probe && blockIdx.x == 0 && lane == 0 && wi == 0) { p.probe[3] = w_fa; p.probe[4] = w_fb; p.probe[5] = clock64() - t_start; }
     }
-  } else {
-    // ===================== epilogue (warps 2..5) =====================
+  }
+  // ===================== epilogue: warps 2..5, joined by the producer and issuer warps (0, 1, 6, 7 -- one per TMEM lane
+  // quarter as well) once their loops are done: both phases are chains of load -> store latencies, two groups of four warps
+  // run two such chains at once =====================
+  const bool primary = warp >= 2 && warp < 6;
+  const int eh = p.epi_helpers ? 1 : 0;                        // 1: eight epilogue warps
+  if (primary || eh) {
+    const int hw = primary ? 0 : 1;                            // which half of the work this group of four warps takes
     const int q = warp & 3;                                    // TMEM lane quarter = 32 output channels
     const int c = q * 32 + lane;                               // this thread's output channel (phase 1)
     long long t_e0 = clock64();
@@ -224,7 +231,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     float* stage = reinterpret_cast<float*>(base);
     const int npx = 128 * p.MT;
     if (q * 32 < p.Cout) {                                     // warp-uniform: quarters past Cout hold nothing
-      for (int n0 = 0; n0 < npx; n0 += 16) {                   // 16 pixels = 2 tile rows of 8
+      for (int n0 = eh * hw * 16; n0 < npx; n0 += 16 << eh) {  // 16 pixels = 2 tile rows of 8
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, v);
         if (p.two_issuers) {
@@ -243,8 +250,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     // bias goes through shared memory: with ~206 KB of dynamic shared memory the L1 cache is a few KB, and a
     // __ldg per output element costs an L2 round trip (measured: 630 cycles per store iteration)
     float* s_bias = stage + 128 * p.MT * HC_PITCH;
-    s_bias[threadIdx.x - 64] = ((int)threadIdx.x - 64 < p.Cout) ? __ldg(p.bias + threadIdx.x - 64) : 0.f;   // 128 entries
-    asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps
+    if (primary) s_bias[threadIdx.x - 64] = ((int)threadIdx.x - 64 < p.Cout) ? __ldg(p.bias + threadIdx.x - 64) : 0.f;   // 128 entries
+    if (eh) asm volatile("bar.sync 1, 256;" ::: "memory");    // the eight epilogue warps
+    else asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps
     const long long t_e2 = clock64();
     // phase 2: pixel-major 16-byte stores with bias + LeakyReLU (+ residual).  A warp serves 32/c4p pixels per
     // step (c4p = channel quads per pixel rounded up to a power of two): a lane keeps the same 4 channels for the
@@ -258,7 +266,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const bool vec_out = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     const float4 bv = lane_on ? *reinterpret_cast<const float4*>(s_bias + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
     const size_t img = (size_t)n * p.H * p.W;
-    for (int nn0 = q * ppw + sub; nn0 < npx; nn0 += 16 * ppw) {      // 4 pixels per thread per trip: loads first, then stores
+    for (int nn0 = q * ppw + sub + eh * hw * 16 * ppw; nn0 < npx; nn0 += (16 * ppw) << eh) {   // 4 pixels per thread per trip: loads first, then stores
       float4 t[4];
       size_t pix[4];
       bool ok[4];
@@ -313,6 +321,7 @@ static int g_halo_enabled = 1;
 static int g_halo_mc = 1;          // pairs of CTAs share every weight tile by TMA multicast (upf_debug_conv_halo enabled bit 2 = OFF): with ONE MMA
                                    // issuer no faster (2.765 vs 2.764 ms per KITTI forward), with two 2.657 vs 2.672 ms
 static int g_halo_a_boxes = 1;     // TMA boxes per halo tile (upf_debug_conv_halo enabled bits 4..7; must divide the halo rows)
+static int g_halo_epi_helpers = 1; // upf_debug_conv_halo bo_mode bit 4 = four epilogue warps (A/B)
 static int g_halo_two_issuers = 1; // upf_debug_conv_halo enabled bit 3 = one issuer (A/B)
 static int g_halo_two_cta = 0;     // A/B (upf_debug_conv_halo enabled bit 1): 8x16-pixel tiles with ~108 KB rings, two resident CTAs per SM
 static int g_halo_min_cin = 64;    // A/B on the whole KITTI forward (tools/ab_forward.py): off 3.83 ms, >=192 3.72, >=64 3.60, all 3.61
@@ -386,6 +395,7 @@ int conv2d_fwd_halo(const float* x, int ldx, const float* w_packed, const float*
   p.probe = g_halo_probe;
   const bool two_issuers = g_halo_two_issuers && !two_cta;
   p.two_issuers = two_issuers ? 1 : 0;
+  p.epi_helpers = g_halo_epi_helpers;
   p.tmem_cols = (two_issuers ? 2 : 1) * 128 * MT;   // lanes = channels, columns = pixels; one accumulator per issuer
   // ring depths within ~212 KB: at least 2 A stages, then as many B stages as fit (3..8)
   const int budget = two_cta ? 108 * 1024 : 212 * 1024;
@@ -449,6 +459,7 @@ extern "C" int upf_debug_conv_halo(int enabled, int bo_mode) {
   upf::g_halo_a_boxes = ((enabled >> 4) & 15) ? ((enabled >> 4) & 15) : 1;
   upf::g_halo_bo_mode = bo_mode & 7;
   upf::g_tc_pdl = (bo_mode & 8) ? 0 : 1;
+  upf::g_halo_epi_helpers = (bo_mode & 16) ? 0 : 1;
   if ((bo_mode >> 8) & 0xff) upf::g_tc_box_rows = (bo_mode >> 8) & 0xff;     // tuning: rows per TMA box in bits 8..15 (0 = keep)
   if (bo_mode >> 16) upf::g_halo_min_cin = (bo_mode >> 16) - 1;              // tuning: min Cin + 1 in bits 16.. (0 = keep)
   return 0;

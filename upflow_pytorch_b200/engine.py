@@ -67,7 +67,7 @@ def _dense_slots(x_width, x_slots, out_offsets, out_channels, k):
 
 
 CHAIN_MAX_PIXELS = 4096      # feature maps (N*h*w) up to this size run their dense blocks as ONE persistent launch (conv_chain.cu)
-EXPAND_MAX_COUT = 8          # 3x3 convs with at most this many outputs run as 1x1-expand + tap-combine ...
+EXPAND_MAX_COUT = 0          # 3x3 convs with at most this many outputs run as 1x1-expand + tap-combine (0 = never: since conv_win.cu puts the horizontal taps along N, one N = 48 MMA per kernel row beats the expansion -- KITTI forward 2.519 -> 2.444 ms, profiles/r2_ab_expand.txt; tests and A/B runs set it) ...
 EXPAND_MIN_PIXELS = 5000     # ... on images with at least this many pixels (below, the extra launch costs more)
 
 
