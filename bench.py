@@ -480,7 +480,7 @@ def _main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="kitti_375x1242_b1", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "tf32x3"])
-    ap.add_argument("--lanes", type=int, default=3,
+    ap.add_argument("--lanes", type=int, default=4,
                     help="e2e: pairs in flight in pipeline.PipelinedInference (1 = one pair at a time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the `train` sub-record (BASELINE config 4) of the default line")
