@@ -480,7 +480,7 @@ def test_conv_tf32_large_grid_kernels_agree(upf, case):
     ldo = (Cout + 3) // 4 * 4 + 4
     HALO = (1 << 16) | (128 << 8)
     modes = {"tap": (0, 0, 0), "halo": (0, 0, 1), "win": (3, 0, 0), "win m1": (3, 1, 0), "win m2": (3, 2, 0), "win m4": (3, 4, 0),
-             "win one CTA": (3, 16, 0), "win unit split": (3, 8, 0), "win four epilogue warps": (3, 32, 0),
+             "win one CTA": (3, 16, 0), "win unit split": (3, 8, 0), "win four epilogue warps": (3, 32, 0), "win weight multicast": (3, 64, 0), "win9 weight multicast": (7, 64, 0),
              "win9": (7, 0, 0), "win9 m1": (7, 1, 0), "win9 m2": (7, 2, 0), "win9 m4": (7, 4, 0)}
     try:
         modes["halo four epilogue warps"] = (0, 0, 1, 16)

@@ -50,11 +50,25 @@ struct WinParams {
   int tmem_cols;
   int tap_split;              // 1: issuers alternate taps (two accumulator sets), 0: issuers alternate units
   int epi_helpers;            // 1: warps 0, 1, 6, 7 take the odd units of the epilogue
+  int mc;                     // 1: clusters of two CTAs share every weight tile (each fetches half of its rows, TMA multicast)
   int kxn;                    // 1: the three horizontal taps along N (one MMA per ky and K step, N = 3*BN; header note (4))
   long long* probe;
   float slope;
   int flags;
 };
+
+// half a weight slab, delivered to the same shared-memory offset (and counted on the same mbarrier offset) of BOTH CTAs of a pair
+__device__ __forceinline__ void win_tma_load_3d_mc2(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at this offset in BOTH CTAs of the pair (a shared weight slot is free when both have read it)
+__device__ __forceinline__ void win_umma_commit_mc2(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
 
 template <bool PROBE>
 __global__ void __launch_bounds__(CW_THREADS)
@@ -89,7 +103,7 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     for (int s = 0; s < p.na; ++s) { mbar_init(smem_u32(&fullA[s]), 1); mbar_init(smem_u32(&emptyA[s]), 2); }
-    for (int s = 0; s < p.nb; ++s) { mbar_init(smem_u32(&fullB[s]), 1); mbar_init(smem_u32(&emptyB[s]), p.tap_split ? 1 : 2); }
+    for (int s = 0; s < p.nb; ++s) { mbar_init(smem_u32(&fullB[s]), 1); mbar_init(smem_u32(&emptyB[s]), (p.tap_split ? 1 : 2) * (p.mc ? 2 : 1)); }
     mbar_init(smem_u32(accum_full), 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -102,9 +116,11 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     s_bias[c] = c < p.Cout ? __ldg(p.bias + c) : 0.f;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (p.mc) cluster_sync_all();        // the peer's barriers exist before anything is multicast into this CTA
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  const int crank = p.mc ? (int)cluster_ctarank() : 0;
   // programmatic dependent launch: everything above touched only this CTA's state and constant weights
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
@@ -121,8 +137,16 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (PROBE) w_eb += clock64() - t0;
         const uint32_t fb = smem_u32(&fullB[sb]);
         mbar_expect_tx(fb, b_bytes);
-        // kxn: the box holds the three taps of kernel row `tap`, rows (kx, co) -- 3*BN operand rows of 128 bytes
-        tma_load_3d(smem_u32(b_ring + (size_t)sb * p.b_stage_bytes), &map_w, fb, kb * 32, 0, p.kxn ? tap * 3 : tap);
+        const uint32_t b_dst = smem_u32(b_ring + (size_t)sb * p.b_stage_bytes);
+        if (p.mc) {
+          // this CTA fetches rows [rank BN/2, +BN/2) of every tap slab for both CTAs; the peer's halves arrive on the same barrier
+          const int hr = p.BN >> 1;
+          for (int t = 0; t < (p.kxn ? 3 : 1); ++t)
+            win_tma_load_3d_mc2(b_dst + (uint32_t)((t * p.BN + crank * hr) * 128), &map_w, fb, kb * 32, crank * hr, p.kxn ? tap * 3 + t : tap);
+        } else {
+          // kxn: the box holds the three taps of kernel row `tap`, rows (kx, co) -- 3*BN operand rows of 128 bytes
+          tma_load_3d(b_dst, &map_w, fb, kb * 32, 0, p.kxn ? tap * 3 : tap);
+        }
       }
       if (PROBE && p.probe && blockIdx.x == 0) { p.probe[1] = w_eb; p.probe[2] = clock64() - t_start; }
     }
@@ -178,7 +202,8 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           for (int u = u0; u < p.m; u += ustep)      // unit u: 4 halo rows = 16 KB further (1024 descriptor units)
             umma_tf32(tset + (uint32_t)(u * NB), dx + (uint64_t)(u * 1024 + k * 2), dw + (uint64_t)(k * 2), idesc, acc | (uint32_t)k);
         }
-        umma_commit(smem_u32(&emptyB[sb]));
+        if (p.mc) win_umma_commit_mc2(smem_u32(&emptyB[sb]));
+        else umma_commit(smem_u32(&emptyB[sb]));
         if ((ib + step) / ntap != kb) umma_commit(smem_u32(&emptyA[sa]));  // this issuer's last tap of the channel block
         if (ib + step >= total) umma_commit(smem_u32(accum_full));
       }
@@ -288,7 +313,8 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     if (PROBE && p.probe && blockIdx.x == 0 && threadIdx.x == 64) { p.probe[6] = 0; p.probe[7] = clock64() - t_e1; }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
-  __syncthreads();
+  if (p.mc) cluster_sync_all();        // nobody leaves while the peer may still multicast into it or arrive on its barriers
+  else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -362,6 +388,12 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
   if (tiles * m < 96) return 0;                              // coarse levels: the cluster split-K kernel is the better fit
   const int rows = 4 * m + 2 * dil;
 
+  // pairs of CTAs sharing every weight tile by TMA multicast (as conv_halo.cu does): built, parity-green, and measured SLOWER here
+  // (544->32 at 2x94x311 61.4 vs 59.4 us, KITTI forward 2.403 vs 2.386 ms, Sintel b8 12.10 vs 12.00 ms; profiles/r2_ab_mcw.txt):
+  // these layers are not bound by weight traffic out of L2 but by shared-memory bandwidth -- an M = 128, N = 96, K = 8 MMA reads
+  // (128 + 96) x 32 B = 7 KB of operands in its 57 cycles, ~123 B/clk next to the TMA writes -- and the lock-step of the pair
+  // costs more than the halved fetches save.  Off by default; force_m bit 6 (64) switches it on (A/B, tests).
+  const bool mc = (g_win_force_m & 64) != 0 && !two_cta && (tiles % 2 == 0) && BN >= 32 && kblocks >= 3;
   CUtensorMap mx, mw;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -375,9 +407,9 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
   {
     const cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)BN, 9};
     const cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 4, (cuuint64_t)cin_pad * BN * 4};
-    const cuuint32_t box[3] = {32, (cuuint32_t)BN, kxn ? 3u : 1u};
+    const cuuint32_t box[3] = {32, (cuuint32_t)(mc ? BN / 2 : BN), (kxn && !mc) ? 3u : 1u};
     const cuuint32_t estr[3] = {1, 1, 1};
-    MapKey key{w_packed, cin_pad, BN, 9, kxn ? 3000 + BN : BN, 3};
+    MapKey key{w_packed, cin_pad, BN, 9, mc ? 6000 + BN : kxn ? 3000 + BN : BN, 3};
     int e = encode_cached(key, &mw, 3, const_cast<float*>(w_packed), dims, strides, box, estr);
     if (e) return e;
   }
@@ -395,6 +427,7 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
   p.tmem_cols = cols;
   p.tap_split = tap_split;
   p.kxn = kxn ? 1 : 0;
+  p.mc = mc ? 1 : 0;
   p.epi_helpers = (g_win_force_m & 32) ? 0 : 1;
   int na = (kblocks >= 3 && 3 * p.a_bytes + 4 * b_stage_bytes <= budget) ? 3 : 2;
   if (na > kblocks) na = kblocks;
@@ -419,11 +452,20 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
   cfg.blockDim = dim3(CW_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na_ = 0;
+  if (g_tc_pdl) {
+    attr[na_].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na_].val.programmaticStreamSerializationAllowed = 1;
+    ++na_;
+  }
+  if (mc) {
+    attr[na_].id = cudaLaunchAttributeClusterDimension;
+    attr[na_].val.clusterDim.x = 2; attr[na_].val.clusterDim.y = 1; attr[na_].val.clusterDim.z = 1;
+    ++na_;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = g_tc_pdl ? 1 : 0;
+  cfg.numAttrs = na_;
   {
     cudaError_t e = p.probe ? cudaLaunchKernelEx(&cfg, conv_win_kernel<true>, mx, mw, p) : cudaLaunchKernelEx(&cfg, conv_win_kernel<false>, mx, mw, p);
     if (e != cudaSuccess) { set_error("conv_win launch: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return (int)e; }
