@@ -390,8 +390,9 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
 
   // pairs of CTAs sharing every weight tile by TMA multicast (as conv_halo.cu does): built, parity-green, and measured SLOWER here
   // (544->32 at 2x94x311 61.4 vs 59.4 us, KITTI forward 2.403 vs 2.386 ms, Sintel b8 12.10 vs 12.00 ms; profiles/r2_ab_mcw.txt):
-  // these layers are not bound by weight traffic out of L2 but by shared-memory bandwidth -- an M = 128, N = 96, K = 8 MMA reads
-  // (128 + 96) x 32 B = 7 KB of operands in its 57 cycles, ~123 B/clk next to the TMA writes -- and the lock-step of the pair
+  // these layers are not bound by weight traffic out of L2.  ncu on 544->32 (profiles/r2_ncu_full_conv_win_544to32_kxn.md): L2
+  // 20 % of its peak throughput, tensor-core shared-memory reads 40 %, tensor pipe 43 % active -- no unit is saturated; what is
+  // left is the issue side (commit / poll bubbles per ring item), the prologue and the epilogue, and the lock-step of a pair
   // costs more than the halved fetches save.  Off by default; force_m bit 6 (64) switches it on (A/B, tests).
   const bool mc = (g_win_force_m & 64) != 0 && !two_cta && (tiles % 2 == 0) && BN >= 32 && kblocks >= 3;
   CUtensorMap mx, mw;
