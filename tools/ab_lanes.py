@@ -1,5 +1,5 @@
 """A/B: PipelinedInference with 1, 2, 3 compute lanes (graphs of consecutive pairs replaying concurrently).
-   python tools/ab_lanes.py [workload] [steps]
+   python tools/ab_lanes.py [workload] [steps] [lanes,lanes,...]
 Prints pairs/s end to end (pinned host in, host out) per lane count and checks that every lane count returns
 bit-identical flows for a sequence of different pairs."""
 import os, sys, time
@@ -14,7 +14,8 @@ H, W, B = bench.WORKLOADS[wl]
 net, sd, wdesc = bench.build_net(None, "tf32")
 pairs = [tuple(t.pin_memory() for t in bench.synth_inputs(B, H, W, 1234 + i)) for i in range(4)]
 ref = None
-for lanes in (1, 2, 3, 1, 2):
+LANES = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else [1, 2, 3, 1, 2]
+for lanes in LANES:
     pipe = PipelinedInference(net, lanes=lanes)
     got = []
     for i in range(8):

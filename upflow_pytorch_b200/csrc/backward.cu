@@ -252,25 +252,40 @@ blend_bwd_kernel(const float* __restrict__ w, int ldw, const float* __restrict__
 // y = (x - mean) / std with mean, std functions of x (unbiased variance, std = sqrt(var + 1e-16)):
 //   dx = ( g - mean(g) - y * sum(g*y) / (n-1) ) / std
 // pass 1: per split, per (image, channel): sum g and sum g*y over a pixel range -> part[split][n][c][2] (double)
+// Like colsum_kernel: a CTA is cw channel lanes x 256/cw pixel slots (cw = C rounded up to a power of two, <= 256), every
+// thread walks its slot's pixels of the split, the slots are summed through shared memory in slot order (deterministic).
+// (First version: one thread per channel walking the split alone -- 32 of 256 threads at C = 32, 65 us per call.)
 __global__ void __launch_bounds__(256)
 featnorm_bwd_sums_kernel(const float* __restrict__ x, int ldx, const double* __restrict__ stats, const float* __restrict__ g,
-                         int ldg, double* __restrict__ part, int N, int HW, int C, int splits) {
+                         int ldg, double* __restrict__ part, int N, int HW, int C, int splits, int cw) {
+  __shared__ double s_sg[256], s_sgy[256];
   const int n = blockIdx.x / splits, split = blockIdx.x % splits;
   const int per = (HW + splits - 1) / splits;
   const int p_begin = split * per, p_end = min(HW, p_begin + per);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float m, s;
-    stats_to_mean_std(stats + ((size_t)n * C + c) * 2, (double)HW, m, s);
+  const int slots = 256 / cw, lane_c = threadIdx.x % cw, slot = threadIdx.x / cw;
+  for (int c0 = 0; c0 < C; c0 += cw) {
+    const int c = c0 + lane_c;
     double sg = 0.0, sgy = 0.0;
-    for (int p = p_begin; p < p_end; ++p) {
-      const size_t pix = (size_t)n * HW + p;
-      const float gv = g[pix * ldg + c];
-      const float y = __fdiv_rn(__fsub_rn(x[pix * ldx + c], m), s);
-      sg += (double)gv;
-      sgy += (double)gv * (double)y;
+    if (c < C) {
+      float m, s;
+      stats_to_mean_std(stats + ((size_t)n * C + c) * 2, (double)HW, m, s);
+      for (int p = p_begin + slot; p < p_end; p += slots) {
+        const size_t pix = (size_t)n * HW + p;
+        const float gv = __ldg(g + pix * ldg + c);
+        const float y = __fdiv_rn(__fsub_rn(__ldg(x + pix * ldx + c), m), s);
+        sg += (double)gv;
+        sgy += (double)gv * (double)y;
+      }
     }
-    double* d = part + (((size_t)split * N + n) * C + c) * 2;
-    d[0] = sg; d[1] = sgy;
+    s_sg[threadIdx.x] = sg; s_sgy[threadIdx.x] = sgy;
+    __syncthreads();
+    if (slot == 0 && c < C) {
+      double a = 0.0, b = 0.0;
+      for (int k = 0; k < slots; ++k) { a += s_sg[k * cw + lane_c]; b += s_sgy[k * cw + lane_c]; }
+      double* d = part + (((size_t)split * N + n) * C + c) * 2;
+      d[0] = a; d[1] = b;
+    }
+    __syncthreads();
   }
 }
 __global__ void __launch_bounds__(256)
@@ -544,7 +559,9 @@ extern "C" int upf_featnorm_bwd(const float* x, int ldx, const double* stats, co
   UPF_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && ldx >= C && ldg >= C && ldgx >= C, "featnorm_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   const int splits = UPF_FEATNORM_BWD_SPLITS;
-  featnorm_bwd_sums_kernel<<<N * splits, 256, 0, st>>>(x, ldx, stats, grad_out, ldg, workspace, N, H * W, C, splits);
+  int cw = 1;
+  while (cw < C && cw < 256) cw <<= 1;
+  featnorm_bwd_sums_kernel<<<N * splits, 256, 0, st>>>(x, ldx, stats, grad_out, ldg, workspace, N, H * W, C, splits, cw);
   int e = check_launch("featnorm_bwd_sums");
   if (e) return e;
   featnorm_bwd_apply_kernel<<<grid_for((long long)N * H * W * C), 256, 0, st>>>(x, ldx, stats, grad_out, ldg, workspace, grad_x, ldgx,

@@ -278,6 +278,119 @@ warp_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ 
 }
 
 
+// Vector form (C % 4 == 0, 16-byte aligned rows): lpp lanes share a pixel, a lane owns channel quads -- one 16-byte load of
+// the gradient and ONE 16-byte reduction (red.global.add.v4.f32) per corner instead of four scalar atomics, 32/lpp pixels per
+// warp; the per-pixel taps are computed by one lane of the group and broadcast, like the forward kernel.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+warp_bwd_vec_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ flow, int ldf,
+                    const float* __restrict__ go, int ldg, float* __restrict__ gx, int ldgx,
+                    float* __restrict__ gflow, int ldgf, int N, int H, int W, int C, int align_corners, float mask_thr, int lpp) {
+  pdl_prologue();
+  const long long npix = (long long)N * H * W;
+  const int lane = threadIdx.x & 31;
+  const int ppw = 32 / lpp;                                   // pixels per warp
+  const int sub = lane % lpp;
+  const int leader = lane - sub;
+  const int quads = VEC ? C >> 2 : C;                         // work items per pixel: channel quads, or single channels
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long pb = warp0 * ppw; pb < npix; pb += nwarps * ppw) {   // warp-uniform trip count (shuffles below)
+    const long long p_raw = pb + lane / lpp;
+    const bool live = p_raw < npix;
+    const long long p = live ? p_raw : npix - 1;
+    const int xpix = (int)(p % W);
+    const int y = (int)((p / W) % H);
+    const long long n = p / ((long long)W * H);
+    BilinearTaps t;
+    float ix = 0.f, iy = 0.f;
+    int flags = 0;
+    if (lane == leader) {
+      const float* fl = flow + (size_t)p * ldf;
+      ix = sample_coord((float)xpix, __ldg(fl), W, align_corners);
+      iy = sample_coord((float)y, __ldg(fl + 1), H, align_corners);
+      t = bilinear_taps(ix, iy, H, W);
+      const bool k = !(mask_thr > 0.f) || t.wsum >= mask_thr;
+      flags = (t.in_nw ? 1 : 0) | (t.in_ne ? 2 : 0) | (t.in_sw ? 4 : 0) | (t.in_se ? 8 : 0) | (k ? 16 : 0);
+    }
+    t.x0 = __shfl_sync(0xffffffffu, t.x0, leader);
+    t.y0 = __shfl_sync(0xffffffffu, t.y0, leader);
+    t.w_nw = __shfl_sync(0xffffffffu, t.w_nw, leader);
+    t.w_ne = __shfl_sync(0xffffffffu, t.w_ne, leader);
+    t.w_sw = __shfl_sync(0xffffffffu, t.w_sw, leader);
+    t.w_se = __shfl_sync(0xffffffffu, t.w_se, leader);
+    ix = __shfl_sync(0xffffffffu, ix, leader);
+    iy = __shfl_sync(0xffffffffu, iy, leader);
+    flags = __shfl_sync(0xffffffffu, flags, leader);
+    const bool in_nw = flags & 1, in_ne = flags & 2, in_sw = flags & 4, in_se = flags & 8;
+    const bool keep = live && (flags & 16) != 0;
+    float gix = 0.f, giy = 0.f;
+    if (keep) {
+      const long long base = ((long long)n * H + t.y0) * W + t.x0;   // corners are only touched when in_*
+      const float fx0 = floorf(ix), fy0 = floorf(iy);
+      const float ax1 = (fx0 + 1.f) - ix, ax0 = ix - fx0, ay1 = (fy0 + 1.f) - iy, ay0 = iy - fy0;
+      for (int q4 = sub; q4 < quads; q4 += lpp) {
+        if (!VEC) {
+          // few channels (the 3-channel images of the photometric loss), or unaligned rows: one channel per lane
+          const int c = q4;
+          const float g = __ldg(go + (size_t)p * ldg + c);
+          if (gx) {
+            if (in_nw) atomicAdd(gx + base * ldgx + c, g * t.w_nw);
+            if (in_ne) atomicAdd(gx + (base + 1) * ldgx + c, g * t.w_ne);
+            if (in_sw) atomicAdd(gx + (base + W) * ldgx + c, g * t.w_sw);
+            if (in_se) atomicAdd(gx + (base + W + 1) * ldgx + c, g * t.w_se);
+          }
+          if (gflow) {
+            const float v_nw = in_nw ? __ldg(x + base * ldx + c) : 0.f;
+            const float v_ne = in_ne ? __ldg(x + (base + 1) * ldx + c) : 0.f;
+            const float v_sw = in_sw ? __ldg(x + (base + W) * ldx + c) : 0.f;
+            const float v_se = in_se ? __ldg(x + (base + W + 1) * ldx + c) : 0.f;
+            gix += g * ((v_ne - v_nw) * ay1 + (v_se - v_sw) * ay0);
+            giy += g * ((v_sw - v_nw) * ax1 + (v_se - v_ne) * ax0);
+          }
+          continue;
+        }
+        const int c = q4 * 4;
+        const float4 g = ldg4(go + (size_t)p * ldg + c);
+        if (gx) {
+          if (in_nw) atomicAdd(reinterpret_cast<float4*>(gx + base * ldgx + c), make_float4(g.x * t.w_nw, g.y * t.w_nw, g.z * t.w_nw, g.w * t.w_nw));
+          if (in_ne) atomicAdd(reinterpret_cast<float4*>(gx + (base + 1) * ldgx + c), make_float4(g.x * t.w_ne, g.y * t.w_ne, g.z * t.w_ne, g.w * t.w_ne));
+          if (in_sw) atomicAdd(reinterpret_cast<float4*>(gx + (base + W) * ldgx + c), make_float4(g.x * t.w_sw, g.y * t.w_sw, g.z * t.w_sw, g.w * t.w_sw));
+          if (in_se) atomicAdd(reinterpret_cast<float4*>(gx + (base + W + 1) * ldgx + c), make_float4(g.x * t.w_se, g.y * t.w_se, g.z * t.w_se, g.w * t.w_se));
+        }
+        if (gflow) {
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 v_nw = in_nw ? ldg4(x + base * ldx + c) : z;
+          const float4 v_ne = in_ne ? ldg4(x + (base + 1) * ldx + c) : z;
+          const float4 v_sw = in_sw ? ldg4(x + (base + W) * ldx + c) : z;
+          const float4 v_se = in_se ? ldg4(x + (base + W + 1) * ldx + c) : z;
+          gix += g.x * ((v_ne.x - v_nw.x) * ay1 + (v_se.x - v_sw.x) * ay0);
+          giy += g.x * ((v_sw.x - v_nw.x) * ax1 + (v_se.x - v_ne.x) * ax0);
+          gix += g.y * ((v_ne.y - v_nw.y) * ay1 + (v_se.y - v_sw.y) * ay0);
+          giy += g.y * ((v_sw.y - v_nw.y) * ax1 + (v_se.y - v_ne.y) * ax0);
+          gix += g.z * ((v_ne.z - v_nw.z) * ay1 + (v_se.z - v_sw.z) * ay0);
+          giy += g.z * ((v_sw.z - v_nw.z) * ax1 + (v_se.z - v_ne.z) * ax0);
+          gix += g.w * ((v_ne.w - v_nw.w) * ay1 + (v_se.w - v_sw.w) * ay0);
+          giy += g.w * ((v_sw.w - v_nw.w) * ax1 + (v_se.w - v_ne.w) * ax0);
+        }
+      }
+    }
+    if (gflow) {
+      for (int o = lpp >> 1; o > 0; o >>= 1) {                 // within the lpp lanes of a pixel (lpp is a power of two)
+        gix += __shfl_xor_sync(0xffffffffu, gix, o);
+        giy += __shfl_xor_sync(0xffffffffu, giy, o);
+      }
+      if (sub == 0 && live) {
+        const float sx = align_corners ? 1.0f : (float)W / (float)(W > 1 ? W - 1 : 1);
+        const float sy = align_corners ? 1.0f : (float)H / (float)(H > 1 ? H - 1 : 1);
+        gflow[(size_t)p * ldgf + 0] = gix * sx;
+        gflow[(size_t)p * ldgf + 1] = giy * sy;
+      }
+    }
+  }
+}
+
+
 // ---- normalize_features' other moment modes (model/upflow.py:94-137) ----------------------------------------------
 // The correlation kernels normalise with per-(image, channel) statistics given as (sum, sum of squares).  The
 // reference can also pool the moments over the channels of an image (moments_across_channels: mean / unbiased var
@@ -444,6 +557,23 @@ extern "C" int upf_warp_bwd(const float* x, int ldx, const float* flow, int ldf,
   UPF_REQUIRE(x && flow && grad_out, "warp_bwd: null tensor");
   UPF_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "warp_bwd: bad shape");
   const long long npix = (long long)N * H * W;
+  const bool vec = (C % 4 == 0) && (ldx % 4 == 0) && (ldg % 4 == 0) && (!grad_x || ldgx % 4 == 0) && aligned16(x) && aligned16(grad_out) &&
+                   (!grad_x || aligned16(grad_x));
+  if (vec || C <= 16) {
+    const int items = vec ? C / 4 : C;
+    int lpp = 1;
+    while (lpp < items && lpp < 32) lpp <<= 1;
+    const int ppw = 32 / lpp;
+    long long vblocks = ((npix + ppw - 1) / ppw * 32 + 255) / 256;
+    if (vblocks > UPF_NUM_SMS * 16) vblocks = UPF_NUM_SMS * 16;
+    if (vec)
+      UPF_LAUNCH((warp_bwd_vec_kernel<true>), (unsigned)vblocks, 256, 0, (cudaStream_t)stream, x, ldx, flow, ldf, grad_out, ldg, grad_x, ldgx,
+                                                                                    grad_flow, ldgf, N, H, W, C, align_corners, mask_threshold, lpp);
+    else
+      UPF_LAUNCH((warp_bwd_vec_kernel<false>), (unsigned)vblocks, 256, 0, (cudaStream_t)stream, x, ldx, flow, ldf, grad_out, ldg, grad_x, ldgx,
+                                                                                     grad_flow, ldgf, N, H, W, C, align_corners, mask_threshold, lpp);
+    return check_launch("warp_bwd");
+  }
   long long blocks = (npix * 32 + 255) / 256;
   if (blocks > UPF_NUM_SMS * 16) blocks = UPF_NUM_SMS * 16;
   UPF_LAUNCH((warp_bwd_kernel), (unsigned)blocks, 256, 0, (cudaStream_t)stream, x, ldx, flow, ldf, grad_out, ldg, grad_x, ldgx,
