@@ -12,7 +12,7 @@ lib = _ext.load()
 sd = bench.make_weights()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 # name, conv_win mode, conv_win force bits, largest Cout that runs as 1x1-expand + tap-combine
-VARIANTS = (("default", 1, 0, E.EXPAND_MAX_COUT), ("conv_win: weight multicast", 1, 64, E.EXPAND_MAX_COUT), ("conv_win: every Cout <= 128", 3, 0, E.EXPAND_MAX_COUT),
+VARIANTS = (("default", 1, 0, E.EXPAND_MAX_COUT), ("conv_win: ring item per kernel row", 9, 0, E.EXPAND_MAX_COUT), ("conv_win: BN=16 kernel-row items, two CTAs", 1, 0, E.EXPAND_MAX_COUT, 0, 1000 + (1 << 20)),
             ("per tap, 4 epilogue warps, expand (before)", 5, 32, 8, 16))
 if os.environ.get("AB_FULL"):
     VARIANTS += (("kxn, 4 epilogue warps", 1, 32, E.EXPAND_MAX_COUT), ("per tap, 8 warps", 5, 0, E.EXPAND_MAX_COUT))
@@ -23,7 +23,7 @@ for wl in (sys.argv[1:] or ["kitti_375x1242_b1"]):
     for rep in range(2):
         for var in VARIANTS:
             name, wmode, wforce, exp_cout = var[:4]
-            lib.upf_debug_conv_win(wmode, 0, wforce)
+            lib.upf_debug_conv_win(wmode, var[5] if len(var) > 5 else 1003, wforce)
             lib.upf_debug_conv_halo(1, (65 << 16) | (128 << 8) | (var[4] if len(var) > 4 else 0))
             E.EXPAND_MAX_COUT = exp_cout
             eng = DecoderEngine({k: v.cuda() for k, v in sd.items()}, precision="tf32")

@@ -95,14 +95,16 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int d = p.dil;
   const int useful = CW_POS - 2 * d;
   const int x0 = tx * useful, y0 = ty * 4 * p.m;
-  const int ntap = p.kxn ? 3 : 9;                                     // ring items per channel block: kernel rows / taps
+  const int ntap = p.kxn == 2 ? 1 : p.kxn ? 3 : 9;                    // ring items per channel block: one / kernel rows / taps
+  const int nslab = p.kxn == 2 ? 9 : p.kxn ? 3 : 1;                   // [BN][32] weight slabs (taps) per ring item
   const int NB = p.kxn ? 3 * p.BN : p.BN;                             // accumulator width of one unit
-  const uint32_t b_bytes = (uint32_t)NB * 128u;
+  const uint32_t b_bytes = (uint32_t)(nslab * p.BN) * 128u;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    for (int s = 0; s < p.na; ++s) { mbar_init(smem_u32(&fullA[s]), 1); mbar_init(smem_u32(&emptyA[s]), 2); }
+    // a halo slot is released by both issuers -- except where a ring item is a whole channel block and the issuers alternate items
+    for (int s = 0; s < p.na; ++s) { mbar_init(smem_u32(&fullA[s]), 1); mbar_init(smem_u32(&emptyA[s]), (p.kxn == 2 && p.tap_split) ? 1 : 2); }
     for (int s = 0; s < p.nb; ++s) { mbar_init(smem_u32(&fullB[s]), 1); mbar_init(smem_u32(&emptyB[s]), (p.tap_split ? 1 : 2) * (p.mc ? 2 : 1)); }
     mbar_init(smem_u32(accum_full), 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -141,11 +143,11 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (p.mc) {
           // this CTA fetches rows [rank BN/2, +BN/2) of every tap slab for both CTAs; the peer's halves arrive on the same barrier
           const int hr = p.BN >> 1;
-          for (int t = 0; t < (p.kxn ? 3 : 1); ++t)
-            win_tma_load_3d_mc2(b_dst + (uint32_t)((t * p.BN + crank * hr) * 128), &map_w, fb, kb * 32, crank * hr, p.kxn ? tap * 3 + t : tap);
+          for (int t = 0; t < nslab; ++t)
+            win_tma_load_3d_mc2(b_dst + (uint32_t)((t * p.BN + crank * hr) * 128), &map_w, fb, kb * 32, crank * hr, tap * nslab + t);
         } else {
-          // kxn: the box holds the three taps of kernel row `tap`, rows (kx, co) -- 3*BN operand rows of 128 bytes
-          tma_load_3d(b_dst, &map_w, fb, kb * 32, 0, p.kxn ? tap * 3 : tap);
+          // kxn: the box holds the three taps of kernel row `tap`, rows (kx, co) -- 3*BN operand rows of 128 bytes (kxn = 2: all nine)
+          tma_load_3d(b_dst, &map_w, fb, kb * 32, 0, tap * nslab);
         }
       }
       if (PROBE && p.probe && blockIdx.x == 0) { p.probe[1] = w_eb; p.probe[2] = clock64() - t_start; }
@@ -194,13 +196,17 @@ conv_win_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
-        const int ky = p.kxn ? tap : tap / 3, kx = p.kxn ? 0 : tap - ky * 3;
-        const uint64_t dw = umma_desc_sw128(smem_u32(b_ring + (size_t)sb * p.b_stage_bytes));
-        const uint64_t dx = umma_desc_sw128(smem_u32(a_ring + (size_t)sa * p.a_bytes) + (uint32_t)(((ky * d) * CW_POS + kx * d) * 128));
+        const int ky0 = p.kxn ? tap : tap / 3, kx = p.kxn ? 0 : tap - ky0 * 3;
+        const int nky = p.kxn == 2 ? 3 : 1;                  // kxn = 2: the item is the whole channel block, the three kernel rows in turn
+        for (int kyi = 0; kyi < nky; ++kyi) {
+          const int ky = ky0 + kyi;
+          const uint64_t dw = umma_desc_sw128(smem_u32(b_ring + (size_t)sb * p.b_stage_bytes) + (uint32_t)(kyi * 3 * p.BN * 128));
+          const uint64_t dx = umma_desc_sw128(smem_u32(a_ring + (size_t)sa * p.a_bytes) + (uint32_t)(((ky * d) * CW_POS + kx * d) * 128));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          for (int u = u0; u < p.m; u += ustep)      // unit u: 4 halo rows = 16 KB further (1024 descriptor units)
-            umma_tf32(tset + (uint32_t)(u * NB), dx + (uint64_t)(u * 1024 + k * 2), dw + (uint64_t)(k * 2), idesc, acc | (uint32_t)k);
+          for (int k = 0; k < 4; ++k) {
+            for (int u = u0; u < p.m; u += ustep)      // unit u: 4 halo rows = 16 KB further (1024 descriptor units)
+              umma_tf32(tset + (uint32_t)(u * NB), dx + (uint64_t)(u * 1024 + k * 2), dw + (uint64_t)(k * 2), idesc, acc | (uint32_t)(k | kyi));
+          }
         }
         if (p.mc) win_umma_commit_mc2(smem_u32(&emptyB[sb]));
         else umma_commit(smem_u32(&emptyB[sb]));
@@ -329,6 +335,9 @@ static int g_win_max_cout = 64;   // measured (tools/bench_win.py, 1/4- and 1/8-
                                   // (544->32: 97 vs 139 us, 480->64: 108 vs 130, 576->2: 91 vs 131), slower for 96..128
 static int g_win_force_m = 0;
 static int g_win_kxn = 1;         // the three horizontal taps along N (header note (4)); upf_debug_conv_win bit 2 switches it off
+static int g_win_kxn2_min_kb16 = 3;         // BN = 16: channel-block items (one CTA per SM) from this many channel blocks on, two CTAs with kernel-row items
+                                            // below (A/B: upf_debug_conv_win min_cin >= 1000 sets it; KITTI forward 2.366 -> 2.348 ms)
+static int g_win_kxn2 = 1;        // ... with ONE ring item per channel block (all nine weight slabs in a stage); bit 3 = one item per kernel row
 
 // returns with *taken = 1 when the launch was made, 0 when the shape is not eligible (caller falls through)
 int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
@@ -352,7 +361,13 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
   // column groups to read and shift) outweighs the shorter K loop (64->32 22.5 -> 24.5, 32->32 at 1/2 res 47 -> 58).
   const bool kxn = g_win_kxn && BN <= 64 && (BN <= 16 || kblocks >= 3);
   const int NB = kxn ? 3 * BN : BN;                          // accumulator columns per unit
-  const int b_stage_bytes = NB * 128;                        // multiple of 2048
+  // kxn = 2: a ring item is a whole CHANNEL BLOCK -- the nine weight slabs in one stage, the issuer walks the three kernel rows
+  // inside the item: a third of the commits / polls again (a commit idles the tensor pipe for ~280 cycles, and with the unit
+  // split both issuers reach it together), where two halo stages and two 9-slab weight stages fit.  tools/bench_win.py at
+  // 2x94x311: 544->32 59.3 -> 51.1 us, 480->64 86.0 -> 71.6; at 2x47x156 544->32 26.5 -> 22.4; KITTI forward 2.406 -> 2.369 ms,
+  // Sintel b8 12.13 -> 11.90 ms (profiles/r2_ab_kxn2.txt)
+  bool kxn2 = kxn && g_win_kxn2 && (BN >= 32 || (kblocks >= g_win_kxn2_min_kb16)) && kblocks >= 3 && 2 * (8 + 2 * dil) * CW_ROW_BYTES + 2 * 9 * BN * 128 <= 224 * 1024;
+  const int b_stage_bytes = (kxn2 ? 9 * BN : NB) * 128;      // multiple of 2048
   // two resident CTAs per SM (~108 KB rings each): one CTA's epilogue -- 4-8 us of stores per tile with the tensor pipe idle --
   // runs under the other's MMAs.  Measured on whole forwards (tools/ab_win2.py): KITTI b1 2.813 -> 2.790 ms, Sintel b8
   // 15.10 -> 14.56 ms, HD b2 16.39 -> 15.94 ms.  force_m bit 4 (16): one CTA with 224 KB rings (A/B switch)
@@ -373,7 +388,7 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
     if (g_win_force_m & 8) split = 0;
     if (!split && (cand * NB > 512 || cand < 2)) continue;
     const int a_bytes = (4 * cand + 2 * dil) * CW_ROW_BYTES;
-    if (2 * a_bytes + (two_cta ? 2 : 3) * b_stage_bytes > budget) continue;
+    if (2 * a_bytes + ((two_cta || kxn2) ? 2 : 3) * b_stage_bytes > budget) continue;
     if (two_cta && (split ? 2 : 1) * cand * NB > 256) continue;          // both CTAs' accumulators must fit the 512 TMEM columns
     const long long t = (long long)tiles_x * ((H + 4 * cand - 1) / (4 * cand)) * N;
     const double issuer = split ? (490. + 145. * cand) / 2 : (490. + 145. * cand / 2);
@@ -408,9 +423,9 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
   {
     const cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)BN, 9};
     const cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 4, (cuuint64_t)cin_pad * BN * 4};
-    const cuuint32_t box[3] = {32, (cuuint32_t)(mc ? BN / 2 : BN), (kxn && !mc) ? 3u : 1u};
+    const cuuint32_t box[3] = {32, (cuuint32_t)(mc ? BN / 2 : BN), mc ? 1u : kxn2 ? 9u : kxn ? 3u : 1u};
     const cuuint32_t estr[3] = {1, 1, 1};
-    MapKey key{w_packed, cin_pad, BN, 9, mc ? 6000 + BN : kxn ? 3000 + BN : BN, 3};
+    MapKey key{w_packed, cin_pad, BN, 9, mc ? 6000 + BN : kxn2 ? 9000 + BN : kxn ? 3000 + BN : BN, 3};
     int e = encode_cached(key, &mw, 3, const_cast<float*>(w_packed), dims, strides, box, estr);
     if (e) return e;
   }
@@ -427,7 +442,7 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
   while (cols < (tap_split ? 2 : 1) * m * NB) cols <<= 1;
   p.tmem_cols = cols;
   p.tap_split = tap_split;
-  p.kxn = kxn ? 1 : 0;
+  p.kxn = kxn2 ? 2 : kxn ? 1 : 0;
   p.mc = mc ? 1 : 0;
   p.epi_helpers = (g_win_force_m & 32) ? 0 : 1;
   int na = (kblocks >= 3 && 3 * p.a_bytes + 4 * b_stage_bytes <= budget) ? 3 : 2;
@@ -482,7 +497,9 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
 extern "C" int upf_debug_conv_win(int enabled, int min_cin, int force_m) {
   upf::g_win_enabled = enabled & 1;
   upf::g_win_max_cout = (enabled & 2) ? 128 : 64;      // bit 1: take every Cout <= 128 (A/B runs)
+  upf::g_win_kxn2 = (enabled & 8) ? 0 : 1;             // bit 3: one ring item per kernel row instead of per channel block
   upf::g_win_kxn = (enabled & 4) ? 0 : 1;              // bit 2: one MMA per TAP (N = BN) instead of per kernel row (N = 3 BN)
+  if (min_cin >= 1000) { upf::g_win_kxn2_min_kb16 = min_cin - 1000; min_cin = 0; }
   if (min_cin >= 0) upf::g_win_min_cin = min_cin;
   upf::g_win_force_m = force_m;
   return 0;
