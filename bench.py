@@ -522,6 +522,8 @@ def _main():
 
     from upflow_pytorch_b200 import _ext, profiler
     from upflow_pytorch_b200.pipeline import PipelinedInference
+    if os.environ.get("UPF_WIN_DEBUG"):          # triage runs only: "mode,min_cin,force" for upf_debug_conv_win
+        _ext.load().upf_debug_conv_win(*[int(x) for x in os.environ["UPF_WIN_DEBUG"].split(",")])
     net, sd, wdesc = build_net(None, args.precision)                         # public API object (drop-in UPFlow_net)
     im1_h, im2_h = synth_inputs(B, H, W, 1234 + rank)
     im1_h, im2_h = im1_h.pin_memory(), im2_h.pin_memory()

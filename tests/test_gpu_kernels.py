@@ -480,12 +480,12 @@ def test_conv_tf32_large_grid_kernels_agree(upf, case):
     ldo = (Cout + 3) // 4 * 4 + 4
     HALO = (1 << 16) | (128 << 8)
     modes = {"tap": (0, 0, 0), "halo": (0, 0, 1), "win": (3, 0, 0), "win m1": (3, 1, 0), "win m2": (3, 2, 0), "win m4": (3, 4, 0),
-             "win one CTA": (3, 16, 0), "win unit split": (3, 8, 0), "win four epilogue warps": (3, 32, 0), "win item per kernel row": (11, 0, 0), "win item per kernel row m2": (11, 2, 0), "win weight multicast": (3, 64, 0), "win9 weight multicast": (7, 64, 0),
+             "win one CTA": (3, 16, 0), "win unit split": (3, 8, 0), "win four epilogue warps": (3, 32, 0), "win item per channel block": (19, 0, 0), "win item per channel block m2": (19, 2, 0), "win weight multicast": (3, 64, 0), "win9 weight multicast": (7, 64, 0),
              "win9": (7, 0, 0), "win9 m1": (7, 1, 0), "win9 m2": (7, 2, 0), "win9 m4": (7, 4, 0)}
     try:
         modes["halo four epilogue warps"] = (0, 0, 1, 16)
-        modes["win BN=16 kernel-row items"] = (3, 0, 0, 0, 1000 + (1 << 20))   # min_cin >= 1000: channel-block items from (min_cin - 1000) blocks on
-        modes["win BN=16 channel-block items"] = (3, 0, 0, 0, 1003)             # (the default; also puts the switch back)
+        modes["win BN=16 kernel-row items"] = (19, 0, 0, 0, 1000 + (1 << 20))   # min_cin >= 1000: channel-block items from (min_cin - 1000) blocks on
+        modes["win BN=16 channel-block items"] = (19, 0, 0, 0, 1003)            # (also puts the switch back)
         for name, mode in modes.items():
             wen, fm, hen = mode[:3]
             lib.upf_debug_conv_win(wen, mode[4] if len(mode) > 4 else 0, fm)

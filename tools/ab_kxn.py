@@ -12,7 +12,7 @@ lib = _ext.load()
 sd = bench.make_weights()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 # name, conv_win mode, conv_win force bits, largest Cout that runs as 1x1-expand + tap-combine
-VARIANTS = (("default", 1, 0, E.EXPAND_MAX_COUT), ("conv_win: ring item per kernel row", 9, 0, E.EXPAND_MAX_COUT), ("conv_win: BN=16 kernel-row items, two CTAs", 1, 0, E.EXPAND_MAX_COUT, 0, 1000 + (1 << 20)),
+VARIANTS = (("default", 1, 0, E.EXPAND_MAX_COUT), ("conv_win: ring item per channel block", 17, 0, E.EXPAND_MAX_COUT),
             ("per tap, 4 epilogue warps, expand (before)", 5, 32, 8, 16))
 if os.environ.get("AB_FULL"):
     VARIANTS += (("kxn, 4 epilogue warps", 1, 32, E.EXPAND_MAX_COUT), ("per tap, 8 warps", 5, 0, E.EXPAND_MAX_COUT))

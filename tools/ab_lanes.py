@@ -11,7 +11,10 @@ from upflow_pytorch_b200.pipeline import PipelinedInference
 wl = sys.argv[1] if len(sys.argv) > 1 else "kitti_375x1242_b1"
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 H, W, B = bench.WORKLOADS[wl]
-net, sd, wdesc = bench.build_net(None, "tf32")
+if os.environ.get("UPF_WIN_DEBUG"):          # "mode,min_cin,force" for upf_debug_conv_win (triage runs)
+    from upflow_pytorch_b200 import _ext
+    _ext.load().upf_debug_conv_win(*[int(x) for x in os.environ["UPF_WIN_DEBUG"].split(",")])
+net, sd, wdesc = bench.build_net(None, os.environ.get("UPF_PRECISION", "tf32"))
 pairs = [tuple(t.pin_memory() for t in bench.synth_inputs(B, H, W, 1234 + i)) for i in range(4)]
 ref = None
 LANES = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else [1, 2, 3, 1, 2]

@@ -13,7 +13,7 @@ probe = torch.zeros(8, dtype=torch.int64, device="cuda")
 lib.upf_debug_probe(ctypes.c_void_p(probe.data_ptr()))
 
 # name -> (win enabled, force_m, halo enabled)
-MODES = (("tap", (0, 0, 0)), ("halo", (0, 0, 1)), ("win9", (7, 0, 0)), ("win", (3, 0, 0)), ("win4w", (3, 32, 0)), ("winMc", (3, 64, 0)), ("win3", (11, 0, 0)), ("win9 4w", (7, 32, 0)), ("win m1", (3, 1, 0)), ("win m2", (3, 2, 0)), ("win m4", (3, 4, 0)))
+MODES = (("tap", (0, 0, 0)), ("halo", (0, 0, 1)), ("win9", (7, 0, 0)), ("win", (3, 0, 0)), ("win4w", (3, 32, 0)), ("winMc", (3, 64, 0)), ("winKb", (19, 0, 0)), ("win9 4w", (7, 32, 0)), ("win m1", (3, 1, 0)), ("win m2", (3, 2, 0)), ("win m4", (3, 4, 0)))
 if os.environ.get("BW_MODES"):
     MODES = tuple(m for m in MODES if m[0] in os.environ["BW_MODES"].split(",") or m[0] == "tap")
 

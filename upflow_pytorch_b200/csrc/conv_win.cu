@@ -337,7 +337,11 @@ static int g_win_force_m = 0;
 static int g_win_kxn = 1;         // the three horizontal taps along N (header note (4)); upf_debug_conv_win bit 2 switches it off
 static int g_win_kxn2_min_kb16 = 3;         // BN = 16: channel-block items (one CTA per SM) from this many channel blocks on, two CTAs with kernel-row items
                                             // below (A/B: upf_debug_conv_win min_cin >= 1000 sets it; KITTI forward 2.366 -> 2.348 ms)
-static int g_win_kxn2 = 1;        // ... with ONE ring item per channel block (all nine weight slabs in a stage); bit 3 = one item per kernel row
+// ... with ONE ring item per channel block (all nine weight slabs in a stage).  OFF by default: alone it is faster and parity-green
+// (KITTI forward 2.406 -> 2.348 ms), but with four forwards replaying concurrently (pipeline.PipelinedInference lanes, bench.py)
+// the run hung or died with a launch failure in 5 of 7 bench runs with it on and in none of 6 with it off
+// (profiles/r2_triage_lanes.txt); cause not found.  upf_debug_conv_win bit 4 (16) switches it ON (A/B, tests).
+static int g_win_kxn2 = 0;
 
 // returns with *taken = 1 when the launch was made, 0 when the shape is not eligible (caller falls through)
 int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* bias, float* out, int ldo,
@@ -497,7 +501,7 @@ int conv2d_fwd_win(const float* x, int ldx, const float* w_packed, const float* 
 extern "C" int upf_debug_conv_win(int enabled, int min_cin, int force_m) {
   upf::g_win_enabled = enabled & 1;
   upf::g_win_max_cout = (enabled & 2) ? 128 : 64;      // bit 1: take every Cout <= 128 (A/B runs)
-  upf::g_win_kxn2 = (enabled & 8) ? 0 : 1;             // bit 3: one ring item per kernel row instead of per channel block
+  upf::g_win_kxn2 = (enabled & 16) ? 1 : 0;            // bit 4: one ring item per channel block instead of per kernel row (see g_win_kxn2)
   upf::g_win_kxn = (enabled & 4) ? 0 : 1;              // bit 2: one MMA per TAP (N = BN) instead of per kernel row (N = 3 BN)
   if (min_cin >= 1000) { upf::g_win_kxn2_min_kb16 = min_cin - 1000; min_cin = 0; }
   if (min_cin >= 0) upf::g_win_min_cin = min_cin;
