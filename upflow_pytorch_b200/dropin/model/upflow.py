@@ -375,7 +375,9 @@ class UPFlow_net(tools.abstract_model):
             key = tuple(x1_raw.shape) + (eng.lane,)
             g = self._graphs.get(key)
             if g is None:
-                if len(self._graphs) >= 8:
+                lanes = 1 + max([k[-1] for k in self._graphs] + [eng.lane])
+                if len(self._graphs) >= 8 * lanes:         # 8 input shapes per lane
+                    torch.cuda.synchronize(x1_raw.device)  # other lanes' replays may still be running on these buffers
                     self._graphs.clear()
                     eng.release_workspaces()       # the graphs' buffers go with them
                 g = self._graphs[key] = eng.capture(x1_raw.shape[0], x1_raw.shape[2], x1_raw.shape[3])
