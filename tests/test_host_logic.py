@@ -220,3 +220,60 @@ def test_bench_reference_arm_under_torchrun_prints_once():
     assert len(lines) == 1, r.stdout[-800:]
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["value"] > 0
+
+
+def test_pipelined_inference_bookkeeping_with_fake_streams(monkeypatch):
+    """pipeline.PipelinedInference, host logic only (streams, events and pinning faked, tensors on the CPU): results come
+    back in submission order `lanes` submits later, drain() hands out the rest, every pair is one call of the public model
+    on lane k % lanes, and a result slot is not reused before the caller could have read it (lanes + 2 slots)."""
+    import torch
+    from upflow_pytorch_b200 import pipeline
+
+    class FakeEvent:
+        def record(self, stream=None): pass
+        def synchronize(self): pass
+
+    class FakeStream:
+        def __init__(self, device=None): pass
+        def wait_event(self, ev): pass
+
+    class FakeCtx:
+        def __init__(self, s): pass
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "stream", FakeCtx)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None)
+
+    class FakeNet:
+        def __init__(self):
+            self.lane, self.calls = 0, []
+        def set_lane(self, k):
+            self.lane = k
+        def __call__(self, d):
+            self.calls.append(self.lane)
+            return {"flow_f_out": d["im1"][:, :2] + d["im2"][:, :2]}
+
+    pairs = [(torch.full((1, 3, 4, 5), float(i)), torch.full((1, 3, 4, 5), 10.0 * i)) for i in range(9)]
+    for lanes in (1, 2, 4):
+        net = FakeNet()
+        pipe = pipeline.PipelinedInference(net, device="cpu", lanes=lanes)
+        got, held = [], None
+        for i, (a, b) in enumerate(pairs):
+            r = pipe.submit(a, b)
+            assert (r is None) == (i < lanes)
+            if held is not None:                      # the flow handed out one submit ago is still intact (valid until the next-but-one)
+                assert torch.equal(held[0], torch.full((1, 2, 4, 5), 11.0 * held[1]))
+            held = None
+            if r is not None:
+                got.append(r.clone())
+                held = (r, i - lanes)
+        rest = pipe.drain()
+        assert len(rest) == lanes and pipe.drain() == [] and pipe.flush() is None
+        got += [r.clone() for r in rest]
+        assert [float(g[0, 0, 0, 0]) for g in got] == [11.0 * i for i in range(9)]
+        assert net.calls == ([i % lanes for i in range(9)] if lanes > 1 else [0] * 9)
+        assert net.lane == 0                          # drain() puts the model back on lane 0
