@@ -143,7 +143,9 @@ def workload_config(workload, weights_desc):
     H, W, B = WORKLOADS[workload]
     return {"workload": workload, "image": [H, W], "pairs_per_step_per_gpu": B, "pyramid_levels": 6, "decoder_levels": 5,
             "sgu": True, "directions": "forward + backward flow", "weights": weights_desc,
-            "inputs": "synthetic textured pair with known motion (-3,+2) px, seed 1234 + rank"}
+            "inputs": "synthetic textured pair with known motion (-3,+2) px, seed 1234 + rank",
+            "l2": "GPU arm: L2 flushed between timed steps (a 256 MiB write before every step, outside the step's events; "
+                  "`value_lanes`: a 160 MiB write per step inside the timed region; `e2e`: every step's inputs arrive from the host)"}
 
 
 def run_reference(args, rank, world):
